@@ -1,0 +1,318 @@
+"""Generate tests/golden/* by running the UNMODIFIED reference (titus-leistner/mmlf)
+on CPU.  Run in the build container only (needs /root/reference):
+
+    PYTHONDONTWRITEBYTECODE=1 python oracle/gen_golden.py
+
+The reference holds no golden vectors of its own; these files
+are what pins the oracle (tests/test_oracle_golden.py) and, through it and
+directly, the CUDA path.  Inputs come from tests/_fixtures.py (seeded), so the
+fixtures store mostly outputs.
+"""
+import inspect
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, '/root/reference')
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+sys.dont_write_bytecode = True
+
+import _fixtures as fx  # noqa: E402
+from mmlf.data import hci4d  # noqa: E402
+from mmlf.model import loss as rloss  # noqa: E402
+from mmlf.model.ensamble import Ensamble  # noqa: E402
+from mmlf.model.feed_forward import FeedForward  # noqa: E402
+from mmlf.utils import dl  # noqa: E402
+
+OUT = os.path.join(ROOT, 'tests', 'golden')
+os.makedirs(OUT, exist_ok=True)
+torch.set_num_threads(8)
+T = torch.from_numpy
+
+
+def save(name, **arrs):
+    np.savez_compressed(os.path.join(OUT, name), **arrs)
+    print('wrote', name, sum(np.asarray(a).nbytes for a in arrs.values()) // 1024, 'KiB raw')
+
+
+# ---------------------------------------------------------------------------- a1
+def gen_indices():
+    src = inspect.getsource(hci4d.HCI4D.load_scene).splitlines()
+    start = next(i for i, l in enumerate(src) if 'w, h = self.nviews' in l)
+    end = next(i for i, l in enumerate(src) if 'dds = ' in l)
+    body = '\n'.join(l.strip() for l in src[start:end + 1])
+    res = {}
+    for n in (9, 7, 5):
+        class _S:
+            nviews = (n, n)
+        env = {'self': _S}
+        exec(body, env)  # the reference's own index lines (hci4d.py:142-149)
+        res.update({f'us{n}': env['us'], f'vs{n}': env['vs'], f'ids{n}': env['ids'], f'dds{n}': env['dds']})
+    save('indices.npz', **{k: np.array(v) for k, v in res.items()})
+
+
+# ---------------------------------------------------------------------------- a2
+def gen_shift():
+    rng = np.random.RandomState(7)
+    H, W = 12, 12
+    base = [rng.uniform(0, 1, (9, 3, H, W)).astype(np.float32) for _ in range(4)]
+    gt = rng.uniform(-2, 2, (H, W)).astype(np.float32)
+    mpi = rng.uniform(-2, 2, (2, 5, H, W)).astype(np.float64)
+    arange = np.arange(-3.5, 3.5, 0.1)
+    disps = [2.5, -1.3, 0.0, 1.0, -2.0, 0.49999, float(arange[35]), float(arange[3]), float(arange[69]), 7.25, -3.0]
+    out = {'disps': np.array(disps), 'gt': gt, 'mpi': mpi}
+    for k, b in enumerate(base):
+        out[f'in{k}'] = b
+    for j, disp in enumerate(disps):
+        data = [b.copy() for b in base] + [np.zeros(1), gt.copy(), mpi.copy()]
+        res = hci4d.Shift(float(disp))(tuple(data))
+        for k in range(4):
+            out[f'out{j}_{k}'] = res[k]
+        out[f'gt{j}'] = res[5]
+        out[f'mpi{j}'] = res[6]
+        # torch branch with a batch dimension, as Ensamble uses it (ensamble.py:63-70)
+        tdata = tuple(T(np.stack([b, b[::-1].copy()])) for b in base)
+        tres = hci4d.Shift(float(disp))(tdata)
+        for k in range(4):
+            assert np.array_equal(tres[k][0].numpy(), res[k]), 'numpy and torch Shift differ'
+            out[f'tout{j}_{k}'] = tres[k][1].numpy()
+    # non-square image for the h/v stacks only is not reachable (Shift always touches 4 stacks)
+    save('shift.npz', **out)
+
+
+# ---------------------------------------------------------------------------- bins
+def gen_bins():
+    out = {}
+    for n in (54, 70, 108):
+        out[f'torch{n}'] = torch.linspace(-3.5, 3.5, n).numpy()
+        out[f'numpy{n}'] = torch.zeros(n).copy_(T(np.linspace(-3.5, 3.5, n))).numpy()
+    out['torch_odd'] = torch.linspace(-1.25, 2.0, 37).numpy()
+    rng = np.random.RandomState(3)
+    gt = rng.uniform(-3.7, 3.7, (2, 9, 11)).astype(np.float32)
+    mpi = fx.synth_mpi(5, gt)
+    out['gt'] = gt
+    out['mpi'] = mpi
+    for n in (54, 108):
+        out[f'reg_to_class{n}'] = dl.reg_to_class(T(gt), -3.5, 3.5, n).numpy()
+        out[f'mpi_to_weights{n}'] = dl.mpi_to_weights(T(mpi), -3.5, 3.5, n).numpy()
+        oh = torch.zeros(2, n, 9, 11)
+        oh.scatter_(1, torch.randint(0, n, (2, 1, 9, 11), generator=torch.Generator().manual_seed(1)), 1.0)
+        out[f'onehot{n}'] = oh.numpy()
+        out[f'class_to_reg{n}'] = dl.class_to_reg(oh, -3.5, 3.5, n).numpy()
+    for m in (0, 3, 11):
+        out[f'margin{m}'] = rloss.create_mask_margin((2, 30, 26), m).numpy()
+    save('bins.npz', **out)
+
+
+# ---------------------------------------------------------------------------- net
+def _loss_for(variant, multimodal):
+    if variant == 'upr':
+        return rloss.ImprovedMultiUncertaintyL1Loss() if multimodal else rloss.ImprovedUncertaintyL1Loss()
+    if variant == 'dpp':
+        return rloss.MaskedCrossEntropy()
+    return rloss.MultiMaskedL1Loss() if multimodal else rloss.MaskedL1Loss()
+
+
+def _calibrate_bn(model, kw, seed, H, W):
+    """Eval-mode fixtures need running statistics that match the (scaled) weights,
+    otherwise activations explode through 22 convs.  Take them from one train-mode
+    pass with momentum 1 on a calibration input, then detune them a little so that
+    eval-mode and train-mode normalisation differ.  The resulting running stats
+    are stored in the fixture ('state/*running*')."""
+    if kw['model_no_batchnorm']:
+        return
+    cal = FeedForward(**dict(kw, model_batchnorm_momentum=1.0))
+    cal.load_state_dict(model.state_dict())
+    cal.train()
+    h, v, i, d, _ = fx.synth_batch(seed + 100, 2, H, W)
+    cal(T(h), T(v), T(i), T(d))
+    rng = np.random.RandomState(seed + 1)
+    sd = model.state_dict()
+    for k, t in cal.state_dict().items():
+        if k.endswith('running_var'):
+            sd[k].copy_(t * T(rng.uniform(0.8, 1.25, tuple(t.shape)).astype(np.float32)))
+        elif k.endswith('running_mean'):
+            sd[k].copy_(t + 0.1 * T(rng.uniform(-1, 1, tuple(t.shape)).astype(np.float32)))
+
+
+def _run_net(kw, state_seed, B, H, W, in_seed, store_state, multimodal=False, sample_stride=None):
+    torch.manual_seed(0)
+    model = FeedForward(**kw)
+    sd = model.state_dict()
+    with torch.no_grad():
+        fx.perturb_state(sd, state_seed)
+        _calibrate_bn(model, kw, state_seed, H, W)
+    sd = model.state_dict()
+    out = {}
+    for k, v in sd.items():
+        if store_state or 'running' in k:
+            out['state/' + k] = v.numpy().copy()
+    h, v, i, d, gt = fx.synth_batch(in_seed, B, H, W)
+    mask = fx.synth_mask(in_seed + 1, B, H, W)
+    mpi = fx.synth_mpi(in_seed + 2, gt)
+    args = [T(h), T(v), T(i), T(d)]
+    variant = 'upr' if kw['model_uncert'] else ('dpp' if kw['model_discrete'] else 'base')
+    # ---- eval forward
+    model.eval()
+    with torch.no_grad():
+        o = model(*[a.clone() for a in args])
+    for k, t in o.items():
+        if t is not None:
+            out['eval/' + k] = t.numpy()
+    # ---- train forward + loss + backward
+    model.train()
+    o = model(*[a.clone() for a in args])
+    if variant == 'dpp':
+        if multimodal:
+            target = dl.mpi_to_weights(T(mpi), kw['val_disp_min'], kw['val_disp_max'], model.steps)
+        else:
+            target = dl.reg_to_class(T(gt), kw['val_disp_min'], kw['val_disp_max'], model.steps)
+    else:
+        target = T(mpi) if multimodal else T(gt)
+    lossv = _loss_for(variant, multimodal)(o, target, T(mask))
+    lossv.backward()
+    out['train/loss'] = np.array(lossv.item(), np.float64)
+    for k, t in o.items():
+        if t is not None and k in ('mean', 'logvar', 'scores'):
+            out['train/' + k] = t.detach().numpy()
+    for name, p in model.named_parameters():
+        g = p.grad.numpy()
+        if sample_stride and g.size > 4096:
+            g = g.reshape(-1)[::sample_stride].copy()
+        out['grad/' + name] = g
+    for k, vv in model.state_dict().items():
+        if 'running' in k or 'num_batches' in k:
+            out['after/' + k] = vv.numpy().copy()
+    return out
+
+
+def gen_net():
+    for variant in ('base', 'upr', 'dpp'):
+        for cross in (False, True):
+            for mm in (False, True):
+                if cross and mm:
+                    continue
+                kw = fx.model_kwargs(variant, cross, chs=8)
+                res = _run_net(kw, 11, 2, 20, 20, 21, store_state=True, multimodal=mm)
+                save(f'net_tiny_{variant}_{"cross" if cross else "full"}{"_mm" if mm else ""}.npz', **res)
+    # full-width models: parameters are re-created from the seed in the tests (not stored)
+    for variant in ('base', 'upr', 'dpp'):
+        kw = fx.model_kwargs(variant, False, chs=70)
+        res = _run_net(kw, 13, 2, 16, 16, 31, store_state=False, sample_stride=97)
+        save(f'net_full_{variant}.npz', **res)
+    kw = fx.model_kwargs('base', True, chs=70)
+    save('net_full_base_cross.npz', **_run_net(kw, 13, 1, 16, 16, 33, store_state=False, sample_stride=97))
+    # no-batchnorm topology (state_dict index 3 vanishes, feed_forward.py:132-135)
+    kw = fx.model_kwargs('base', False, chs=8, model_no_batchnorm=True)
+    save('net_tiny_base_nobn.npz', **_run_net(kw, 11, 2, 20, 20, 21, store_state=True))
+
+
+# ---------------------------------------------------------------------------- losses
+def gen_losses():
+    rng = np.random.RandomState(17)
+    B, H, W, n = 2, 14, 18, 108
+    gt = rng.uniform(-2, 2, (B, H, W)).astype(np.float32)
+    mean = (gt + rng.normal(0, 0.3, gt.shape)).astype(np.float32)
+    logvar = rng.normal(-0.5, 0.7, gt.shape).astype(np.float32)
+    scores = rng.normal(0, 1.5, (B, n, H, W)).astype(np.float32)
+    mask = fx.synth_mask(4, B, H, W)
+    mpi = fx.synth_mpi(6, gt)
+    mask_padding = (np.abs(gt) < 1.5).astype(np.int32)
+    out = dict(gt=gt, mean=mean, logvar=logvar, scores=scores, mask=mask, mpi=mpi, mask_padding=mask_padding)
+
+    def run(name, fn, target, *extra, keys=('mean',), m=mask):
+        o = {'mean': T(mean).requires_grad_(), 'logvar': T(logvar).requires_grad_(),
+             'scores': T(scores).requires_grad_()}
+        val = fn(o, target, T(m), *extra)
+        out[name + '/value'] = np.array(val.item(), np.float64)
+        if val.requires_grad:
+            val.backward()
+            for k in keys:
+                out[f'{name}/g_{k}'] = o[k].grad.numpy()
+
+    run('l1', rloss.MaskedL1Loss(), T(gt))
+    run('l1_empty', rloss.MaskedL1Loss(), T(gt), m=np.zeros_like(mask))
+    run('multi_l1', rloss.MultiMaskedL1Loss(), T(mpi))
+    run('mse', rloss.MaskedMSELoss(), T(gt))
+    run('badpix', rloss.MaskedBadPix(), T(gt), keys=())
+    run('upr', rloss.ImprovedUncertaintyL1Loss(), T(gt), keys=('mean', 'logvar'))
+    run('upr_pad', rloss.ImprovedUncertaintyL1Loss(), T(gt), T(mask_padding), keys=('mean', 'logvar'))
+    run('multi_upr', rloss.ImprovedMultiUncertaintyL1Loss(), T(mpi), keys=('mean', 'logvar'))
+    t1 = dl.reg_to_class(T(gt), -3.5, 3.5, n)
+    t2 = dl.mpi_to_weights(T(mpi), -3.5, 3.5, n)
+    run('ce', rloss.MaskedCrossEntropy(), t1, keys=('scores',))
+    run('ce_mm', rloss.MaskedCrossEntropy(), t2, keys=('scores',))
+    save('losses.npz', **out)
+
+
+# ---------------------------------------------------------------------------- ESE
+def gen_ese():
+    kw = fx.model_kwargs('upr', False, chs=8)
+    torch.manual_seed(0)
+    model = FeedForward(**kw)
+    sd = model.state_dict()
+    with torch.no_grad():
+        fx.perturb_state(sd, 19)
+        _calibrate_bn(model, kw, 19, 16, 16)
+    model.eval()
+    h, v, i, d, gt = fx.synth_batch(41, 1, 16, 16)
+    out = {'state/' + k: t.numpy().copy() for k, t in model.state_dict().items()}
+    for step, tag in ((0.1, 'full'), (1.0, 'coarse')):
+        ens = Ensamble(model, -3.5, 3.5, step)
+        with torch.no_grad():
+            o = ens(T(h), T(v), T(i), T(d))
+        for k, t in o.items():
+            out[f'{tag}/{k}'] = t.numpy()
+    save('ese_tiny.npz', **out)
+
+
+# ---------------------------------------------------------------------------- Adam
+def gen_adam():
+    rng = np.random.RandomState(23)
+    p0 = rng.normal(0, 1, (5, 7)).astype(np.float32)
+    grads = rng.normal(0, 1, (4, 5, 7)).astype(np.float32)
+    p = torch.nn.Parameter(T(p0.copy()))
+    opt = torch.optim.Adam([p], lr=1e-3)
+    out = {'p0': p0, 'grads': grads}
+    lrs = [0.0, 1e-3, 1e-3, 2.5e-4]
+    for s in range(4):
+        for g in opt.param_groups:
+            g['lr'] = lrs[s]
+        p.grad = T(grads[s].copy())
+        opt.step()
+        out[f'p{s + 1}'] = p.detach().numpy().copy()
+    st = opt.state_dict()['state'][0]
+    out['exp_avg'] = st['exp_avg'].numpy()
+    out['exp_avg_sq'] = st['exp_avg_sq'].numpy()
+    out['lrs'] = np.array(lrs)
+    save('adam.npz', **out)
+
+
+# ---------------------------------------------------------------------------- checkpoint
+def gen_checkpoint():
+    """A checkpoint.pt written by the reference's own ModelSaver (utils/dl.py:21-74)
+    from a random-init reference model + Adam state, as train/cli.py:327-329 does."""
+    kw = fx.model_kwargs('upr', False, chs=8)
+    hyper = dict(kw, train_lr=1e-3, train_bs=2, train_ps=20, train_shift=2.5, val_ensamble=False,
+                 val_disp_step=0.1, model_radius=11, train_loss_multimodal=False)
+    torch.manual_seed(5)
+    model = FeedForward(**kw)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    h, v, i, d, gt = fx.synth_batch(51, 2, 20, 20)
+    o = model(T(h), T(v), T(i), T(d))
+    rloss.ImprovedUncertaintyL1Loss()(o, T(gt), T(fx.synth_mask(52, 2, 20, 20))).backward()
+    opt.step()
+    dl.ModelSaver()(os.path.join(OUT, 'ref_checkpoint_tiny.pt'), torch.nn.DataParallel(model), opt, hyper, None, 1, 0.5)
+    model.eval()
+    with torch.no_grad():
+        o = model(T(h), T(v), T(i), T(d))
+    save('ref_checkpoint_tiny_out.npz', mean=o['mean'].numpy(), logvar=o['logvar'].numpy())
+
+
+if __name__ == '__main__':
+    which = sys.argv[1:] or ['indices', 'shift', 'bins', 'net', 'losses', 'ese', 'adam', 'checkpoint']
+    for w in which:
+        globals()['gen_' + w]()

@@ -1,0 +1,141 @@
+"""Deterministic synthetic inputs shared by oracle/gen_golden.py and the tests.
+
+Follows the recipe of SURVEY.md H1 / section 8(d): structured light fields
+(a smooth texture actually displaced by a disparity map), randomised BatchNorm
+statistics and scaled conv weights, so that network outputs are not the
+degenerate constant that default init + i.i.d. noise produces.
+Everything is numpy / CPU-torch with fixed seeds, so the GPU box regenerates
+bit-identical inputs without /root/reference.
+"""
+import numpy as np
+
+FULL_KW = dict(model_ksize=2, model_in_blocks=3, model_out_blocks=8, model_chs=70, model_views=9,
+               model_cross=False, model_uncert=False, model_unet=False, model_discrete=False,
+               model_no_batchnorm=False, model_batchnorm_momentum=0.1,
+               val_disp_min=-3.5, val_disp_max=3.5)
+
+
+def model_kwargs(variant='base', cross=False, chs=70, **over):
+    kw = dict(FULL_KW)
+    kw.update(model_chs=chs, model_cross=cross,
+              model_uncert=(variant == 'upr'), model_discrete=(variant == 'dpp'))
+    kw.update(over)
+    return kw
+
+
+def synth_lf(seed, H, W, n=9, disp_amp=1.5):
+    """Returns (views (n, n, 3, H, W) float32 in [0,1], disparity (H, W) float32).
+
+    View (v, u) is the base texture sampled at (y + d*(v-c), x + d*(u-c)) where
+    d is a smooth disparity field with one step edge; analytic texture, so the
+    warp is exact (no interpolation).
+    """
+    rng = np.random.RandomState(seed)
+    yy, xx = np.meshgrid(np.arange(H, dtype=np.float64), np.arange(W, dtype=np.float64), indexing='ij')
+    d = disp_amp * np.sin(2 * np.pi * (yy / (1.7 * H) + xx / (2.3 * W)))
+    d = d + 0.8 * (xx > 0.55 * W)
+    nwave = 6
+    fy = rng.uniform(0.05, 0.9, (3, nwave))
+    fx = rng.uniform(0.05, 0.9, (3, nwave))
+    ph = rng.uniform(0, 2 * np.pi, (3, nwave))
+    amp = rng.uniform(0.3, 1.0, (3, nwave))
+    c = n // 2
+    views = np.zeros((n, n, 3, H, W), np.float64)
+    for v in range(n):
+        for u in range(n):
+            ys = yy + d * (v - c)
+            xs = xx + d * (u - c)
+            for ch in range(3):
+                t = sum(amp[ch, k] * np.sin(fy[ch, k] * ys + fx[ch, k] * xs + ph[ch, k]) for k in range(nwave))
+                views[v, u, ch] = 0.5 + 0.5 * t / amp[ch].sum()
+    views += rng.uniform(-0.01, 0.01, views.shape)
+    return np.clip(views, 0, 1).astype(np.float32), d.astype(np.float32)
+
+
+def stacks_from_views(views):
+    """(n, n, 3, H, W) grid -> h, v, i, d stacks (n, 3, H, W) with the index
+    pattern of hci4d.py:142-149 applied to the row-major flattened grid."""
+    n = views.shape[0]
+    flat = views.reshape((n * n,) + views.shape[2:])
+    us = [(n // 2) * n + i for i in range(n)]
+    vs = [n // 2 + n * i for i in range(n)]
+    ids = [n - i - 1 + n * i for i in range(n)][::-1]
+    dds = [i + n * i for i in range(n)]
+    return tuple(np.ascontiguousarray(flat[idx]) for idx in (us, vs, ids, dds))
+
+
+def synth_batch(seed, B, H, W, n=9):
+    """B independent light fields -> four stacks (B, n, 3, H, W) + gt (B, H, W)."""
+    hs, vs, is_, ds, gts = [], [], [], [], []
+    for b in range(B):
+        views, d = synth_lf(seed * 1000 + b, H, W, n)
+        h, v, i, dd = stacks_from_views(views)
+        hs.append(h), vs.append(v), is_.append(i), ds.append(dd), gts.append(d)
+    st = lambda x: np.ascontiguousarray(np.stack(x))  # noqa: E731
+    return st(hs), st(vs), st(is_), st(ds), st(gts)
+
+
+def synth_mpi(seed, gt, K=3):
+    """(B, K, 5, H, W) float32 multi-plane target [rgb, alpha, disp]; alpha is
+    zero on >= 5 % of the pixels (ImprovedMultiUncertaintyL1Loss is NaN otherwise,
+    SURVEY.md a19)."""
+    rng = np.random.RandomState(seed)
+    B, H, W = gt.shape
+    mpi = np.zeros((B, K, 5, H, W), np.float32)
+    mpi[:, :, :3] = rng.uniform(0, 1, (B, K, 3, H, W))
+    alpha = rng.uniform(0, 1, (B, K, H, W)).astype(np.float32)
+    alpha[:, 0] = 1.0 - 0.5 * alpha[:, 1]
+    dead = rng.uniform(0, 1, (B, 1, H, W)) < 0.08
+    alpha = np.where(dead, 0.0, alpha)
+    mpi[:, :, 3] = alpha
+    off = rng.uniform(-1.5, 1.5, (B, K, 1, 1)).astype(np.float32)
+    off[:, 0] = 0
+    mpi[:, :, 4] = gt[:, None] + off[..., 0, 0][:, :, None, None]
+    return mpi
+
+
+def synth_mask(seed, B, H, W, margin=3):
+    rng = np.random.RandomState(seed)
+    m = (rng.uniform(0, 1, (B, H, W)) > 0.1).astype(np.int32)
+    if margin:
+        m[:, :margin] = 0
+        m[:, -margin:] = 0
+        m[:, :, :margin] = 0
+        m[:, :, -margin:] = 0
+    return m
+
+
+def perturb_state(state, seed, wscale=2.0):
+    """In-place on a dict of numpy arrays or torch tensors: scale conv weights,
+    randomise BN affine + running statistics.  Works on both
+    because it only uses ``*=`` / ``[...] =`` with numpy-generated values."""
+    rng = np.random.RandomState(seed)
+    for k in sorted(state.keys()):
+        v = state[k]
+        is_bn = '.3.' in k
+        if k.endswith('num_batches_tracked'):
+            continue
+        shape = tuple(v.shape)
+
+        def put(arr):
+            arr = arr.astype(np.float32)
+            if isinstance(v, np.ndarray):
+                v[...] = arr
+            else:
+                import torch
+                v.copy_(torch.from_numpy(arr))
+
+        if is_bn and k.endswith('running_mean'):
+            put(rng.uniform(-0.2, 0.2, shape))
+        elif is_bn and k.endswith('running_var'):
+            put(rng.uniform(0.5, 1.5, shape))
+        elif is_bn and k.endswith('weight'):
+            put(rng.uniform(0.6, 1.4, shape))
+        elif is_bn and k.endswith('bias'):
+            put(rng.uniform(-0.2, 0.2, shape))
+        elif k.endswith('weight'):
+            cur = v if isinstance(v, np.ndarray) else v.detach().numpy()
+            put(cur * wscale)
+        else:  # conv bias
+            put(rng.uniform(-0.1, 0.1, shape))
+    return state
