@@ -1,0 +1,239 @@
+/* mmlf_b200 -- C ABI of the B200 (sm_100a) hot path of titus-leistner/mmlf.
+ *
+ * The reference is pure Python/PyTorch and has no FFI of its own; each entry point below
+ * names the reference call site(s) it replaces (paths relative to /root/reference).
+ * INTEGRATION.md shows the ctypes binding a maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter is documented as host memory;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it;
+ *   - return value 0 = success, anything else = failure, text via mmlf_last_error();
+ *   - nothing here allocates device memory: the caller owns every buffer.
+ *
+ * "Slot" layout: activations of a batch of B images of H x W pixels are
+ * stored channel-last in bf16 as rows of a 2-D array [n_slots][ld] with
+ *     Hp = H + 1, Wp = W + 1, n_slots = B * Hp * Wp, slot(b, sy, sx) = (b * Hp + sy) * Wp + sx.
+ * An H x W tensor lives at slots (y + 1, x + 1) with slot row 0 / slot column 0 holding zeros;
+ * an (H+1) x (W+1) tensor (output of the padded first conv of a block) fills the whole grid.
+ * With this layout each tap of a 2x2 convolution is a constant row offset, so the implicit
+ * GEMM reads its A operand with plain 2-D TMA boxes.
+ */
+#ifndef MMLF_B200_H
+#define MMLF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMLF_ABI_VERSION 1
+
+const char* mmlf_last_error(void);
+int mmlf_abi_version(void);
+/* 0 if the current device is sm_100 and the kernels can run, else an error. */
+int mmlf_check_device(void);
+
+/* ------------------------------------------------------------------ light-field input (mmlf/data/hci4d.py) */
+
+/* View-index extraction + u8 -> f32 (hci4d.py:142-193, HCI4D.load_scene).
+ * views: [n*n][H][W][3] uint8 in sorted-file (row-major grid) order.
+ * h, v, i, d: [n][3][H][W] float32 stacks (centre row, centre column, rising diagonal reversed,
+ * falling diagonal); center: [3][H][W] = v[n/2] (may be NULL).  Bit-exact: x / 255. */
+int mmlf_lf_extract_u8(const uint8_t* views, int n, int H, int W, float* h, float* v, float* i, float* d,
+                       float* center, void* stream);
+
+/* Shift.__call__ (hci4d.py:907-990) on the four stacks, out of place, one launch.
+ * src_x / dst_x: [batch][n][3][H][W] float32, src != dst.  Two-tap circular lerp per view; diagonal stacks get the
+ * W lerp, an fp32 rounding, then the H lerp (opposite sign for the i stack).  Bit-exact. */
+int mmlf_lf_shift(const float* src_h, const float* src_v, const float* src_i, const float* src_d, float* dst_h,
+                  float* dst_v, float* dst_i, float* dst_d, int batch, int n, int H, int W, double disp,
+                  void* stream);
+
+/* Host helper: the per-view taps of Shift (hci4d.py:934-938): weights rounded to f32, integer shifts.
+ * All four arrays are HOST memory of length n. */
+int mmlf_shift_taps(double disp, int n, float* w0, float* w1, int* s0, int* s1);
+
+/* Fold views into channels and convert to the bf16 slot layout (feed_forward.py:226-232).
+ * views: [B][C][H][W] float32 (C = n*3); out: [n_slots][ld] bf16, channels >= C and halo slots zeroed. */
+int mmlf_pack_views(const float* views, int B, int C, int H, int W, void* out, int ld, void* stream);
+
+/* Fused Shift + pack for the ESE sweep (ensamble.py:63-70 + feed_forward.py:226-232): the shifted fp32 value
+ * is rounded to bf16 and written straight into the slot layout.  stack: 0 = h, 1 = v, 2 = i, 3 = d. */
+int mmlf_shift_pack(const float* src, int stack, int B, int n, int H, int W, double disp, void* out, int ld,
+                    void* stream);
+
+/* ------------------------------------------------------------------ convolution (mmlf/model/feed_forward.py:122-137) */
+
+/* Weight packing: canonical nn.Conv2d weight (cout, cin, 2, 2) f32 -> bf16 K-major GEMM B operand
+ * [n_pad][4 * kc * 64] (kc = ceil(cin_pad / 64)); column (tap * kc * 64 + c), tap = dy * 2 + dx.
+ *   spatial: 0 = as is (v / d streams), 1 = transposed taps (h stream, replaces the permutes of
+ *            feed_forward.py:236-241), 2 = flipped + transposed (i stream, feed_forward.py:248-256)
+ *   dgrad  : 0 = forward operand; 1 = data-gradient operand (taps rotated by 180 degrees, cin/cout swapped:
+ *            rows = cin, columns = cout)
+ *   in_groups/group_real/group_pad: the input channels form `in_groups` groups of `group_real` real channels
+ *            stored with pitch `group_pad` (the 4 x 70 -> 4 x 80 concatenated feature buffer); 1/cin/cin_pad else. */
+int mmlf_pack_conv_weight(const float* w, int cout, int cin, int spatial, int dgrad, int in_groups, int group_real,
+                          int group_pad, void* out, int n_pad, int cin_pad, void* stream);
+
+/* Inverse for gradients: dw_packed [n_pad][4][cin_pad] f32 (same tap/column convention, forward orientation)
+ * -> canonical (cout, cin, 2, 2) f32; accumulate != 0 adds (two streams share one module). */
+int mmlf_unpack_conv_wgrad(const float* dw_packed, int n_pad, int cin_pad, int cout, int cin, int spatial,
+                           int in_groups, int group_real, int group_pad, float* dw, int accumulate, void* stream);
+
+typedef struct mmlf_conv_args {
+  const void* in;        /* bf16 [n_slots][ld_in]; first cin_pad channels are the operand        */
+  int ld_in;             /* row pitch in elements (multiple of 8)                                 */
+  int cin_pad;           /* multiple of 16                                                         */
+  const void* wpack;     /* from mmlf_pack_conv_weight, [n_pad][4 * kc * 64] bf16                  */
+  int n_pad;             /* multiple of 16, <= 320                                                 */
+  int B, H, W;           /* image geometry (slot grid is (H+1) x (W+1))                            */
+  int type;              /* 0: padded conv (nn.Conv2d(.., 2, padding=1), feed_forward.py:123): output on the
+                               whole slot grid, taps at rows {0, 1, Wp, Wp+1};
+                            1: valid conv (padding=0, feed_forward.py:125): output at slots (y+1, x+1), taps at
+                               rows {-Wp-1, -Wp, -1, 0}; halo slots are written as zero                 */
+  const float* bias;     /* [n_pad] or NULL                                                        */
+  const float* scale;    /* [n_pad] or NULL: y = (acc + bias) * scale + shift (eval-mode BN fold)   */
+  const float* shift;    /* [n_pad] or NULL                                                        */
+  int relu;              /* apply max(.,0) (nn.ReLU, feed_forward.py:124,135)                       */
+  const void* gate;      /* bf16 [n_slots][ld_gate] or NULL: multiply by (gate > 0) -- ReLU backward */
+  int ld_gate;
+  void* out;             /* see out_mode                                                           */
+  int ld_out;
+  int out_mode;          /* 0: bf16 [n_slots][ld_out]; 1: f32 [n_slots][ld_out];
+                            2: f32 planar (B, n_real, Ho, Wo), Ho x Wo = (H+1)x(W+1) for type 0, H x W for type 1 */
+  int n_real;            /* channels written in out_mode 2 (<= n_pad); out_mode 0/1 write n_pad channels */
+} mmlf_conv_args;
+
+/* 2x2 convolution as an implicit GEMM on tcgen05 (TMA-fed, TMEM accumulators, fused epilogue).  Forward of
+ * nn.Conv2d at feed_forward.py:123/125 and, with dgrad-packed weights, its data gradient. */
+int mmlf_conv2x2(const mmlf_conv_args* args, void* stream);
+
+/* Same contract on CUDA cores (fp32 FMA over the bf16 operands); slow; used by the tests to cross-check the
+ * tensor-core kernel on the device. */
+int mmlf_conv2x2_simt(const mmlf_conv_args* args, void* stream);
+
+/* Weight gradient of the same convolution (autograd of feed_forward.py:123/125):
+ *   dw[n][tap][c] = sum_slots dout[slot][n] * act[slot + tap_offset(type)][c]
+ * dout: bf16 [n_slots][ld_dout] (n_pad channels), act: bf16 [n_slots][ld_act] (cin_pad channels).
+ * workspace: f32, at least mmlf_conv2x2_wgrad_workspace(...) bytes.  dw: f32 [n_pad][4][cin_pad]. */
+int64_t mmlf_conv2x2_wgrad_workspace(int n_pad, int cin_pad);
+int mmlf_conv2x2_wgrad(const void* dout, int ld_dout, int n_pad, const void* act, int ld_act, int cin_pad, int B,
+                       int H, int W, int type, float* workspace, float* dw, void* stream);
+
+/* Column sums of a bf16 slot array: out[c] (+)= sum_slots x[slot][c]  (bias gradients). */
+int mmlf_colsum_bf16(const void* x, int ld, int C, int64_t n_slots, float* out, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------ BatchNorm (feed_forward.py:134) */
+
+/* Per-channel sum and sum of squares over the valid pixels of z (bf16 slots, H x W tensor at (y+1, x+1)).
+ * sums: double[2][C], must be zeroed by the caller. */
+int mmlf_bn_stats(const void* z, int ld, int C, int B, int H, int W, double* sums, void* stream);
+
+/* Training-mode finalisation: batch mean / biased var -> scale = gamma * invstd, shift = beta - mean * scale;
+ * running_mean / running_var (unbiased) momentum update and num_batches_tracked += 1, as nn.BatchNorm2d does.
+ * save_mean / save_invstd (f32 [C]) are kept for the backward pass. */
+int mmlf_bn_finalize(const double* sums, int C_real, int C, int64_t count, const float* gamma, const float* beta,
+                     float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,
+                     float eps, float* scale, float* shift, float* save_mean, float* save_invstd, void* stream);
+
+/* Eval-mode fold: scale = gamma / sqrt(running_var + eps), shift = (conv_bias - running_mean) * scale + beta;
+ * the conv epilogue then needs no separate bias. */
+int mmlf_bn_fold_eval(int C_real, int C, const float* gamma, const float* beta, const float* running_mean,
+                      const float* running_var, const float* conv_bias, float eps, float* scale, float* shift,
+                      void* stream);
+
+/* y = relu(z * scale + shift) on valid slots, zero on halo slots; bf16 in, bf16 out (ReLU at feed_forward.py:135). */
+int mmlf_bn_apply_relu(const void* z, int ld_z, const float* scale, const float* shift, int C, int B, int H, int W,
+                       void* y, int ld_y, void* stream);
+
+/* Backward of BN(+ReLU) in training mode.  Pass 1: with g = dy * (y > 0) and xhat = (z - mean) * invstd,
+ * sums[0][c] = sum g, sums[1][c] = sum g * xhat (double[2][C], zeroed by the caller). */
+int mmlf_bn_bwd_reduce(const void* dy, int ld_dy, const void* y, int ld_y, const void* z, int ld_z,
+                       const float* save_mean, const float* save_invstd, int C, int B, int H, int W, double* sums,
+                       void* stream);
+/* Pass 2: dz = gamma * invstd * (g - sum_g / count - xhat * sum_gx / count) (bf16, halo zero);
+ * dgamma = sum_gx, dbeta = sum_g (f32 [C]).  train = 0 gives the eval-mode gradient dz = g * gamma * invstd. */
+int mmlf_bn_bwd_apply(const void* dy, int ld_dy, const void* y, int ld_y, const void* z, int ld_z,
+                      const float* gamma, const float* save_mean, const float* save_invstd, const double* sums,
+                      int64_t count, int train, int C_real, int C, int B, int H, int W, void* dz, int ld_dz,
+                      float* dgamma, float* dbeta, void* stream);
+
+/* ReLU backward alone (blocks without BatchNorm): dz = dy * (y > 0), bf16 slots. */
+int mmlf_relu_bwd(const void* dy, int ld_dy, const void* y, int ld_y, int C, int64_t n_slots, void* dz, int ld_dz,
+                  void* stream);
+
+/* ------------------------------------------------------------------ heads (feed_forward.py:270-302) */
+
+/* Last conv of the BASE / UPR head: nn.Conv2d(OC, OC, 2, padding=0) with OC in {1, 2} in fp32 on CUDA cores.
+ * mid: f32 [n_slots][ld_mid] (relu'd output of the first head conv, whole slot grid); w2: (OC, OC, 2, 2),
+ * b2: (OC); out: (B, OC, H, W) f32.  mean = out[:, 0], logvar = out[:, 1] (feed_forward.py:270, 293). */
+int mmlf_head_small(const float* mid, int ld_mid, int OC, const float* w2, const float* b2, int B, int H, int W,
+                    float* out, void* stream);
+/* Its backward: gout (B, OC, H, W) -> gmid bf16 [n_slots][ld_gmid] (first OC channels, rest zero, gated by
+ * mid > 0), dw2 (OC, OC, 2, 2) and db2 (OC) accumulated into zeroed f32 buffers. */
+int mmlf_head_small_bwd(const float* gout, const float* mid, int ld_mid, int OC, const float* w2, int B, int H,
+                        int W, void* gmid, int ld_gmid, float* dw2, float* db2, void* stream);
+
+/* UPR posterior (feed_forward.py:292-302 + laplacian :9-12): post[b][j] = exp(-|x_j - mean| / e^logvar) / (2 e^logvar). */
+int mmlf_upr_posterior(const float* mean, const float* logvar, const float* bins, int steps, int64_t B, int64_t HW,
+                       float* posterior, void* stream);
+
+/* DPP head (feed_forward.py:276-290): one_hot = (max_c s == s); posterior = exp(s) / sum exp(s) (unstabilised);
+ * mean = sum_c bins_t[c] * one_hot[c]; logvar = log sum_c (bins_n[c] - mean)^2 * posterior[c].
+ * bins_t = torch.linspace table, bins_n = np.linspace table (they differ by 1 ulp in places).
+ * one_hot / posterior may be NULL to skip materialising them. */
+int mmlf_dpp_head(const float* scores, const float* bins_t, const float* bins_n, int steps, int64_t B, int64_t HW,
+                  float* one_hot, float* posterior, float* mean, float* logvar, void* stream);
+
+/* DPP targets (utils/dl.py:109-157). */
+int mmlf_reg_to_class(const float* gt, const float* bins_t, int steps, double half_step, int64_t B, int64_t HW,
+                      float* out, void* stream);
+int mmlf_mpi_to_weights(const float* mpi, int K, const float* bins_t, int steps, double half_step, int64_t B,
+                        int64_t HW, float* out, void* stream);
+
+/* ------------------------------------------------------------------ losses (mmlf/model/loss.py), value + gradient fused */
+
+/* Normaliser pre-pass.  sums (double[8], zeroed by caller):
+ *   [0] sum(mask)                                              (loss.py:71 etc.)
+ *   [1] sum(mask_padding), if given                            (loss.py:274)
+ *   [2] sum_px sum_k w_k, if mpi given                         (loss.py:356)
+ *   [3] count(sum_k w_k < 0.01), if mpi given                  (loss.py:359)
+ *   [4] number of pixels B * HW                                (loss.py:275,361: flatten().shape[0])
+ * mpi: (B, K, 5, H, W) f32 or NULL.  In a multi-rank job the caller all-reduces sums before the main pass. */
+int mmlf_loss_prepass(const int32_t* mask, const int32_t* mask_padding, const float* mpi, int K, int64_t B,
+                      int64_t HW, double* sums, void* stream);
+
+/* kind: 0 MaskedL1Loss (loss.py:46-77)            1 MultiMaskedL1Loss (:88-103)
+ *       2 ImprovedUncertaintyL1Loss (:262-294)    3 ImprovedMultiUncertaintyL1Loss (:344-372)
+ *       4 MaskedMSELoss (:114-122, value only)    5 MaskedBadPix (:177-187, value only, threshold in `param`)
+ * target: gt (B, H, W) for kinds 0/2/4/5, mpi (B, K, 5, H, W) for kinds 1/3.  sums: the (all-reduced) pre-pass sums.
+ * loss_sum (double[1], zeroed): receives the un-normalised masked sum; value = loss_sum / max(sums[0], 1 if 0).
+ * g_mean / g_logvar (B, H, W) f32 or NULL: d value / d mean, d value / d logvar. */
+int mmlf_loss_regression(int kind, const float* mean, const float* logvar, const float* target, int K,
+                         const int32_t* mask, const int32_t* mask_padding, const double* sums, double param,
+                         int64_t B, int64_t HW, double* loss_sum, float* g_mean, float* g_logvar, void* stream);
+
+/* MaskedCrossEntropy (loss.py:145-160): l = logsumexp(relu(s)) - sum_c relu(s_c) t_c, masked mean.
+ * target (B, S, H, W) f32 or, if NULL, built on the fly from gt with reg_to_class (utils/dl.py:109-131).
+ * g_scores (B, S, H, W) f32 or NULL. */
+int mmlf_loss_cross_entropy(const float* scores, const float* target, const float* gt, const float* bins_t,
+                            double half_step, int steps, const int32_t* mask, const double* sums, int64_t B,
+                            int64_t HW, double* loss_sum, float* g_scores, void* stream);
+
+/* ------------------------------------------------------------------ ESE (mmlf/model/ensamble.py:78-101) */
+/* means / logvars: (K, B, H, W) f32; disp: np.linspace(min, max, K) as f32 [K].
+ * mean / logvar (B, H, W): member with minimal logvar (first on ties); posterior (B, K, H, W): Laplace mixture. */
+int mmlf_ese_reduce(const float* means, const float* logvars, const float* disp, int K, int64_t B, int64_t HW,
+                    float* mean, float* logvar, float* posterior, void* stream);
+
+/* ------------------------------------------------------------------ optimiser (mmlf/train/cli.py:113-118,258) */
+/* torch.optim.Adam update (betas, eps as given; no weight decay, no amsgrad) over one flat f32 buffer.
+ * step = 1-based step count after the increment. */
+int mmlf_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
+                   double eps, int64_t step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMLF_B200_H */

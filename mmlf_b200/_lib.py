@@ -1,0 +1,104 @@
+"""ctypes binding of the C-ABI library ``libmmlf_b200.so`` (declared in include/mmlf_b200.h).
+
+The library is built in-tree by ``mmlf_b200/csrc/Makefile`` (``__graft_entry__.build()``).  There is no CPU
+fallback: if the library is missing, or a kernel is called without an sm_100 device, this module raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libmmlf_b200.so')
+
+c_p = C.c_void_p
+c_i = C.c_int
+c_i64 = C.c_int64
+c_d = C.c_double
+c_f = C.c_float
+
+
+class ConvArgs(C.Structure):
+    """Mirror of ``mmlf_conv_args`` (include/mmlf_b200.h)."""
+    _fields_ = [('in_', c_p), ('ld_in', c_i), ('cin_pad', c_i), ('wpack', c_p), ('n_pad', c_i),
+                ('B', c_i), ('H', c_i), ('W', c_i), ('type', c_i),
+                ('bias', c_p), ('scale', c_p), ('shift', c_p), ('relu', c_i),
+                ('gate', c_p), ('ld_gate', c_i), ('out', c_p), ('ld_out', c_i), ('out_mode', c_i),
+                ('n_real', c_i)]
+
+
+_PROTOS = {
+    'mmlf_last_error': (C.c_char_p, []),
+    'mmlf_abi_version': (c_i, []),
+    'mmlf_check_device': (c_i, []),
+    'mmlf_lf_extract_u8': (c_i, [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
+    'mmlf_lf_shift': (c_i, [c_p] * 8 + [c_i, c_i, c_i, c_i, c_d, c_p]),
+    'mmlf_shift_taps': (c_i, [c_d, c_i, C.POINTER(c_f), C.POINTER(c_f), C.POINTER(c_i), C.POINTER(c_i)]),
+    'mmlf_pack_views': (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_p]),
+    'mmlf_shift_pack': (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_d, c_p, c_i, c_p]),
+    'mmlf_pack_conv_weight': (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p]),
+    'mmlf_unpack_conv_wgrad': (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_p]),
+    'mmlf_conv2x2': (c_i, [C.POINTER(ConvArgs), c_p]),
+    'mmlf_conv2x2_simt': (c_i, [C.POINTER(ConvArgs), c_p]),
+    'mmlf_conv2x2_wgrad_workspace': (c_i64, [c_i, c_i]),
+    'mmlf_conv2x2_wgrad': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
+    'mmlf_colsum_bf16': (c_i, [c_p, c_i, c_i, c_i64, c_p, c_i, c_p]),
+    'mmlf_bn_stats': (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
+    'mmlf_bn_finalize': (c_i, [c_p, c_i, c_i, c_i64, c_p, c_p, c_p, c_p, c_p, c_f, c_f, c_p, c_p, c_p, c_p, c_p]),
+    'mmlf_bn_fold_eval': (c_i, [c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_f, c_p, c_p, c_p]),
+    'mmlf_bn_apply_relu': (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_p]),
+    'mmlf_bn_bwd_reduce': (c_i, [c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
+    'mmlf_bn_bwd_apply': (c_i, [c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_i64, c_i, c_i, c_i, c_i, c_i,
+                                c_i, c_p, c_i, c_p, c_p, c_p]),
+    'mmlf_relu_bwd': (c_i, [c_p, c_i, c_p, c_i, c_i, c_i64, c_p, c_i, c_p]),
+    'mmlf_head_small': (c_i, [c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_i, c_p, c_p]),
+    'mmlf_head_small_bwd': (c_i, [c_p, c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_p]),
+    'mmlf_upr_posterior': (c_i, [c_p, c_p, c_p, c_i, c_i64, c_i64, c_p, c_p]),
+    'mmlf_dpp_head': (c_i, [c_p, c_p, c_p, c_i, c_i64, c_i64, c_p, c_p, c_p, c_p, c_p]),
+    'mmlf_reg_to_class': (c_i, [c_p, c_p, c_i, c_d, c_i64, c_i64, c_p, c_p]),
+    'mmlf_mpi_to_weights': (c_i, [c_p, c_i, c_p, c_i, c_d, c_i64, c_i64, c_p, c_p]),
+    'mmlf_loss_prepass': (c_i, [c_p, c_p, c_p, c_i, c_i64, c_i64, c_p, c_p]),
+    'mmlf_loss_regression': (c_i, [c_i, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_d, c_i64, c_i64, c_p, c_p, c_p, c_p]),
+    'mmlf_loss_cross_entropy': (c_i, [c_p, c_p, c_p, c_p, c_d, c_i, c_p, c_p, c_i64, c_i64, c_p, c_p, c_p]),
+    'mmlf_ese_reduce': (c_i, [c_p, c_p, c_p, c_i, c_i64, c_i64, c_p, c_p, c_p, c_p]),
+    'mmlf_adam_step': (c_i, [c_p, c_p, c_p, c_p, c_i64, c_d, c_d, c_d, c_d, c_i64, c_p]),
+}
+
+EXPORTS = tuple(_PROTOS)
+_lib = None
+
+
+def lib():
+    """The loaded library (raises if it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f'{LIB_PATH} is missing: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                '(make -C mmlf_b200/csrc).  mmlf_b200 has no CPU / PyTorch fallback.')
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        if l.mmlf_abi_version() != 1:
+            raise RuntimeError('libmmlf_b200.so ABI version mismatch')
+        _lib = l
+    return _lib
+
+
+def call(name, *args):
+    """Call an ``int``-returning entry point and raise with the library's error text on failure."""
+    l = lib()
+    rc = getattr(l, name)(*args)
+    if rc != 0:
+        raise RuntimeError(f'{name} failed ({rc}): {l.mmlf_last_error().decode()}')
+
+
+_device_ok = False
+
+
+def require_device():
+    """Fail loudly when there is no sm_100 device (no fallback path exists)."""
+    global _device_ok
+    if not _device_ok:
+        call('mmlf_check_device')
+        _device_ok = True

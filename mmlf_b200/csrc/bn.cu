@@ -1,0 +1,323 @@
+// BatchNorm (training and eval), ReLU backward and column sums on the bf16 slot layout.
+// Replaces nn.BatchNorm2d / nn.ReLU of /root/reference/mmlf/model/feed_forward.py:134-135 and their autograd.
+// All kernels are HBM-bound: 128-bit loads/stores, one thread = 8 consecutive channels of one slot, so a warp
+// reads contiguous runs of the channel-last rows.
+#include "../../include/mmlf_b200.h"
+#include "common.cuh"
+#include "host_util.h"
+
+namespace mmlf {
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+__device__ __forceinline__ uint4 ld8(const void* base, int64_t slot, int ld, int c) {
+  return __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + slot * ld + c));
+}
+__device__ __forceinline__ void st8(void* base, int64_t slot, int ld, int c, const uint4& v) {
+  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + slot * ld + c) = v;
+}
+__device__ __forceinline__ bool slot_valid(int64_t s, int Hp, int Wp) {
+  const int rem = static_cast<int>(s % (static_cast<int64_t>(Hp) * Wp));
+  const int sy = rem / Wp, sx = rem - sy * Wp;
+  return sy >= 1 && sx >= 1;
+}
+
+// ---------------------------------------------------------------------------- column reductions
+// MODE 0: sum x, sum x^2 (bn_stats)      MODE 1: sum x (colsum)
+// MODE 2: g = dy * (y > 0), xhat = (z - mean) * invstd: sum g, sum g * xhat (bn_bwd_reduce)
+constexpr int kRedThreads = 256;
+
+template <int MODE>
+__global__ void __launch_bounds__(kRedThreads)
+col_reduce_kernel(const void* __restrict__ x, int ld_x, const void* __restrict__ y, int ld_y,
+                  const void* __restrict__ z, int ld_z, const float* __restrict__ mean,
+                  const float* __restrict__ invstd, int C, int64_t n_slots, double* __restrict__ sums,
+                  float* __restrict__ fsum, int accumulate) {
+  extern __shared__ float red[];                    // [lanes][groups * 16]
+  const int groups = C >> 3;
+  const int lanes = kRedThreads / groups;           // slot lanes per block
+  const int g = threadIdx.x % groups, sl = threadIdx.x / groups;
+  float a0[8], a1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.f;
+  float mu[8], is[8];
+  if (MODE == 2) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { mu[j] = mean[g * 8 + j]; is[j] = invstd[g * 8 + j]; }
+  }
+  if (sl < lanes) {
+    for (int64_t s = static_cast<int64_t>(blockIdx.x) * lanes + sl; s < n_slots; s += static_cast<int64_t>(gridDim.x) * lanes) {
+      float v[8];
+      unpack8(ld8(x, s, ld_x, g * 8), v);
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { a0[j] += v[j]; a1[j] = fmaf(v[j], v[j], a1[j]); }
+      } else if (MODE == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a0[j] += v[j];
+      } else {
+        float yy[8], zz[8];
+        unpack8(ld8(y, s, ld_y, g * 8), yy);
+        unpack8(ld8(z, s, ld_z, g * 8), zz);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float gg = yy[j] > 0.f ? v[j] : 0.f;
+          a0[j] += gg;
+          a1[j] = fmaf(gg, (zz[j] - mu[j]) * is[j], a1[j]);
+        }
+      }
+    }
+  }
+  // block reduction over the slot lanes
+  const int stride = groups * 16;
+  if (sl < lanes) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      red[sl * stride + g * 16 + j] = a0[j];
+      red[sl * stride + g * 16 + 8 + j] = a1[j];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < stride; i += kRedThreads) {
+    double acc = 0.0;
+    for (int l = 0; l < lanes; ++l) acc += static_cast<double>(red[l * stride + i]);
+    const int gg = i / 16, j = i % 16;
+    const int c = gg * 8 + (j & 7);
+    if (MODE == 1) {
+      if (j < 8) atomicAdd(&fsum[c], static_cast<float>(acc));
+    } else {
+      atomicAdd(&sums[(j >> 3) * C + c], acc);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------- finalize (training)
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, int C_real, int C, int64_t count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ rmean, float* __restrict__ rvar, int64_t* __restrict__ nbt,
+                                   float momentum, float eps, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && nbt) *nbt += 1;
+  if (c >= C) return;
+  if (c >= C_real) {                                // padding channels stay exactly zero
+    scale[c] = 0.f; shift[c] = 0.f; save_mean[c] = 0.f; save_invstd[c] = 0.f;
+    return;
+  }
+  const double n = static_cast<double>(count);
+  const double mean = sums[c] / n;
+  double var = sums[C + c] / n - mean * mean;       // biased, used to normalise
+  if (var < 0.0) var = 0.0;
+  const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float sc = gamma[c] * invstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - static_cast<float>(mean) * sc;
+  save_mean[c] = static_cast<float>(mean);
+  save_invstd[c] = invstd;
+  if (rmean) {
+    const double unbiased = count > 1 ? var * n / (n - 1.0) : var;
+    rmean[c] = static_cast<float>((1.0 - momentum) * rmean[c] + momentum * mean);
+    rvar[c] = static_cast<float>((1.0 - momentum) * rvar[c] + momentum * unbiased);
+  }
+}
+
+__global__ void bn_fold_eval_kernel(int C_real, int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ rmean, const float* __restrict__ rvar,
+                                    const float* __restrict__ conv_bias, float eps, float* __restrict__ scale,
+                                    float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (c >= C_real) { scale[c] = 0.f; shift[c] = 0.f; return; }
+  const float invstd = static_cast<float>(1.0 / sqrt(static_cast<double>(rvar[c]) + static_cast<double>(eps)));
+  const float sc = gamma[c] * invstd;
+  scale[c] = sc;
+  shift[c] = ((conv_bias ? conv_bias[c] : 0.f) - rmean[c]) * sc + beta[c];
+}
+
+// ---------------------------------------------------------------------------- elementwise passes
+// MODE 0: y = relu(z * scale + shift), halo -> 0                     (bn_apply_relu)
+// MODE 1: dz = dy * (y > 0)                                          (relu_bwd)
+// MODE 2: dz = gamma*invstd*(g - sg/n - xhat*sgx/n), halo -> 0       (bn_bwd_apply, train)
+// MODE 3: dz = g * gamma * invstd                                    (bn_bwd_apply, eval-mode BN)
+template <int MODE>
+__global__ void __launch_bounds__(256)
+slot_map_kernel(const void* __restrict__ a, int ld_a, const void* __restrict__ y, int ld_y,
+                const void* __restrict__ z, int ld_z, const float* __restrict__ p0, const float* __restrict__ p1,
+                const float* __restrict__ p2, const double* __restrict__ sums, double inv_count, int C, int Hp, int Wp,
+                int64_t n_slots, void* __restrict__ out, int ld_out) {
+  const int groups = C >> 3;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t s = idx / groups;
+  if (s >= n_slots) return;
+  const int c = static_cast<int>(idx - s * groups) * 8;
+  float r[8];
+  if ((MODE == 0 || MODE == 2) && !slot_valid(s, Hp, Wp)) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = 0.f;
+    st8(out, s, ld_out, c, pack8(r));
+    return;
+  }
+  float av[8];
+  unpack8(ld8(a, s, ld_a, c), av);
+  if (MODE == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = fmaxf(fmaf(av[j], p0[c + j], p1[c + j]), 0.f);
+  } else {
+    float yv[8];
+    unpack8(ld8(y, s, ld_y, c), yv);
+    if (MODE == 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = yv[j] > 0.f ? av[j] : 0.f;
+    } else {
+      float zv[8];
+      unpack8(ld8(z, s, ld_z, c), zv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float g = yv[j] > 0.f ? av[j] : 0.f;
+        const float k = p0[c + j] * p2[c + j];               // gamma * invstd
+        if (MODE == 3) {
+          r[j] = g * k;
+        } else {
+          const float xhat = (zv[j] - p1[c + j]) * p2[c + j];
+          const float mg = static_cast<float>(sums[c + j] * inv_count);
+          const float mgx = static_cast<float>(sums[C + c + j] * inv_count);
+          r[j] = k * (g - mg - xhat * mgx);
+        }
+      }
+    }
+  }
+  st8(out, s, ld_out, c, pack8(r));
+}
+
+__global__ void bn_param_grads_kernel(const double* __restrict__ sums, int C_real, int C, float* __restrict__ dgamma,
+                                      float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C_real) return;
+  dbeta[c] = static_cast<float>(sums[c]);
+  dgamma[c] = static_cast<float>(sums[C + c]);
+}
+
+static int red_grid(int64_t n_slots, int lanes) {
+  int64_t want = ceil_div64(n_slots, static_cast<int64_t>(lanes) * 8);
+  int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return static_cast<int>(want);
+}
+
+}  // namespace mmlf
+
+using namespace mmlf;
+
+#define CHECK_C(C) MMLF_REQUIRE((C) % 8 == 0 && (C) >= 8 && (C) <= 2048, "channel count %d must be a multiple of 8 in [8, 2048]", (C))
+
+extern "C" int mmlf_bn_stats(const void* z, int ld, int C, int B, int H, int W, double* sums, void* stream) {
+  MMLF_REQUIRE(z && sums, "bn_stats: null buffer");
+  CHECK_C(C);
+  MMLF_REQUIRE(C / 8 <= kRedThreads, "bn_stats: too many channels");
+  const int64_t n_slots = static_cast<int64_t>(B) * (H + 1) * (W + 1);
+  const int groups = C / 8, lanes = kRedThreads / groups;
+  const size_t smem = static_cast<size_t>(lanes) * groups * 16 * sizeof(float);
+  col_reduce_kernel<0><<<red_grid(n_slots, lanes), kRedThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      z, ld, nullptr, 0, nullptr, 0, nullptr, nullptr, C, n_slots, sums, nullptr, 0);
+  return check_launch("bn_stats");
+}
+
+extern "C" int mmlf_colsum_bf16(const void* x, int ld, int C, int64_t n_slots, float* out, int accumulate,
+                                void* stream) {
+  MMLF_REQUIRE(x && out, "colsum: null buffer");
+  CHECK_C(C);
+  if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float) * C, static_cast<cudaStream_t>(stream));
+  const int groups = C / 8, lanes = kRedThreads / groups;
+  const size_t smem = static_cast<size_t>(lanes) * groups * 16 * sizeof(float);
+  col_reduce_kernel<1><<<red_grid(n_slots, lanes), kRedThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      x, ld, nullptr, 0, nullptr, 0, nullptr, nullptr, C, n_slots, nullptr, out, 1);
+  return check_launch("colsum");
+}
+
+extern "C" int mmlf_bn_finalize(const double* sums, int C_real, int C, int64_t count, const float* gamma,
+                                const float* beta, float* running_mean, float* running_var,
+                                int64_t* num_batches_tracked, float momentum, float eps, float* scale, float* shift,
+                                float* save_mean, float* save_invstd, void* stream) {
+  MMLF_REQUIRE(sums && gamma && beta && scale && shift && save_mean && save_invstd, "bn_finalize: null buffer");
+  MMLF_REQUIRE(count > 0 && C_real <= C, "bn_finalize: bad sizes");
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      sums, C_real, C, count, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, scale, shift,
+      save_mean, save_invstd);
+  return check_launch("bn_finalize");
+}
+
+extern "C" int mmlf_bn_fold_eval(int C_real, int C, const float* gamma, const float* beta, const float* running_mean,
+                                 const float* running_var, const float* conv_bias, float eps, float* scale,
+                                 float* shift, void* stream) {
+  MMLF_REQUIRE(gamma && beta && running_mean && running_var && scale && shift, "bn_fold_eval: null buffer");
+  bn_fold_eval_kernel<<<ceil_div(C, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      C_real, C, gamma, beta, running_mean, running_var, conv_bias, eps, scale, shift);
+  return check_launch("bn_fold_eval");
+}
+
+extern "C" int mmlf_bn_apply_relu(const void* z, int ld_z, const float* scale, const float* shift, int C, int B,
+                                  int H, int W, void* y, int ld_y, void* stream) {
+  MMLF_REQUIRE(z && scale && shift && y, "bn_apply_relu: null buffer");
+  CHECK_C(C);
+  const int64_t n_slots = static_cast<int64_t>(B) * (H + 1) * (W + 1);
+  const int64_t total = n_slots * (C / 8);
+  slot_map_kernel<0><<<static_cast<unsigned>(ceil_div64(total, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      z, ld_z, nullptr, 0, nullptr, 0, scale, shift, nullptr, nullptr, 0.0, C, H + 1, W + 1, n_slots, y, ld_y);
+  return check_launch("bn_apply_relu");
+}
+
+extern "C" int mmlf_relu_bwd(const void* dy, int ld_dy, const void* y, int ld_y, int C, int64_t n_slots, void* dz,
+                             int ld_dz, void* stream) {
+  MMLF_REQUIRE(dy && y && dz, "relu_bwd: null buffer");
+  CHECK_C(C);
+  const int64_t total = n_slots * (C / 8);
+  slot_map_kernel<1><<<static_cast<unsigned>(ceil_div64(total, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      dy, ld_dy, y, ld_y, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0.0, C, 1, 1, n_slots, dz, ld_dz);
+  return check_launch("relu_bwd");
+}
+
+extern "C" int mmlf_bn_bwd_reduce(const void* dy, int ld_dy, const void* y, int ld_y, const void* z, int ld_z,
+                                  const float* save_mean, const float* save_invstd, int C, int B, int H, int W,
+                                  double* sums, void* stream) {
+  MMLF_REQUIRE(dy && y && z && save_mean && save_invstd && sums, "bn_bwd_reduce: null buffer");
+  CHECK_C(C);
+  const int64_t n_slots = static_cast<int64_t>(B) * (H + 1) * (W + 1);
+  const int groups = C / 8, lanes = kRedThreads / groups;
+  const size_t smem = static_cast<size_t>(lanes) * groups * 16 * sizeof(float);
+  col_reduce_kernel<2><<<red_grid(n_slots, lanes), kRedThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      dy, ld_dy, y, ld_y, z, ld_z, save_mean, save_invstd, C, n_slots, sums, nullptr, 0);
+  return check_launch("bn_bwd_reduce");
+}
+
+extern "C" int mmlf_bn_bwd_apply(const void* dy, int ld_dy, const void* y, int ld_y, const void* z, int ld_z,
+                                 const float* gamma, const float* save_mean, const float* save_invstd,
+                                 const double* sums, int64_t count, int train, int C_real, int C, int B, int H, int W,
+                                 void* dz, int ld_dz, float* dgamma, float* dbeta, void* stream) {
+  MMLF_REQUIRE(dy && y && z && gamma && save_mean && save_invstd && sums && dz, "bn_bwd_apply: null buffer");
+  CHECK_C(C);
+  const int64_t n_slots = static_cast<int64_t>(B) * (H + 1) * (W + 1);
+  const int64_t total = n_slots * (C / 8);
+  const unsigned blocks = static_cast<unsigned>(ceil_div64(total, 256));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (train)
+    slot_map_kernel<2><<<blocks, 256, 0, st>>>(dy, ld_dy, y, ld_y, z, ld_z, gamma, save_mean, save_invstd, sums,
+                                               1.0 / static_cast<double>(count), C, H + 1, W + 1, n_slots, dz, ld_dz);
+  else
+    slot_map_kernel<3><<<blocks, 256, 0, st>>>(dy, ld_dy, y, ld_y, z, ld_z, gamma, save_mean, save_invstd, sums, 0.0,
+                                               C, H + 1, W + 1, n_slots, dz, ld_dz);
+  if (int rc = check_launch("bn_bwd_apply")) return rc;
+  if (dgamma && dbeta) {
+    bn_param_grads_kernel<<<ceil_div(C_real, 128), 128, 0, st>>>(sums, C_real, C, dgamma, dbeta);
+    return check_launch("bn_param_grads");
+  }
+  return 0;
+}

@@ -1,0 +1,371 @@
+// 2x2 convolution as an implicit GEMM on the 5th-gen tensor cores (tcgen05 + TMEM), fed by TMA.
+//
+// Replaces nn.Conv2d(cin, cout, 2, padding=1|0) of /root/reference/mmlf/model/feed_forward.py:123,125
+// (forward) and, with dgrad-packed weights, its data gradient.  See DESIGN.md section 4.
+//
+//   GEMM view : D[slot][n] = sum_{tap, c} A[slot + off(tap)][c] * Wp[n][tap][c]
+//   A operand : activations in the bf16 slot layout; one (tap, 64-channel chunk) = one 2-D TMA box of
+//               128 rows x 128 B landing as a canonical K-major SWIZZLE_128B tile.  Rows outside the array and
+//               channels >= cin_pad are zero-filled by TMA (that is the conv padding of the first/last image).
+//   B operand : packed weights [n_pad][4 * kc * 64], K-major, SWIZZLE_128B, re-streamed from L2 per tile.
+//   D         : fp32 in TMEM, 128 lanes x n_pad columns, split into <= 2 MMAs of N <= 256 per k-step.
+//   roles     : warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 = epilogue (one TMEM lane
+//               quadrant each).  Persistent CTAs, static round-robin over 128-slot tiles.
+#include "../../include/mmlf_b200.h"
+#include "common.cuh"
+#include "host_util.h"
+
+namespace mmlf {
+
+constexpr int kTileM = 128;
+constexpr int kABytes = kTileM * 128;  // one A stage: 128 rows x 64 bf16
+constexpr int kConvThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr uint32_t kTmemCols = 512;
+
+struct ConvParams {
+  int64_t n_slots;
+  int Hp, Wp, H, W;
+  int n_pad, n_parts, n_part;
+  int n_kc, last_ksteps;
+  int tap_off[4];
+  int num_tiles, stages;
+  int b_boxes, b_box_rows;
+  int type, relu, out_mode, n_real, ld_out, ld_gate;
+  const float* bias;
+  const float* scale;
+  const float* shift;
+  const __nv_bfloat16* gate;
+  void* out;
+};
+
+// Epilogue math + store for 16 consecutive output channels [c0, c0+16) of one slot.  Shared by the tensor-core
+// kernel and the CUDA-core cross-check kernel so that both have identical semantics.
+__device__ __forceinline__ void epilogue_store16(const ConvParams& p, const float* s_bias, const float* s_scale,
+                                                 const float* s_shift, int64_t s, bool in_range, bool valid, int b,
+                                                 int sy, int sx, int c0, float (&v)[16]) {
+  if (!in_range) return;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float x = v[j];
+    if (s_bias) x += s_bias[c0 + j];
+    if (s_scale) x = x * s_scale[c0 + j] + s_shift[c0 + j];
+    if (p.relu) x = fmaxf(x, 0.f);
+    v[j] = valid ? x : 0.f;
+  }
+  if (p.gate) {
+    const uint4* g = reinterpret_cast<const uint4*>(p.gate + s * p.ld_gate + c0);
+    uint4 g0 = g[0], g1 = g[1];
+    const uint32_t gw[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (!(bf16_lo(gw[j]) > 0.f)) v[2 * j] = 0.f;
+      if (!(bf16_hi(gw[j]) > 0.f)) v[2 * j + 1] = 0.f;
+    }
+  }
+  if (p.out_mode == 0) {
+    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + s * p.ld_out + c0);
+    uint4 a, c;
+    a.x = pack_bf16x2(v[0], v[1]);
+    a.y = pack_bf16x2(v[2], v[3]);
+    a.z = pack_bf16x2(v[4], v[5]);
+    a.w = pack_bf16x2(v[6], v[7]);
+    c.x = pack_bf16x2(v[8], v[9]);
+    c.y = pack_bf16x2(v[10], v[11]);
+    c.z = pack_bf16x2(v[12], v[13]);
+    c.w = pack_bf16x2(v[14], v[15]);
+    o[0] = a;
+    o[1] = c;
+  } else if (p.out_mode == 1) {
+    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + s * p.ld_out + c0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  } else {
+    if (!valid) return;
+    const int Ho = p.type ? p.H : p.Hp, Wo = p.type ? p.W : p.Wp;
+    const int y = p.type ? sy - 1 : sy, x = p.type ? sx - 1 : sx;
+    float* o = reinterpret_cast<float*>(p.out) + ((static_cast<int64_t>(b) * p.n_real + c0) * Ho + y) * Wo + x;
+    const int64_t plane = static_cast<int64_t>(Ho) * Wo;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (c0 + j < p.n_real) o[j * plane] = v[j];
+  }
+}
+
+__device__ __forceinline__ void slot_coords(const ConvParams& p, int64_t s, int& b, int& sy, int& sx) {
+  const int per_img = p.Hp * p.Wp;
+  b = static_cast<int>(s / per_img);
+  const int rem = static_cast<int>(s - static_cast<int64_t>(b) * per_img);
+  sy = rem / p.Wp;
+  sx = rem - sy * p.Wp;
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv2x2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;   // SWIZZLE_128B atoms need 1024 B alignment
+  uint8_t* smem = smem_raw + (tiles_addr - raw_addr);
+  const uint32_t stage_bytes = kABytes + static_cast<uint32_t>(p.n_pad) * 128u;
+
+  uint8_t* aux = smem + static_cast<size_t>(p.stages) * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full_bar = empty_bar + kMaxStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 1;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 1);
+  float* s_bias = reinterpret_cast<float*>(tmem_ptr_smem + 4);
+  float* s_scale = s_bias + p.n_pad;
+  float* s_shift = s_scale + p.n_pad;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < p.stages; ++i) {
+        mbar_init(smem_u32(&full_bar[i]), 1);
+        mbar_init(smem_u32(&empty_bar[i]), 1);
+      }
+      mbar_init(smem_u32(tmem_full_bar), 1);
+      mbar_init(smem_u32(tmem_empty_bar), 128);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_ptr_smem), kTmemCols);
+  }
+  for (int i = threadIdx.x; i < p.n_pad; i += kConvThreads) {
+    s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    s_scale[i] = p.scale ? p.scale[i] : 1.f;
+    s_shift[i] = p.shift ? p.shift[i] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int row0 = tile * kTileM;
+        for (int tap = 0; tap < 4; ++tap) {
+          for (int kc = 0; kc < p.n_kc; ++kc) {
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+            const uint32_t fb = smem_u32(&full_bar[stage]);
+            mbar_arrive_expect_tx(fb, stage_bytes);
+            const uint32_t a_dst = tiles_addr + stage * stage_bytes;
+            tma_load_2d(a_dst, &tmap_a, fb, kc * 64, row0 + p.tap_off[tap]);
+            const uint32_t b_dst = a_dst + kABytes;
+            const int kcol = (tap * p.n_kc + kc) * 64;
+            for (int bb = 0; bb < p.b_boxes; ++bb)
+              tma_load_2d_hint(b_dst + bb * p.b_box_rows * 128, &tmap_b, fb, kcol, bb * p.b_box_rows, kEvictLast);
+            if (++stage == static_cast<uint32_t>(p.stages)) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (single thread)
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(kTileM, p.n_part, 0, 0);
+      uint32_t stage = 0, phase = 0, tphase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(tmem_empty_bar), tphase ^ 1u);   // epilogue has drained the accumulator
+        tc_fence_after();
+        uint32_t accumulate = 0;
+        for (int tap = 0; tap < 4; ++tap) {
+          for (int kc = 0; kc < p.n_kc; ++kc) {
+            mbar_wait(smem_u32(&full_bar[stage]), phase);
+            tc_fence_after();
+            const uint32_t a_addr = tiles_addr + stage * stage_bytes;
+            const uint32_t b_addr = a_addr + kABytes;
+            const int ksteps = (kc == p.n_kc - 1) ? p.last_ksteps : 4;
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t adesc = make_sw128_desc(a_addr + k * 32, 0, 1024);
+              for (int part = 0; part < p.n_parts; ++part) {
+                const uint64_t bdesc = make_sw128_desc(b_addr + part * p.n_part * 128 + k * 32, 0, 1024);
+                umma_f16(tmem_base + part * p.n_part, adesc, bdesc, idesc, accumulate);
+              }
+              accumulate = 1;
+            }
+            umma_commit(smem_u32(&empty_bar[stage]));       // frees the smem stage once these MMAs retire
+            if (++stage == static_cast<uint32_t>(p.stages)) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+        umma_commit(smem_u32(tmem_full_bar));                // accumulator complete -> epilogue
+        tphase ^= 1u;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: TMEM -> regs -> global
+    const int q = warp & 3;                                  // TMEM lane quadrant this warp may access
+    uint32_t tphase = 0;
+    const float* eb = p.bias ? s_bias : nullptr;
+    const float* es = p.scale ? s_scale : nullptr;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(smem_u32(tmem_full_bar), tphase);
+      tc_fence_after();
+      const int64_t s = static_cast<int64_t>(tile) * kTileM + q * 32 + lane;
+      const bool in_range = s < p.n_slots;
+      int b = 0, sy = 0, sx = 0;
+      if (in_range) slot_coords(p, s, b, sy, sx);
+      const bool valid = in_range && (p.type == 0 || (sy >= 1 && sx >= 1));
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+      for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c0, r);
+        tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        epilogue_store16(p, eb, es, s_shift, s, in_range, valid, b, sy, sx, c0, v);
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(tmem_empty_bar));
+      tphase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// CUDA-core cross-check kernel: one thread per (slot, 16 output channels); fp32 FMA over the same bf16 operands.
+__global__ void conv2x2_simt_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, int cin_pad,
+                                    const __nv_bfloat16* __restrict__ wpack, int k_total, const ConvParams p) {
+  const int groups = p.n_pad / 16;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t s = idx / groups;
+  const int c0 = static_cast<int>(idx - s * groups) * 16;
+  if (s >= p.n_slots) return;
+  int b, sy, sx;
+  slot_coords(p, s, b, sy, sx);
+  const bool valid = (p.type == 0 || (sy >= 1 && sx >= 1));
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = 0.f;
+  for (int tap = 0; tap < 4; ++tap) {
+    const int64_t r = s + p.tap_off[tap];
+    if (r < 0 || r >= p.n_slots) continue;
+    const __nv_bfloat16* a = in + r * ld_in;
+    const __nv_bfloat16* w = wpack + static_cast<int64_t>(tap) * p.n_kc * 64;
+    for (int c = 0; c < cin_pad; ++c) {
+      const float av = __bfloat162float(a[c]);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaf(av, __bfloat162float(w[static_cast<int64_t>(c0 + j) * k_total + c]), v[j]);
+    }
+  }
+  epilogue_store16(p, p.bias, p.scale, p.shift, s, true, valid, b, sy, sx, c0, v);
+}
+
+static int fill_params(const mmlf_conv_args* a, ConvParams& p) {
+  MMLF_REQUIRE(a != nullptr, "conv2x2: null args");
+  MMLF_REQUIRE(a->in && a->wpack && a->out, "conv2x2: null buffer");
+  MMLF_REQUIRE(a->cin_pad > 0 && a->cin_pad % 16 == 0, "conv2x2: cin_pad %d must be a positive multiple of 16", a->cin_pad);
+  MMLF_REQUIRE(a->n_pad >= 16 && a->n_pad % 16 == 0 && a->n_pad <= 320, "conv2x2: n_pad %d must be a multiple of 16 in [16, 320]", a->n_pad);
+  MMLF_REQUIRE(a->ld_in % 8 == 0 && a->ld_in >= a->cin_pad, "conv2x2: ld_in %d must be a multiple of 8 and >= cin_pad", a->ld_in);
+  MMLF_REQUIRE(a->B > 0 && a->H > 0 && a->W > 0, "conv2x2: bad geometry");
+  MMLF_REQUIRE(a->type == 0 || a->type == 1, "conv2x2: type must be 0 or 1");
+  MMLF_REQUIRE(a->out_mode >= 0 && a->out_mode <= 2, "conv2x2: bad out_mode");
+  MMLF_REQUIRE(a->out_mode == 2 || (a->ld_out >= a->n_pad && a->ld_out % (a->out_mode == 0 ? 8 : 4) == 0),
+               "conv2x2: ld_out %d too small / misaligned for n_pad %d", a->ld_out, a->n_pad);
+  MMLF_REQUIRE(a->out_mode != 2 || (a->n_real >= 1 && a->n_real <= a->n_pad), "conv2x2: bad n_real");
+  MMLF_REQUIRE((a->scale == nullptr) == (a->shift == nullptr), "conv2x2: scale and shift come together");
+  MMLF_REQUIRE(!a->gate || a->ld_gate % 8 == 0, "conv2x2: ld_gate must be a multiple of 8");
+  p.Hp = a->H + 1;
+  p.Wp = a->W + 1;
+  p.H = a->H;
+  p.W = a->W;
+  p.n_slots = static_cast<int64_t>(a->B) * p.Hp * p.Wp;
+  MMLF_REQUIRE(p.n_slots + kTileM < (1ll << 31), "conv2x2: too many slots for 32-bit TMA coordinates");
+  p.n_pad = a->n_pad;
+  p.n_parts = a->n_pad > 256 ? 2 : 1;
+  p.n_part = a->n_pad / p.n_parts;
+  MMLF_REQUIRE(p.n_part % 16 == 0, "conv2x2: n_pad %d does not split into MMA N multiples of 16", a->n_pad);
+  p.n_kc = ceil_div(a->cin_pad, 64);
+  p.last_ksteps = (a->cin_pad - (p.n_kc - 1) * 64) / 16;
+  if (a->type == 0) {
+    p.tap_off[0] = 0; p.tap_off[1] = 1; p.tap_off[2] = p.Wp; p.tap_off[3] = p.Wp + 1;
+  } else {
+    p.tap_off[0] = -p.Wp - 1; p.tap_off[1] = -p.Wp; p.tap_off[2] = -1; p.tap_off[3] = 0;
+  }
+  p.num_tiles = static_cast<int>(ceil_div64(p.n_slots, kTileM));
+  p.b_boxes = a->n_pad > 256 ? 2 : 1;
+  p.b_box_rows = a->n_pad / p.b_boxes;
+  p.type = a->type;
+  p.relu = a->relu;
+  p.out_mode = a->out_mode;
+  p.n_real = a->n_real;
+  p.ld_out = a->ld_out;
+  p.ld_gate = a->ld_gate;
+  p.bias = a->bias;
+  p.scale = a->scale;
+  p.shift = a->shift;
+  p.gate = reinterpret_cast<const __nv_bfloat16*>(a->gate);
+  p.out = a->out;
+  p.stages = 0;
+  return 0;
+}
+
+}  // namespace mmlf
+
+using namespace mmlf;
+
+extern "C" int mmlf_conv2x2(const mmlf_conv_args* a, void* stream) {
+  ConvParams p;
+  if (int rc = fill_params(a, p)) return rc;
+  const uint32_t stage_bytes = kABytes + p.n_pad * 128;
+  const uint32_t aux_bytes = (2 * kMaxStages + 2) * 8 + 16 + 3 * p.n_pad * 4 + 64;
+  const uint32_t max_smem = 232448;   // 227 KB opt-in limit per CTA on sm_100
+  int stages = static_cast<int>((max_smem - 1024 - aux_bytes) / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  MMLF_REQUIRE(stages >= 2, "conv2x2: not enough shared memory for a 2-stage pipeline (n_pad %d)", p.n_pad);
+  p.stages = stages;
+  const uint32_t smem_bytes = 1024 + stages * stage_bytes + aux_bytes;
+
+  CUtensorMap tmap_a, tmap_b;
+  if (int rc = make_tmap_2d_bf16(&tmap_a, a->in, a->cin_pad, p.n_slots, static_cast<uint64_t>(a->ld_in) * 2, 64, kTileM))
+    return rc;
+  const uint64_t k_total = static_cast<uint64_t>(4) * p.n_kc * 64;
+  if (int rc = make_tmap_2d_bf16(&tmap_b, a->wpack, k_total, p.n_pad, k_total * 2, 64, p.b_box_rows)) return rc;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv2x2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    MMLF_REQUIRE(e == cudaSuccess, "conv2x2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  conv2x2_tc_kernel<<<grid, kConvThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmap_a, tmap_b, p);
+  return check_launch("conv2x2_tc_kernel");
+}
+
+extern "C" int mmlf_conv2x2_simt(const mmlf_conv_args* a, void* stream) {
+  ConvParams p;
+  if (int rc = fill_params(a, p)) return rc;
+  const int64_t total = p.n_slots * (p.n_pad / 16);
+  const int threads = 128;
+  const int64_t blocks = ceil_div64(total, threads);
+  conv2x2_simt_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(a->in), a->ld_in, a->cin_pad,
+      reinterpret_cast<const __nv_bfloat16*>(a->wpack), 4 * p.n_kc * 64, p);
+  return check_launch("conv2x2_simt_kernel");
+}

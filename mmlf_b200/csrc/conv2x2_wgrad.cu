@@ -1,0 +1,248 @@
+// Weight gradient of the 2x2 convolution on tcgen05: both operands are read "MN-major" straight from the
+// channel-last slot arrays, so no transposed copies of activations or gradients are ever made.
+//
+//   dW[(tap, c)][n] = sum_slots act[slot + off(tap)][c] * dout[slot][n]         (autograd of feed_forward.py:123,125)
+//
+//   GEMM view : M = (tap, 64-channel chunk, channel) -> 4 * kc * 64 rows in blocks of 128 (two chunks),
+//               N = n_pad output channels (one TMEM accumulator of <= 320 columns), K = slots.
+//   A operand : act rows [64 slots][64 channels] per chunk (TMA box, SWIZZLE_128B), MN-major descriptor
+//               (LBO = distance between the two channel chunks, SBO = 1024 B between 8-slot groups).
+//   B operand : dout rows [64 slots][64 channels] x ceil(n_pad / 64) boxes, MN-major.
+//   split-K   : the slot range is divided over CTAs; partial sums go to a workspace and are reduced by a second,
+//               deterministic kernel that also writes the [n][tap][c] layout.
+#include "../../include/mmlf_b200.h"
+#include "common.cuh"
+#include "host_util.h"
+
+namespace mmlf {
+
+constexpr int kWgThreads = 192;
+constexpr int kWgKb = 64;                       // slots per pipeline stage
+constexpr int kWgBox = kWgKb * 128;             // bytes of one [64 slots][64 ch] box
+constexpr int kWgMaxStages = 6;
+
+struct WgradParams {
+  int64_t n_slots;
+  int n_pad, n_boxes;                           // output channels, ceil(n_pad / 64)
+  int kc;                                       // channel chunks per tap of the activation operand
+  int n_mblocks, ksplits;
+  int64_t slots_per_split;                      // multiple of kWgKb
+  int tap_off[4];
+  int stages;
+  int part_n[2], n_parts;
+  float* ws;                                    // [ksplits][n_mblocks * 128][ws_ld]
+  int ws_ld;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv2x2_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_dout,
+                     const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (tiles_addr - raw_addr);
+  const uint32_t a_bytes = 2 * kWgBox, b_bytes = static_cast<uint32_t>(p.n_boxes) * kWgBox;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  uint8_t* aux = smem + static_cast<size_t>(p.stages) * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* empty_bar = full_bar + kWgMaxStages;
+  uint64_t* done_bar = empty_bar + kWgMaxStages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mblock = blockIdx.x % p.n_mblocks, ks = blockIdx.x / p.n_mblocks;
+  const int64_t k_begin = static_cast<int64_t>(ks) * p.slots_per_split;
+  int64_t k_end = k_begin + p.slots_per_split;
+  if (k_end > p.n_slots) k_end = p.n_slots;
+  const int n_chunks = k_end > k_begin ? static_cast<int>((k_end - k_begin + kWgKb - 1) / kWgKb) : 0;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_act);
+    prefetch_tmap(&tmap_dout);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < p.stages; ++i) {
+        mbar_init(smem_u32(&full_bar[i]), 1);
+        mbar_init(smem_u32(&empty_bar[i]), 1);
+      }
+      mbar_init(smem_u32(done_bar), 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_ptr_smem), 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        const int row0 = static_cast<int>(k_begin + static_cast<int64_t>(ch) * kWgKb);
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+        const uint32_t fb = smem_u32(&full_bar[stage]);
+        mbar_arrive_expect_tx(fb, stage_bytes);
+        const uint32_t a_dst = tiles_addr + stage * stage_bytes;
+        for (int h = 0; h < 2; ++h) {
+          const int atom = mblock * 2 + h;                 // (tap, chunk) index
+          const int tap = atom / p.kc, chunk = atom - tap * p.kc;
+          tma_load_2d(a_dst + h * kWgBox, &tmap_act, fb, chunk * 64, row0 + p.tap_off[tap]);
+        }
+        const uint32_t b_dst = a_dst + a_bytes;
+        for (int j = 0; j < p.n_boxes; ++j) tma_load_2d(b_dst + j * kWgBox, &tmap_dout, fb, j * 64, row0);
+        if (++stage == static_cast<uint32_t>(p.stages)) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t idesc[2];
+      for (int q = 0; q < p.n_parts; ++q) idesc[q] = make_idesc_bf16(128, p.part_n[q], 1, 1);
+      uint32_t stage = 0, phase = 0, accumulate = 0;
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        tc_fence_after();
+        const uint32_t a_addr = tiles_addr + stage * stage_bytes;
+        const uint32_t b_addr = a_addr + a_bytes;
+        for (int k = 0; k < kWgKb / 16; ++k) {
+          const uint64_t adesc = make_sw128_desc(a_addr + k * 2048, kWgBox, 1024);
+          int col = 0;
+          for (int q = 0; q < p.n_parts; ++q) {
+            const uint64_t bdesc = make_sw128_desc(b_addr + (col / 64) * kWgBox + k * 2048, kWgBox, 1024);
+            umma_f16(tmem_base + col, adesc, bdesc, idesc[q], accumulate);
+            col += p.part_n[q];
+          }
+          accumulate = 1;
+        }
+        umma_commit(smem_u32(&empty_bar[stage]));
+        if (++stage == static_cast<uint32_t>(p.stages)) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      if (n_chunks > 0) umma_commit(smem_u32(done_bar));
+      else mbar_arrive(smem_u32(done_bar));
+    }
+  } else {
+    const int q = warp & 3;
+    mbar_wait(smem_u32(done_bar), 0);
+    tc_fence_after();
+    const int row = q * 32 + lane;
+    float* dst = p.ws + (static_cast<int64_t>(ks) * p.n_mblocks * 128 + mblock * 128 + row) * p.ws_ld;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+      uint32_t r[16];
+      if (n_chunks > 0) {
+        tmem_ld16(taddr + c0, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = 0u;
+      }
+      float4* o = reinterpret_cast<float4*>(dst + c0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        o[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                           __uint_as_float(r[4 * j + 3]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// dw[n][tap][c] = sum_ks ws[ks][(tap * kc + c / 64) * 64 + c % 64][n]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int ksplits, int m_rows, int ws_ld, int kc, int n_pad,
+                                    int cin_pad, float* __restrict__ dw) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<int64_t>(n_pad) * 4 * cin_pad) return;
+  // consecutive threads walk n (contiguous in the workspace) for a fixed (tap, c)
+  const int n = static_cast<int>(idx % n_pad);
+  const int tc = static_cast<int>(idx / n_pad);
+  const int tap = tc / cin_pad, c = tc - tap * cin_pad;
+  const int m = (tap * kc + (c >> 6)) * 64 + (c & 63);
+  float acc = 0.f;
+  for (int k = 0; k < ksplits; ++k) acc += ws[(static_cast<int64_t>(k) * m_rows + m) * ws_ld + n];
+  dw[(static_cast<int64_t>(n) * 4 + tap) * cin_pad + c] = acc;
+}
+
+static void wgrad_shape(int n_pad, int cin_pad, int& kc, int& n_mblocks, int& ksplits, int& ws_ld) {
+  kc = ceil_div(cin_pad, 64);
+  n_mblocks = 4 * kc / 2;
+  ksplits = sm_count() / n_mblocks;
+  if (ksplits < 1) ksplits = 1;
+  ws_ld = n_pad;
+}
+
+}  // namespace mmlf
+
+using namespace mmlf;
+
+extern "C" int64_t mmlf_conv2x2_wgrad_workspace(int n_pad, int cin_pad) {
+  int kc, n_mblocks, ksplits, ws_ld;
+  wgrad_shape(n_pad, cin_pad, kc, n_mblocks, ksplits, ws_ld);
+  return static_cast<int64_t>(ksplits) * n_mblocks * 128 * ws_ld * sizeof(float);
+}
+
+extern "C" int mmlf_conv2x2_wgrad(const void* dout, int ld_dout, int n_pad, const void* act, int ld_act, int cin_pad,
+                                  int B, int H, int W, int type, float* workspace, float* dw, void* stream) {
+  MMLF_REQUIRE(dout && act && workspace && dw, "wgrad: null buffer");
+  MMLF_REQUIRE(n_pad % 16 == 0 && n_pad >= 16 && n_pad <= 320, "wgrad: n_pad %d must be a multiple of 16 in [16, 320]", n_pad);
+  MMLF_REQUIRE(cin_pad % 16 == 0 && cin_pad >= 16 && cin_pad <= 320, "wgrad: cin_pad %d must be a multiple of 16 in [16, 320]", cin_pad);
+  MMLF_REQUIRE(ld_dout % 8 == 0 && ld_act % 8 == 0 && ld_dout >= n_pad && ld_act >= cin_pad, "wgrad: bad row pitch");
+  MMLF_REQUIRE(type == 0 || type == 1, "wgrad: type must be 0 or 1");
+  WgradParams p;
+  const int Hp = H + 1, Wp = W + 1;
+  p.n_slots = static_cast<int64_t>(B) * Hp * Wp;
+  MMLF_REQUIRE(p.n_slots + 4096 < (1ll << 31), "wgrad: too many slots");
+  p.n_pad = n_pad;
+  p.n_boxes = ceil_div(n_pad, 64);
+  wgrad_shape(n_pad, cin_pad, p.kc, p.n_mblocks, p.ksplits, p.ws_ld);
+  int64_t per = ceil_div64(p.n_slots, p.ksplits);
+  per = ceil_div64(per, kWgKb) * kWgKb;
+  p.slots_per_split = per;
+  if (type == 0) {
+    p.tap_off[0] = 0; p.tap_off[1] = 1; p.tap_off[2] = Wp; p.tap_off[3] = Wp + 1;
+  } else {
+    p.tap_off[0] = -Wp - 1; p.tap_off[1] = -Wp; p.tap_off[2] = -1; p.tap_off[3] = 0;
+  }
+  if (n_pad > 256) {
+    p.n_parts = 2; p.part_n[0] = 256; p.part_n[1] = n_pad - 256;
+  } else {
+    p.n_parts = 1; p.part_n[0] = n_pad; p.part_n[1] = 0;
+  }
+  p.ws = workspace;
+  const uint32_t stage_bytes = (2 + p.n_boxes) * kWgBox;
+  const uint32_t aux_bytes = (2 * kWgMaxStages + 1) * 8 + 16 + 64;
+  const uint32_t max_smem = 232448;
+  int stages = static_cast<int>((max_smem - 1024 - aux_bytes) / stage_bytes);
+  if (stages > kWgMaxStages) stages = kWgMaxStages;
+  MMLF_REQUIRE(stages >= 2, "wgrad: not enough shared memory");
+  p.stages = stages;
+  const uint32_t smem_bytes = 1024 + stages * stage_bytes + aux_bytes;
+
+  CUtensorMap tmap_act, tmap_dout;
+  if (int rc = make_tmap_2d_bf16(&tmap_act, act, cin_pad, p.n_slots, static_cast<uint64_t>(ld_act) * 2, 64, kWgKb)) return rc;
+  if (int rc = make_tmap_2d_bf16(&tmap_dout, dout, n_pad, p.n_slots, static_cast<uint64_t>(ld_dout) * 2, 64, kWgKb)) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv2x2_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    MMLF_REQUIRE(e == cudaSuccess, "wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  conv2x2_wgrad_kernel<<<p.n_mblocks * p.ksplits, kWgThreads, smem_bytes, st>>>(tmap_act, tmap_dout, p);
+  if (int rc = check_launch("conv2x2_wgrad_kernel")) return rc;
+  const int64_t total = static_cast<int64_t>(n_pad) * 4 * cin_pad;
+  wgrad_reduce_kernel<<<static_cast<unsigned>(ceil_div64(total, 256)), 256, 0, st>>>(
+      workspace, p.ksplits, p.n_mblocks * 128, p.ws_ld, p.kc, n_pad, cin_pad, dw);
+  return check_launch("wgrad_reduce_kernel");
+}

@@ -1,0 +1,243 @@
+// Masked losses with their gradients fused into the same pass, and the Adam update.
+// Reference: /root/reference/mmlf/model/loss.py (MaskedL1Loss :46-77, MultiMaskedL1Loss :88-103, MaskedMSELoss
+// :114-122, MaskedCrossEntropy :145-160, MaskedBadPix :177-187, ImprovedUncertaintyL1Loss :262-294,
+// ImprovedMultiUncertaintyL1Loss :344-372) and torch.optim.Adam as used at train/cli.py:113-118,258.
+//
+// Every loss divides by global scalars (mask count, ...).  Those come from a cheap pre-pass so that (a) the main
+// kernel can write final gradients in one pass and (b) the scalars can be all-reduced across ranks in between
+//  without a host synchronisation.
+#include "../../include/mmlf_b200.h"
+#include "common.cuh"
+#include "host_util.h"
+
+namespace mmlf {
+
+__device__ __forceinline__ double block_sum_double(double v, double* red) {
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) red[wrp] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < (blockDim.x >> 5); ++w) r += red[w];
+  __syncthreads();
+  return r;   // valid in thread 0
+}
+
+__global__ void __launch_bounds__(256)
+loss_prepass_kernel(const int32_t* __restrict__ mask, const int32_t* __restrict__ mask_padding,
+                    const float* __restrict__ mpi, int K, int64_t B, int64_t HW, double* __restrict__ sums) {
+  __shared__ double red[8];
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < B * HW;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    a0 += static_cast<double>(mask[idx]);
+    if (mask_padding) a1 += static_cast<double>(mask_padding[idx]);
+    if (mpi) {
+      const int64_t b = idx / HW, pix = idx - b * HW;
+      float ws = 0.f;
+      for (int k = 0; k < K; ++k) ws += mpi[((b * K + k) * 5 + 3) * HW + pix];
+      a2 += static_cast<double>(ws);
+      if (ws < 0.01f) a3 += 1.0;
+    }
+  }
+  double r;
+  r = block_sum_double(a0, red); if (threadIdx.x == 0) atomicAdd(&sums[0], r);
+  r = block_sum_double(a1, red); if (threadIdx.x == 0 && mask_padding) atomicAdd(&sums[1], r);
+  r = block_sum_double(a2, red); if (threadIdx.x == 0 && mpi) atomicAdd(&sums[2], r);
+  r = block_sum_double(a3, red); if (threadIdx.x == 0 && mpi) atomicAdd(&sums[3], r);
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&sums[4], static_cast<double>(B * HW));
+}
+
+__device__ __forceinline__ float sgn(float d) { return d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f); }
+
+__global__ void __launch_bounds__(256)
+loss_regression_kernel(int kind, const float* __restrict__ mean, const float* __restrict__ logvar,
+                       const float* __restrict__ target, int K, const int32_t* __restrict__ mask,
+                       const int32_t* __restrict__ mask_padding, const double* __restrict__ sums, float param,
+                       int64_t B, int64_t HW, double* __restrict__ loss_sum, float* __restrict__ g_mean,
+                       float* __restrict__ g_logvar) {
+  __shared__ double red[8];
+  const double cnt = sums[0];
+  const float scale = cnt == 0.0 ? 1.f : static_cast<float>(1.0 / cnt);
+  const double N = sums[4];                                   // global pixel count (all-reduced with the rest)
+  float k_in = 1.f, k_oor = 1.f, inv_mw = 1.f;
+  if (kind == 2 && mask_padding) {
+    const double sp = sums[1], so = N - sums[1];
+    if (sp > 0) k_in = static_cast<float>(N / sp);
+    if (so > 0) k_oor = static_cast<float>(N / so);
+  }
+  if (kind == 3) {
+    inv_mw = static_cast<float>(1.0 / (sums[2] / N));        // 1 / mean_px(sum_k w_k)      (loss.py:356)
+    k_oor = static_cast<float>(N / sums[3]);                 // inf when no OOR pixel -> NaN as in the reference (loss.py:361)
+  }
+  double acc = 0.0;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < B * HW;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float m = static_cast<float>(mask[idx]);
+    const float mu = mean[idx];
+    float l = 0.f, gm = 0.f, gl = 0.f;
+    if (kind == 0 || kind == 4 || kind == 5) {
+      const float d = mu - target[idx];
+      if (kind == 0) { l = fabsf(d); gm = sgn(d); }
+      else if (kind == 4) { l = d * d; }
+      else { l = fabsf(d) > param ? 1.f : 0.f; }
+    } else if (kind == 2) {
+      const float lv = logvar[idx];
+      const float d = mu - target[idx];
+      const float e = expf(-lv);
+      l = e * fabsf(d) + lv;
+      gm = e * sgn(d);
+      gl = 1.f - e * fabsf(d);
+      if (mask_padding) {
+        const float mp = static_cast<float>(mask_padding[idx]), mo = 1.f - mp;
+        l = (l * mp * k_in + (-lv) * mo * k_oor) * 0.5f;
+        gm = gm * mp * k_in * 0.5f;
+        gl = (gl * mp * k_in - mo * k_oor) * 0.5f;
+      }
+    } else {                                                  // multi-plane targets (B, K, 5, H, W)
+      const int64_t b = idx / HW, pix = idx - b * HW;
+      const float lv = kind == 3 ? logvar[idx] : 0.f;
+      const float e = kind == 3 ? expf(-lv) : 1.f;
+      float ws = 0.f, sl = 0.f, sg = 0.f, sad = 0.f;
+      for (int k = 0; k < K; ++k) {
+        const float w = target[((b * K + k) * 5 + 3) * HW + pix];
+        const float d = mu - target[((b * K + k) * 5 + 4) * HW + pix];
+        ws += w;
+        sad += w * fabsf(d);
+        sg += w * sgn(d);
+        sl += w * (e * fabsf(d) + lv);
+      }
+      if (kind == 1) {
+        l = sad;
+        gm = sg;
+      } else {
+        const float oor = ws < 0.01f ? 1.f : 0.f;
+        l = (sl * inv_mw + (-lv) * oor * k_oor) * 0.5f;
+        gm = e * sg * inv_mw * 0.5f;
+        gl = ((ws - e * sad) * inv_mw - oor * k_oor) * 0.5f;
+      }
+    }
+    acc += static_cast<double>(l * m);
+    if (g_mean) g_mean[idx] = gm * m * scale;
+    if (g_logvar) g_logvar[idx] = gl * m * scale;
+  }
+  const double r = block_sum_double(acc, red);
+  if (threadIdx.x == 0) atomicAdd(loss_sum, r);
+}
+
+__global__ void __launch_bounds__(128)
+loss_ce_kernel(const float* __restrict__ scores, const float* __restrict__ target, const float* __restrict__ gt,
+               const float* __restrict__ bins, float half_step, int steps, const int32_t* __restrict__ mask,
+               const double* __restrict__ sums, int64_t B, int64_t HW, double* __restrict__ loss_sum,
+               float* __restrict__ g_scores) {
+  __shared__ double red[4];
+  extern __shared__ float sb[];
+  for (int i = threadIdx.x; i < steps; i += blockDim.x) sb[i] = bins ? bins[i] : 0.f;
+  __syncthreads();
+  const double cnt = sums[0];
+  const float scale = cnt == 0.0 ? 1.f : static_cast<float>(1.0 / cnt);
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  double acc = 0.0;
+  if (idx < B * HW) {
+    const int64_t b = idx / HW, pix = idx - b * HW;
+    const float* s = scores + b * steps * HW + pix;
+    const float* t = target ? target + b * steps * HW + pix : nullptr;
+    const float g = gt ? gt[idx] : 0.f;
+    const float m = static_cast<float>(mask[idx]);
+    float z = 0.f, dot = 0.f;
+    for (int c = 0; c < steps; ++c) {
+      const float v = fmaxf(__ldg(s + c * HW), 0.f);           // ReLU on the logits (loss.py:146)
+      const float tc = t ? __ldg(t + c * HW) : (fabsf(sb[c] - g) < half_step ? 1.f : 0.f);
+      z += expf(v);                                             // unstabilised (loss.py:147-149)
+      dot += v * tc;
+    }
+    const float l = -logf(expf(dot) / z);
+    acc = static_cast<double>(l * m);
+    if (g_scores) {
+      float* go = g_scores + b * steps * HW + pix;
+      const float k = m * scale;
+      for (int c = 0; c < steps; ++c) {
+        const float raw = __ldg(s + c * HW);
+        const float tc = t ? __ldg(t + c * HW) : (fabsf(sb[c] - g) < half_step ? 1.f : 0.f);
+        go[c * HW] = raw > 0.f ? (expf(raw) / z - tc) * k : 0.f;
+      }
+    }
+  }
+  const double r = block_sum_double(acc, red);
+  if (threadIdx.x == 0) atomicAdd(loss_sum, r);
+}
+
+// torch.optim.Adam single-tensor update: exp_avg.lerp_(g, 1-b1); exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2);
+// denom = exp_avg_sq.sqrt() / sqrt(bc2) + eps; p.addcdiv_(exp_avg, denom, value=-lr/bc1)
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float one_minus_b1, float b2, float one_minus_b2,
+                            float step_size, float bc2_sqrt, float eps) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i];
+  const float mi = m[i] + one_minus_b1 * (gi - m[i]);
+  const float vi = v[i] * b2 + one_minus_b2 * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] = p[i] - step_size * (mi / denom);
+}
+
+static int grid_for(int64_t n, int threads, int per_thread) {
+  int64_t want = ceil_div64(n, static_cast<int64_t>(threads) * per_thread);
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return static_cast<int>(want);
+}
+
+}  // namespace mmlf
+
+using namespace mmlf;
+
+extern "C" int mmlf_loss_prepass(const int32_t* mask, const int32_t* mask_padding, const float* mpi, int K, int64_t B,
+                                 int64_t HW, double* sums, void* stream) {
+  MMLF_REQUIRE(mask && sums, "loss_prepass: null buffer");
+  MMLF_REQUIRE(!mpi || (K >= 1 && K <= 64), "loss_prepass: bad K");
+  loss_prepass_kernel<<<grid_for(B * HW, 256, 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, mask_padding, mpi, K,
+                                                                                          B, HW, sums);
+  return check_launch("loss_prepass");
+}
+
+extern "C" int mmlf_loss_regression(int kind, const float* mean, const float* logvar, const float* target, int K,
+                                    const int32_t* mask, const int32_t* mask_padding, const double* sums, double param,
+                                    int64_t B, int64_t HW, double* loss_sum, float* g_mean, float* g_logvar,
+                                    void* stream) {
+  MMLF_REQUIRE(kind >= 0 && kind <= 5, "loss_regression: kind must be 0..5");
+  MMLF_REQUIRE(mean && target && mask && sums && loss_sum, "loss_regression: null buffer");
+  MMLF_REQUIRE((kind != 2 && kind != 3) || logvar, "loss_regression: logvar required for the uncertainty losses");
+  MMLF_REQUIRE((kind != 1 && kind != 3) || (K >= 1 && K <= 64), "loss_regression: bad K");
+  loss_regression_kernel<<<grid_for(B * HW, 256, 2), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      kind, mean, logvar, target, K, mask, mask_padding, sums, static_cast<float>(param), B, HW, loss_sum, g_mean,
+      g_logvar);
+  return check_launch("loss_regression");
+}
+
+extern "C" int mmlf_loss_cross_entropy(const float* scores, const float* target, const float* gt, const float* bins_t,
+                                       double half_step, int steps, const int32_t* mask, const double* sums, int64_t B,
+                                       int64_t HW, double* loss_sum, float* g_scores, void* stream) {
+  MMLF_REQUIRE(scores && mask && sums && loss_sum, "loss_cross_entropy: null buffer");
+  MMLF_REQUIRE(target || (gt && bins_t), "loss_cross_entropy: need a target tensor or gt + bins");
+  loss_ce_kernel<<<static_cast<unsigned>(ceil_div64(B * HW, 128)), 128, steps * sizeof(float),
+                   static_cast<cudaStream_t>(stream)>>>(scores, target, gt, bins_t, static_cast<float>(half_step), steps,
+                                                        mask, sums, B, HW, loss_sum, g_scores);
+  return check_launch("loss_cross_entropy");
+}
+
+extern "C" int mmlf_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1,
+                              double beta2, double eps, int64_t step, void* stream) {
+  MMLF_REQUIRE(p && g && m && v && step >= 1, "adam_step: bad arguments");
+  const double bc1 = 1.0 - pow(beta1, static_cast<double>(step));
+  const double bc2 = 1.0 - pow(beta2, static_cast<double>(step));
+  adam_kernel<<<static_cast<unsigned>(ceil_div64(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      p, g, m, v, n, static_cast<float>(1.0 - beta1), static_cast<float>(beta2), static_cast<float>(1.0 - beta2),
+      static_cast<float>(lr / bc1), static_cast<float>(sqrt(bc2)), static_cast<float>(eps));
+  return check_launch("adam_step");
+}

@@ -1,0 +1,390 @@
+"""Execution plan of the FeedForward disparity network on the sm_100a kernels.
+
+Mirrors ``FeedForward.forward`` of the reference (/root/reference/mmlf/model/feed_forward.py:206-305) and its
+autograd, but on the bf16 "slot" layout (include/mmlf_b200.h): every conv is one launch of the tcgen05 implicit
+GEMM, BatchNorm/ReLU/heads are fused or bandwidth kernels, and the backward pass is written out by hand
+(dgrad = the same conv kernel with rotated weights, wgrad = the MN-major tcgen05 kernel).
+
+PyTorch is used for device memory, streams and autograd plumbing only; no ATen compute op runs on the path.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import ConvArgs, call
+
+
+def pad16(x):
+    return (x + 15) // 16 * 16
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Geometry:
+    def __init__(self, B, H, W):
+        self.B, self.H, self.W = B, H, W
+        self.Hp, self.Wp = H + 1, W + 1
+        self.n_slots = B * self.Hp * self.Wp
+        self.count = B * H * W
+
+
+class ConvSpec:
+    """One nn.Conv2d of the reference with its padded GEMM shapes and packed operands."""
+
+    def __init__(self, name, cout, cin, ctype, spatial=0, groups=1, group_real=None, group_pad=None):
+        self.name = name                      # state_dict prefix, e.g. 'out_net.0.0'
+        self.cout, self.cin, self.type, self.spatial = cout, cin, ctype, spatial
+        self.groups = groups
+        self.group_real = group_real if group_real is not None else cin
+        self.group_pad = group_pad if group_pad is not None else pad16(cin)
+        self.cin_pad = groups * self.group_pad if groups > 1 else pad16(cin)
+        self.n_pad = pad16(cout)
+        self.w_fwd = None                     # bf16 [n_pad][4*kc*64]
+        self.w_dgrad = None                   # bf16 [cin_pad][4*kc'*64]
+        self.bias_pad = None                  # f32 [n_pad]
+
+    @property
+    def kc(self):
+        return (self.cin_pad + 63) // 64
+
+
+class Engine:
+    """Owns packed parameters and scratch buffers for one FeedForward module."""
+
+    def __init__(self, module):
+        self.m = module
+        self.chs = module.chs
+        self.views = module.views
+        self.cross = module.cross
+        self.has_bn = not module.no_batchnorm
+        self.n_streams = 2 if self.cross else 4
+        self.in_blocks = module.n_in_blocks
+        self.out_blocks = module.n_out_blocks
+        self.oc = module.out_chs
+        self.small_head = self.oc <= 2
+        self.cp = pad16(self.chs)                       # per-stream feature pitch (70 -> 80)
+        self.feat_ld = self.n_streams * self.cp         # concatenated feature buffer (280 -> 320)
+        self.width = self.n_streams * self.chs          # out-net width (280)
+        self.wp = pad16(self.width)                     # 288
+        assert self.feat_ld <= 320 and self.wp <= 320, 'model_chs too large for the 320-column TMEM plan'
+        self._pack_version = None
+        self._build_specs()
+
+    # ------------------------------------------------------------------ static plan
+    def _build_specs(self):
+        cin0 = self.views * 3
+        self.stream_defs = [('h', 'in_net_hv', 1), ('v', 'in_net_hv', 0)]
+        if not self.cross:
+            self.stream_defs += [('i', 'in_net_id', 2), ('d', 'in_net_id', 0)]
+        self.in_specs = {}
+        for key, net, spatial in self.stream_defs:
+            blocks = []
+            for k in range(self.in_blocks):
+                cin = cin0 if k == 0 else self.chs
+                c1 = ConvSpec(f'{net}.{k}.0', self.chs, cin, 0, spatial)
+                c2 = ConvSpec(f'{net}.{k}.2', self.chs, self.chs, 1, spatial)
+                blocks.append((c1, c2, f'{net}.{k}.3'))
+            self.in_specs[key] = blocks
+        self.out_specs = []
+        for k in range(self.out_blocks - 1):
+            if k == 0:
+                c1 = ConvSpec(f'out_net.{k}.0', self.width, self.width, 0, 0, self.n_streams, self.chs, self.cp)
+            else:
+                c1 = ConvSpec(f'out_net.{k}.0', self.width, self.width, 0)
+            c2 = ConvSpec(f'out_net.{k}.2', self.width, self.width, 1)
+            self.out_specs.append((c1, c2, f'out_net.{k}.3'))
+        k = self.out_blocks - 1
+        if k == 0:
+            self.head1 = ConvSpec(f'out_net.{k}.0', self.oc, self.width, 0, 0, self.n_streams, self.chs, self.cp)
+        else:
+            self.head1 = ConvSpec(f'out_net.{k}.0', self.oc, self.width, 0)
+        self.head2 = ConvSpec(f'out_net.{k}.2', self.oc, self.oc, 1)
+
+    def all_convs(self):
+        seen = []
+        for blocks in self.in_specs.values():
+            for c1, c2, _ in blocks:
+                seen += [c1, c2]
+        for c1, c2, _ in self.out_specs:
+            seen += [c1, c2]
+        seen.append(self.head1)
+        if not self.small_head:
+            seen.append(self.head2)
+        return seen
+
+    # ------------------------------------------------------------------ parameters
+    def _params(self):
+        return dict(self.m.named_parameters())
+
+    def _buffers(self):
+        return dict(self.m.named_buffers())
+
+    def repack(self, need_dgrad):
+        """(Re)build the packed bf16 operands when the canonical fp32 parameters changed."""
+        params = self._params()
+        version = tuple(p._version for p in params.values()) + tuple(p.data_ptr() for p in params.values())
+        if self._pack_version is not None and self._pack_version[0] == version and \
+                (self._pack_version[1] or not need_dgrad):
+            return
+        dev = next(iter(params.values())).device
+        st = _stream()
+        for cs in self.all_convs():
+            w = params[cs.name + '.weight'].detach()
+            b = params[cs.name + '.bias'].detach()
+            kc = cs.kc
+            if cs.w_fwd is None:
+                cs.w_fwd = torch.empty((cs.n_pad, 4 * kc * 64), dtype=torch.bfloat16, device=dev)
+                cs.bias_pad = torch.zeros(cs.n_pad, dtype=torch.float32, device=dev)
+            call('mmlf_pack_conv_weight', _ptr(w), cs.cout, cs.cin, cs.spatial, 0, cs.groups, cs.group_real,
+                 cs.group_pad, _ptr(cs.w_fwd), cs.n_pad, cs.cin_pad, st)
+            cs.bias_pad[:cs.cout].copy_(b)
+            if need_dgrad:
+                kd = (cs.n_pad + 63) // 64
+                if cs.w_dgrad is None:
+                    cs.w_dgrad = torch.empty((cs.cin_pad, 4 * kd * 64), dtype=torch.bfloat16, device=dev)
+                call('mmlf_pack_conv_weight', _ptr(w), cs.cout, cs.cin, cs.spatial, 1, cs.groups, cs.group_real,
+                     cs.group_pad, _ptr(cs.w_dgrad), cs.cin_pad, cs.n_pad, st)
+        self._pack_version = (version, bool(need_dgrad))
+
+    def _bn_padded(self, prefix, C_real, C, dev):
+        """gamma/beta padded with zeros to the channel pitch (fp32)."""
+        p = self._params()
+        g = torch.zeros(C, dtype=torch.float32, device=dev)
+        b = torch.zeros(C, dtype=torch.float32, device=dev)
+        g[:C_real].copy_(p[prefix + '.weight'].detach())
+        b[:C_real].copy_(p[prefix + '.bias'].detach())
+        return g, b
+
+    # ------------------------------------------------------------------ kernel launch helpers
+    def conv(self, geo, x, ld_in, cs, w, n_pad, cin_pad, ctype, out, ld_out, *, bias=None, scale=None, shift=None,
+             relu=False, gate=None, ld_gate=0, out_mode=0, n_real=0, simt=False):
+        a = ConvArgs()
+        a.in_, a.ld_in, a.cin_pad = x.data_ptr(), ld_in, cin_pad
+        a.wpack, a.n_pad = w.data_ptr(), n_pad
+        a.B, a.H, a.W, a.type = geo.B, geo.H, geo.W, ctype
+        a.bias = bias.data_ptr() if bias is not None else None
+        a.scale = scale.data_ptr() if scale is not None else None
+        a.shift = shift.data_ptr() if shift is not None else None
+        a.relu = 1 if relu else 0
+        a.gate = gate.data_ptr() if gate is not None else None
+        a.ld_gate = ld_gate
+        a.out, a.ld_out, a.out_mode, a.n_real = out.data_ptr(), ld_out, out_mode, n_real
+        call('mmlf_conv2x2_simt' if simt else 'mmlf_conv2x2', C.byref(a), _stream())
+
+    def _slots(self, geo, ch, dtype=torch.bfloat16):
+        return torch.empty((geo.n_slots, ch), dtype=dtype, device=self.dev)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, views, training, save, shift_disp=None):
+        """views: list of (B, n, 3, H, W) fp32 CUDA tensors (h, v[, i, d]).  Returns (B, OC, H, W) fp32 and, when
+        ``save`` is set, the tape needed by :meth:`backward`.  ``shift_disp`` fuses the ESE Shift into the packing."""
+        _lib.require_device()
+        h = views[0]
+        B, n, c3, H, W = h.shape
+        self.dev = h.device
+        geo = Geometry(B, H, W)
+        st = _stream()
+        self.repack(need_dgrad=save)
+        bn_train = training and self.has_bn
+        tape = {'geo': geo, 'streams': {}, 'out': [], 'bn_train': bn_train} if save else None
+        bufs = self._buffers()
+        params = self._params()
+        cin0_pad = pad16(n * c3)
+
+        feats = self._slots(geo, self.feat_ld)
+        for si, (key, net, spatial) in enumerate(self.stream_defs):
+            v = views[si]
+            assert v.is_cuda and v.dtype == torch.float32 and v.is_contiguous(), \
+                'view stacks must be contiguous fp32 CUDA tensors (feed_forward.py:226-232 uses .view)'
+            x = self._slots(geo, cin0_pad)
+            if shift_disp is None:
+                call('mmlf_pack_views', _ptr(v), B, n * c3, H, W, _ptr(x), cin0_pad, st)
+            else:
+                call('mmlf_shift_pack', _ptr(v), si, B, n, H, W, float(shift_disp), _ptr(x), cin0_pad, st)
+            ld_x = cin0_pad
+            recs = []
+            blocks = self.in_specs[key]
+            for k, (c1, c2, bnp) in enumerate(blocks):
+                last = k == len(blocks) - 1
+                if last:      # write straight into this stream's slice of the concatenated feature buffer
+                    y, ld_y = feats[:, si * self.cp:], self.feat_ld
+                else:
+                    y, ld_y = self._slots(geo, c2.n_pad), c2.n_pad
+                rec = self._block_fwd(geo, x, ld_x, c1, c2, bnp, y, ld_y, training, bn_train, save, bufs, params)
+                recs.append(rec)
+                x, ld_x = y, ld_y
+            if save:
+                tape['streams'][key] = recs
+        x, ld_x = feats, self.feat_ld
+        for k, (c1, c2, bnp) in enumerate(self.out_specs):
+            y = self._slots(geo, c2.n_pad)
+            rec = self._block_fwd(geo, x, ld_x, c1, c2, bnp, y, c2.n_pad, training, bn_train, save, bufs, params)
+            if save:
+                tape['out'].append(rec)
+            x, ld_x = y, c2.n_pad
+        # head block: conv -> ReLU -> conv, no BN / ReLU after (feed_forward.py:185)
+        h1 = self.head1
+        out = torch.empty((B, self.oc, H, W), dtype=torch.float32, device=self.dev)
+        if self.small_head:
+            mid = self._slots(geo, h1.n_pad, torch.float32)
+            self.conv(geo, x, ld_x, h1, h1.w_fwd, h1.n_pad, h1.cin_pad, 0, mid, h1.n_pad, bias=h1.bias_pad, relu=True,
+                      out_mode=1)
+            w2 = params[self.head2.name + '.weight'].detach()
+            b2 = params[self.head2.name + '.bias'].detach()
+            call('mmlf_head_small', _ptr(mid), h1.n_pad, self.oc, _ptr(w2), _ptr(b2), B, H, W, _ptr(out), st)
+        else:
+            h2 = self.head2
+            mid = self._slots(geo, h1.n_pad)
+            self.conv(geo, x, ld_x, h1, h1.w_fwd, h1.n_pad, h1.cin_pad, 0, mid, h1.n_pad, bias=h1.bias_pad, relu=True)
+            self.conv(geo, mid, h1.n_pad, h2, h2.w_fwd, h2.n_pad, h2.cin_pad, 1, out, 0, bias=h2.bias_pad,
+                      out_mode=2, n_real=self.oc)
+        if save:
+            tape['head'] = {'x': x, 'ld_x': ld_x, 'mid': mid}
+        return out, tape
+
+    def _block_fwd(self, geo, x, ld_x, c1, c2, bnp, y, ld_y, training, bn_train, save, bufs, params):
+        """conv(k2,p1) -> ReLU -> conv(k2,p0) [-> BN] -> ReLU   (feed_forward.py:122-137)"""
+        st = _stream()
+        a1 = self._slots(geo, c1.n_pad)
+        self.conv(geo, x, ld_x, c1, c1.w_fwd, c1.n_pad, c1.cin_pad, 0, a1, c1.n_pad, bias=c1.bias_pad, relu=True)
+        rec = {'x': x, 'ld_x': ld_x, 'a1': a1, 'y': y, 'ld_y': ld_y, 'c1': c1, 'c2': c2, 'bnp': bnp} if save else None
+        C_real, Cp = c2.cout, c2.n_pad
+        if not self.has_bn:
+            self.conv(geo, a1, c1.n_pad, c2, c2.w_fwd, Cp, c2.cin_pad, 1, y, ld_y, bias=c2.bias_pad, relu=True)
+            return rec
+        gamma, beta = params[bnp + '.weight'].detach(), params[bnp + '.bias'].detach()
+        rmean, rvar = bufs[bnp + '.running_mean'], bufs[bnp + '.running_var']
+        scale = torch.empty(Cp, dtype=torch.float32, device=self.dev)
+        shift = torch.empty(Cp, dtype=torch.float32, device=self.dev)
+        if not bn_train:
+            # eval: BN folded into the conv epilogue, y = relu(acc * scale + shift)
+            call('mmlf_bn_fold_eval', C_real, Cp, _ptr(gamma), _ptr(beta), _ptr(rmean), _ptr(rvar),
+                 _ptr(c2.bias_pad), float(self.m.bn_eps), _ptr(scale), _ptr(shift), st)
+            self.conv(geo, a1, c1.n_pad, c2, c2.w_fwd, Cp, c2.cin_pad, 1, y, ld_y, scale=scale, shift=shift, relu=True)
+            if save:
+                raise NotImplementedError('--train_eval_mode (training through eval-mode BatchNorm) is not supported')
+            return rec
+        z = self._slots(geo, Cp)
+        self.conv(geo, a1, c1.n_pad, c2, c2.w_fwd, Cp, c2.cin_pad, 1, z, Cp, bias=c2.bias_pad)
+        sums = torch.zeros(2 * Cp, dtype=torch.float64, device=self.dev)
+        call('mmlf_bn_stats', _ptr(z), Cp, Cp, geo.B, geo.H, geo.W, _ptr(sums), st)
+        save_mean = torch.empty(Cp, dtype=torch.float32, device=self.dev)
+        save_invstd = torch.empty(Cp, dtype=torch.float32, device=self.dev)
+        nbt = bufs.get(bnp + '.num_batches_tracked')
+        call('mmlf_bn_finalize', _ptr(sums), C_real, Cp, geo.count, _ptr(gamma), _ptr(beta), _ptr(rmean), _ptr(rvar),
+             _ptr(nbt), float(self.m.batchnorm_momentum), float(self.m.bn_eps), _ptr(scale), _ptr(shift),
+             _ptr(save_mean), _ptr(save_invstd), st)
+        call('mmlf_bn_apply_relu', _ptr(z), Cp, _ptr(scale), _ptr(shift), Cp, geo.B, geo.H, geo.W, _ptr(y), ld_y, st)
+        if save:
+            rec.update(z=z, save_mean=save_mean, save_invstd=save_invstd)
+        return rec
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, tape, g_out):
+        """g_out: (B, OC, H, W) fp32.  Returns {param name: fp32 gradient} for every parameter."""
+        geo = tape['geo']
+        st = _stream()
+        params = self._params()
+        grads = {}
+        dev = self.dev
+        ws_bytes = max(_lib.lib().mmlf_conv2x2_wgrad_workspace(cs.n_pad, cs.cin_pad) for cs in self.all_convs())
+        ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
+        dwp = torch.empty(320 * 4 * 320, dtype=torch.float32, device=dev)
+
+        def conv_param_grads(cs, dout, ld_dout, act, ld_act):
+            """dW via the tcgen05 wgrad kernel, db via a column sum; accumulates for shared modules."""
+            call('mmlf_conv2x2_wgrad', _ptr(dout), ld_dout, cs.n_pad, _ptr(act), ld_act, cs.cin_pad, geo.B, geo.H,
+                 geo.W, cs.type, _ptr(ws), _ptr(dwp), st)
+            wname, bname = cs.name + '.weight', cs.name + '.bias'
+            acc = wname in grads
+            if not acc:
+                grads[wname] = torch.empty_like(params[wname], memory_format=torch.contiguous_format)
+                grads[bname] = torch.zeros(cs.n_pad, dtype=torch.float32, device=dev)
+            call('mmlf_unpack_conv_wgrad', _ptr(dwp), cs.n_pad, cs.cin_pad, cs.cout, cs.cin, cs.spatial, cs.groups,
+                 cs.group_real, cs.group_pad, _ptr(grads[wname]), 1 if acc else 0, st)
+            call('mmlf_colsum_bf16', _ptr(dout), ld_dout, cs.n_pad, geo.n_slots, _ptr(grads[bname]), 1, st)
+
+        def dgrad(cs, dout, ld_dout, out, ld_out, gate=None, ld_gate=0):
+            """Data gradient: the conv kernel of the other type with rotated, transposed weights."""
+            self.conv(geo, dout, ld_dout, cs, cs.w_dgrad, cs.cin_pad, cs.n_pad, 1 - cs.type, out, ld_out, gate=gate,
+                      ld_gate=ld_gate)
+
+        # ---- head
+        hd = tape['head']
+        h1 = self.head1
+        g_x = self._slots(geo, h1.cin_pad)
+        if self.small_head:
+            h2n = self.head2.name
+            w2 = params[h2n + '.weight'].detach()
+            gmid = self._slots(geo, h1.n_pad)
+            grads[h2n + '.weight'] = torch.zeros_like(params[h2n + '.weight'])
+            grads[h2n + '.bias'] = torch.zeros_like(params[h2n + '.bias'])
+            call('mmlf_head_small_bwd', _ptr(g_out), _ptr(hd['mid']), h1.n_pad, self.oc, _ptr(w2), geo.B, geo.H, geo.W,
+                 _ptr(gmid), h1.n_pad, _ptr(grads[h2n + '.weight']), _ptr(grads[h2n + '.bias']), st)
+        else:
+            h2 = self.head2
+            gz = self._slots(geo, h2.n_pad)
+            call('mmlf_pack_views', _ptr(g_out), geo.B, self.oc, geo.H, geo.W, _ptr(gz), h2.n_pad, st)
+            conv_param_grads(h2, gz, h2.n_pad, hd['mid'], h1.n_pad)
+            gmid = self._slots(geo, h1.n_pad)
+            dgrad(h2, gz, h2.n_pad, gmid, h1.n_pad, gate=hd['mid'], ld_gate=h1.n_pad)
+        conv_param_grads(h1, gmid, h1.n_pad, hd['x'], hd['ld_x'])
+        dgrad(h1, gmid, h1.n_pad, g_x, h1.cin_pad)
+        gy, ld_gy = g_x, h1.cin_pad
+
+        def block_bwd(rec, gy, ld_gy, need_gx):
+            c1, c2, bnp = rec['c1'], rec['c2'], rec['bnp']
+            Cp, C_real = c2.n_pad, c2.cout
+            dz = self._slots(geo, Cp)
+            if self.has_bn:
+                sums = torch.zeros(2 * Cp, dtype=torch.float64, device=dev)
+                call('mmlf_bn_bwd_reduce', _ptr(gy), ld_gy, _ptr(rec['y']), rec['ld_y'], _ptr(rec['z']), Cp,
+                     _ptr(rec['save_mean']), _ptr(rec['save_invstd']), Cp, geo.B, geo.H, geo.W, _ptr(sums), st)
+                gpad, _ = self._bn_padded(bnp, C_real, Cp, dev)
+                acc = bnp + '.weight' in grads
+                dgam = torch.empty(C_real, dtype=torch.float32, device=dev)
+                dbet = torch.empty(C_real, dtype=torch.float32, device=dev)
+                call('mmlf_bn_bwd_apply', _ptr(gy), ld_gy, _ptr(rec['y']), rec['ld_y'], _ptr(rec['z']), Cp, _ptr(gpad),
+                     _ptr(rec['save_mean']), _ptr(rec['save_invstd']), _ptr(sums), geo.count, 1, C_real, Cp, geo.B,
+                     geo.H, geo.W, _ptr(dz), Cp, _ptr(dgam), _ptr(dbet), st)
+                if acc:
+                    grads[bnp + '.weight'] += dgam
+                    grads[bnp + '.bias'] += dbet
+                else:
+                    grads[bnp + '.weight'], grads[bnp + '.bias'] = dgam, dbet
+            else:
+                call('mmlf_relu_bwd', _ptr(gy), ld_gy, _ptr(rec['y']), rec['ld_y'], Cp, geo.n_slots, _ptr(dz), Cp, st)
+            conv_param_grads(c2, dz, Cp, rec['a1'], c1.n_pad)
+            da1 = self._slots(geo, c1.n_pad)
+            dgrad(c2, dz, Cp, da1, c1.n_pad, gate=rec['a1'], ld_gate=c1.n_pad)
+            conv_param_grads(c1, da1, c1.n_pad, rec['x'], rec['ld_x'])
+            if not need_gx:
+                return None
+            gx = self._slots(geo, c1.cin_pad)
+            dgrad(c1, da1, c1.n_pad, gx, c1.cin_pad)
+            return gx
+
+        for rec in reversed(tape['out']):
+            gy = block_bwd(rec, gy, ld_gy, True)
+            ld_gy = rec['c1'].cin_pad
+        # gy is now the gradient of the concatenated feature buffer [n_slots][feat_ld]
+        for si, (key, net, spatial) in enumerate(self.stream_defs):
+            g, ld_g = gy[:, si * self.cp:], ld_gy
+            recs = tape['streams'][key]
+            for j, rec in enumerate(reversed(recs)):
+                g = block_bwd(rec, g, ld_g, need_gx=(j != len(recs) - 1))
+                ld_g = rec['c1'].cin_pad
+        # bias gradients were accumulated on the padded pitch
+        for cs in self.all_convs():
+            bname = cs.name + '.bias'
+            if bname in grads and grads[bname].numel() != cs.cout:
+                grads[bname] = grads[bname][:cs.cout].contiguous()
+        return grads

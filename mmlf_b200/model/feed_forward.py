@@ -1,0 +1,204 @@
+"""Drop-in for ``mmlf.model.feed_forward`` (/root/reference/mmlf/model/feed_forward.py).
+
+Same constructor keywords, same ``state_dict`` layout (the parameter containers are the
+same ``nn.Sequential`` of ``nn.Conv2d`` / ``nn.ReLU`` / ``nn.BatchNorm2d`` modules, created in the same order so
+that a given ``torch.manual_seed`` yields the same initial weights), same output dict.  The modules are parameter
+containers only: ``forward`` runs the hand-written sm_100a kernels through :class:`mmlf_b200.engine.Engine`.
+"""
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..engine import Engine
+
+
+def laplacian(x, mu, b):
+    """feed_forward.py:9-12 (kept for API parity; the fused kernel is ``ops.upr_posterior``)."""
+    mu = mu.unsqueeze(1)
+    b = b.unsqueeze(1)
+    return 1.0 / (2.0 * b) * torch.exp(-torch.abs(x - mu) / b)
+
+
+class _NetFunction(torch.autograd.Function):
+    """Whole-network forward/backward as one autograd node: the backward pass is the hand-written chain in
+    Engine.backward, not autograd over per-layer ops."""
+
+    @staticmethod
+    def forward(ctx, engine, training, n_views, *tensors):
+        views, params = tensors[:n_views], tensors[n_views:]
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        out, tape = engine.forward(list(views), training, save=need_grad)
+        ctx.engine, ctx.tape, ctx.n_views = engine, tape, n_views
+        ctx.names = [n for n, _ in engine.m.named_parameters()]
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        if ctx.tape is None:
+            raise RuntimeError('backward through a forward pass that did not record a tape')
+        grads = ctx.engine.backward(ctx.tape, g_out.contiguous())
+        ctx.tape = None
+        return (None, None, None) + (None,) * ctx.n_views + tuple(grads.get(n) for n in ctx.names)
+
+
+class LazyOutputs(dict):
+    """Output dict whose heavy side outputs (UPR posterior, DPP one_hot/posterior: SURVEY.md H7) are computed on
+    first access.  Behaves like the reference's plain dict for every read access."""
+
+    def __init__(self, eager, lazy):
+        super().__init__(eager)
+        self._lazy = dict(lazy)
+        for k in lazy:
+            super().__setitem__(k, None)
+
+    def _resolve(self, k):
+        if k in self._lazy:
+            for kk, vv in self._lazy.pop(k)().items():
+                self._lazy.pop(kk, None)
+                super().__setitem__(kk, vv)
+
+    def __getitem__(self, k):
+        self._resolve(k)
+        return super().__getitem__(k)
+
+    def get(self, k, default=None):
+        if k not in self:
+            return default
+        return self[k]
+
+    def items(self):
+        for k in list(self._lazy):
+            self._resolve(k)
+        return super().items()
+
+    def values(self):
+        for k in list(self._lazy):
+            self._resolve(k)
+        return super().values()
+
+
+class FeedForward(nn.Module):
+    """EPINET-style multi-stream FCN (feed_forward.py:15) on B200 kernels."""
+
+    def __init__(self, model_ksize, model_in_blocks, model_out_blocks, model_chs, model_views, model_cross,
+                 model_uncert, model_unet, model_discrete, model_no_batchnorm, model_batchnorm_momentum,
+                 val_disp_min, val_disp_max, **kwargs):
+        super(FeedForward, self).__init__()
+        if model_ksize != 2:
+            raise NotImplementedError('mmlf_b200 implements the published model_ksize=2 topology only '
+                                      '(SURVEY.md section 8f.4 lists odd kernel sizes as a later row)')
+        if model_unet:
+            raise NotImplementedError('--model_unet is out of scope of the B200 hot path (SURVEY.md section 2, row 9)')
+        self.ksize = model_ksize
+        self.chs = model_chs
+        self.views = model_views
+        self.cross = model_cross
+        self.uncert = model_uncert
+        self.discrete = model_discrete
+        self.no_batchnorm = model_no_batchnorm
+        self.batchnorm_momentum = model_batchnorm_momentum
+        self.bn_eps = 1e-5
+        self.disp_min = val_disp_min
+        self.disp_max = val_disp_max
+        self.steps = 4
+        if model_cross:
+            self.steps = 2
+        self.steps *= model_views * 3                                   # feed_forward.py:81-84
+        self.padding1 = model_ksize // 2                                 # feed_forward.py:86-92
+        self.padding2 = model_ksize // 2 - 1
+        self.n_in_blocks = model_in_blocks
+        self.n_out_blocks = model_out_blocks
+
+        self.in_net_hv = self.init_in_net(model_in_blocks)
+        if not model_cross:
+            self.in_net_id = self.init_in_net(model_in_blocks)
+        self.out_net = self.init_out_net(model_out_blocks)
+        self._engine = None
+        self._bins = {}
+
+    # -- parameter containers, same construction order as the reference (feed_forward.py:104-187)
+    def block(self, ch_in, ch_out=None, out_bn_relu=True):
+        if ch_out is None:
+            ch_out = ch_in
+        layers = [nn.Conv2d(ch_in, ch_out, self.ksize, padding=self.padding1), nn.ReLU(),
+                  nn.Conv2d(ch_out, ch_out, self.ksize, padding=self.padding2)]
+        if out_bn_relu:
+            if not self.no_batchnorm:
+                layers.append(nn.BatchNorm2d(ch_out, momentum=self.batchnorm_momentum))
+            layers.append(nn.ReLU())
+        return nn.Sequential(*layers)
+
+    def init_in_net(self, n_blocks):
+        assert n_blocks >= 1
+        blocks = [self.block(self.views * 3, self.chs)]
+        for _ in range(n_blocks - 1):
+            blocks.append(self.block(self.chs))
+        return nn.Sequential(*blocks)
+
+    def init_out_net(self, n_blocks):
+        assert n_blocks >= 1
+        chs = 4 * self.chs
+        if self.cross:
+            chs = 2 * self.chs
+        blocks = []
+        for _ in range(n_blocks - 1):
+            blocks.append(self.block(chs))
+        out_chs = 1
+        if self.uncert:
+            out_chs = 2
+        elif self.discrete:
+            out_chs = self.steps
+        self.out_chs = out_chs
+        blocks.append(self.block(chs, out_chs, False))
+        return nn.Sequential(*blocks)
+
+    # -- execution
+    @property
+    def engine(self):
+        if self._engine is None:
+            self._engine = Engine(self)
+        return self._engine
+
+    def _bin_tables(self, device):
+        key = str(device)
+        if key not in self._bins:
+            self._bins[key] = (ops.torch_bins(self.disp_min, self.disp_max, self.steps, device),
+                               ops.numpy_bins(self.disp_min, self.disp_max, self.steps, device))
+        return self._bins[key]
+
+    def raw_forward(self, views, shift_disp=None):
+        """(B, OC, H, W) network output without heads and without autograd (ESE inner loop)."""
+        out, _ = self.engine.forward(views, self.training, save=False, shift_disp=shift_disp)
+        return out
+
+    def forward(self, h_views, v_views, i_views=None, d_views=None):
+        """Same contract as feed_forward.py:206-305: stacks (b, n, 3, h, w) -> dict mean/logvar/scores/one_hot/posterior."""
+        views = [h_views, v_views] if self.cross else [h_views, v_views, i_views, d_views]
+        if not self.cross and (i_views is None or d_views is None):
+            raise TypeError('the 4-stream model needs i_views and d_views (feed_forward.py:230-231)')
+        params = [p for _, p in self.named_parameters()]
+        output = _NetFunction.apply(self.engine, self.training, len(views), *views, *params)
+        mean = output[:, 0]
+        eager = {'mean': mean, 'logvar': None, 'scores': None, 'one_hot': None, 'posterior': None}
+        lazy = {}
+        bins_t, bins_n = self._bin_tables(output.device)
+        if self.discrete:
+            # feed_forward.py:276-290.  mean/logvar/one_hot/posterior carry no gradient here; the reference only
+            # trains DPP through `scores` (loss.py:145-160).
+            scores = output
+            det = scores.detach()
+
+            def head():
+                one_hot, post, m, lv = ops.dpp_head(det, bins_t, bins_n)
+                return {'one_hot': one_hot, 'posterior': post, 'mean': m, 'logvar': lv}
+            eager = {'scores': scores}
+            lazy = {'mean': head, 'logvar': head, 'one_hot': head, 'posterior': head}
+        if self.uncert:
+            logvar = output[:, 1]                                        # feed_forward.py:293
+            eager['logvar'] = logvar
+
+            def post():
+                return {'posterior': ops.upr_posterior(mean.detach(), logvar.detach(), bins_n)}
+            lazy = {'posterior': post}
+        out = LazyOutputs(eager, lazy)
+        return out

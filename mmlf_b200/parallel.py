@@ -1,0 +1,78 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), NCCL over NVLink for the only real exchange steps of the
+path -- the gradient all-reduce, the loss normalisers and the ESE member gather.  Replaces the
+single-process ``torch.nn.DataParallel`` of /root/reference/mmlf/train/cli.py:159."""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed from torchrun's environment; returns (rank, world, local_rank)."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+        if backend == 'nccl':
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend)
+    return rank, world, local
+
+
+def shard_info():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def all_reduce_sum_(t):
+    """In-place SUM all-reduce when running multi-rank; no-op otherwise."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def shard_batch(tensors, rank, world):
+    """Contiguous dim-0 shard of each tensor (DataParallel scatter, train/cli.py:245)."""
+    out = []
+    for t in tensors:
+        n = t.shape[0]
+        per = (n + world - 1) // world
+        out.append(t[rank * per:min(n, (rank + 1) * per)])
+    return out
+
+
+def gather_members(means, logvars, K, rank, world):
+    """ESE: every rank computed members rank, rank+world, ...; exchange them so each rank holds all K."""
+    for k in range(K):
+        src = k % world
+        dist.broadcast(means[k], src)
+        dist.broadcast(logvars[k], src)
+
+
+class GradBucket:
+    """All parameter gradients of a module in one flat fp32 buffer -> a single all-reduce per step
+    (18.4 MB for the 4-stream model) instead of DataParallel's replicate/scatter/gather/reduce."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero_(self):
+        self.flat.zero_()
+        off = 0
+        for p in self.params:          # re-attach in case an optimizer set .grad to None
+            if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + off * 4:
+                p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def all_reduce(self):
+        all_reduce_sum_(self.flat)

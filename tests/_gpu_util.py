@@ -1,0 +1,97 @@
+"""Helpers for the -m gpu parity tests: build slot-layout tensors with plain torch indexing (independently of the
+pack kernels) and call the C-ABI through mmlf_b200._lib."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from mmlf_b200 import _lib
+from mmlf_b200._lib import ConvArgs, call
+from oracle.net import bf16_round
+
+DEV = 'cuda'
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def pad16(x):
+    return (x + 15) // 16 * 16
+
+
+def to_slots(x_nhwc, ld, full_grid, Hp, Wp):
+    """numpy (B, h, w, C) -> torch bf16 [B*Hp*Wp, ld] on the device.  full_grid: the tensor covers the whole
+    (H+1)x(W+1) slot grid; otherwise it is H x W and lives at slots (y+1, x+1) with a zero halo."""
+    B, h, w, Cc = x_nhwc.shape
+    s = torch.zeros((B, Hp, Wp, ld), dtype=torch.float32)
+    t = torch.from_numpy(np.ascontiguousarray(x_nhwc))
+    if full_grid:
+        s[:, :, :, :Cc] = t
+    else:
+        s[:, 1:, 1:, :Cc] = t
+    return s.reshape(B * Hp * Wp, ld).to(torch.bfloat16).to(DEV)
+
+
+def from_slots(t, B, Hp, Wp, Cc, full_grid):
+    a = t.float().cpu().numpy().reshape(B, Hp, Wp, -1)
+    return a[..., :Cc] if full_grid else a[:, 1:, 1:, :Cc]
+
+
+def pack_weight(w, spatial=0, dgrad=0, groups=1, group_real=None, group_pad=None, n_pad=None, cin_pad=None):
+    cout, cin = w.shape[:2]
+    group_real = group_real or cin
+    group_pad = group_pad or pad16(cin)
+    if not dgrad:
+        n_pad = n_pad or pad16(cout)
+        cin_pad = cin_pad or (groups * group_pad if groups > 1 else pad16(cin))
+    kc = (cin_pad + 63) // 64
+    wd = torch.from_numpy(np.ascontiguousarray(w)).to(DEV)
+    out = torch.empty((n_pad, 4 * kc * 64), dtype=torch.bfloat16, device=DEV)
+    call('mmlf_pack_conv_weight', ptr(wd), cout, cin, spatial, dgrad, groups, group_real, group_pad, ptr(out), n_pad,
+         cin_pad, stream())
+    return out
+
+
+def run_conv(x_slots, ld_in, cin_pad, wpack, n_pad, B, H, W, ctype, *, bias=None, scale=None, shift=None, relu=False,
+             gate=None, ld_gate=0, out_mode=0, n_real=0, simt=False, ld_out=None):
+    n_slots = B * (H + 1) * (W + 1)
+    ld_out = ld_out or n_pad
+    if out_mode == 0:
+        out = torch.full((n_slots, ld_out), float('nan'), dtype=torch.bfloat16, device=DEV)
+    elif out_mode == 1:
+        out = torch.full((n_slots, ld_out), float('nan'), dtype=torch.float32, device=DEV)
+    else:
+        Ho, Wo = (H, W) if ctype else (H + 1, W + 1)
+        out = torch.full((B, n_real, Ho, Wo), float('nan'), dtype=torch.float32, device=DEV)
+    a = ConvArgs()
+    a.in_, a.ld_in, a.cin_pad = x_slots.data_ptr(), ld_in, cin_pad
+    a.wpack, a.n_pad = wpack.data_ptr(), n_pad
+    a.B, a.H, a.W, a.type = B, H, W, ctype
+    a.bias = bias.data_ptr() if bias is not None else None
+    a.scale = scale.data_ptr() if scale is not None else None
+    a.shift = shift.data_ptr() if shift is not None else None
+    a.relu = int(relu)
+    a.gate = gate.data_ptr() if gate is not None else None
+    a.ld_gate = ld_gate
+    a.out, a.ld_out, a.out_mode, a.n_real = out.data_ptr(), ld_out, out_mode, n_real
+    call('mmlf_conv2x2_simt' if simt else 'mmlf_conv2x2', C.byref(a), stream())
+    torch.cuda.synchronize()
+    return out
+
+
+def dev_f32(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(DEV)
+
+
+def assert_close_bf16(got, want, what, ulps=1.0, atol=1e-6):
+    """|got - want| within `ulps` bf16 units-in-the-last-place of `want` (got is a bf16-rounded result)."""
+    want = np.asarray(want, np.float32)
+    got = np.asarray(got, np.float32)
+    tol = ulps * np.abs(want) * 2.0 ** -7 + atol
+    bad = np.abs(got - want) > tol
+    assert not bad.any(), f'{what}: {bad.sum()} / {bad.size} outside {ulps} bf16 ulp; worst |d|={np.abs(got - want).max():.4g}'

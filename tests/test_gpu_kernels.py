@@ -1,0 +1,417 @@
+"""Kernel-level parity tests (-m gpu): every C-ABI entry point against the numpy oracle on seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import losses as olosses
+from oracle.net import bf16_round, conv2x2, conv2x2_bwd, np_linspace_f32, torch_linspace_f32
+
+pytestmark = pytest.mark.gpu
+
+
+def _u():
+    import _gpu_util
+    return _gpu_util
+
+
+# ------------------------------------------------------------------------------------------------ light field
+def test_lf_extract_bit_exact():
+    from mmlf_b200.data import hci4d
+    rng = np.random.RandomState(0)
+    views = rng.randint(0, 256, (81, 24, 32, 3), dtype=np.uint8)
+    got = hci4d.extract_stacks(torch.from_numpy(views).cuda())
+    want = oracle.extract_stacks(views)
+    for g, w in zip(got, want):
+        assert np.array_equal(g.cpu().numpy(), w)
+
+
+@pytest.mark.parametrize('shape', [(1, 9, 16, 16), (2, 9, 12, 20), (1, 9, 33, 18)])
+def test_lf_shift_bit_exact(shape, golden):
+    from mmlf_b200 import ops
+    B, n, H, W = shape
+    rng = np.random.RandomState(1)
+    stacks = [rng.uniform(0, 1, (B, n, 3, H, W)).astype(np.float32) for _ in range(4)]
+    if H != W:   # the diagonal stacks assume square images in the reference; h / v are still checked
+        pass
+    g = golden('shift.npz')
+    for disp in list(g['disps']) + [0.37, -2.75]:
+        want = oracle.shift(tuple(stacks), float(disp))
+        got = ops.lf_shift(*[torch.from_numpy(s).cuda() for s in stacks], float(disp))
+        for k in range(4):
+            assert np.array_equal(got[k].cpu().numpy(), want[k]), (disp, k)
+
+
+def test_lf_shift_golden(golden):
+    """Directly against the reference's own Shift outputs, through the drop-in transform (in-place semantics)."""
+    from mmlf_b200.data.hci4d import Shift
+    g = golden('shift.npz')
+    for j, disp in enumerate(g['disps']):
+        data = [torch.from_numpy(g[f'in{k}'].copy()).cuda() for k in range(4)]
+        data += [torch.zeros(1), torch.from_numpy(g['gt'].copy()).cuda(), torch.from_numpy(g['mpi'].copy()).cuda()]
+        res = Shift(float(disp))(tuple(data))
+        for k in range(4):
+            assert np.array_equal(res[k].cpu().numpy(), g[f'out{j}_{k}']), (disp, k)
+            assert res[k] is data[k]
+        assert np.array_equal(res[5].cpu().numpy(), g[f'gt{j}'])
+        assert np.array_equal(res[6].cpu().numpy(), g[f'mpi{j}'])
+
+
+def test_pack_views_and_shift_pack():
+    u = _u()
+    B, n, H, W = 2, 9, 10, 14
+    rng = np.random.RandomState(2)
+    v = rng.uniform(0, 1, (B, n, 3, H, W)).astype(np.float32)
+    out = torch.full((B * (H + 1) * (W + 1), 32), float('nan'), dtype=torch.bfloat16, device='cuda')
+    u.call('mmlf_pack_views', u.ptr(torch.from_numpy(v).cuda()), B, n * 3, H, W, u.ptr(out), 32, u.stream())
+    got = out.float().cpu().numpy().reshape(B, H + 1, W + 1, 32)
+    want = np.zeros_like(got)
+    want[:, 1:, 1:, :27] = bf16_round(v.reshape(B, 27, H, W).transpose(0, 2, 3, 1))
+    assert np.array_equal(got, want)
+    # fused shift + pack == pack(shift(.)) for every stack
+    stacks = [rng.uniform(0, 1, (B, n, 3, 12, 12)).astype(np.float32) for _ in range(4)]
+    for disp in (2.5, -1.3, 0.0, 7.25):
+        sh = oracle.shift(tuple(stacks), disp)
+        for k in range(4):
+            o = torch.full((B * 13 * 13, 32), float('nan'), dtype=torch.bfloat16, device='cuda')
+            u.call('mmlf_shift_pack', u.ptr(torch.from_numpy(stacks[k]).cuda()), k, B, n, 12, 12, float(disp),
+                   u.ptr(o), 32, u.stream())
+            got = o.float().cpu().numpy().reshape(B, 13, 13, 32)
+            want = np.zeros_like(got)
+            want[:, 1:, 1:, :27] = bf16_round(sh[k].reshape(B, 27, 12, 12).transpose(0, 2, 3, 1))
+            assert np.array_equal(got, want), (disp, k)
+
+
+# ------------------------------------------------------------------------------------------------ convolution
+def _conv_case(B, H, W, cin, cout, ctype, seed, simt, relu=True, mode=0, with_bn=False, groups=1, group_real=None,
+               group_pad=None):
+    u = _u()
+    rng = np.random.RandomState(seed)
+    Hp, Wp = H + 1, W + 1
+    cin_pad = groups * group_pad if groups > 1 else u.pad16(cin)
+    n_pad = u.pad16(cout)
+    w = (rng.normal(0, 1, (cout, cin, 2, 2)) / np.sqrt(4 * cin)).astype(np.float32)
+    b = rng.normal(0, 0.1, cout).astype(np.float32)
+    if ctype == 0:
+        x = rng.normal(0, 1, (B, H, W, cin)).astype(np.float32)
+    else:
+        x = rng.normal(0, 1, (B, Hp, Wp, cin)).astype(np.float32)
+    xq, wq = bf16_round(x), bf16_round(w)
+    want = conv2x2(xq, wq, b, 1 if ctype == 0 else 0)
+    scale = shift = None
+    if with_bn:
+        scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+        shift = rng.normal(0, 0.2, cout).astype(np.float32)
+        want = want * scale + shift
+    if relu:
+        want = np.maximum(want, 0)
+    # channel layout on the device (groups of group_real real channels at pitch group_pad)
+    if groups > 1:
+        xl = np.zeros(x.shape[:3] + (cin_pad,), np.float32)
+        for g in range(groups):
+            xl[..., g * group_pad:g * group_pad + group_real] = xq[..., g * group_real:(g + 1) * group_real]
+    else:
+        xl = xq
+    xs = u.to_slots(xl, cin_pad, ctype == 1, Hp, Wp)
+    wp = u.pack_weight(w, groups=groups, group_real=group_real, group_pad=group_pad)
+    bias = torch.zeros(n_pad, device='cuda')
+    bias[:cout] = torch.from_numpy(b)
+    kw = dict(bias=bias, relu=relu, simt=simt, out_mode=mode)
+    if with_bn:
+        sc = torch.zeros(n_pad, device='cuda')
+        sh = torch.zeros(n_pad, device='cuda')
+        sc[:cout] = torch.from_numpy(scale)
+        sh[:cout] = torch.from_numpy(shift)
+        kw.update(scale=sc, shift=sh)
+    if mode == 2:
+        kw['n_real'] = cout
+    out = u.run_conv(xs, cin_pad, cin_pad, wp, n_pad, B, H, W, ctype, **kw)
+    if mode == 2:
+        got = out.cpu().numpy().transpose(0, 2, 3, 1)
+        np.testing.assert_allclose(got, want, rtol=2e-4, atol=2e-4)
+        return
+    full = out.float().cpu().numpy().reshape(B, Hp, Wp, -1)
+    assert np.isfinite(full).all(), 'kernel left unwritten (NaN) output slots'
+    got = full[..., :cout] if ctype == 0 else full[:, 1:, 1:, :cout]
+    if ctype == 1:
+        assert not full[:, 0].any() and not full[:, :, 0].any(), 'halo slots must be zero'
+    assert not full[..., cout:].any() or not relu, 'padding channels must stay zero'
+    if mode == 0:
+        u.assert_close_bf16(got, want, f'conv type {ctype} {cin}->{cout}', ulps=1.01, atol=2e-3)
+    else:
+        np.testing.assert_allclose(got, want, rtol=2e-4, atol=2e-4)
+
+
+CONV_CASES = [
+    # B, H, W, cin, cout, type
+    (2, 12, 12, 27, 70, 0), (2, 12, 12, 70, 70, 1), (1, 20, 24, 280, 280, 0), (1, 20, 24, 280, 280, 1),
+    (1, 16, 16, 280, 2, 0), (1, 16, 16, 280, 108, 0), (1, 16, 16, 108, 108, 1), (2, 9, 11, 140, 140, 0),
+]
+
+
+@pytest.mark.parametrize('case', CONV_CASES)
+def test_conv_simt_vs_oracle(case):
+    _conv_case(*case, seed=3, simt=True)
+
+
+@pytest.mark.parametrize('case', CONV_CASES)
+def test_conv_tc_vs_oracle(case):
+    _conv_case(*case, seed=3, simt=False)
+
+
+def test_conv_tc_epilogues():
+    _conv_case(1, 16, 16, 280, 280, 1, seed=4, simt=False, with_bn=True)
+    _conv_case(1, 16, 16, 280, 280, 1, seed=5, simt=False, relu=False)
+    _conv_case(1, 16, 16, 280, 16, 0, seed=6, simt=False, mode=1)
+    _conv_case(1, 16, 16, 108, 108, 1, seed=7, simt=False, relu=False, mode=2)
+    _conv_case(1, 16, 16, 280, 280, 0, seed=8, simt=False, groups=4, group_real=70, group_pad=80)
+
+
+def test_conv_tc_many_tiles():
+    """More tiles than SMs and more k-chunks than pipeline stages: exercises barrier phase wrap-around."""
+    _conv_case(4, 80, 80, 280, 280, 0, seed=9, simt=False)
+    _conv_case(4, 80, 80, 280, 280, 1, seed=10, simt=False)
+
+
+def test_conv_dgrad_and_gate():
+    """Data gradient = the other conv type with dgrad-packed weights; ReLU gate fused in the epilogue."""
+    u = _u()
+    rng = np.random.RandomState(11)
+    B, H, W, cin, cout = 2, 10, 12, 70, 70
+    Hp, Wp = H + 1, W + 1
+    w = (rng.normal(0, 1, (cout, cin, 2, 2)) / np.sqrt(4 * cin)).astype(np.float32)
+    wq = bf16_round(w)
+    for ctype in (0, 1):
+        if ctype == 0:
+            x = rng.normal(0, 1, (B, H, W, cin)).astype(np.float32)
+            gout = bf16_round(rng.normal(0, 1, (B, Hp, Wp, cout)).astype(np.float32))
+        else:
+            x = rng.normal(0, 1, (B, Hp, Wp, cin)).astype(np.float32)
+            gout = bf16_round(rng.normal(0, 1, (B, H, W, cout)).astype(np.float32))
+        gx, _, _ = conv2x2_bwd(bf16_round(x), wq, gout, 1 if ctype == 0 else 0)
+        gate = (rng.uniform(size=gx.shape) > 0.4).astype(np.float32)
+        want = gx * gate
+        wd = u.pack_weight(w, dgrad=1, n_pad=u.pad16(cin), cin_pad=u.pad16(cout))
+        gs = u.to_slots(gout, u.pad16(cout), ctype == 0, Hp, Wp)
+        gate_s = u.to_slots(gate, u.pad16(cin), ctype == 1, Hp, Wp)
+        out = u.run_conv(gs, u.pad16(cout), u.pad16(cout), wd, u.pad16(cin), B, H, W, 1 - ctype, gate=gate_s,
+                         ld_gate=u.pad16(cin))
+        got = u.from_slots(out, B, Hp, Wp, cin, ctype == 1)
+        u.assert_close_bf16(got, want, f'dgrad of type {ctype}', ulps=1.01, atol=2e-3)
+
+
+@pytest.mark.parametrize('case', [(2, 12, 12, 27, 70, 0), (2, 12, 12, 70, 70, 1), (2, 20, 20, 280, 280, 0),
+                                  (2, 20, 20, 280, 280, 1), (1, 16, 16, 280, 2, 0), (1, 16, 16, 108, 108, 1),
+                                  (6, 40, 40, 280, 280, 1)])
+def test_conv_wgrad(case):
+    u = _u()
+    B, H, W, cin, cout, ctype = case
+    rng = np.random.RandomState(12)
+    Hp, Wp = H + 1, W + 1
+    cin_pad, n_pad = u.pad16(cin), u.pad16(cout)
+    if ctype == 0:
+        x = bf16_round(rng.normal(0, 1, (B, H, W, cin)).astype(np.float32))
+        gout = bf16_round(rng.normal(0, 1, (B, Hp, Wp, cout)).astype(np.float32))
+    else:
+        x = bf16_round(rng.normal(0, 1, (B, Hp, Wp, cin)).astype(np.float32))
+        gout = bf16_round(rng.normal(0, 1, (B, H, W, cout)).astype(np.float32))
+    w = np.zeros((cout, cin, 2, 2), np.float32)
+    _, gw, gb = conv2x2_bwd(x, w, gout, 1 if ctype == 0 else 0)
+    xs = u.to_slots(x, cin_pad, ctype == 1, Hp, Wp)
+    gs = u.to_slots(gout, n_pad, ctype == 0, Hp, Wp)
+    ws_bytes = u._lib.lib().mmlf_conv2x2_wgrad_workspace(n_pad, cin_pad)
+    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device='cuda')
+    dwp = torch.full((n_pad, 4, cin_pad), float('nan'), dtype=torch.float32, device='cuda')
+    u.call('mmlf_conv2x2_wgrad', u.ptr(gs), n_pad, n_pad, u.ptr(xs), cin_pad, cin_pad, B, H, W, ctype, u.ptr(ws),
+           u.ptr(dwp), u.stream())
+    dw = torch.empty((cout, cin, 2, 2), dtype=torch.float32, device='cuda')
+    u.call('mmlf_unpack_conv_wgrad', u.ptr(dwp), n_pad, cin_pad, cout, cin, 0, 1, cin, cin_pad, u.ptr(dw), 0, u.stream())
+    torch.cuda.synchronize()
+    scale = np.abs(gw).max()
+    assert np.abs(dw.cpu().numpy() - gw).max() <= 2e-4 * scale + 1e-4
+    db = torch.zeros(n_pad, device='cuda')
+    u.call('mmlf_colsum_bf16', u.ptr(gs), n_pad, n_pad, B * Hp * Wp, u.ptr(db), 0, u.stream())
+    np.testing.assert_allclose(db.cpu().numpy()[:cout], gb, rtol=1e-4, atol=1e-3)
+
+
+def test_weight_pack_variants():
+    """The three spatial variants against the reference's permute/flip plumbing (feed_forward.py:236-256)."""
+    u = _u()
+    rng = np.random.RandomState(13)
+    B, H, W, cin, cout = 1, 8, 8, 27, 16
+    w = rng.normal(0, 0.3, (cout, cin, 2, 2)).astype(np.float32)
+    b = np.zeros(cout, np.float32)
+    x = bf16_round(rng.normal(0, 1, (B, H, W, cin)).astype(np.float32))
+    wq = bf16_round(w)
+    for spatial in (0, 1, 2):
+        if spatial == 0:
+            want = conv2x2(x, wq, b, 1)
+        elif spatial == 1:          # permute(0,1,3,2) -> net -> permute back
+            want = conv2x2(x.transpose(0, 2, 1, 3), wq, b, 1).transpose(0, 2, 1, 3)
+        else:                       # permute, flip(-1) -> net -> flip(-1), permute
+            xi = np.ascontiguousarray(x.transpose(0, 2, 1, 3)[:, :, ::-1])
+            want = conv2x2(xi, wq, b, 1)[:, :, ::-1].transpose(0, 2, 1, 3)
+        wp = u.pack_weight(w, spatial=spatial)
+        xs = u.to_slots(x, 32, False, H + 1, W + 1)
+        out = u.run_conv(xs, 32, 32, wp, 16, B, H, W, 0, simt=True, out_mode=1)
+        got = out.cpu().numpy().reshape(B, H + 1, W + 1, 16)
+        np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4, err_msg=f'spatial {spatial}')
+
+
+# ------------------------------------------------------------------------------------------------ batch norm
+def test_bn_train_roundtrip():
+    u = _u()
+    rng = np.random.RandomState(14)
+    B, H, W, Cr = 2, 9, 13, 70
+    Cp = u.pad16(Cr)
+    Hp, Wp = H + 1, W + 1
+    z = bf16_round(rng.normal(0.3, 1.7, (B, H, W, Cr)).astype(np.float32))
+    zs = u.to_slots(z, Cp, False, Hp, Wp)
+    sums = torch.zeros(2 * Cp, dtype=torch.float64, device='cuda')
+    u.call('mmlf_bn_stats', u.ptr(zs), Cp, Cp, B, H, W, u.ptr(sums), u.stream())
+    gamma = rng.uniform(0.5, 1.5, Cr).astype(np.float32)
+    beta = rng.normal(0, 0.2, Cr).astype(np.float32)
+    rm0 = rng.normal(0, 0.1, Cr).astype(np.float32)
+    rv0 = rng.uniform(0.5, 1.5, Cr).astype(np.float32)
+    d = {k: u.dev_f32(v) for k, v in dict(gamma=gamma, beta=beta, rm=rm0, rv=rv0).items()}
+    nbt = torch.zeros((), dtype=torch.int64, device='cuda')
+    scale, shift, smean, sinv = [torch.empty(Cp, device='cuda') for _ in range(4)]
+    n = B * H * W
+    u.call('mmlf_bn_finalize', u.ptr(sums), Cr, Cp, n, u.ptr(d['gamma']), u.ptr(d['beta']), u.ptr(d['rm']),
+           u.ptr(d['rv']), u.ptr(nbt), 0.1, 1e-5, u.ptr(scale), u.ptr(shift), u.ptr(smean), u.ptr(sinv), u.stream())
+    y = torch.full((B * Hp * Wp, Cp), float('nan'), dtype=torch.bfloat16, device='cuda')
+    u.call('mmlf_bn_apply_relu', u.ptr(zs), Cp, u.ptr(scale), u.ptr(shift), Cp, B, H, W, u.ptr(y), Cp, u.stream())
+    torch.cuda.synchronize()
+    z2 = z.reshape(-1, Cr).astype(np.float64)
+    mean, var = z2.mean(0), z2.var(0)
+    np.testing.assert_allclose(smean.cpu().numpy()[:Cr], mean, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(sinv.cpu().numpy()[:Cr], 1 / np.sqrt(var + 1e-5), rtol=1e-5)
+    np.testing.assert_allclose(d['rm'].cpu().numpy(), 0.9 * rm0 + 0.1 * mean, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(d['rv'].cpu().numpy(), 0.9 * rv0 + 0.1 * var * n / (n - 1), rtol=1e-5)
+    assert int(nbt.item()) == 1
+    want = np.maximum((z - mean) / np.sqrt(var + 1e-5) * gamma + beta, 0).astype(np.float32)
+    full = y.float().cpu().numpy().reshape(B, Hp, Wp, Cp)
+    assert not full[:, 0].any() and not full[:, :, 0].any() and not full[..., Cr:].any()
+    u.assert_close_bf16(full[:, 1:, 1:, :Cr], want, 'bn_apply_relu', ulps=1.01, atol=2e-3)
+    # backward
+    gy = bf16_round(rng.normal(0, 1, (B, H, W, Cr)).astype(np.float32))
+    gys = u.to_slots(gy, Cp, False, Hp, Wp)
+    bs = torch.zeros(2 * Cp, dtype=torch.float64, device='cuda')
+    u.call('mmlf_bn_bwd_reduce', u.ptr(gys), Cp, u.ptr(y), Cp, u.ptr(zs), Cp, u.ptr(smean), u.ptr(sinv), Cp, B, H, W,
+           u.ptr(bs), u.stream())
+    gpad = torch.zeros(Cp, device='cuda')
+    gpad[:Cr] = d['gamma']
+    dz = torch.full((B * Hp * Wp, Cp), float('nan'), dtype=torch.bfloat16, device='cuda')
+    dgam, dbet = torch.empty(Cr, device='cuda'), torch.empty(Cr, device='cuda')
+    u.call('mmlf_bn_bwd_apply', u.ptr(gys), Cp, u.ptr(y), Cp, u.ptr(zs), Cp, u.ptr(gpad), u.ptr(smean), u.ptr(sinv),
+           u.ptr(bs), n, 1, Cr, Cp, B, H, W, u.ptr(dz), Cp, u.ptr(dgam), u.ptr(dbet), u.stream())
+    torch.cuda.synchronize()
+    yq = full[:, 1:, 1:, :Cr]
+    g = gy * (yq > 0)
+    invstd = (1 / np.sqrt(var + 1e-5)).astype(np.float32)
+    xhat = ((z - mean) * invstd).astype(np.float32)
+    g2, x2 = g.reshape(-1, Cr), xhat.reshape(-1, Cr)
+    want_dz = gamma * invstd * (g - g2.mean(0) - xhat * (g2 * x2).mean(0))
+    np.testing.assert_allclose(dbet.cpu().numpy(), g2.sum(0), rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(dgam.cpu().numpy(), (g2 * x2).sum(0), rtol=1e-4, atol=1e-3)
+    dzf = dz.float().cpu().numpy().reshape(B, Hp, Wp, Cp)
+    assert not dzf[:, 0].any() and not dzf[:, :, 0].any()
+    u.assert_close_bf16(dzf[:, 1:, 1:, :Cr], want_dz, 'bn_bwd_apply', ulps=1.01, atol=2e-3)
+
+
+# ------------------------------------------------------------------------------------------------ heads / targets / ESE
+def test_heads_against_golden(golden):
+    from mmlf_b200 import ops
+    g = golden('net_tiny_upr_full.npz')
+    mean, logvar = torch.from_numpy(g['eval/mean']).cuda(), torch.from_numpy(g['eval/logvar']).cuda()
+    bins = ops.numpy_bins(-3.5, 3.5, 108, 'cuda')
+    post = ops.upr_posterior(mean, logvar, bins).cpu().numpy()
+    np.testing.assert_allclose(post, g['eval/posterior'], rtol=2e-5, atol=1e-30)
+    g = golden('net_tiny_dpp_full.npz')
+    s = torch.from_numpy(g['eval/scores']).cuda()
+    one_hot, post, m, lv = ops.dpp_head(s, ops.torch_bins(-3.5, 3.5, 108, 'cuda'), bins)
+    assert np.array_equal(one_hot.cpu().numpy(), g['eval/one_hot'])
+    assert np.array_equal(m.cpu().numpy(), g['eval/mean'])
+    np.testing.assert_allclose(post.cpu().numpy(), g['eval/posterior'], rtol=2e-5, atol=1e-12)
+    np.testing.assert_allclose(lv.cpu().numpy(), g['eval/logvar'], rtol=1e-4, atol=1e-5)
+
+
+def test_targets_against_golden(golden):
+    from mmlf_b200.utils import dl
+    g = golden('bins.npz')
+    gt, mpi = torch.from_numpy(g['gt']).cuda(), torch.from_numpy(g['mpi']).cuda()
+    for n in (54, 108):
+        assert np.array_equal(dl.reg_to_class(gt, -3.5, 3.5, n).cpu().numpy(), g[f'reg_to_class{n}'])
+        np.testing.assert_allclose(dl.mpi_to_weights(mpi, -3.5, 3.5, n).cpu().numpy(), g[f'mpi_to_weights{n}'],
+                                   rtol=1e-6, atol=1e-7)
+        oh = torch.from_numpy(g[f'onehot{n}']).cuda()
+        assert np.array_equal(dl.class_to_reg(oh, -3.5, 3.5, n).cpu().numpy(), g[f'class_to_reg{n}'])
+
+
+def test_ese_reduce_against_golden(golden):
+    from mmlf_b200 import ops
+    g = golden('ese_tiny.npz')
+    for tag in ('coarse', 'full'):
+        means, logvars = torch.from_numpy(g[f'{tag}/means']).cuda(), torch.from_numpy(g[f'{tag}/logvars']).cuda()
+        disp = ops.numpy_bins(-3.5, 3.5, means.shape[0], 'cuda')
+        mean, logvar, post = ops.ese_reduce(means, logvars, disp)
+        assert np.array_equal(mean.cpu().numpy(), g[f'{tag}/mean'])
+        assert np.array_equal(logvar.cpu().numpy(), g[f'{tag}/logvar'])
+        np.testing.assert_allclose(post.cpu().numpy(), g[f'{tag}/posterior'], rtol=3e-5, atol=1e-9)
+
+
+# ------------------------------------------------------------------------------------------------ losses / Adam
+def test_losses_against_golden(golden):
+    from mmlf_b200.model import loss as L
+    from mmlf_b200.utils import dl
+    g = golden('losses.npz')
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    mask, gt, mpi = T(g['mask']), T(g['gt']), T(g['mpi'])
+
+    def run(name, fn, target, *extra, keys=('mean',), m=mask):
+        o = {'mean': T(g['mean']).requires_grad_(), 'logvar': T(g['logvar']).requires_grad_(),
+             'scores': T(g['scores']).requires_grad_()}
+        val = fn(o, target, m, *extra)
+        np.testing.assert_allclose(val.item(), float(g[name + '/value']), rtol=1e-5, err_msg=name)
+        if keys:
+            val.backward()
+        for k in keys:
+            ref = g[f'{name}/g_{k}']
+            np.testing.assert_allclose(o[k].grad.cpu().numpy(), ref, rtol=2e-4, atol=1e-6 * np.abs(ref).max() + 1e-12,
+                                       err_msg=name + k)
+
+    run('l1', L.MaskedL1Loss(), gt)
+    run('l1_empty', L.MaskedL1Loss(), gt, m=torch.zeros_like(mask))
+    run('multi_l1', L.MultiMaskedL1Loss(), mpi)
+    run('mse', L.MaskedMSELoss(), gt, keys=())
+    run('badpix', L.MaskedBadPix(), gt, keys=())
+    run('upr', L.ImprovedUncertaintyL1Loss(), gt, keys=('mean', 'logvar'))
+    run('upr_pad', L.ImprovedUncertaintyL1Loss(), gt, T(g['mask_padding']), keys=('mean', 'logvar'))
+    run('multi_upr', L.ImprovedMultiUncertaintyL1Loss(), mpi, keys=('mean', 'logvar'))
+    run('ce', L.MaskedCrossEntropy(), dl.reg_to_class(gt, -3.5, 3.5, 108), keys=('scores',))
+    run('ce_mm', L.MaskedCrossEntropy(), dl.mpi_to_weights(mpi, -3.5, 3.5, 108), keys=('scores',))
+
+
+def test_ce_on_the_fly_target(golden):
+    from mmlf_b200 import ops
+    g = golden('losses.npz')
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    mask = T(g['mask'])
+    sums = ops.loss_prepass(mask)
+    ls, gs = ops.loss_cross_entropy(T(g['scores']), None, T(g['gt']), ops.torch_bins(-3.5, 3.5, 108, 'cuda'),
+                                    7.0 / 108 / 2.0, mask, sums)
+    np.testing.assert_allclose(ls.item() / sums[0].item(), float(g['ce/value']), rtol=1e-5)
+    np.testing.assert_allclose(gs.cpu().numpy(), g['ce/g_scores'], rtol=2e-4, atol=1e-9)
+
+
+def test_adam_against_golden(golden):
+    from mmlf_b200 import ops
+    g = golden('adam.npz')
+    p = torch.from_numpy(g['p0'].copy()).cuda()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for s in range(4):
+        ops.adam_step(p, torch.from_numpy(g['grads'][s].copy()).cuda(), m, v, float(g['lrs'][s]), 0.9, 0.999, 1e-8,
+                      s + 1)
+        np.testing.assert_allclose(p.cpu().numpy(), g[f'p{s + 1}'], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(m.cpu().numpy(), g['exp_avg'], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(v.cpu().numpy(), g['exp_avg_sq'], rtol=1e-5, atol=1e-9)

@@ -1,0 +1,109 @@
+"""CPU tests of the host-side mirror of the reference interface (no kernels are launched)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import _fixtures as fx
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize('variant,cross,n_keys,n_params', [
+    ('base', False, 121, 4612166), ('upr', False, 121, 4613300), ('dpp', False, 121, 4778872),
+    ('base', True, 94, 1208486)])
+def test_state_dict_layout_matches_reference(variant, cross, n_keys, n_params):
+    """Key set / shapes / parameter counts of SURVEY.md Appendix B (verified there on the reference)."""
+    from mmlf_b200.model.feed_forward import FeedForward
+    m = FeedForward(**fx.model_kwargs(variant, cross))
+    sd = m.state_dict()
+    assert len(sd) == n_keys
+    assert sum(p.numel() for p in m.parameters()) == n_params
+    assert sd['in_net_hv.0.0.weight'].shape == (70, 27, 2, 2)
+    assert sd['in_net_hv.0.3.num_batches_tracked'].dtype == torch.int64
+    assert ('in_net_id.0.0.weight' in sd) == (not cross)
+    oc = {'base': 1, 'upr': 2, 'dpp': 54 if cross else 108}[variant]
+    assert sd['out_net.7.0.weight'].shape == (oc, 140 if cross else 280, 2, 2)
+    assert sd['out_net.7.2.weight'].shape == (oc, oc, 2, 2)
+    assert m.steps == (54 if cross else 108) and m.disp_min == -3.5 and m.disp_max == 3.5
+
+
+def test_state_dict_keys_equal_reference_fixture(golden):
+    from mmlf_b200.model.feed_forward import FeedForward
+    for name, variant, cross, kw in [('net_tiny_upr_full', 'upr', False, {}), ('net_tiny_dpp_cross', 'dpp', True, {}),
+                                     ('net_tiny_base_nobn', 'base', False, {'model_no_batchnorm': True})]:
+        g = golden(name + '.npz')
+        ref = {k[6:]: g[k].shape for k in g.files if k.startswith('state/')}
+        m = FeedForward(**fx.model_kwargs(variant, cross, chs=8, **kw))
+        mine = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        assert mine == {k: tuple(v) for k, v in ref.items()}
+
+
+def test_init_matches_reference_rng_stream(golden):
+    """Same construction order as the reference => same default init under the same seed (used by the full-width
+    fixtures, which store no weights).  The checkpoint written by the reference under seed 5 carries its init."""
+    from mmlf_b200.model.feed_forward import FeedForward
+    state = torch.load(os.path.join(ROOT, 'tests', 'golden', 'ref_checkpoint_tiny.pt'))
+    torch.manual_seed(5)
+    m = FeedForward(**state['hyper_parameters'])
+    # the reference took one Adam step after init: biases of the last conv moved by at most lr = 1e-3
+    for k, v in m.state_dict().items():
+        if v.dtype.is_floating_point and 'running' not in k:
+            assert (v - state['model_state_dict'][k]).abs().max() <= 1.1e-3, k
+    assert set(state.keys()) == {'model_state_dict', 'optimizer_state_dict', 'hyper_parameters', 'epoch', 'iteration',
+                                 'loss'}
+
+
+def test_unsupported_topologies_raise():
+    from mmlf_b200.model.feed_forward import FeedForward
+    with pytest.raises(NotImplementedError):
+        FeedForward(**fx.model_kwargs('base', model_ksize=3))
+    with pytest.raises(NotImplementedError):
+        FeedForward(**fx.model_kwargs('base', model_unet=True))
+
+
+def test_lazy_outputs():
+    from mmlf_b200.model.feed_forward import LazyOutputs
+    calls = []
+
+    def heavy():
+        calls.append(1)
+        return {'posterior': 'P', 'one_hot': 'O'}
+    o = LazyOutputs({'mean': 1, 'scores': None}, {'posterior': heavy, 'one_hot': heavy})
+    assert set(o.keys()) == {'mean', 'scores', 'posterior', 'one_hot'} and not calls
+    assert o['mean'] == 1 and not calls
+    assert o.get('posterior') == 'P' and o['one_hot'] == 'O' and len(calls) == 1
+    assert o.get('missing', 7) == 7
+    assert dict(o.items())['posterior'] == 'P'
+
+
+def test_model_saver_roundtrip(tmp_path):
+    from mmlf_b200.model.feed_forward import FeedForward
+    from mmlf_b200.utils.dl import ModelSaver
+    kw = fx.model_kwargs('upr', False, chs=8)
+    m = FeedForward(**kw)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    f = str(tmp_path / 'checkpoint.pt')
+    ModelSaver()(f, torch.nn.DataParallel(m), opt, dict(kw, model_radius=11), None, 3, 0.25)
+    st = torch.load(f)
+    assert set(st) == {'model_state_dict', 'optimizer_state_dict', 'hyper_parameters', 'epoch', 'iteration', 'loss'}
+    assert st['iteration'] == 3 and not any(k.startswith('module.') for k in st['model_state_dict'])
+    m2 = FeedForward(**st['hyper_parameters'])
+    m2.load_state_dict(st['model_state_dict'])
+
+
+def test_create_mask_margin_and_view_indices(golden):
+    from mmlf_b200.data import hci4d
+    from mmlf_b200.model import loss
+    g = golden('bins.npz')
+    for mg in (0, 3, 11):
+        assert np.array_equal(loss.create_mask_margin((2, 30, 26), mg).numpy(), g[f'margin{mg}'])
+        assert np.array_equal(hci4d.create_mask_margin((2, 30, 26), mg).numpy(), g[f'margin{mg}'])
+    gi = golden('indices.npz')
+    for n in (9, 7, 5):
+        us, vs, ids, dds = hci4d.view_indices((n, n))
+        assert us == list(gi[f'us{n}']) and vs == list(gi[f'vs{n}']) and ids == list(gi[f'ids{n}']) and \
+            dds == list(gi[f'dds{n}'])
+    with pytest.raises(AssertionError):
+        hci4d.Shift(1)          # the reference requires a python float (hci4d.py:904)
