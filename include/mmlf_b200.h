@@ -29,6 +29,11 @@ extern "C" {
 
 #define MMLF_ABI_VERSION 1
 
+/* 16-bit storage formats.  Forward activations and weights are fp16 (11 significant bits; the reference's own GPU
+ * path multiplies in TF32, 11 bits), gradients are bf16 (fp32 exponent range); accumulation is always fp32. */
+#define MMLF_BF16 0
+#define MMLF_FP16 1
+
 const char* mmlf_last_error(void);
 int mmlf_abi_version(void);
 /* 0 if the current device is sm_100 and the kernels can run, else an error. */
@@ -56,12 +61,12 @@ int mmlf_shift_taps(double disp, int n, float* w0, float* w1, int* s0, int* s1);
 
 /* Fold views into channels and convert to the bf16 slot layout (feed_forward.py:226-232).
  * views: [B][C][H][W] float32 (C = n*3); out: [n_slots][ld] bf16, channels >= C and halo slots zeroed. */
-int mmlf_pack_views(const float* views, int B, int C, int H, int W, void* out, int ld, void* stream);
+int mmlf_pack_views(const float* views, int B, int C, int H, int W, void* out, int ld, int dtype, void* stream);
 
 /* Fused Shift + pack for the ESE sweep (ensamble.py:63-70 + feed_forward.py:226-232): the shifted fp32 value
  * is rounded to bf16 and written straight into the slot layout.  stack: 0 = h, 1 = v, 2 = i, 3 = d. */
 int mmlf_shift_pack(const float* src, int stack, int B, int n, int H, int W, double disp, void* out, int ld,
-                    void* stream);
+                    int dtype, void* stream);
 
 /* ------------------------------------------------------------------ convolution (mmlf/model/feed_forward.py:122-137) */
 
@@ -74,7 +79,7 @@ int mmlf_shift_pack(const float* src, int stack, int B, int n, int H, int W, dou
  *   in_groups/group_real/group_pad: the input channels form `in_groups` groups of `group_real` real channels
  *            stored with pitch `group_pad` (the 4 x 70 -> 4 x 80 concatenated feature buffer); 1/cin/cin_pad else. */
 int mmlf_pack_conv_weight(const float* w, int cout, int cin, int spatial, int dgrad, int in_groups, int group_real,
-                          int group_pad, void* out, int n_pad, int cin_pad, void* stream);
+                          int group_pad, void* out, int n_pad, int cin_pad, int dtype, void* stream);
 
 /* Inverse for gradients: dw_packed [n_pad][4][cin_pad] f32 (same tap/column convention, forward orientation)
  * -> canonical (cout, cin, 2, 2) f32; accumulate != 0 adds (two streams share one module). */
@@ -103,6 +108,9 @@ typedef struct mmlf_conv_args {
   int out_mode;          /* 0: bf16 [n_slots][ld_out]; 1: f32 [n_slots][ld_out];
                             2: f32 planar (B, n_real, Ho, Wo), Ho x Wo = (H+1)x(W+1) for type 0, H x W for type 1 */
   int n_real;            /* channels written in out_mode 2 (<= n_pad); out_mode 0/1 write n_pad channels */
+  int ab_dtype;          /* storage format of `in` and `wpack`: MMLF_BF16 or MMLF_FP16                */
+  int gate_dtype;        /* storage format of `gate`                                                  */
+  int out_dtype;         /* storage format of `out` in out_mode 0                                     */
 } mmlf_conv_args;
 
 /* 2x2 convolution as an implicit GEMM on tcgen05 (TMA-fed, TMEM accumulators, fused epilogue).  Forward of
@@ -119,16 +127,17 @@ int mmlf_conv2x2_simt(const mmlf_conv_args* args, void* stream);
  * workspace: f32, at least mmlf_conv2x2_wgrad_workspace(...) bytes.  dw: f32 [n_pad][4][cin_pad]. */
 int64_t mmlf_conv2x2_wgrad_workspace(int n_pad, int cin_pad);
 int mmlf_conv2x2_wgrad(const void* dout, int ld_dout, int n_pad, const void* act, int ld_act, int cin_pad, int B,
-                       int H, int W, int type, float* workspace, float* dw, void* stream);
+                       int H, int W, int type, int act_dtype, int dout_dtype, float* workspace, float* dw,
+                       void* stream);
 
-/* Column sums of a bf16 slot array: out[c] (+)= sum_slots x[slot][c]  (bias gradients). */
-int mmlf_colsum_bf16(const void* x, int ld, int C, int64_t n_slots, float* out, int accumulate, void* stream);
+/* Column sums of a 16-bit slot array: out[c] (+)= sum_slots x[slot][c]  (bias gradients). */
+int mmlf_colsum16(const void* x, int ld, int C, int64_t n_slots, int dtype, float* out, int accumulate, void* stream);
 
 /* ------------------------------------------------------------------ BatchNorm (feed_forward.py:134) */
 
 /* Per-channel sum and sum of squares over the valid pixels of z (bf16 slots, H x W tensor at (y+1, x+1)).
  * sums: double[2][C], must be zeroed by the caller. */
-int mmlf_bn_stats(const void* z, int ld, int C, int B, int H, int W, double* sums, void* stream);
+int mmlf_bn_stats(const void* z, int ld, int C, int B, int H, int W, int act_dtype, double* sums, void* stream);
 
 /* Training-mode finalisation: batch mean / biased var -> scale = gamma * invstd, shift = beta - mean * scale;
  * running_mean / running_var (unbiased) momentum update and num_batches_tracked += 1, as nn.BatchNorm2d does.
@@ -145,23 +154,23 @@ int mmlf_bn_fold_eval(int C_real, int C, const float* gamma, const float* beta, 
 
 /* y = relu(z * scale + shift) on valid slots, zero on halo slots; bf16 in, bf16 out (ReLU at feed_forward.py:135). */
 int mmlf_bn_apply_relu(const void* z, int ld_z, const float* scale, const float* shift, int C, int B, int H, int W,
-                       void* y, int ld_y, void* stream);
+                       int act_dtype, void* y, int ld_y, void* stream);
 
 /* Backward of BN(+ReLU) in training mode.  Pass 1: with g = dy * (y > 0) and xhat = (z - mean) * invstd,
  * sums[0][c] = sum g, sums[1][c] = sum g * xhat (double[2][C], zeroed by the caller). */
 int mmlf_bn_bwd_reduce(const void* dy, int ld_dy, const void* y, int ld_y, const void* z, int ld_z,
-                       const float* save_mean, const float* save_invstd, int C, int B, int H, int W, double* sums,
-                       void* stream);
+                       const float* save_mean, const float* save_invstd, int C, int B, int H, int W, int grad_dtype,
+                       int act_dtype, double* sums, void* stream);
 /* Pass 2: dz = gamma * invstd * (g - sum_g / count - xhat * sum_gx / count) (bf16, halo zero);
  * dgamma = sum_gx, dbeta = sum_g (f32 [C]).  train = 0 gives the eval-mode gradient dz = g * gamma * invstd. */
 int mmlf_bn_bwd_apply(const void* dy, int ld_dy, const void* y, int ld_y, const void* z, int ld_z,
                       const float* gamma, const float* save_mean, const float* save_invstd, const double* sums,
-                      int64_t count, int train, int C_real, int C, int B, int H, int W, void* dz, int ld_dz,
-                      float* dgamma, float* dbeta, void* stream);
+                      int64_t count, int train, int C_real, int C, int B, int H, int W, int grad_dtype, int act_dtype,
+                      void* dz, int ld_dz, float* dgamma, float* dbeta, void* stream);
 
 /* ReLU backward alone (blocks without BatchNorm): dz = dy * (y > 0), bf16 slots. */
-int mmlf_relu_bwd(const void* dy, int ld_dy, const void* y, int ld_y, int C, int64_t n_slots, void* dz, int ld_dz,
-                  void* stream);
+int mmlf_relu_bwd(const void* dy, int ld_dy, const void* y, int ld_y, int C, int64_t n_slots, int grad_dtype,
+                  int act_dtype, void* dz, int ld_dz, void* stream);
 
 /* ------------------------------------------------------------------ heads (feed_forward.py:270-302) */
 

@@ -22,7 +22,7 @@ class ConvArgs(C.Structure):
                 ('B', c_i), ('H', c_i), ('W', c_i), ('type', c_i),
                 ('bias', c_p), ('scale', c_p), ('shift', c_p), ('relu', c_i),
                 ('gate', c_p), ('ld_gate', c_i), ('out', c_p), ('ld_out', c_i), ('out_mode', c_i),
-                ('n_real', c_i)]
+                ('n_real', c_i), ('ab_dtype', c_i), ('gate_dtype', c_i), ('out_dtype', c_i)]
 
 
 _PROTOS = {
@@ -32,23 +32,23 @@ _PROTOS = {
     'mmlf_lf_extract_u8': (c_i, [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
     'mmlf_lf_shift': (c_i, [c_p] * 8 + [c_i, c_i, c_i, c_i, c_d, c_p]),
     'mmlf_shift_taps': (c_i, [c_d, c_i, C.POINTER(c_f), C.POINTER(c_f), C.POINTER(c_i), C.POINTER(c_i)]),
-    'mmlf_pack_views': (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_p]),
-    'mmlf_shift_pack': (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_d, c_p, c_i, c_p]),
-    'mmlf_pack_conv_weight': (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p]),
+    'mmlf_pack_views': (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p]),
+    'mmlf_shift_pack': (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_d, c_p, c_i, c_i, c_p]),
+    'mmlf_pack_conv_weight': (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_p]),
     'mmlf_unpack_conv_wgrad': (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_p]),
     'mmlf_conv2x2': (c_i, [C.POINTER(ConvArgs), c_p]),
     'mmlf_conv2x2_simt': (c_i, [C.POINTER(ConvArgs), c_p]),
     'mmlf_conv2x2_wgrad_workspace': (c_i64, [c_i, c_i]),
-    'mmlf_conv2x2_wgrad': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
-    'mmlf_colsum_bf16': (c_i, [c_p, c_i, c_i, c_i64, c_p, c_i, c_p]),
-    'mmlf_bn_stats': (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
+    'mmlf_conv2x2_wgrad': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
+    'mmlf_colsum16': (c_i, [c_p, c_i, c_i, c_i64, c_i, c_p, c_i, c_p]),
+    'mmlf_bn_stats': (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     'mmlf_bn_finalize': (c_i, [c_p, c_i, c_i, c_i64, c_p, c_p, c_p, c_p, c_p, c_f, c_f, c_p, c_p, c_p, c_p, c_p]),
     'mmlf_bn_fold_eval': (c_i, [c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_f, c_p, c_p, c_p]),
-    'mmlf_bn_apply_relu': (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_p]),
-    'mmlf_bn_bwd_reduce': (c_i, [c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
+    'mmlf_bn_apply_relu': (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_p]),
+    'mmlf_bn_bwd_reduce': (c_i, [c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     'mmlf_bn_bwd_apply': (c_i, [c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_i64, c_i, c_i, c_i, c_i, c_i,
-                                c_i, c_p, c_i, c_p, c_p, c_p]),
-    'mmlf_relu_bwd': (c_i, [c_p, c_i, c_p, c_i, c_i, c_i64, c_p, c_i, c_p]),
+                                c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_p]),
+    'mmlf_relu_bwd': (c_i, [c_p, c_i, c_p, c_i, c_i, c_i64, c_i, c_i, c_p, c_i, c_p]),
     'mmlf_head_small': (c_i, [c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_i, c_p, c_p]),
     'mmlf_head_small_bwd': (c_i, [c_p, c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_p]),
     'mmlf_upr_posterior': (c_i, [c_p, c_p, c_p, c_i, c_i64, c_i64, c_p, c_p]),
@@ -92,6 +92,8 @@ def call(name, *args):
     if rc != 0:
         raise RuntimeError(f'{name} failed ({rc}): {l.mmlf_last_error().decode()}')
 
+
+BF16, FP16 = 0, 1        # MMLF_BF16 / MMLF_FP16 storage codes
 
 _device_ok = False
 

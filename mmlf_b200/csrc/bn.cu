@@ -1,4 +1,5 @@
-// BatchNorm (training and eval), ReLU backward and column sums on the bf16 slot layout.
+// BatchNorm (training and eval), ReLU backward and column sums on the 16-bit slot layout (fp16 activations,
+// bf16 gradients; dtype codes as in common.cuh).
 // Replaces nn.BatchNorm2d / nn.ReLU of /root/reference/mmlf/model/feed_forward.py:134-135 and their autograd.
 // All kernels are HBM-bound: 128-bit loads/stores, one thread = 8 consecutive channels of one slot, so a warp
 // reads contiguous runs of the channel-last rows.
@@ -8,14 +9,16 @@
 
 namespace mmlf {
 
-__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
-  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
-  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8], int dt) {
+  unpack16x2(u.x, dt, f[0], f[1]);
+  unpack16x2(u.y, dt, f[2], f[3]);
+  unpack16x2(u.z, dt, f[4], f[5]);
+  unpack16x2(u.w, dt, f[6], f[7]);
 }
-__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+__device__ __forceinline__ uint4 pack8(const float (&f)[8], int dt) {
   uint4 u;
-  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
-  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  u.x = pack16x2(f[0], f[1], dt); u.y = pack16x2(f[2], f[3], dt);
+  u.z = pack16x2(f[4], f[5], dt); u.w = pack16x2(f[6], f[7], dt);
   return u;
 }
 __device__ __forceinline__ uint4 ld8(const void* base, int64_t slot, int ld, int c) {
@@ -40,7 +43,7 @@ __global__ void __launch_bounds__(kRedThreads)
 col_reduce_kernel(const void* __restrict__ x, int ld_x, const void* __restrict__ y, int ld_y,
                   const void* __restrict__ z, int ld_z, const float* __restrict__ mean,
                   const float* __restrict__ invstd, int C, int64_t n_slots, double* __restrict__ sums,
-                  float* __restrict__ fsum, int accumulate) {
+                  float* __restrict__ fsum, int dt_x, int dt_yz) {
   extern __shared__ float red[];                    // [lanes][groups * 16]
   const int groups = C >> 3;
   const int lanes = kRedThreads / groups;           // slot lanes per block
@@ -56,7 +59,7 @@ col_reduce_kernel(const void* __restrict__ x, int ld_x, const void* __restrict__
   if (sl < lanes) {
     for (int64_t s = static_cast<int64_t>(blockIdx.x) * lanes + sl; s < n_slots; s += static_cast<int64_t>(gridDim.x) * lanes) {
       float v[8];
-      unpack8(ld8(x, s, ld_x, g * 8), v);
+      unpack8(ld8(x, s, ld_x, g * 8), v, dt_x);
       if (MODE == 0) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) { a0[j] += v[j]; a1[j] = fmaf(v[j], v[j], a1[j]); }
@@ -65,8 +68,8 @@ col_reduce_kernel(const void* __restrict__ x, int ld_x, const void* __restrict__
         for (int j = 0; j < 8; ++j) a0[j] += v[j];
       } else {
         float yy[8], zz[8];
-        unpack8(ld8(y, s, ld_y, g * 8), yy);
-        unpack8(ld8(z, s, ld_z, g * 8), zz);
+        unpack8(ld8(y, s, ld_y, g * 8), yy, dt_yz);
+        unpack8(ld8(z, s, ld_z, g * 8), zz, dt_yz);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float gg = yy[j] > 0.f ? v[j] : 0.f;
@@ -152,7 +155,7 @@ __global__ void __launch_bounds__(256)
 slot_map_kernel(const void* __restrict__ a, int ld_a, const void* __restrict__ y, int ld_y,
                 const void* __restrict__ z, int ld_z, const float* __restrict__ p0, const float* __restrict__ p1,
                 const float* __restrict__ p2, const double* __restrict__ sums, double inv_count, int C, int Hp, int Wp,
-                int64_t n_slots, void* __restrict__ out, int ld_out) {
+                int64_t n_slots, void* __restrict__ out, int ld_out, int dt_a, int dt_yz) {
   const int groups = C >> 3;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t s = idx / groups;
@@ -162,23 +165,23 @@ slot_map_kernel(const void* __restrict__ a, int ld_a, const void* __restrict__ y
   if ((MODE == 0 || MODE == 2) && !slot_valid(s, Hp, Wp)) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) r[j] = 0.f;
-    st8(out, s, ld_out, c, pack8(r));
+    st8(out, s, ld_out, c, pack8(r, dt_a));
     return;
   }
   float av[8];
-  unpack8(ld8(a, s, ld_a, c), av);
+  unpack8(ld8(a, s, ld_a, c), av, dt_a);
   if (MODE == 0) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) r[j] = fmaxf(fmaf(av[j], p0[c + j], p1[c + j]), 0.f);
   } else {
     float yv[8];
-    unpack8(ld8(y, s, ld_y, c), yv);
+    unpack8(ld8(y, s, ld_y, c), yv, dt_yz);
     if (MODE == 1) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) r[j] = yv[j] > 0.f ? av[j] : 0.f;
     } else {
       float zv[8];
-      unpack8(ld8(z, s, ld_z, c), zv);
+      if (MODE == 2) unpack8(ld8(z, s, ld_z, c), zv, dt_yz);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float g = yv[j] > 0.f ? av[j] : 0.f;
@@ -194,7 +197,7 @@ slot_map_kernel(const void* __restrict__ a, int ld_a, const void* __restrict__ y
       }
     }
   }
-  st8(out, s, ld_out, c, pack8(r));
+  st8(out, s, ld_out, c, pack8(r, dt_a));
 }
 
 __global__ void bn_param_grads_kernel(const double* __restrict__ sums, int C_real, int C, float* __restrict__ dgamma,
@@ -219,7 +222,8 @@ using namespace mmlf;
 
 #define CHECK_C(C) MMLF_REQUIRE((C) % 8 == 0 && (C) >= 8 && (C) <= 2048, "channel count %d must be a multiple of 8 in [8, 2048]", (C))
 
-extern "C" int mmlf_bn_stats(const void* z, int ld, int C, int B, int H, int W, double* sums, void* stream) {
+extern "C" int mmlf_bn_stats(const void* z, int ld, int C, int B, int H, int W, int act_dtype, double* sums,
+                             void* stream) {
   MMLF_REQUIRE(z && sums, "bn_stats: null buffer");
   CHECK_C(C);
   MMLF_REQUIRE(C / 8 <= kRedThreads, "bn_stats: too many channels");
@@ -227,19 +231,19 @@ extern "C" int mmlf_bn_stats(const void* z, int ld, int C, int B, int H, int W, 
   const int groups = C / 8, lanes = kRedThreads / groups;
   const size_t smem = static_cast<size_t>(lanes) * groups * 16 * sizeof(float);
   col_reduce_kernel<0><<<red_grid(n_slots, lanes), kRedThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      z, ld, nullptr, 0, nullptr, 0, nullptr, nullptr, C, n_slots, sums, nullptr, 0);
+      z, ld, nullptr, 0, nullptr, 0, nullptr, nullptr, C, n_slots, sums, nullptr, act_dtype, 0);
   return check_launch("bn_stats");
 }
 
-extern "C" int mmlf_colsum_bf16(const void* x, int ld, int C, int64_t n_slots, float* out, int accumulate,
-                                void* stream) {
+extern "C" int mmlf_colsum16(const void* x, int ld, int C, int64_t n_slots, int dtype, float* out, int accumulate,
+                             void* stream) {
   MMLF_REQUIRE(x && out, "colsum: null buffer");
   CHECK_C(C);
   if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float) * C, static_cast<cudaStream_t>(stream));
   const int groups = C / 8, lanes = kRedThreads / groups;
   const size_t smem = static_cast<size_t>(lanes) * groups * 16 * sizeof(float);
   col_reduce_kernel<1><<<red_grid(n_slots, lanes), kRedThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      x, ld, nullptr, 0, nullptr, 0, nullptr, nullptr, C, n_slots, nullptr, out, 1);
+      x, ld, nullptr, 0, nullptr, 0, nullptr, nullptr, C, n_slots, nullptr, out, dtype, 0);
   return check_launch("colsum");
 }
 
@@ -265,43 +269,46 @@ extern "C" int mmlf_bn_fold_eval(int C_real, int C, const float* gamma, const fl
 }
 
 extern "C" int mmlf_bn_apply_relu(const void* z, int ld_z, const float* scale, const float* shift, int C, int B,
-                                  int H, int W, void* y, int ld_y, void* stream) {
+                                  int H, int W, int act_dtype, void* y, int ld_y, void* stream) {
   MMLF_REQUIRE(z && scale && shift && y, "bn_apply_relu: null buffer");
   CHECK_C(C);
   const int64_t n_slots = static_cast<int64_t>(B) * (H + 1) * (W + 1);
   const int64_t total = n_slots * (C / 8);
   slot_map_kernel<0><<<static_cast<unsigned>(ceil_div64(total, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      z, ld_z, nullptr, 0, nullptr, 0, scale, shift, nullptr, nullptr, 0.0, C, H + 1, W + 1, n_slots, y, ld_y);
+      z, ld_z, nullptr, 0, nullptr, 0, scale, shift, nullptr, nullptr, 0.0, C, H + 1, W + 1, n_slots, y, ld_y, act_dtype,
+      act_dtype);
   return check_launch("bn_apply_relu");
 }
 
-extern "C" int mmlf_relu_bwd(const void* dy, int ld_dy, const void* y, int ld_y, int C, int64_t n_slots, void* dz,
-                             int ld_dz, void* stream) {
+extern "C" int mmlf_relu_bwd(const void* dy, int ld_dy, const void* y, int ld_y, int C, int64_t n_slots,
+                             int grad_dtype, int act_dtype, void* dz, int ld_dz, void* stream) {
   MMLF_REQUIRE(dy && y && dz, "relu_bwd: null buffer");
   CHECK_C(C);
   const int64_t total = n_slots * (C / 8);
   slot_map_kernel<1><<<static_cast<unsigned>(ceil_div64(total, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      dy, ld_dy, y, ld_y, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0.0, C, 1, 1, n_slots, dz, ld_dz);
+      dy, ld_dy, y, ld_y, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0.0, C, 1, 1, n_slots, dz, ld_dz, grad_dtype,
+      act_dtype);
   return check_launch("relu_bwd");
 }
 
 extern "C" int mmlf_bn_bwd_reduce(const void* dy, int ld_dy, const void* y, int ld_y, const void* z, int ld_z,
                                   const float* save_mean, const float* save_invstd, int C, int B, int H, int W,
-                                  double* sums, void* stream) {
+                                  int grad_dtype, int act_dtype, double* sums, void* stream) {
   MMLF_REQUIRE(dy && y && z && save_mean && save_invstd && sums, "bn_bwd_reduce: null buffer");
   CHECK_C(C);
   const int64_t n_slots = static_cast<int64_t>(B) * (H + 1) * (W + 1);
   const int groups = C / 8, lanes = kRedThreads / groups;
   const size_t smem = static_cast<size_t>(lanes) * groups * 16 * sizeof(float);
   col_reduce_kernel<2><<<red_grid(n_slots, lanes), kRedThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      dy, ld_dy, y, ld_y, z, ld_z, save_mean, save_invstd, C, n_slots, sums, nullptr, 0);
+      dy, ld_dy, y, ld_y, z, ld_z, save_mean, save_invstd, C, n_slots, sums, nullptr, grad_dtype, act_dtype);
   return check_launch("bn_bwd_reduce");
 }
 
 extern "C" int mmlf_bn_bwd_apply(const void* dy, int ld_dy, const void* y, int ld_y, const void* z, int ld_z,
                                  const float* gamma, const float* save_mean, const float* save_invstd,
                                  const double* sums, int64_t count, int train, int C_real, int C, int B, int H, int W,
-                                 void* dz, int ld_dz, float* dgamma, float* dbeta, void* stream) {
+                                 int grad_dtype, int act_dtype, void* dz, int ld_dz, float* dgamma, float* dbeta,
+                                 void* stream) {
   MMLF_REQUIRE(dy && y && z && gamma && save_mean && save_invstd && sums && dz, "bn_bwd_apply: null buffer");
   CHECK_C(C);
   const int64_t n_slots = static_cast<int64_t>(B) * (H + 1) * (W + 1);
@@ -310,10 +317,11 @@ extern "C" int mmlf_bn_bwd_apply(const void* dy, int ld_dy, const void* y, int l
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (train)
     slot_map_kernel<2><<<blocks, 256, 0, st>>>(dy, ld_dy, y, ld_y, z, ld_z, gamma, save_mean, save_invstd, sums,
-                                               1.0 / static_cast<double>(count), C, H + 1, W + 1, n_slots, dz, ld_dz);
+                                               1.0 / static_cast<double>(count), C, H + 1, W + 1, n_slots, dz, ld_dz,
+                                               grad_dtype, act_dtype);
   else
     slot_map_kernel<3><<<blocks, 256, 0, st>>>(dy, ld_dy, y, ld_y, z, ld_z, gamma, save_mean, save_invstd, sums, 0.0,
-                                               C, H + 1, W + 1, n_slots, dz, ld_dz);
+                                               C, H + 1, W + 1, n_slots, dz, ld_dz, grad_dtype, act_dtype);
   if (int rc = check_launch("bn_bwd_apply")) return rc;
   if (dgamma && dbeta) {
     bn_param_grads_kernel<<<ceil_div(C_real, 128), 128, 0, st>>>(sums, C_real, C, dgamma, dbeta);

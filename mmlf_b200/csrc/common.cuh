@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -136,9 +137,11 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr, uint32_t
 // Instruction descriptor for kind::f16, bf16 x bf16 -> f32.
 //   [4,6) D fmt (1 = f32)  [7,10) A fmt (1 = bf16)  [10,13) B fmt  [15] A major  [16] B major (0 = K-major, 1 = MN-major)
 //   [17,23) N >> 3         [24,29) M >> 4
-__host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) |
-         ((M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_16(uint32_t M, uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major,
+                                                    uint32_t a_fp16, uint32_t b_fp16) {
+  // A/B format field: 0 = f16, 1 = bf16
+  return (1u << 4) | ((a_fp16 ? 0u : 1u) << 7) | ((b_fp16 ? 0u : 1u) << 10) | (a_mn_major << 15) | (b_mn_major << 16) |
+         ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 // TMEM -> registers: 32 lanes x 32 bit, 16 consecutive columns per thread
@@ -153,13 +156,49 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// ---------------------------------------------------------------- misc
+// ---------------------------------------------------------------- 16-bit storage formats
+// dtype codes used across the C ABI: 0 = bf16, 1 = fp16 (IEEE half).  Forward activations and weights default to
+// fp16 (11 significant bits, same tensor-core rate as bf16); gradients are bf16 (fp32 exponent range).
+constexpr int kBF16 = 0;
+constexpr int kFP16 = 1;
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  // saturate instead of producing inf: fp16 tops out at 65504
+  lo = fminf(fmaxf(lo, -65504.f), 65504.f);
+  hi = fminf(fmaxf(hi, -65504.f), 65504.f);
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi, int dtype) {
+  return dtype == kFP16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ void unpack16x2(uint32_t v, int dtype, float& lo, float& hi) {
+  if (dtype == kFP16) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v));
+    lo = f.x;
+    hi = f.y;
+  } else {
+    lo = bf16_lo(v);
+    hi = bf16_hi(v);
+  }
+}
+__device__ __forceinline__ uint16_t to16(float x, int dtype) {
+  if (dtype == kFP16) {
+    x = fminf(fmaxf(x, -65504.f), 65504.f);
+    return __half_as_ushort(__float2half_rn(x));
+  }
+  return __bfloat16_as_ushort(__float2bfloat16_rn(x));
+}
+__device__ __forceinline__ float from16(uint16_t v, int dtype) {
+  return dtype == kFP16 ? __half2float(__ushort_as_half(v)) : __uint_as_float(static_cast<uint32_t>(v) << 16);
+}
 
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {

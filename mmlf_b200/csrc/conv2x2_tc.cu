@@ -32,6 +32,7 @@ struct ConvParams {
   int num_tiles, stages;
   int b_boxes, b_box_rows;
   int type, relu, out_mode, n_real, ld_out, ld_gate;
+  int ab_dtype, gate_dtype, out_dtype;          // 0 = bf16, 1 = fp16
   const float* bias;
   const float* scale;
   const float* shift;
@@ -59,21 +60,23 @@ __device__ __forceinline__ void epilogue_store16(const ConvParams& p, const floa
     const uint32_t gw[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      if (!(bf16_lo(gw[j]) > 0.f)) v[2 * j] = 0.f;
-      if (!(bf16_hi(gw[j]) > 0.f)) v[2 * j + 1] = 0.f;
+      float lo, hi;
+      unpack16x2(gw[j], p.gate_dtype, lo, hi);
+      if (!(lo > 0.f)) v[2 * j] = 0.f;
+      if (!(hi > 0.f)) v[2 * j + 1] = 0.f;
     }
   }
   if (p.out_mode == 0) {
     uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + s * p.ld_out + c0);
     uint4 a, c;
-    a.x = pack_bf16x2(v[0], v[1]);
-    a.y = pack_bf16x2(v[2], v[3]);
-    a.z = pack_bf16x2(v[4], v[5]);
-    a.w = pack_bf16x2(v[6], v[7]);
-    c.x = pack_bf16x2(v[8], v[9]);
-    c.y = pack_bf16x2(v[10], v[11]);
-    c.z = pack_bf16x2(v[12], v[13]);
-    c.w = pack_bf16x2(v[14], v[15]);
+    a.x = pack16x2(v[0], v[1], p.out_dtype);
+    a.y = pack16x2(v[2], v[3], p.out_dtype);
+    a.z = pack16x2(v[4], v[5], p.out_dtype);
+    a.w = pack16x2(v[6], v[7], p.out_dtype);
+    c.x = pack16x2(v[8], v[9], p.out_dtype);
+    c.y = pack16x2(v[10], v[11], p.out_dtype);
+    c.z = pack16x2(v[12], v[13], p.out_dtype);
+    c.w = pack16x2(v[14], v[15], p.out_dtype);
     o[0] = a;
     o[1] = c;
   } else if (p.out_mode == 1) {
@@ -177,7 +180,7 @@ conv2x2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (single thread)
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(kTileM, p.n_part, 0, 0);
+      const uint32_t idesc = make_idesc_16(kTileM, p.n_part, 0, 0, p.ab_dtype, p.ab_dtype);
       uint32_t stage = 0, phase = 0, tphase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         mbar_wait(smem_u32(tmem_empty_bar), tphase ^ 1u);   // epilogue has drained the accumulator
@@ -268,9 +271,9 @@ __global__ void conv2x2_simt_kernel(const __nv_bfloat16* __restrict__ in, int ld
     const __nv_bfloat16* a = in + r * ld_in;
     const __nv_bfloat16* w = wpack + static_cast<int64_t>(tap) * p.n_kc * 64;
     for (int c = 0; c < cin_pad; ++c) {
-      const float av = __bfloat162float(a[c]);
+      const float av = from16(reinterpret_cast<const uint16_t*>(a)[c], p.ab_dtype);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = fmaf(av, __bfloat162float(w[static_cast<int64_t>(c0 + j) * k_total + c]), v[j]);
+      for (int j = 0; j < 16; ++j) v[j] = fmaf(av, from16(reinterpret_cast<const uint16_t*>(w)[static_cast<int64_t>(c0 + j) * k_total + c], p.ab_dtype), v[j]);
     }
   }
   epilogue_store16(p, p.bias, p.scale, p.shift, s, true, valid, b, sy, sx, c0, v);
@@ -316,6 +319,10 @@ static int fill_params(const mmlf_conv_args* a, ConvParams& p) {
   p.n_real = a->n_real;
   p.ld_out = a->ld_out;
   p.ld_gate = a->ld_gate;
+  MMLF_REQUIRE((a->ab_dtype | a->gate_dtype | a->out_dtype) >> 1 == 0, "conv2x2: dtype codes are 0 (bf16) or 1 (fp16)");
+  p.ab_dtype = a->ab_dtype;
+  p.gate_dtype = a->gate_dtype;
+  p.out_dtype = a->out_dtype;
   p.bias = a->bias;
   p.scale = a->scale;
   p.shift = a->shift;

@@ -30,6 +30,7 @@ struct WgradParams {
   int tap_off[4];
   int stages;
   int part_n[2], n_parts;
+  int act_dtype, dout_dtype;                    // 0 = bf16, 1 = fp16
   float* ws;                                    // [ksplits][n_mblocks * 128][ws_ld]
   int ws_ld;
 };
@@ -102,7 +103,7 @@ conv2x2_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_
   } else if (warp == 1) {
     if (lane == 0) {
       uint32_t idesc[2];
-      for (int q = 0; q < p.n_parts; ++q) idesc[q] = make_idesc_bf16(128, p.part_n[q], 1, 1);
+      for (int q = 0; q < p.n_parts; ++q) idesc[q] = make_idesc_16(128, p.part_n[q], 1, 1, p.act_dtype, p.dout_dtype);
       uint32_t stage = 0, phase = 0, accumulate = 0;
       for (int ch = 0; ch < n_chunks; ++ch) {
         mbar_wait(smem_u32(&full_bar[stage]), phase);
@@ -193,8 +194,10 @@ extern "C" int64_t mmlf_conv2x2_wgrad_workspace(int n_pad, int cin_pad) {
 }
 
 extern "C" int mmlf_conv2x2_wgrad(const void* dout, int ld_dout, int n_pad, const void* act, int ld_act, int cin_pad,
-                                  int B, int H, int W, int type, float* workspace, float* dw, void* stream) {
+                                  int B, int H, int W, int type, int act_dtype, int dout_dtype, float* workspace, float* dw,
+                                  void* stream) {
   MMLF_REQUIRE(dout && act && workspace && dw, "wgrad: null buffer");
+  MMLF_REQUIRE((act_dtype | dout_dtype) >> 1 == 0, "wgrad: dtype codes are 0 (bf16) or 1 (fp16)");
   MMLF_REQUIRE(n_pad % 16 == 0 && n_pad >= 16 && n_pad <= 320, "wgrad: n_pad %d must be a multiple of 16 in [16, 320]", n_pad);
   MMLF_REQUIRE(cin_pad % 16 == 0 && cin_pad >= 16 && cin_pad <= 320, "wgrad: cin_pad %d must be a multiple of 16 in [16, 320]", cin_pad);
   MMLF_REQUIRE(ld_dout % 8 == 0 && ld_act % 8 == 0 && ld_dout >= n_pad && ld_act >= cin_pad, "wgrad: bad row pitch");
@@ -220,6 +223,8 @@ extern "C" int mmlf_conv2x2_wgrad(const void* dout, int ld_dout, int n_pad, cons
     p.n_parts = 1; p.part_n[0] = n_pad; p.part_n[1] = 0;
   }
   p.ws = workspace;
+  p.act_dtype = act_dtype;
+  p.dout_dtype = dout_dtype;
   const uint32_t stage_bytes = (2 + p.n_boxes) * kWgBox;
   const uint32_t aux_bytes = (2 * kWgMaxStages + 1) * 8 + 16 + 64;
   const uint32_t max_smem = 232448;

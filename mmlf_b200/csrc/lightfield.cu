@@ -161,7 +161,7 @@ struct PackParams {
   const float* views;
   __nv_bfloat16* out;
   int B, C, H, W, ld;
-  int do_shift, stack, n;
+  int do_shift, stack, n, dtype;
   ShiftTaps taps;
 };
 
@@ -212,8 +212,8 @@ __global__ void __launch_bounds__(256) pack_views_kernel(const PackParams p) {
     const int sx = sx0 + slot;
     if (sx < Wp && cbase + cq < p.ld) {
       uint2 o;
-      o.x = pack_bf16x2(tile[cq][slot], tile[cq + 1][slot]);
-      o.y = pack_bf16x2(tile[cq + 2][slot], tile[cq + 3][slot]);
+      o.x = pack16x2(tile[cq][slot], tile[cq + 1][slot], p.dtype);
+      o.y = pack16x2(tile[cq + 2][slot], tile[cq + 3][slot], p.dtype);
       *reinterpret_cast<uint2*>(p.out + (slot_row + sx) * p.ld + cbase + cq) = o;
     }
     __syncthreads();
@@ -264,7 +264,6 @@ extern "C" int mmlf_lf_shift(const float* src_h, const float* src_v, const float
   MMLF_REQUIRE(src_h && src_v && src_i && src_d && dst_h && dst_v && dst_i && dst_d, "lf_shift: null buffer");
   MMLF_REQUIRE(n >= 1 && n <= 16, "lf_shift: n must be in [1, 16]");
   MMLF_REQUIRE(src_h != dst_h && src_v != dst_v && src_i != dst_i && src_d != dst_d, "lf_shift is out of place");
-  MMLF_REQUIRE(static_cast<int64_t>(4) * batch * n * 3 <= 65535 * 1ll || true, "unused");
   ShiftParams p;
   p.src[0] = src_h; p.src[1] = src_v; p.src[2] = src_i; p.src[3] = src_d;
   p.dst[0] = dst_h; p.dst[1] = dst_v; p.dst[2] = dst_i; p.dst[3] = dst_d;
@@ -297,15 +296,16 @@ extern "C" int mmlf_lf_shift(const float* src_h, const float* src_v, const float
   return 0;
 }
 
-static int launch_pack(const float* views, int B, int C, int H, int W, void* out, int ld, int do_shift, int stack,
-                       int n, double disp, void* stream) {
+static int launch_pack(const float* views, int B, int C, int H, int W, void* out, int ld, int dtype, int do_shift,
+                       int stack, int n, double disp, void* stream) {
+  MMLF_REQUIRE(dtype == 0 || dtype == 1, "pack_views: dtype must be 0 (bf16) or 1 (fp16)");
   MMLF_REQUIRE(views && out, "pack_views: null buffer");
   MMLF_REQUIRE(ld % 8 == 0 && ld >= C, "pack_views: ld %d must be a multiple of 8 and >= C %d", ld, C);
   MMLF_REQUIRE(static_cast<int64_t>(B) * (H + 1) <= 65535 * 1024ll, "pack_views: batch too large");
   PackParams p;
   p.views = views; p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.B = B; p.C = C; p.H = H; p.W = W; p.ld = ld;
-  p.do_shift = do_shift; p.stack = stack; p.n = n;
+  p.do_shift = do_shift; p.stack = stack; p.n = n; p.dtype = dtype;
   if (do_shift) host_taps(disp, n, p.taps);
   const int64_t rows = static_cast<int64_t>(B) * (H + 1);
   // grid.y <= 65535: split the batch into slabs
@@ -324,13 +324,14 @@ static int launch_pack(const float* views, int B, int C, int H, int W, void* out
   return 0;
 }
 
-extern "C" int mmlf_pack_views(const float* views, int B, int C, int H, int W, void* out, int ld, void* stream) {
-  return launch_pack(views, B, C, H, W, out, ld, 0, 0, 0, 0.0, stream);
+extern "C" int mmlf_pack_views(const float* views, int B, int C, int H, int W, void* out, int ld, int dtype,
+                               void* stream) {
+  return launch_pack(views, B, C, H, W, out, ld, dtype, 0, 0, 0, 0.0, stream);
 }
 
 extern "C" int mmlf_shift_pack(const float* src, int stack, int B, int n, int H, int W, double disp, void* out,
-                               int ld, void* stream) {
+                               int ld, int dtype, void* stream) {
   MMLF_REQUIRE(stack >= 0 && stack < 4, "shift_pack: stack must be 0..3");
   MMLF_REQUIRE(n >= 1 && n <= 16, "shift_pack: n must be in [1, 16]");
-  return launch_pack(src, B, n * 3, H, W, out, ld, 1, stack, n, disp, stream);
+  return launch_pack(src, B, n * 3, H, W, out, ld, dtype, 1, stack, n, disp, stream);
 }

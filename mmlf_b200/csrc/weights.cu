@@ -22,8 +22,8 @@ __host__ __device__ __forceinline__ int real_channel(int c, int groups, int grou
 }
 
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int cout, int cin, int spatial, int dgrad,
-                                        int groups, int group_real, int group_pad, __nv_bfloat16* __restrict__ out,
-                                        int n_pad, int n_kc) {
+                                        int groups, int group_real, int group_pad, uint16_t* __restrict__ out,
+                                        int n_pad, int n_kc, int dtype) {
   const int k_total = 4 * n_kc * 64;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<int64_t>(n_pad) * k_total) return;
@@ -48,7 +48,7 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int cout, i
     eff_to_canonical(spatial, p, q, a, b);
     v = w[((static_cast<int64_t>(n) * cin + ci) * 2 + a) * 2 + b];
   }
-  out[idx] = __float2bfloat16_rn(v);
+  out[idx] = to16(v, dtype);
 }
 
 __global__ void unpack_conv_wgrad_kernel(const float* __restrict__ dwp, int n_pad, int cin_pad, int cout, int cin,
@@ -74,8 +74,10 @@ __global__ void unpack_conv_wgrad_kernel(const float* __restrict__ dwp, int n_pa
 using namespace mmlf;
 
 extern "C" int mmlf_pack_conv_weight(const float* w, int cout, int cin, int spatial, int dgrad, int in_groups,
-                                     int group_real, int group_pad, void* out, int n_pad, int cin_pad, void* stream) {
+                                     int group_real, int group_pad, void* out, int n_pad, int cin_pad, int dtype,
+                                     void* stream) {
   MMLF_REQUIRE(w && out, "pack_conv_weight: null buffer");
+  MMLF_REQUIRE(dtype == 0 || dtype == 1, "pack_conv_weight: dtype must be 0 (bf16) or 1 (fp16)");
   MMLF_REQUIRE(spatial >= 0 && spatial <= 2, "pack_conv_weight: spatial must be 0..2");
   MMLF_REQUIRE(in_groups >= 1 && group_real >= 1 && group_pad >= group_real, "pack_conv_weight: bad channel groups");
   MMLF_REQUIRE(in_groups * group_real == cin, "pack_conv_weight: groups (%d x %d) do not cover cin %d", in_groups, group_real, cin);
@@ -87,7 +89,7 @@ extern "C" int mmlf_pack_conv_weight(const float* w, int cout, int cin, int spat
   const int n_kc = ceil_div(cin_pad, 64);
   const int64_t total = static_cast<int64_t>(n_pad) * 4 * n_kc * 64;
   pack_conv_weight_kernel<<<static_cast<unsigned>(ceil_div64(total, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      w, cout, cin, spatial, dgrad, in_groups, group_real, group_pad, reinterpret_cast<__nv_bfloat16*>(out), n_pad, n_kc);
+      w, cout, cin, spatial, dgrad, in_groups, group_real, group_pad, reinterpret_cast<uint16_t*>(out), n_pad, n_kc, dtype);
   return check_launch("pack_conv_weight_kernel");
 }
 

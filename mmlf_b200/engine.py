@@ -13,7 +13,10 @@ import math
 import torch
 
 from . import _lib
-from ._lib import ConvArgs, call
+from ._lib import BF16, FP16, ConvArgs, call
+
+_TORCH_DT = {BF16: torch.bfloat16, FP16: torch.float16}
+GRAD = BF16      # gradients are always bf16 (fp32 exponent range)
 
 
 def pad16(x):
@@ -78,6 +81,11 @@ class Engine:
         self._pack_version = None
         self._build_specs()
 
+    @property
+    def act(self):
+        """Storage format of forward activations and weights ('fp16' default, 'bf16' optional)."""
+        return FP16 if getattr(self.m, 'precision', 'fp16') == 'fp16' else BF16
+
     # ------------------------------------------------------------------ static plan
     def _build_specs(self):
         cin0 = self.views * 3
@@ -130,7 +138,7 @@ class Engine:
     def repack(self, need_dgrad):
         """(Re)build the packed bf16 operands when the canonical fp32 parameters changed."""
         params = self._params()
-        version = tuple(p._version for p in params.values()) + tuple(p.data_ptr() for p in params.values())
+        version = tuple(p._version for p in params.values()) + tuple(p.data_ptr() for p in params.values()) + (self.act,)
         if self._pack_version is not None and self._pack_version[0] == version and \
                 (self._pack_version[1] or not need_dgrad):
             return
@@ -141,17 +149,17 @@ class Engine:
             b = params[cs.name + '.bias'].detach()
             kc = cs.kc
             if cs.w_fwd is None:
-                cs.w_fwd = torch.empty((cs.n_pad, 4 * kc * 64), dtype=torch.bfloat16, device=dev)
+                cs.w_fwd = torch.empty((cs.n_pad, 4 * kc * 64), dtype=torch.int16, device=dev)
                 cs.bias_pad = torch.zeros(cs.n_pad, dtype=torch.float32, device=dev)
             call('mmlf_pack_conv_weight', _ptr(w), cs.cout, cs.cin, cs.spatial, 0, cs.groups, cs.group_real,
-                 cs.group_pad, _ptr(cs.w_fwd), cs.n_pad, cs.cin_pad, st)
+                 cs.group_pad, _ptr(cs.w_fwd), cs.n_pad, cs.cin_pad, self.act, st)
             cs.bias_pad[:cs.cout].copy_(b)
             if need_dgrad:
                 kd = (cs.n_pad + 63) // 64
                 if cs.w_dgrad is None:
-                    cs.w_dgrad = torch.empty((cs.cin_pad, 4 * kd * 64), dtype=torch.bfloat16, device=dev)
+                    cs.w_dgrad = torch.empty((cs.cin_pad, 4 * kd * 64), dtype=torch.int16, device=dev)
                 call('mmlf_pack_conv_weight', _ptr(w), cs.cout, cs.cin, cs.spatial, 1, cs.groups, cs.group_real,
-                     cs.group_pad, _ptr(cs.w_dgrad), cs.cin_pad, cs.n_pad, st)
+                     cs.group_pad, _ptr(cs.w_dgrad), cs.cin_pad, cs.n_pad, GRAD, st)
         self._pack_version = (version, bool(need_dgrad))
 
     def _bn_padded(self, prefix, C_real, C, dev):
@@ -165,8 +173,11 @@ class Engine:
 
     # ------------------------------------------------------------------ kernel launch helpers
     def conv(self, geo, x, ld_in, cs, w, n_pad, cin_pad, ctype, out, ld_out, *, bias=None, scale=None, shift=None,
-             relu=False, gate=None, ld_gate=0, out_mode=0, n_real=0, simt=False):
+             relu=False, gate=None, ld_gate=0, out_mode=0, n_real=0, simt=False, ab=None, out_dt=None, gate_dt=None):
         a = ConvArgs()
+        a.ab_dtype = self.act if ab is None else ab
+        a.out_dtype = self.act if out_dt is None else out_dt
+        a.gate_dtype = self.act if gate_dt is None else gate_dt
         a.in_, a.ld_in, a.cin_pad = x.data_ptr(), ld_in, cin_pad
         a.wpack, a.n_pad = w.data_ptr(), n_pad
         a.B, a.H, a.W, a.type = geo.B, geo.H, geo.W, ctype
@@ -179,7 +190,12 @@ class Engine:
         a.out, a.ld_out, a.out_mode, a.n_real = out.data_ptr(), ld_out, out_mode, n_real
         call('mmlf_conv2x2_simt' if simt else 'mmlf_conv2x2', C.byref(a), _stream())
 
-    def _slots(self, geo, ch, dtype=torch.bfloat16):
+    def _slots(self, geo, ch, dtype=None):
+        """Activation-format slot array by default; pass GRAD or torch.float32 for the others."""
+        if dtype is None:
+            dtype = self.act
+        if not isinstance(dtype, torch.dtype):
+            dtype = _TORCH_DT[dtype]
         return torch.empty((geo.n_slots, ch), dtype=dtype, device=self.dev)
 
     # ------------------------------------------------------------------ forward
@@ -206,9 +222,9 @@ class Engine:
                 'view stacks must be contiguous fp32 CUDA tensors (feed_forward.py:226-232 uses .view)'
             x = self._slots(geo, cin0_pad)
             if shift_disp is None:
-                call('mmlf_pack_views', _ptr(v), B, n * c3, H, W, _ptr(x), cin0_pad, st)
+                call('mmlf_pack_views', _ptr(v), B, n * c3, H, W, _ptr(x), cin0_pad, self.act, st)
             else:
-                call('mmlf_shift_pack', _ptr(v), si, B, n, H, W, float(shift_disp), _ptr(x), cin0_pad, st)
+                call('mmlf_shift_pack', _ptr(v), si, B, n, H, W, float(shift_disp), _ptr(x), cin0_pad, self.act, st)
             ld_x = cin0_pad
             recs = []
             blocks = self.in_specs[key]
@@ -275,14 +291,15 @@ class Engine:
         z = self._slots(geo, Cp)
         self.conv(geo, a1, c1.n_pad, c2, c2.w_fwd, Cp, c2.cin_pad, 1, z, Cp, bias=c2.bias_pad)
         sums = torch.zeros(2 * Cp, dtype=torch.float64, device=self.dev)
-        call('mmlf_bn_stats', _ptr(z), Cp, Cp, geo.B, geo.H, geo.W, _ptr(sums), st)
+        call('mmlf_bn_stats', _ptr(z), Cp, Cp, geo.B, geo.H, geo.W, self.act, _ptr(sums), st)
         save_mean = torch.empty(Cp, dtype=torch.float32, device=self.dev)
         save_invstd = torch.empty(Cp, dtype=torch.float32, device=self.dev)
         nbt = bufs.get(bnp + '.num_batches_tracked')
         call('mmlf_bn_finalize', _ptr(sums), C_real, Cp, geo.count, _ptr(gamma), _ptr(beta), _ptr(rmean), _ptr(rvar),
              _ptr(nbt), float(self.m.batchnorm_momentum), float(self.m.bn_eps), _ptr(scale), _ptr(shift),
              _ptr(save_mean), _ptr(save_invstd), st)
-        call('mmlf_bn_apply_relu', _ptr(z), Cp, _ptr(scale), _ptr(shift), Cp, geo.B, geo.H, geo.W, _ptr(y), ld_y, st)
+        call('mmlf_bn_apply_relu', _ptr(z), Cp, _ptr(scale), _ptr(shift), Cp, geo.B, geo.H, geo.W, self.act, _ptr(y),
+             ld_y, st)
         if save:
             rec.update(z=z, save_mean=save_mean, save_invstd=save_invstd)
         return rec
@@ -302,7 +319,7 @@ class Engine:
         def conv_param_grads(cs, dout, ld_dout, act, ld_act):
             """dW via the tcgen05 wgrad kernel, db via a column sum; accumulates for shared modules."""
             call('mmlf_conv2x2_wgrad', _ptr(dout), ld_dout, cs.n_pad, _ptr(act), ld_act, cs.cin_pad, geo.B, geo.H,
-                 geo.W, cs.type, _ptr(ws), _ptr(dwp), st)
+                 geo.W, cs.type, self.act, GRAD, _ptr(ws), _ptr(dwp), st)
             wname, bname = cs.name + '.weight', cs.name + '.bias'
             acc = wname in grads
             if not acc:
@@ -310,31 +327,31 @@ class Engine:
                 grads[bname] = torch.zeros(cs.n_pad, dtype=torch.float32, device=dev)
             call('mmlf_unpack_conv_wgrad', _ptr(dwp), cs.n_pad, cs.cin_pad, cs.cout, cs.cin, cs.spatial, cs.groups,
                  cs.group_real, cs.group_pad, _ptr(grads[wname]), 1 if acc else 0, st)
-            call('mmlf_colsum_bf16', _ptr(dout), ld_dout, cs.n_pad, geo.n_slots, _ptr(grads[bname]), 1, st)
+            call('mmlf_colsum16', _ptr(dout), ld_dout, cs.n_pad, geo.n_slots, GRAD, _ptr(grads[bname]), 1, st)
 
         def dgrad(cs, dout, ld_dout, out, ld_out, gate=None, ld_gate=0):
             """Data gradient: the conv kernel of the other type with rotated, transposed weights."""
             self.conv(geo, dout, ld_dout, cs, cs.w_dgrad, cs.cin_pad, cs.n_pad, 1 - cs.type, out, ld_out, gate=gate,
-                      ld_gate=ld_gate)
+                      ld_gate=ld_gate, ab=GRAD, out_dt=GRAD, gate_dt=self.act)
 
         # ---- head
         hd = tape['head']
         h1 = self.head1
-        g_x = self._slots(geo, h1.cin_pad)
+        g_x = self._slots(geo, h1.cin_pad, GRAD)
         if self.small_head:
             h2n = self.head2.name
             w2 = params[h2n + '.weight'].detach()
-            gmid = self._slots(geo, h1.n_pad)
+            gmid = self._slots(geo, h1.n_pad, GRAD)
             grads[h2n + '.weight'] = torch.zeros_like(params[h2n + '.weight'])
             grads[h2n + '.bias'] = torch.zeros_like(params[h2n + '.bias'])
             call('mmlf_head_small_bwd', _ptr(g_out), _ptr(hd['mid']), h1.n_pad, self.oc, _ptr(w2), geo.B, geo.H, geo.W,
                  _ptr(gmid), h1.n_pad, _ptr(grads[h2n + '.weight']), _ptr(grads[h2n + '.bias']), st)
         else:
             h2 = self.head2
-            gz = self._slots(geo, h2.n_pad)
-            call('mmlf_pack_views', _ptr(g_out), geo.B, self.oc, geo.H, geo.W, _ptr(gz), h2.n_pad, st)
+            gz = self._slots(geo, h2.n_pad, GRAD)
+            call('mmlf_pack_views', _ptr(g_out), geo.B, self.oc, geo.H, geo.W, _ptr(gz), h2.n_pad, GRAD, st)
             conv_param_grads(h2, gz, h2.n_pad, hd['mid'], h1.n_pad)
-            gmid = self._slots(geo, h1.n_pad)
+            gmid = self._slots(geo, h1.n_pad, GRAD)
             dgrad(h2, gz, h2.n_pad, gmid, h1.n_pad, gate=hd['mid'], ld_gate=h1.n_pad)
         conv_param_grads(h1, gmid, h1.n_pad, hd['x'], hd['ld_x'])
         dgrad(h1, gmid, h1.n_pad, g_x, h1.cin_pad)
@@ -343,32 +360,34 @@ class Engine:
         def block_bwd(rec, gy, ld_gy, need_gx):
             c1, c2, bnp = rec['c1'], rec['c2'], rec['bnp']
             Cp, C_real = c2.n_pad, c2.cout
-            dz = self._slots(geo, Cp)
+            dz = self._slots(geo, Cp, GRAD)
             if self.has_bn:
                 sums = torch.zeros(2 * Cp, dtype=torch.float64, device=dev)
                 call('mmlf_bn_bwd_reduce', _ptr(gy), ld_gy, _ptr(rec['y']), rec['ld_y'], _ptr(rec['z']), Cp,
-                     _ptr(rec['save_mean']), _ptr(rec['save_invstd']), Cp, geo.B, geo.H, geo.W, _ptr(sums), st)
+                     _ptr(rec['save_mean']), _ptr(rec['save_invstd']), Cp, geo.B, geo.H, geo.W, GRAD, self.act,
+                     _ptr(sums), st)
                 gpad, _ = self._bn_padded(bnp, C_real, Cp, dev)
                 acc = bnp + '.weight' in grads
                 dgam = torch.empty(C_real, dtype=torch.float32, device=dev)
                 dbet = torch.empty(C_real, dtype=torch.float32, device=dev)
                 call('mmlf_bn_bwd_apply', _ptr(gy), ld_gy, _ptr(rec['y']), rec['ld_y'], _ptr(rec['z']), Cp, _ptr(gpad),
                      _ptr(rec['save_mean']), _ptr(rec['save_invstd']), _ptr(sums), geo.count, 1, C_real, Cp, geo.B,
-                     geo.H, geo.W, _ptr(dz), Cp, _ptr(dgam), _ptr(dbet), st)
+                     geo.H, geo.W, GRAD, self.act, _ptr(dz), Cp, _ptr(dgam), _ptr(dbet), st)
                 if acc:
                     grads[bnp + '.weight'] += dgam
                     grads[bnp + '.bias'] += dbet
                 else:
                     grads[bnp + '.weight'], grads[bnp + '.bias'] = dgam, dbet
             else:
-                call('mmlf_relu_bwd', _ptr(gy), ld_gy, _ptr(rec['y']), rec['ld_y'], Cp, geo.n_slots, _ptr(dz), Cp, st)
+                call('mmlf_relu_bwd', _ptr(gy), ld_gy, _ptr(rec['y']), rec['ld_y'], Cp, geo.n_slots, GRAD, self.act,
+                     _ptr(dz), Cp, st)
             conv_param_grads(c2, dz, Cp, rec['a1'], c1.n_pad)
-            da1 = self._slots(geo, c1.n_pad)
+            da1 = self._slots(geo, c1.n_pad, GRAD)
             dgrad(c2, dz, Cp, da1, c1.n_pad, gate=rec['a1'], ld_gate=c1.n_pad)
             conv_param_grads(c1, da1, c1.n_pad, rec['x'], rec['ld_x'])
             if not need_gx:
                 return None
-            gx = self._slots(geo, c1.cin_pad)
+            gx = self._slots(geo, c1.cin_pad, GRAD)
             dgrad(c1, da1, c1.n_pad, gx, c1.cin_pad)
             return gx
 

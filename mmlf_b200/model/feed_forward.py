@@ -24,10 +24,9 @@ class _NetFunction(torch.autograd.Function):
     Engine.backward, not autograd over per-layer ops."""
 
     @staticmethod
-    def forward(ctx, engine, training, n_views, *tensors):
-        views, params = tensors[:n_views], tensors[n_views:]
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        out, tape = engine.forward(list(views), training, save=need_grad)
+    def forward(ctx, engine, training, save, n_views, *tensors):
+        views = tensors[:n_views]
+        out, tape = engine.forward(list(views), training, save=save)
         ctx.engine, ctx.tape, ctx.n_views = engine, tape, n_views
         ctx.names = [n for n, _ in engine.m.named_parameters()]
         return out
@@ -38,7 +37,7 @@ class _NetFunction(torch.autograd.Function):
             raise RuntimeError('backward through a forward pass that did not record a tape')
         grads = ctx.engine.backward(ctx.tape, g_out.contiguous())
         ctx.tape = None
-        return (None, None, None) + (None,) * ctx.n_views + tuple(grads.get(n) for n in ctx.names)
+        return (None, None, None, None) + (None,) * ctx.n_views + tuple(grads.get(n) for n in ctx.names)
 
 
 class LazyOutputs(dict):
@@ -177,7 +176,9 @@ class FeedForward(nn.Module):
         if not self.cross and (i_views is None or d_views is None):
             raise TypeError('the 4-stream model needs i_views and d_views (feed_forward.py:230-231)')
         params = [p for _, p in self.named_parameters()]
-        output = _NetFunction.apply(self.engine, self.training, len(views), *views, *params)
+        # grad mode is off inside Function.forward, so decide here whether the backward tape is needed
+        save = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        output = _NetFunction.apply(self.engine, self.training, save, len(views), *views, *params)
         mean = output[:, 0]
         eager = {'mean': mean, 'logvar': None, 'scores': None, 'one_hot': None, 'posterior': None}
         lazy = {}

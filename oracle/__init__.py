@@ -17,7 +17,7 @@ committed under ``tests/golden/``; ``tests/test_oracle_golden.py`` replays them.
 """
 from .lf import view_indices, extract_stacks, shift, shift_taps, ese_shift_values  # noqa: F401
 from .net import (FeedForwardOracle, torch_linspace_f32, np_linspace_f32,  # noqa: F401
-                  bf16_round, laplacian)
+                  bf16_round, fp16_round, laplacian)
 from .losses import (create_mask_margin, reg_to_class, mpi_to_weights, class_to_reg,  # noqa: F401
                      masked_l1, multi_masked_l1, masked_mse, masked_badpix,
                      masked_cross_entropy, improved_uncertainty_l1,

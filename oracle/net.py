@@ -26,6 +26,12 @@ def bf16_round(x):
     return np.where(np.isnan(x), x, out)
 
 
+def fp16_round(x):
+    """fp32 -> fp16 (round-to-nearest-even, saturating at +-65504 like the kernels' epilogue) -> fp32."""
+    x = np.clip(np.asarray(x, dtype=np.float32), -65504.0, 65504.0)
+    return x.astype(np.float16).astype(np.float32)
+
+
 def torch_linspace_f32(start, end, steps):
     """``torch.linspace(start, end, steps)`` for float32 as ATen's CPU kernel
     computes it (RangeFactories: step in float32; first half ``start + step*i``,
@@ -112,12 +118,21 @@ class FeedForwardOracle:
         self.training = False
 
     # -- precision emulation ---------------------------------------------------
+    # quant=None: fp32 restatement.  'fp16': what the CUDA path does by default -- forward activations and
+    # weights stored in fp16 (saturating), gradients and the dgrad weight operand in bf16.  'bf16': everything bf16.
     def _q(self, x):
+        if self.quant == 'fp16':
+            return fp16_round(x)
         return bf16_round(x) if self.quant == 'bf16' else x
 
-    def _w(self, name):
+    def _qg(self, x):
+        return bf16_round(x) if self.quant else x
+
+    def _w(self, name, grad=False):
         w = self.p[name]
-        return bf16_round(w) if self.quant == 'bf16' else w
+        if not self.quant:
+            return w
+        return bf16_round(w) if (grad or self.quant == 'bf16') else fp16_round(w)
 
     # -- one block: conv(k2,p1) -> ReLU -> conv(k2,p0) [-> BN -> ReLU]  (feed_forward.py:122-137)
     def _block_fwd(self, prefix, x, bn, tape, head_fp32=False, relu_out=True):
@@ -125,7 +140,7 @@ class FeedForwardOracle:
         w2, b2 = self._w(prefix + '.2.weight'), self.p[prefix + '.2.bias']
         a1 = np.maximum(conv2x2(x, w1, b1, 1), 0)
         a1 = a1 if head_fp32 else self._q(a1)
-        if head_fp32 and self.quant == 'bf16':
+        if head_fp32 and self.quant:
             w2 = self.p[prefix + '.2.weight']          # tiny head conv2 runs in fp32 on CUDA cores
         z = conv2x2(a1, w2, b2, 0)
         rec = {'prefix': prefix, 'x': x, 'a1': a1, 'bn': bn, 'relu_out': relu_out}
@@ -173,16 +188,16 @@ class FeedForwardOracle:
                 gz = (g * rec['invstd']) * (gy - gy2.mean(0) - rec['xhat'] * (gy2 * xh2).sum(0) / n)
             else:
                 gz = gy * (g * rec['invstd'])
-            gz = self._q(gz)
+            gz = self._qg(gz)
         else:
-            gz = self._q(gy * (rec['y'] > 0)) if rec['relu_out'] else gy
-        w1, w2 = self._w(prefix + '.0.weight'), self._w(prefix + '.2.weight')
+            gz = self._qg(gy * (rec['y'] > 0)) if rec['relu_out'] else gy
+        w1, w2 = self._w(prefix + '.0.weight', grad=True), self._w(prefix + '.2.weight', grad=True)
         ga1, gw2, gb2 = conv2x2_bwd(rec['a1'], w2, gz, 0)
-        ga1 = self._q(ga1 * (rec['a1'] > 0))
+        ga1 = self._qg(ga1 * (rec['a1'] > 0))
         gx, gw1, gb1 = conv2x2_bwd(rec['x'], w1, ga1, 1)
         grads[prefix + '.0.weight'], grads[prefix + '.0.bias'] = gw1, gb1
         grads[prefix + '.2.weight'], grads[prefix + '.2.bias'] = gw2, gb2
-        return (self._q(gx) if need_gx else None), grads
+        return (self._qg(gx) if need_gx else None), grads
 
     def _in_net(self, name, x, tape):
         for k in range(self.in_blocks):

@@ -7,7 +7,12 @@ import torch
 
 from mmlf_b200 import _lib
 from mmlf_b200._lib import ConvArgs, call
-from oracle.net import bf16_round
+from oracle.net import bf16_round, fp16_round
+
+BF16, FP16 = 0, 1
+TDT = {BF16: torch.bfloat16, FP16: torch.float16}
+ROUND = {BF16: bf16_round, FP16: fp16_round}
+ULP = {BF16: 2.0 ** -7, FP16: 2.0 ** -10}
 
 DEV = 'cuda'
 
@@ -24,7 +29,7 @@ def pad16(x):
     return (x + 15) // 16 * 16
 
 
-def to_slots(x_nhwc, ld, full_grid, Hp, Wp):
+def to_slots(x_nhwc, ld, full_grid, Hp, Wp, dt=BF16):
     """numpy (B, h, w, C) -> torch bf16 [B*Hp*Wp, ld] on the device.  full_grid: the tensor covers the whole
     (H+1)x(W+1) slot grid; otherwise it is H x W and lives at slots (y+1, x+1) with a zero halo."""
     B, h, w, Cc = x_nhwc.shape
@@ -34,7 +39,7 @@ def to_slots(x_nhwc, ld, full_grid, Hp, Wp):
         s[:, :, :, :Cc] = t
     else:
         s[:, 1:, 1:, :Cc] = t
-    return s.reshape(B * Hp * Wp, ld).to(torch.bfloat16).to(DEV)
+    return s.reshape(B * Hp * Wp, ld).to(TDT[dt]).to(DEV)
 
 
 def from_slots(t, B, Hp, Wp, Cc, full_grid):
@@ -42,7 +47,7 @@ def from_slots(t, B, Hp, Wp, Cc, full_grid):
     return a[..., :Cc] if full_grid else a[:, 1:, 1:, :Cc]
 
 
-def pack_weight(w, spatial=0, dgrad=0, groups=1, group_real=None, group_pad=None, n_pad=None, cin_pad=None):
+def pack_weight(w, spatial=0, dgrad=0, groups=1, group_real=None, group_pad=None, n_pad=None, cin_pad=None, dt=BF16):
     cout, cin = w.shape[:2]
     group_real = group_real or cin
     group_pad = group_pad or pad16(cin)
@@ -51,18 +56,18 @@ def pack_weight(w, spatial=0, dgrad=0, groups=1, group_real=None, group_pad=None
         cin_pad = cin_pad or (groups * group_pad if groups > 1 else pad16(cin))
     kc = (cin_pad + 63) // 64
     wd = torch.from_numpy(np.ascontiguousarray(w)).to(DEV)
-    out = torch.empty((n_pad, 4 * kc * 64), dtype=torch.bfloat16, device=DEV)
+    out = torch.empty((n_pad, 4 * kc * 64), dtype=TDT[dt], device=DEV)
     call('mmlf_pack_conv_weight', ptr(wd), cout, cin, spatial, dgrad, groups, group_real, group_pad, ptr(out), n_pad,
-         cin_pad, stream())
+         cin_pad, dt, stream())
     return out
 
 
 def run_conv(x_slots, ld_in, cin_pad, wpack, n_pad, B, H, W, ctype, *, bias=None, scale=None, shift=None, relu=False,
-             gate=None, ld_gate=0, out_mode=0, n_real=0, simt=False, ld_out=None):
+             gate=None, ld_gate=0, out_mode=0, n_real=0, simt=False, ld_out=None, ab=BF16, out_dt=BF16, gate_dt=BF16):
     n_slots = B * (H + 1) * (W + 1)
     ld_out = ld_out or n_pad
     if out_mode == 0:
-        out = torch.full((n_slots, ld_out), float('nan'), dtype=torch.bfloat16, device=DEV)
+        out = torch.full((n_slots, ld_out), float('nan'), dtype=TDT[out_dt], device=DEV)
     elif out_mode == 1:
         out = torch.full((n_slots, ld_out), float('nan'), dtype=torch.float32, device=DEV)
     else:
@@ -79,6 +84,7 @@ def run_conv(x_slots, ld_in, cin_pad, wpack, n_pad, B, H, W, ctype, *, bias=None
     a.gate = gate.data_ptr() if gate is not None else None
     a.ld_gate = ld_gate
     a.out, a.ld_out, a.out_mode, a.n_real = out.data_ptr(), ld_out, out_mode, n_real
+    a.ab_dtype, a.out_dtype, a.gate_dtype = ab, out_dt, gate_dt
     call('mmlf_conv2x2_simt' if simt else 'mmlf_conv2x2', C.byref(a), stream())
     torch.cuda.synchronize()
     return out
@@ -88,10 +94,10 @@ def dev_f32(a):
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(DEV)
 
 
-def assert_close_bf16(got, want, what, ulps=1.0, atol=1e-6):
-    """|got - want| within `ulps` bf16 units-in-the-last-place of `want` (got is a bf16-rounded result)."""
+def assert_close_bf16(got, want, what, ulps=1.0, atol=1e-6, dt=BF16):
+    """|got - want| within `ulps` units-in-the-last-place (of the 16-bit storage format) of `want`."""
     want = np.asarray(want, np.float32)
     got = np.asarray(got, np.float32)
-    tol = ulps * np.abs(want) * 2.0 ** -7 + atol
+    tol = ulps * np.abs(want) * ULP[dt] + atol
     bad = np.abs(got - want) > tol
     assert not bad.any(), f'{what}: {bad.sum()} / {bad.size} outside {ulps} bf16 ulp; worst |d|={np.abs(got - want).max():.4g}'

@@ -63,29 +63,32 @@ def test_pack_views_and_shift_pack():
     rng = np.random.RandomState(2)
     v = rng.uniform(0, 1, (B, n, 3, H, W)).astype(np.float32)
     out = torch.full((B * (H + 1) * (W + 1), 32), float('nan'), dtype=torch.bfloat16, device='cuda')
-    u.call('mmlf_pack_views', u.ptr(torch.from_numpy(v).cuda()), B, n * 3, H, W, u.ptr(out), 32, u.stream())
-    got = out.float().cpu().numpy().reshape(B, H + 1, W + 1, 32)
-    want = np.zeros_like(got)
-    want[:, 1:, 1:, :27] = bf16_round(v.reshape(B, 27, H, W).transpose(0, 2, 3, 1))
-    assert np.array_equal(got, want)
+    for dt in (u.BF16, u.FP16):
+        out = torch.full((B * (H + 1) * (W + 1), 32), float('nan'), dtype=u.TDT[dt], device='cuda')
+        u.call('mmlf_pack_views', u.ptr(torch.from_numpy(v).cuda()), B, n * 3, H, W, u.ptr(out), 32, dt, u.stream())
+        got = out.float().cpu().numpy().reshape(B, H + 1, W + 1, 32)
+        want = np.zeros_like(got)
+        want[:, 1:, 1:, :27] = u.ROUND[dt](v.reshape(B, 27, H, W).transpose(0, 2, 3, 1))
+        assert np.array_equal(got, want)
     # fused shift + pack == pack(shift(.)) for every stack
     stacks = [rng.uniform(0, 1, (B, n, 3, 12, 12)).astype(np.float32) for _ in range(4)]
     for disp in (2.5, -1.3, 0.0, 7.25):
         sh = oracle.shift(tuple(stacks), disp)
         for k in range(4):
-            o = torch.full((B * 13 * 13, 32), float('nan'), dtype=torch.bfloat16, device='cuda')
+            o = torch.full((B * 13 * 13, 32), float('nan'), dtype=torch.float16, device='cuda')
             u.call('mmlf_shift_pack', u.ptr(torch.from_numpy(stacks[k]).cuda()), k, B, n, 12, 12, float(disp),
-                   u.ptr(o), 32, u.stream())
+                   u.ptr(o), 32, u.FP16, u.stream())
             got = o.float().cpu().numpy().reshape(B, 13, 13, 32)
             want = np.zeros_like(got)
-            want[:, 1:, 1:, :27] = bf16_round(sh[k].reshape(B, 27, 12, 12).transpose(0, 2, 3, 1))
+            want[:, 1:, 1:, :27] = u.ROUND[u.FP16](sh[k].reshape(B, 27, 12, 12).transpose(0, 2, 3, 1))
             assert np.array_equal(got, want), (disp, k)
 
 
 # ------------------------------------------------------------------------------------------------ convolution
 def _conv_case(B, H, W, cin, cout, ctype, seed, simt, relu=True, mode=0, with_bn=False, groups=1, group_real=None,
-               group_pad=None):
+               group_pad=None, dt=1):
     u = _u()
+    rnd = u.ROUND[dt]
     rng = np.random.RandomState(seed)
     Hp, Wp = H + 1, W + 1
     cin_pad = groups * group_pad if groups > 1 else u.pad16(cin)
@@ -96,7 +99,7 @@ def _conv_case(B, H, W, cin, cout, ctype, seed, simt, relu=True, mode=0, with_bn
         x = rng.normal(0, 1, (B, H, W, cin)).astype(np.float32)
     else:
         x = rng.normal(0, 1, (B, Hp, Wp, cin)).astype(np.float32)
-    xq, wq = bf16_round(x), bf16_round(w)
+    xq, wq = rnd(x), rnd(w)
     want = conv2x2(xq, wq, b, 1 if ctype == 0 else 0)
     scale = shift = None
     if with_bn:
@@ -112,11 +115,11 @@ def _conv_case(B, H, W, cin, cout, ctype, seed, simt, relu=True, mode=0, with_bn
             xl[..., g * group_pad:g * group_pad + group_real] = xq[..., g * group_real:(g + 1) * group_real]
     else:
         xl = xq
-    xs = u.to_slots(xl, cin_pad, ctype == 1, Hp, Wp)
-    wp = u.pack_weight(w, groups=groups, group_real=group_real, group_pad=group_pad)
+    xs = u.to_slots(xl, cin_pad, ctype == 1, Hp, Wp, dt)
+    wp = u.pack_weight(w, groups=groups, group_real=group_real, group_pad=group_pad, dt=dt)
     bias = torch.zeros(n_pad, device='cuda')
     bias[:cout] = torch.from_numpy(b)
-    kw = dict(bias=bias, relu=relu, simt=simt, out_mode=mode)
+    kw = dict(bias=bias, relu=relu, simt=simt, out_mode=mode, ab=dt, out_dt=dt)
     if with_bn:
         sc = torch.zeros(n_pad, device='cuda')
         sh = torch.zeros(n_pad, device='cuda')
@@ -137,7 +140,8 @@ def _conv_case(B, H, W, cin, cout, ctype, seed, simt, relu=True, mode=0, with_bn
         assert not full[:, 0].any() and not full[:, :, 0].any(), 'halo slots must be zero'
     assert not full[..., cout:].any() or not relu, 'padding channels must stay zero'
     if mode == 0:
-        u.assert_close_bf16(got, want, f'conv type {ctype} {cin}->{cout}', ulps=1.01, atol=2e-3)
+        u.assert_close_bf16(got, want, f'conv type {ctype} {cin}->{cout}', ulps=1.01, atol=2e-3 if dt == 0 else 3e-4,
+                            dt=dt)
     else:
         np.testing.assert_allclose(got, want, rtol=2e-4, atol=2e-4)
 
@@ -149,14 +153,16 @@ CONV_CASES = [
 ]
 
 
+@pytest.mark.parametrize('dt', [0, 1])
 @pytest.mark.parametrize('case', CONV_CASES)
-def test_conv_simt_vs_oracle(case):
-    _conv_case(*case, seed=3, simt=True)
+def test_conv_simt_vs_oracle(case, dt):
+    _conv_case(*case, seed=3, simt=True, dt=dt)
 
 
+@pytest.mark.parametrize('dt', [0, 1])
 @pytest.mark.parametrize('case', CONV_CASES)
-def test_conv_tc_vs_oracle(case):
-    _conv_case(*case, seed=3, simt=False)
+def test_conv_tc_vs_oracle(case, dt):
+    _conv_case(*case, seed=3, simt=False, dt=dt)
 
 
 def test_conv_tc_epilogues():
@@ -193,9 +199,9 @@ def test_conv_dgrad_and_gate():
         want = gx * gate
         wd = u.pack_weight(w, dgrad=1, n_pad=u.pad16(cin), cin_pad=u.pad16(cout))
         gs = u.to_slots(gout, u.pad16(cout), ctype == 0, Hp, Wp)
-        gate_s = u.to_slots(gate, u.pad16(cin), ctype == 1, Hp, Wp)
+        gate_s = u.to_slots(gate, u.pad16(cin), ctype == 1, Hp, Wp, u.FP16)
         out = u.run_conv(gs, u.pad16(cout), u.pad16(cout), wd, u.pad16(cin), B, H, W, 1 - ctype, gate=gate_s,
-                         ld_gate=u.pad16(cin))
+                         ld_gate=u.pad16(cin), gate_dt=u.FP16)
         got = u.from_slots(out, B, Hp, Wp, cin, ctype == 1)
         u.assert_close_bf16(got, want, f'dgrad of type {ctype}', ulps=1.01, atol=2e-3)
 
@@ -203,34 +209,36 @@ def test_conv_dgrad_and_gate():
 @pytest.mark.parametrize('case', [(2, 12, 12, 27, 70, 0), (2, 12, 12, 70, 70, 1), (2, 20, 20, 280, 280, 0),
                                   (2, 20, 20, 280, 280, 1), (1, 16, 16, 280, 2, 0), (1, 16, 16, 108, 108, 1),
                                   (6, 40, 40, 280, 280, 1)])
-def test_conv_wgrad(case):
+@pytest.mark.parametrize('act_dt', [0, 1])
+def test_conv_wgrad(case, act_dt):
     u = _u()
+    rnd = u.ROUND[act_dt]
     B, H, W, cin, cout, ctype = case
     rng = np.random.RandomState(12)
     Hp, Wp = H + 1, W + 1
     cin_pad, n_pad = u.pad16(cin), u.pad16(cout)
     if ctype == 0:
-        x = bf16_round(rng.normal(0, 1, (B, H, W, cin)).astype(np.float32))
+        x = rnd(rng.normal(0, 1, (B, H, W, cin)).astype(np.float32))
         gout = bf16_round(rng.normal(0, 1, (B, Hp, Wp, cout)).astype(np.float32))
     else:
-        x = bf16_round(rng.normal(0, 1, (B, Hp, Wp, cin)).astype(np.float32))
+        x = rnd(rng.normal(0, 1, (B, Hp, Wp, cin)).astype(np.float32))
         gout = bf16_round(rng.normal(0, 1, (B, H, W, cout)).astype(np.float32))
     w = np.zeros((cout, cin, 2, 2), np.float32)
     _, gw, gb = conv2x2_bwd(x, w, gout, 1 if ctype == 0 else 0)
-    xs = u.to_slots(x, cin_pad, ctype == 1, Hp, Wp)
+    xs = u.to_slots(x, cin_pad, ctype == 1, Hp, Wp, act_dt)
     gs = u.to_slots(gout, n_pad, ctype == 0, Hp, Wp)
     ws_bytes = u._lib.lib().mmlf_conv2x2_wgrad_workspace(n_pad, cin_pad)
     ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device='cuda')
     dwp = torch.full((n_pad, 4, cin_pad), float('nan'), dtype=torch.float32, device='cuda')
-    u.call('mmlf_conv2x2_wgrad', u.ptr(gs), n_pad, n_pad, u.ptr(xs), cin_pad, cin_pad, B, H, W, ctype, u.ptr(ws),
-           u.ptr(dwp), u.stream())
+    u.call('mmlf_conv2x2_wgrad', u.ptr(gs), n_pad, n_pad, u.ptr(xs), cin_pad, cin_pad, B, H, W, ctype, act_dt, u.BF16,
+           u.ptr(ws), u.ptr(dwp), u.stream())
     dw = torch.empty((cout, cin, 2, 2), dtype=torch.float32, device='cuda')
     u.call('mmlf_unpack_conv_wgrad', u.ptr(dwp), n_pad, cin_pad, cout, cin, 0, 1, cin, cin_pad, u.ptr(dw), 0, u.stream())
     torch.cuda.synchronize()
     scale = np.abs(gw).max()
     assert np.abs(dw.cpu().numpy() - gw).max() <= 2e-4 * scale + 1e-4
     db = torch.zeros(n_pad, device='cuda')
-    u.call('mmlf_colsum_bf16', u.ptr(gs), n_pad, n_pad, B * Hp * Wp, u.ptr(db), 0, u.stream())
+    u.call('mmlf_colsum16', u.ptr(gs), n_pad, n_pad, B * Hp * Wp, u.BF16, u.ptr(db), 0, u.stream())
     np.testing.assert_allclose(db.cpu().numpy()[:cout], gb, rtol=1e-4, atol=1e-3)
 
 
@@ -265,10 +273,11 @@ def test_bn_train_roundtrip():
     B, H, W, Cr = 2, 9, 13, 70
     Cp = u.pad16(Cr)
     Hp, Wp = H + 1, W + 1
-    z = bf16_round(rng.normal(0.3, 1.7, (B, H, W, Cr)).astype(np.float32))
-    zs = u.to_slots(z, Cp, False, Hp, Wp)
+    A, G = u.FP16, u.BF16
+    z = u.ROUND[A](rng.normal(0.3, 1.7, (B, H, W, Cr)).astype(np.float32))
+    zs = u.to_slots(z, Cp, False, Hp, Wp, A)
     sums = torch.zeros(2 * Cp, dtype=torch.float64, device='cuda')
-    u.call('mmlf_bn_stats', u.ptr(zs), Cp, Cp, B, H, W, u.ptr(sums), u.stream())
+    u.call('mmlf_bn_stats', u.ptr(zs), Cp, Cp, B, H, W, A, u.ptr(sums), u.stream())
     gamma = rng.uniform(0.5, 1.5, Cr).astype(np.float32)
     beta = rng.normal(0, 0.2, Cr).astype(np.float32)
     rm0 = rng.normal(0, 0.1, Cr).astype(np.float32)
@@ -279,8 +288,8 @@ def test_bn_train_roundtrip():
     n = B * H * W
     u.call('mmlf_bn_finalize', u.ptr(sums), Cr, Cp, n, u.ptr(d['gamma']), u.ptr(d['beta']), u.ptr(d['rm']),
            u.ptr(d['rv']), u.ptr(nbt), 0.1, 1e-5, u.ptr(scale), u.ptr(shift), u.ptr(smean), u.ptr(sinv), u.stream())
-    y = torch.full((B * Hp * Wp, Cp), float('nan'), dtype=torch.bfloat16, device='cuda')
-    u.call('mmlf_bn_apply_relu', u.ptr(zs), Cp, u.ptr(scale), u.ptr(shift), Cp, B, H, W, u.ptr(y), Cp, u.stream())
+    y = torch.full((B * Hp * Wp, Cp), float('nan'), dtype=torch.float16, device='cuda')
+    u.call('mmlf_bn_apply_relu', u.ptr(zs), Cp, u.ptr(scale), u.ptr(shift), Cp, B, H, W, A, u.ptr(y), Cp, u.stream())
     torch.cuda.synchronize()
     z2 = z.reshape(-1, Cr).astype(np.float64)
     mean, var = z2.mean(0), z2.var(0)
@@ -292,19 +301,19 @@ def test_bn_train_roundtrip():
     want = np.maximum((z - mean) / np.sqrt(var + 1e-5) * gamma + beta, 0).astype(np.float32)
     full = y.float().cpu().numpy().reshape(B, Hp, Wp, Cp)
     assert not full[:, 0].any() and not full[:, :, 0].any() and not full[..., Cr:].any()
-    u.assert_close_bf16(full[:, 1:, 1:, :Cr], want, 'bn_apply_relu', ulps=1.01, atol=2e-3)
+    u.assert_close_bf16(full[:, 1:, 1:, :Cr], want, 'bn_apply_relu', ulps=1.01, atol=3e-4, dt=A)
     # backward
     gy = bf16_round(rng.normal(0, 1, (B, H, W, Cr)).astype(np.float32))
     gys = u.to_slots(gy, Cp, False, Hp, Wp)
     bs = torch.zeros(2 * Cp, dtype=torch.float64, device='cuda')
     u.call('mmlf_bn_bwd_reduce', u.ptr(gys), Cp, u.ptr(y), Cp, u.ptr(zs), Cp, u.ptr(smean), u.ptr(sinv), Cp, B, H, W,
-           u.ptr(bs), u.stream())
+           G, A, u.ptr(bs), u.stream())
     gpad = torch.zeros(Cp, device='cuda')
     gpad[:Cr] = d['gamma']
     dz = torch.full((B * Hp * Wp, Cp), float('nan'), dtype=torch.bfloat16, device='cuda')
     dgam, dbet = torch.empty(Cr, device='cuda'), torch.empty(Cr, device='cuda')
     u.call('mmlf_bn_bwd_apply', u.ptr(gys), Cp, u.ptr(y), Cp, u.ptr(zs), Cp, u.ptr(gpad), u.ptr(smean), u.ptr(sinv),
-           u.ptr(bs), n, 1, Cr, Cp, B, H, W, u.ptr(dz), Cp, u.ptr(dgam), u.ptr(dbet), u.stream())
+           u.ptr(bs), n, 1, Cr, Cp, B, H, W, G, A, u.ptr(dz), Cp, u.ptr(dgam), u.ptr(dbet), u.stream())
     torch.cuda.synchronize()
     yq = full[:, 1:, 1:, :Cr]
     g = gy * (yq > 0)

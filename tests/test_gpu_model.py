@@ -14,11 +14,13 @@ from oracle import losses as olosses
 
 pytestmark = pytest.mark.gpu
 
-# Stated bf16 bound: activations and weights are stored in bf16 (8 mantissa bits), accumulation
-# is fp32.  Against the fp32 reference the network outputs agree to 4 % of the output range (max-abs), against the
-# oracle with the same bf16 rounding points to 1.5 %.
-BF16_BOUND_VS_REF = 0.04
-BF16_BOUND_VS_EMU = 0.015
+# Stated precision bound.  Forward activations and weights are stored in fp16 (11 significant bits,
+# the precision at which the reference's own GPU path multiplies: TF32), gradients in bf16; accumulation is fp32.
+# On the deliberately ill-conditioned fixtures (22 convs, weights scaled x2, detuned BN statistics) the network outputs
+# agree with the fp32 reference to 6 % of the output range max-abs and 0.5 % mean-abs, and with the oracle run with the
+# same rounding points to 3 % / 0.2 % (residual = fp32 summation order flipping individual fp16 roundings).
+MAX_VS_REF, MEAN_VS_REF = 0.06, 0.005
+MAX_VS_EMU, MEAN_VS_EMU = 0.03, 0.002
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -62,6 +64,10 @@ def _rel(a, b, scale):
     return float(np.abs(a - b).max() / scale)
 
 
+def _mrel(a, b, scale):
+    return float(np.abs(a - b).mean() / scale)
+
+
 def _check(name, kw, state, g, B, H, W, in_seed, mm, grads=True):
     variant = 'upr' if kw['model_uncert'] else ('dpp' if kw['model_discrete'] else 'base')
     T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
@@ -70,7 +76,7 @@ def _check(name, kw, state, g, B, H, W, in_seed, mm, grads=True):
     mpi = fx.synth_mpi(in_seed + 2, gt)
     m = _build(kw, state)
     okw = dict(model_cross=kw['model_cross'], model_uncert=kw['model_uncert'], model_discrete=kw['model_discrete'])
-    emu = oracle.FeedForwardOracle(state, quant='bf16', **okw)
+    emu = oracle.FeedForwardOracle(state, quant='fp16', **okw)
     key = 'scores' if variant == 'dpp' else 'mean'
     # ---------------- eval
     m.eval()
@@ -81,14 +87,17 @@ def _check(name, kw, state, g, B, H, W, in_seed, mm, grads=True):
     scale = float(np.abs(ref).max())
     got = out[key].cpu().numpy()
     r_ref, r_emu = _rel(got, ref, scale), _rel(got, e[key], scale)
-    report(test=name, mode='eval', key=key, vs_ref=r_ref, vs_emu=r_emu, scale=scale)
-    assert r_emu <= BF16_BOUND_VS_EMU, f'{name} eval {key}: vs bf16-emulating oracle {r_emu:.4f}'
-    assert r_ref <= BF16_BOUND_VS_REF, f'{name} eval {key}: vs reference {r_ref:.4f}'
+    m_ref, m_emu = _mrel(got, ref, scale), _mrel(got, e[key], scale)
+    report(test=name, mode='eval', key=key, max_vs_ref=r_ref, mean_vs_ref=m_ref, max_vs_emu=r_emu, mean_vs_emu=m_emu,
+           scale=scale)
+    assert r_emu <= MAX_VS_EMU and m_emu <= MEAN_VS_EMU, f'{name} eval {key}: vs emulating oracle {r_emu:.4f}/{m_emu:.5f}'
+    assert r_ref <= MAX_VS_REF and m_ref <= MEAN_VS_REF, f'{name} eval {key}: vs reference {r_ref:.4f}/{m_ref:.5f}'
     if variant == 'upr':
         lv = out['logvar'].cpu().numpy()
         s2 = float(np.abs(g['eval/logvar']).max())
-        report(test=name, mode='eval', key='logvar', vs_ref=_rel(lv, g['eval/logvar'], s2), vs_emu=_rel(lv, e['logvar'], s2))
-        assert _rel(lv, g['eval/logvar'], s2) <= BF16_BOUND_VS_REF
+        report(test=name, mode='eval', key='logvar', max_vs_ref=_rel(lv, g['eval/logvar'], s2),
+               mean_vs_ref=_mrel(lv, g['eval/logvar'], s2), max_vs_emu=_rel(lv, e['logvar'], s2))
+        assert _rel(lv, g['eval/logvar'], s2) <= MAX_VS_REF
         assert out['posterior'].shape == g['eval/posterior'].shape
     if variant == 'dpp':
         assert out['one_hot'].shape == g['eval/one_hot'].shape and out['posterior'].shape == ref.shape
@@ -126,8 +135,8 @@ def _check(name, kw, state, g, B, H, W, in_seed, mm, grads=True):
     lossv.backward()
     lv = lossv.item()
     report(test=name, mode='train', key='loss', got=lv, ref=float(g['train/loss']), emu=float(ev))
-    assert abs(lv - float(g['train/loss'])) <= 0.03 * abs(float(g['train/loss'])) + 1e-3
-    assert abs(lv - float(ev)) <= 0.01 * abs(float(ev)) + 1e-3
+    assert abs(lv - float(g['train/loss'])) <= 0.01 * abs(float(g['train/loss'])) + 1e-3
+    assert abs(lv - float(ev)) <= 0.005 * abs(float(ev)) + 1e-3
     egrads = emu.backward(e_gout)
     worst_ref = worst_emu = 0.0
     gmax = max(np.abs(g[k]).max() for k in g.files if k.startswith('grad/'))
@@ -144,15 +153,15 @@ def _check(name, kw, state, g, B, H, W, in_seed, mm, grads=True):
         worst_emu = max(worst_emu, float(np.abs(got_s - eg_s).max() / den))
         assert np.isfinite(got).all(), pname
     report(test=name, mode='train', key='grads', worst_rel_vs_ref=worst_ref, worst_rel_vs_emu=worst_emu)
-    # gradients pass through ~20 ReLU gates whose on/off pattern flips under bf16 rounding (see test_oracle_golden):
-    # per-tensor max-abs error relative to that tensor's largest gradient
-    assert worst_emu <= 0.10, f'{name}: gradients vs bf16-emulating oracle {worst_emu:.3f}'
-    assert worst_ref <= 0.25, f'{name}: gradients vs reference {worst_ref:.3f}'
+    # gradients are carried in bf16 and pass through ~20 ReLU gates whose on/off pattern flips under rounding (see
+    # test_oracle_golden): per-tensor max-abs error relative to that tensor's largest gradient
+    assert worst_emu <= 0.10, f'{name}: gradients vs emulating oracle {worst_emu:.3f}'
+    assert worst_ref <= 0.15, f'{name}: gradients vs reference {worst_ref:.3f}'
     # BN running statistics after one training forward (two updates for the shared in-nets)
     for k in g.files:
         if k.startswith('after/'):
             got = m.state_dict()[k[6:]].cpu().numpy()
-            np.testing.assert_allclose(got, g[k], rtol=0.03, atol=0.03 * max(1e-3, float(np.abs(g[k]).max())), err_msg=k)
+            np.testing.assert_allclose(got, g[k], rtol=0.01, atol=0.01 * max(1e-3, float(np.abs(g[k]).max())), err_msg=k)
 
 
 @pytest.mark.parametrize('name,variant,cross,mm', [
@@ -207,7 +216,7 @@ def test_reference_checkpoint_loads(golden):
     with torch.no_grad():
         out = m(T(h), T(v), T(i), T(d))
     scale = max(float(np.abs(g['mean']).max()), 1e-3)
-    assert np.abs(out['mean'].cpu().numpy() - g['mean']).max() <= BF16_BOUND_VS_REF * scale + 1e-3
+    assert np.abs(out['mean'].cpu().numpy() - g['mean']).max() <= MAX_VS_REF * scale + 1e-3
 
 
 def test_ensamble(golden):
@@ -225,8 +234,8 @@ def test_ensamble(golden):
         assert set(out.keys()) == {'mean', 'logvar', 'means', 'logvars', 'posterior'}
         scale = float(np.abs(g[f'{tag}/means']).max())
         r = _rel(out['means'].cpu().numpy(), g[f'{tag}/means'], scale)
-        report(test='ese_' + tag, key='means', vs_ref=r)
-        assert r <= BF16_BOUND_VS_REF
+        report(test='ese_' + tag, key='means', max_vs_ref=r)
+        assert r <= MAX_VS_REF
         assert out['posterior'].shape == g[f'{tag}/posterior'].shape
         # reduce consistency: mean/logvar are the min-logvar member of OUR members, exactly
         mm_, lv_, _ = oracle.ensemble_reduce(out['means'].cpu().numpy(), out['logvars'].cpu().numpy(), -3.5, 3.5)
