@@ -124,11 +124,16 @@ int mmlf_conv2x2_simt(const mmlf_conv_args* args, void* stream);
 /* Weight gradient of the same convolution (autograd of feed_forward.py:123/125):
  *   dw[n][tap][c] = sum_slots dout[slot][n] * act[slot + tap_offset(type)][c]
  * dout: bf16 [n_slots][ld_dout] (n_pad channels), act: bf16 [n_slots][ld_act] (cin_pad channels).
- * workspace: f32, at least mmlf_conv2x2_wgrad_workspace(...) bytes.  dw: f32 [n_pad][4][cin_pad]. */
+ * workspace: f32, at least mmlf_conv2x2_wgrad_workspace(...) bytes.  dw: f32 [n_pad][4][cin_pad].
+ * act_dtype must equal dout_dtype: tcgen05.mma kind::f16 faults on mixed f16 x bf16 operands (measured on B200). */
 int64_t mmlf_conv2x2_wgrad_workspace(int n_pad, int cin_pad);
 int mmlf_conv2x2_wgrad(const void* dout, int ld_dout, int n_pad, const void* act, int ld_act, int cin_pad, int B,
                        int H, int W, int type, int act_dtype, int dout_dtype, float* workspace, float* dw,
                        void* stream);
+
+/* Format conversion of a 16-bit slot array (C channels per slot, multiple of 8). */
+int mmlf_convert16(const void* src, int ld_src, int src_dtype, void* dst, int ld_dst, int dst_dtype, int C,
+                   int64_t n_slots, void* stream);
 
 /* Column sums of a 16-bit slot array: out[c] (+)= sum_slots x[slot][c]  (bias gradients). */
 int mmlf_colsum16(const void* x, int ld, int C, int64_t n_slots, int dtype, float* out, int accumulate, void* stream);

@@ -40,6 +40,7 @@ _PROTOS = {
     'mmlf_conv2x2_simt': (c_i, [C.POINTER(ConvArgs), c_p]),
     'mmlf_conv2x2_wgrad_workspace': (c_i64, [c_i, c_i]),
     'mmlf_conv2x2_wgrad': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
+    'mmlf_convert16': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_i64, c_p]),
     'mmlf_colsum16': (c_i, [c_p, c_i, c_i, c_i64, c_i, c_p, c_i, c_p]),
     'mmlf_bn_stats': (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     'mmlf_bn_finalize': (c_i, [c_p, c_i, c_i, c_i64, c_p, c_p, c_p, c_p, c_p, c_f, c_f, c_p, c_p, c_p, c_p, c_p]),

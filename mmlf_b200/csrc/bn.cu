@@ -208,6 +208,21 @@ __global__ void bn_param_grads_kernel(const double* __restrict__ sums, int C_rea
   dgamma[c] = static_cast<float>(sums[C + c]);
 }
 
+// 16-bit format conversion of a slot array (fp16 activations -> bf16 operand of the weight-gradient GEMM, whose two
+// operands must share one format: tcgen05.mma kind::f16 rejects mixed f16 x bf16 with an illegal-instruction fault).
+__global__ void __launch_bounds__(256)
+convert16_kernel(const void* __restrict__ src, int ld_src, void* __restrict__ dst, int ld_dst, int C, int64_t n_slots,
+                 int dt_src, int dt_dst) {
+  const int groups = C >> 3;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t s = idx / groups;
+  if (s >= n_slots) return;
+  const int c = static_cast<int>(idx - s * groups) * 8;
+  float v[8];
+  unpack8(ld8(src, s, ld_src, c), v, dt_src);
+  st8(dst, s, ld_dst, c, pack8(v, dt_dst));
+}
+
 static int red_grid(int64_t n_slots, int lanes) {
   int64_t want = ceil_div64(n_slots, static_cast<int64_t>(lanes) * 8);
   int64_t cap = static_cast<int64_t>(sm_count()) * 8;
@@ -221,6 +236,16 @@ static int red_grid(int64_t n_slots, int lanes) {
 using namespace mmlf;
 
 #define CHECK_C(C) MMLF_REQUIRE((C) % 8 == 0 && (C) >= 8 && (C) <= 2048, "channel count %d must be a multiple of 8 in [8, 2048]", (C))
+
+extern "C" int mmlf_convert16(const void* src, int ld_src, int src_dtype, void* dst, int ld_dst, int dst_dtype, int C,
+                              int64_t n_slots, void* stream) {
+  MMLF_REQUIRE(src && dst, "convert16: null buffer");
+  CHECK_C(C);
+  const int64_t total = n_slots * (C / 8);
+  convert16_kernel<<<static_cast<unsigned>(ceil_div64(total, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, ld_src, dst, ld_dst, C, n_slots, src_dtype, dst_dtype);
+  return check_launch("convert16");
+}
 
 extern "C" int mmlf_bn_stats(const void* z, int ld, int C, int B, int H, int W, int act_dtype, double* sums,
                              void* stream) {

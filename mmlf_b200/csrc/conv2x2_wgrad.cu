@@ -198,6 +198,7 @@ extern "C" int mmlf_conv2x2_wgrad(const void* dout, int ld_dout, int n_pad, cons
                                   void* stream) {
   MMLF_REQUIRE(dout && act && workspace && dw, "wgrad: null buffer");
   MMLF_REQUIRE((act_dtype | dout_dtype) >> 1 == 0, "wgrad: dtype codes are 0 (bf16) or 1 (fp16)");
+  MMLF_REQUIRE(act_dtype == dout_dtype, "wgrad: both operands must share one 16-bit format (convert with mmlf_convert16)");
   MMLF_REQUIRE(n_pad % 16 == 0 && n_pad >= 16 && n_pad <= 320, "wgrad: n_pad %d must be a multiple of 16 in [16, 320]", n_pad);
   MMLF_REQUIRE(cin_pad % 16 == 0 && cin_pad >= 16 && cin_pad <= 320, "wgrad: cin_pad %d must be a multiple of 16 in [16, 320]", cin_pad);
   MMLF_REQUIRE(ld_dout % 8 == 0 && ld_act % 8 == 0 && ld_dout >= n_pad && ld_act >= cin_pad, "wgrad: bad row pitch");

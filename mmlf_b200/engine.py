@@ -316,10 +316,18 @@ class Engine:
         ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
         dwp = torch.empty(320 * 4 * 320, dtype=torch.float32, device=dev)
 
+        cvt = None
+        if self.act != GRAD:
+            cvt = torch.empty((geo.n_slots, max(cs.cin_pad for cs in self.all_convs())), dtype=_TORCH_DT[GRAD], device=dev)
+
         def conv_param_grads(cs, dout, ld_dout, act, ld_act):
-            """dW via the tcgen05 wgrad kernel, db via a column sum; accumulates for shared modules."""
+            """dW via the tcgen05 wgrad kernel, db via a column sum; accumulates for shared modules.  The wgrad GEMM
+            needs both operands in one 16-bit format, so fp16 activations are converted to bf16 first."""
+            if cvt is not None:
+                call('mmlf_convert16', _ptr(act), ld_act, self.act, _ptr(cvt), cs.cin_pad, GRAD, cs.cin_pad, geo.n_slots, st)
+                act, ld_act = cvt, cs.cin_pad
             call('mmlf_conv2x2_wgrad', _ptr(dout), ld_dout, cs.n_pad, _ptr(act), ld_act, cs.cin_pad, geo.B, geo.H,
-                 geo.W, cs.type, self.act, GRAD, _ptr(ws), _ptr(dwp), st)
+                 geo.W, cs.type, GRAD, GRAD, _ptr(ws), _ptr(dwp), st)
             wname, bname = cs.name + '.weight', cs.name + '.bias'
             acc = wname in grads
             if not acc:

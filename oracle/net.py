@@ -192,9 +192,10 @@ class FeedForwardOracle:
         else:
             gz = self._qg(gy * (rec['y'] > 0)) if rec['relu_out'] else gy
         w1, w2 = self._w(prefix + '.0.weight', grad=True), self._w(prefix + '.2.weight', grad=True)
-        ga1, gw2, gb2 = conv2x2_bwd(rec['a1'], w2, gz, 0)
+        # the weight-gradient GEMM reads its activation operand converted to the gradient format (bf16)
+        ga1, gw2, gb2 = conv2x2_bwd(self._qg(rec['a1']), w2, gz, 0)
         ga1 = self._qg(ga1 * (rec['a1'] > 0))
-        gx, gw1, gb1 = conv2x2_bwd(rec['x'], w1, ga1, 1)
+        gx, gw1, gb1 = conv2x2_bwd(self._qg(rec['x']), w1, ga1, 1)
         grads[prefix + '.0.weight'], grads[prefix + '.0.bias'] = gw1, gb1
         grads[prefix + '.2.weight'], grads[prefix + '.2.bias'] = gw2, gb2
         return (self._qg(gx) if need_gx else None), grads

@@ -211,6 +211,7 @@ def test_conv_dgrad_and_gate():
                                   (6, 40, 40, 280, 280, 1)])
 @pytest.mark.parametrize('act_dt', [0, 1])
 def test_conv_wgrad(case, act_dt):
+    """act_dt = 1: fp16 activations are converted to bf16 first (mixed-format MMA operands fault on B200)."""
     u = _u()
     rnd = u.ROUND[act_dt]
     B, H, W, cin, cout, ctype = case
@@ -226,11 +227,17 @@ def test_conv_wgrad(case, act_dt):
     w = np.zeros((cout, cin, 2, 2), np.float32)
     _, gw, gb = conv2x2_bwd(x, w, gout, 1 if ctype == 0 else 0)
     xs = u.to_slots(x, cin_pad, ctype == 1, Hp, Wp, act_dt)
+    if act_dt == u.FP16:
+        x = bf16_round(x)
+        _, gw, gb = conv2x2_bwd(x, w, gout, 1 if ctype == 0 else 0)
+        xb = torch.full_like(xs, float('nan'), dtype=torch.bfloat16)
+        u.call('mmlf_convert16', u.ptr(xs), cin_pad, u.FP16, u.ptr(xb), cin_pad, u.BF16, cin_pad, B * Hp * Wp, u.stream())
+        xs = xb
     gs = u.to_slots(gout, n_pad, ctype == 0, Hp, Wp)
     ws_bytes = u._lib.lib().mmlf_conv2x2_wgrad_workspace(n_pad, cin_pad)
     ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device='cuda')
     dwp = torch.full((n_pad, 4, cin_pad), float('nan'), dtype=torch.float32, device='cuda')
-    u.call('mmlf_conv2x2_wgrad', u.ptr(gs), n_pad, n_pad, u.ptr(xs), cin_pad, cin_pad, B, H, W, ctype, act_dt, u.BF16,
+    u.call('mmlf_conv2x2_wgrad', u.ptr(gs), n_pad, n_pad, u.ptr(xs), cin_pad, cin_pad, B, H, W, ctype, u.BF16, u.BF16,
            u.ptr(ws), u.ptr(dwp), u.stream())
     dw = torch.empty((cout, cin, 2, 2), dtype=torch.float32, device='cuda')
     u.call('mmlf_unpack_conv_wgrad', u.ptr(dwp), n_pad, cin_pad, cout, cin, 0, 1, cin, cin_pad, u.ptr(dw), 0, u.stream())
