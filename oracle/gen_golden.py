@@ -138,12 +138,12 @@ def _calibrate_bn(model, kw, seed, H, W):
             sd[k].copy_(t + 0.1 * T(rng.uniform(-1, 1, tuple(t.shape)).astype(np.float32)))
 
 
-def _run_net(kw, state_seed, B, H, W, in_seed, store_state, multimodal=False, sample_stride=None):
+def _run_net(kw, state_seed, B, H, W, in_seed, store_state, multimodal=False, sample_stride=None, wscale=2.0):
     torch.manual_seed(0)
     model = FeedForward(**kw)
     sd = model.state_dict()
     with torch.no_grad():
-        fx.perturb_state(sd, state_seed)
+        fx.perturb_state(sd, state_seed, wscale=wscale)
         _calibrate_bn(model, kw, state_seed, H, W)
     sd = model.state_dict()
     out = {}
@@ -207,7 +207,8 @@ def gen_net():
     save('net_full_base_cross.npz', **_run_net(kw, 13, 1, 16, 16, 33, store_state=False, sample_stride=97))
     # no-batchnorm topology (state_dict index 3 vanishes, feed_forward.py:132-135)
     kw = fx.model_kwargs('base', False, chs=8, model_no_batchnorm=True)
-    save('net_tiny_base_nobn.npz', **_run_net(kw, 11, 2, 20, 20, 21, store_state=True))
+    # without BN the scale of the activations is set by the weights alone: x2.8 keeps the output from collapsing
+    save('net_tiny_base_nobn.npz', **_run_net(kw, 11, 2, 20, 20, 21, store_state=True, wscale=2.8))
 
 
 # ---------------------------------------------------------------------------- losses

@@ -112,7 +112,7 @@ def perturb_state(state, seed, wscale=2.0):
     rng = np.random.RandomState(seed)
     for k in sorted(state.keys()):
         v = state[k]
-        is_bn = '.3.' in k
+        is_bn = k.split('.')[2] == '3'          # <net>.<block>.<index>.<name>: index 3 is the BatchNorm
         if k.endswith('num_batches_tracked'):
             continue
         shape = tuple(v.shape)
