@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""Benchmark of the MMLF hot path on B200 (driver contract: one JSON line on stdout from rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload train|infer] [--variant base|upr|dpp]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the CPU port of the reference algorithm (oracle/) on the host cores
+
+workload train (default): one training step of the 4-stream FeedForward model -- forward, masked loss, backward,
+gradient all-reduce, Adam -- on a global batch of 512 patches of 96 x 96 px, 9 views per stack (BASELINE.json
+configs[1]); the batch is sharded over the ranks (strong scaling: the global batch is fixed).
+workload infer: full-light-field inference, one 9x9-view 512 x 512 light field per rank and step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+import numpy as np  # noqa: E402
+
+FULL_KW = dict(model_ksize=2, model_in_blocks=3, model_out_blocks=8, model_chs=70, model_views=9, model_cross=False,
+               model_uncert=False, model_unet=False, model_discrete=False, model_no_batchnorm=False,
+               model_batchnorm_momentum=0.1, val_disp_min=-3.5, val_disp_max=3.5)
+
+
+def model_kwargs(variant):
+    kw = dict(FULL_KW)
+    kw.update(model_uncert=(variant == 'upr'), model_discrete=(variant == 'dpp'))
+    return kw
+
+
+# ----------------------------------------------------------------------------------------------- algorithmic work
+def conv_flops(B, H, W, cin, cout, ctype):
+    """2 * MACs of one nn.Conv2d(cin, cout, 2): type 0 = padding 1 -> (H+1)x(W+1) outputs, type 1 = padding 0."""
+    m = B * (H + 1) * (W + 1) if ctype == 0 else B * H * W
+    return 2.0 * m * cout * 4 * cin
+
+
+def net_forward_flops(B, H, W, variant, chs=70, views=9, streams=4, in_blocks=3, out_blocks=8):
+    oc = {'base': 1, 'upr': 2, 'dpp': streams * views * 3}[variant]
+    f = 0.0
+    for _ in range(streams):
+        cin = views * 3
+        for _k in range(in_blocks):
+            f += conv_flops(B, H, W, cin, chs, 0) + conv_flops(B, H, W, chs, chs, 1)
+            cin = chs
+    w = streams * chs
+    for _k in range(out_blocks - 1):
+        f += conv_flops(B, H, W, w, w, 0) + conv_flops(B, H, W, w, w, 1)
+    f += conv_flops(B, H, W, w, oc, 0) + conv_flops(B, H, W, oc, oc, 1)
+    return f
+
+
+def train_step_flops(B, H, W, variant):
+    """forward + weight gradients + data gradients (none for the first conv of each stream): SURVEY.md section 6."""
+    fwd = net_forward_flops(B, H, W, variant)
+    first = 4 * conv_flops(B, H, W, 27, 70, 0)
+    return 3.0 * fwd - first
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ts, line in self.lines:
+            if ts < t0 or ts > t1 + 0.3:
+                continue
+            p = [x.strip() for x in line.split(',')]
+            try:
+                sm.append(float(p[0]))
+                mx = max(mx, float(p[1]))
+            except (ValueError, IndexError):
+                continue
+            for nm, val in zip(names, p[3:7]):
+                if val.lower().startswith('active'):
+                    reasons.add(nm)
+        if not sm:
+            return None
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU baseline (oracle)
+def cpu_train_step(variant, b, ps, threads):
+    """One training step of the numpy port of the reference algorithm (oracle/): forward, loss, backward, Adam."""
+    import torch
+    import _fixtures as fx
+    import oracle
+    from oracle import losses as olosses
+    torch.set_num_threads(threads)
+    from mmlf_b200.model.feed_forward import FeedForward   # parameter containers only (same init as the reference)
+    torch.manual_seed(0)
+    state = {k: v.numpy().copy() for k, v in FeedForward(**model_kwargs(variant)).state_dict().items()}
+    net = oracle.FeedForwardOracle(state, model_uncert=(variant == 'upr'), model_discrete=(variant == 'dpp'))
+    net.training = True
+    rng = np.random.RandomState(0)
+    views = [rng.uniform(0, 1, (b, 9, 3, ps, ps)).astype(np.float32) for _ in range(4)]
+    gt = rng.uniform(-2, 2, (b, ps, ps)).astype(np.float32)
+    mask = fx.synth_mask(1, b, ps, ps, margin=11)
+    adam = {}
+
+    def step(it):
+        r = net.forward(*views, keep_tape=True)
+        if variant == 'upr':
+            _, g = olosses.improved_uncertainty_l1({'mean': r['mean'], 'logvar': r['logvar']}, gt, mask)
+            gout = np.stack([g['mean'], g['logvar']], 1)
+        elif variant == 'dpp':
+            _, g = olosses.masked_cross_entropy({'scores': r['scores']}, olosses.reg_to_class(gt, -3.5, 3.5, 108), mask)
+            gout = g['scores']
+        else:
+            _, g = olosses.masked_l1({'mean': r['mean']}, gt, mask)
+            gout = g['mean'][:, None]
+        grads = net.backward(gout)
+        for k, gr in grads.items():
+            m, v = adam.get(k, (np.zeros_like(net.p[k]), np.zeros_like(net.p[k])))
+            net.p[k], m, v = oracle.adam_step(net.p[k], gr.reshape(net.p[k].shape), m, v, it + 1, 1e-3)
+            adam[k] = (m, v)
+    return step
+
+
+def cpu_infer_step(variant, size, threads):
+    import torch
+    import oracle
+    torch.set_num_threads(threads)
+    from mmlf_b200.model.feed_forward import FeedForward
+    torch.manual_seed(0)
+    state = {k: v.numpy().copy() for k, v in FeedForward(**model_kwargs(variant)).state_dict().items()}
+    net = oracle.FeedForwardOracle(state, model_uncert=(variant == 'upr'), model_discrete=(variant == 'dpp'))
+    rng = np.random.RandomState(0)
+    views = [rng.uniform(0, 1, (1, 9, 3, size, size)).astype(np.float32) for _ in range(4)]
+    return lambda it: net.forward(*views)
+
+
+def run_cpu(args, steps, warmup):
+    """Times the oracle port on the host cores on a bounded sample of the workload."""
+    threads = os.cpu_count() or 1
+    if args.workload == 'train':
+        b = args.cpu_batch
+        step = cpu_train_step(args.variant, b, args.ps, threads)
+        units, unit, sample = b, 'patches/s', f'{b} patches of {args.ps} px per step (fwd + loss + bwd + Adam), fp32 numpy'
+    else:
+        size = args.cpu_size
+        step = cpu_infer_step(args.variant, size, threads)
+        units, unit = size * size / 1e6, 'Mpx/s'
+        sample = f'one {size}x{size} crop of a 9x9-view light field per step, fp32 numpy'
+    for i in range(warmup):
+        step(i)
+    t0 = time.time()
+    for i in range(steps):
+        step(warmup + i)
+    dt = (time.time() - t0) / max(steps, 1)
+    return {'value': units / dt, 'unit': unit, 'cores': threads, 'kind': 'port', 'sample': sample}, dt
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=8)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='train', choices=['train', 'infer'])
+    ap.add_argument('--variant', default='base', choices=['base', 'upr', 'dpp'])
+    ap.add_argument('--bs', type=int, default=512, help='global batch (train)')
+    ap.add_argument('--ps', type=int, default=96, help='patch size (train)')
+    ap.add_argument('--size', type=int, default=512, help='light-field size (infer)')
+    ap.add_argument('--precision', default='fp16', choices=['fp16', 'bf16'], help='activation storage format')
+    ap.add_argument('--cpu-batch', type=int, default=2)
+    ap.add_argument('--cpu-size', type=int, default=128)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    metric = ('train patches/s (bs512, 96px)' if args.workload == 'train' else 'full-LF inference Mpx/s')
+    unit = 'patches/s' if args.workload == 'train' else 'Mpx/s'
+    config = {'workload': (f'{args.variant.upper()} training step bs={args.bs} ps={args.ps}, 4-stream FeedForward '
+                           f'(9 views, 70 ch, 108 bins), fwd+loss+bwd+allreduce+Adam' if args.workload == 'train' else
+                           f'{args.variant.upper()} full-LF inference, one 9x9-view {args.size}x{args.size} light field '
+                           f'per GPU and step'),
+              'global_batch': args.bs if args.workload == 'train' else world,
+              'parallelism': f'dp{world}', 'l2': 'inputs larger than L2 (>= 113 MB fp32 per step and GPU)',
+              'activation_storage': args.precision, 'gradient_storage': 'bf16', 'accumulate': 'fp32'}
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        base, dt = run_cpu(args, max(args.steps, 1), min(args.warmup, 1))
+        line = {'impl': 'reference', 'metric': metric, 'value': base['value'], 'unit': unit, 'n_gpus': world,
+                'steps': args.steps, 'warmup': min(args.warmup, 1), 'ms_per_step': dt * 1e3, 'higher_is_better': True,
+                'scaling': 'strong' if args.workload == 'train' else 'weak', 'vs_baseline': None, 'dtype': 'f32',
+                'data': 'synthetic', 'config': config, 'cpu_baseline': base,
+                'e2e': {'value': base['value'], 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+                'gpu_launches': 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from mmlf_b200 import _lib, parallel
+    from mmlf_b200.model.feed_forward import FeedForward
+    from mmlf_b200.model import loss as L
+    from mmlf_b200.optim import FusedAdam
+    from mmlf_b200.utils import dl
+
+    rank, world, local = parallel.init_from_env('nccl')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    torch.manual_seed(0)
+    model = FeedForward(**model_kwargs(args.variant)).to(dev)
+    model.precision = args.precision
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if args.workload == 'train':
+        B = args.bs // world
+        H = W = args.ps
+        views = [torch.rand((B, 9, 3, H, W), device=dev, generator=gen) for _ in range(4)]
+        gt = torch.rand((B, H, W), device=dev, generator=gen) * 4 - 2
+        mask = L.create_mask_margin((B, H, W), 11).to(torch.int32).to(dev)
+        opt = FusedAdam(model.parameters(), lr=1e-3)
+        loss_fn = {'base': L.MaskedL1Loss(), 'upr': L.ImprovedUncertaintyL1Loss(), 'dpp': L.MaskedCrossEntropy()}[args.variant]
+        model.train()
+
+        def step(vs, gt_, mask_):
+            opt.zero_grad()
+            out = model(*vs)
+            if args.variant == 'dpp':
+                tgt = dl.reg_to_class(gt_, -3.5, 3.5, model.steps)
+                lossv = loss_fn(out, tgt, mask_)
+            else:
+                lossv = loss_fn(out, gt_, mask_)
+            lossv.backward()
+            parallel.all_reduce_sum_(opt.flat_grad)          # DataParallel's reduce-add (train/cli.py:159)
+            opt.step()
+            return lossv
+        units_per_step = args.bs
+        flops_per_step = train_step_flops(args.bs, H, W, args.variant)
+        host = [t.cpu().pin_memory() for t in views + [gt, mask]]
+    else:
+        B, H, W = 1, args.size, args.size
+        views = [torch.rand((B, 9, 3, H, W), device=dev, generator=gen) for _ in range(4)]
+        model.eval()
+
+        def step(vs, gt_=None, mask_=None):
+            with torch.no_grad():
+                out = model(*vs)
+                _ = out['mean']
+                if args.variant != 'base':
+                    _ = out['posterior']
+            return out['mean']
+        units_per_step = world * H * W / 1e6
+        flops_per_step = world * net_forward_flops(1, H, W, args.variant)
+        host = [t.cpu().pin_memory() for t in views]
+        gt = mask = None
+
+    # ---------------- warm-up
+    for _ in range(args.warmup):
+        step(views, gt, mask)
+    barrier()
+
+    # ---------------- timed region: inputs resident in HBM, CUDA events, max over ranks
+    sampler = ClockSampler(local) if rank == 0 else None
+    _lib.launch_count = 0
+    _lib.set_profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        step(views, gt, mask)
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    prof = _lib.set_profile(False)
+    launches = _lib.launch_count
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = ms.item() / args.steps
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+
+    # ---------------- per-kernel shares and the roofline of the dominant kernel (the tcgen05 conv)
+    by_name = {}
+    for name, a, b in prof:
+        by_name.setdefault(name, []).append(a.elapsed_time(b))
+    shares = {k: sum(v) / args.steps for k, v in by_name.items()}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except OSError:
+        pass
+    peak_tf, peak_src = peaks.get('bf16_tflops_sustained'), 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)'
+    if not peak_tf:
+        peak_tf, peak_src = 1400.0, 'fallback (B200_PROFILING.md: sustained ~1.4 PFLOP/s)'
+    conv_ms = by_name.get('mmlf_conv2x2', [])
+    wgrad_ms = by_name.get('mmlf_conv2x2_wgrad', [])
+    n_conv = len(conv_ms) / args.steps
+    # algorithmic flops of all conv2x2 launches of one step on this rank: forward convs + data gradients
+    Bl = B
+    fwd = net_forward_flops(Bl, H, W, args.variant)
+    if args.workload == 'train':
+        conv_flops_rank = 2.0 * fwd - 4 * conv_flops(Bl, H, W, 27, 70, 0)
+        # the small head convs of BASE / UPR run partly on CUDA cores: negligible (< 0.1 %)
+    else:
+        conv_flops_rank = fwd
+    conv_time = sum(conv_ms) / args.steps / 1e3
+    achieved = conv_flops_rank / conv_time / 1e12 if conv_time > 0 else 0.0
+    roofline = {'kernel': 'conv2x2_tc_kernel (all forward + data-gradient launches of a step)', 'bound': 'tensor',
+                'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
+                'peak_source': peak_src, 'traffic': None, 'launches_per_step': n_conv,
+                'avg_launch_ms': (sum(conv_ms) / len(conv_ms)) if conv_ms else None,
+                'share_of_step': conv_time * 1e3 / ms_per_step}
+    if wgrad_ms:
+        wg_time = sum(wgrad_ms) / args.steps / 1e3
+        wg_flops = fwd                                        # weight gradients cost one forward's worth of MACs
+        roofline['wgrad'] = {'kernel': 'conv2x2_wgrad_kernel + reduce', 'achieved': wg_flops / wg_time / 1e12,
+                             'frac': wg_flops / wg_time / 1e12 / peak_tf, 'share_of_step': wg_time * 1e3 / ms_per_step}
+    roofline['step'] = {'achieved': flops_per_step / world / (ms_per_step / 1e3) / 1e12,
+                        'frac': flops_per_step / world / (ms_per_step / 1e3) / 1e12 / peak_tf,
+                        'note': 'whole step, algorithmic FLOPs of SURVEY.md section 6 per GPU'}
+
+    # ---------------- end to end: host (pinned) inputs copied in every step, loss read back every step
+    copy_stream = torch.cuda.Stream()
+    bufs = [[torch.empty_like(t, device=dev) for t in host] for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    h2d = sum(t.numel() * t.element_size() for t in host)
+
+    def upload(slot):
+        with torch.cuda.stream(copy_stream):
+            for d, s in zip(bufs[slot], host):
+                d.copy_(s, non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    e2e_steps = max(3, min(args.steps, 5))
+    barrier()
+    upload(0)
+    e0.record()
+    d2h = 0
+    for i in range(e2e_steps):
+        slot = i & 1
+        torch.cuda.current_stream().wait_event(ready[slot])
+        if i + 1 < e2e_steps:
+            copy_stream.wait_stream(torch.cuda.current_stream()) if i >= 1 else None
+            upload(slot ^ 1)
+        cur = bufs[slot]
+        res = step(cur[:4], cur[4] if len(cur) > 4 else None, cur[5] if len(cur) > 5 else None)
+        if args.workload == 'train':
+            _ = res.item()
+            d2h = 4
+        else:
+            _ = res.cpu()
+            d2h = res.numel() * 4
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e = {'value': units_per_step / (ms2.item() / e2e_steps / 1e3), 'unit': unit, 'h2d_bytes_per_step': h2d * world,
+           'd2h_bytes_per_step': d2h * world, 'steps': e2e_steps,
+           'note': 'pinned host inputs, double-buffered H2D on a copy stream, result read back every step'}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu_base = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_base, _ = run_cpu(args, 2, 1)
+    line = {'metric': metric, 'value': units_per_step / (ms_per_step / 1e3), 'unit': unit, 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
+            'scaling': 'strong' if args.workload == 'train' else 'weak', 'vs_baseline': None,
+            'dtype': args.precision + ' storage / fp32 accumulate', 'data': 'synthetic', 'config': config,
+            'roofline': roofline, 'cpu_baseline': cpu_base, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
+            'kernel_ms_per_step': {k: round(v, 3) for k, v in sorted(shares.items(), key=lambda kv: -kv[1])}}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -86,12 +86,37 @@ def lib():
     return _lib
 
 
+# kernels launched per C-ABI call (for the launch count reported by bench.py)
+_KERNELS_PER_CALL = {'mmlf_conv2x2_wgrad': 2, 'mmlf_bn_bwd_apply': 2, 'mmlf_head_small_bwd': 2, 'mmlf_shift_taps': 0}
+launch_count = 0
+_profile = None          # when set to a list, call() appends (name, start_event, end_event)
+
+
+def set_profile(enabled):
+    """Record a CUDA-event pair around every C-ABI call on the current stream (used by bench.py for the per-kernel
+    time shares).  Returns the previous record list."""
+    global _profile
+    old = _profile
+    _profile = [] if enabled else None
+    return old
+
+
 def call(name, *args):
     """Call an ``int``-returning entry point and raise with the library's error text on failure."""
+    global launch_count
     l = lib()
-    rc = getattr(l, name)(*args)
+    if _profile is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(l, name)(*args)
+        e1.record()
+        _profile.append((name, e0, e1))
+    else:
+        rc = getattr(l, name)(*args)
     if rc != 0:
         raise RuntimeError(f'{name} failed ({rc}): {l.mmlf_last_error().decode()}')
+    launch_count += _KERNELS_PER_CALL.get(name, 1)
 
 
 BF16, FP16 = 0, 1        # MMLF_BF16 / MMLF_FP16 storage codes
