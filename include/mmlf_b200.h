@@ -167,11 +167,11 @@ int mmlf_bn_bwd_reduce(const void* dy, int ld_dy, const void* y, int ld_y, const
                        const float* save_mean, const float* save_invstd, int C, int B, int H, int W, int grad_dtype,
                        int act_dtype, double* sums, void* stream);
 /* Pass 2: dz = gamma * invstd * (g - sum_g / count - xhat * sum_gx / count) (bf16, halo zero);
- * dgamma = sum_gx, dbeta = sum_g (f32 [C]).  train = 0 gives the eval-mode gradient dz = g * gamma * invstd. */
+ * dgamma = sum_gx, dbeta = sum_g (f32 [C_real]).  fsums: f32 scratch [2 * C].  train = 0 gives the eval-mode gradient dz = g * gamma * invstd. */
 int mmlf_bn_bwd_apply(const void* dy, int ld_dy, const void* y, int ld_y, const void* z, int ld_z,
                       const float* gamma, const float* save_mean, const float* save_invstd, const double* sums,
                       int64_t count, int train, int C_real, int C, int B, int H, int W, int grad_dtype, int act_dtype,
-                      void* dz, int ld_dz, float* dgamma, float* dbeta, void* stream);
+                      void* dz, int ld_dz, float* dgamma, float* dbeta, float* fsums, void* stream);
 
 /* ReLU backward alone (blocks without BatchNorm): dz = dy * (y > 0), bf16 slots. */
 int mmlf_relu_bwd(const void* dy, int ld_dy, const void* y, int ld_y, int C, int64_t n_slots, int grad_dtype,

@@ -48,7 +48,7 @@ _PROTOS = {
     'mmlf_bn_apply_relu': (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_p]),
     'mmlf_bn_bwd_reduce': (c_i, [c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     'mmlf_bn_bwd_apply': (c_i, [c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_i64, c_i, c_i, c_i, c_i, c_i,
-                                c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_p]),
+                                c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p]),
     'mmlf_relu_bwd': (c_i, [c_p, c_i, c_p, c_i, c_i, c_i64, c_i, c_i, c_p, c_i, c_p]),
     'mmlf_head_small': (c_i, [c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_i, c_p, c_p]),
     'mmlf_head_small_bwd': (c_i, [c_p, c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_p]),

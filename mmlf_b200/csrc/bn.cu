@@ -154,7 +154,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256)
 slot_map_kernel(const void* __restrict__ a, int ld_a, const void* __restrict__ y, int ld_y,
                 const void* __restrict__ z, int ld_z, const float* __restrict__ p0, const float* __restrict__ p1,
-                const float* __restrict__ p2, const double* __restrict__ sums, double inv_count, int C, int Hp, int Wp,
+                const float* __restrict__ p2, const float* __restrict__ fsums, int C, int Hp, int Wp,
                 int64_t n_slots, void* __restrict__ out, int ld_out, int dt_a, int dt_yz) {
   const int groups = C >> 3;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -190,9 +190,9 @@ slot_map_kernel(const void* __restrict__ a, int ld_a, const void* __restrict__ y
           r[j] = g * k;
         } else {
           const float xhat = (zv[j] - p1[c + j]) * p2[c + j];
-          const float mg = static_cast<float>(sums[c + j] * inv_count);
-          const float mgx = static_cast<float>(sums[C + c + j] * inv_count);
-          r[j] = k * (g - mg - xhat * mgx);
+          // fsums = {mean(g), mean(g * xhat)} per channel in fp32, prepared by bn_bwd_means_kernel (fp64 math per
+          // element would run at the 1/64-rate fp64 pipe)
+          r[j] = k * (g - fsums[c + j] - xhat * fsums[C + c + j]);
         }
       }
     }
@@ -200,12 +200,17 @@ slot_map_kernel(const void* __restrict__ a, int ld_a, const void* __restrict__ y
   st8(out, s, ld_out, c, pack8(r, dt_a));
 }
 
-__global__ void bn_param_grads_kernel(const double* __restrict__ sums, int C_real, int C, float* __restrict__ dgamma,
-                                      float* __restrict__ dbeta) {
+// per-channel means of the two backward reductions in fp32 (+ the parameter gradients dgamma = sum g*xhat, dbeta = sum g)
+__global__ void bn_bwd_means_kernel(const double* __restrict__ sums, double inv_count, int C_real, int C,
+                                    float* __restrict__ fsums, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C_real) return;
-  dbeta[c] = static_cast<float>(sums[c]);
-  dgamma[c] = static_cast<float>(sums[C + c]);
+  if (c >= C) return;
+  fsums[c] = static_cast<float>(sums[c] * inv_count);
+  fsums[C + c] = static_cast<float>(sums[C + c] * inv_count);
+  if (c < C_real && dgamma && dbeta) {
+    dbeta[c] = static_cast<float>(sums[c]);
+    dgamma[c] = static_cast<float>(sums[C + c]);
+  }
 }
 
 // 16-bit format conversion of a slot array (fp16 activations -> bf16 operand of the weight-gradient GEMM, whose two
@@ -300,7 +305,7 @@ extern "C" int mmlf_bn_apply_relu(const void* z, int ld_z, const float* scale, c
   const int64_t n_slots = static_cast<int64_t>(B) * (H + 1) * (W + 1);
   const int64_t total = n_slots * (C / 8);
   slot_map_kernel<0><<<static_cast<unsigned>(ceil_div64(total, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      z, ld_z, nullptr, 0, nullptr, 0, scale, shift, nullptr, nullptr, 0.0, C, H + 1, W + 1, n_slots, y, ld_y, act_dtype,
+      z, ld_z, nullptr, 0, nullptr, 0, scale, shift, nullptr, nullptr, C, H + 1, W + 1, n_slots, y, ld_y, act_dtype,
       act_dtype);
   return check_launch("bn_apply_relu");
 }
@@ -311,7 +316,7 @@ extern "C" int mmlf_relu_bwd(const void* dy, int ld_dy, const void* y, int ld_y,
   CHECK_C(C);
   const int64_t total = n_slots * (C / 8);
   slot_map_kernel<1><<<static_cast<unsigned>(ceil_div64(total, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      dy, ld_dy, y, ld_y, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0.0, C, 1, 1, n_slots, dz, ld_dz, grad_dtype,
+      dy, ld_dy, y, ld_y, nullptr, 0, nullptr, nullptr, nullptr, nullptr, C, 1, 1, n_slots, dz, ld_dz, grad_dtype,
       act_dtype);
   return check_launch("relu_bwd");
 }
@@ -333,24 +338,22 @@ extern "C" int mmlf_bn_bwd_apply(const void* dy, int ld_dy, const void* y, int l
                                  const float* gamma, const float* save_mean, const float* save_invstd,
                                  const double* sums, int64_t count, int train, int C_real, int C, int B, int H, int W,
                                  int grad_dtype, int act_dtype, void* dz, int ld_dz, float* dgamma, float* dbeta,
-                                 void* stream) {
+                                 float* fsums, void* stream) {
   MMLF_REQUIRE(dy && y && z && gamma && save_mean && save_invstd && sums && dz, "bn_bwd_apply: null buffer");
   CHECK_C(C);
   const int64_t n_slots = static_cast<int64_t>(B) * (H + 1) * (W + 1);
   const int64_t total = n_slots * (C / 8);
   const unsigned blocks = static_cast<unsigned>(ceil_div64(total, 256));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MMLF_REQUIRE(fsums != nullptr, "bn_bwd_apply: fsums scratch (float[2*C]) required");
+  bn_bwd_means_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, 1.0 / static_cast<double>(count), C_real, C, fsums, dgamma,
+                                                         dbeta);
+  if (int rc = check_launch("bn_bwd_means")) return rc;
   if (train)
-    slot_map_kernel<2><<<blocks, 256, 0, st>>>(dy, ld_dy, y, ld_y, z, ld_z, gamma, save_mean, save_invstd, sums,
-                                               1.0 / static_cast<double>(count), C, H + 1, W + 1, n_slots, dz, ld_dz,
-                                               grad_dtype, act_dtype);
+    slot_map_kernel<2><<<blocks, 256, 0, st>>>(dy, ld_dy, y, ld_y, z, ld_z, gamma, save_mean, save_invstd, fsums, C,
+                                               H + 1, W + 1, n_slots, dz, ld_dz, grad_dtype, act_dtype);
   else
-    slot_map_kernel<3><<<blocks, 256, 0, st>>>(dy, ld_dy, y, ld_y, z, ld_z, gamma, save_mean, save_invstd, sums, 0.0,
-                                               C, H + 1, W + 1, n_slots, dz, ld_dz, grad_dtype, act_dtype);
-  if (int rc = check_launch("bn_bwd_apply")) return rc;
-  if (dgamma && dbeta) {
-    bn_param_grads_kernel<<<ceil_div(C_real, 128), 128, 0, st>>>(sums, C_real, C, dgamma, dbeta);
-    return check_launch("bn_param_grads");
-  }
-  return 0;
+    slot_map_kernel<3><<<blocks, 256, 0, st>>>(dy, ld_dy, y, ld_y, z, ld_z, gamma, save_mean, save_invstd, fsums, C,
+                                               H + 1, W + 1, n_slots, dz, ld_dz, grad_dtype, act_dtype);
+  return check_launch("bn_bwd_apply");
 }

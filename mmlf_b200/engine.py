@@ -376,11 +376,12 @@ class Engine:
                      _ptr(sums), st)
                 gpad, _ = self._bn_padded(bnp, C_real, Cp, dev)
                 acc = bnp + '.weight' in grads
+                fsums = torch.empty(2 * Cp, dtype=torch.float32, device=dev)
                 dgam = torch.empty(C_real, dtype=torch.float32, device=dev)
                 dbet = torch.empty(C_real, dtype=torch.float32, device=dev)
                 call('mmlf_bn_bwd_apply', _ptr(gy), ld_gy, _ptr(rec['y']), rec['ld_y'], _ptr(rec['z']), Cp, _ptr(gpad),
                      _ptr(rec['save_mean']), _ptr(rec['save_invstd']), _ptr(sums), geo.count, 1, C_real, Cp, geo.B,
-                     geo.H, geo.W, GRAD, self.act, _ptr(dz), Cp, _ptr(dgam), _ptr(dbet), st)
+                     geo.H, geo.W, GRAD, self.act, _ptr(dz), Cp, _ptr(dgam), _ptr(dbet), _ptr(fsums), st)
                 if acc:
                     grads[bnp + '.weight'] += dgam
                     grads[bnp + '.bias'] += dbet

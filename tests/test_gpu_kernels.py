@@ -320,7 +320,8 @@ def test_bn_train_roundtrip():
     dz = torch.full((B * Hp * Wp, Cp), float('nan'), dtype=torch.bfloat16, device='cuda')
     dgam, dbet = torch.empty(Cr, device='cuda'), torch.empty(Cr, device='cuda')
     u.call('mmlf_bn_bwd_apply', u.ptr(gys), Cp, u.ptr(y), Cp, u.ptr(zs), Cp, u.ptr(gpad), u.ptr(smean), u.ptr(sinv),
-           u.ptr(bs), n, 1, Cr, Cp, B, H, W, G, A, u.ptr(dz), Cp, u.ptr(dgam), u.ptr(dbet), u.stream())
+           u.ptr(bs), n, 1, Cr, Cp, B, H, W, G, A, u.ptr(dz), Cp, u.ptr(dgam), u.ptr(dbet), u.ptr(torch.empty(2 * Cp, device='cuda')),
+           u.stream())
     torch.cuda.synchronize()
     yq = full[:, 1:, 1:, :Cr]
     g = gy * (yq > 0)
