@@ -13,6 +13,8 @@
 //               quadrant each).  Persistent CTAs, static round-robin over 128-slot tiles.
 #include "../../include/mmlf_b200.h"
 #include "common.cuh"
+#include <stdlib.h>
+
 #include "host_util.h"
 
 namespace mmlf {
@@ -251,6 +253,164 @@ conv2x2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// CTA-pair version (cta_group::2): two SMs of a cluster compute one 256-slot tile.  Each CTA loads its own 128 A rows
+// and HALF of the weight rows of every MMA (the hardware reads the other half from the peer's shared memory), which
+// halves the dominant shared-memory fill traffic (the weights are re-streamed from L2 for every tile).  The leader CTA
+// (cluster rank 0) issues all MMAs; both CTAs run a TMA producer and a 128-row epilogue out of their own TMEM.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
+conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                   const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (tiles_addr - raw_addr);
+  const uint32_t b_bytes = static_cast<uint32_t>(p.n_pad) * 64u;          // half of the weight rows per CTA
+  const uint32_t stage_bytes = kABytes + b_bytes;
+
+  uint8_t* aux = smem + static_cast<size_t>(p.stages) * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full_bar = empty_bar + kMaxStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 1;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 1);
+  float* s_bias = reinterpret_cast<float*>(tmem_ptr_smem + 4);
+  float* s_scale = s_bias + p.n_pad;
+  float* s_shift = s_scale + p.n_pad;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < p.stages; ++i) {
+        mbar_init(smem_u32(&full_bar[i]), 1);          // leader: one arrive.expect_tx covering both CTAs' bytes
+        mbar_init(smem_u32(&empty_bar[i]), 1);         // one multicast commit from the leader's MMA thread
+      }
+      mbar_init(smem_u32(tmem_full_bar), 1);
+      mbar_init(smem_u32(tmem_empty_bar), 8);          // leader: one elected lane of the 4 epilogue warps of both CTAs
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc_pair(smem_u32(tmem_ptr_smem), kTmemCols);
+  }
+  for (int i = threadIdx.x; i < p.n_pad; i += kConvThreads) {
+    s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    s_scale[i] = p.scale ? p.scale[i] : 1.f;
+    s_shift[i] = p.shift ? p.shift[i] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();                                      // peer barriers are initialised before any remote arrive
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const int half_rows = p.n_part >> 1;                 // weight rows each CTA supplies per MMA
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = pair; tile < p.num_tiles; tile += n_pairs) {
+        const int row0 = tile * (2 * kTileM) + static_cast<int>(rank) * kTileM;
+        for (int tap = 0; tap < 4; ++tap) {
+          for (int kc = 0; kc < p.n_kc; ++kc) {
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+            const uint32_t fb = smem_u32(&full_bar[stage]);
+            if (leader) mbar_arrive_expect_tx(fb, 2 * stage_bytes);
+            const uint32_t a_dst = tiles_addr + stage * stage_bytes;
+            tma_load_2d_pair(a_dst, &tmap_a, fb, kc * 64, row0 + p.tap_off[tap], kEvictNormal);
+            const uint32_t b_dst = a_dst + kABytes;
+            const int kcol = (tap * p.n_kc + kc) * 64;
+            for (int part = 0; part < p.n_parts; ++part)
+              tma_load_2d_pair(b_dst + part * half_rows * 128, &tmap_b, fb, kcol,
+                               part * p.n_part + static_cast<int>(rank) * half_rows, kEvictLast);
+            if (++stage == static_cast<uint32_t>(p.stages)) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      const uint32_t idesc = make_idesc_16(2 * kTileM, p.n_part, 0, 0, p.ab_dtype, p.ab_dtype);
+      uint32_t stage = 0, phase = 0, tphase = 0;
+      for (int tile = pair; tile < p.num_tiles; tile += n_pairs) {
+        mbar_wait(smem_u32(tmem_empty_bar), tphase ^ 1u);
+        tc_fence_after();
+        uint32_t accumulate = 0;
+        for (int tap = 0; tap < 4; ++tap) {
+          for (int kc = 0; kc < p.n_kc; ++kc) {
+            mbar_wait(smem_u32(&full_bar[stage]), phase);
+            tc_fence_after();
+            const uint32_t a_addr = tiles_addr + stage * stage_bytes;
+            const uint32_t b_addr = a_addr + kABytes;
+            const int ksteps = (kc == p.n_kc - 1) ? p.last_ksteps : 4;
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t adesc = make_sw128_desc(a_addr + k * 32, 0, 1024);
+              for (int part = 0; part < p.n_parts; ++part) {
+                const uint64_t bdesc = make_sw128_desc(b_addr + part * half_rows * 128 + k * 32, 0, 1024);
+                umma_f16_pair(tmem_base + part * p.n_part, adesc, bdesc, idesc, accumulate);
+              }
+              accumulate = 1;
+            }
+            umma_commit_pair(smem_u32(&empty_bar[stage]));
+            if (++stage == static_cast<uint32_t>(p.stages)) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+        umma_commit_pair(smem_u32(tmem_full_bar));
+        tphase ^= 1u;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    uint32_t tphase = 0;
+    const float* eb = p.bias ? s_bias : nullptr;
+    const float* es = p.scale ? s_scale : nullptr;
+    for (int tile = pair; tile < p.num_tiles; tile += n_pairs) {
+      mbar_wait(smem_u32(tmem_full_bar), tphase);
+      tc_fence_after();
+      const int64_t s = static_cast<int64_t>(tile) * (2 * kTileM) + rank * kTileM + q * 32 + lane;
+      const bool in_range = s < p.n_slots;
+      int b = 0, sy = 0, sx = 0;
+      if (in_range) slot_coords(p, s, b, sy, sx);
+      const bool valid = in_range && (p.type == 0 || (sy >= 1 && sx >= 1));
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+      for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c0, r);
+        tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        epilogue_store16(p, eb, es, s_shift, s, in_range, valid, b, sy, sx, c0, v);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(smem_u32(tmem_empty_bar));
+      tphase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();                                      // nobody leaves while the peer may still touch its memory
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // CUDA-core cross-check kernel: one thread per (slot, 16 output channels); fp32 FMA over the same bf16 operands.
 __global__ void conv2x2_simt_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, int cin_pad,
                                     const __nv_bfloat16* __restrict__ wpack, int k_total, const ConvParams p) {
@@ -336,10 +496,21 @@ static int fill_params(const mmlf_conv_args* a, ConvParams& p) {
 
 using namespace mmlf;
 
+static int conv_impl() {
+  // MMLF_CONV_IMPL=1cta selects the single-CTA kernel (debugging); default is the CTA-pair kernel
+  static int impl = -1;
+  if (impl < 0) {
+    const char* e = getenv("MMLF_CONV_IMPL");
+    impl = (e && e[0] == '1') ? 1 : 2;
+  }
+  return impl;
+}
+
 extern "C" int mmlf_conv2x2(const mmlf_conv_args* a, void* stream) {
   ConvParams p;
   if (int rc = fill_params(a, p)) return rc;
-  const uint32_t stage_bytes = kABytes + p.n_pad * 128;
+  const bool pair = conv_impl() == 2;
+  const uint32_t stage_bytes = kABytes + (pair ? p.n_pad * 64 : p.n_pad * 128);
   const uint32_t aux_bytes = (2 * kMaxStages + 2) * 8 + 16 + 3 * p.n_pad * 4 + 64;
   const uint32_t max_smem = 232448;   // 227 KB opt-in limit per CTA on sm_100
   int stages = static_cast<int>((max_smem - 1024 - aux_bytes) / stage_bytes);
@@ -352,13 +523,23 @@ extern "C" int mmlf_conv2x2(const mmlf_conv_args* a, void* stream) {
   if (int rc = make_tmap_2d_bf16(&tmap_a, a->in, a->cin_pad, p.n_slots, static_cast<uint64_t>(a->ld_in) * 2, 64, kTileM))
     return rc;
   const uint64_t k_total = static_cast<uint64_t>(4) * p.n_kc * 64;
-  if (int rc = make_tmap_2d_bf16(&tmap_b, a->wpack, k_total, p.n_pad, k_total * 2, 64, p.b_box_rows)) return rc;
+  const uint32_t b_rows = pair ? p.n_part / 2 : p.b_box_rows;
+  if (int rc = make_tmap_2d_bf16(&tmap_b, a->wpack, k_total, p.n_pad, k_total * 2, 64, b_rows)) return rc;
 
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv2x2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv2x2_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     MMLF_REQUIRE(e == cudaSuccess, "conv2x2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
+  }
+  if (pair) {
+    p.num_tiles = static_cast<int>(ceil_div64(p.n_slots, 2 * kTileM));
+    const int max_pairs = sm_count() / 2;
+    const int pairs = p.num_tiles < max_pairs ? p.num_tiles : max_pairs;
+    conv2x2_tc2_kernel<<<2 * pairs, kConvThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmap_a, tmap_b, p);
+    return check_launch("conv2x2_tc2_kernel");
   }
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   conv2x2_tc_kernel<<<grid, kConvThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmap_a, tmap_b, p);
