@@ -257,6 +257,11 @@ conv2x2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 // and HALF of the weight rows of every MMA (the hardware reads the other half from the peer's shared memory), which
 // halves the dominant shared-memory fill traffic (the weights are re-streamed from L2 for every tile).  The leader CTA
 // (cluster rank 0) issues all MMAs; both CTAs run a TMA producer and a 128-row epilogue out of their own TMEM.
+//
+// TMEM plan: consecutive tiles alternate between two accumulator regions so that the epilogue of tile t overlaps the
+// MMAs of tile t+1.  Two 288-column accumulators do not fit into 512 columns, so the regions are [0, n_pad) and
+// [512 - n_pad, 512) and share `ovl` = 2 * n_pad - 512 columns; the epilogue drains the shared columns first and
+// releases them through a separate barrier, after which the next tile's MMAs may start.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const ConvParams p) {
@@ -270,9 +275,10 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   uint8_t* aux = smem + static_cast<size_t>(p.stages) * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
   uint64_t* empty_bar = full_bar + kMaxStages;
-  uint64_t* tmem_full_bar = empty_bar + kMaxStages;
-  uint64_t* tmem_empty_bar = tmem_full_bar + 1;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + kMaxStages;      // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;          // [2], leader's copy is used
+  uint64_t* tmem_ovl_bar = tmem_empty_bar + 2;           // leader's copy is used
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_ovl_bar + 1);
   float* s_bias = reinterpret_cast<float*>(tmem_ptr_smem + 4);
   float* s_scale = s_bias + p.n_pad;
   float* s_shift = s_scale + p.n_pad;
@@ -282,6 +288,8 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const bool leader = rank == 0;
+  const int base1 = p.n_pad > 256 ? 512 - p.n_pad : 256;      // TMEM column base of odd tiles
+  const int ovl = p.n_pad > 256 ? 2 * p.n_pad - 512 : 0;      // columns shared by the two regions (multiple of 32)
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -293,8 +301,11 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         mbar_init(smem_u32(&full_bar[i]), 1);          // leader: one arrive.expect_tx covering both CTAs' bytes
         mbar_init(smem_u32(&empty_bar[i]), 1);         // one multicast commit from the leader's MMA thread
       }
-      mbar_init(smem_u32(tmem_full_bar), 1);
-      mbar_init(smem_u32(tmem_empty_bar), 8);          // leader: one elected lane of the 4 epilogue warps of both CTAs
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(smem_u32(&tmem_full_bar[i]), 1);
+        mbar_init(smem_u32(&tmem_empty_bar[i]), 8);    // one elected lane of the 4 epilogue warps of both CTAs
+      }
+      mbar_init(smem_u32(tmem_ovl_bar), 8);
       fence_barrier_init();
     }
     __syncwarp();
@@ -340,10 +351,14 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   } else if (warp == 1) {
     if (leader && lane == 0) {
       const uint32_t idesc = make_idesc_16(2 * kTileM, p.n_part, 0, 0, p.ab_dtype, p.ab_dtype);
-      uint32_t stage = 0, phase = 0, tphase = 0;
-      for (int tile = pair; tile < p.num_tiles; tile += n_pairs) {
-        mbar_wait(smem_u32(tmem_empty_bar), tphase ^ 1u);
+      uint32_t stage = 0, phase = 0;
+      int it = 0;
+      for (int tile = pair; tile < p.num_tiles; tile += n_pairs, ++it) {
+        const int par = it & 1;
+        mbar_wait(smem_u32(&tmem_empty_bar[par]), ((it >> 1) & 1) ^ 1u);   // region drained (tile it - 2)
+        if (ovl > 0 && it > 0) mbar_wait(smem_u32(tmem_ovl_bar), (it - 1) & 1);   // shared columns drained (tile it - 1)
         tc_fence_after();
+        const uint32_t acc_base = tmem_base + (par ? base1 : 0);
         uint32_t accumulate = 0;
         for (int tap = 0; tap < 4; ++tap) {
           for (int kc = 0; kc < p.n_kc; ++kc) {
@@ -356,7 +371,7 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               const uint64_t adesc = make_sw128_desc(a_addr + k * 32, 0, 1024);
               for (int part = 0; part < p.n_parts; ++part) {
                 const uint64_t bdesc = make_sw128_desc(b_addr + part * half_rows * 128 + k * 32, 0, 1024);
-                umma_f16_pair(tmem_base + part * p.n_part, adesc, bdesc, idesc, accumulate);
+                umma_f16_pair(acc_base + part * p.n_part, adesc, bdesc, idesc, accumulate);
               }
               accumulate = 1;
             }
@@ -367,37 +382,61 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             }
           }
         }
-        umma_commit_pair(smem_u32(tmem_full_bar));
-        tphase ^= 1u;
+        umma_commit_pair(smem_u32(&tmem_full_bar[par]));
       }
     }
   } else {
     const int q = warp & 3;
-    uint32_t tphase = 0;
     const float* eb = p.bias ? s_bias : nullptr;
     const float* es = p.scale ? s_scale : nullptr;
-    for (int tile = pair; tile < p.num_tiles; tile += n_pairs) {
-      mbar_wait(smem_u32(tmem_full_bar), tphase);
+    const int n_chunks = p.n_pad >> 4, ovl_chunks = ovl >> 4;
+    int it = 0;
+    for (int tile = pair; tile < p.num_tiles; tile += n_pairs, ++it) {
+      const int par = it & 1;
+      mbar_wait(smem_u32(&tmem_full_bar[par]), (it >> 1) & 1);
       tc_fence_after();
       const int64_t s = static_cast<int64_t>(tile) * (2 * kTileM) + rank * kTileM + q * 32 + lane;
       const bool in_range = s < p.n_slots;
       int b = 0, sy = 0, sx = 0;
       if (in_range) slot_coords(p, s, b, sy, sx);
       const bool valid = in_range && (p.type == 0 || (sy >= 1 && sx >= 1));
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-      for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + c0, r);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (par ? base1 : 0);
+      // chunk order: the columns shared with the other region first (the last ones of an even tile, the first ones
+      // of an odd tile)
+      auto chunk_at = [&](int i) { return (par == 0 && ovl_chunks > 0) ? (i < ovl_chunks ? n_chunks - ovl_chunks + i : i - ovl_chunks) : i; };
+      uint32_t ra[16], rb[16];
+      float v[16];
+      tmem_ld16(taddr + chunk_at(0) * 16, ra);
+      for (int i = 0; i < n_chunks; i += 2) {
         tmem_ld_wait();
-        float v[16];
+        if (i + 1 < n_chunks) tmem_ld16(taddr + chunk_at(i + 1) * 16, rb);     // in flight while chunk i is stored
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-        epilogue_store16(p, eb, es, s_shift, s, in_range, valid, b, sy, sx, c0, v);
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(ra[j]);
+        epilogue_store16(p, eb, es, s_shift, s, in_range, valid, b, sy, sx, chunk_at(i) * 16, v);
+        if (i + 1 == ovl_chunks) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(smem_u32(tmem_ovl_bar));
+        }
+        if (i + 1 < n_chunks) {
+          tmem_ld_wait();
+          if (i + 2 < n_chunks) tmem_ld16(taddr + chunk_at(i + 2) * 16, ra);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rb[j]);
+          epilogue_store16(p, eb, es, s_shift, s, in_range, valid, b, sy, sx, chunk_at(i + 1) * 16, v);
+          if (i + 2 == ovl_chunks) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(smem_u32(tmem_ovl_bar));
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_leader(smem_u32(tmem_empty_bar));
-      tphase ^= 1u;
+      if (lane == 0) {
+        if (ovl_chunks == 0) mbar_arrive_leader(smem_u32(tmem_ovl_bar));   // keep the phase count in step
+        mbar_arrive_leader(smem_u32(&tmem_empty_bar[par]));
+      }
     }
   }
 
@@ -511,7 +550,7 @@ extern "C" int mmlf_conv2x2(const mmlf_conv_args* a, void* stream) {
   if (int rc = fill_params(a, p)) return rc;
   const bool pair = conv_impl() == 2;
   const uint32_t stage_bytes = kABytes + (pair ? p.n_pad * 64 : p.n_pad * 128);
-  const uint32_t aux_bytes = (2 * kMaxStages + 2) * 8 + 16 + 3 * p.n_pad * 4 + 64;
+  const uint32_t aux_bytes = (2 * kMaxStages + 5) * 8 + 16 + 3 * p.n_pad * 4 + 64;
   const uint32_t max_smem = 232448;   // 227 KB opt-in limit per CTA on sm_100
   int stages = static_cast<int>((max_smem - 1024 - aux_bytes) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
