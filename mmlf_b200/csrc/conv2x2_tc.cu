@@ -40,6 +40,7 @@ struct ConvParams {
   const float* shift;
   const __nv_bfloat16* gate;
   void* out;
+  long long* stats;                             // optional per-CTA cycle counters (debug): [grid][8]
 };
 
 // Epilogue math + store for 16 consecutive output channels [c0, c0+16) of one slot.  Shared by the tensor-core
@@ -326,11 +327,14 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   if (warp == 0) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      long long t_wait = 0, t_begin = clock64();
       for (int tile = pair; tile < p.num_tiles; tile += n_pairs) {
         const int row0 = tile * (2 * kTileM) + static_cast<int>(rank) * kTileM;
         for (int tap = 0; tap < 4; ++tap) {
           for (int kc = 0; kc < p.n_kc; ++kc) {
+            const long long tw = clock64();
             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+            t_wait += clock64() - tw;
             const uint32_t fb = smem_u32(&full_bar[stage]);
             if (leader) mbar_arrive_expect_tx(fb, 2 * stage_bytes);
             const uint32_t a_dst = tiles_addr + stage * stage_bytes;
@@ -347,22 +351,31 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           }
         }
       }
+      if (p.stats) {
+        p.stats[blockIdx.x * 8 + 0] = clock64() - t_begin;   // producer total
+        p.stats[blockIdx.x * 8 + 1] = t_wait;                // producer waiting for free stages
+      }
     }
   } else if (warp == 1) {
     if (leader && lane == 0) {
       const uint32_t idesc = make_idesc_16(2 * kTileM, p.n_part, 0, 0, p.ab_dtype, p.ab_dtype);
       uint32_t stage = 0, phase = 0;
       int it = 0;
+      long long t_full = 0, t_tmem = 0, t_begin = clock64();
       for (int tile = pair; tile < p.num_tiles; tile += n_pairs, ++it) {
         const int par = it & 1;
+        long long tw = clock64();
         mbar_wait(smem_u32(&tmem_empty_bar[par]), ((it >> 1) & 1) ^ 1u);   // region drained (tile it - 2)
         if (ovl > 0 && it > 0) mbar_wait(smem_u32(tmem_ovl_bar), (it - 1) & 1);   // shared columns drained (tile it - 1)
+        t_tmem += clock64() - tw;
         tc_fence_after();
         const uint32_t acc_base = tmem_base + (par ? base1 : 0);
         uint32_t accumulate = 0;
         for (int tap = 0; tap < 4; ++tap) {
           for (int kc = 0; kc < p.n_kc; ++kc) {
+            tw = clock64();
             mbar_wait(smem_u32(&full_bar[stage]), phase);
+            t_full += clock64() - tw;
             tc_fence_after();
             const uint32_t a_addr = tiles_addr + stage * stage_bytes;
             const uint32_t b_addr = a_addr + kABytes;
@@ -384,6 +397,11 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
         umma_commit_pair(smem_u32(&tmem_full_bar[par]));
       }
+      if (p.stats) {
+        p.stats[blockIdx.x * 8 + 2] = clock64() - t_begin;   // MMA issuer total
+        p.stats[blockIdx.x * 8 + 3] = t_full;                // ... waiting for TMA data
+        p.stats[blockIdx.x * 8 + 4] = t_tmem;                // ... waiting for the epilogue to free TMEM
+      }
     }
   } else {
     const int q = warp & 3;
@@ -391,9 +409,12 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const float* es = p.scale ? s_scale : nullptr;
     const int n_chunks = p.n_pad >> 4, ovl_chunks = ovl >> 4;
     int it = 0;
+    long long t_wait = 0, t_begin = clock64();
     for (int tile = pair; tile < p.num_tiles; tile += n_pairs, ++it) {
       const int par = it & 1;
+      const long long tw = clock64();
       mbar_wait(smem_u32(&tmem_full_bar[par]), (it >> 1) & 1);
+      t_wait += clock64() - tw;
       tc_fence_after();
       const int64_t s = static_cast<int64_t>(tile) * (2 * kTileM) + rank * kTileM + q * 32 + lane;
       const bool in_range = s < p.n_slots;
@@ -437,6 +458,10 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         if (ovl_chunks == 0) mbar_arrive_leader(smem_u32(tmem_ovl_bar));   // keep the phase count in step
         mbar_arrive_leader(smem_u32(&tmem_empty_bar[par]));
       }
+    }
+    if (p.stats && warp == 2 && lane == 0) {
+      p.stats[blockIdx.x * 8 + 5] = clock64() - t_begin;     // epilogue total
+      p.stats[blockIdx.x * 8 + 6] = t_wait;                  // ... waiting for accumulators
     }
   }
 
@@ -527,6 +552,7 @@ static int fill_params(const mmlf_conv_args* a, ConvParams& p) {
   p.shift = a->shift;
   p.gate = reinterpret_cast<const __nv_bfloat16*>(a->gate);
   p.out = a->out;
+  p.stats = nullptr;
   p.stages = 0;
   return 0;
 }
@@ -545,9 +571,14 @@ static int conv_impl() {
   return impl;
 }
 
+static long long* g_conv_stats = nullptr;
+// debug hook (not part of the public header): per-CTA cycle counters of the next conv launches, [grid][8] int64
+extern "C" void mmlf_debug_conv_stats(long long* device_buf) { g_conv_stats = device_buf; }
+
 extern "C" int mmlf_conv2x2(const mmlf_conv_args* a, void* stream) {
   ConvParams p;
   if (int rc = fill_params(a, p)) return rc;
+  p.stats = g_conv_stats;
   const bool pair = conv_impl() == 2;
   const uint32_t stage_bytes = kABytes + (pair ? p.n_pad * 64 : p.n_pad * 128);
   const uint32_t aux_bytes = (2 * kMaxStages + 5) * 8 + 16 + 3 * p.n_pad * 4 + 64;
