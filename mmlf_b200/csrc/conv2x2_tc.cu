@@ -325,40 +325,47 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   const int half_rows = p.n_part >> 1;                 // weight rows each CTA supplies per MMA
 
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      long long t_wait = 0, t_begin = clock64();
-      for (int tile = pair; tile < p.num_tiles; tile += n_pairs) {
-        const int row0 = tile * (2 * kTileM) + static_cast<int>(rank) * kTileM;
-        for (int tap = 0; tap < 4; ++tap) {
-          for (int kc = 0; kc < p.n_kc; ++kc) {
-            const long long tw = clock64();
-            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
-            t_wait += clock64() - tw;
-            const uint32_t fb = smem_u32(&full_bar[stage]);
+    // ------------------------------------------------------------------ TMA producer.  The whole warp runs the loop so
+    // that every operand is warp-uniform (UTMALDG takes uniform registers; a lane-0-only region makes the compiler
+    // wrap each instruction in an elect/broadcast loop); one elected lane issues.
+    uint32_t stage = 0, phase = 0;
+    long long t_wait = 0, t_begin = clock64();
+    for (int tile = pair; tile < p.num_tiles; tile += n_pairs) {
+      const int row0 = tile * (2 * kTileM) + static_cast<int>(rank) * kTileM;
+      for (int tap = 0; tap < 4; ++tap) {
+        for (int kc = 0; kc < p.n_kc; ++kc) {
+          const long long tw = clock64();
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+          t_wait += clock64() - tw;
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          const uint32_t a_dst = tiles_addr + stage * stage_bytes;
+          const uint32_t b_dst = a_dst + kABytes;
+          const int kcol = (tap * p.n_kc + kc) * 64;
+          if (elect_one()) {
             if (leader) mbar_arrive_expect_tx(fb, 2 * stage_bytes);
-            const uint32_t a_dst = tiles_addr + stage * stage_bytes;
             tma_load_2d_pair(a_dst, &tmap_a, fb, kc * 64, row0 + p.tap_off[tap], kEvictNormal);
-            const uint32_t b_dst = a_dst + kABytes;
-            const int kcol = (tap * p.n_kc + kc) * 64;
             for (int part = 0; part < p.n_parts; ++part)
               tma_load_2d_pair(b_dst + part * half_rows * 128, &tmap_b, fb, kcol,
                                part * p.n_part + static_cast<int>(rank) * half_rows, kEvictLast);
-            if (++stage == static_cast<uint32_t>(p.stages)) {
-              stage = 0;
-              phase ^= 1u;
-            }
+          }
+          __syncwarp();
+          if (++stage == static_cast<uint32_t>(p.stages)) {
+            stage = 0;
+            phase ^= 1u;
           }
         }
       }
-      if (p.stats) {
-        p.stats[blockIdx.x * 8 + 0] = clock64() - t_begin;   // producer total
-        p.stats[blockIdx.x * 8 + 1] = t_wait;                // producer waiting for free stages
-      }
+    }
+    if (p.stats && lane == 0) {
+      p.stats[blockIdx.x * 8 + 0] = clock64() - t_begin;   // producer total
+      p.stats[blockIdx.x * 8 + 1] = t_wait;                // producer waiting for free stages
     }
   } else if (warp == 1) {
-    if (leader && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA; warp-uniform loop,
+    // one elected lane issues the MMAs and the commits that track them)
+    if (leader) {
       const uint32_t idesc = make_idesc_16(2 * kTileM, p.n_part, 0, 0, p.ab_dtype, p.ab_dtype);
+      const uint32_t part_bytes = static_cast<uint32_t>(half_rows) * 128u;
       uint32_t stage = 0, phase = 0;
       int it = 0;
       long long t_full = 0, t_tmem = 0, t_begin = clock64();
@@ -380,24 +387,34 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             const uint32_t a_addr = tiles_addr + stage * stage_bytes;
             const uint32_t b_addr = a_addr + kABytes;
             const int ksteps = (kc == p.n_kc - 1) ? p.last_ksteps : 4;
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t adesc = make_sw128_desc(a_addr + k * 32, 0, 1024);
-              for (int part = 0; part < p.n_parts; ++part) {
-                const uint64_t bdesc = make_sw128_desc(b_addr + part * half_rows * 128 + k * 32, 0, 1024);
-                umma_f16_pair(acc_base + part * p.n_part, adesc, bdesc, idesc, accumulate);
+            const uint64_t adesc0 = make_sw128_desc(a_addr, 0, 1024);
+            const uint64_t bdesc0 = make_sw128_desc(b_addr, 0, 1024);
+            const bool last = (tap == 3 && kc == p.n_kc - 1);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (k < ksteps) {
+                  // advancing by k * 32 bytes inside the 128-byte swizzle row = +2k in the (addr >> 4) field
+                  umma_f16_pair(acc_base, adesc0 + 2 * k, bdesc0 + 2 * k, idesc, accumulate);
+                  if (p.n_parts == 2)
+                    umma_f16_pair(acc_base + p.n_part, adesc0 + 2 * k, bdesc0 + (part_bytes >> 4) + 2 * k, idesc,
+                                  accumulate);
+                  accumulate = 1;
+                }
               }
-              accumulate = 1;
+              umma_commit_pair(smem_u32(&empty_bar[stage]));
+              if (last) umma_commit_pair(smem_u32(&tmem_full_bar[par]));
             }
-            umma_commit_pair(smem_u32(&empty_bar[stage]));
+            accumulate = 1;
+            __syncwarp();
             if (++stage == static_cast<uint32_t>(p.stages)) {
               stage = 0;
               phase ^= 1u;
             }
           }
         }
-        umma_commit_pair(smem_u32(&tmem_full_bar[par]));
       }
-      if (p.stats) {
+      if (p.stats && lane == 0) {
         p.stats[blockIdx.x * 8 + 2] = clock64() - t_begin;   // MMA issuer total
         p.stats[blockIdx.x * 8 + 3] = t_full;                // ... waiting for TMA data
         p.stats[blockIdx.x * 8 + 4] = t_tmem;                // ... waiting for the epilogue to free TMEM

@@ -79,56 +79,62 @@ conv2x2_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int ch = 0; ch < n_chunks; ++ch) {
-        const int row0 = static_cast<int>(k_begin + static_cast<int64_t>(ch) * kWgKb);
-        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
-        const uint32_t fb = smem_u32(&full_bar[stage]);
+    // TMA producer: warp-uniform loop, one elected lane issues (keeps every operand in uniform registers)
+    uint32_t stage = 0, phase = 0;
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      const int row0 = static_cast<int>(k_begin + static_cast<int64_t>(ch) * kWgKb);
+      mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+      const uint32_t fb = smem_u32(&full_bar[stage]);
+      const uint32_t a_dst = tiles_addr + stage * stage_bytes;
+      const uint32_t b_dst = a_dst + a_bytes;
+      if (elect_one()) {
         mbar_arrive_expect_tx(fb, stage_bytes);
-        const uint32_t a_dst = tiles_addr + stage * stage_bytes;
         for (int h = 0; h < 2; ++h) {
           const int atom = mblock * 2 + h;                 // (tap, chunk) index
           const int tap = atom / p.kc, chunk = atom - tap * p.kc;
           tma_load_2d(a_dst + h * kWgBox, &tmap_act, fb, chunk * 64, row0 + p.tap_off[tap]);
         }
-        const uint32_t b_dst = a_dst + a_bytes;
         for (int j = 0; j < p.n_boxes; ++j) tma_load_2d(b_dst + j * kWgBox, &tmap_dout, fb, j * 64, row0);
-        if (++stage == static_cast<uint32_t>(p.stages)) {
-          stage = 0;
-          phase ^= 1u;
-        }
+      }
+      __syncwarp();
+      if (++stage == static_cast<uint32_t>(p.stages)) {
+        stage = 0;
+        phase ^= 1u;
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      uint32_t idesc[2];
-      for (int q = 0; q < p.n_parts; ++q) idesc[q] = make_idesc_16(128, p.part_n[q], 1, 1, p.act_dtype, p.dout_dtype);
-      uint32_t stage = 0, phase = 0, accumulate = 0;
-      for (int ch = 0; ch < n_chunks; ++ch) {
-        mbar_wait(smem_u32(&full_bar[stage]), phase);
-        tc_fence_after();
-        const uint32_t a_addr = tiles_addr + stage * stage_bytes;
-        const uint32_t b_addr = a_addr + a_bytes;
+    // MMA issuer: warp-uniform loop, one elected lane issues MMAs and commits
+    const uint32_t idesc0 = make_idesc_16(128, p.part_n[0], 1, 1, p.act_dtype, p.dout_dtype);
+    const uint32_t idesc1 = make_idesc_16(128, p.n_parts > 1 ? p.part_n[1] : 16, 1, 1, p.act_dtype, p.dout_dtype);
+    const uint32_t part1_off = static_cast<uint32_t>(p.part_n[0] / 64) * kWgBox;
+    uint32_t stage = 0, phase = 0, accumulate = 0;
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      mbar_wait(smem_u32(&full_bar[stage]), phase);
+      tc_fence_after();
+      const uint32_t a_addr = tiles_addr + stage * stage_bytes;
+      const uint32_t b_addr = a_addr + a_bytes;
+      const uint64_t adesc0 = make_sw128_desc(a_addr, kWgBox, 1024);
+      const uint64_t bdesc0 = make_sw128_desc(b_addr, kWgBox, 1024);
+      const uint64_t bdesc1 = make_sw128_desc(b_addr + part1_off, kWgBox, 1024);
+      if (elect_one()) {
+#pragma unroll
         for (int k = 0; k < kWgKb / 16; ++k) {
-          const uint64_t adesc = make_sw128_desc(a_addr + k * 2048, kWgBox, 1024);
-          int col = 0;
-          for (int q = 0; q < p.n_parts; ++q) {
-            const uint64_t bdesc = make_sw128_desc(b_addr + (col / 64) * kWgBox + k * 2048, kWgBox, 1024);
-            umma_f16(tmem_base + col, adesc, bdesc, idesc[q], accumulate);
-            col += p.part_n[q];
-          }
+          // 16 slots further along K = 2048 bytes = +128 in the (addr >> 4) field
+          umma_f16(tmem_base, adesc0 + 128 * k, bdesc0 + 128 * k, idesc0, accumulate);
+          if (p.n_parts > 1) umma_f16(tmem_base + p.part_n[0], adesc0 + 128 * k, bdesc1 + 128 * k, idesc1, accumulate);
           accumulate = 1;
         }
         umma_commit(smem_u32(&empty_bar[stage]));
-        if (++stage == static_cast<uint32_t>(p.stages)) {
-          stage = 0;
-          phase ^= 1u;
-        }
+        if (ch == n_chunks - 1) umma_commit(smem_u32(done_bar));
       }
-      if (n_chunks > 0) umma_commit(smem_u32(done_bar));
-      else mbar_arrive(smem_u32(done_bar));
+      accumulate = 1;
+      __syncwarp();
+      if (++stage == static_cast<uint32_t>(p.stages)) {
+        stage = 0;
+        phase ^= 1u;
+      }
     }
+    if (n_chunks == 0 && lane == 0) mbar_arrive(smem_u32(done_bar));
   } else {
     const int q = warp & 3;
     mbar_wait(smem_u32(done_bar), 0);
