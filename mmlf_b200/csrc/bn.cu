@@ -28,8 +28,8 @@ __device__ __forceinline__ void st8(void* base, int64_t slot, int ld, int c, con
   *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + slot * ld + c) = v;
 }
 __device__ __forceinline__ bool slot_valid(int64_t s, int Hp, int Wp) {
-  const int rem = static_cast<int>(s % (static_cast<int64_t>(Hp) * Wp));
-  const int sy = rem / Wp, sx = rem - sy * Wp;
+  const uint32_t rem = static_cast<uint32_t>(s) % static_cast<uint32_t>(Hp * Wp);   // n_slots < 2^31
+  const uint32_t sy = rem / static_cast<uint32_t>(Wp), sx = rem - sy * Wp;
   return sy >= 1 && sx >= 1;
 }
 
@@ -156,11 +156,15 @@ slot_map_kernel(const void* __restrict__ a, int ld_a, const void* __restrict__ y
                 const void* __restrict__ z, int ld_z, const float* __restrict__ p0, const float* __restrict__ p1,
                 const float* __restrict__ p2, const float* __restrict__ fsums, int C, int Hp, int Wp,
                 int64_t n_slots, void* __restrict__ out, int ld_out, int dt_a, int dt_yz) {
+  // block = (channel groups) x (slot lanes): consecutive threads walk the channels of one slot (contiguous 16-byte
+  // pieces of a row), no integer division on the index path
   const int groups = C >> 3;
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int64_t s = idx / groups;
+  const int lanes = blockDim.x / groups;
+  const int g = threadIdx.x % groups, sl = threadIdx.x / groups;
+  if (sl >= lanes) return;
+  const int64_t s = static_cast<int64_t>(blockIdx.x) * lanes + sl;
   if (s >= n_slots) return;
-  const int c = static_cast<int>(idx - s * groups) * 8;
+  const int c = g * 8;
   float r[8];
   if ((MODE == 0 || MODE == 2) && !slot_valid(s, Hp, Wp)) {
 #pragma unroll
@@ -219,10 +223,12 @@ __global__ void __launch_bounds__(256)
 convert16_kernel(const void* __restrict__ src, int ld_src, void* __restrict__ dst, int ld_dst, int C, int64_t n_slots,
                  int dt_src, int dt_dst) {
   const int groups = C >> 3;
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int64_t s = idx / groups;
+  const int lanes = blockDim.x / groups;
+  const int g = threadIdx.x % groups, sl = threadIdx.x / groups;
+  if (sl >= lanes) return;
+  const int64_t s = static_cast<int64_t>(blockIdx.x) * lanes + sl;
   if (s >= n_slots) return;
-  const int c = static_cast<int>(idx - s * groups) * 8;
+  const int c = g * 8;
   float v[8];
   unpack8(ld8(src, s, ld_src, c), v, dt_src);
   st8(dst, s, ld_dst, c, pack8(v, dt_dst));
@@ -246,8 +252,8 @@ extern "C" int mmlf_convert16(const void* src, int ld_src, int src_dtype, void* 
                               int64_t n_slots, void* stream) {
   MMLF_REQUIRE(src && dst, "convert16: null buffer");
   CHECK_C(C);
-  const int64_t total = n_slots * (C / 8);
-  convert16_kernel<<<static_cast<unsigned>(ceil_div64(total, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  MMLF_REQUIRE(C / 8 <= 256, "convert16: too many channels");
+  convert16_kernel<<<static_cast<unsigned>(ceil_div64(n_slots, 256 / (C / 8))), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, ld_src, dst, ld_dst, C, n_slots, src_dtype, dst_dtype);
   return check_launch("convert16");
 }
@@ -303,7 +309,7 @@ extern "C" int mmlf_bn_apply_relu(const void* z, int ld_z, const float* scale, c
   MMLF_REQUIRE(z && scale && shift && y, "bn_apply_relu: null buffer");
   CHECK_C(C);
   const int64_t n_slots = static_cast<int64_t>(B) * (H + 1) * (W + 1);
-  const int64_t total = n_slots * (C / 8);
+  const int64_t total = ceil_div64(n_slots, 256 / (C / 8)) * 256;
   slot_map_kernel<0><<<static_cast<unsigned>(ceil_div64(total, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       z, ld_z, nullptr, 0, nullptr, 0, scale, shift, nullptr, nullptr, C, H + 1, W + 1, n_slots, y, ld_y, act_dtype,
       act_dtype);
@@ -314,7 +320,7 @@ extern "C" int mmlf_relu_bwd(const void* dy, int ld_dy, const void* y, int ld_y,
                              int grad_dtype, int act_dtype, void* dz, int ld_dz, void* stream) {
   MMLF_REQUIRE(dy && y && dz, "relu_bwd: null buffer");
   CHECK_C(C);
-  const int64_t total = n_slots * (C / 8);
+  const int64_t total = ceil_div64(n_slots, 256 / (C / 8)) * 256;
   slot_map_kernel<1><<<static_cast<unsigned>(ceil_div64(total, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       dy, ld_dy, y, ld_y, nullptr, 0, nullptr, nullptr, nullptr, nullptr, C, 1, 1, n_slots, dz, ld_dz, grad_dtype,
       act_dtype);
@@ -342,8 +348,7 @@ extern "C" int mmlf_bn_bwd_apply(const void* dy, int ld_dy, const void* y, int l
   MMLF_REQUIRE(dy && y && z && gamma && save_mean && save_invstd && sums && dz, "bn_bwd_apply: null buffer");
   CHECK_C(C);
   const int64_t n_slots = static_cast<int64_t>(B) * (H + 1) * (W + 1);
-  const int64_t total = n_slots * (C / 8);
-  const unsigned blocks = static_cast<unsigned>(ceil_div64(total, 256));
+  const unsigned blocks = static_cast<unsigned>(ceil_div64(n_slots, 256 / (C / 8)));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MMLF_REQUIRE(fsums != nullptr, "bn_bwd_apply: fsums scratch (float[2*C]) required");
   bn_bwd_means_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, 1.0 / static_cast<double>(count), C_real, C, fsums, dgamma,
