@@ -150,58 +150,105 @@ __global__ void bn_fold_eval_kernel(int C_real, int C, const float* __restrict__
 // MODE 1: dz = dy * (y > 0)                                          (relu_bwd)
 // MODE 2: dz = gamma*invstd*(g - sg/n - xhat*sgx/n), halo -> 0       (bn_bwd_apply, train)
 // MODE 3: dz = g * gamma * invstd                                    (bn_bwd_apply, eval-mode BN)
+// MODE 4: 16-bit format conversion                                   (convert16)
+// block = (channel groups) x (slot lanes); a thread owns 8 consecutive channels, keeps their per-channel constants
+// in registers and walks the slots with a grid stride, so the per-slot work is 2-4 128-bit memory operations.
+struct SlotDiv {   // s -> (sy >= 1 && sx >= 1) without integer division when the slot index fits a float exactly
+  float rcp_img, rcp_w;
+  uint32_t per_img, Wp;
+  int exact;
+};
+__device__ __forceinline__ uint32_t fast_div(uint32_t x, uint32_t d, float rcp) {
+  uint32_t q = static_cast<uint32_t>(__uint2float_rz(x) * rcp);
+  int32_t r = static_cast<int32_t>(x - q * d);
+  if (r < 0) { --q; r += d; }
+  if (r >= static_cast<int32_t>(d)) ++q;
+  return q;
+}
+__device__ __forceinline__ bool slot_valid_fast(int64_t s, const SlotDiv& d) {
+  const uint32_t x = static_cast<uint32_t>(s);
+  uint32_t rem, sy;
+  if (d.exact) {
+    rem = x - fast_div(x, d.per_img, d.rcp_img) * d.per_img;
+    sy = fast_div(rem, d.Wp, d.rcp_w);
+  } else {
+    rem = x % d.per_img;
+    sy = rem / d.Wp;
+  }
+  const uint32_t sx = rem - sy * d.Wp;
+  return sy >= 1 && sx >= 1;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256)
 slot_map_kernel(const void* __restrict__ a, int ld_a, const void* __restrict__ y, int ld_y,
                 const void* __restrict__ z, int ld_z, const float* __restrict__ p0, const float* __restrict__ p1,
-                const float* __restrict__ p2, const float* __restrict__ fsums, int C, int Hp, int Wp,
+                const float* __restrict__ p2, const float* __restrict__ fsums, int C, SlotDiv dv,
                 int64_t n_slots, void* __restrict__ out, int ld_out, int dt_a, int dt_yz) {
-  // block = (channel groups) x (slot lanes): consecutive threads walk the channels of one slot (contiguous 16-byte
-  // pieces of a row), no integer division on the index path
   const int groups = C >> 3;
   const int lanes = blockDim.x / groups;
   const int g = threadIdx.x % groups, sl = threadIdx.x / groups;
   if (sl >= lanes) return;
-  const int64_t s = static_cast<int64_t>(blockIdx.x) * lanes + sl;
-  if (s >= n_slots) return;
   const int c = g * 8;
-  float r[8];
-  if ((MODE == 0 || MODE == 2) && !slot_valid(s, Hp, Wp)) {
+  // per-channel constants -> registers (two 128-bit loads per array)
+  float k0[8], k1[8], k2[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = 0.f;
-    st8(out, s, ld_out, c, pack8(r, dt_a));
-    return;
-  }
-  float av[8];
-  unpack8(ld8(a, s, ld_a, c), av, dt_a);
+  for (int j = 0; j < 8; ++j) k0[j] = k1[j] = k2[j] = 0.f;
   if (MODE == 0) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = fmaxf(fmaf(av[j], p0[c + j], p1[c + j]), 0.f);
-  } else {
-    float yv[8];
-    unpack8(ld8(y, s, ld_y, c), yv, dt_yz);
-    if (MODE == 1) {
+    for (int j = 0; j < 8; ++j) { k0[j] = p0[c + j]; k1[j] = p1[c + j]; }             // scale, shift
+  } else if (MODE == 2) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] = yv[j] > 0.f ? av[j] : 0.f;
+    for (int j = 0; j < 8; ++j) {
+      const float invstd = p2[c + j], kk = p0[c + j] * invstd;                         // gamma * invstd
+      // dz = kk*g - kk*mg - kk*mgx*xhat,  xhat = (z - mean) * invstd
+      k0[j] = kk;
+      k1[j] = kk * fsums[C + c + j] * invstd;                                          // coefficient of (z - mean)
+      k2[j] = kk * fsums[c + j] - k1[j] * p1[c + j];                                   // constant part, mean folded in
+    }
+  } else if (MODE == 3) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) k0[j] = p0[c + j] * p2[c + j];
+  }
+  for (int64_t s = static_cast<int64_t>(blockIdx.x) * lanes + sl; s < n_slots; s += static_cast<int64_t>(gridDim.x) * lanes) {
+    float r[8];
+    if ((MODE == 0 || MODE == 2) && !slot_valid_fast(s, dv)) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = 0.f;
+      st8(out, s, ld_out, c, pack8(r, dt_a));
+      continue;
+    }
+    float av[8];
+    if (MODE == 4) {
+      unpack8(ld8(a, s, ld_a, c), av, dt_yz);
+      st8(out, s, ld_out, c, pack8(av, dt_a));
+      continue;
+    }
+    unpack8(ld8(a, s, ld_a, c), av, dt_a);
+    if (MODE == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = fmaxf(fmaf(av[j], k0[j], k1[j]), 0.f);
     } else {
-      float zv[8];
-      if (MODE == 2) unpack8(ld8(z, s, ld_z, c), zv, dt_yz);
+      float yv[8];
+      unpack8(ld8(y, s, ld_y, c), yv, dt_yz);
+      if (MODE == 1) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float g = yv[j] > 0.f ? av[j] : 0.f;
-        const float k = p0[c + j] * p2[c + j];               // gamma * invstd
-        if (MODE == 3) {
-          r[j] = g * k;
-        } else {
-          const float xhat = (zv[j] - p1[c + j]) * p2[c + j];
-          // fsums = {mean(g), mean(g * xhat)} per channel in fp32, prepared by bn_bwd_means_kernel (fp64 math per
-          // element would run at the 1/64-rate fp64 pipe)
-          r[j] = k * (g - fsums[c + j] - xhat * fsums[C + c + j]);
+        for (int j = 0; j < 8; ++j) r[j] = yv[j] > 0.f ? av[j] : 0.f;
+      } else if (MODE == 3) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = yv[j] > 0.f ? av[j] * k0[j] : 0.f;
+      } else {
+        float zv[8];
+        unpack8(ld8(z, s, ld_z, c), zv, dt_yz);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float gg = yv[j] > 0.f ? av[j] : 0.f;
+          r[j] = fmaf(k0[j], gg, -fmaf(k1[j], zv[j], k2[j]));
         }
       }
     }
+    st8(out, s, ld_out, c, pack8(r, dt_a));
   }
-  st8(out, s, ld_out, c, pack8(r, dt_a));
 }
 
 // per-channel means of the two backward reductions in fp32 (+ the parameter gradients dgamma = sum g*xhat, dbeta = sum g)
@@ -217,21 +264,22 @@ __global__ void bn_bwd_means_kernel(const double* __restrict__ sums, double inv_
   }
 }
 
-// 16-bit format conversion of a slot array (fp16 activations -> bf16 operand of the weight-gradient GEMM, whose two
-// operands must share one format: tcgen05.mma kind::f16 rejects mixed f16 x bf16 with an illegal-instruction fault).
-__global__ void __launch_bounds__(256)
-convert16_kernel(const void* __restrict__ src, int ld_src, void* __restrict__ dst, int ld_dst, int C, int64_t n_slots,
-                 int dt_src, int dt_dst) {
-  const int groups = C >> 3;
-  const int lanes = blockDim.x / groups;
-  const int g = threadIdx.x % groups, sl = threadIdx.x / groups;
-  if (sl >= lanes) return;
-  const int64_t s = static_cast<int64_t>(blockIdx.x) * lanes + sl;
-  if (s >= n_slots) return;
-  const int c = g * 8;
-  float v[8];
-  unpack8(ld8(src, s, ld_src, c), v, dt_src);
-  st8(dst, s, ld_dst, c, pack8(v, dt_dst));
+static SlotDiv make_div(int Hp, int Wp, int64_t n_slots) {
+  SlotDiv d;
+  d.per_img = static_cast<uint32_t>(Hp) * Wp;
+  d.Wp = static_cast<uint32_t>(Wp);
+  d.rcp_img = 1.0f / static_cast<float>(d.per_img);
+  d.rcp_w = 1.0f / static_cast<float>(Wp);
+  d.exact = n_slots < (1 << 24);
+  return d;
+}
+static int map_grid(int64_t n_slots, int C) {
+  const int lanes = 256 / (C / 8);
+  int64_t want = ceil_div64(n_slots, static_cast<int64_t>(lanes) * 4);     // >= 4 slots per thread
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return static_cast<int>(want);
 }
 
 static int red_grid(int64_t n_slots, int lanes) {
@@ -248,13 +296,15 @@ using namespace mmlf;
 
 #define CHECK_C(C) MMLF_REQUIRE((C) % 8 == 0 && (C) >= 8 && (C) <= 2048, "channel count %d must be a multiple of 8 in [8, 2048]", (C))
 
+// 16-bit format conversion of a slot array (fp16 activations -> bf16 operand of the weight-gradient GEMM, whose two
+// operands must share one format: tcgen05.mma kind::f16 rejects mixed f16 x bf16 with an illegal-instruction fault).
 extern "C" int mmlf_convert16(const void* src, int ld_src, int src_dtype, void* dst, int ld_dst, int dst_dtype, int C,
                               int64_t n_slots, void* stream) {
   MMLF_REQUIRE(src && dst, "convert16: null buffer");
   CHECK_C(C);
-  MMLF_REQUIRE(C / 8 <= 256, "convert16: too many channels");
-  convert16_kernel<<<static_cast<unsigned>(ceil_div64(n_slots, 256 / (C / 8))), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      src, ld_src, dst, ld_dst, C, n_slots, src_dtype, dst_dtype);
+  slot_map_kernel<4><<<map_grid(n_slots, C), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, ld_src, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, nullptr, C, make_div(1, 1, n_slots), n_slots, dst,
+      ld_dst, dst_dtype, src_dtype);
   return check_launch("convert16");
 }
 
@@ -309,10 +359,9 @@ extern "C" int mmlf_bn_apply_relu(const void* z, int ld_z, const float* scale, c
   MMLF_REQUIRE(z && scale && shift && y, "bn_apply_relu: null buffer");
   CHECK_C(C);
   const int64_t n_slots = static_cast<int64_t>(B) * (H + 1) * (W + 1);
-  const int64_t total = ceil_div64(n_slots, 256 / (C / 8)) * 256;
-  slot_map_kernel<0><<<static_cast<unsigned>(ceil_div64(total, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      z, ld_z, nullptr, 0, nullptr, 0, scale, shift, nullptr, nullptr, C, H + 1, W + 1, n_slots, y, ld_y, act_dtype,
-      act_dtype);
+  slot_map_kernel<0><<<map_grid(n_slots, C), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      z, ld_z, nullptr, 0, nullptr, 0, scale, shift, nullptr, nullptr, C, make_div(H + 1, W + 1, n_slots), n_slots, y, ld_y,
+      act_dtype, act_dtype);
   return check_launch("bn_apply_relu");
 }
 
@@ -320,10 +369,9 @@ extern "C" int mmlf_relu_bwd(const void* dy, int ld_dy, const void* y, int ld_y,
                              int grad_dtype, int act_dtype, void* dz, int ld_dz, void* stream) {
   MMLF_REQUIRE(dy && y && dz, "relu_bwd: null buffer");
   CHECK_C(C);
-  const int64_t total = ceil_div64(n_slots, 256 / (C / 8)) * 256;
-  slot_map_kernel<1><<<static_cast<unsigned>(ceil_div64(total, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      dy, ld_dy, y, ld_y, nullptr, 0, nullptr, nullptr, nullptr, nullptr, C, 1, 1, n_slots, dz, ld_dz, grad_dtype,
-      act_dtype);
+  slot_map_kernel<1><<<map_grid(n_slots, C), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      dy, ld_dy, y, ld_y, nullptr, 0, nullptr, nullptr, nullptr, nullptr, C, make_div(1, 1, n_slots), n_slots, dz, ld_dz,
+      grad_dtype, act_dtype);
   return check_launch("relu_bwd");
 }
 
@@ -348,17 +396,18 @@ extern "C" int mmlf_bn_bwd_apply(const void* dy, int ld_dy, const void* y, int l
   MMLF_REQUIRE(dy && y && z && gamma && save_mean && save_invstd && sums && dz, "bn_bwd_apply: null buffer");
   CHECK_C(C);
   const int64_t n_slots = static_cast<int64_t>(B) * (H + 1) * (W + 1);
-  const unsigned blocks = static_cast<unsigned>(ceil_div64(n_slots, 256 / (C / 8)));
+  const int blocks = map_grid(n_slots, C);
+  const SlotDiv dv = make_div(H + 1, W + 1, n_slots);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MMLF_REQUIRE(fsums != nullptr, "bn_bwd_apply: fsums scratch (float[2*C]) required");
   bn_bwd_means_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, 1.0 / static_cast<double>(count), C_real, C, fsums, dgamma,
                                                          dbeta);
   if (int rc = check_launch("bn_bwd_means")) return rc;
   if (train)
-    slot_map_kernel<2><<<blocks, 256, 0, st>>>(dy, ld_dy, y, ld_y, z, ld_z, gamma, save_mean, save_invstd, fsums, C,
-                                               H + 1, W + 1, n_slots, dz, ld_dz, grad_dtype, act_dtype);
+    slot_map_kernel<2><<<blocks, 256, 0, st>>>(dy, ld_dy, y, ld_y, z, ld_z, gamma, save_mean, save_invstd, fsums, C, dv,
+                                               n_slots, dz, ld_dz, grad_dtype, act_dtype);
   else
-    slot_map_kernel<3><<<blocks, 256, 0, st>>>(dy, ld_dy, y, ld_y, z, ld_z, gamma, save_mean, save_invstd, fsums, C,
-                                               H + 1, W + 1, n_slots, dz, ld_dz, grad_dtype, act_dtype);
+    slot_map_kernel<3><<<blocks, 256, 0, st>>>(dy, ld_dy, y, ld_y, z, ld_z, gamma, save_mean, save_invstd, fsums, C, dv,
+                                               n_slots, dz, ld_dz, grad_dtype, act_dtype);
   return check_launch("bn_bwd_apply");
 }

@@ -1,0 +1,203 @@
+"""Drop-in for ``python -m mmlf.train.cli`` (/root/reference/mmlf/train/cli.py): same click options and defaults, same
+loop (warm start, cooling, periodic validation, log.csv, checkpoint.pt through ModelSaver).
+
+Differences, all on the B200 side of the boundary:
+  * one process per GPU under torchrun (NCCL all-reduce of one flat gradient bucket + the loss normalisers) replaces
+    the single-process ``torch.nn.DataParallel`` of train/cli.py:159;
+  * ``torch.optim.Adam`` is replaced by the fused flat-buffer Adam (same update rule, same state_dict format);
+  * the dataset is the synthetic light-field source unless ``--train_trainset`` names an existing directory with a
+    loader the user supplies (the HCI4D file loader and CPU augmentations are out of scope).
+``--max_iterations`` (extra option, default 0 = run forever like the reference) bounds the loop for tests.
+"""
+import os
+import sys
+import time
+
+import click
+import torch
+
+from .. import parallel
+from ..data import synthetic
+from ..model import loss
+from ..model.ensamble import Ensamble
+from ..model.feed_forward import FeedForward
+from ..optim import FusedAdam
+from ..utils.dl import ModelSaver, mpi_to_weights, reg_to_class
+
+
+@click.command()
+@click.argument('output_dir', type=click.Path(exists=True))
+@click.option('--model_ksize', default=2, help='Kernel size for convolutions, e.g. 3 for 3x3 kernels')
+@click.option('--model_in_blocks', default=3, help='Number of blocks for input network')
+@click.option('--model_out_blocks', default=8, help='Number of blocks for output network')
+@click.option('--model_chs', default=70, help='Number of channels for input network')
+@click.option('--model_views', default=9, help='Number of viewpoints of the input light field, e.g. 9 for 9+8 views')
+@click.option('--model_cross', is_flag=True, help='Only use cross input?')
+@click.option('--model_uncert', is_flag=True, help='Use uncertainty model?')
+@click.option('--model_discrete', is_flag=True, help='Discretize disparity output?')
+@click.option('--model_unet', is_flag=True, help='Use a U-Net after the multistream network?')
+@click.option('--model_invertible', is_flag=True, help='Use invertible architecture?')
+@click.option('--model_clamp', default=0.7, help='Output clamp for coupling block?')
+@click.option('--model_act_norm', default=0.7, help='Activation normalization for coupling block?')
+@click.option('--model_act_norm_type', default='SOFTPLUS', help='Type of activation normalization for coupling block?')
+@click.option('--model_soft_permutation', is_flag=True, help='Use soft permuation for coupling block?')
+@click.option('--model_no_batchnorm', is_flag=True, help='Disable BatchNorm layers')
+@click.option('--model_batchnorm_momentum', default=0.1, help='Momentum for BatchNorm layers')
+@click.option('--train_trainset', default='../lf-dataset/additional', help='Location of training dataset')
+@click.option('--train_valset', default='../lf-dataset/training', help='Location of validation dataset')
+@click.option('--train_no_data_augment', is_flag=True, help='Don\'t use any data augmentation?')
+@click.option('--train_num_workers', default=4, help='Number of workors for data loader')
+@click.option('--train_lr', default=1e-5, help='Learning rate')
+@click.option('--train_bs', default=1, help='Batch size')
+@click.option('--train_ps', default=32, help='Size of training patches')
+@click.option('--train_beta', default=1.0, help='Weighting between NLL and Cat CE')
+@click.option('--train_mae_threshold', default=0.02, help='If the MAE of one patch is under this threshold, no loss is applied')
+@click.option('--train_max_downscale', default=4, help='Maximum factor of down scaling for data augmentation')
+@click.option('--train_resume', is_flag=True, help='Resume training from old checkpoint?')
+@click.option('--train_loss_padding', default=None, type=float, help='Margin around ground truth to apply loss')
+@click.option('--train_shift', default=0.0, type=float, help='Static shift to apply to off-center training datasets')
+@click.option('--train_loss_multimodal', is_flag=True, help='Use multimodal training loss?')
+@click.option('--train_loss_strongest', is_flag=True, help='Use strongest depth instead of nearest?')
+@click.option('--train_eval_mode', is_flag=True, help='Also train in eval mode?')
+@click.option('--train_eval_mode_start', default=0, help='Start iteration for eval mode')
+@click.option('--train_warm_start', is_flag=True, help='Use lower learning rate during initial iterations?')
+@click.option('--train_cooling', default=0, help='Cooling interval')
+@click.option('--val_interval', default=100, help='Validation interval')
+@click.option('--val_loss_margin', default=15, help='Margin around each image to omit for the validation loss.')
+@click.option('--val_ensamble', is_flag=True, help='Use a network ensamble?')
+@click.option('--val_disp_min', default=-3.5, help='Minimum disparity of dataset')
+@click.option('--val_disp_max', default=3.5, help='Maximum disparity of dataset')
+@click.option('--val_disp_step', default=0.1, help='Disparity increment for ensamble')
+@click.option('--max_iterations', default=0, help='[mmlf_b200] stop after this many iterations (0 = never, like the reference)')
+def main(output_dir, max_iterations, **kwargs):
+    assert not (kwargs['train_loss_strongest'] and kwargs['train_loss_multimodal'])
+    if kwargs['model_invertible']:
+        raise NotImplementedError('INNs are not supported anymore')          # train/cli.py:252
+    if kwargs['train_eval_mode']:
+        raise NotImplementedError('--train_eval_mode is not supported by the B200 path')
+    kwargs['model_radius'] = (kwargs['model_in_blocks'] + kwargs['model_out_blocks']) * ((kwargs['model_ksize'] + 1) // 2)
+    if kwargs['val_ensamble']:
+        kwargs['model_uncert'] = True                                          # train/cli.py:68-69
+
+    rank, world, local = parallel.init_from_env()
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    ps = kwargs['train_ps']
+    # synthetic stand-in for HCI4D(train_trainset, transform=[Shift(train_shift), ...augmentations...])
+    trainset = synthetic.SyntheticLF(length=4096, n=kwargs['model_views'], H=ps, W=ps, seed=1)
+    sampler = torch.utils.data.distributed.DistributedSampler(trainset, world, rank, shuffle=True) if world > 1 else None
+    trainloader = torch.utils.data.DataLoader(trainset, batch_size=max(1, kwargs['train_bs'] // world),
+                                              shuffle=sampler is None, sampler=sampler,
+                                              num_workers=kwargs['train_num_workers'])
+    valset = synthetic.SyntheticLF(length=2, n=kwargs['model_views'], H=4 * ps, W=4 * ps, seed=2, name='val')
+    valloader = torch.utils.data.DataLoader(valset, batch_size=1, shuffle=False, num_workers=1)
+
+    model = FeedForward(**kwargs).to(dev)
+    optimizer = FusedAdam(model.parameters(), lr=kwargs['train_lr'])
+    if kwargs['train_loss_multimodal']:
+        loss_fn, loss_uncert_fn = loss.MultiMaskedL1Loss(), loss.ImprovedMultiUncertaintyL1Loss()
+    else:
+        loss_fn, loss_uncert_fn = loss.MaskedL1Loss(), loss.ImprovedUncertaintyL1Loss()
+    loss_discrete_fn = loss.MaskedCrossEntropy()
+    mse_fn, bad_pix_fn = loss.MaskedMSELoss(), loss.MaskedBadPix()
+
+    i = 0
+    if kwargs['train_resume']:                                                # train/cli.py:137-157
+        print('Resume training...')
+        state = torch.load(os.path.join(output_dir, 'checkpoint.pt'), map_location=dev)
+        for k in list(state['model_state_dict']):
+            if 'tmp' in k:
+                del state['model_state_dict'][k]
+        model.load_state_dict(state['model_state_dict'])
+        optimizer.load_state_dict(state['optimizer_state_dict'])
+        for param_group in optimizer.param_groups:
+            param_group['lr'] = kwargs['train_lr']
+        i = state['iteration']
+    val_model = Ensamble(model, **kwargs) if kwargs['val_ensamble'] else model
+
+    log = None
+    header = f'{"iter":>7}, loss_train,   loss_val,        mse, badpix_007, time_elapsed'
+    if rank == 0:
+        log = open(os.path.join(output_dir, 'log.csv'), 'a' if kwargs['train_resume'] else 'w')
+        print(header)
+        if not kwargs['train_resume']:
+            print(header, file=log)
+    model_saver = ModelSaver(only_best=False)
+    loss_val_avg = mse_avg = bad_pix_avg = 0.0
+    dims = (2 if kwargs['model_cross'] else 4) * kwargs['model_views'] * 3
+    time_start = 0
+    while True:
+        for data in trainloader:
+            h_views, v_views, i_views, d_views, center, gt, mpi, mask, index = data
+            if kwargs['train_loss_strongest']:
+                inds = torch.max(mpi[:, :, 3, :, :], dim=1)[1].unsqueeze(1)
+                gt = torch.gather(mpi[:, :, 4, :, :], dim=1, index=inds).squeeze()
+            mask = mask.int() * loss.create_mask_margin(mask.shape, 11)       # train/cli.py:194
+            h_views, v_views, i_views, d_views = (t.to(dev, non_blocking=True) for t in (h_views, v_views, i_views, d_views))
+            gt, mpi, mask = gt.to(dev), mpi.to(dev).float(), mask.to(dev)
+            gt_classes = None
+            if kwargs['model_discrete']:                                      # targets are built on the GPU
+                gt_classes = (mpi_to_weights(mpi, kwargs['val_disp_min'], kwargs['val_disp_max'], dims)
+                              if kwargs['train_loss_multimodal'] else
+                              reg_to_class(gt, kwargs['val_disp_min'], kwargs['val_disp_max'], dims))
+            mask_padding = None
+            if kwargs['train_loss_padding'] is not None:
+                if kwargs['train_loss_multimodal']:
+                    mpi[:, :, 3, :, :] *= (torch.abs(mpi[:, :, 4, :, :]) < kwargs['train_loss_padding']).float()
+                else:
+                    mask_padding = (torch.abs(gt) < kwargs['train_loss_padding']).int()
+            if kwargs['train_loss_multimodal']:
+                gt = mpi
+            model.train()
+            if kwargs['train_warm_start'] and i <= 1000:                      # train/cli.py:233-236
+                for g in optimizer.param_groups:
+                    g['lr'] = kwargs['train_lr'] * float(i) / 1000.0
+            if kwargs['train_cooling'] > 0 and i >= kwargs['train_cooling']:
+                lr = kwargs['train_lr'] / (10.0 ** (i / kwargs['train_cooling'] - 1.0))
+                for g in optimizer.param_groups:
+                    g['lr'] = lr
+            optimizer.zero_grad()
+            output = model(h_views, v_views, i_views, d_views)
+            if kwargs['model_uncert']:
+                loss_train = loss_uncert_fn(output, gt, mask, mask_padding)
+            elif kwargs['model_discrete']:
+                loss_train = loss_discrete_fn(output, gt_classes, mask)
+            else:
+                loss_train = loss_fn(output, gt, mask)
+            loss_train.backward()
+            parallel.all_reduce_sum_(optimizer.flat_grad)                     # replaces DataParallel's reduce-add
+            optimizer.step()
+            time_elap = time.time() - time_start
+
+            if i % kwargs['val_interval'] == 0:
+                with torch.no_grad():
+                    model.eval()
+                    loss_val_avg = mse_avg = bad_pix_avg = 0.0
+                    for j, vdata in enumerate(valloader):
+                        vh, vv, vi, vd, center, vgt, vmpi, _, index = vdata
+                        vh, vv, vi, vd = (t.to(dev) for t in (vh, vv, vi, vd))
+                        vgt, vmpi = vgt.to(dev), vmpi.to(dev).float()
+                        vmask = loss.create_mask_margin(vgt.shape, kwargs['val_loss_margin']).to(dev)
+                        output = val_model(vh, vv, vi, vd)
+                        tgt = vmpi if kwargs['train_loss_multimodal'] else vgt
+                        loss_val = (loss_uncert_fn if kwargs['model_uncert'] else loss_fn)(output, tgt, vmask)
+                        loss_val_avg += loss_val.item()
+                        mse_avg += mse_fn(output, vgt, vmask).item()
+                        bad_pix_avg += bad_pix_fn(output, vgt, vmask).item()
+                    j += 1
+                    loss_val_avg, mse_avg, bad_pix_avg = loss_val_avg / j, mse_avg / j, bad_pix_avg / j
+                    if rank == 0:
+                        model_saver(os.path.join(output_dir, 'checkpoint.pt'), model, optimizer, kwargs, None, i,
+                                    loss_val_avg)
+            if rank == 0:
+                line = f'{i:>7}, {loss_train.item():.8f}, {loss_val_avg:.8f}, {mse_avg:.8f}, {bad_pix_avg:.8f}, {time_elap:.8f}'
+                print(line)
+                print(line, file=log, flush=True)
+            i += 1
+            time_start = time.time()
+            if max_iterations and i >= max_iterations:
+                return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())
