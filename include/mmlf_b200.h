@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MMLF_ABI_VERSION 1
+#define MMLF_ABI_VERSION 2
 
 /* 16-bit storage formats.  Forward activations and weights are fp16 (11 significant bits; the reference's own GPU
  * path multiplies in TF32, 11 bits), gradients are bf16 (fp32 exponent range); accumulation is always fp32. */
@@ -87,10 +87,10 @@ int mmlf_unpack_conv_wgrad(const float* dw_packed, int n_pad, int cin_pad, int c
                            int in_groups, int group_real, int group_pad, float* dw, int accumulate, void* stream);
 
 typedef struct mmlf_conv_args {
-  const void* in;        /* bf16 [n_slots][ld_in]; first cin_pad channels are the operand        */
+  const void* in;        /* 16-bit [n_slots][ld_in]; first cin_pad channels are the operand       */
   int ld_in;             /* row pitch in elements (multiple of 8)                                 */
   int cin_pad;           /* multiple of 16                                                         */
-  const void* wpack;     /* from mmlf_pack_conv_weight, [n_pad][4 * kc * 64] bf16                  */
+  const void* wpack;     /* from mmlf_pack_conv_weight, [n_pad][4 * kc * 64], same format as `in`  */
   int n_pad;             /* multiple of 16, <= 320                                                 */
   int B, H, W;           /* image geometry (slot grid is (H+1) x (W+1))                            */
   int type;              /* 0: padded conv (nn.Conv2d(.., 2, padding=1), feed_forward.py:123): output on the
@@ -101,16 +101,25 @@ typedef struct mmlf_conv_args {
   const float* scale;    /* [n_pad] or NULL: y = (acc + bias) * scale + shift (eval-mode BN fold)   */
   const float* shift;    /* [n_pad] or NULL                                                        */
   int relu;              /* apply max(.,0) (nn.ReLU, feed_forward.py:124,135)                       */
-  const void* gate;      /* bf16 [n_slots][ld_gate] or NULL: multiply by (gate > 0) -- ReLU backward */
-  int ld_gate;
+  const uint32_t* gate_bits; /* [n_slots][ld_bits] or NULL: out[slot][c] is zeroed unless bit (c & 31) of word c / 32
+                            is set -- ReLU backward with the sign bits saved by the forward pass (out_mode 0)   */
+  uint32_t* relu_bits;   /* [n_slots][ld_bits] or NULL: receives the bits (out[slot][c] > 0) (out_mode 0)   */
+  int ld_bits;           /* words per slot of gate_bits / relu_bits, >= ceil(n_pad / 32), <= 10      */
   void* out;             /* see out_mode                                                           */
   int ld_out;
-  int out_mode;          /* 0: bf16 [n_slots][ld_out]; 1: f32 [n_slots][ld_out];
+  int out_mode;          /* 0: 16-bit [n_slots][ld_out]; 1: f32 [n_slots][ld_out];
                             2: f32 planar (B, n_real, Ho, Wo), Ho x Wo = (H+1)x(W+1) for type 0, H x W for type 1 */
   int n_real;            /* channels written in out_mode 2 (<= n_pad); out_mode 0/1 write n_pad channels */
+  void* out2;            /* NULL or a second copy of the out_mode-0 output in out2_dtype, [n_slots][ld_out2]:
+                            the forward pass of training keeps fp16 for the next conv and bf16 for the weight
+                            gradient (tcgen05 kind::f16 needs both operands in one format)              */
+  int ld_out2;
+  double* col_sums;      /* NULL or [2][n_pad]: += per-channel sum and sum of squares of the stored (rounded)
+                            output over all slots (halo slots are zero): BatchNorm batch statistics
+                            (feed_forward.py:134) and bias gradients come out of the conv epilogue (out_mode 0) */
   int ab_dtype;          /* storage format of `in` and `wpack`: MMLF_BF16 or MMLF_FP16                */
-  int gate_dtype;        /* storage format of `gate`                                                  */
   int out_dtype;         /* storage format of `out` in out_mode 0                                     */
+  int out2_dtype;        /* storage format of `out2`                                                  */
 } mmlf_conv_args;
 
 /* 2x2 convolution as an implicit GEMM on tcgen05 (TMA-fed, TMEM accumulators, fused epilogue).  Forward of
@@ -157,21 +166,27 @@ int mmlf_bn_fold_eval(int C_real, int C, const float* gamma, const float* beta, 
                       const float* running_var, const float* conv_bias, float eps, float* scale, float* shift,
                       void* stream);
 
-/* y = relu(z * scale + shift) on valid slots, zero on halo slots; bf16 in, bf16 out (ReLU at feed_forward.py:135). */
+/* y = relu(z * scale + shift) on valid slots, zero on halo slots; 16-bit in, 16-bit out (ReLU at feed_forward.py:135).
+ * y2 (optional, NULL to skip): second copy of y in y2_dtype -- training keeps fp16 for the next convolution and bf16
+ * for its weight gradient. */
 int mmlf_bn_apply_relu(const void* z, int ld_z, const float* scale, const float* shift, int C, int B, int H, int W,
-                       int act_dtype, void* y, int ld_y, void* stream);
+                       int act_dtype, void* y, int ld_y, void* y2, int ld_y2, int y2_dtype, void* stream);
 
-/* Backward of BN(+ReLU) in training mode.  Pass 1: with g = dy * (y > 0) and xhat = (z - mean) * invstd,
+/* Backward of BN(+ReLU) in training mode.  The ReLU mask is recomputed from z exactly as the forward pass computed
+ * y = relu(fma(z, scale, shift)) (scale / shift from mmlf_bn_finalize), so y itself is not read.
+ * Pass 1: with g = dy * (z * scale + shift > 0) and xhat = (z - mean) * invstd,
  * sums[0][c] = sum g, sums[1][c] = sum g * xhat (double[2][C], zeroed by the caller). */
-int mmlf_bn_bwd_reduce(const void* dy, int ld_dy, const void* y, int ld_y, const void* z, int ld_z,
+int mmlf_bn_bwd_reduce(const void* dy, int ld_dy, const void* z, int ld_z, const float* scale, const float* shift,
                        const float* save_mean, const float* save_invstd, int C, int B, int H, int W, int grad_dtype,
                        int act_dtype, double* sums, void* stream);
-/* Pass 2: dz = gamma * invstd * (g - sum_g / count - xhat * sum_gx / count) (bf16, halo zero);
- * dgamma = sum_gx, dbeta = sum_g (f32 [C_real]).  fsums: f32 scratch [2 * C].  train = 0 gives the eval-mode gradient dz = g * gamma * invstd. */
-int mmlf_bn_bwd_apply(const void* dy, int ld_dy, const void* y, int ld_y, const void* z, int ld_z,
+/* Pass 2: dz = gamma * invstd * (g - sum_g / count - xhat * sum_gx / count) (16-bit, halo zero);
+ * dgamma = sum_gx, dbeta = sum_g (f32 [C_real]).  fsums: f32 scratch [2 * C].  train = 0 gives the eval-mode gradient
+ * dz = g * gamma * invstd.  dz_colsum (optional, f32 [C]): += sum over slots of dz as stored = the bias gradient of
+ * the convolution in front of the BatchNorm (feed_forward.py:125). */
+int mmlf_bn_bwd_apply(const void* dy, int ld_dy, const void* z, int ld_z, const float* scale, const float* shift,
                       const float* gamma, const float* save_mean, const float* save_invstd, const double* sums,
                       int64_t count, int train, int C_real, int C, int B, int H, int W, int grad_dtype, int act_dtype,
-                      void* dz, int ld_dz, float* dgamma, float* dbeta, float* fsums, void* stream);
+                      void* dz, int ld_dz, float* dgamma, float* dbeta, float* fsums, float* dz_colsum, void* stream);
 
 /* ReLU backward alone (blocks without BatchNorm): dz = dy * (y > 0), bf16 slots. */
 int mmlf_relu_bwd(const void* dy, int ld_dy, const void* y, int ld_y, int C, int64_t n_slots, int grad_dtype,

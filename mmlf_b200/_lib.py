@@ -21,8 +21,10 @@ class ConvArgs(C.Structure):
     _fields_ = [('in_', c_p), ('ld_in', c_i), ('cin_pad', c_i), ('wpack', c_p), ('n_pad', c_i),
                 ('B', c_i), ('H', c_i), ('W', c_i), ('type', c_i),
                 ('bias', c_p), ('scale', c_p), ('shift', c_p), ('relu', c_i),
-                ('gate', c_p), ('ld_gate', c_i), ('out', c_p), ('ld_out', c_i), ('out_mode', c_i),
-                ('n_real', c_i), ('ab_dtype', c_i), ('gate_dtype', c_i), ('out_dtype', c_i)]
+                ('gate_bits', c_p), ('relu_bits', c_p), ('ld_bits', c_i),
+                ('out', c_p), ('ld_out', c_i), ('out_mode', c_i), ('n_real', c_i),
+                ('out2', c_p), ('ld_out2', c_i), ('col_sums', c_p),
+                ('ab_dtype', c_i), ('out_dtype', c_i), ('out2_dtype', c_i)]
 
 
 _PROTOS = {
@@ -45,10 +47,10 @@ _PROTOS = {
     'mmlf_bn_stats': (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     'mmlf_bn_finalize': (c_i, [c_p, c_i, c_i, c_i64, c_p, c_p, c_p, c_p, c_p, c_f, c_f, c_p, c_p, c_p, c_p, c_p]),
     'mmlf_bn_fold_eval': (c_i, [c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_f, c_p, c_p, c_p]),
-    'mmlf_bn_apply_relu': (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_p]),
-    'mmlf_bn_bwd_reduce': (c_i, [c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
-    'mmlf_bn_bwd_apply': (c_i, [c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_i64, c_i, c_i, c_i, c_i, c_i,
-                                c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p]),
+    'mmlf_bn_apply_relu': (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_p, c_i, c_i, c_p]),
+    'mmlf_bn_bwd_reduce': (c_i, [c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
+    'mmlf_bn_bwd_apply': (c_i, [c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i, c_i, c_i, c_i, c_i,
+                                c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p]),
     'mmlf_relu_bwd': (c_i, [c_p, c_i, c_p, c_i, c_i, c_i64, c_i, c_i, c_p, c_i, c_p]),
     'mmlf_head_small': (c_i, [c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_i, c_p, c_p]),
     'mmlf_head_small_bwd': (c_i, [c_p, c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_p]),
@@ -64,6 +66,7 @@ _PROTOS = {
 }
 
 EXPORTS = tuple(_PROTOS)
+ABI_VERSION = 2
 _lib = None
 
 
@@ -80,7 +83,7 @@ def lib():
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.mmlf_abi_version() != 1:
+        if l.mmlf_abi_version() != ABI_VERSION:
             raise RuntimeError('libmmlf_b200.so ABI version mismatch')
         _lib = l
     return _lib

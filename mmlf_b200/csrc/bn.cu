@@ -35,13 +35,14 @@ __device__ __forceinline__ bool slot_valid(int64_t s, int Hp, int Wp) {
 
 // ---------------------------------------------------------------------------- column reductions
 // MODE 0: sum x, sum x^2 (bn_stats)      MODE 1: sum x (colsum)
-// MODE 2: g = dy * (y > 0), xhat = (z - mean) * invstd: sum g, sum g * xhat (bn_bwd_reduce)
+// MODE 2: g = dy * (z * scale + shift > 0), xhat = (z - mean) * invstd: sum g, sum g * xhat (bn_bwd_reduce); the ReLU
+//         mask is recomputed from z exactly as the forward pass computed y = relu(fma(z, scale, shift))
 constexpr int kRedThreads = 256;
 
 template <int MODE>
 __global__ void __launch_bounds__(kRedThreads)
-col_reduce_kernel(const void* __restrict__ x, int ld_x, const void* __restrict__ y, int ld_y,
-                  const void* __restrict__ z, int ld_z, const float* __restrict__ mean,
+col_reduce_kernel(const void* __restrict__ x, int ld_x, const float* __restrict__ scale,
+                  const float* __restrict__ shift, const void* __restrict__ z, int ld_z, const float* __restrict__ mean,
                   const float* __restrict__ invstd, int C, int64_t n_slots, double* __restrict__ sums,
                   float* __restrict__ fsum, int dt_x, int dt_yz) {
   extern __shared__ float red[];                    // [lanes][groups * 16]
@@ -51,10 +52,12 @@ col_reduce_kernel(const void* __restrict__ x, int ld_x, const void* __restrict__
   float a0[8], a1[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.f;
-  float mu[8], is[8];
+  float mu[8], is[8], sc[8], sh[8];
   if (MODE == 2) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { mu[j] = mean[g * 8 + j]; is[j] = invstd[g * 8 + j]; }
+    for (int j = 0; j < 8; ++j) {
+      mu[j] = mean[g * 8 + j]; is[j] = invstd[g * 8 + j]; sc[j] = scale[g * 8 + j]; sh[j] = shift[g * 8 + j];
+    }
   }
   if (sl < lanes) {
     for (int64_t s = static_cast<int64_t>(blockIdx.x) * lanes + sl; s < n_slots; s += static_cast<int64_t>(gridDim.x) * lanes) {
@@ -67,12 +70,11 @@ col_reduce_kernel(const void* __restrict__ x, int ld_x, const void* __restrict__
 #pragma unroll
         for (int j = 0; j < 8; ++j) a0[j] += v[j];
       } else {
-        float yy[8], zz[8];
-        unpack8(ld8(y, s, ld_y, g * 8), yy, dt_yz);
+        float zz[8];
         unpack8(ld8(z, s, ld_z, g * 8), zz, dt_yz);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float gg = yy[j] > 0.f ? v[j] : 0.f;
+          const float gg = fmaf(zz[j], sc[j], sh[j]) > 0.f ? v[j] : 0.f;
           a0[j] += gg;
           a1[j] = fmaf(gg, (zz[j] - mu[j]) * is[j], a1[j]);
         }
@@ -146,10 +148,12 @@ __global__ void bn_fold_eval_kernel(int C_real, int C, const float* __restrict__
 }
 
 // ---------------------------------------------------------------------------- elementwise passes
-// MODE 0: y = relu(z * scale + shift), halo -> 0                     (bn_apply_relu)
+// MODE 0: y = relu(z * scale + shift), halo -> 0; optional second copy of y in another 16-bit format (bn_apply_relu)
 // MODE 1: dz = dy * (y > 0)                                          (relu_bwd)
 // MODE 2: dz = gamma*invstd*(g - sg/n - xhat*sgx/n), halo -> 0       (bn_bwd_apply, train)
 // MODE 3: dz = g * gamma * invstd                                    (bn_bwd_apply, eval-mode BN)
+//         in modes 2/3 g = dy * (z * scale + shift > 0) and, if csum is given, csum[c] += sum_slots dz (as stored):
+//         the bias gradient of the convolution in front of the BatchNorm
 // MODE 4: 16-bit format conversion                                   (convert16)
 // block = (channel groups) x (slot lanes); a thread owns 8 consecutive channels, keeps their per-channel constants
 // in registers and walks the slots with a grid stride, so the per-slot work is 2-4 128-bit memory operations.
@@ -183,18 +187,29 @@ template <int MODE>
 __global__ void __launch_bounds__(256)
 slot_map_kernel(const void* __restrict__ a, int ld_a, const void* __restrict__ y, int ld_y,
                 const void* __restrict__ z, int ld_z, const float* __restrict__ p0, const float* __restrict__ p1,
-                const float* __restrict__ p2, const float* __restrict__ fsums, int C, SlotDiv dv,
-                int64_t n_slots, void* __restrict__ out, int ld_out, int dt_a, int dt_yz) {
+                const float* __restrict__ p2, const float* __restrict__ fsums, const float* __restrict__ scale,
+                const float* __restrict__ shift, int C, SlotDiv dv, int64_t n_slots, void* __restrict__ out, int ld_out,
+                void* __restrict__ out2, int ld_out2, int dt_out2, float* __restrict__ csum, int dt_a, int dt_yz) {
+  extern __shared__ float map_red[];               // [lanes][groups * 8], only used with csum
   const int groups = C >> 3;
   const int lanes = blockDim.x / groups;
   const int g = threadIdx.x % groups, sl = threadIdx.x / groups;
-  if (sl >= lanes) return;
+  const bool active = sl < lanes;
+  if (!active && !((MODE == 2 || MODE == 3) && csum)) return;
   const int c = g * 8;
+  float cs[8], msc[8], msh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) cs[j] = msc[j] = msh[j] = 0.f;
+  if ((MODE == 2 || MODE == 3) && active) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { msc[j] = scale[c + j]; msh[j] = shift[c + j]; }
+  }
   // per-channel constants -> registers (two 128-bit loads per array)
   float k0[8], k1[8], k2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) k0[j] = k1[j] = k2[j] = 0.f;
-  if (MODE == 0) {
+  if (!active) {
+  } else if (MODE == 0) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) { k0[j] = p0[c + j]; k1[j] = p1[c + j]; }             // scale, shift
   } else if (MODE == 2) {
@@ -210,12 +225,14 @@ slot_map_kernel(const void* __restrict__ a, int ld_a, const void* __restrict__ y
 #pragma unroll
     for (int j = 0; j < 8; ++j) k0[j] = p0[c + j] * p2[c + j];
   }
-  for (int64_t s = static_cast<int64_t>(blockIdx.x) * lanes + sl; s < n_slots; s += static_cast<int64_t>(gridDim.x) * lanes) {
+  for (int64_t s = static_cast<int64_t>(blockIdx.x) * lanes + sl; active && s < n_slots;
+       s += static_cast<int64_t>(gridDim.x) * lanes) {
     float r[8];
     if ((MODE == 0 || MODE == 2) && !slot_valid_fast(s, dv)) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) r[j] = 0.f;
       st8(out, s, ld_out, c, pack8(r, dt_a));
+      if (MODE == 0 && out2) st8(out2, s, ld_out2, c, pack8(r, dt_out2));
       continue;
     }
     float av[8];
@@ -228,26 +245,42 @@ slot_map_kernel(const void* __restrict__ a, int ld_a, const void* __restrict__ y
     if (MODE == 0) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) r[j] = fmaxf(fmaf(av[j], k0[j], k1[j]), 0.f);
-    } else {
+      if (out2) st8(out2, s, ld_out2, c, pack8(r, dt_out2));
+    } else if (MODE == 1) {
       float yv[8];
       unpack8(ld8(y, s, ld_y, c), yv, dt_yz);
-      if (MODE == 1) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = yv[j] > 0.f ? av[j] : 0.f;
-      } else if (MODE == 3) {
+      for (int j = 0; j < 8; ++j) r[j] = yv[j] > 0.f ? av[j] : 0.f;
+    } else {
+      float zv[8];
+      unpack8(ld8(z, s, ld_z, c), zv, dt_yz);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = yv[j] > 0.f ? av[j] * k0[j] : 0.f;
-      } else {
-        float zv[8];
-        unpack8(ld8(z, s, ld_z, c), zv, dt_yz);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float gg = yv[j] > 0.f ? av[j] : 0.f;
-          r[j] = fmaf(k0[j], gg, -fmaf(k1[j], zv[j], k2[j]));
-        }
+      for (int j = 0; j < 8; ++j) {
+        const float gg = fmaf(zv[j], msc[j], msh[j]) > 0.f ? av[j] : 0.f;
+        r[j] = MODE == 3 ? gg * k0[j] : fmaf(k0[j], gg, -fmaf(k1[j], zv[j], k2[j]));
       }
     }
-    st8(out, s, ld_out, c, pack8(r, dt_a));
+    const uint4 pk = pack8(r, dt_a);
+    st8(out, s, ld_out, c, pk);
+    if ((MODE == 2 || MODE == 3) && csum) {
+      float rr[8];
+      unpack8(pk, rr, dt_a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cs[j] += rr[j];
+    }
+  }
+  if ((MODE == 2 || MODE == 3) && csum) {
+    const int stride = groups * 8;
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) map_red[sl * stride + c + j] = cs[j];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < stride; i += blockDim.x) {
+      float acc = 0.f;
+      for (int l = 0; l < lanes; ++l) acc += map_red[l * stride + i];
+      atomicAdd(&csum[i], acc);
+    }
   }
 }
 
@@ -303,8 +336,8 @@ extern "C" int mmlf_convert16(const void* src, int ld_src, int src_dtype, void* 
   MMLF_REQUIRE(src && dst, "convert16: null buffer");
   CHECK_C(C);
   slot_map_kernel<4><<<map_grid(n_slots, C), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      src, ld_src, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, nullptr, C, make_div(1, 1, n_slots), n_slots, dst,
-      ld_dst, dst_dtype, src_dtype);
+      src, ld_src, nullptr, 0, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, C, make_div(1, 1, n_slots),
+      n_slots, dst, ld_dst, nullptr, 0, 0, nullptr, dst_dtype, src_dtype);
   return check_launch("convert16");
 }
 
@@ -317,7 +350,7 @@ extern "C" int mmlf_bn_stats(const void* z, int ld, int C, int B, int H, int W, 
   const int groups = C / 8, lanes = kRedThreads / groups;
   const size_t smem = static_cast<size_t>(lanes) * groups * 16 * sizeof(float);
   col_reduce_kernel<0><<<red_grid(n_slots, lanes), kRedThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      z, ld, nullptr, 0, nullptr, 0, nullptr, nullptr, C, n_slots, sums, nullptr, act_dtype, 0);
+      z, ld, nullptr, nullptr, nullptr, 0, nullptr, nullptr, C, n_slots, sums, nullptr, act_dtype, 0);
   return check_launch("bn_stats");
 }
 
@@ -329,7 +362,7 @@ extern "C" int mmlf_colsum16(const void* x, int ld, int C, int64_t n_slots, int 
   const int groups = C / 8, lanes = kRedThreads / groups;
   const size_t smem = static_cast<size_t>(lanes) * groups * 16 * sizeof(float);
   col_reduce_kernel<1><<<red_grid(n_slots, lanes), kRedThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      x, ld, nullptr, 0, nullptr, 0, nullptr, nullptr, C, n_slots, nullptr, out, dtype, 0);
+      x, ld, nullptr, nullptr, nullptr, 0, nullptr, nullptr, C, n_slots, nullptr, out, dtype, 0);
   return check_launch("colsum");
 }
 
@@ -355,13 +388,15 @@ extern "C" int mmlf_bn_fold_eval(int C_real, int C, const float* gamma, const fl
 }
 
 extern "C" int mmlf_bn_apply_relu(const void* z, int ld_z, const float* scale, const float* shift, int C, int B,
-                                  int H, int W, int act_dtype, void* y, int ld_y, void* stream) {
+                                  int H, int W, int act_dtype, void* y, int ld_y, void* y2, int ld_y2, int y2_dtype,
+                                  void* stream) {
   MMLF_REQUIRE(z && scale && shift && y, "bn_apply_relu: null buffer");
   CHECK_C(C);
+  MMLF_REQUIRE(!y2 || (ld_y2 >= C && ld_y2 % 8 == 0), "bn_apply_relu: bad ld_y2 %d", ld_y2);
   const int64_t n_slots = static_cast<int64_t>(B) * (H + 1) * (W + 1);
   slot_map_kernel<0><<<map_grid(n_slots, C), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      z, ld_z, nullptr, 0, nullptr, 0, scale, shift, nullptr, nullptr, C, make_div(H + 1, W + 1, n_slots), n_slots, y, ld_y,
-      act_dtype, act_dtype);
+      z, ld_z, nullptr, 0, nullptr, 0, scale, shift, nullptr, nullptr, nullptr, nullptr, C,
+      make_div(H + 1, W + 1, n_slots), n_slots, y, ld_y, y2, ld_y2, y2_dtype, nullptr, act_dtype, act_dtype);
   return check_launch("bn_apply_relu");
 }
 
@@ -370,30 +405,30 @@ extern "C" int mmlf_relu_bwd(const void* dy, int ld_dy, const void* y, int ld_y,
   MMLF_REQUIRE(dy && y && dz, "relu_bwd: null buffer");
   CHECK_C(C);
   slot_map_kernel<1><<<map_grid(n_slots, C), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      dy, ld_dy, y, ld_y, nullptr, 0, nullptr, nullptr, nullptr, nullptr, C, make_div(1, 1, n_slots), n_slots, dz, ld_dz,
-      grad_dtype, act_dtype);
+      dy, ld_dy, y, ld_y, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, C, make_div(1, 1, n_slots),
+      n_slots, dz, ld_dz, nullptr, 0, 0, nullptr, grad_dtype, act_dtype);
   return check_launch("relu_bwd");
 }
 
-extern "C" int mmlf_bn_bwd_reduce(const void* dy, int ld_dy, const void* y, int ld_y, const void* z, int ld_z,
-                                  const float* save_mean, const float* save_invstd, int C, int B, int H, int W,
-                                  int grad_dtype, int act_dtype, double* sums, void* stream) {
-  MMLF_REQUIRE(dy && y && z && save_mean && save_invstd && sums, "bn_bwd_reduce: null buffer");
+extern "C" int mmlf_bn_bwd_reduce(const void* dy, int ld_dy, const void* z, int ld_z, const float* scale,
+                                  const float* shift, const float* save_mean, const float* save_invstd, int C, int B,
+                                  int H, int W, int grad_dtype, int act_dtype, double* sums, void* stream) {
+  MMLF_REQUIRE(dy && z && scale && shift && save_mean && save_invstd && sums, "bn_bwd_reduce: null buffer");
   CHECK_C(C);
   const int64_t n_slots = static_cast<int64_t>(B) * (H + 1) * (W + 1);
   const int groups = C / 8, lanes = kRedThreads / groups;
   const size_t smem = static_cast<size_t>(lanes) * groups * 16 * sizeof(float);
   col_reduce_kernel<2><<<red_grid(n_slots, lanes), kRedThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      dy, ld_dy, y, ld_y, z, ld_z, save_mean, save_invstd, C, n_slots, sums, nullptr, grad_dtype, act_dtype);
+      dy, ld_dy, scale, shift, z, ld_z, save_mean, save_invstd, C, n_slots, sums, nullptr, grad_dtype, act_dtype);
   return check_launch("bn_bwd_reduce");
 }
 
-extern "C" int mmlf_bn_bwd_apply(const void* dy, int ld_dy, const void* y, int ld_y, const void* z, int ld_z,
-                                 const float* gamma, const float* save_mean, const float* save_invstd,
-                                 const double* sums, int64_t count, int train, int C_real, int C, int B, int H, int W,
-                                 int grad_dtype, int act_dtype, void* dz, int ld_dz, float* dgamma, float* dbeta,
-                                 float* fsums, void* stream) {
-  MMLF_REQUIRE(dy && y && z && gamma && save_mean && save_invstd && sums && dz, "bn_bwd_apply: null buffer");
+extern "C" int mmlf_bn_bwd_apply(const void* dy, int ld_dy, const void* z, int ld_z, const float* scale,
+                                 const float* shift, const float* gamma, const float* save_mean,
+                                 const float* save_invstd, const double* sums, int64_t count, int train, int C_real,
+                                 int C, int B, int H, int W, int grad_dtype, int act_dtype, void* dz, int ld_dz,
+                                 float* dgamma, float* dbeta, float* fsums, float* dz_colsum, void* stream) {
+  MMLF_REQUIRE(dy && z && scale && shift && gamma && save_mean && save_invstd && sums && dz, "bn_bwd_apply: null buffer");
   CHECK_C(C);
   const int64_t n_slots = static_cast<int64_t>(B) * (H + 1) * (W + 1);
   const int blocks = map_grid(n_slots, C);
@@ -403,11 +438,14 @@ extern "C" int mmlf_bn_bwd_apply(const void* dy, int ld_dy, const void* y, int l
   bn_bwd_means_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, 1.0 / static_cast<double>(count), C_real, C, fsums, dgamma,
                                                          dbeta);
   if (int rc = check_launch("bn_bwd_means")) return rc;
+  const size_t smem = dz_colsum ? sizeof(float) * 256 * 8 : 0;
   if (train)
-    slot_map_kernel<2><<<blocks, 256, 0, st>>>(dy, ld_dy, y, ld_y, z, ld_z, gamma, save_mean, save_invstd, fsums, C, dv,
-                                               n_slots, dz, ld_dz, grad_dtype, act_dtype);
+    slot_map_kernel<2><<<blocks, 256, smem, st>>>(dy, ld_dy, nullptr, 0, z, ld_z, gamma, save_mean, save_invstd, fsums,
+                                                  scale, shift, C, dv, n_slots, dz, ld_dz, nullptr, 0, 0, dz_colsum,
+                                                  grad_dtype, act_dtype);
   else
-    slot_map_kernel<3><<<blocks, 256, 0, st>>>(dy, ld_dy, y, ld_y, z, ld_z, gamma, save_mean, save_invstd, fsums, C, dv,
-                                               n_slots, dz, ld_dz, grad_dtype, act_dtype);
+    slot_map_kernel<3><<<blocks, 256, smem, st>>>(dy, ld_dy, nullptr, 0, z, ld_z, gamma, save_mean, save_invstd, fsums,
+                                                  scale, shift, C, dv, n_slots, dz, ld_dz, nullptr, 0, 0, dz_colsum,
+                                                  grad_dtype, act_dtype);
   return check_launch("bn_bwd_apply");
 }

@@ -242,8 +242,8 @@ extern "C" int mmlf_conv2x2_wgrad(const void* dout, int ld_dout, int n_pad, cons
   const uint32_t smem_bytes = 1024 + stages * stage_bytes + aux_bytes;
 
   CUtensorMap tmap_act, tmap_dout;
-  if (int rc = make_tmap_2d_bf16(&tmap_act, act, cin_pad, p.n_slots, static_cast<uint64_t>(ld_act) * 2, 64, kWgKb)) return rc;
-  if (int rc = make_tmap_2d_bf16(&tmap_dout, dout, n_pad, p.n_slots, static_cast<uint64_t>(ld_dout) * 2, 64, kWgKb)) return rc;
+  if (int rc = make_tmap_2d_16(&tmap_act, act, cin_pad, p.n_slots, static_cast<uint64_t>(ld_act) * 2, 64, kWgKb, 128)) return rc;
+  if (int rc = make_tmap_2d_16(&tmap_dout, dout, n_pad, p.n_slots, static_cast<uint64_t>(ld_dout) * 2, 64, kWgKb, 128)) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv2x2_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);

@@ -43,8 +43,8 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
-                      uint32_t box_inner, uint32_t box_outer) {
+int make_tmap_2d_16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                    uint32_t box_inner, uint32_t box_outer, int swizzle_bytes) {
   EncodeTiledFn enc = get_encode();
   MMLF_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
   MMLF_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
@@ -54,8 +54,11 @@ int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64
   cuuint64_t strides[1] = {pitch_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
+  MMLF_REQUIRE(swizzle_bytes == 128 || swizzle_bytes == 64, "TMA swizzle must be 64 or 128 bytes");
+  MMLF_REQUIRE(box_inner * 2 <= static_cast<uint32_t>(swizzle_bytes), "TMA box rows must fit the swizzle span");
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MMLF_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (inner %llu outer %llu pitch %llu box %u x %u)",
                (int)r, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)pitch_bytes,

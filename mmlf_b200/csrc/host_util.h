@@ -13,10 +13,10 @@ namespace mmlf {
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 
-// 2-D bf16 tensor map: dims {inner, outer}, row pitch in bytes, box {box_inner, box_outer}, 128 B swizzle,
-// out-of-bounds elements read as zero.
-int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
-                      uint32_t box_inner, uint32_t box_outer);
+// 2-D tensor map over 16-bit elements (bf16 / fp16 move identically): dims {inner, outer}, row pitch in bytes,
+// box {box_inner, box_outer}, 64 or 128 B swizzle; out-of-bounds elements read as zero and are not written.
+int make_tmap_2d_16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                    uint32_t box_inner, uint32_t box_outer, int swizzle_bytes);
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

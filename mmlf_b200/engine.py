@@ -23,6 +23,11 @@ def pad16(x):
     return (x + 15) // 16 * 16
 
 
+def bits_words(n_pad):
+    """Words per slot of a ReLU sign-bit array (one bit per channel)."""
+    return (n_pad + 31) // 32
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
@@ -79,6 +84,7 @@ class Engine:
         self.wp = pad16(self.width)                     # 288
         assert self.feat_ld <= 320 and self.wp <= 320, 'model_chs too large for the 320-column TMEM plan'
         self._pack_version = None
+        self._fold_cache = {}
         self._build_specs()
 
     @property
@@ -173,11 +179,12 @@ class Engine:
 
     # ------------------------------------------------------------------ kernel launch helpers
     def conv(self, geo, x, ld_in, cs, w, n_pad, cin_pad, ctype, out, ld_out, *, bias=None, scale=None, shift=None,
-             relu=False, gate=None, ld_gate=0, out_mode=0, n_real=0, simt=False, ab=None, out_dt=None, gate_dt=None):
+             relu=False, gate_bits=None, relu_bits=None, out_mode=0, n_real=0, simt=False, ab=None, out_dt=None,
+             out2=None, ld_out2=0, out2_dt=None, col_sums=None):
         a = ConvArgs()
         a.ab_dtype = self.act if ab is None else ab
         a.out_dtype = self.act if out_dt is None else out_dt
-        a.gate_dtype = self.act if gate_dt is None else gate_dt
+        a.out2_dtype = GRAD if out2_dt is None else out2_dt
         a.in_, a.ld_in, a.cin_pad = x.data_ptr(), ld_in, cin_pad
         a.wpack, a.n_pad = w.data_ptr(), n_pad
         a.B, a.H, a.W, a.type = geo.B, geo.H, geo.W, ctype
@@ -185,9 +192,13 @@ class Engine:
         a.scale = scale.data_ptr() if scale is not None else None
         a.shift = shift.data_ptr() if shift is not None else None
         a.relu = 1 if relu else 0
-        a.gate = gate.data_ptr() if gate is not None else None
-        a.ld_gate = ld_gate
+        a.gate_bits = gate_bits.data_ptr() if gate_bits is not None else None
+        a.relu_bits = relu_bits.data_ptr() if relu_bits is not None else None
+        a.ld_bits = bits_words(n_pad)
         a.out, a.ld_out, a.out_mode, a.n_real = out.data_ptr(), ld_out, out_mode, n_real
+        a.out2 = out2.data_ptr() if out2 is not None else None
+        a.ld_out2 = ld_out2
+        a.col_sums = col_sums.data_ptr() if col_sums is not None else None
         call('mmlf_conv2x2_simt' if simt else 'mmlf_conv2x2', C.byref(a), _stream())
 
     def _slots(self, geo, ch, dtype=None):
@@ -198,10 +209,19 @@ class Engine:
             dtype = _TORCH_DT[dtype]
         return torch.empty((geo.n_slots, ch), dtype=dtype, device=self.dev)
 
+    def _bits(self, geo, n_pad):
+        """ReLU sign bits of a slot array: one word per 32 channels."""
+        return torch.empty((geo.n_slots, bits_words(n_pad)), dtype=torch.int32, device=self.dev)
+
     # ------------------------------------------------------------------ forward
     def forward(self, views, training, save, shift_disp=None):
         """views: list of (B, n, 3, H, W) fp32 CUDA tensors (h, v[, i, d]).  Returns (B, OC, H, W) fp32 and, when
-        ``save`` is set, the tape needed by :meth:`backward`.  ``shift_disp`` fuses the ESE Shift into the packing."""
+        ``save`` is set, the tape needed by :meth:`backward`.  ``shift_disp`` fuses the ESE Shift into the packing.
+
+        With ``save`` every activation that the backward pass multiplies on the tensor cores (block inputs and the
+        ReLU'd output of each first conv) is additionally written in the gradient format (bf16) by the kernel that
+        produces it -- tcgen05 kind::f16 needs both operands of the weight-gradient GEMM in one format -- and the
+        fp16 copies are dropped as soon as the next layer has consumed them."""
         _lib.require_device()
         h = views[0]
         B, n, c3, H, W = h.shape
@@ -214,17 +234,21 @@ class Engine:
         bufs = self._buffers()
         params = self._params()
         cin0_pad = pad16(n * c3)
+        dual = save and self.act != GRAD          # keep a bf16 copy of the MMA operands of the backward pass
 
         feats = self._slots(geo, self.feat_ld)
+        featsg = self._slots(geo, self.feat_ld, GRAD) if dual else (feats if save else None)
         for si, (key, net, spatial) in enumerate(self.stream_defs):
             v = views[si]
             assert v.is_cuda and v.dtype == torch.float32 and v.is_contiguous(), \
                 'view stacks must be contiguous fp32 CUDA tensors (feed_forward.py:226-232 uses .view)'
             x = self._slots(geo, cin0_pad)
-            if shift_disp is None:
-                call('mmlf_pack_views', _ptr(v), B, n * c3, H, W, _ptr(x), cin0_pad, self.act, st)
-            else:
-                call('mmlf_shift_pack', _ptr(v), si, B, n, H, W, float(shift_disp), _ptr(x), cin0_pad, self.act, st)
+            xg = self._slots(geo, cin0_pad, GRAD) if dual else (x if save else None)
+            for dst, dt in ((x, self.act),) + (((xg, GRAD),) if dual else ()):
+                if shift_disp is None:
+                    call('mmlf_pack_views', _ptr(v), B, n * c3, H, W, _ptr(dst), cin0_pad, dt, st)
+                else:
+                    call('mmlf_shift_pack', _ptr(v), si, B, n, H, W, float(shift_disp), _ptr(dst), cin0_pad, dt, st)
             ld_x = cin0_pad
             recs = []
             blocks = self.in_specs[key]
@@ -232,23 +256,27 @@ class Engine:
                 last = k == len(blocks) - 1
                 if last:      # write straight into this stream's slice of the concatenated feature buffer
                     y, ld_y = feats[:, si * self.cp:], self.feat_ld
+                    yg = featsg[:, si * self.cp:] if save else None
                 else:
                     y, ld_y = self._slots(geo, c2.n_pad), c2.n_pad
-                rec = self._block_fwd(geo, x, ld_x, c1, c2, bnp, y, ld_y, training, bn_train, save, bufs, params)
+                    yg = self._slots(geo, c2.n_pad, GRAD) if dual else (y if save else None)
+                rec = self._block_fwd(geo, x, xg, ld_x, c1, c2, bnp, y, yg, ld_y, training, bn_train, save, bufs, params)
                 recs.append(rec)
-                x, ld_x = y, ld_y
+                x, xg, ld_x = y, yg, ld_y
             if save:
                 tape['streams'][key] = recs
-        x, ld_x = feats, self.feat_ld
+        x, xg, ld_x = feats, featsg, self.feat_ld
         for k, (c1, c2, bnp) in enumerate(self.out_specs):
             y = self._slots(geo, c2.n_pad)
-            rec = self._block_fwd(geo, x, ld_x, c1, c2, bnp, y, c2.n_pad, training, bn_train, save, bufs, params)
+            yg = self._slots(geo, c2.n_pad, GRAD) if dual else (y if save else None)
+            rec = self._block_fwd(geo, x, xg, ld_x, c1, c2, bnp, y, yg, c2.n_pad, training, bn_train, save, bufs, params)
             if save:
                 tape['out'].append(rec)
-            x, ld_x = y, c2.n_pad
+            x, xg, ld_x = y, yg, c2.n_pad
         # head block: conv -> ReLU -> conv, no BN / ReLU after (feed_forward.py:185)
         h1 = self.head1
         out = torch.empty((B, self.oc, H, W), dtype=torch.float32, device=self.dev)
+        midg = bits = None
         if self.small_head:
             mid = self._slots(geo, h1.n_pad, torch.float32)
             self.conv(geo, x, ld_x, h1, h1.w_fwd, h1.n_pad, h1.cin_pad, 0, mid, h1.n_pad, bias=h1.bias_pad, relu=True,
@@ -259,50 +287,78 @@ class Engine:
         else:
             h2 = self.head2
             mid = self._slots(geo, h1.n_pad)
-            self.conv(geo, x, ld_x, h1, h1.w_fwd, h1.n_pad, h1.cin_pad, 0, mid, h1.n_pad, bias=h1.bias_pad, relu=True)
+            if save:
+                midg = self._slots(geo, h1.n_pad, GRAD) if dual else mid
+                bits = self._bits(geo, h1.n_pad)
+            self.conv(geo, x, ld_x, h1, h1.w_fwd, h1.n_pad, h1.cin_pad, 0, mid, h1.n_pad, bias=h1.bias_pad, relu=True,
+                      out2=midg if dual else None, ld_out2=h1.n_pad, relu_bits=bits)
             self.conv(geo, mid, h1.n_pad, h2, h2.w_fwd, h2.n_pad, h2.cin_pad, 1, out, 0, bias=h2.bias_pad,
                       out_mode=2, n_real=self.oc)
         if save:
-            tape['head'] = {'x': x, 'ld_x': ld_x, 'mid': mid}
+            tape['head'] = {'xg': xg, 'ld_x': ld_x, 'mid': mid if self.small_head else None, 'midg': midg, 'bits': bits}
         return out, tape
 
-    def _block_fwd(self, geo, x, ld_x, c1, c2, bnp, y, ld_y, training, bn_train, save, bufs, params):
-        """conv(k2,p1) -> ReLU -> conv(k2,p0) [-> BN] -> ReLU   (feed_forward.py:122-137)"""
+    def _block_fwd(self, geo, x, xg, ld_x, c1, c2, bnp, y, yg, ld_y, training, bn_train, save, bufs, params):
+        """conv(k2,p1) -> ReLU -> conv(k2,p0) [-> BN] -> ReLU   (feed_forward.py:122-137).  x / y are the block input
+        and output in the activation format, xg / yg their gradient-format twins (None unless ``save``)."""
         st = _stream()
+        dual = save and self.act != GRAD
         a1 = self._slots(geo, c1.n_pad)
-        self.conv(geo, x, ld_x, c1, c1.w_fwd, c1.n_pad, c1.cin_pad, 0, a1, c1.n_pad, bias=c1.bias_pad, relu=True)
-        rec = {'x': x, 'ld_x': ld_x, 'a1': a1, 'y': y, 'ld_y': ld_y, 'c1': c1, 'c2': c2, 'bnp': bnp} if save else None
+        a1g = bits = None
+        if save:
+            a1g = self._slots(geo, c1.n_pad, GRAD) if dual else a1
+            bits = self._bits(geo, c1.n_pad)
+        self.conv(geo, x, ld_x, c1, c1.w_fwd, c1.n_pad, c1.cin_pad, 0, a1, c1.n_pad, bias=c1.bias_pad, relu=True,
+                  out2=a1g if dual else None, ld_out2=c1.n_pad, relu_bits=bits)
+        rec = {'xg': xg, 'ld_x': ld_x, 'a1g': a1g, 'bits': bits, 'yg': yg, 'ld_y': ld_y, 'c1': c1, 'c2': c2,
+               'bnp': bnp} if save else None
         C_real, Cp = c2.cout, c2.n_pad
         if not self.has_bn:
-            self.conv(geo, a1, c1.n_pad, c2, c2.w_fwd, Cp, c2.cin_pad, 1, y, ld_y, bias=c2.bias_pad, relu=True)
+            self.conv(geo, a1, c1.n_pad, c2, c2.w_fwd, Cp, c2.cin_pad, 1, y, ld_y, bias=c2.bias_pad, relu=True,
+                      out2=yg if dual else None, ld_out2=ld_y)
             return rec
         gamma, beta = params[bnp + '.weight'].detach(), params[bnp + '.bias'].detach()
         rmean, rvar = bufs[bnp + '.running_mean'], bufs[bnp + '.running_var']
-        scale = torch.empty(Cp, dtype=torch.float32, device=self.dev)
-        shift = torch.empty(Cp, dtype=torch.float32, device=self.dev)
         if not bn_train:
             # eval: BN folded into the conv epilogue, y = relu(acc * scale + shift)
-            call('mmlf_bn_fold_eval', C_real, Cp, _ptr(gamma), _ptr(beta), _ptr(rmean), _ptr(rvar),
-                 _ptr(c2.bias_pad), float(self.m.bn_eps), _ptr(scale), _ptr(shift), st)
+            scale, shift = self._eval_fold(bnp, c2, gamma, beta, rmean, rvar)
             self.conv(geo, a1, c1.n_pad, c2, c2.w_fwd, Cp, c2.cin_pad, 1, y, ld_y, scale=scale, shift=shift, relu=True)
             if save:
                 raise NotImplementedError('--train_eval_mode (training through eval-mode BatchNorm) is not supported')
             return rec
+        scale = torch.empty(Cp, dtype=torch.float32, device=self.dev)
+        shift = torch.empty(Cp, dtype=torch.float32, device=self.dev)
         z = self._slots(geo, Cp)
-        self.conv(geo, a1, c1.n_pad, c2, c2.w_fwd, Cp, c2.cin_pad, 1, z, Cp, bias=c2.bias_pad)
+        # batch statistics (sum, sum of squares of the stored z) come out of the conv epilogue
         sums = torch.zeros(2 * Cp, dtype=torch.float64, device=self.dev)
-        call('mmlf_bn_stats', _ptr(z), Cp, Cp, geo.B, geo.H, geo.W, self.act, _ptr(sums), st)
+        self.conv(geo, a1, c1.n_pad, c2, c2.w_fwd, Cp, c2.cin_pad, 1, z, Cp, bias=c2.bias_pad, col_sums=sums)
         save_mean = torch.empty(Cp, dtype=torch.float32, device=self.dev)
         save_invstd = torch.empty(Cp, dtype=torch.float32, device=self.dev)
         nbt = bufs.get(bnp + '.num_batches_tracked')
         call('mmlf_bn_finalize', _ptr(sums), C_real, Cp, geo.count, _ptr(gamma), _ptr(beta), _ptr(rmean), _ptr(rvar),
              _ptr(nbt), float(self.m.batchnorm_momentum), float(self.m.bn_eps), _ptr(scale), _ptr(shift),
              _ptr(save_mean), _ptr(save_invstd), st)
+        torch.autograd.graph.increment_version([t for t in (rmean, rvar, nbt) if t is not None])   # raw-pointer writes
         call('mmlf_bn_apply_relu', _ptr(z), Cp, _ptr(scale), _ptr(shift), Cp, geo.B, geo.H, geo.W, self.act, _ptr(y),
-             ld_y, st)
+             ld_y, _ptr(yg) if dual else C.c_void_p(0), ld_y, GRAD, st)
         if save:
-            rec.update(z=z, save_mean=save_mean, save_invstd=save_invstd)
+            rec.update(z=z, scale=scale, shift=shift, save_mean=save_mean, save_invstd=save_invstd)
         return rec
+
+    def _eval_fold(self, bnp, c2, gamma, beta, rmean, rvar):
+        """Eval-mode BN folded to per-channel scale / shift; cached until a parameter or running statistic changes."""
+        key = (gamma._version, beta._version, rmean._version, rvar._version, c2.bias_pad._version,
+               gamma.data_ptr(), rmean.data_ptr())
+        hit = self._fold_cache.get(bnp)
+        if hit is not None and hit[0] == key:
+            return hit[1], hit[2]
+        Cp = c2.n_pad
+        scale = torch.empty(Cp, dtype=torch.float32, device=self.dev)
+        shift = torch.empty(Cp, dtype=torch.float32, device=self.dev)
+        call('mmlf_bn_fold_eval', c2.cout, Cp, _ptr(gamma), _ptr(beta), _ptr(rmean), _ptr(rvar),
+             _ptr(c2.bias_pad), float(self.m.bn_eps), _ptr(scale), _ptr(shift), _stream())
+        self._fold_cache[bnp] = (key, scale, shift)
+        return scale, shift
 
     # ------------------------------------------------------------------ backward
     def backward(self, tape, g_out):
@@ -316,17 +372,11 @@ class Engine:
         ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
         dwp = torch.empty(320 * 4 * 320, dtype=torch.float32, device=dev)
 
-        cvt = None
-        if self.act != GRAD:
-            cvt = torch.empty((geo.n_slots, max(cs.cin_pad for cs in self.all_convs())), dtype=_TORCH_DT[GRAD], device=dev)
-
-        def conv_param_grads(cs, dout, ld_dout, act, ld_act):
-            """dW via the tcgen05 wgrad kernel, db via a column sum; accumulates for shared modules.  The wgrad GEMM
-            needs both operands in one 16-bit format, so fp16 activations are converted to bf16 first."""
-            if cvt is not None:
-                call('mmlf_convert16', _ptr(act), ld_act, self.act, _ptr(cvt), cs.cin_pad, GRAD, cs.cin_pad, geo.n_slots, st)
-                act, ld_act = cvt, cs.cin_pad
-            call('mmlf_conv2x2_wgrad', _ptr(dout), ld_dout, cs.n_pad, _ptr(act), ld_act, cs.cin_pad, geo.B, geo.H,
+        def conv_param_grads(cs, dout, ld_dout, actg, ld_act, dbias=None):
+            """dW via the tcgen05 wgrad kernel (both operands in the gradient format); db from ``dbias`` when the
+            kernel that produced ``dout`` already summed its columns, else via a column-sum pass.  Accumulates for
+            modules that are called twice per forward."""
+            call('mmlf_conv2x2_wgrad', _ptr(dout), ld_dout, cs.n_pad, _ptr(actg), ld_act, cs.cin_pad, geo.B, geo.H,
                  geo.W, cs.type, GRAD, GRAD, _ptr(ws), _ptr(dwp), st)
             wname, bname = cs.name + '.weight', cs.name + '.bias'
             acc = wname in grads
@@ -335,12 +385,15 @@ class Engine:
                 grads[bname] = torch.zeros(cs.n_pad, dtype=torch.float32, device=dev)
             call('mmlf_unpack_conv_wgrad', _ptr(dwp), cs.n_pad, cs.cin_pad, cs.cout, cs.cin, cs.spatial, cs.groups,
                  cs.group_real, cs.group_pad, _ptr(grads[wname]), 1 if acc else 0, st)
-            call('mmlf_colsum16', _ptr(dout), ld_dout, cs.n_pad, geo.n_slots, GRAD, _ptr(grads[bname]), 1, st)
+            if dbias is None:
+                call('mmlf_colsum16', _ptr(dout), ld_dout, cs.n_pad, geo.n_slots, GRAD, _ptr(grads[bname]), 1, st)
+            else:
+                grads[bname] += dbias[:cs.n_pad]
 
-        def dgrad(cs, dout, ld_dout, out, ld_out, gate=None, ld_gate=0):
+        def dgrad(cs, dout, ld_dout, out, ld_out, gate_bits=None, col_sums=None):
             """Data gradient: the conv kernel of the other type with rotated, transposed weights."""
-            self.conv(geo, dout, ld_dout, cs, cs.w_dgrad, cs.cin_pad, cs.n_pad, 1 - cs.type, out, ld_out, gate=gate,
-                      ld_gate=ld_gate, ab=GRAD, out_dt=GRAD, gate_dt=self.act)
+            self.conv(geo, dout, ld_dout, cs, cs.w_dgrad, cs.cin_pad, cs.n_pad, 1 - cs.type, out, ld_out,
+                      gate_bits=gate_bits, ab=GRAD, out_dt=GRAD, col_sums=col_sums)
 
         # ---- head
         hd = tape['head']
@@ -354,14 +407,16 @@ class Engine:
             grads[h2n + '.bias'] = torch.zeros_like(params[h2n + '.bias'])
             call('mmlf_head_small_bwd', _ptr(g_out), _ptr(hd['mid']), h1.n_pad, self.oc, _ptr(w2), geo.B, geo.H, geo.W,
                  _ptr(gmid), h1.n_pad, _ptr(grads[h2n + '.weight']), _ptr(grads[h2n + '.bias']), st)
+            conv_param_grads(h1, gmid, h1.n_pad, hd['xg'], hd['ld_x'])
         else:
             h2 = self.head2
             gz = self._slots(geo, h2.n_pad, GRAD)
             call('mmlf_pack_views', _ptr(g_out), geo.B, self.oc, geo.H, geo.W, _ptr(gz), h2.n_pad, GRAD, st)
-            conv_param_grads(h2, gz, h2.n_pad, hd['mid'], h1.n_pad)
+            conv_param_grads(h2, gz, h2.n_pad, hd['midg'], h1.n_pad)
             gmid = self._slots(geo, h1.n_pad, GRAD)
-            dgrad(h2, gz, h2.n_pad, gmid, h1.n_pad, gate=hd['mid'], ld_gate=h1.n_pad)
-        conv_param_grads(h1, gmid, h1.n_pad, hd['x'], hd['ld_x'])
+            sums = torch.zeros(2 * h1.n_pad, dtype=torch.float64, device=dev)
+            dgrad(h2, gz, h2.n_pad, gmid, h1.n_pad, gate_bits=hd['bits'], col_sums=sums)
+            conv_param_grads(h1, gmid, h1.n_pad, hd['xg'], hd['ld_x'], dbias=sums.float())
         dgrad(h1, gmid, h1.n_pad, g_x, h1.cin_pad)
         gy, ld_gy = g_x, h1.cin_pad
 
@@ -369,9 +424,10 @@ class Engine:
             c1, c2, bnp = rec['c1'], rec['c2'], rec['bnp']
             Cp, C_real = c2.n_pad, c2.cout
             dz = self._slots(geo, Cp, GRAD)
+            db2 = None
             if self.has_bn:
                 sums = torch.zeros(2 * Cp, dtype=torch.float64, device=dev)
-                call('mmlf_bn_bwd_reduce', _ptr(gy), ld_gy, _ptr(rec['y']), rec['ld_y'], _ptr(rec['z']), Cp,
+                call('mmlf_bn_bwd_reduce', _ptr(gy), ld_gy, _ptr(rec['z']), Cp, _ptr(rec['scale']), _ptr(rec['shift']),
                      _ptr(rec['save_mean']), _ptr(rec['save_invstd']), Cp, geo.B, geo.H, geo.W, GRAD, self.act,
                      _ptr(sums), st)
                 gpad, _ = self._bn_padded(bnp, C_real, Cp, dev)
@@ -379,21 +435,24 @@ class Engine:
                 fsums = torch.empty(2 * Cp, dtype=torch.float32, device=dev)
                 dgam = torch.empty(C_real, dtype=torch.float32, device=dev)
                 dbet = torch.empty(C_real, dtype=torch.float32, device=dev)
-                call('mmlf_bn_bwd_apply', _ptr(gy), ld_gy, _ptr(rec['y']), rec['ld_y'], _ptr(rec['z']), Cp, _ptr(gpad),
-                     _ptr(rec['save_mean']), _ptr(rec['save_invstd']), _ptr(sums), geo.count, 1, C_real, Cp, geo.B,
-                     geo.H, geo.W, GRAD, self.act, _ptr(dz), Cp, _ptr(dgam), _ptr(dbet), _ptr(fsums), st)
+                db2 = torch.zeros(Cp, dtype=torch.float32, device=dev)
+                call('mmlf_bn_bwd_apply', _ptr(gy), ld_gy, _ptr(rec['z']), Cp, _ptr(rec['scale']), _ptr(rec['shift']),
+                     _ptr(gpad), _ptr(rec['save_mean']), _ptr(rec['save_invstd']), _ptr(sums), geo.count, 1, C_real, Cp,
+                     geo.B, geo.H, geo.W, GRAD, self.act, _ptr(dz), Cp, _ptr(dgam), _ptr(dbet), _ptr(fsums), _ptr(db2),
+                     st)
                 if acc:
                     grads[bnp + '.weight'] += dgam
                     grads[bnp + '.bias'] += dbet
                 else:
                     grads[bnp + '.weight'], grads[bnp + '.bias'] = dgam, dbet
             else:
-                call('mmlf_relu_bwd', _ptr(gy), ld_gy, _ptr(rec['y']), rec['ld_y'], Cp, geo.n_slots, GRAD, self.act,
+                call('mmlf_relu_bwd', _ptr(gy), ld_gy, _ptr(rec['yg']), rec['ld_y'], Cp, geo.n_slots, GRAD, GRAD,
                      _ptr(dz), Cp, st)
-            conv_param_grads(c2, dz, Cp, rec['a1'], c1.n_pad)
+            conv_param_grads(c2, dz, Cp, rec['a1g'], c1.n_pad, dbias=db2)
             da1 = self._slots(geo, c1.n_pad, GRAD)
-            dgrad(c2, dz, Cp, da1, c1.n_pad, gate=rec['a1'], ld_gate=c1.n_pad)
-            conv_param_grads(c1, da1, c1.n_pad, rec['x'], rec['ld_x'])
+            sums1 = torch.zeros(2 * c1.n_pad, dtype=torch.float64, device=dev)
+            dgrad(c2, dz, Cp, da1, c1.n_pad, gate_bits=rec['bits'], col_sums=sums1)
+            conv_param_grads(c1, da1, c1.n_pad, rec['xg'], rec['ld_x'], dbias=sums1.float())
             if not need_gx:
                 return None
             gx = self._slots(geo, c1.cin_pad, GRAD)

@@ -62,12 +62,34 @@ def pack_weight(w, spatial=0, dgrad=0, groups=1, group_real=None, group_pad=None
     return out
 
 
+def pack_bits(mask, ld_bits=None):
+    """numpy bool (n_slots, C) -> torch int32 [n_slots][ld_bits] words, bit (c & 31) of word c // 32."""
+    n, Cc = mask.shape
+    words = (Cc + 31) // 32
+    ld_bits = ld_bits or words
+    m = np.zeros((n, ld_bits * 32), np.uint8)
+    m[:, :Cc] = mask
+    packed = np.packbits(m.reshape(n, ld_bits, 32), axis=2, bitorder='little').view(np.uint32).reshape(n, ld_bits)
+    return torch.from_numpy(packed.view(np.int32).copy()).to(DEV)
+
+
+def unpack_bits(t, Cc):
+    a = t.cpu().numpy().view(np.uint32)
+    bits = np.unpackbits(a.view(np.uint8).reshape(a.shape[0], -1), axis=1, bitorder='little')
+    return bits[:, :Cc].astype(bool)
+
+
 def run_conv(x_slots, ld_in, cin_pad, wpack, n_pad, B, H, W, ctype, *, bias=None, scale=None, shift=None, relu=False,
-             gate=None, ld_gate=0, out_mode=0, n_real=0, simt=False, ld_out=None, ab=BF16, out_dt=BF16, gate_dt=BF16):
+             gate_bits=None, relu_bits=None, ld_bits=0, out_mode=0, n_real=0, simt=False, ld_out=None, ab=BF16,
+             out_dt=BF16, out2_dt=None, col_sums=None):
+    """Returns out, or (out, out2) when out2_dt is given."""
     n_slots = B * (H + 1) * (W + 1)
     ld_out = ld_out or n_pad
+    out2 = None
     if out_mode == 0:
         out = torch.full((n_slots, ld_out), float('nan'), dtype=TDT[out_dt], device=DEV)
+        if out2_dt is not None:
+            out2 = torch.full((n_slots, ld_out), float('nan'), dtype=TDT[out2_dt], device=DEV)
     elif out_mode == 1:
         out = torch.full((n_slots, ld_out), float('nan'), dtype=torch.float32, device=DEV)
     else:
@@ -81,13 +103,17 @@ def run_conv(x_slots, ld_in, cin_pad, wpack, n_pad, B, H, W, ctype, *, bias=None
     a.scale = scale.data_ptr() if scale is not None else None
     a.shift = shift.data_ptr() if shift is not None else None
     a.relu = int(relu)
-    a.gate = gate.data_ptr() if gate is not None else None
-    a.ld_gate = ld_gate
+    a.gate_bits = gate_bits.data_ptr() if gate_bits is not None else None
+    a.relu_bits = relu_bits.data_ptr() if relu_bits is not None else None
+    a.ld_bits = ld_bits
     a.out, a.ld_out, a.out_mode, a.n_real = out.data_ptr(), ld_out, out_mode, n_real
-    a.ab_dtype, a.out_dtype, a.gate_dtype = ab, out_dt, gate_dt
+    a.out2 = out2.data_ptr() if out2 is not None else None
+    a.ld_out2 = ld_out
+    a.col_sums = col_sums.data_ptr() if col_sums is not None else None
+    a.ab_dtype, a.out_dtype, a.out2_dtype = ab, out_dt, (out2_dt or 0)
     call('mmlf_conv2x2_simt' if simt else 'mmlf_conv2x2', C.byref(a), stream())
     torch.cuda.synchronize()
-    return out
+    return (out, out2) if out2 is not None else out
 
 
 def dev_f32(a):

@@ -200,10 +200,58 @@ def test_conv_dgrad_and_gate():
         wd = u.pack_weight(w, dgrad=1, n_pad=u.pad16(cin), cin_pad=u.pad16(cout))
         gs = u.to_slots(gout, u.pad16(cout), ctype == 0, Hp, Wp)
         gate_s = u.to_slots(gate, u.pad16(cin), ctype == 1, Hp, Wp, u.FP16)
-        out = u.run_conv(gs, u.pad16(cout), u.pad16(cout), wd, u.pad16(cin), B, H, W, 1 - ctype, gate=gate_s,
-                         ld_gate=u.pad16(cin), gate_dt=u.FP16)
+        bits = u.pack_bits(gate_s.float().cpu().numpy() > 0, ld_bits=4)
+        for simt in (True, False):
+            out = u.run_conv(gs, u.pad16(cout), u.pad16(cout), wd, u.pad16(cin), B, H, W, 1 - ctype, gate_bits=bits,
+                             ld_bits=4, simt=simt)
+            got = u.from_slots(out, B, Hp, Wp, cin, ctype == 1)
+            u.assert_close_bf16(got, want, f'dgrad of type {ctype} (simt={simt})', ulps=1.01, atol=2e-3)
         got = u.from_slots(out, B, Hp, Wp, cin, ctype == 1)
         u.assert_close_bf16(got, want, f'dgrad of type {ctype}', ulps=1.01, atol=2e-3)
+
+
+@pytest.mark.parametrize('case', [(3, 40, 40, 280, 280, 0, 1), (3, 40, 40, 280, 280, 1, 1), (2, 24, 20, 70, 70, 1, 1),
+                                  (2, 24, 20, 27, 70, 0, 0), (1, 30, 30, 280, 108, 0, 1), (2, 17, 13, 320, 320, 1, 0)])
+def test_conv_fused_epilogue_outputs(case):
+    """Second output copy in the other 16-bit format, ReLU sign bits and per-channel sum / sum of squares all come
+    out of the same epilogue and must describe exactly the stored primary output."""
+    u = _u()
+    B, H, W, cin, cout, ctype, dt = case
+    rng = np.random.RandomState(21)
+    Hp, Wp = H + 1, W + 1
+    n_pad, cin_pad = u.pad16(cout), u.pad16(cin)
+    w = (rng.normal(0, 1, (cout, cin, 2, 2)) / np.sqrt(4 * cin)).astype(np.float32)
+    b = rng.normal(0, 0.3, cout).astype(np.float32)
+    shp = (B, H, W, cin) if ctype == 0 else (B, Hp, Wp, cin)
+    xs = u.to_slots(rng.normal(0, 1, shp).astype(np.float32), cin_pad, ctype == 1, Hp, Wp, dt)
+    wp = u.pack_weight(w, dt=dt)
+    bias = torch.zeros(n_pad, device='cuda')
+    bias[:cout] = torch.from_numpy(b)
+    ld_bits = (n_pad + 31) // 32
+    n_slots = B * Hp * Wp
+    ref = u.run_conv(xs, cin_pad, cin_pad, wp, n_pad, B, H, W, ctype, bias=bias, relu=True, ab=dt, out_dt=dt)
+    rbits = torch.full((n_slots, ld_bits), -1, dtype=torch.int32, device='cuda')
+    sums = torch.zeros(2 * n_pad, dtype=torch.float64, device='cuda')
+    out, out2 = u.run_conv(xs, cin_pad, cin_pad, wp, n_pad, B, H, W, ctype, bias=bias, relu=True, ab=dt, out_dt=dt,
+                           out2_dt=1 - dt, relu_bits=rbits, ld_bits=ld_bits, col_sums=sums)
+    assert torch.equal(out, ref), 'primary output must not depend on the optional epilogue outputs'
+    o = out.float()
+    want2 = o.to(u.TDT[1 - dt])
+    if 1 - dt == u.FP16:      # the kernel converts the fp32 value, not the rounded primary: allow one fp16 ulp
+        d = (out2.float() - o).abs()
+        assert bool((d <= o.abs() * 2.0 ** -7 + 1e-6).all()), 'second copy differs from the primary by more than a bf16 ulp'
+    else:
+        d = (out2.float() - o).abs()
+        assert bool((d <= o.abs() * 2.0 ** -7 + 1e-6).all()), 'bf16 copy differs from the fp16 primary by more than a bf16 ulp'
+    assert want2.shape == out2.shape
+    got_bits = u.unpack_bits(rbits, n_pad)
+    assert np.array_equal(got_bits, (o > 0).cpu().numpy()), 'ReLU bits do not match the stored output'
+    assert not u.unpack_bits(rbits, ld_bits * 32)[:, n_pad:].any()
+    od = o.double()
+    s1, s2 = od.sum(0).cpu().numpy(), (od * od).sum(0).cpu().numpy()
+    gs = sums.cpu().numpy()
+    np.testing.assert_allclose(gs[:n_pad], s1, rtol=2e-5, atol=1e-3)
+    np.testing.assert_allclose(gs[n_pad:], s2, rtol=2e-5, atol=1e-3)
 
 
 @pytest.mark.parametrize('case', [(2, 12, 12, 27, 70, 0), (2, 12, 12, 70, 70, 1), (2, 20, 20, 280, 280, 0),
@@ -296,8 +344,12 @@ def test_bn_train_roundtrip():
     u.call('mmlf_bn_finalize', u.ptr(sums), Cr, Cp, n, u.ptr(d['gamma']), u.ptr(d['beta']), u.ptr(d['rm']),
            u.ptr(d['rv']), u.ptr(nbt), 0.1, 1e-5, u.ptr(scale), u.ptr(shift), u.ptr(smean), u.ptr(sinv), u.stream())
     y = torch.full((B * Hp * Wp, Cp), float('nan'), dtype=torch.float16, device='cuda')
-    u.call('mmlf_bn_apply_relu', u.ptr(zs), Cp, u.ptr(scale), u.ptr(shift), Cp, B, H, W, A, u.ptr(y), Cp, u.stream())
+    y2 = torch.full((B * Hp * Wp, Cp), float('nan'), dtype=torch.bfloat16, device='cuda')
+    u.call('mmlf_bn_apply_relu', u.ptr(zs), Cp, u.ptr(scale), u.ptr(shift), Cp, B, H, W, A, u.ptr(y), Cp, u.ptr(y2), Cp, G,
+           u.stream())
     torch.cuda.synchronize()
+    assert bool(((y2.float() - y.float()).abs() <= y.float().abs() * 2.0 ** -7 + 1e-6).all()), 'bf16 copy of y is off'
+    assert bool(((y2 > 0) == (y > 0)).all())
     z2 = z.reshape(-1, Cr).astype(np.float64)
     mean, var = z2.mean(0), z2.var(0)
     np.testing.assert_allclose(smean.cpu().numpy()[:Cr], mean, rtol=1e-5, atol=1e-6)
@@ -313,16 +365,18 @@ def test_bn_train_roundtrip():
     gy = bf16_round(rng.normal(0, 1, (B, H, W, Cr)).astype(np.float32))
     gys = u.to_slots(gy, Cp, False, Hp, Wp)
     bs = torch.zeros(2 * Cp, dtype=torch.float64, device='cuda')
-    u.call('mmlf_bn_bwd_reduce', u.ptr(gys), Cp, u.ptr(y), Cp, u.ptr(zs), Cp, u.ptr(smean), u.ptr(sinv), Cp, B, H, W,
-           G, A, u.ptr(bs), u.stream())
+    u.call('mmlf_bn_bwd_reduce', u.ptr(gys), Cp, u.ptr(zs), Cp, u.ptr(scale), u.ptr(shift), u.ptr(smean), u.ptr(sinv),
+           Cp, B, H, W, G, A, u.ptr(bs), u.stream())
     gpad = torch.zeros(Cp, device='cuda')
     gpad[:Cr] = d['gamma']
     dz = torch.full((B * Hp * Wp, Cp), float('nan'), dtype=torch.bfloat16, device='cuda')
     dgam, dbet = torch.empty(Cr, device='cuda'), torch.empty(Cr, device='cuda')
-    u.call('mmlf_bn_bwd_apply', u.ptr(gys), Cp, u.ptr(y), Cp, u.ptr(zs), Cp, u.ptr(gpad), u.ptr(smean), u.ptr(sinv),
-           u.ptr(bs), n, 1, Cr, Cp, B, H, W, G, A, u.ptr(dz), Cp, u.ptr(dgam), u.ptr(dbet), u.ptr(torch.empty(2 * Cp, device='cuda')),
-           u.stream())
+    dzsum = torch.zeros(Cp, device='cuda')
+    u.call('mmlf_bn_bwd_apply', u.ptr(gys), Cp, u.ptr(zs), Cp, u.ptr(scale), u.ptr(shift), u.ptr(gpad), u.ptr(smean),
+           u.ptr(sinv), u.ptr(bs), n, 1, Cr, Cp, B, H, W, G, A, u.ptr(dz), Cp, u.ptr(dgam), u.ptr(dbet),
+           u.ptr(torch.empty(2 * Cp, device='cuda')), u.ptr(dzsum), u.stream())
     torch.cuda.synchronize()
+    np.testing.assert_allclose(dzsum.cpu().numpy(), dz.double().sum(0).cpu().numpy(), rtol=1e-4, atol=1e-3)
     yq = full[:, 1:, 1:, :Cr]
     g = gy * (yq > 0)
     invstd = (1 / np.sqrt(var + 1e-5)).astype(np.float32)
