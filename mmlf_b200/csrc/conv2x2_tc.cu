@@ -14,7 +14,8 @@
 //   roles     : warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA) + TMEM owner, warps 2..5 = epilogue (one
 //               TMEM lane quadrant = 32 slots each).  Persistent, static round-robin over 256-slot tiles.
 //   epilogue  : TMEM -> registers -> (+bias | *scale+shift, ReLU, ReLU-bit gate, halo mask) -> 16-bit ->
-//               per-warp swizzled shared-memory staging -> TMA store (32 slots x 32 channels per box); optional
+//               per-warp swizzled shared-memory staging (32 slots x 64 channels) -> coalesced 128-bit global stores
+//               (TMA stores queue behind the producer's bulk loads and cost > 1000 cycles each: measured); optional
 //               second copy in the other 16-bit format, ReLU sign bits, per-channel sum / sum of squares.
 #include "../../include/mmlf_b200.h"
 #include "common.cuh"
@@ -26,11 +27,11 @@ namespace mmlf {
 
 constexpr int kTileM = 128;
 constexpr int kABytes = kTileM * 128;  // one A stage: 128 rows x 64 16-bit channels
-constexpr int kConvThreads = 192;
+constexpr int kEpiWarps = 8;           // two per TMEM lane quadrant
+constexpr int kConvThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 8;
 constexpr uint32_t kTmemCols = 512;
-constexpr int kBoxBytes = 32 * 64;     // epilogue staging box: 32 slots x 32 channels x 2 B (SWIZZLE_64B)
-constexpr int kBitsPitch = 11;         // words per slot row of the per-warp bit scratch (odd: conflict-free)
+constexpr int kSegBytes = 32 * 64;     // epilogue staging per warp: 32 slots x 32 channels x 2 B, 16-byte chunks XOR-swizzled
 constexpr int kMaxNPad = 320;
 
 struct ConvParams {
@@ -40,10 +41,10 @@ struct ConvParams {
   int n_kc, last_ksteps;
   int tap_off[4];
   int num_tiles, stages;
-  int type, relu, out_mode, n_real, ld_out;
+  int type, relu, out_mode, n_real, ld_out, ld_out2;
   int ab_dtype, out_dtype, out2_dtype;
   int has_scale, dual, ld_bits;
-  uint32_t epi_off, bits_off, stat_off, aux_off;   // shared-memory offsets from the 1024-aligned base
+  uint32_t epi_off, stat_off, aux_off;             // shared-memory offsets from the 1024-aligned base
   const float* bias;
   const float* scale;
   const float* shift;
@@ -51,6 +52,7 @@ struct ConvParams {
   uint32_t* relu_bits;
   double* col_sums;
   void* out;
+  void* out2;
   long long* stats;                             // optional per-CTA cycle counters (debug): [grid][8]
 };
 
@@ -90,18 +92,6 @@ __device__ __forceinline__ void direct_store16(const ConvParams& p, int64_t s, b
   }
 }
 
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -132,28 +122,65 @@ __device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// Epilogue feature mask.  The kernel is instantiated for the combinations the network uses (every runtime branch in
+// the epilogue costs issue slots that the lone epilogue warps of an SM sub-partition cannot hide) plus one generic
+// instance (kFGeneric) that reads all switches from the parameter block.
+enum : uint32_t {
+  kFScale = 1,      // y = acc * scale + shift instead of acc + bias
+  kFRelu = 2,
+  kFGate = 4,       // multiply by the saved ReLU sign bits
+  kFBits = 8,       // emit ReLU sign bits
+  kFDual = 16,      // second 16-bit copy of the output
+  kFStats = 32,     // per-channel sum / sum of squares
+  kFOutF16 = 64,    // primary output is fp16 (else bf16)
+  kFOut2F16 = 128,  // secondary output is fp16 (else bf16)
+  kFDirect = 256,   // out_mode 1 / 2: fp32 rows or planar fp32, written straight from registers
+  kFGeneric = 512,
+};
+
+template <uint32_t F> struct Flags {
+  static constexpr bool generic = (F & kFGeneric) != 0;
+  __device__ __forceinline__ static bool scale(const ConvParams& p) { return generic ? p.has_scale != 0 : (F & kFScale) != 0; }
+  __device__ __forceinline__ static bool relu(const ConvParams& p) { return generic ? p.relu != 0 : (F & kFRelu) != 0; }
+  __device__ __forceinline__ static bool gate(const ConvParams& p) { return generic ? p.gate_bits != nullptr : (F & kFGate) != 0; }
+  __device__ __forceinline__ static bool bits(const ConvParams& p) { return generic ? p.relu_bits != nullptr : (F & kFBits) != 0; }
+  __device__ __forceinline__ static bool dual(const ConvParams& p) { return generic ? p.dual != 0 : (F & kFDual) != 0; }
+  __device__ __forceinline__ static bool stats(const ConvParams& p) { return generic ? p.col_sums != nullptr : (F & kFStats) != 0; }
+  __device__ __forceinline__ static bool out_f16(const ConvParams& p) { return generic ? p.out_dtype == kFP16 : (F & kFOutF16) != 0; }
+  __device__ __forceinline__ static bool out2_f16(const ConvParams& p) { return generic ? p.out2_dtype == kFP16 : (F & kFOut2F16) != 0; }
+  __device__ __forceinline__ static bool direct(const ConvParams& p) { return generic ? p.out_mode != 0 : (F & kFDirect) != 0; }
+};
 
 // One epilogue warp's context for the staged (out_mode 0) path
 struct EpiWarp {
-  uint32_t stg_addr;        // shared address of this warp's staging boxes: [2 (ring)][1 + dual] x kBoxBytes
-  uint32_t* s_gate;         // [32][kBitsPitch] gate bits of the current tile (or nullptr)
-  uint32_t* s_relu;         // [32][kBitsPitch] relu bits of the current tile (or nullptr)
-  float* s_stat;            // [2][n_pad] per-warp partial column sums (or nullptr)
+  uint32_t stg_addr;        // shared address of this warp's staging rows: [1 + dual] x kSegBytes
+  float* s_stat;            // [2][n_pad] partial column sums of this warp's TMEM lane quadrant (or nullptr)
   const float* s_add;
   const float* s_mul;
-  uint32_t ring;            // boxes stored so far (selects the staging buffer)
 };
 
-// Processes one box of 32 output channels [box * 32, box * 32 + 32) of the warp's 32 slots: math, 16-bit packing,
-// swizzled staging, TMA store, statistics.  r holds the fp32 accumulators of this thread's slot.
-__device__ __forceinline__ void epi_box_staged(const ConvParams& p, EpiWarp& w, const CUtensorMap* tmap_o,
-                                               const CUtensorMap* tmap_o2, const uint32_t (&r)[32], int box,
-                                               int row0, bool valid, int lane) {
-  const int c0 = box * 32;
+// One segment of up to 32 output channels [c0, c0 + ncols) of the warp's 32 slots (c0 is a multiple of 32): epilogue
+// math, ReLU bits, 16-bit packing into the staging rows, coalesced write-out, column statistics.
+// r holds the fp32 accumulators of this thread's slot.  gate_word: this slot's saved ReLU bits of channels [c0, c0+32).
+// Returns the ReLU bits of the segment.
+template <uint32_t F>
+__device__ __forceinline__ uint32_t epi_segment(const ConvParams& p, const EpiWarp& w, const uint32_t (&r)[32], int c0,
+                                                int ncols, uint32_t gate_word, bool valid, int row0, int rows_valid,
+                                                int lane) {
+  using FL = Flags<F>;
   float x[32];
   {
     const float4* add4 = reinterpret_cast<const float4*>(w.s_add + c0);
-    if (p.has_scale) {
+    if (FL::scale(p)) {
       const float4* mul4 = reinterpret_cast<const float4*>(w.s_mul + c0);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -174,109 +201,99 @@ __device__ __forceinline__ void epi_box_staged(const ConvParams& p, EpiWarp& w, 
       }
     }
   }
-  if (p.relu) {
+  if (FL::relu(p)) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
   }
-  if (w.s_gate) {
-    const uint32_t g = w.s_gate[lane * kBitsPitch + box];
+  if (FL::gate(p)) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) x[j] = ((g >> j) & 1u) ? x[j] : 0.f;
+    for (int j = 0; j < 32; ++j) x[j] = ((gate_word >> j) & 1u) ? x[j] : 0.f;
   }
-  if (!valid) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) x[j] = 0.f;
-  }
-  if (w.s_relu) {
-    uint32_t bits = 0;
+  const uint32_t vmask = valid ? 0xFFFFFFFFu : 0u;      // halo slots and slots past the end store zeros
+  uint32_t bits = 0;
+  if (FL::bits(p)) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) bits |= (x[j] > 0.f ? 1u : 0u) << j;
-    w.s_relu[lane * kBitsPitch + box] = bits;
+    if (ncols < 32) bits &= 0xFFFFu;
+    bits &= vmask;
   }
-
-  // staging buffer of this box; the TMA store that used it two boxes ago must have finished reading it
-  const uint32_t buf = w.stg_addr + (w.ring & 1u) * (p.dual ? 2u * kBoxBytes : kBoxBytes);
-  if (lane == 0) bulk_wait_read<1>();
-  __syncwarp();
-  // slot row `lane` occupies 64 B; SWIZZLE_64B: 16-byte chunk j lands at chunk j ^ ((row >> 1) & 3)
-  const uint32_t row_addr = buf + lane * 64;
+  // slot row `lane` occupies 64 B of the staging buffer; 16-byte chunk j lands at chunk j ^ ((lane >> 1) & 3)
+  const uint32_t row_addr = w.stg_addr + lane * 64;
   const uint32_t sw = (lane >> 1) & 3;
-  {
-    uint32_t pk[16];
-    if (p.out_dtype == kFP16) {
+  const int nch = ncols >> 3;
+  __syncwarp();                                           // the previous segment's write-out has finished reading
 #pragma unroll
-      for (int j = 0; j < 16; ++j) pk[j] = pack_f16x2_sat(x[2 * j], x[2 * j + 1]);
+  for (int o = 0; o < 2; ++o) {
+    if (o == 1 && !FL::dual(p)) break;
+    const bool f16 = o ? FL::out2_f16(p) : FL::out_f16(p);
+    uint32_t pk[16];
+    if (f16) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pk[j] = pack_f16x2_sat(x[2 * j], x[2 * j + 1]) & vmask;
     } else {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
+      for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]) & vmask;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + ((j ^ sw) << 4)), "r"(pk[4 * j]),
-                   "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
-                   : "memory");
+      if (j < nch) sts128(row_addr + o * kSegBytes + ((j ^ sw) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
   }
-  if (p.dual) {
-    uint32_t pk[16];
-    if (p.out2_dtype == kFP16) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) pk[j] = pack_f16x2_sat(x[2 * j], x[2 * j + 1]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + kBoxBytes + ((j ^ sw) << 4)),
-                   "r"(pk[4 * j]), "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
-                   : "memory");
-  }
-  fence_async_smem();
   __syncwarp();
-  if (lane == 0) {
-    tma_store_2d(tmap_o, buf, c0, row0);
-    if (p.dual) tma_store_2d(tmap_o2, buf + kBoxBytes, c0, row0);
-    bulk_commit();
-  }
-  ++w.ring;
-
-  if (w.s_stat) {
-    // per-channel sum / sum of squares of the stored (rounded) values: lane handles channel pair (lane & 15) of the
-    // 16 slots with parity (lane >> 4); rows 2k and 2k+1 share a 128-byte line, so the two half-warps never conflict
-    const int cp = lane & 15, par = lane >> 4;
-    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  // write-out: 4 lanes cover the 64 staged bytes of one slot row, one store instruction covers 8 rows
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const int row = 2 * k + par;
-      const uint32_t a = buf + row * 64 + ((((cp >> 2) ^ ((row >> 1) & 3))) << 4) + ((cp & 3) << 2);
-      uint32_t v;
-      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-      float lo, hi;
-      unpack16x2(v, p.out_dtype, lo, hi);
-      s0 += lo;
-      s1 += hi;
-      q0 = fmaf(lo, lo, q0);
-      q1 = fmaf(hi, hi, q1);
-    }
-    s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
-    s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-    q0 += __shfl_xor_sync(0xffffffffu, q0, 16);
-    q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
-    float2* dst = reinterpret_cast<float2*>(w.s_stat + (par ? p.n_pad : 0) + c0 + 2 * cp);
-    if (c0 + 2 * cp < p.n_pad) {
-      float2 cur = *dst;
-      cur.x += par ? q0 : s0;
-      cur.y += par ? q1 : s1;
-      *dst = cur;
+  for (int o = 0; o < 2; ++o) {
+    if (o == 1 && !FL::dual(p)) break;
+    uint16_t* gbase = reinterpret_cast<uint16_t*>(o ? p.out2 : p.out);
+    const int ld = o ? p.ld_out2 : p.ld_out;
+    const uint32_t sbase = w.stg_addr + o * kSegBytes;
+    if (ncols == 32) {
+      const int r0 = lane >> 2, ch = lane & 3;
+      const uint32_t a0 = sbase + r0 * 64 + ((ch ^ ((r0 >> 1) & 3)) << 4);
+      uint16_t* g = gbase + (static_cast<int64_t>(row0) + r0) * ld + c0 + ch * 8;
+      const int64_t gstep = static_cast<int64_t>(8) * ld;
+      if (rows_valid == 32) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(g + k * gstep) = lds128(a0 + k * 512);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (8 * k + r0 < rows_valid) *reinterpret_cast<uint4*>(g + k * gstep) = lds128(a0 + k * 512);
+      }
+    } else {                                              // 16 channels: 2 lanes per row, 16 rows per instruction
+      const int r0 = lane >> 1, ch = lane & 1;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int row = 16 * k + r0;
+        const uint4 v = lds128(sbase + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
+        if (row < rows_valid) *reinterpret_cast<uint4*>(gbase + (static_cast<int64_t>(row0) + row) * ld + c0 + ch * 8) = v;
+      }
     }
   }
+  if (FL::stats(p)) {
+    // lane owns channel c0 + lane over the 32 slots (2-byte reads of one row are conflict-free)
+    if (lane < ncols) {
+      float s0 = 0.f, q0 = 0.f;
+      const uint32_t col = w.stg_addr + (lane & 7) * 2;
+      const uint32_t chunk = lane >> 3;
+#pragma unroll 8
+      for (int row = 0; row < 32; ++row) {
+        uint16_t v;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(col + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)) : "memory");
+        const float f = FL::out_f16(p) ? __half2float(__ushort_as_half(v)) : __uint_as_float(static_cast<uint32_t>(v) << 16);
+        s0 += f;
+        q0 = fmaf(f, f, q0);
+      }
+      w.s_stat[c0 + lane] += s0;
+      w.s_stat[p.n_pad + c0 + lane] += q0;
+    }
+  }
+  return bits;
 }
 
 // Direct-store variant (fp32 slot rows / planar fp32 outputs of the heads)
 __device__ __forceinline__ void epi_box_direct(const ConvParams& p, const float* s_add, const float* s_mul,
-                                               const uint32_t (&r)[32], int box, int ncols, int64_t s, bool in_range,
+                                               const uint32_t (&r)[32], int c0, int ncols, int64_t s, bool in_range,
                                                bool valid, int b, int sy, int sx) {
-  const int c0 = box * 32;
   float x[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) x[j] = epi_value(p, __uint_as_float(r[j]), s_add[c0 + j], s_mul[c0 + j], valid);
@@ -289,10 +306,14 @@ __device__ __forceinline__ void epi_box_direct(const ConvParams& p, const float*
 // MMAs of tile t+1.  Two 288-column accumulators do not fit into 512 columns, so the regions are [0, n_pad) and
 // [512 - n_pad, 512) and share `ovl` = 2 * n_pad - 512 columns; the epilogue pulls the shared columns into registers
 // first and releases them through a separate barrier, after which the next tile's MMAs may start.
+//
+// Epilogue warps: two per TMEM lane quadrant (warps 2..5 take the even 32-column segments of a tile, warps 6..9 the odd
+// ones), i.e. two per SM sub-partition, so that one warp's shared-memory / TMEM latencies are covered by the other.
+template <uint32_t F>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                   const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_o2,
                    const ConvParams p) {
+  using FL = Flags<F>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;
@@ -315,8 +336,8 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const bool leader = rank == 0;
-  // the overlap trick needs the shared columns to be whole 32-channel boxes; otherwise the regions are used strictly
-  // one after the other (ovl_wait_all)
+  // the overlap trick needs the shared columns to be whole 32-channel segments; otherwise the regions are used
+  // strictly one after the other
   const int ovl_cols = p.n_pad > 256 ? 2 * p.n_pad - 512 : 0;
   const bool ovl_ok = (ovl_cols & 31) == 0 && (p.n_pad & 31) == 0;
   const int base1 = p.n_pad > 256 ? 512 - p.n_pad : 256;      // TMEM column base of odd tiles
@@ -325,8 +346,6 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
-    if (p.out_mode == 0) prefetch_tmap(&tmap_o);
-    if (p.dual) prefetch_tmap(&tmap_o2);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -336,9 +355,9 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(smem_u32(&tmem_full_bar[i]), 1);
-        mbar_init(smem_u32(&tmem_empty_bar[i]), 8);    // one elected lane of the 4 epilogue warps of both CTAs
+        mbar_init(smem_u32(&tmem_empty_bar[i]), 2 * kEpiWarps);   // one lane of every epilogue warp of both CTAs
       }
-      mbar_init(smem_u32(tmem_ovl_bar), 8);
+      mbar_init(smem_u32(tmem_ovl_bar), 2 * kEpiWarps);
       fence_barrier_init();
     }
     __syncwarp();
@@ -466,22 +485,14 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue: one warp per TMEM lane quadrant
-    const int q = warp & 3;
-    const bool staged = p.out_mode == 0;
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;                              // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;                    // 0: even segments of a tile, 1: odd segments
     EpiWarp w;
-    w.stg_addr = tiles_addr + p.epi_off + q * (p.dual ? 4u : 2u) * kBoxBytes;
-    uint32_t* bits_base = reinterpret_cast<uint32_t*>(smem + p.bits_off) + q * 2 * 32 * kBitsPitch;
-    w.s_gate = p.gate_bits ? bits_base : nullptr;
-    w.s_relu = p.relu_bits ? bits_base + 32 * kBitsPitch : nullptr;
-    w.s_stat = p.stat_off ? reinterpret_cast<float*>(smem + p.stat_off) + q * 2 * p.n_pad : nullptr;
+    w.stg_addr = tiles_addr + p.epi_off + (warp - 2) * (FL::dual(p) ? 2u : 1u) * kSegBytes;
+    w.s_stat = (FL::stats(p) && p.stat_off) ? reinterpret_cast<float*>(smem + p.stat_off) + q * 2 * p.n_pad : nullptr;
     w.s_add = s_add;
     w.s_mul = s_mul;
-    w.ring = 0;
-    const int n_boxes = (p.n_pad + 31) >> 5;
-    const int last_cols = p.n_pad - (n_boxes - 1) * 32;        // 32 or 16
-    const int ovl_boxes = ovl >> 5;
-    const int bits_words = 32 * p.ld_bits;                     // words of bit rows per warp and tile
     int it = 0;
     long long t_wait = 0, t_begin = clock64();
     for (int tile = pair; tile < p.num_tiles; tile += n_pairs, ++it) {
@@ -489,36 +500,44 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const int row0 = tile * (2 * kTileM) + static_cast<int>(rank) * kTileM + q * 32;
       const int64_t s = static_cast<int64_t>(row0) + lane;
       const bool in_range = s < p.n_slots;
+      const int rows_valid = p.n_slots - row0 >= 32 ? 32 : static_cast<int>(p.n_slots - row0);   // may be <= 0
       int b = 0, sy = 0, sx = 0;
       if (in_range) slot_coords(p, s, b, sy, sx);
       const bool valid = in_range && (p.type == 0 || (sy >= 1 && sx >= 1));
-      if (w.s_gate) {
-        // the warp's 32 gate rows are contiguous in global memory: coalesced copy into the scratch
-        const uint32_t* g = p.gate_bits + static_cast<int64_t>(row0) * p.ld_bits;
-        const int64_t lim = (p.n_slots - row0) * p.ld_bits;
-        for (int i = lane; i < bits_words; i += 32) {
-          const int rr = i / p.ld_bits, ww = i - rr * p.ld_bits;
-          w.s_gate[rr * kBitsPitch + ww] = i < lim ? __ldg(g + i) : 0u;
+      // Column order: the columns shared with the other TMEM region first (the last `ovl` columns of an even tile, the
+      // first ones of an odd tile).  Range 1 = [start1, n_pad), then range 2 = [0, start1); 32-column segments, this
+      // warp takes the positions i = half, half + 2, ...
+      const int start1 = (par == 0 && ovl > 0) ? p.n_pad - ovl : 0;
+      const int nseg1 = (p.n_pad - start1 + 31) >> 5;
+      const int nseg = nseg1 + ((start1 + 31) >> 5);
+      const int ovl_pos = ovl > 0 ? (ovl >> 5) : nseg;          // positions after which the shared columns are free
+      auto seg_c0 = [&](int i) { return i < nseg1 ? start1 + 32 * i : 32 * (i - nseg1); };
+      auto seg_n = [&](int i) { const int end = i < nseg1 ? p.n_pad : start1; const int c = seg_c0(i); return end - c < 32 ? end - c : 32; };
+      // last position of this warp inside the shared columns / overall (-1: none)
+      const int last_ovl_i = ovl_pos > half ? half + ((ovl_pos - 1 - half) & ~1) : -1;
+      const int last_i = nseg > half ? half + ((nseg - 1 - half) & ~1) : -1;
+      // this slot's saved ReLU bits, fetched before the accumulators are ready (one word per 32 channels)
+      uint32_t gw[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+      if (FL::gate(p)) {
+        if (in_range) {
+          const uint32_t* g = p.gate_bits + s * p.ld_bits;
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            const int i = half + 2 * k;
+            if (i < nseg) gw[k] = __ldg(g + (seg_c0(i) >> 5));
+          }
         }
-        __syncwarp();
       }
       const long long tw = clock64();
       mbar_wait(smem_u32(&tmem_full_bar[par]), (it >> 1) & 1);
       t_wait += clock64() - tw;
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (par ? base1 : 0);
-      // box order: the columns shared with the other region first (the last boxes of an even tile, the first ones of
-      // an odd tile) -- a rotation of the natural order
-      const int first = (par == 0 && ovl_boxes > 0) ? n_boxes - ovl_boxes : 0;
-      auto box_at = [&](int i) { int bx = first + i; return bx >= n_boxes ? bx - n_boxes : bx; };
-      auto load_box = [&](int bx, uint32_t (&r)[32]) {
-        if (bx == n_boxes - 1 && last_cols == 16) tmem_ld16_lo(taddr + bx * 32, r);
-        else tmem_ld32(taddr + bx * 32, r);
+      auto load_seg = [&](int i, uint32_t (&r)[32]) {
+        if (seg_n(i) == 32) tmem_ld32(taddr + seg_c0(i), r);
+        else tmem_ld16_lo(taddr + seg_c0(i), r);
       };
-      // releases: after the loads of positions [0, ovl_boxes) have landed -> shared columns free; after the last -> region free
-      auto after_loaded = [&](int i) {
-        const bool rel_ovl = (ovl_boxes > 0) ? (i + 1 == ovl_boxes) : (i + 1 == n_boxes);
-        const bool rel_all = (i + 1 == n_boxes);
+      auto release = [&](bool rel_ovl, bool rel_all) {
         if (rel_ovl || rel_all) {
           tc_fence_before();
           __syncwarp();
@@ -528,36 +547,49 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           }
         }
       };
-      auto process = [&](const uint32_t (&r)[32], int bx) {
-        if (staged) epi_box_staged(p, w, &tmap_o, &tmap_o2, r, bx, row0, valid, lane);
-        else epi_box_direct(p, s_add, s_mul, r, bx, bx == n_boxes - 1 ? last_cols : 32, s, in_range, valid, b, sy, sx);
+      release(last_ovl_i < 0, last_i < 0);               // nothing of mine in the shared columns / in this tile
+      uint32_t rbits[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+      auto process = [&](const uint32_t (&r)[32], int i, int k) {
+        const int c0 = seg_c0(i), n = seg_n(i);
+        if (!FL::direct(p)) {
+          const uint32_t bts = epi_segment<F>(p, w, r, c0, n, gw[k], valid, row0, rows_valid, lane);
+          if (FL::bits(p)) rbits[k] = bts;
+        } else {
+          epi_box_direct(p, s_add, s_mul, r, c0, n, s, in_range, valid, b, sy, sx);
+        }
       };
       uint32_t ra[32], rb[32];
-      load_box(box_at(0), ra);
-      for (int i = 0; i < n_boxes; i += 2) {
-        tmem_ld_wait();
-        if (i + 1 < n_boxes) load_box(box_at(i + 1), rb);      // in flight while box i is processed
-        after_loaded(i);
-        process(ra, box_at(i));
-        if (i + 1 < n_boxes) {
+      if (half < nseg) load_seg(half, ra);
+#pragma unroll
+      for (int k = 0; k < 5; k += 2) {
+        const int i = half + 2 * k;
+        if (i < nseg) {
           tmem_ld_wait();
-          if (i + 2 < n_boxes) load_box(box_at(i + 2), ra);
-          after_loaded(i + 1);
-          process(rb, box_at(i + 1));
+          if (i + 2 < nseg) load_seg(i + 2, rb);               // in flight while segment i is processed
+          release(i == last_ovl_i, i == last_i);
+          process(ra, i, k);
+          if (i + 2 < nseg) {
+            tmem_ld_wait();
+            if (i + 4 < nseg) load_seg(i + 4, ra);
+            release(i + 2 == last_ovl_i, i + 2 == last_i);
+            process(rb, i + 2, k + 1);
+          }
         }
       }
-      if (w.s_relu) {
-        __syncwarp();
-        uint32_t* g = p.relu_bits + static_cast<int64_t>(row0) * p.ld_bits;
-        const int64_t lim = (p.n_slots - row0) * p.ld_bits;
-        for (int i = lane; i < bits_words; i += 32) {
-          const int rr = i / p.ld_bits, ww = i - rr * p.ld_bits;
-          if (i < lim) g[i] = ww < n_boxes ? w.s_relu[rr * kBitsPitch + ww] : 0u;
+      if (FL::bits(p)) {
+        if (in_range) {
+          uint32_t* g = p.relu_bits + s * p.ld_bits;
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            const int i = half + 2 * k;
+            if (i < nseg) g[seg_c0(i) >> 5] = rbits[k];
+          }
+          // words beyond the channels (ld_bits > ceil(n_pad / 32)) are cleared by the even warp
+          if (half == 0)
+            for (int ww = (p.n_pad + 31) >> 5; ww < p.ld_bits; ++ww) g[ww] = 0u;
         }
-        __syncwarp();
       }
     }
-    if (staged && lane == 0) bulk_wait_read<0>();            // shared memory must outlive the last TMA store
     if (p.stats && warp == 2 && lane == 0) {
       p.stats[blockIdx.x * 8 + 5] = clock64() - t_begin;     // epilogue total
       p.stats[blockIdx.x * 8 + 6] = t_wait;                  // ... waiting for accumulators
@@ -567,7 +599,7 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   tc_fence_before();
   __syncthreads();
   if (p.stat_off && p.col_sums) {
-    // combine the four epilogue warps' partial sums and add them to the global fp64 accumulators
+    // combine the four lane quadrants' partial sums and add them to the global fp64 accumulators
     const float* st = reinterpret_cast<const float*>(smem + p.stat_off);
     for (int i = threadIdx.x; i < 2 * p.n_pad; i += kConvThreads) {
       const float v = st[i] + st[2 * p.n_pad + i] + st[4 * p.n_pad + i] + st[6 * p.n_pad + i];
@@ -655,7 +687,7 @@ static int fill_params(const mmlf_conv_args* a, ConvParams& p) {
   MMLF_REQUIRE((a->scale == nullptr) == (a->shift == nullptr), "conv2x2: scale and shift come together");
   MMLF_REQUIRE(!(a->gate_bits || a->relu_bits) || a->ld_bits >= (a->n_pad + 31) / 32,
                "conv2x2: ld_bits %d too small for n_pad %d", a->ld_bits, a->n_pad);
-  MMLF_REQUIRE(!(a->gate_bits || a->relu_bits) || a->ld_bits < kBitsPitch, "conv2x2: ld_bits %d too large", a->ld_bits);
+  MMLF_REQUIRE(!(a->gate_bits || a->relu_bits) || a->ld_bits <= 16, "conv2x2: ld_bits %d too large", a->ld_bits);
   MMLF_REQUIRE(a->out_mode == 0 || !(a->out2 || a->relu_bits || a->col_sums || a->gate_bits),
                "conv2x2: out2 / relu_bits / gate_bits / col_sums need out_mode 0");
   MMLF_REQUIRE(!a->out2 || (a->ld_out2 >= a->n_pad && a->ld_out2 % 8 == 0), "conv2x2: bad ld_out2 %d", a->ld_out2);
@@ -696,9 +728,11 @@ static int fill_params(const mmlf_conv_args* a, ConvParams& p) {
   p.relu_bits = a->relu_bits;
   p.col_sums = a->col_sums;
   p.out = a->out;
+  p.out2 = a->out2;
+  p.ld_out2 = a->ld_out2;
   p.stats = nullptr;
   p.stages = 0;
-  p.epi_off = p.bits_off = p.stat_off = p.aux_off = 0;
+  p.epi_off = p.stat_off = p.aux_off = 0;
   return 0;
 }
 
@@ -710,53 +744,81 @@ static long long* g_conv_stats = nullptr;
 // debug hook (not part of the public header): per-CTA cycle counters of the next conv launches, [grid][8] int64
 extern "C" void mmlf_debug_conv_stats(long long* device_buf) { g_conv_stats = device_buf; }
 
+typedef void (*ConvKernel)(CUtensorMap, CUtensorMap, ConvParams);
+struct ConvVariant {
+  uint32_t mask;
+  ConvKernel fn;
+};
+#define MMLF_CONV_VARIANT(m) {static_cast<uint32_t>(m), conv2x2_tc2_kernel<static_cast<uint32_t>(m)>}
+// the epilogue combinations the network uses (fp16 and bf16 activation storage) + the generic instance (last)
+static const ConvVariant kConvVariants[] = {
+    MMLF_CONV_VARIANT(kFRelu | kFOutF16),                          // eval / no-grad: first conv of a block
+    MMLF_CONV_VARIANT(kFScale | kFRelu | kFOutF16),                // eval: second conv with folded BatchNorm
+    MMLF_CONV_VARIANT(kFRelu | kFBits | kFDual | kFOutF16),        // training: first conv (fp16 + bf16 copy + bits)
+    MMLF_CONV_VARIANT(kFStats | kFOutF16),                         // training: second conv with batch statistics
+    MMLF_CONV_VARIANT(kFRelu),
+    MMLF_CONV_VARIANT(kFScale | kFRelu),
+    MMLF_CONV_VARIANT(kFRelu | kFBits),
+    MMLF_CONV_VARIANT(kFStats),
+    MMLF_CONV_VARIANT(0),                                          // data gradient
+    MMLF_CONV_VARIANT(kFGate | kFStats),                           // data gradient through a ReLU + bias gradient
+    MMLF_CONV_VARIANT(kFDirect),                                   // heads (fp32 outputs)
+    MMLF_CONV_VARIANT(kFGeneric),
+};
+constexpr int kNumConvVariants = sizeof(kConvVariants) / sizeof(kConvVariants[0]);
+
 extern "C" int mmlf_conv2x2(const mmlf_conv_args* a, void* stream) {
   ConvParams p;
   if (int rc = fill_params(a, p)) return rc;
   p.stats = g_conv_stats;
   const uint32_t stage_bytes = kABytes + p.n_pad * 64;
-  // shared-memory plan behind the operand stages: [epilogue staging | bit scratch | statistics | barriers + constants]
-  const uint32_t epi_bytes = p.out_mode == 0 ? 4u * (p.dual ? 4u : 2u) * kBoxBytes : 0u;
-  const uint32_t bits_bytes = (p.gate_bits || p.relu_bits) ? 4u * 2u * 32u * kBitsPitch * 4u : 0u;
+  // shared-memory plan behind the operand stages: [epilogue staging | statistics | barriers + constants]
+  const uint32_t epi_bytes = p.out_mode == 0 ? kEpiWarps * (p.dual ? 2u : 1u) * kSegBytes : 0u;
   const uint32_t stat_bytes = p.col_sums ? 4u * 2u * p.n_pad * 4u : 0u;
   const uint32_t aux_bytes = 192 + 2 * kMaxNPad * 4 + 64;   // barriers + TMEM pointer, then the per-channel constants
-  const uint32_t tail_bytes = epi_bytes + bits_bytes + ((stat_bytes + 15u) & ~15u) + aux_bytes;
+  const uint32_t tail_bytes = epi_bytes + ((stat_bytes + 15u) & ~15u) + aux_bytes;
   const uint32_t max_smem = 232448;   // 227 KB opt-in limit per CTA on sm_100
   int stages = static_cast<int>((max_smem - 1024 - tail_bytes) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   MMLF_REQUIRE(stages >= 2, "conv2x2: not enough shared memory for a 2-stage pipeline (n_pad %d)", p.n_pad);
   p.stages = stages;
   p.epi_off = stages * stage_bytes;                       // multiple of 1024 (stage_bytes = 16384 + n_pad * 64)
-  p.bits_off = p.epi_off + epi_bytes;
-  p.stat_off = stat_bytes ? p.bits_off + bits_bytes : 0;
-  p.aux_off = p.bits_off + bits_bytes + ((stat_bytes + 15u) & ~15u);
+  p.stat_off = stat_bytes ? p.epi_off + epi_bytes : 0;
+  p.aux_off = p.epi_off + epi_bytes + ((stat_bytes + 15u) & ~15u);
   const uint32_t smem_bytes = 1024 + p.aux_off + aux_bytes;
 
-  CUtensorMap tmap_a, tmap_b, tmap_o, tmap_o2;
+  CUtensorMap tmap_a, tmap_b;
   if (int rc = make_tmap_2d_16(&tmap_a, a->in, a->cin_pad, p.n_slots, static_cast<uint64_t>(a->ld_in) * 2, 64, kTileM, 128))
     return rc;
   const uint64_t k_total = static_cast<uint64_t>(4) * p.n_kc * 64;
   if (int rc = make_tmap_2d_16(&tmap_b, a->wpack, k_total, p.n_pad, k_total * 2, 64, p.n_part / 2, 128)) return rc;
-  tmap_o = tmap_a;
-  tmap_o2 = tmap_a;
-  if (p.out_mode == 0) {
-    if (int rc = make_tmap_2d_16(&tmap_o, a->out, p.n_pad, p.n_slots, static_cast<uint64_t>(a->ld_out) * 2, 32, 32, 64))
-      return rc;
-    if (p.dual)
-      if (int rc = make_tmap_2d_16(&tmap_o2, a->out2, p.n_pad, p.n_slots, static_cast<uint64_t>(a->ld_out2) * 2, 32, 32, 64))
-        return rc;
-  }
 
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv2x2_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    MMLF_REQUIRE(e == cudaSuccess, "conv2x2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    for (int i = 0; i < kNumConvVariants; ++i) {
+      cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(kConvVariants[i].fn),
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+      MMLF_REQUIRE(e == cudaSuccess, "conv2x2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
     attr_set = true;
   }
+  uint32_t mask;
+  if (p.out_mode != 0) {
+    mask = kFDirect;
+  } else {
+    mask = (p.has_scale ? kFScale : 0u) | (p.relu ? kFRelu : 0u) | (p.gate_bits ? kFGate : 0u) |
+           (p.relu_bits ? kFBits : 0u) | (p.dual ? kFDual : 0u) | (p.col_sums ? kFStats : 0u) |
+           (p.out_dtype == kFP16 ? kFOutF16 : 0u) | (p.dual && p.out2_dtype == kFP16 ? kFOut2F16 : 0u);
+  }
+  ConvKernel fn = kConvVariants[kNumConvVariants - 1].fn;
+  for (int i = 0; i < kNumConvVariants - 1; ++i)
+    if (kConvVariants[i].mask == mask) fn = kConvVariants[i].fn;
   const int max_pairs = sm_count() / 2;
   const int pairs = p.num_tiles < max_pairs ? p.num_tiles : max_pairs;
-  conv2x2_tc2_kernel<<<2 * pairs, kConvThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmap_a, tmap_b, tmap_o,
-                                                                                              tmap_o2, p);
+  void* args[] = {&tmap_a, &tmap_b, &p};
+  cudaError_t e = cudaLaunchKernel(reinterpret_cast<const void*>(fn), dim3(2 * pairs), dim3(kConvThreads), args, smem_bytes,
+                                   static_cast<cudaStream_t>(stream));
+  MMLF_REQUIRE(e == cudaSuccess, "conv2x2_tc2_kernel: %s", cudaGetErrorString(e));
   return check_launch("conv2x2_tc2_kernel");
 }
 
