@@ -12,6 +12,8 @@
 //               deterministic kernel that also writes the [n][tap][c] layout.
 #include "../../include/mmlf_b200.h"
 #include "common.cuh"
+#include <stdlib.h>
+
 #include "host_util.h"
 
 namespace mmlf {
@@ -166,6 +168,172 @@ conv2x2_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair version (cta_group::2, M = 256): the pair owns one 64-channel chunk of the activation operand for ALL four
+// taps.  CTA r loads ONE box of 72 slots x 64 channels starting at the rows of tap (dy = r, dx = 0); tap (r, 1) is the
+// same box shifted by one slot row, expressed in the MMA descriptor as a second MN atom 128 B after the first (the
+// 128-byte swizzle is a function of the shared-memory address, so overlapping atoms read consistently: measured).
+// The gradient operand is split in N between the two CTAs (each supplies half of the columns of every MMA, loaded as
+// boxes that START at its slice so both CTAs use identical shared-memory offsets).  Per stage and CTA: 9 KB of
+// activations + <= 24 KB of gradients for 64 slots x 256 x 288 MACs, versus 16 + 40 KB for 128 x 288 before.
+constexpr int kWg2ABytes = 72 * 128;
+constexpr int kWg2MaxStages = 8;
+
+struct Wgrad2Params {
+  int64_t n_slots;
+  int n_pad, kc, ksplits;
+  int64_t slots_per_split;
+  int tap_base[2];                              // row offset of tap (dy, 0), dy = CTA rank
+  int stages;
+  int n_parts, part_n[2], part_col[2];          // MMA N parts: columns [part_col, part_col + part_n)
+  int part_box0[2], part_boxes[2];              // per CTA: first B box of the part and number of boxes (1 or 2)
+  int nb;                                       // B boxes per CTA and stage
+  int act_dtype, dout_dtype;
+  float* ws;                                    // [ksplits][4 * kc * 64][ws_ld]
+  int ws_ld;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWgThreads, 1)
+conv2x2_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_dout,
+                      const Wgrad2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (tiles_addr - raw_addr);
+  const uint32_t stage_bytes = kWg2ABytes + static_cast<uint32_t>(p.nb) * kWgBox;
+  uint8_t* aux = smem + static_cast<size_t>(p.stages) * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* empty_bar = full_bar + kWg2MaxStages;
+  uint64_t* done_bar = empty_bar + kWg2MaxStages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int chunk = pair % p.kc, ks = pair / p.kc;
+  const int64_t k_begin = static_cast<int64_t>(ks) * p.slots_per_split;
+  int64_t k_end = k_begin + p.slots_per_split;
+  if (k_end > p.n_slots) k_end = p.n_slots;
+  const int n_chunks = k_end > k_begin ? static_cast<int>((k_end - k_begin + kWgKb - 1) / kWgKb) : 0;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_act);
+    prefetch_tmap(&tmap_dout);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < p.stages; ++i) {
+        mbar_init(smem_u32(&full_bar[i]), 1);
+        mbar_init(smem_u32(&empty_bar[i]), 1);
+      }
+      mbar_init(smem_u32(done_bar), 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc_pair(smem_u32(tmem_ptr_smem), 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    uint32_t stage = 0, phase = 0;
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      const int row0 = static_cast<int>(k_begin + static_cast<int64_t>(ch) * kWgKb);
+      mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+      const uint32_t fb = smem_u32(&full_bar[stage]);
+      const uint32_t a_dst = tiles_addr + stage * stage_bytes;
+      const uint32_t b_dst = a_dst + kWg2ABytes;
+      if (elect_one()) {
+        if (leader) mbar_arrive_expect_tx(fb, 2 * stage_bytes);
+        tma_load_2d_pair(a_dst, &tmap_act, fb, chunk * 64, row0 + p.tap_base[rank], kEvictNormal);
+        for (int part = 0; part < p.n_parts; ++part) {
+          const int col = p.part_col[part] + static_cast<int>(rank) * (p.part_n[part] >> 1);
+          for (int j = 0; j < p.part_boxes[part]; ++j)
+            tma_load_2d_pair(b_dst + (p.part_box0[part] + j) * kWgBox, &tmap_dout, fb, col + 64 * j, row0, kEvictNormal);
+        }
+      }
+      __syncwarp();
+      if (++stage == static_cast<uint32_t>(p.stages)) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      const uint32_t idesc0 = make_idesc_16(256, p.part_n[0], 1, 1, p.act_dtype, p.dout_dtype);
+      const uint32_t idesc1 = make_idesc_16(256, p.n_parts > 1 ? p.part_n[1] : 16, 1, 1, p.act_dtype, p.dout_dtype);
+      uint32_t stage = 0, phase = 0, accumulate = 0;
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        tc_fence_after();
+        const uint32_t a_addr = tiles_addr + stage * stage_bytes;
+        const uint32_t b_addr = a_addr + kWg2ABytes;
+        // A: two MN atoms (taps dx = 0, 1) 128 B apart; 8-slot groups 1024 B apart
+        const uint64_t adesc0 = make_sw128_desc(a_addr, 128, 1024);
+        const uint64_t bdesc0 = make_sw128_desc(b_addr + p.part_box0[0] * kWgBox, kWgBox, 1024);
+        const uint64_t bdesc1 = make_sw128_desc(b_addr + p.part_box0[1] * kWgBox, kWgBox, 1024);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kWgKb / 16; ++k) {
+            // 16 slots further along K = 2048 bytes = +128 in the (addr >> 4) field
+            umma_f16_pair(tmem_base + p.part_col[0], adesc0 + 128 * k, bdesc0 + 128 * k, idesc0, accumulate);
+            if (p.n_parts > 1)
+              umma_f16_pair(tmem_base + p.part_col[1], adesc0 + 128 * k, bdesc1 + 128 * k, idesc1, accumulate);
+            accumulate = 1;
+          }
+          umma_commit_pair(smem_u32(&empty_bar[stage]));
+          if (ch == n_chunks - 1) umma_commit_pair(smem_u32(done_bar));
+        }
+        accumulate = 1;
+        __syncwarp();
+        if (++stage == static_cast<uint32_t>(p.stages)) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      if (n_chunks == 0 && lane == 0) {
+        mbar_arrive(smem_u32(done_bar));
+        asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(done_bar) | 0x01000000u) : "memory");
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    mbar_wait(smem_u32(done_bar), 0);
+    tc_fence_after();
+    const int row = q * 32 + lane;                        // TMEM lane = M row of this CTA: (dx = row / 64, channel)
+    const int tap = 2 * static_cast<int>(rank) + (row >> 6);
+    const int m_row = (tap * p.kc + chunk) * 64 + (row & 63);
+    float* dst = p.ws + (static_cast<int64_t>(ks) * (4 * p.kc * 64) + m_row) * p.ws_ld;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+      uint32_t r[16];
+      if (n_chunks > 0) {
+        tmem_ld16(taddr + c0, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = 0u;
+      }
+      float4* o = reinterpret_cast<float4*>(dst + c0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        o[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                           __uint_as_float(r[4 * j + 3]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
 // dw[n][tap][c] = sum_ks ws[ks][(tap * kc + c / 64) * 64 + c % 64][n]
 __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int ksplits, int m_rows, int ws_ld, int kc, int n_pad,
                                     int cin_pad, float* __restrict__ dw) {
@@ -181,10 +349,25 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int ksplits, i
   dw[(static_cast<int64_t>(n) * 4 + tap) * cin_pad + c] = acc;
 }
 
+static int wgrad_impl() {
+  // MMLF_WGRAD_IMPL=1 selects the single-CTA kernel (debugging); default is the CTA-pair kernel
+  static int impl = -1;
+  if (impl < 0) {
+    const char* e = getenv("MMLF_WGRAD_IMPL");
+    impl = (e && e[0] == '1') ? 1 : 2;
+  }
+  return impl;
+}
+
 static void wgrad_shape(int n_pad, int cin_pad, int& kc, int& n_mblocks, int& ksplits, int& ws_ld) {
   kc = ceil_div(cin_pad, 64);
-  n_mblocks = 4 * kc / 2;
-  ksplits = sm_count() / n_mblocks;
+  if (wgrad_impl() == 2) {
+    n_mblocks = 2 * kc;                       // rows of the workspace / 128; one CTA pair per 64-channel chunk
+    ksplits = (sm_count() / 2) / kc;
+  } else {
+    n_mblocks = 4 * kc / 2;
+    ksplits = sm_count() / n_mblocks;
+  }
   if (ksplits < 1) ksplits = 1;
   ws_ld = n_pad;
 }
@@ -199,6 +382,65 @@ extern "C" int64_t mmlf_conv2x2_wgrad_workspace(int n_pad, int cin_pad) {
   return static_cast<int64_t>(ksplits) * n_mblocks * 128 * ws_ld * sizeof(float);
 }
 
+static int wgrad_pair(const void* dout, int ld_dout, int n_pad, const void* act, int ld_act, int cin_pad, int B, int H,
+                      int W, int type, int dtype, float* workspace, float* dw, void* stream) {
+  Wgrad2Params p;
+  const int Wp = W + 1;
+  p.n_slots = static_cast<int64_t>(B) * (H + 1) * Wp;
+  MMLF_REQUIRE(p.n_slots + 4096 < (1ll << 31), "wgrad: too many slots");
+  p.n_pad = n_pad;
+  int n_mblocks;
+  wgrad_shape(n_pad, cin_pad, p.kc, n_mblocks, p.ksplits, p.ws_ld);
+  int64_t per = ceil_div64(p.n_slots, p.ksplits);
+  per = ceil_div64(per, kWgKb) * kWgKb;
+  p.slots_per_split = per;
+  if (type == 0) {
+    p.tap_base[0] = 0; p.tap_base[1] = Wp;
+  } else {
+    p.tap_base[0] = -Wp - 1; p.tap_base[1] = -1;
+  }
+  // N parts: <= 256 columns each; every CTA supplies half of a part as 1 or 2 boxes of 64 columns starting at its slice
+  p.n_parts = n_pad > 256 ? 2 : 1;
+  p.part_col[0] = 0;
+  p.part_n[0] = n_pad > 256 ? 256 : n_pad;
+  p.part_col[1] = 256;
+  p.part_n[1] = n_pad > 256 ? n_pad - 256 : 0;
+  p.nb = 0;
+  for (int i = 0; i < 2; ++i) {
+    p.part_box0[i] = p.nb;
+    p.part_boxes[i] = i < p.n_parts ? ceil_div(p.part_n[i] / 2, 64) : 0;
+    p.nb += p.part_boxes[i];
+    MMLF_REQUIRE(i >= p.n_parts || p.part_n[i] % 16 == 0, "wgrad: N part %d is not a multiple of 16", p.part_n[i]);
+  }
+  p.ws = workspace;
+  p.act_dtype = p.dout_dtype = dtype;
+  const uint32_t stage_bytes = kWg2ABytes + p.nb * kWgBox;
+  const uint32_t aux_bytes = (2 * kWg2MaxStages + 1) * 8 + 16 + 64;
+  const uint32_t max_smem = 232448;
+  int stages = static_cast<int>((max_smem - 1024 - aux_bytes) / stage_bytes);
+  if (stages > kWg2MaxStages) stages = kWg2MaxStages;
+  MMLF_REQUIRE(stages >= 2, "wgrad: not enough shared memory");
+  p.stages = stages;
+  const uint32_t smem_bytes = 1024 + stages * stage_bytes + aux_bytes;
+
+  CUtensorMap tmap_act, tmap_dout;
+  if (int rc = make_tmap_2d_16(&tmap_act, act, cin_pad, p.n_slots, static_cast<uint64_t>(ld_act) * 2, 64, 72, 128)) return rc;
+  if (int rc = make_tmap_2d_16(&tmap_dout, dout, n_pad, p.n_slots, static_cast<uint64_t>(ld_dout) * 2, 64, kWgKb, 128)) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv2x2_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    MMLF_REQUIRE(e == cudaSuccess, "wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  conv2x2_wgrad2_kernel<<<2 * p.kc * p.ksplits, kWgThreads, smem_bytes, st>>>(tmap_act, tmap_dout, p);
+  if (int rc = check_launch("conv2x2_wgrad2_kernel")) return rc;
+  const int64_t total = static_cast<int64_t>(n_pad) * 4 * cin_pad;
+  wgrad_reduce_kernel<<<static_cast<unsigned>(ceil_div64(total, 256)), 256, 0, st>>>(
+      workspace, p.ksplits, 4 * p.kc * 64, p.ws_ld, p.kc, n_pad, cin_pad, dw);
+  return check_launch("wgrad_reduce_kernel");
+}
+
 extern "C" int mmlf_conv2x2_wgrad(const void* dout, int ld_dout, int n_pad, const void* act, int ld_act, int cin_pad,
                                   int B, int H, int W, int type, int act_dtype, int dout_dtype, float* workspace, float* dw,
                                   void* stream) {
@@ -209,6 +451,7 @@ extern "C" int mmlf_conv2x2_wgrad(const void* dout, int ld_dout, int n_pad, cons
   MMLF_REQUIRE(cin_pad % 16 == 0 && cin_pad >= 16 && cin_pad <= 320, "wgrad: cin_pad %d must be a multiple of 16 in [16, 320]", cin_pad);
   MMLF_REQUIRE(ld_dout % 8 == 0 && ld_act % 8 == 0 && ld_dout >= n_pad && ld_act >= cin_pad, "wgrad: bad row pitch");
   MMLF_REQUIRE(type == 0 || type == 1, "wgrad: type must be 0 or 1");
+  if (wgrad_impl() == 2) return wgrad_pair(dout, ld_dout, n_pad, act, ld_act, cin_pad, B, H, W, type, act_dtype, workspace, dw, stream);
   WgradParams p;
   const int Hp = H + 1, Wp = W + 1;
   p.n_slots = static_cast<int64_t>(B) * Hp * Wp;
