@@ -53,7 +53,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// Slow path of mbar_wait, kept out of line: every wait site would otherwise carry the whole polling loop with its
+// watchdog, and the warp-specialised kernels are sensitive to their instruction-cache footprint.
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
 #if MMLF_WATCHDOG
   long long t0 = 0;
   uint32_t spins = 0;
@@ -71,6 +73,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #else
   while (!mbar_try_wait(bar, parity)) {}
 #endif
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
 
 // ---------------------------------------------------------------- TMA
@@ -161,6 +166,66 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, 
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// One pipeline entry worth of pair MMAs in a single asm block: K16 k-steps (K16 = 1..4), each against one or two
+// N parts.  The single issuing thread is the bottleneck of the kernel (one 72-cycle MMA must be issued every 72
+// cycles), so the descriptors are advanced inside the block with two uniform adds per MMA instead of being rebuilt
+// and moved to uniform registers by the compiler for every instruction (measured: ~16 -> ~5 instructions per MMA).
+//   d0 / d1  : TMEM addresses of the accumulator parts        a_lo / b0_lo / b1_lo : low words of the descriptors
+//   desc_hi  : common high word of all three descriptors       acc : 0 = the very first MMA overwrites the accumulator
+//   idesc / idesc1 : instruction descriptors of the two N parts
+//   kstep    : descriptor-low-word advance per 16-deep k-step (2 for K-major SWIZZLE_128B, 128 for MN-major)
+#define MMLF_MMA_STEP(OFF, PRED, P2)                                            \
+  "add.u32 t, %2, " OFF ";\n\t"                                                  \
+  "mov.b64 da, {t, %5};\n\t"                                                     \
+  "add.u32 t, %3, " OFF ";\n\t"                                                  \
+  "mov.b64 db, {t, %5};\n\t"                                                     \
+  "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %6, " PRED ";\n\t" P2
+#define MMLF_MMA_PART2(OFF, PRED)                                               \
+  "add.u32 t, %4, " OFF ";\n\t"                                                  \
+  "mov.b64 db, {t, %5};\n\t"                                                     \
+  "tcgen05.mma.cta_group::2.kind::f16 [%1], da, db, %8, " PRED ";\n\t"
+#define MMLF_MMA_BLOCK(BODY)                                                    \
+  asm volatile("{\n\t.reg .pred p, pt;\n\t.reg .b32 t;\n\t.reg .b64 da, db;\n\t" \
+               "setp.ne.b32 p, %7, 0;\n\t"                                       \
+               "setp.eq.b32 pt, %7, %7;\n\t" BODY "}"                            \
+               ::"r"(d0), "r"(d1), "r"(a_lo), "r"(b0_lo), "r"(b1_lo), "r"(desc_hi), "r"(idesc), "r"(acc), "r"(idesc1) \
+               : "memory")
+template <int kParts, int kStepLo>
+__device__ __forceinline__ void umma_f16_pair_entry(uint32_t d0, uint32_t d1, uint32_t a_lo, uint32_t b0_lo,
+                                                    uint32_t b1_lo, uint32_t desc_hi, uint32_t idesc, uint32_t idesc1,
+                                                    uint32_t acc, int ksteps) {
+  static_assert(kStepLo == 2 || kStepLo == 128, "descriptor advance per k-step");
+  if constexpr (kParts == 2 && kStepLo == 2) {
+    if (ksteps == 4) {
+      MMLF_MMA_BLOCK(MMLF_MMA_STEP("0", "p", MMLF_MMA_PART2("0", "p")) MMLF_MMA_STEP("2", "pt", MMLF_MMA_PART2("2", "pt"))
+                     MMLF_MMA_STEP("4", "pt", MMLF_MMA_PART2("4", "pt")) MMLF_MMA_STEP("6", "pt", MMLF_MMA_PART2("6", "pt")));
+    } else if (ksteps == 3) {
+      MMLF_MMA_BLOCK(MMLF_MMA_STEP("0", "p", MMLF_MMA_PART2("0", "p")) MMLF_MMA_STEP("2", "pt", MMLF_MMA_PART2("2", "pt"))
+                     MMLF_MMA_STEP("4", "pt", MMLF_MMA_PART2("4", "pt")));
+    } else if (ksteps == 2) {
+      MMLF_MMA_BLOCK(MMLF_MMA_STEP("0", "p", MMLF_MMA_PART2("0", "p")) MMLF_MMA_STEP("2", "pt", MMLF_MMA_PART2("2", "pt")));
+    } else {
+      MMLF_MMA_BLOCK(MMLF_MMA_STEP("0", "p", MMLF_MMA_PART2("0", "p")));
+    }
+  } else if constexpr (kParts == 1 && kStepLo == 2) {
+    if (ksteps == 4) {
+      MMLF_MMA_BLOCK(MMLF_MMA_STEP("0", "p", "") MMLF_MMA_STEP("2", "pt", "") MMLF_MMA_STEP("4", "pt", "")
+                     MMLF_MMA_STEP("6", "pt", ""));
+    } else if (ksteps == 3) {
+      MMLF_MMA_BLOCK(MMLF_MMA_STEP("0", "p", "") MMLF_MMA_STEP("2", "pt", "") MMLF_MMA_STEP("4", "pt", ""));
+    } else if (ksteps == 2) {
+      MMLF_MMA_BLOCK(MMLF_MMA_STEP("0", "p", "") MMLF_MMA_STEP("2", "pt", ""));
+    } else {
+      MMLF_MMA_BLOCK(MMLF_MMA_STEP("0", "p", ""));
+    }
+  } else if constexpr (kParts == 2) {      // MN-major operands: 16 slots further along K = 2048 bytes = +128
+    MMLF_MMA_BLOCK(MMLF_MMA_STEP("0", "p", MMLF_MMA_PART2("0", "p")) MMLF_MMA_STEP("128", "pt", MMLF_MMA_PART2("128", "pt"))
+                   MMLF_MMA_STEP("256", "pt", MMLF_MMA_PART2("256", "pt")) MMLF_MMA_STEP("384", "pt", MMLF_MMA_PART2("384", "pt")));
+  } else {
+    MMLF_MMA_BLOCK(MMLF_MMA_STEP("0", "p", "") MMLF_MMA_STEP("128", "pt", "") MMLF_MMA_STEP("256", "pt", "")
+                   MMLF_MMA_STEP("384", "pt", ""));
+  }
 }
 // arrive on the mbarrier at the same offset in both CTAs of the pair once the issued MMAs have completed
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {

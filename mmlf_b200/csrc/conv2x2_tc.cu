@@ -171,11 +171,10 @@ struct EpiWarp {
 // One segment of up to 32 output channels [c0, c0 + ncols) of the warp's 32 slots (c0 is a multiple of 32): epilogue
 // math, ReLU bits, 16-bit packing into the staging rows, coalesced write-out, column statistics.
 // r holds the fp32 accumulators of this thread's slot.  gate_word: this slot's saved ReLU bits of channels [c0, c0+32).
-// Returns the ReLU bits of the segment.
 template <uint32_t F>
-__device__ __forceinline__ uint32_t epi_segment(const ConvParams& p, const EpiWarp& w, const uint32_t (&r)[32], int c0,
-                                                int ncols, uint32_t gate_word, bool valid, int row0, int rows_valid,
-                                                int lane) {
+__device__ __forceinline__ void epi_segment(const ConvParams& p, const EpiWarp& w, const uint32_t (&r)[32], int c0,
+                                            int ncols, uint32_t gate_word, bool valid, int row0, int rows_valid,
+                                            int lane) {
   using FL = Flags<F>;
   float x[32];
   {
@@ -216,6 +215,7 @@ __device__ __forceinline__ uint32_t epi_segment(const ConvParams& p, const EpiWa
     for (int j = 0; j < 32; ++j) bits |= (x[j] > 0.f ? 1u : 0u) << j;
     if (ncols < 32) bits &= 0xFFFFu;
     bits &= vmask;
+    if (lane < rows_valid) p.relu_bits[(static_cast<int64_t>(row0) + lane) * p.ld_bits + (c0 >> 5)] = bits;
   }
   // slot row `lane` occupies 64 B of the staging buffer; 16-byte chunk j lands at chunk j ^ ((lane >> 1) & 3)
   const uint32_t row_addr = w.stg_addr + lane * 64;
@@ -287,7 +287,6 @@ __device__ __forceinline__ uint32_t epi_segment(const ConvParams& p, const EpiWa
       w.s_stat[p.n_pad + c0 + lane] += q0;
     }
   }
-  return bits;
 }
 
 // Direct-store variant (fp32 slot rows / planar fp32 outputs of the heads)
@@ -391,25 +390,32 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     // ------------------------------------------------------------------ TMA producer.  The whole warp runs the loop so
     // that every operand is warp-uniform (UTMALDG takes uniform registers; a lane-0-only region makes the compiler
     // wrap each instruction in an elect/broadcast loop); one elected lane issues.
+    const bool prof = p.stats != nullptr;
     uint32_t stage = 0, phase = 0;
-    long long t_wait = 0, t_begin = clock64();
+    long long t_wait = 0, t_begin = prof ? clock64() : 0;
+    const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+    const int b_row0 = static_cast<int>(rank) * half_rows;
+    const uint32_t tx_bytes = 2 * stage_bytes;
     for (int tile = pair; tile < p.num_tiles; tile += n_pairs) {
       const int row0 = tile * (2 * kTileM) + static_cast<int>(rank) * kTileM;
+      int kcol = 0;
+#pragma unroll 1
       for (int tap = 0; tap < 4; ++tap) {
-        for (int kc = 0; kc < p.n_kc; ++kc) {
-          const long long tw = clock64();
-          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
-          t_wait += clock64() - tw;
-          const uint32_t fb = smem_u32(&full_bar[stage]);
+        const int arow = row0 + p.tap_off[tap];
+#pragma unroll 1
+        for (int kc = 0; kc < p.n_kc; ++kc, kcol += 64) {
+          long long tw = 0;
+          if (prof) tw = clock64();
+          mbar_wait(empty0 + stage * 8, phase ^ 1u);
+          if (prof) t_wait += clock64() - tw;
+          const uint32_t fb = full0 + stage * 8;
           const uint32_t a_dst = tiles_addr + stage * stage_bytes;
           const uint32_t b_dst = a_dst + kABytes;
-          const int kcol = (tap * p.n_kc + kc) * 64;
           if (elect_one()) {
-            if (leader) mbar_arrive_expect_tx(fb, 2 * stage_bytes);
-            tma_load_2d_pair(a_dst, &tmap_a, fb, kc * 64, row0 + p.tap_off[tap], kEvictNormal);
-            for (int part = 0; part < p.n_parts; ++part)
-              tma_load_2d_pair(b_dst + part * half_rows * 128, &tmap_b, fb, kcol,
-                               part * p.n_part + static_cast<int>(rank) * half_rows, kEvictLast);
+            if (leader) mbar_arrive_expect_tx(fb, tx_bytes);
+            tma_load_2d_pair(a_dst, &tmap_a, fb, kc * 64, arow, kEvictNormal);
+            tma_load_2d_pair(b_dst, &tmap_b, fb, kcol, b_row0, kEvictLast);
+            if (p.n_parts == 2) tma_load_2d_pair(b_dst + half_rows * 128, &tmap_b, fb, kcol, p.n_part + b_row0, kEvictLast);
           }
           __syncwarp();
           if (++stage == static_cast<uint32_t>(p.stages)) {
@@ -419,7 +425,7 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
       }
     }
-    if (p.stats && lane == 0) {
+    if (prof && lane == 0) {
       p.stats[blockIdx.x * 8 + 0] = clock64() - t_begin;   // producer total
       p.stats[blockIdx.x * 8 + 1] = t_wait;                // producer waiting for free stages
     }
@@ -429,44 +435,45 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     if (leader) {
       const uint32_t idesc = make_idesc_16(2 * kTileM, p.n_part, 0, 0, p.ab_dtype, p.ab_dtype);
       const uint32_t part_bytes = static_cast<uint32_t>(half_rows) * 128u;
+      const bool prof = p.stats != nullptr;
+      // descriptor template (address field 0): low word = LBO field, high word = SBO 1024 | version 1 | SWIZZLE_128B
+      const uint64_t desc0 = make_sw128_desc(0, 0, 1024);
+      const uint32_t desc_lo0 = static_cast<uint32_t>(desc0), desc_hi = static_cast<uint32_t>(desc0 >> 32);
+      const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
       uint32_t stage = 0, phase = 0;
       int it = 0;
-      long long t_full = 0, t_tmem = 0, t_begin = clock64();
+      long long t_full = 0, t_tmem = 0, t_begin = prof ? clock64() : 0;
       for (int tile = pair; tile < p.num_tiles; tile += n_pairs, ++it) {
         const int par = it & 1;
-        long long tw = clock64();
+        long long tw = 0;
+        if (prof) tw = clock64();
         mbar_wait(smem_u32(&tmem_empty_bar[par]), ((it >> 1) & 1) ^ 1u);   // region drained (tile it - 2)
         // regions overlap only when n_pad > 256: then the columns shared with tile it - 1 must have been drained
         if (p.n_pad > 256 && it > 0) mbar_wait(smem_u32(tmem_ovl_bar), (it - 1) & 1);
-        t_tmem += clock64() - tw;
+        if (prof) t_tmem += clock64() - tw;
         tc_fence_after();
         const uint32_t acc_base = tmem_base + (par ? base1 : 0);
         uint32_t accumulate = 0;
+#pragma unroll 1
         for (int tap = 0; tap < 4; ++tap) {
+#pragma unroll 1
           for (int kc = 0; kc < p.n_kc; ++kc) {
-            tw = clock64();
-            mbar_wait(smem_u32(&full_bar[stage]), phase);
-            t_full += clock64() - tw;
+            if (prof) tw = clock64();
+            mbar_wait(full0 + stage * 8, phase);
+            if (prof) t_full += clock64() - tw;
             tc_fence_after();
             const uint32_t a_addr = tiles_addr + stage * stage_bytes;
-            const uint32_t b_addr = a_addr + kABytes;
             const int ksteps = (kc == p.n_kc - 1) ? p.last_ksteps : 4;
-            const uint64_t adesc0 = make_sw128_desc(a_addr, 0, 1024);
-            const uint64_t bdesc0 = make_sw128_desc(b_addr, 0, 1024);
+            const uint32_t a_lo = desc_lo0 + ((a_addr & 0x3FFFFu) >> 4);
+            const uint32_t b_lo = desc_lo0 + (((a_addr + kABytes) & 0x3FFFFu) >> 4);
             const bool last = (tap == 3 && kc == p.n_kc - 1);
             if (elect_one()) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (k < ksteps) {
-                  // advancing by k * 32 bytes inside the 128-byte swizzle row = +2k in the (addr >> 4) field
-                  umma_f16_pair(acc_base, adesc0 + 2 * k, bdesc0 + 2 * k, idesc, accumulate);
-                  if (p.n_parts == 2)
-                    umma_f16_pair(acc_base + p.n_part, adesc0 + 2 * k, bdesc0 + (part_bytes >> 4) + 2 * k, idesc,
-                                  accumulate);
-                  accumulate = 1;
-                }
-              }
-              umma_commit_pair(smem_u32(&empty_bar[stage]));
+              if (p.n_parts == 2)
+                umma_f16_pair_entry<2, 2>(acc_base, acc_base + p.n_part, a_lo, b_lo, b_lo + (part_bytes >> 4), desc_hi, idesc,
+                                          idesc, accumulate, ksteps);
+              else
+                umma_f16_pair_entry<1, 2>(acc_base, acc_base, a_lo, b_lo, b_lo, desc_hi, idesc, idesc, accumulate, ksteps);
+              umma_commit_pair(empty0 + stage * 8);
               if (last) umma_commit_pair(smem_u32(&tmem_full_bar[par]));
             }
             accumulate = 1;
@@ -478,7 +485,7 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           }
         }
       }
-      if (p.stats && lane == 0) {
+      if (prof && lane == 0) {
         p.stats[blockIdx.x * 8 + 2] = clock64() - t_begin;   // MMA issuer total
         p.stats[blockIdx.x * 8 + 3] = t_full;                // ... waiting for TMA data
         p.stats[blockIdx.x * 8 + 4] = t_tmem;                // ... waiting for the epilogue to free TMEM
@@ -516,21 +523,17 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       // last position of this warp inside the shared columns / overall (-1: none)
       const int last_ovl_i = ovl_pos > half ? half + ((ovl_pos - 1 - half) & ~1) : -1;
       const int last_i = nseg > half ? half + ((nseg - 1 - half) & ~1) : -1;
-      // this slot's saved ReLU bits, fetched before the accumulators are ready (one word per 32 channels)
-      uint32_t gw[6] = {0u, 0u, 0u, 0u, 0u, 0u};
-      if (FL::gate(p)) {
-        if (in_range) {
-          const uint32_t* g = p.gate_bits + s * p.ld_bits;
-#pragma unroll
-          for (int k = 0; k < 5; ++k) {
-            const int i = half + 2 * k;
-            if (i < nseg) gw[k] = __ldg(g + (seg_c0(i) >> 5));
-          }
-        }
-      }
-      const long long tw = clock64();
+      // this slot's saved ReLU bits of the first two segments, fetched before the accumulators are ready (one word per
+      // 32 channels); the words of the following segments are prefetched one loop iteration ahead
+      const uint32_t* gate_row = (FL::gate(p) && in_range) ? p.gate_bits + s * p.ld_bits : nullptr;
+      auto gate_word = [&](int i) { return (gate_row && i < nseg) ? __ldg(gate_row + (seg_c0(i) >> 5)) : 0u; };
+      uint32_t g0 = gate_word(half), g1 = gate_word(half + 2);
+      if (FL::bits(p) && half == 0 && in_range)                 // words beyond the channels (ld_bits > ceil(n_pad / 32))
+        for (int ww = (p.n_pad + 31) >> 5; ww < p.ld_bits; ++ww) p.relu_bits[s * p.ld_bits + ww] = 0u;
+      long long tw = 0;
+      if (p.stats) tw = clock64();
       mbar_wait(smem_u32(&tmem_full_bar[par]), (it >> 1) & 1);
-      t_wait += clock64() - tw;
+      if (p.stats) t_wait += clock64() - tw;
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (par ? base1 : 0);
       auto load_seg = [&](int i, uint32_t (&r)[32]) {
@@ -548,46 +551,30 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
       };
       release(last_ovl_i < 0, last_i < 0);               // nothing of mine in the shared columns / in this tile
-      uint32_t rbits[6] = {0u, 0u, 0u, 0u, 0u, 0u};
-      auto process = [&](const uint32_t (&r)[32], int i, int k) {
+      auto process = [&](const uint32_t (&r)[32], int i, uint32_t gword) {
         const int c0 = seg_c0(i), n = seg_n(i);
-        if (!FL::direct(p)) {
-          const uint32_t bts = epi_segment<F>(p, w, r, c0, n, gw[k], valid, row0, rows_valid, lane);
-          if (FL::bits(p)) rbits[k] = bts;
-        } else {
-          epi_box_direct(p, s_add, s_mul, r, c0, n, s, in_range, valid, b, sy, sx);
-        }
+        if (!FL::direct(p)) epi_segment<F>(p, w, r, c0, n, gword, valid, row0, rows_valid, lane);
+        else epi_box_direct(p, s_add, s_mul, r, c0, n, s, in_range, valid, b, sy, sx);
       };
       uint32_t ra[32], rb[32];
       if (half < nseg) load_seg(half, ra);
-#pragma unroll
-      for (int k = 0; k < 5; k += 2) {
-        const int i = half + 2 * k;
-        if (i < nseg) {
+      // NOT unrolled: the body (two segments) is ~1000 instructions; unrolling it five times pushed the kernel far
+      // beyond the instruction cache and starved the producer / MMA warps ('no_inst' stalls)
+#pragma unroll 1
+      for (int i = half; i < nseg; i += 4) {
+        const uint32_t g2 = gate_word(i + 4), g3 = gate_word(i + 6);
+        tmem_ld_wait();
+        if (i + 2 < nseg) load_seg(i + 2, rb);               // in flight while segment i is processed
+        release(i == last_ovl_i, i == last_i);
+        process(ra, i, g0);
+        if (i + 2 < nseg) {
           tmem_ld_wait();
-          if (i + 2 < nseg) load_seg(i + 2, rb);               // in flight while segment i is processed
-          release(i == last_ovl_i, i == last_i);
-          process(ra, i, k);
-          if (i + 2 < nseg) {
-            tmem_ld_wait();
-            if (i + 4 < nseg) load_seg(i + 4, ra);
-            release(i + 2 == last_ovl_i, i + 2 == last_i);
-            process(rb, i + 2, k + 1);
-          }
+          if (i + 4 < nseg) load_seg(i + 4, ra);
+          release(i + 2 == last_ovl_i, i + 2 == last_i);
+          process(rb, i + 2, g1);
         }
-      }
-      if (FL::bits(p)) {
-        if (in_range) {
-          uint32_t* g = p.relu_bits + s * p.ld_bits;
-#pragma unroll
-          for (int k = 0; k < 5; ++k) {
-            const int i = half + 2 * k;
-            if (i < nseg) g[seg_c0(i) >> 5] = rbits[k];
-          }
-          // words beyond the channels (ld_bits > ceil(n_pad / 32)) are cleared by the even warp
-          if (half == 0)
-            for (int ww = (p.n_pad + 31) >> 5; ww < p.ld_bits; ++ww) g[ww] = 0u;
-        }
+        g0 = g2;
+        g1 = g3;
       }
     }
     if (p.stats && warp == 2 && lane == 0) {

@@ -266,25 +266,26 @@ conv2x2_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
     if (leader) {
       const uint32_t idesc0 = make_idesc_16(256, p.part_n[0], 1, 1, p.act_dtype, p.dout_dtype);
       const uint32_t idesc1 = make_idesc_16(256, p.n_parts > 1 ? p.part_n[1] : 16, 1, 1, p.act_dtype, p.dout_dtype);
+      const uint64_t adesc_t = make_sw128_desc(0, 128, 1024), bdesc_t = make_sw128_desc(0, kWgBox, 1024);
+      const uint32_t a_lo0 = static_cast<uint32_t>(adesc_t), b_lo0 = static_cast<uint32_t>(bdesc_t);
+      const uint32_t desc_hi = static_cast<uint32_t>(adesc_t >> 32);
       uint32_t stage = 0, phase = 0, accumulate = 0;
       for (int ch = 0; ch < n_chunks; ++ch) {
         mbar_wait(smem_u32(&full_bar[stage]), phase);
         tc_fence_after();
         const uint32_t a_addr = tiles_addr + stage * stage_bytes;
         const uint32_t b_addr = a_addr + kWg2ABytes;
-        // A: two MN atoms (taps dx = 0, 1) 128 B apart; 8-slot groups 1024 B apart
-        const uint64_t adesc0 = make_sw128_desc(a_addr, 128, 1024);
-        const uint64_t bdesc0 = make_sw128_desc(b_addr + p.part_box0[0] * kWgBox, kWgBox, 1024);
-        const uint64_t bdesc1 = make_sw128_desc(b_addr + p.part_box0[1] * kWgBox, kWgBox, 1024);
+        // A: two MN atoms (taps dx = 0, 1) 128 B apart; B: atoms kWgBox apart; 8-slot groups 1024 B apart
+        const uint32_t a_lo = a_lo0 + ((a_addr & 0x3FFFFu) >> 4);
+        const uint32_t b0_lo = b_lo0 + (((b_addr + p.part_box0[0] * kWgBox) & 0x3FFFFu) >> 4);
+        const uint32_t b1_lo = b_lo0 + (((b_addr + p.part_box0[1] * kWgBox) & 0x3FFFFu) >> 4);
         if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < kWgKb / 16; ++k) {
-            // 16 slots further along K = 2048 bytes = +128 in the (addr >> 4) field
-            umma_f16_pair(tmem_base + p.part_col[0], adesc0 + 128 * k, bdesc0 + 128 * k, idesc0, accumulate);
-            if (p.n_parts > 1)
-              umma_f16_pair(tmem_base + p.part_col[1], adesc0 + 128 * k, bdesc1 + 128 * k, idesc1, accumulate);
-            accumulate = 1;
-          }
+          if (p.n_parts > 1)
+            umma_f16_pair_entry<2, 128>(tmem_base + p.part_col[0], tmem_base + p.part_col[1], a_lo, b0_lo, b1_lo, desc_hi,
+                                        idesc0, idesc1, accumulate, 4);
+          else
+            umma_f16_pair_entry<1, 128>(tmem_base + p.part_col[0], tmem_base, a_lo, b0_lo, b0_lo, desc_hi, idesc0, idesc0,
+                                        accumulate, 4);
           umma_commit_pair(smem_u32(&empty_bar[stage]));
           if (ch == n_chunks - 1) umma_commit_pair(smem_u32(done_bar));
         }
