@@ -24,6 +24,7 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 import numpy as np  # noqa: E402
 
+ESE_MEMBERS = 70
 FULL_KW = dict(model_ksize=2, model_in_blocks=3, model_out_blocks=8, model_chs=70, model_views=9, model_cross=False,
                model_uncert=False, model_unet=False, model_discrete=False, model_no_batchnorm=False,
                model_batchnorm_momentum=0.1, val_disp_min=-3.5, val_disp_max=3.5)
@@ -161,6 +162,20 @@ def cpu_infer_step(variant, size, threads):
     return lambda it: net.forward(*views)
 
 
+def cpu_ese_step(size, members, threads):
+    import torch
+    import oracle
+    torch.set_num_threads(threads)
+    from mmlf_b200.model.feed_forward import FeedForward
+    torch.manual_seed(0)
+    state = {k: v.numpy().copy() for k, v in FeedForward(**model_kwargs('upr')).state_dict().items()}
+    net = oracle.FeedForwardOracle(state, model_uncert=True)
+    rng = np.random.RandomState(0)
+    views = [rng.uniform(0, 1, (1, 9, 3, size, size)).astype(np.float32) for _ in range(4)]
+    step_size = 7.0 / members
+    return lambda it: oracle.ensemble_forward(net, *views, -3.5, 3.5, step_size)
+
+
 def run_cpu(args, steps, warmup):
     """Times the oracle port on the host cores on a bounded sample of the workload."""
     threads = os.cpu_count() or 1
@@ -168,6 +183,12 @@ def run_cpu(args, steps, warmup):
         b = args.cpu_batch
         step = cpu_train_step(args.variant, b, args.ps, threads)
         units, unit, sample = b, 'patches/s', f'{b} patches of {args.ps} px per step (fwd + loss + bwd + Adam), fp32 numpy'
+    elif args.workload == 'ese':
+        size, members = args.cpu_size, 2
+        step = cpu_ese_step(size, members, threads)
+        units, unit = size * size / 1e6 * members / ESE_MEMBERS, 'Mpx/s'
+        sample = (f'{members} of the {ESE_MEMBERS} ensemble members (Shift + UPR forward + reduce) on one {size}x{size} '
+                  f'crop per step, scaled x{members}/{ESE_MEMBERS}, fp32 numpy')
     else:
         size = args.cpu_size
         step = cpu_infer_step(args.variant, size, threads)
@@ -189,7 +210,7 @@ def main():
     ap.add_argument('--steps', type=int, default=8)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='train', choices=['train', 'infer'])
+    ap.add_argument('--workload', default='train', choices=['train', 'infer', 'ese'])
     ap.add_argument('--variant', default='base', choices=['base', 'upr', 'dpp'])
     ap.add_argument('--bs', type=int, default=512, help='global batch (train)')
     ap.add_argument('--ps', type=int, default=96, help='patch size (train)')
@@ -200,16 +221,23 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+    if args.workload == 'ese':
+        args.variant = 'upr'                                 # --val_ensamble forces model_uncert (train/cli.py:68-69)
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     metric = ('train patches/s (bs512, 96px)' if args.workload == 'train' else 'full-LF inference Mpx/s')
     unit = 'patches/s' if args.workload == 'train' else 'Mpx/s'
-    config = {'workload': (f'{args.variant.upper()} training step bs={args.bs} ps={args.ps}, 4-stream FeedForward '
-                           f'(9 views, 70 ch, 108 bins), fwd+loss+bwd+allreduce+Adam' if args.workload == 'train' else
-                           f'{args.variant.upper()} full-LF inference, one 9x9-view {args.size}x{args.size} light field '
-                           f'per GPU and step'),
-              'global_batch': args.bs if args.workload == 'train' else world,
+    wl = {'train': f'{args.variant.upper()} training step bs={args.bs} ps={args.ps}, 4-stream FeedForward '
+                   f'(9 views, 70 ch, 108 bins), fwd+loss+bwd+allreduce+Adam',
+          'infer': f'{args.variant.upper()} full-LF inference, one 9x9-view {args.size}x{args.size} light field per GPU '
+                   f'and step',
+          'ese': f'ESE (--val_ensamble) full-LF shift-ensemble inference, {ESE_MEMBERS} UPR members (shift -3.5..3.4 step '
+                 f'0.1) of one 9x9-view {args.size}x{args.size} light field per step, members sharded over the GPUs, '
+                 f'incl. shifts + Laplace-mixture reduce'}[args.workload]
+    strong = args.workload in ('train', 'ese')
+    config = {'workload': wl,
+              'global_batch': args.bs if args.workload == 'train' else (1 if args.workload == 'ese' else world),
               'parallelism': f'dp{world}', 'l2': 'inputs larger than L2 (>= 113 MB fp32 per step and GPU)',
               'activation_storage': args.precision, 'gradient_storage': 'bf16', 'accumulate': 'fp32'}
 
@@ -219,7 +247,7 @@ def main():
         base, dt = run_cpu(args, max(args.steps, 1), min(args.warmup, 1))
         line = {'impl': 'reference', 'metric': metric, 'value': base['value'], 'unit': unit, 'n_gpus': world,
                 'steps': args.steps, 'warmup': min(args.warmup, 1), 'ms_per_step': dt * 1e3, 'higher_is_better': True,
-                'scaling': 'strong' if args.workload == 'train' else 'weak', 'vs_baseline': None, 'dtype': 'f32',
+                'scaling': 'strong' if strong else 'weak', 'vs_baseline': None, 'dtype': 'f32',
                 'data': 'synthetic', 'config': config, 'cpu_baseline': base,
                 'e2e': {'value': base['value'], 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
                 'gpu_launches': 0}
@@ -272,6 +300,22 @@ def main():
         units_per_step = args.bs
         flops_per_step = train_step_flops(args.bs, H, W, args.variant)
         host = [t.cpu().pin_memory() for t in views + [gt, mask]]
+    elif args.workload == 'ese':
+        from mmlf_b200.model.ensamble import Ensamble
+        B, H, W = 1, args.size, args.size
+        gen = torch.Generator(device=dev).manual_seed(1234)          # every rank sees the same light field
+        views = [torch.rand((B, 9, 3, H, W), device=dev, generator=gen) for _ in range(4)]
+        model.eval()
+        ens = Ensamble(model, -3.5, 3.5, 0.1)
+
+        def step(vs, gt_=None, mask_=None):
+            with torch.no_grad():
+                return ens(*vs)['mean']
+        my_members = len(range(rank, ESE_MEMBERS, world))
+        units_per_step = H * W / 1e6
+        flops_per_step = ESE_MEMBERS * net_forward_flops(1, H, W, 'upr')
+        host = [t.cpu().pin_memory() for t in views]
+        gt = mask = None
     else:
         B, H, W = 1, args.size, args.size
         views = [torch.rand((B, 9, 3, H, W), device=dev, generator=gen) for _ in range(4)]
@@ -337,6 +381,8 @@ def main():
     if args.workload == 'train':
         conv_flops_rank = 2.0 * fwd - 4 * conv_flops(Bl, H, W, 27, 70, 0)
         # the small head convs of BASE / UPR run partly on CUDA cores: negligible (< 0.1 %)
+    elif args.workload == 'ese':
+        conv_flops_rank = my_members * fwd
     else:
         conv_flops_rank = fwd
     conv_time = sum(conv_ms) / args.steps / 1e3
@@ -404,7 +450,7 @@ def main():
         cpu_base, _ = run_cpu(args, 2, 1)
     line = {'metric': metric, 'value': units_per_step / (ms_per_step / 1e3), 'unit': unit, 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
-            'scaling': 'strong' if args.workload == 'train' else 'weak', 'vs_baseline': None,
+            'scaling': 'strong' if strong else 'weak', 'vs_baseline': None,
             'dtype': args.precision + ' storage / fp32 accumulate', 'data': 'synthetic', 'config': config,
             'roofline': roofline, 'cpu_baseline': cpu_base, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
             'kernel_ms_per_step': {k: round(v, 3) for k, v in sorted(shares.items(), key=lambda kv: -kv[1])}}

@@ -393,6 +393,8 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const bool prof = p.stats != nullptr;
     uint32_t stage = 0, phase = 0;
     long long t_wait = 0, t_begin = prof ? clock64() : 0;
+    unsigned long long ns_begin = 0;
+    if (prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_begin));
     const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
     const int b_row0 = static_cast<int>(rank) * half_rows;
     const uint32_t tx_bytes = 2 * stage_bytes;
@@ -428,6 +430,9 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     if (prof && lane == 0) {
       p.stats[blockIdx.x * 8 + 0] = clock64() - t_begin;   // producer total
       p.stats[blockIdx.x * 8 + 1] = t_wait;                // producer waiting for free stages
+      unsigned long long ns_end;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_end));
+      p.stats[blockIdx.x * 8 + 7] = static_cast<long long>(ns_end - ns_begin);   // producer total in ns (-> SM clock)
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA; warp-uniform loop,

@@ -17,7 +17,9 @@ def init_from_env(backend=None):
             backend = 'nccl' if torch.cuda.is_available() else 'gloo'
         if backend == 'nccl':
             torch.cuda.set_device(local)
-        dist.init_process_group(backend=backend)
+            dist.init_process_group(backend=backend, device_id=torch.device('cuda', local))
+        else:
+            dist.init_process_group(backend=backend)
     return rank, world, local
 
 
@@ -76,3 +78,47 @@ class GradBucket:
 
     def all_reduce(self):
         all_reduce_sum_(self.flat)
+
+
+# ------------------------------------------------------------------------------------------------- full-image bands
+def band_rows(H, rank, world, radius):
+    """Row band of rank `rank` when an H-row image is split over `world` ranks: returns
+    (lo, hi, a, b) -- the rank owns output rows [lo, hi) and reads input rows [a, b) = the band plus a `radius`-row
+    halo clipped to the image (at the image border the network's own zero padding applies, which is exact)."""
+    per = (H + world - 1) // world
+    lo = min(H, rank * per)
+    hi = min(H, lo + per)
+    return lo, hi, max(0, lo - radius), min(H, hi + radius)
+
+
+def gather_bands(band, H, rank, world, radius, dim):
+    """All-gather the owned rows of every rank along `dim` -> the whole image on every rank."""
+    if world == 1:
+        return band
+    per = (H + world - 1) // world
+    shape = list(band.shape)
+    shape[dim] = per
+    padded = band.new_zeros(shape)
+    padded.narrow(dim, 0, band.shape[dim]).copy_(band)
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded)
+    rows = [p.narrow(dim, 0, band_rows(H, r, world, radius)[1] - band_rows(H, r, world, radius)[0])
+            for r, p in enumerate(parts)]
+    return torch.cat(rows, dim)
+
+
+def banded_forward(model, views, radius=11):
+    """Full-image inference of one light field sharded by rows over the ranks: the FCN's receptive field is
+    `radius` = 11 px for the published topology (3 + 8 blocks of 2x2 conv pairs; `model_radius` in train/cli.py:95),
+    so each rank runs the network on its band + halo and keeps its own rows.  Any circular Shift must already have
+    been applied to the whole image.  Returns the gathered dict {'mean', 'logvar'} (B, H, W) / {'scores'} (B, S, H, W)."""
+    rank, world = shard_info()
+    H = views[0].shape[-2]
+    lo, hi, a, b = band_rows(H, rank, world, radius)
+    out = model(*[None if v is None else v[..., a:b, :].contiguous() for v in views])
+    res = {}
+    for k in ('mean', 'logvar', 'scores'):
+        t = out[k]
+        if t is not None:
+            res[k] = gather_bands(t[..., lo - a:hi - a, :].contiguous(), H, rank, world, radius, dim=t.dim() - 2)
+    return res

@@ -13,7 +13,8 @@ w = u.pack_weight((np.random.RandomState(0).normal(0, 0.03, (cout, cin, 2, 2))).
 stats = torch.zeros((148, 8), dtype=torch.int64, device='cuda')
 lib = u._lib.lib()
 lib.mmlf_debug_conv_stats.argtypes = [C.c_void_p]
-for i in range(3):
+REPS = int(os.environ.get('CONV_STATS_REPS', '3'))
+for i in range(REPS):
     u.run_conv(x, cin_pad, cin_pad, w, n_pad, B, H, W, ctype, relu=True, ab=u.FP16, out_dt=u.FP16)
 lib.mmlf_debug_conv_stats(C.c_void_p(stats.data_ptr()))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -27,5 +28,6 @@ names = ['producer total', 'producer wait-empty', 'mma total', 'mma wait-full(TM
 print(f'{B}x{H}x{W} {cin}->{cout} type {ctype}: {e0.elapsed_time(e1)*1e3:.1f} us; tiles/pair = {np.ceil(n_slots/256)/74:.2f}')
 for i, n in enumerate(names):
     print(f'  {n:28s} leader {lead[:, i].mean():10.0f}  peer {peer[:, i].mean():10.0f} cycles')
+print(f'  SM clock during the kernel: {lead[:, 0].mean() / lead[:, 7].mean() * 1e3:.0f} MHz (producer cycles / globaltimer ns)')
 flops = 2.0 * n_slots * cout * 4 * cin
 print(f'  {flops / (e0.elapsed_time(e1) * 1e-3) / 1e12:.1f} TFLOP/s algorithmic')

@@ -1,7 +1,7 @@
 #!/bin/bash
-# One gpurun call worth of round evidence: -m gpu suites, benches (train / infer / reference arm), ncu launch lists
-# and one full capture of the conv kernel (B200_PROFILING.md recipe).  Everything lands in gpurun_out/.
-#   usage: tests/run_gpu_round.sh [tag]      (tag is appended to the output file names)
+# One gpurun call worth of round evidence: -m gpu suites, benches (train / infer / ese / reference arm), the per-kernel
+# roofline table, ncu launch lists and full captures of the dominant kernels (B200_PROFILING.md recipe).
+# Everything lands in gpurun_out/.   usage: tests/run_gpu_round.sh [tag] [noncu]
 cd "$(dirname "$0")/.."
 TAG=${1:-r01}
 O=gpurun_out
@@ -15,18 +15,34 @@ timeout 600 python __graft_entry__.py smoke > $O/smoke_$TAG.log 2>&1; echo "smok
 
 timeout 900 python bench.py > $O/bench_train_$TAG.json 2> $O/bench_train_$TAG.err; echo "bench train: $?"
 timeout 600 python bench.py --workload infer > $O/bench_infer_$TAG.json 2> $O/bench_infer_$TAG.err; echo "bench infer: $?"
+timeout 600 python bench.py --workload ese --steps 3 > $O/bench_ese_$TAG.json 2> $O/bench_ese_$TAG.err; echo "bench ese: $?"
+timeout 600 python bench.py --variant upr --steps 4 --no-cpu-baseline > $O/bench_train_upr_$TAG.json 2> $O/bench_train_upr_$TAG.err; echo "bench upr: $?"
+timeout 600 python bench.py --variant dpp --steps 4 --no-cpu-baseline > $O/bench_train_dpp_$TAG.json 2> $O/bench_train_dpp_$TAG.err; echo "bench dpp: $?"
 timeout 600 python bench.py --bs 64 --no-cpu-baseline > $O/bench_train_bs64_$TAG.json 2> $O/bench_train_bs64_$TAG.err; echo "bench bs64: $?"
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_reference_$TAG.json 2> $O/bench_reference_$TAG.err; echo "bench reference: $?"
+timeout 900 python tools/kernel_bench.py --out $O/kernel_roofline_$TAG.jsonl > $O/kernel_bench_$TAG.log 2>&1; echo "kernel bench: $?"
 
 if [ "$2" != "noncu" ]; then
-  CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
+  NCU="ncu --clock-control none"
+  CMD="python bench.py --bs 64 --steps 2 --warmup 3 --no-cpu-baseline"
   $CMD > $O/plain_train.log 2>&1 &&
-  ncu --metrics gpu__time_duration.sum --clock-control none -s 1400 -c 1000 --csv --log-file $O/launches_train_$TAG.csv $CMD > $O/ncu_launch_train.log 2>&1
+  $NCU --metrics gpu__time_duration.sum -s 1400 -c 1000 --csv --log-file $O/launches_train_bs64_$TAG.csv $CMD > $O/ncu_launch_train.log 2>&1
   CMD="python bench.py --workload infer --steps 2 --warmup 3 --no-cpu-baseline"
   $CMD > $O/plain_infer.log 2>&1 &&
-  ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/launches_infer_$TAG.csv $CMD > $O/ncu_launch_infer.log 2>&1
-  $CMD > $O/plain_infer2.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:conv2x2_tc -s 143 -c 2 -f -o $O/prof_conv_$TAG $CMD > $O/ncu_full.log 2>&1
-  tail -n 2 $O/ncu_launch_train.log $O/ncu_launch_infer.log $O/ncu_full.log
+  $NCU --metrics gpu__time_duration.sum -c 300 --csv --log-file $O/launches_infer_$TAG.csv $CMD > $O/ncu_launch_infer.log 2>&1
+  # full captures, one kernel each, from the per-kernel bench (3 warm-up launches skipped)
+  cap() {   # name, kernel regex, --only filter
+    python tools/kernel_bench.py --only "$3" --reps 1 > $O/plain_$1.log 2>&1 &&
+    $NCU --set full --import-source on -k "regex:$2" -s 3 -c 1 -f -o $O/prof_$1_$TAG python tools/kernel_bench.py --only "$3" --reps 1 > $O/ncu_$1.log 2>&1
+    tail -n 1 $O/ncu_$1.log
+  }
+  cap conv280 conv2x2_tc2 "conv2x2 280->280 pad0 train"
+  cap conv70 conv2x2_tc2 "conv2x2 70->70 pad0 train"
+  cap wgrad280 conv2x2_wgrad2 "wgrad 280->280 pad0 train"
+  cap bn_apply slot_map "bn_apply_relu"
+  cap bn_bwd_reduce col_reduce "bn_bwd_reduce"
+  cap bn_bwd_apply slot_map "bn_bwd_apply"
+  cap lf_shift lf_shift "lf_shift"
+  cap loss_ce loss_ce "loss_ce"
 fi
-ls -la $O | tail -n 30
+ls -la $O | tail -n 40

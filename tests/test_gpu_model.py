@@ -294,6 +294,32 @@ def test_ensamble(golden):
         Ensamble(m, -3.5, 3.5, 1.0)(T(h), T(v))
 
 
+def test_row_bands_with_halo_equal_whole_image(golden):
+    """full-image inference split into row bands with an 11-px halo is exact.  The three 'ranks'
+    are simulated on one GPU with parallel.band_rows (the gather itself is covered by the gloo tests)."""
+    from mmlf_b200 import parallel
+    g = golden('net_tiny_upr_full.npz')
+    kw = fx.model_kwargs('upr', False, chs=8)
+    m = _build(kw, _state(g))
+    m.eval()
+    h, v, i, d, gt = fx.synth_batch(91, 1, 64, 40)
+    views = [torch.from_numpy(a).cuda() for a in (h, v, i, d)]
+    radius = kw['model_in_blocks'] + kw['model_out_blocks']
+    with torch.no_grad():
+        whole = m(*views)
+        parts = {'mean': [], 'logvar': []}
+        for r in range(3):
+            lo, hi, a, b = parallel.band_rows(64, r, 3, radius)
+            out = m(*[t[..., a:b, :].contiguous() for t in views])
+            for k in parts:
+                parts[k].append(out[k][..., lo - a:hi - a, :])
+    for k in parts:
+        got = torch.cat(parts[k], -2)
+        err = (got - whole[k]).abs().max().item()
+        report(test='row_bands', key=k, max_abs=err)
+        assert err == 0.0, (k, err)
+
+
 def test_no_cpu_fallback():
     from mmlf_b200.model.feed_forward import FeedForward
     m = FeedForward(**fx.model_kwargs('base', False, chs=8))
