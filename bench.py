@@ -339,9 +339,13 @@ def main():
     barrier()
 
     # ---------------- timed region: inputs resident in HBM, CUDA events, max over ranks
+    # train: every C-ABI call is bracketed by a CUDA-event pair (the stream is always full at these sizes, so the pairs
+    # measure kernel time).  infer / ese: the product path replays a CUDA graph, which cannot be bracketed per kernel;
+    # the per-kernel times come from a second, un-graphed pass below.
+    graphed = args.workload != 'train'
     sampler = ClockSampler(local) if rank == 0 else None
     _lib.launch_count = 0
-    _lib.set_profile(True)
+    _lib.set_profile(not graphed)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_wall0 = time.time()
@@ -349,6 +353,7 @@ def main():
     for _ in range(args.steps):
         step(views, gt, mask)
     e1.record()
+    host_ms_per_step = (time.time() - t_wall0) * 1e3 / args.steps      # time the host needs to enqueue one step
     barrier()
     t_wall1 = time.time()
     prof = _lib.set_profile(False)
@@ -358,12 +363,30 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = ms.item() / args.steps
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    prof_steps = args.steps
+    if graphed:
+        # un-graphed profiling pass: a device-side sleep in front of every forward lets the host enqueue the whole
+        # forward before the first kernel starts, so each event pair brackets exactly one kernel
+        net = model
+        net.use_cuda_graph = False
+        prof_steps = 3
+        _lib.set_profile(True)
+        with torch.no_grad():
+            for i in range(prof_steps):
+                torch.cuda._sleep(20_000_000)
+                if args.workload == 'ese':
+                    net.raw_forward(views, shift_disp=-3.5 + 0.1 * (7 * i + 3))
+                else:
+                    step(views, gt, mask)
+        torch.cuda.synchronize()
+        prof = _lib.set_profile(False)
+        net.use_cuda_graph = True
 
     # ---------------- per-kernel shares and the roofline of the dominant kernel (the tcgen05 conv)
     by_name = {}
     for name, a, b in prof:
         by_name.setdefault(name, []).append(a.elapsed_time(b))
-    shares = {k: sum(v) / args.steps for k, v in by_name.items()}
+    shares = {k: sum(v) / prof_steps for k, v in by_name.items()}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -374,7 +397,7 @@ def main():
         peak_tf, peak_src = 1400.0, 'fallback (B200_PROFILING.md: sustained ~1.4 PFLOP/s)'
     conv_ms = by_name.get('mmlf_conv2x2', [])
     wgrad_ms = by_name.get('mmlf_conv2x2_wgrad', [])
-    n_conv = len(conv_ms) / args.steps
+    n_conv = len(conv_ms) / prof_steps
     # algorithmic flops of all conv2x2 launches of one step on this rank: forward convs + data gradients
     Bl = B
     fwd = net_forward_flops(Bl, H, W, args.variant)
@@ -382,18 +405,21 @@ def main():
         conv_flops_rank = 2.0 * fwd - 4 * conv_flops(Bl, H, W, 27, 70, 0)
         # the small head convs of BASE / UPR run partly on CUDA cores: negligible (< 0.1 %)
     elif args.workload == 'ese':
-        conv_flops_rank = my_members * fwd
+        conv_flops_rank = fwd                                # the profiling pass times single members
     else:
         conv_flops_rank = fwd
-    conv_time = sum(conv_ms) / args.steps / 1e3
+    conv_time = sum(conv_ms) / prof_steps / 1e3
     achieved = conv_flops_rank / conv_time / 1e12 if conv_time > 0 else 0.0
     roofline = {'kernel': 'conv2x2_tc_kernel (all forward + data-gradient launches of a step)', 'bound': 'tensor',
                 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
                 'peak_source': peak_src, 'traffic': None, 'launches_per_step': n_conv,
                 'avg_launch_ms': (sum(conv_ms) / len(conv_ms)) if conv_ms else None,
-                'share_of_step': conv_time * 1e3 / ms_per_step}
+                'share_of_step': conv_time * 1e3 * (my_members if args.workload == 'ese' else 1) / ms_per_step}
+    if graphed:
+        roofline['note'] = ('value: CUDA-graph replay; kernel times: separate un-graphed pass of %d forward(s), events '
+                            'around every launch' % prof_steps)
     if wgrad_ms:
-        wg_time = sum(wgrad_ms) / args.steps / 1e3
+        wg_time = sum(wgrad_ms) / prof_steps / 1e3
         wg_flops = fwd                                        # weight gradients cost one forward's worth of MACs
         roofline['wgrad'] = {'kernel': 'conv2x2_wgrad_kernel + reduce', 'achieved': wg_flops / wg_time / 1e12,
                              'frac': wg_flops / wg_time / 1e12 / peak_tf, 'share_of_step': wg_time * 1e3 / ms_per_step}
@@ -452,7 +478,8 @@ def main():
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
             'scaling': 'strong' if strong else 'weak', 'vs_baseline': None,
             'dtype': args.precision + ' storage / fp32 accumulate', 'data': 'synthetic', 'config': config,
-            'roofline': roofline, 'cpu_baseline': cpu_base, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
+            'host_enqueue_ms_per_step': round(host_ms_per_step, 3), 'roofline': roofline, 'cpu_baseline': cpu_base, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
+            'kernel_ms_note': ('per training step' if not graphed else 'per single un-graphed forward (ESE: one member)'),
             'kernel_ms_per_step': {k: round(v, 3) for k, v in sorted(shares.items(), key=lambda kv: -kv[1])}}
     print(json.dumps(line))
     if world > 1:

@@ -172,12 +172,12 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, 
 // cycles), so the descriptors are advanced inside the block with two uniform adds per MMA instead of being rebuilt
 // and moved to uniform registers by the compiler for every instruction (measured: ~16 -> ~5 instructions per MMA).
 //   d0 / d1  : TMEM addresses of the accumulator parts        a_lo / b0_lo / b1_lo : low words of the descriptors
-//   desc_hi  : common high word of all three descriptors       acc : 0 = the very first MMA overwrites the accumulator
+//   a_hi / desc_hi : high words of the A / the B descriptors       acc : 0 = the very first MMA overwrites the accumulator
 //   idesc / idesc1 : instruction descriptors of the two N parts
 //   kstep    : descriptor-low-word advance per 16-deep k-step (2 for K-major SWIZZLE_128B, 128 for MN-major)
 #define MMLF_MMA_STEP(OFF, PRED, P2)                                            \
   "add.u32 t, %2, " OFF ";\n\t"                                                  \
-  "mov.b64 da, {t, %5};\n\t"                                                     \
+  "mov.b64 da, {t, %9};\n\t"                                                     \
   "add.u32 t, %3, " OFF ";\n\t"                                                  \
   "mov.b64 db, {t, %5};\n\t"                                                     \
   "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %6, " PRED ";\n\t" P2
@@ -189,11 +189,11 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, 
   asm volatile("{\n\t.reg .pred p, pt;\n\t.reg .b32 t;\n\t.reg .b64 da, db;\n\t" \
                "setp.ne.b32 p, %7, 0;\n\t"                                       \
                "setp.eq.b32 pt, %7, %7;\n\t" BODY "}"                            \
-               ::"r"(d0), "r"(d1), "r"(a_lo), "r"(b0_lo), "r"(b1_lo), "r"(desc_hi), "r"(idesc), "r"(acc), "r"(idesc1) \
+               ::"r"(d0), "r"(d1), "r"(a_lo), "r"(b0_lo), "r"(b1_lo), "r"(desc_hi), "r"(idesc), "r"(acc), "r"(idesc1), "r"(a_hi) \
                : "memory")
 template <int kParts, int kStepLo>
 __device__ __forceinline__ void umma_f16_pair_entry(uint32_t d0, uint32_t d1, uint32_t a_lo, uint32_t b0_lo,
-                                                    uint32_t b1_lo, uint32_t desc_hi, uint32_t idesc, uint32_t idesc1,
+                                                    uint32_t b1_lo, uint32_t a_hi, uint32_t desc_hi, uint32_t idesc, uint32_t idesc1,
                                                     uint32_t acc, int ksteps) {
   static_assert(kStepLo == 2 || kStepLo == 128, "descriptor advance per k-step");
   if constexpr (kParts == 2 && kStepLo == 2) {

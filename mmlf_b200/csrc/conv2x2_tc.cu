@@ -26,7 +26,9 @@
 namespace mmlf {
 
 constexpr int kTileM = 128;
-constexpr int kABytes = kTileM * 128;  // one A stage: 128 rows x 64 16-bit channels
+constexpr int kABoxRows = kTileM + 8;   // one activation box serves both dx taps of a dy: rows [r, r + 128] (+7 to keep
+                                        // the 8-row swizzle atoms whole)
+constexpr int kABytes = kABoxRows * 128;  // one A stage: 136 rows x 64 16-bit channels
 constexpr int kEpiWarps = 8;           // two per TMEM lane quadrant
 constexpr int kConvThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 8;
@@ -317,8 +319,8 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (tiles_addr - raw_addr);
-  const uint32_t b_bytes = static_cast<uint32_t>(p.n_pad) * 64u;          // half of the weight rows per CTA
-  const uint32_t stage_bytes = kABytes + b_bytes;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.n_pad) * 64u;          // half of the weight rows of one tap per CTA
+  const uint32_t stage_bytes = kABytes + 2u * b_bytes;                    // one (dy, 64-channel chunk): A box + both dx taps
 
   uint8_t* aux = smem + p.aux_off;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
@@ -400,10 +402,11 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const uint32_t tx_bytes = 2 * stage_bytes;
     for (int tile = pair; tile < p.num_tiles; tile += n_pairs) {
       const int row0 = tile * (2 * kTileM) + static_cast<int>(rank) * kTileM;
-      int kcol = 0;
 #pragma unroll 1
-      for (int tap = 0; tap < 4; ++tap) {
-        const int arow = row0 + p.tap_off[tap];
+      for (int dy = 0; dy < 2; ++dy) {
+        // taps (2 dy, 2 dy + 1) read rows r and r + 1: one box of 136 rows feeds both
+        const int arow = row0 + p.tap_off[2 * dy];
+        int kcol = 2 * dy * p.n_kc * 64;
 #pragma unroll 1
         for (int kc = 0; kc < p.n_kc; ++kc, kcol += 64) {
           long long tw = 0;
@@ -416,8 +419,13 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           if (elect_one()) {
             if (leader) mbar_arrive_expect_tx(fb, tx_bytes);
             tma_load_2d_pair(a_dst, &tmap_a, fb, kc * 64, arow, kEvictNormal);
-            tma_load_2d_pair(b_dst, &tmap_b, fb, kcol, b_row0, kEvictLast);
-            if (p.n_parts == 2) tma_load_2d_pair(b_dst + half_rows * 128, &tmap_b, fb, kcol, p.n_part + b_row0, kEvictLast);
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+              const int kc_col = kcol + dx * p.n_kc * 64;
+              tma_load_2d_pair(b_dst + dx * b_bytes, &tmap_b, fb, kc_col, b_row0, kEvictLast);
+              if (p.n_parts == 2)
+                tma_load_2d_pair(b_dst + dx * b_bytes + half_rows * 128, &tmap_b, fb, kc_col, p.n_part + b_row0, kEvictLast);
+            }
           }
           __syncwarp();
           if (++stage == static_cast<uint32_t>(p.stages)) {
@@ -444,6 +452,10 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       // descriptor template (address field 0): low word = LBO field, high word = SBO 1024 | version 1 | SWIZZLE_128B
       const uint64_t desc0 = make_sw128_desc(0, 0, 1024);
       const uint32_t desc_lo0 = static_cast<uint32_t>(desc0), desc_hi = static_cast<uint32_t>(desc0 >> 32);
+      // The dx = 1 operand starts one row (128 B) into an 8-row swizzle atom.  The hardware swizzles on absolute
+      // shared-memory address bits, exactly as TMA wrote the box, so the descriptor needs no base-offset field
+      // (measured on B200: base offset 1 gives wrong results, 0 is bit-exact against the oracle).
+      const uint32_t desc_hi_dx1 = desc_hi;
       const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
       uint32_t stage = 0, phase = 0;
       int it = 0;
@@ -460,7 +472,7 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         const uint32_t acc_base = tmem_base + (par ? base1 : 0);
         uint32_t accumulate = 0;
 #pragma unroll 1
-        for (int tap = 0; tap < 4; ++tap) {
+        for (int dy = 0; dy < 2; ++dy) {
 #pragma unroll 1
           for (int kc = 0; kc < p.n_kc; ++kc) {
             if (prof) tw = clock64();
@@ -471,13 +483,20 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             const int ksteps = (kc == p.n_kc - 1) ? p.last_ksteps : 4;
             const uint32_t a_lo = desc_lo0 + ((a_addr & 0x3FFFFu) >> 4);
             const uint32_t b_lo = desc_lo0 + (((a_addr + kABytes) & 0x3FFFFu) >> 4);
-            const bool last = (tap == 3 && kc == p.n_kc - 1);
+            const bool last = (dy == 1 && kc == p.n_kc - 1);
             if (elect_one()) {
-              if (p.n_parts == 2)
-                umma_f16_pair_entry<2, 2>(acc_base, acc_base + p.n_part, a_lo, b_lo, b_lo + (part_bytes >> 4), desc_hi, idesc,
-                                          idesc, accumulate, ksteps);
-              else
-                umma_f16_pair_entry<1, 2>(acc_base, acc_base, a_lo, b_lo, b_lo, desc_hi, idesc, idesc, accumulate, ksteps);
+              // dx = 0: rows [0, 128) of the box; dx = 1: rows [1, 129) = start address + 128 B (+8 in the descriptor)
+              if (p.n_parts == 2) {
+                umma_f16_pair_entry<2, 2>(acc_base, acc_base + p.n_part, a_lo, b_lo, b_lo + (part_bytes >> 4), desc_hi, desc_hi,
+                                          idesc, idesc, accumulate, ksteps);
+                umma_f16_pair_entry<2, 2>(acc_base, acc_base + p.n_part, a_lo + 8, b_lo + (b_bytes >> 4),
+                                          b_lo + ((b_bytes + part_bytes) >> 4), desc_hi_dx1, desc_hi, idesc, idesc, 1u, ksteps);
+              } else {
+                umma_f16_pair_entry<1, 2>(acc_base, acc_base, a_lo, b_lo, b_lo, desc_hi, desc_hi, idesc, idesc, accumulate,
+                                          ksteps);
+                umma_f16_pair_entry<1, 2>(acc_base, acc_base, a_lo + 8, b_lo + (b_bytes >> 4), b_lo, desc_hi_dx1, desc_hi,
+                                          idesc, idesc, 1u, ksteps);
+              }
               umma_commit_pair(empty0 + stage * 8);
               if (last) umma_commit_pair(smem_u32(&tmem_full_bar[par]));
             }
@@ -763,7 +782,7 @@ extern "C" int mmlf_conv2x2(const mmlf_conv_args* a, void* stream) {
   ConvParams p;
   if (int rc = fill_params(a, p)) return rc;
   p.stats = g_conv_stats;
-  const uint32_t stage_bytes = kABytes + p.n_pad * 64;
+  const uint32_t stage_bytes = kABytes + 2u * p.n_pad * 64u;
   // shared-memory plan behind the operand stages: [epilogue staging | statistics | barriers + constants]
   const uint32_t epi_bytes = p.out_mode == 0 ? kEpiWarps * (p.dual ? 2u : 1u) * kSegBytes : 0u;
   const uint32_t stat_bytes = p.col_sums ? 4u * 2u * p.n_pad * 4u : 0u;
@@ -774,13 +793,13 @@ extern "C" int mmlf_conv2x2(const mmlf_conv_args* a, void* stream) {
   if (stages > kMaxStages) stages = kMaxStages;
   MMLF_REQUIRE(stages >= 2, "conv2x2: not enough shared memory for a 2-stage pipeline (n_pad %d)", p.n_pad);
   p.stages = stages;
-  p.epi_off = stages * stage_bytes;                       // multiple of 1024 (stage_bytes = 16384 + n_pad * 64)
+  p.epi_off = stages * stage_bytes;                       // multiple of 1024 (stage_bytes = 17408 + n_pad * 128)
   p.stat_off = stat_bytes ? p.epi_off + epi_bytes : 0;
   p.aux_off = p.epi_off + epi_bytes + ((stat_bytes + 15u) & ~15u);
   const uint32_t smem_bytes = 1024 + p.aux_off + aux_bytes;
 
   CUtensorMap tmap_a, tmap_b;
-  if (int rc = make_tmap_2d_16(&tmap_a, a->in, a->cin_pad, p.n_slots, static_cast<uint64_t>(a->ld_in) * 2, 64, kTileM, 128))
+  if (int rc = make_tmap_2d_16(&tmap_a, a->in, a->cin_pad, p.n_slots, static_cast<uint64_t>(a->ld_in) * 2, 64, kABoxRows, 128))
     return rc;
   const uint64_t k_total = static_cast<uint64_t>(4) * p.n_kc * 64;
   if (int rc = make_tmap_2d_16(&tmap_b, a->wpack, k_total, p.n_pad, k_total * 2, 64, p.n_part / 2, 128)) return rc;

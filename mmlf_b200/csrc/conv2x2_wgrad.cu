@@ -282,10 +282,10 @@ conv2x2_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
         if (elect_one()) {
           if (p.n_parts > 1)
             umma_f16_pair_entry<2, 128>(tmem_base + p.part_col[0], tmem_base + p.part_col[1], a_lo, b0_lo, b1_lo, desc_hi,
-                                        idesc0, idesc1, accumulate, 4);
+                                        desc_hi, idesc0, idesc1, accumulate, 4);
           else
-            umma_f16_pair_entry<1, 128>(tmem_base + p.part_col[0], tmem_base, a_lo, b0_lo, b0_lo, desc_hi, idesc0, idesc0,
-                                        accumulate, 4);
+            umma_f16_pair_entry<1, 128>(tmem_base + p.part_col[0], tmem_base, a_lo, b0_lo, b0_lo, desc_hi, desc_hi, idesc0,
+                                        idesc0, accumulate, 4);
           umma_commit_pair(smem_u32(&empty_bar[stage]));
           if (ch == n_chunks - 1) umma_commit_pair(smem_u32(done_bar));
         }

@@ -44,9 +44,15 @@ class Ensamble(nn.Module):
         rank, world = parallel.shard_info()
         was_training = net.training
         net.eval()
+        mine = list(range(rank, K, world))
         with torch.no_grad():
-            for k in range(rank, K, world):
-                out = net.raw_forward(feed, shift_disp=shifts[k])
+            if hasattr(net, '_can_graph') and net._can_graph(feed):
+                # all members of this rank replayed from one CUDA graph (the launches are otherwise host-bound)
+                outs = net.graphed_eval(feed, tuple(shifts[k] for k in mine))
+            else:
+                outs = None
+            for j, k in enumerate(mine):
+                out = outs[j] if outs is not None else net.raw_forward(feed, shift_disp=shifts[k])
                 means[k] = out[:, 0] + shifts[k]                         # ensamble.py:74
                 logvars[k] = out[:, 1]
         net.train(was_training)
