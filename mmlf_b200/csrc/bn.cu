@@ -38,6 +38,7 @@ __device__ __forceinline__ bool slot_valid(int64_t s, int Hp, int Wp) {
 // MODE 2: g = dy * (z * scale + shift > 0), xhat = (z - mean) * invstd: sum g, sum g * xhat (bn_bwd_reduce); the ReLU
 //         mask is recomputed from z exactly as the forward pass computed y = relu(fma(z, scale, shift))
 constexpr int kRedThreads = 256;
+constexpr int kUnroll = 4;
 
 template <int MODE>
 __global__ void __launch_bounds__(kRedThreads)
@@ -60,23 +61,40 @@ col_reduce_kernel(const void* __restrict__ x, int ld_x, const float* __restrict_
     }
   }
   if (sl < lanes) {
-    for (int64_t s = static_cast<int64_t>(blockIdx.x) * lanes + sl; s < n_slots; s += static_cast<int64_t>(gridDim.x) * lanes) {
-      float v[8];
-      unpack8(ld8(x, s, ld_x, g * 8), v, dt_x);
-      if (MODE == 0) {
+    // kUnroll slots per iteration with all loads issued first: one slot's two 16-byte loads per thread in flight kept
+    // the kernel at 58 % of the HBM rate (latency bound)
+    const int64_t step = static_cast<int64_t>(gridDim.x) * lanes;
+    for (int64_t s = static_cast<int64_t>(blockIdx.x) * lanes + sl; s < n_slots; s += kUnroll * step) {
+      uint4 xv[kUnroll], zv[kUnroll];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { a0[j] += v[j]; a1[j] = fmaf(v[j], v[j], a1[j]); }
-      } else if (MODE == 1) {
+      for (int u = 0; u < kUnroll; ++u) {
+        const int64_t su = s + u * step;
+        xv[u] = make_uint4(0u, 0u, 0u, 0u);      // zero bit patterns contribute nothing to any of the sums
+        zv[u] = xv[u];
+        if (su < n_slots) {
+          xv[u] = ld8(x, su, ld_x, g * 8);
+          if (MODE == 2) zv[u] = ld8(z, su, ld_z, g * 8);
+        }
+      }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a0[j] += v[j];
-      } else {
-        float zz[8];
-        unpack8(ld8(z, s, ld_z, g * 8), zz, dt_yz);
+      for (int u = 0; u < kUnroll; ++u) {
+        float v[8];
+        unpack8(xv[u], v, dt_x);
+        if (MODE == 0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float gg = fmaf(zz[j], sc[j], sh[j]) > 0.f ? v[j] : 0.f;
-          a0[j] += gg;
-          a1[j] = fmaf(gg, (zz[j] - mu[j]) * is[j], a1[j]);
+          for (int j = 0; j < 8; ++j) { a0[j] += v[j]; a1[j] = fmaf(v[j], v[j], a1[j]); }
+        } else if (MODE == 1) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a0[j] += v[j];
+        } else {
+          float zz[8];
+          unpack8(zv[u], zz, dt_yz);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float gg = fmaf(zz[j], sc[j], sh[j]) > 0.f ? v[j] : 0.f;
+            a0[j] += gg;
+            a1[j] = fmaf(gg, (zz[j] - mu[j]) * is[j], a1[j]);
+          }
         }
       }
     }
@@ -225,48 +243,60 @@ slot_map_kernel(const void* __restrict__ a, int ld_a, const void* __restrict__ y
 #pragma unroll
     for (int j = 0; j < 8; ++j) k0[j] = p0[c + j] * p2[c + j];
   }
-  for (int64_t s = static_cast<int64_t>(blockIdx.x) * lanes + sl; active && s < n_slots;
-       s += static_cast<int64_t>(gridDim.x) * lanes) {
-    float r[8];
-    if ((MODE == 0 || MODE == 2) && !slot_valid_fast(s, dv)) {
+  const int64_t step = static_cast<int64_t>(gridDim.x) * lanes;
+  for (int64_t s = static_cast<int64_t>(blockIdx.x) * lanes + sl; active && s < n_slots; s += kUnroll * step) {
+    // kUnroll slots per iteration, all loads first (halo slots are loaded too and zeroed afterwards: no divergence)
+    uint4 va[kUnroll], vb[kUnroll];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] = 0.f;
-      st8(out, s, ld_out, c, pack8(r, dt_a));
-      if (MODE == 0 && out2) st8(out2, s, ld_out2, c, pack8(r, dt_out2));
-      continue;
-    }
-    float av[8];
-    if (MODE == 4) {
-      unpack8(ld8(a, s, ld_a, c), av, dt_yz);
-      st8(out, s, ld_out, c, pack8(av, dt_a));
-      continue;
-    }
-    unpack8(ld8(a, s, ld_a, c), av, dt_a);
-    if (MODE == 0) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] = fmaxf(fmaf(av[j], k0[j], k1[j]), 0.f);
-      if (out2) st8(out2, s, ld_out2, c, pack8(r, dt_out2));
-    } else if (MODE == 1) {
-      float yv[8];
-      unpack8(ld8(y, s, ld_y, c), yv, dt_yz);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] = yv[j] > 0.f ? av[j] : 0.f;
-    } else {
-      float zv[8];
-      unpack8(ld8(z, s, ld_z, c), zv, dt_yz);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float gg = fmaf(zv[j], msc[j], msh[j]) > 0.f ? av[j] : 0.f;
-        r[j] = MODE == 3 ? gg * k0[j] : fmaf(k0[j], gg, -fmaf(k1[j], zv[j], k2[j]));
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t su = s + u * step;
+      va[u] = make_uint4(0u, 0u, 0u, 0u);
+      vb[u] = va[u];
+      if (su < n_slots) {
+        va[u] = ld8(a, su, ld_a, c);
+        if (MODE == 1) vb[u] = ld8(y, su, ld_y, c);
+        if (MODE == 2 || MODE == 3) vb[u] = ld8(z, su, ld_z, c);
       }
     }
-    const uint4 pk = pack8(r, dt_a);
-    st8(out, s, ld_out, c, pk);
-    if ((MODE == 2 || MODE == 3) && csum) {
-      float rr[8];
-      unpack8(pk, rr, dt_a);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) cs[j] += rr[j];
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t su = s + u * step;
+      if (su >= n_slots) break;
+      float r[8], av[8];
+      if (MODE == 4) {
+        unpack8(va[u], av, dt_yz);
+        st8(out, su, ld_out, c, pack8(av, dt_a));
+        continue;
+      }
+      const bool halo = (MODE == 0 || MODE == 2) && !slot_valid_fast(su, dv);
+      unpack8(va[u], av, dt_a);
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = halo ? 0.f : fmaxf(fmaf(av[j], k0[j], k1[j]), 0.f);
+        if (out2) st8(out2, su, ld_out2, c, pack8(r, dt_out2));
+      } else if (MODE == 1) {
+        float yv[8];
+        unpack8(vb[u], yv, dt_yz);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = yv[j] > 0.f ? av[j] : 0.f;
+      } else {
+        float zv[8];
+        unpack8(vb[u], zv, dt_yz);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float gg = fmaf(zv[j], msc[j], msh[j]) > 0.f ? av[j] : 0.f;
+          const float d = MODE == 3 ? gg * k0[j] : fmaf(k0[j], gg, -fmaf(k1[j], zv[j], k2[j]));
+          r[j] = halo ? 0.f : d;
+        }
+      }
+      const uint4 pk = pack8(r, dt_a);
+      st8(out, su, ld_out, c, pk);
+      if ((MODE == 2 || MODE == 3) && csum) {
+        float rr[8];
+        unpack8(pk, rr, dt_a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cs[j] += rr[j];
+      }
     }
   }
   if ((MODE == 2 || MODE == 3) && csum) {

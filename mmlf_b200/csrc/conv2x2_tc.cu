@@ -55,8 +55,14 @@ struct ConvParams {
   double* col_sums;
   void* out;
   void* out2;
-  long long* stats;                             // optional per-CTA cycle counters (debug): [grid][8]
+  long long* stats;                             // optional per-CTA cycle counters (debug): [grid][16]
 };
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ void slot_coords(const ConvParams& p, int64_t s, int& b, int& sy, int& sx) {
   const int per_img = p.Hp * p.Wp;
@@ -316,6 +322,7 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                    const ConvParams p) {
   using FL = Flags<F>;
   extern __shared__ uint8_t smem_raw[];
+  if (p.stats && threadIdx.x == 0) p.stats[blockIdx.x * 16 + 8] = static_cast<long long>(global_ns());   // kernel entry
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (tiles_addr - raw_addr);
@@ -396,7 +403,10 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     uint32_t stage = 0, phase = 0;
     long long t_wait = 0, t_begin = prof ? clock64() : 0;
     unsigned long long ns_begin = 0;
-    if (prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_begin));
+    if (prof) {
+      ns_begin = global_ns();
+      if (lane == 0) p.stats[blockIdx.x * 16 + 9] = static_cast<long long>(ns_begin);          // main loop entry
+    }
     const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
     const int b_row0 = static_cast<int>(rank) * half_rows;
     const uint32_t tx_bytes = 2 * stage_bytes;
@@ -436,11 +446,10 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       }
     }
     if (prof && lane == 0) {
-      p.stats[blockIdx.x * 8 + 0] = clock64() - t_begin;   // producer total
-      p.stats[blockIdx.x * 8 + 1] = t_wait;                // producer waiting for free stages
-      unsigned long long ns_end;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_end));
-      p.stats[blockIdx.x * 8 + 7] = static_cast<long long>(ns_end - ns_begin);   // producer total in ns (-> SM clock)
+      p.stats[blockIdx.x * 16 + 0] = clock64() - t_begin;   // producer total
+      p.stats[blockIdx.x * 16 + 1] = t_wait;                // producer waiting for free stages
+      const unsigned long long ns_end = global_ns();
+      p.stats[blockIdx.x * 16 + 7] = static_cast<long long>(ns_end - ns_begin);   // producer total in ns (-> SM clock)
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA; warp-uniform loop,
@@ -510,9 +519,9 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
       }
       if (prof && lane == 0) {
-        p.stats[blockIdx.x * 8 + 2] = clock64() - t_begin;   // MMA issuer total
-        p.stats[blockIdx.x * 8 + 3] = t_full;                // ... waiting for TMA data
-        p.stats[blockIdx.x * 8 + 4] = t_tmem;                // ... waiting for the epilogue to free TMEM
+        p.stats[blockIdx.x * 16 + 2] = clock64() - t_begin;   // MMA issuer total
+        p.stats[blockIdx.x * 16 + 3] = t_full;                // ... waiting for TMA data
+        p.stats[blockIdx.x * 16 + 4] = t_tmem;                // ... waiting for the epilogue to free TMEM
       }
     }
   } else {
@@ -602,11 +611,12 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       }
     }
     if (p.stats && warp == 2 && lane == 0) {
-      p.stats[blockIdx.x * 8 + 5] = clock64() - t_begin;     // epilogue total
-      p.stats[blockIdx.x * 8 + 6] = t_wait;                  // ... waiting for accumulators
+      p.stats[blockIdx.x * 16 + 5] = clock64() - t_begin;     // epilogue total
+      p.stats[blockIdx.x * 16 + 6] = t_wait;                  // ... waiting for accumulators
     }
   }
 
+  if (p.stats && warp == 2 && lane == 0) p.stats[blockIdx.x * 16 + 10] = static_cast<long long>(global_ns());   // epilogue done
   tc_fence_before();
   __syncthreads();
   if (p.stat_off && p.col_sums) {
@@ -622,6 +632,7 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     tc_fence_after();
     tmem_dealloc_pair(tmem_base, kTmemCols);
   }
+  if (p.stats && threadIdx.x == 0) p.stats[blockIdx.x * 16 + 11] = static_cast<long long>(global_ns());          // kernel exit
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -752,7 +763,7 @@ static int fill_params(const mmlf_conv_args* a, ConvParams& p) {
 using namespace mmlf;
 
 static long long* g_conv_stats = nullptr;
-// debug hook (not part of the public header): per-CTA cycle counters of the next conv launches, [grid][8] int64
+// debug hook (not part of the public header): per-CTA cycle counters of the next conv launches, [grid][16] int64
 extern "C" void mmlf_debug_conv_stats(long long* device_buf) { g_conv_stats = device_buf; }
 
 typedef void (*ConvKernel)(CUtensorMap, CUtensorMap, ConvParams);

@@ -2,6 +2,7 @@
 // conversions into the bf16 slot layout.  Bandwidth-bound; bit-exact with the reference
 // (/root/reference/mmlf/data/hci4d.py:142-193, 907-990).
 #include <math.h>
+#include <stdlib.h>
 
 #include "../../include/mmlf_b200.h"
 #include "common.cuh"
@@ -92,56 +93,106 @@ __device__ __forceinline__ float lerp2(float a, float w0, float b, float w1) {
   return __fadd_rn(__fmul_rn(a, w0), __fmul_rn(b, w1));
 }
 
-// One CTA = one output row of one (stack, batch, view, colour) plane.  The one or two source rows are staged in
-// shared memory with aligned 128-bit loads; the shifted (unaligned, wrapping) taps are then read from there.
-__global__ void __launch_bounds__(128) lf_shift_kernel(const ShiftParams p) {
-  extern __shared__ float rows[];               // [2][W]
-  const int y = blockIdx.x;
-  int pl = blockIdx.y;                          // plane index over (stack, batch, view, colour)
+// One CTA = a band of `rows_per_cta` output rows of one (stack, batch, view, colour) plane, full width.  The source
+// rows the band needs -- a circularly contiguous run of rows_per_cta (+1 when the stack is resampled along H: the two
+// taps are neighbouring rows) -- are staged in shared memory with 128-bit loads, 4 in flight per thread; the shifted,
+// wrapping taps are read from there and the band is written with 128-bit stores.  Bands are sized to move >= 64 KB
+// per CTA: the first version (one CTA per output row) moved 0.4 - 2 KB per CTA and reached 16 % (96-px patches) /
+// 48 % (512-px light fields) of the HBM rate.
+constexpr int kShiftThreads = 256;
+
+__global__ void __launch_bounds__(kShiftThreads) lf_shift_kernel(const ShiftParams p, int rows_per_cta, int bands) {
+  extern __shared__ __align__(16) float rows[];   // [rows_per_cta + 1][W]
+  const int band = blockIdx.x % bands;
+  int pl = blockIdx.x / bands;                  // plane index over (stack, batch, view, colour)
   const int planes_per_stack = p.batch * p.n * 3;
   const int stack = pl / planes_per_stack;
   pl -= stack * planes_per_stack;
   const int view = (pl / 3) % p.n;
   const int64_t plane_off = static_cast<int64_t>(pl) * p.H * p.W;
-  const float* src = p.src[stack] + plane_off;
-  float* dst = p.dst[stack] + plane_off;
+  const float* __restrict__ src = p.src[stack] + plane_off;
+  float* __restrict__ dst = p.dst[stack] + plane_off;
   const float w0 = p.taps.w0[view], w1 = p.taps.w1[view];
   const int s0 = p.taps.s0[view], s1 = p.taps.s1[view];
   const bool has_w = stack != 1;                // h, i, d are resampled along W
   const bool has_v = stack != 0;                // v, i, d along H; the i stack with the opposite sign
   const int vsign = stack == 2 ? -1 : +1;
-  const int r0 = has_v ? src_index(y, s0, p.H, vsign) : y;
-  const int r1 = has_v ? src_index(y, s1, p.H, vsign) : y;
-  const int W = p.W;
-  if ((W & 3) == 0) {
-    for (int x = threadIdx.x * 4; x < W; x += blockDim.x * 4) {
-      *reinterpret_cast<float4*>(rows + x) = __ldg(reinterpret_cast<const float4*>(src + static_cast<int64_t>(r0) * W + x));
-      if (has_v)
-        *reinterpret_cast<float4*>(rows + W + x) = __ldg(reinterpret_cast<const float4*>(src + static_cast<int64_t>(r1) * W + x));
+  const int W = p.W, H = p.H;
+  const int y0 = band * rows_per_cta;
+  const int ny = min(rows_per_cta, H - y0);
+  // staged source rows: row (base + k) mod H at rows[k], k in [0, nstage).  The taps of output row y are the rows
+  // src_index(y, s0) and src_index(y, s1); s1 = s0 +- 1, so over a band they cover one circular run.
+  int base = y0, nstage = ny, k0_off = 0, k1_off = 0;
+  if (has_v) {
+    const int a0 = src_index(y0, s0, H, vsign), a1 = src_index(y0, s1, H, vsign);
+    // circular order of the two taps: the one that comes first is the base
+    const int d01 = ((a1 - a0) % H + H) % H;      // distance from tap 0 to tap 1 going up
+    if (d01 <= 1) {
+      base = a0; k0_off = 0; k1_off = d01;
+    } else {                                        // tap 1 is one row below tap 0 (d01 == H - 1), or |s| >= H quirks
+      base = a1; k1_off = 0; k0_off = ((a0 - a1) % H + H) % H;
     }
-  } else {
-    for (int x = threadIdx.x; x < W; x += blockDim.x) {
-      rows[x] = __ldg(src + static_cast<int64_t>(r0) * W + x);
-      if (has_v) rows[W + x] = __ldg(src + static_cast<int64_t>(r1) * W + x);
+    nstage = ny + max(k0_off, k1_off);
+    if (k0_off > 1 || k1_off > 1 || nstage > rows_per_cta + 1) {   // taps further apart than one row (tiny H): generic path
+      nstage = -1;
+    }
+  }
+  if (nstage > 0) {
+    if ((W & 3) == 0) {
+      const int w4 = W >> 2, total = nstage * w4;
+#pragma unroll 4
+      for (int i = threadIdx.x; i < total; i += kShiftThreads) {
+        const int k = i / w4, x4 = i - k * w4;
+        int r = base + k;
+        if (r >= H) r -= H;
+        reinterpret_cast<float4*>(rows)[i] = __ldg(reinterpret_cast<const float4*>(src + static_cast<int64_t>(r) * W) + x4);
+      }
+    } else {
+      const int total = nstage * W;
+      for (int i = threadIdx.x; i < total; i += kShiftThreads) {
+        const int k = i / W, x = i - k * W;
+        int r = base + k;
+        if (r >= H) r -= H;
+        rows[i] = __ldg(src + static_cast<int64_t>(r) * W + x);
+      }
     }
   }
   __syncthreads();
-  for (int x0 = threadIdx.x * 4; x0 < W; x0 += blockDim.x * 4) {
+  const int wq = (W + 3) >> 2;
+  for (int i = threadIdx.x; i < ny * wq; i += kShiftThreads) {
+    const int ky = i / wq, x0 = (i - ky * wq) * 4;
+    const int y = y0 + ky;
     float o[4];
+    if (nstage > 0) {
+      const float* ra = rows + (has_v ? ky + k0_off : ky) * W;
+      const float* rb = rows + (has_v ? ky + k1_off : ky) * W;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int x = x0 + j;
-      if (x >= W) break;
-      float t0, t1 = 0.f;
-      if (has_w) {
-        const int c0 = src_index(x, s0, W, +1), c1 = src_index(x, s1, W, +1);
-        t0 = lerp2(rows[c0], w0, rows[c1], w1);
-        if (has_v) t1 = lerp2(rows[W + c0], w0, rows[W + c1], w1);
-      } else {
-        t0 = rows[x];
-        t1 = rows[W + x];
+      for (int j = 0; j < 4; ++j) {
+        const int x = x0 + j;
+        if (x >= W) break;
+        float t0, t1 = 0.f;
+        if (has_w) {
+          const int c0 = src_index(x, s0, W, +1), c1 = src_index(x, s1, W, +1);
+          t0 = lerp2(ra[c0], w0, ra[c1], w1);
+          if (has_v) t1 = lerp2(rb[c0], w0, rb[c1], w1);
+        } else {
+          t0 = ra[x];
+          t1 = rb[x];
+        }
+        o[j] = has_v ? lerp2(t0, w0, t1, w1) : t0;
       }
-      o[j] = has_v ? lerp2(t0, w0, t1, w1) : t0;
+    } else {                                        // generic path straight from global memory
+      const float* ra = src + static_cast<int64_t>(src_index(y, s0, H, vsign)) * W;
+      const float* rb = src + static_cast<int64_t>(src_index(y, s1, H, vsign)) * W;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int x = x0 + j;
+        if (x >= W) break;
+        const int c0 = has_w ? src_index(x, s0, W, +1) : x, c1 = has_w ? src_index(x, s1, W, +1) : x;
+        const float t0 = has_w ? lerp2(__ldg(ra + c0), w0, __ldg(ra + c1), w1) : __ldg(ra + x);
+        const float t1 = has_w ? lerp2(__ldg(rb + c0), w0, __ldg(rb + c1), w1) : __ldg(rb + x);
+        o[j] = lerp2(t0, w0, t1, w1);
+      }
     }
     float* d = dst + static_cast<int64_t>(y) * W + x0;
     if ((W & 3) == 0) {
@@ -149,6 +200,113 @@ __global__ void __launch_bounds__(128) lf_shift_kernel(const ShiftParams p) {
     } else {
       for (int j = 0; j < 4 && x0 + j < W; ++j) d[j] = o[j];
     }
+  }
+}
+
+// Register-only variant for W % 4 == 0 (every real light field): one thread = 4 consecutive pixels x R consecutive rows
+// of one plane.  The two W taps of the four pixels are 5 circularly consecutive source pixels
+// (s1 = s0 +- 1), i.e. they lie inside two aligned float4 of the source row, so every load is an aligned, coalesced
+// 128-bit load, the lane/row overlaps are served by L1/L2 and HBM sees each byte once.  No shared memory, no barriers.
+
+__device__ __forceinline__ int eff_shift(int s, int n) { return (s == 0 || s >= n || -s >= n) ? 0 : s; }
+__device__ __forceinline__ int wrap(int r, int n) {          // r in (-n, 2n)
+  if (r < 0) r += n;
+  if (r >= n) r -= n;
+  return r;
+}
+
+// the 8 floats [a, a + 8) of a source row (a % 4 == 0, taken modulo W; W % 4 == 0 keeps each float4 on one side of the wrap)
+__device__ __forceinline__ void load8(const float* __restrict__ row, int a, int W, float (&f)[8]) {
+  const float4 lo = __ldg(reinterpret_cast<const float4*>(row + a));
+  int b = a + 4;
+  if (b >= W) b -= W;
+  const float4 hi = __ldg(reinterpret_cast<const float4*>(row + b));
+  f[0] = lo.x; f[1] = lo.y; f[2] = lo.z; f[3] = lo.w;
+  f[4] = hi.x; f[5] = hi.y; f[6] = hi.z; f[7] = hi.w;
+}
+
+// W lerp of 4 pixels from the 8-float window: taps at window offsets o + d0 + j and o + d1 + j
+__device__ __forceinline__ void wlerp4(const float (&f)[8], int o, int d0, int d1, float w0, float w1, float (&t)[4]) {
+  float g[5];
+  switch (o) {                                    // o is uniform per plane
+    case 0: g[0] = f[0]; g[1] = f[1]; g[2] = f[2]; g[3] = f[3]; g[4] = f[4]; break;
+    case 1: g[0] = f[1]; g[1] = f[2]; g[2] = f[3]; g[3] = f[4]; g[4] = f[5]; break;
+    case 2: g[0] = f[2]; g[1] = f[3]; g[2] = f[4]; g[3] = f[5]; g[4] = f[6]; break;
+    default: g[0] = f[3]; g[1] = f[4]; g[2] = f[5]; g[3] = f[6]; g[4] = f[7]; break;
+  }
+  if (d0 == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t[j] = lerp2(g[j], w0, g[j + d1], w1);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t[j] = lerp2(g[j + 1], w0, g[j], w1);
+  }
+}
+
+template <int R>
+__global__ void __launch_bounds__(256) lf_shift_vec_kernel(const ShiftParams p, int64_t total) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int W = p.W, H = p.H, w4 = W >> 2;
+  const int nyb = (H + R - 1) / R;
+  const int x0 = static_cast<int>(i % w4) * 4;
+  const int64_t q = i / w4;
+  const int yb = static_cast<int>(q % nyb);
+  int pl = static_cast<int>(q / nyb);
+  const int planes_per_stack = p.batch * p.n * 3;
+  const int stack = pl / planes_per_stack;
+  pl -= stack * planes_per_stack;
+  const int view = (pl / 3) % p.n;
+  const int64_t plane_off = static_cast<int64_t>(pl) * H * W;
+  const float* __restrict__ src = p.src[stack] + plane_off;
+  float* __restrict__ dst = p.dst[stack] + plane_off;
+  const float w0 = p.taps.w0[view], w1 = p.taps.w1[view];
+  const int s0 = p.taps.s0[view], s1 = p.taps.s1[view];
+  const bool has_w = stack != 1, has_v = stack != 0;
+  const int vsign = stack == 2 ? -1 : +1;
+  // W taps: source columns (x - e0) mod W and (x - e1) mod W; window start = the circularly smaller of the two
+  const int e0 = eff_shift(s0, W), e1 = eff_shift(s1, W);
+  int d0 = 0, d1 = 0, m = x0, o = 0, a = x0;
+  if (has_w) {
+    const int c0 = wrap(x0 - e0, W), c1 = wrap(x0 - e1, W);
+    const int up = wrap(c1 - c0, W);              // 0: same column, 1: tap 1 right of tap 0, W - 1: left of it
+    if (up <= 1) { m = c0; d0 = 0; d1 = up; } else { m = c1; d0 = 1; d1 = 0; }   // (other distances never reach here)
+    o = m & 3;
+    a = m - o;
+  }
+  const int y0 = yb * R;
+  // one output row: all of its loads are issued before the arithmetic; with the row loop fully unrolled (no early exit)
+  // the compiler interleaves the loads of all R rows
+  auto do_row = [&](int y) {
+    const int ra = has_v ? src_index(y, s0, H, vsign) : y;
+    const int rb = has_v ? src_index(y, s1, H, vsign) : y;
+    float t0[4], t1[4];
+    if (has_w) {
+      float f[8], g[8];
+      load8(src + static_cast<int64_t>(ra) * W, a, W, f);
+      if (has_v) load8(src + static_cast<int64_t>(rb) * W, a, W, g);
+      wlerp4(f, o, d0, d1, w0, w1, t0);
+      if (has_v) wlerp4(g, o, d0, d1, w0, w1, t1);
+    } else {
+      const float4 u = __ldg(reinterpret_cast<const float4*>(src + static_cast<int64_t>(ra) * W + x0));
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + static_cast<int64_t>(rb) * W + x0));
+      t0[0] = u.x; t0[1] = u.y; t0[2] = u.z; t0[3] = u.w;
+      t1[0] = v.x; t1[1] = v.y; t1[2] = v.z; t1[3] = v.w;
+    }
+    float4 out;
+    if (has_v) {
+      out = make_float4(lerp2(t0[0], w0, t1[0], w1), lerp2(t0[1], w0, t1[1], w1), lerp2(t0[2], w0, t1[2], w1),
+                        lerp2(t0[3], w0, t1[3], w1));
+    } else {
+      out = make_float4(t0[0], t0[1], t0[2], t0[3]);
+    }
+    __stcs(reinterpret_cast<float4*>(dst + static_cast<int64_t>(y) * W + x0), out);
+  };
+  if (y0 + R <= H) {
+#pragma unroll
+    for (int ky = 0; ky < R; ++ky) do_row(y0 + ky);
+  } else {
+    for (int y = y0; y < H; ++y) do_row(y);
   }
 }
 
@@ -181,43 +339,133 @@ __device__ __forceinline__ float shifted_value(const float* __restrict__ plane, 
   return lerp2(t0, w0, t1, w1);
 }
 
+constexpr int kPackTile = 128;                     // slot columns per CTA
+
 __global__ void __launch_bounds__(256) pack_views_kernel(const PackParams p) {
-  __shared__ float tile[32][33];                 // [channel][slot column], C <= 32 per pass
+  __shared__ float tile[32][kPackTile + 1];        // [channel][slot column], 32 channels per pass
   const int Wp = p.W + 1, Hp = p.H + 1;
-  const int sx0 = blockIdx.x * 32;
+  const int sx0 = blockIdx.x * kPackTile;
   const int sy = blockIdx.y % Hp, b = blockIdx.y / Hp;
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
   const int64_t slot_row = (static_cast<int64_t>(b) * Hp + sy) * Wp;
   for (int cbase = 0; cbase < p.ld; cbase += 32) {
-    // load: warp w handles channels w, w+8, ...; lanes run along x
+    // load: warp w handles channels w, w+8, ...; lanes run along x, four columns (32 apart) per lane in flight
     for (int c = wrp; c < 32; c += 8) {
       const int ch = cbase + c;
-      const int sx = sx0 + lane;
-      float v = 0.f;
-      if (ch < p.C && sy >= 1 && sx >= 1 && sx < Wp) {
-        const float* plane = p.views + (static_cast<int64_t>(b) * p.C + ch) * p.H * p.W;
-        if (p.do_shift) {
-          const int view = ch / 3;
-          v = shifted_value(plane, sy - 1, sx - 1, p.H, p.W, p.stack, p.taps.w0[view], p.taps.w1[view],
-                            p.taps.s0[view], p.taps.s1[view]);
-        } else {
-          v = __ldg(plane + static_cast<int64_t>(sy - 1) * p.W + (sx - 1));
+      const bool row_ok = ch < p.C && sy >= 1;
+      const float* plane = p.views + (static_cast<int64_t>(b) * p.C + (row_ok ? ch : 0)) * p.H * p.W;
+      float w0 = 0.f, w1 = 0.f;
+      int s0 = 0, s1 = 0;
+      if (p.do_shift && row_ok) {
+        const int view = ch / 3;
+        w0 = p.taps.w0[view]; w1 = p.taps.w1[view]; s0 = p.taps.s0[view]; s1 = p.taps.s1[view];
+      }
+      float v[kPackTile / 32];
+#pragma unroll
+      for (int j = 0; j < kPackTile / 32; ++j) {
+        const int sx = sx0 + lane + 32 * j;
+        v[j] = 0.f;
+        if (row_ok && sx >= 1 && sx < Wp) {
+          if (p.do_shift) v[j] = shifted_value(plane, sy - 1, sx - 1, p.H, p.W, p.stack, w0, w1, s0, s1);
+          else v[j] = __ldg(plane + static_cast<int64_t>(sy - 1) * p.W + (sx - 1));
         }
       }
-      tile[c][lane] = v;
+#pragma unroll
+      for (int j = 0; j < kPackTile / 32; ++j) tile[c][lane + 32 * j] = v[j];
     }
     __syncthreads();
-    // store: each thread writes 4 consecutive channels (8 bytes) of one slot; 8 threads cover 32 channels
-    const int slot = threadIdx.x >> 3, cq = (threadIdx.x & 7) * 4;
-    const int sx = sx0 + slot;
-    if (sx < Wp && cbase + cq < p.ld) {
-      uint2 o;
-      o.x = pack16x2(tile[cq][slot], tile[cq + 1][slot], p.dtype);
-      o.y = pack16x2(tile[cq + 2][slot], tile[cq + 3][slot], p.dtype);
-      *reinterpret_cast<uint2*>(p.out + (slot_row + sx) * p.ld + cbase + cq) = o;
+    // store: each thread writes 8 consecutive channels (16 bytes) of one slot; 4 threads cover 32 channels
+    const int cq = (threadIdx.x & 3) * 8;
+#pragma unroll
+    for (int pass = 0; pass < kPackTile / 64; ++pass) {
+      const int slot = (threadIdx.x >> 2) + 64 * pass;
+      const int sx = sx0 + slot;
+      if (sx < Wp && cbase + cq < p.ld) {
+        uint4 o;
+        o.x = pack16x2(tile[cq][slot], tile[cq + 1][slot], p.dtype);
+        o.y = pack16x2(tile[cq + 2][slot], tile[cq + 3][slot], p.dtype);
+        o.z = pack16x2(tile[cq + 4][slot], tile[cq + 5][slot], p.dtype);
+        o.w = pack16x2(tile[cq + 6][slot], tile[cq + 7][slot], p.dtype);
+        *reinterpret_cast<uint4*>(p.out + (slot_row + sx) * p.ld + cbase + cq) = o;
+      }
     }
     __syncthreads();
   }
+}
+
+// Vector variant for W % 4 == 0: one CTA = one slot row x 128 pixels; a lane owns 4 consecutive pixels of a channel, read
+// with aligned 128-bit loads (the Shift taps through the same two-float4 window as lf_shift_vec_kernel), transposed
+// through shared memory and written as 16-byte channel groups.  Slot column 0 (the halo) is written by the first tile.
+__global__ void __launch_bounds__(256) pack_views_vec_kernel(const PackParams p) {
+  __shared__ __align__(16) float tile[32][kPackTile + 4];   // [channel][pixel], 16-byte aligned rows
+  const int Wp = p.W + 1, Hp = p.H + 1, W = p.W, H = p.H;
+  const int X0 = blockIdx.x * kPackTile;
+  const int sy = blockIdx.y % Hp, b = blockIdx.y / Hp;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int64_t slot_row = (static_cast<int64_t>(b) * Hp + sy) * Wp;
+  const int x0 = X0 + 4 * lane, y = sy - 1;
+  const bool has_w = p.do_shift && p.stack != 1, has_v = p.do_shift && p.stack != 0;
+  const int vsign = p.stack == 2 ? -1 : +1;
+  for (int cbase = 0; cbase < p.ld; cbase += 32) {
+    for (int c = wrp; c < 32; c += 8) {
+      const int ch = cbase + c;
+      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ch < p.C && sy >= 1 && x0 < W) {
+        const float* plane = p.views + (static_cast<int64_t>(b) * p.C + ch) * H * W;
+        if (!p.do_shift) {
+          val = __ldg(reinterpret_cast<const float4*>(plane + static_cast<int64_t>(y) * W + x0));
+        } else {
+          const int view = ch / 3;
+          const float w0 = p.taps.w0[view], w1 = p.taps.w1[view];
+          const int s0 = p.taps.s0[view], s1 = p.taps.s1[view];
+          const int ra = has_v ? src_index(y, s0, H, vsign) : y;
+          const int rb = has_v ? src_index(y, s1, H, vsign) : y;
+          float t0[4], t1[4];
+          if (has_w) {
+            const int e0 = eff_shift(s0, W), e1 = eff_shift(s1, W);
+            const int c0 = wrap(x0 - e0, W), c1 = wrap(x0 - e1, W);
+            const int up = wrap(c1 - c0, W);
+            int m, d0, d1;
+            if (up <= 1) { m = c0; d0 = 0; d1 = up; } else { m = c1; d0 = 1; d1 = 0; }
+            const int o = m & 3, a = m - o;
+            float f[8];
+            load8(plane + static_cast<int64_t>(ra) * W, a, W, f);
+            wlerp4(f, o, d0, d1, w0, w1, t0);
+            if (has_v) {
+              load8(plane + static_cast<int64_t>(rb) * W, a, W, f);
+              wlerp4(f, o, d0, d1, w0, w1, t1);
+            }
+          } else {
+            const float4 u = __ldg(reinterpret_cast<const float4*>(plane + static_cast<int64_t>(ra) * W + x0));
+            const float4 v = __ldg(reinterpret_cast<const float4*>(plane + static_cast<int64_t>(rb) * W + x0));
+            t0[0] = u.x; t0[1] = u.y; t0[2] = u.z; t0[3] = u.w;
+            t1[0] = v.x; t1[1] = v.y; t1[2] = v.z; t1[3] = v.w;
+          }
+          if (has_v) val = make_float4(lerp2(t0[0], w0, t1[0], w1), lerp2(t0[1], w0, t1[1], w1), lerp2(t0[2], w0, t1[2], w1),
+                                       lerp2(t0[3], w0, t1[3], w1));
+          else val = make_float4(t0[0], t0[1], t0[2], t0[3]);
+        }
+      }
+      *reinterpret_cast<float4*>(&tile[c][4 * lane]) = val;
+    }
+    __syncthreads();
+    const int cq = (threadIdx.x & 3) * 8;
+#pragma unroll
+    for (int pass = 0; pass < kPackTile / 64; ++pass) {
+      const int px = (threadIdx.x >> 2) + 64 * pass;
+      if (X0 + px < W && cbase + cq < p.ld) {
+        uint4 o;
+        o.x = pack16x2(tile[cq][px], tile[cq + 1][px], p.dtype);
+        o.y = pack16x2(tile[cq + 2][px], tile[cq + 3][px], p.dtype);
+        o.z = pack16x2(tile[cq + 4][px], tile[cq + 5][px], p.dtype);
+        o.w = pack16x2(tile[cq + 6][px], tile[cq + 7][px], p.dtype);
+        *reinterpret_cast<uint4*>(p.out + (slot_row + X0 + px + 1) * p.ld + cbase + cq) = o;
+      }
+    }
+    __syncthreads();
+  }
+  if (blockIdx.x == 0 && threadIdx.x * 8 < p.ld)            // halo column sx = 0
+    *reinterpret_cast<uint4*>(p.out + slot_row * p.ld + threadIdx.x * 8) = make_uint4(0u, 0u, 0u, 0u);
 }
 
 }  // namespace mmlf
@@ -270,30 +518,45 @@ extern "C" int mmlf_lf_shift(const float* src_h, const float* src_v, const float
   p.batch = batch; p.n = n; p.H = H; p.W = W;
   host_taps(disp, n, p.taps);
   const int64_t planes = static_cast<int64_t>(4) * batch * n * 3;
-  // grid.y is limited to 65535: launch in slabs of planes (same kernel, offset pointers)
-  const int64_t per_stack = static_cast<int64_t>(batch) * n * 3;
-  (void)planes;
-  if (4 * per_stack <= 65535) {
-    dim3 grid(H, static_cast<unsigned>(4 * per_stack));
-    lf_shift_kernel<<<grid, 128, 2 * W * sizeof(float), static_cast<cudaStream_t>(stream)>>>(p);
-    return check_launch("lf_shift_kernel");
-  }
-  // large batches: one launch per batch slab so that plane indices stay below the grid.y limit
-  const int slab = static_cast<int>(65535 / (4 * n * 3));
-  for (int b0 = 0; b0 < batch; b0 += slab) {
-    ShiftParams q = p;
-    const int nb = batch - b0 < slab ? batch - b0 : slab;
-    const int64_t off = static_cast<int64_t>(b0) * n * 3 * H * W;
-    for (int s = 0; s < 4; ++s) {
-      q.src[s] = p.src[s] + off;
-      q.dst[s] = p.dst[s] + off;
+  {
+    // W taps must be circular neighbours for the register kernel (always true for W >= 3: s1 = s0 +- 1)
+    bool vec_ok = (W % 4 == 0) && W >= 8;
+    for (int s = 0; s < 4 && vec_ok; ++s)
+      vec_ok = (reinterpret_cast<uintptr_t>(p.src[s]) % 16 == 0) && (reinterpret_cast<uintptr_t>(p.dst[s]) % 16 == 0);
+    if (vec_ok) {
+      static int rows_per_thread = -1;
+      if (rows_per_thread < 0) {
+        const char* e = getenv("MMLF_SHIFT_ROWS");
+        rows_per_thread = e ? atoi(e) : 4;
+      }
+      const int R = rows_per_thread;
+      const int64_t total = planes * ceil_div(H, R) * (W / 4);
+      MMLF_REQUIRE(ceil_div64(total, 256) < (1ll << 31), "lf_shift: too many planes");
+      const unsigned grid = static_cast<unsigned>(ceil_div64(total, 256));
+      cudaStream_t st = static_cast<cudaStream_t>(stream);
+      if (R == 1) lf_shift_vec_kernel<1><<<grid, 256, 0, st>>>(p, total);
+      else if (R == 2) lf_shift_vec_kernel<2><<<grid, 256, 0, st>>>(p, total);
+      else if (R == 8) lf_shift_vec_kernel<8><<<grid, 256, 0, st>>>(p, total);
+      else lf_shift_vec_kernel<4><<<grid, 256, 0, st>>>(p, total);
+      return check_launch("lf_shift_vec_kernel");
     }
-    q.batch = nb;
-    dim3 grid(H, static_cast<unsigned>(4 * nb * n * 3));
-    lf_shift_kernel<<<grid, 128, 2 * W * sizeof(float), static_cast<cudaStream_t>(stream)>>>(q);
-    if (int rc = check_launch("lf_shift_kernel")) return rc;
   }
-  return 0;
+  // band height: >= 8192 elements (32 KB in, 32 KB out) per CTA, bands of equal height
+  int rows = (8192 + W - 1) / W;
+  if (rows > H) rows = H;
+  const int bands = ceil_div(H, rows);
+  rows = ceil_div(H, bands);
+  const size_t smem = static_cast<size_t>(rows + 1) * W * sizeof(float);
+  MMLF_REQUIRE(smem <= 200 * 1024, "lf_shift: rows of %d pixels are too wide for the shared-memory band", W);
+  MMLF_REQUIRE(planes * bands < (1ll << 31), "lf_shift: too many planes");
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(lf_shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    MMLF_REQUIRE(e == cudaSuccess, "lf_shift: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    smem_set = 200 * 1024;
+  }
+  lf_shift_kernel<<<static_cast<unsigned>(planes * bands), kShiftThreads, smem, static_cast<cudaStream_t>(stream)>>>(p, rows, bands);
+  return check_launch("lf_shift_kernel");
 }
 
 static int launch_pack(const float* views, int B, int C, int H, int W, void* out, int ld, int dtype, int do_shift,
@@ -317,8 +580,15 @@ static int launch_pack(const float* views, int B, int C, int H, int W, void* out
     q.B = nb;
     q.views = views + static_cast<int64_t>(b0) * C * H * W;
     q.out = p.out + static_cast<int64_t>(b0) * (H + 1) * (W + 1) * ld;
-    dim3 grid(ceil_div(W + 1, 32), static_cast<unsigned>(nb * (H + 1)));
-    pack_views_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(q);
+    const bool vec = W % 4 == 0 && W >= 8 && reinterpret_cast<uintptr_t>(q.views) % 16 == 0 &&
+                     reinterpret_cast<uintptr_t>(q.out) % 16 == 0;
+    if (vec) {
+      dim3 grid(ceil_div(W, kPackTile), static_cast<unsigned>(nb * (H + 1)));
+      pack_views_vec_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(q);
+    } else {
+      dim3 grid(ceil_div(W + 1, kPackTile), static_cast<unsigned>(nb * (H + 1)));
+      pack_views_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(q);
+    }
     if (int rc = check_launch("pack_views_kernel")) return rc;
   }
   return 0;

@@ -10,7 +10,7 @@ cin_pad, n_pad = u.pad16(cin), u.pad16(cout)
 n_slots = B * (H + 1) * (W + 1)
 x = (torch.randn((n_slots, cin_pad), device='cuda') * 0.5).to(torch.float16)
 w = u.pack_weight((np.random.RandomState(0).normal(0, 0.03, (cout, cin, 2, 2))).astype(np.float32), dt=u.FP16)
-stats = torch.zeros((148, 8), dtype=torch.int64, device='cuda')
+stats = torch.zeros((148, 16), dtype=torch.int64, device='cuda')
 lib = u._lib.lib()
 lib.mmlf_debug_conv_stats.argtypes = [C.c_void_p]
 REPS = int(os.environ.get('CONV_STATS_REPS', '3'))
@@ -29,5 +29,8 @@ print(f'{B}x{H}x{W} {cin}->{cout} type {ctype}: {e0.elapsed_time(e1)*1e3:.1f} us
 for i, n in enumerate(names):
     print(f'  {n:28s} leader {lead[:, i].mean():10.0f}  peer {peer[:, i].mean():10.0f} cycles')
 print(f'  SM clock during the kernel: {lead[:, 0].mean() / lead[:, 7].mean() * 1e3:.0f} MHz (producer cycles / globaltimer ns)')
+t0 = s[:, 8].min()
+for nm, col in (('kernel entry', 8), ('main loop entry', 9), ('epilogue done', 10), ('kernel exit', 11)):
+    print(f'  {nm:18s} first {(s[:, col].min() - t0) / 1e3:7.2f} us   last {(s[:, col].max() - t0) / 1e3:7.2f} us')
 flops = 2.0 * n_slots * cout * 4 * cin
 print(f'  {flops / (e0.elapsed_time(e1) * 1e-3) / 1e12:.1f} TFLOP/s algorithmic')

@@ -26,7 +26,8 @@ def test_lf_extract_bit_exact():
         assert np.array_equal(g.cpu().numpy(), w)
 
 
-@pytest.mark.parametrize('shape', [(1, 9, 16, 16), (2, 9, 12, 20), (1, 9, 33, 18)])
+@pytest.mark.parametrize('shape', [(1, 9, 16, 16), (2, 9, 12, 20), (1, 9, 33, 18), (1, 9, 40, 512), (2, 9, 96, 96),
+                                   (1, 5, 7, 1024), (1, 3, 700, 18)])
 def test_lf_shift_bit_exact(shape, golden):
     from mmlf_b200 import ops
     B, n, H, W = shape
@@ -59,11 +60,9 @@ def test_lf_shift_golden(golden):
 
 def test_pack_views_and_shift_pack():
     u = _u()
-    B, n, H, W = 2, 9, 10, 14
     rng = np.random.RandomState(2)
-    v = rng.uniform(0, 1, (B, n, 3, H, W)).astype(np.float32)
-    out = torch.full((B * (H + 1) * (W + 1), 32), float('nan'), dtype=torch.bfloat16, device='cuda')
-    for dt in (u.BF16, u.FP16):
+    for B, n, H, W, dt in ((2, 9, 10, 14, u.BF16), (2, 9, 10, 14, u.FP16), (1, 9, 5, 300, u.FP16)):
+        v = rng.uniform(0, 1, (B, n, 3, H, W)).astype(np.float32)
         out = torch.full((B * (H + 1) * (W + 1), 32), float('nan'), dtype=u.TDT[dt], device='cuda')
         u.call('mmlf_pack_views', u.ptr(torch.from_numpy(v).cuda()), B, n * 3, H, W, u.ptr(out), 32, dt, u.stream())
         got = out.float().cpu().numpy().reshape(B, H + 1, W + 1, 32)
@@ -71,17 +70,19 @@ def test_pack_views_and_shift_pack():
         want[:, 1:, 1:, :27] = u.ROUND[dt](v.reshape(B, 27, H, W).transpose(0, 2, 3, 1))
         assert np.array_equal(got, want)
     # fused shift + pack == pack(shift(.)) for every stack
-    stacks = [rng.uniform(0, 1, (B, n, 3, 12, 12)).astype(np.float32) for _ in range(4)]
-    for disp in (2.5, -1.3, 0.0, 7.25):
-        sh = oracle.shift(tuple(stacks), disp)
-        for k in range(4):
-            o = torch.full((B * 13 * 13, 32), float('nan'), dtype=torch.float16, device='cuda')
-            u.call('mmlf_shift_pack', u.ptr(torch.from_numpy(stacks[k]).cuda()), k, B, n, 12, 12, float(disp),
-                   u.ptr(o), 32, u.FP16, u.stream())
-            got = o.float().cpu().numpy().reshape(B, 13, 13, 32)
-            want = np.zeros_like(got)
-            want[:, 1:, 1:, :27] = u.ROUND[u.FP16](sh[k].reshape(B, 27, 12, 12).transpose(0, 2, 3, 1))
-            assert np.array_equal(got, want), (disp, k)
+    B, n = 2, 9
+    for Hs, Ws in ((12, 12), (9, 150), (8, 136)):
+        stacks = [rng.uniform(0, 1, (B, n, 3, Hs, Ws)).astype(np.float32) for _ in range(4)]
+        for disp in (2.5, -1.3, 0.0, 7.25):
+            sh = oracle.shift(tuple(stacks), disp)
+            for k in range(4):
+                o = torch.full((B * (Hs + 1) * (Ws + 1), 32), float('nan'), dtype=torch.float16, device='cuda')
+                u.call('mmlf_shift_pack', u.ptr(torch.from_numpy(stacks[k]).cuda()), k, B, n, Hs, Ws, float(disp),
+                       u.ptr(o), 32, u.FP16, u.stream())
+                got = o.float().cpu().numpy().reshape(B, Hs + 1, Ws + 1, 32)
+                want = np.zeros_like(got)
+                want[:, 1:, 1:, :27] = u.ROUND[u.FP16](sh[k].reshape(B, 27, Hs, Ws).transpose(0, 2, 3, 1))
+                assert np.array_equal(got, want), (disp, k, Hs, Ws)
 
 
 # ------------------------------------------------------------------------------------------------ convolution
