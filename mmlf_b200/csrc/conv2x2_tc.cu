@@ -332,11 +332,11 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   uint8_t* aux = smem + p.aux_off;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
   uint64_t* empty_bar = full_bar + kMaxStages;
-  uint64_t* tmem_full_bar = empty_bar + kMaxStages;      // [2]
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;          // [2], leader's copy is used
-  uint64_t* tmem_ovl_bar = tmem_empty_bar + 2;           // leader's copy is used
+  uint64_t* tmem_full_bar = empty_bar + kMaxStages;      // [4]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 4;          // [4], leader's copy is used
+  uint64_t* tmem_ovl_bar = tmem_empty_bar + 4;           // leader's copy is used
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_ovl_bar + 1);
-  float* s_add = reinterpret_cast<float*>(aux + 192);   // 16-byte aligned (read as float4)
+  float* s_add = reinterpret_cast<float*>(aux + 256);   // 16-byte aligned (read as float4)
   float* s_mul = s_add + kMaxNPad;
 
   const int warp = threadIdx.x >> 5;
@@ -350,6 +350,11 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   const bool ovl_ok = (ovl_cols & 31) == 0 && (p.n_pad & 31) == 0;
   const int base1 = p.n_pad > 256 ? 512 - p.n_pad : 256;      // TMEM column base of odd tiles
   const int ovl = ovl_ok ? ovl_cols : 0;
+  // Narrow layers (n_pad <= 128) are bound by the epilogue, not by the MMAs: four 128-column accumulator regions, and
+  // the two epilogue warps of a TMEM lane quadrant take alternate TILES (all segments) instead of alternate segments of
+  // the same tile, so two tiles drain concurrently and the 32/32/16-column split no longer leaves one warp with 2/3 of
+  // the work.
+  const bool quad = p.n_pad <= 128;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -361,9 +366,10 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         mbar_init(smem_u32(&full_bar[i]), 1);          // leader: one arrive.expect_tx covering both CTAs' bytes
         mbar_init(smem_u32(&empty_bar[i]), 1);         // one multicast commit from the leader's MMA thread
       }
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < 4; ++i) {
         mbar_init(smem_u32(&tmem_full_bar[i]), 1);
-        mbar_init(smem_u32(&tmem_empty_bar[i]), 2 * kEpiWarps);   // one lane of every epilogue warp of both CTAs
+        // one lane of every epilogue warp of both CTAs that works on a tile (half of them in the 4-region scheme)
+        mbar_init(smem_u32(&tmem_empty_bar[i]), quad ? kEpiWarps : 2 * kEpiWarps);
       }
       mbar_init(smem_u32(tmem_ovl_bar), 2 * kEpiWarps);
       fence_barrier_init();
@@ -386,7 +392,7 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   }
   if (p.stat_off) {
     float* st = reinterpret_cast<float*>(smem + p.stat_off);
-    for (int i = threadIdx.x; i < 4 * 2 * p.n_pad; i += kConvThreads) st[i] = 0.f;
+    for (int i = threadIdx.x; i < kEpiWarps * 2 * p.n_pad; i += kConvThreads) st[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -470,15 +476,15 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       int it = 0;
       long long t_full = 0, t_tmem = 0, t_begin = prof ? clock64() : 0;
       for (int tile = pair; tile < p.num_tiles; tile += n_pairs, ++it) {
-        const int par = it & 1;
+        const int par = quad ? (it & 3) : (it & 1);
         long long tw = 0;
         if (prof) tw = clock64();
-        mbar_wait(smem_u32(&tmem_empty_bar[par]), ((it >> 1) & 1) ^ 1u);   // region drained (tile it - 2)
+        mbar_wait(smem_u32(&tmem_empty_bar[par]), ((quad ? it >> 2 : it >> 1) & 1) ^ 1u);   // region drained (tile it - 2 | 4)
         // regions overlap only when n_pad > 256: then the columns shared with tile it - 1 must have been drained
         if (p.n_pad > 256 && it > 0) mbar_wait(smem_u32(tmem_ovl_bar), (it - 1) & 1);
         if (prof) t_tmem += clock64() - tw;
         tc_fence_after();
-        const uint32_t acc_base = tmem_base + (par ? base1 : 0);
+        const uint32_t acc_base = tmem_base + (quad ? par * 128 : (par ? base1 : 0));
         uint32_t accumulate = 0;
 #pragma unroll 1
         for (int dy = 0; dy < 2; ++dy) {
@@ -530,13 +536,15 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const int half = (warp - 2) >> 2;                    // 0: even segments of a tile, 1: odd segments
     EpiWarp w;
     w.stg_addr = tiles_addr + p.epi_off + (warp - 2) * (FL::dual(p) ? 2u : 1u) * kSegBytes;
-    w.s_stat = (FL::stats(p) && p.stat_off) ? reinterpret_cast<float*>(smem + p.stat_off) + q * 2 * p.n_pad : nullptr;
+    w.s_stat = (FL::stats(p) && p.stat_off) ? reinterpret_cast<float*>(smem + p.stat_off) + (warp - 2) * 2 * p.n_pad : nullptr;
     w.s_add = s_add;
     w.s_mul = s_mul;
     int it = 0;
     long long t_wait = 0, t_begin = clock64();
+    const int seg_first = quad ? 0 : half, seg_step = quad ? 1 : 2;
     for (int tile = pair; tile < p.num_tiles; tile += n_pairs, ++it) {
-      const int par = it & 1;
+      if (quad && (it & 1) != half) continue;             // the other warp of this lane quadrant drains this tile
+      const int par = quad ? (it & 3) : (it & 1);
       const int row0 = tile * (2 * kTileM) + static_cast<int>(rank) * kTileM + q * 32;
       const int64_t s = static_cast<int64_t>(row0) + lane;
       const bool in_range = s < p.n_slots;
@@ -554,21 +562,21 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       auto seg_c0 = [&](int i) { return i < nseg1 ? start1 + 32 * i : 32 * (i - nseg1); };
       auto seg_n = [&](int i) { const int end = i < nseg1 ? p.n_pad : start1; const int c = seg_c0(i); return end - c < 32 ? end - c : 32; };
       // last position of this warp inside the shared columns / overall (-1: none)
-      const int last_ovl_i = ovl_pos > half ? half + ((ovl_pos - 1 - half) & ~1) : -1;
-      const int last_i = nseg > half ? half + ((nseg - 1 - half) & ~1) : -1;
+      const int last_ovl_i = ovl_pos > seg_first ? seg_first + (ovl_pos - 1 - seg_first) / seg_step * seg_step : -1;
+      const int last_i = nseg > seg_first ? seg_first + (nseg - 1 - seg_first) / seg_step * seg_step : -1;
       // this slot's saved ReLU bits of the first two segments, fetched before the accumulators are ready (one word per
       // 32 channels); the words of the following segments are prefetched one loop iteration ahead
       const uint32_t* gate_row = (FL::gate(p) && in_range) ? p.gate_bits + s * p.ld_bits : nullptr;
       auto gate_word = [&](int i) { return (gate_row && i < nseg) ? __ldg(gate_row + (seg_c0(i) >> 5)) : 0u; };
-      uint32_t g0 = gate_word(half), g1 = gate_word(half + 2);
-      if (FL::bits(p) && half == 0 && in_range)                 // words beyond the channels (ld_bits > ceil(n_pad / 32))
+      uint32_t g0 = gate_word(seg_first), g1 = gate_word(seg_first + seg_step);
+      if (FL::bits(p) && (quad || half == 0) && in_range)                 // words beyond the channels (ld_bits > ceil(n_pad / 32))
         for (int ww = (p.n_pad + 31) >> 5; ww < p.ld_bits; ++ww) p.relu_bits[s * p.ld_bits + ww] = 0u;
       long long tw = 0;
       if (p.stats) tw = clock64();
-      mbar_wait(smem_u32(&tmem_full_bar[par]), (it >> 1) & 1);
+      mbar_wait(smem_u32(&tmem_full_bar[par]), (quad ? it >> 2 : it >> 1) & 1);
       if (p.stats) t_wait += clock64() - tw;
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (par ? base1 : 0);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (quad ? par * 128 : (par ? base1 : 0));
       auto load_seg = [&](int i, uint32_t (&r)[32]) {
         if (seg_n(i) == 32) tmem_ld32(taddr + seg_c0(i), r);
         else tmem_ld16_lo(taddr + seg_c0(i), r);
@@ -590,21 +598,22 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         else epi_box_direct(p, s_add, s_mul, r, c0, n, s, in_range, valid, b, sy, sx);
       };
       uint32_t ra[32], rb[32];
-      if (half < nseg) load_seg(half, ra);
+      if (seg_first < nseg) load_seg(seg_first, ra);
       // NOT unrolled: the body (two segments) is ~1000 instructions; unrolling it five times pushed the kernel far
       // beyond the instruction cache and starved the producer / MMA warps ('no_inst' stalls)
 #pragma unroll 1
-      for (int i = half; i < nseg; i += 4) {
-        const uint32_t g2 = gate_word(i + 4), g3 = gate_word(i + 6);
+      for (int i = seg_first; i < nseg; i += 2 * seg_step) {
+        const int i1 = i + seg_step, i2 = i + 2 * seg_step;
+        const uint32_t g2 = gate_word(i2), g3 = gate_word(i2 + seg_step);
         tmem_ld_wait();
-        if (i + 2 < nseg) load_seg(i + 2, rb);               // in flight while segment i is processed
+        if (i1 < nseg) load_seg(i1, rb);                     // in flight while segment i is processed
         release(i == last_ovl_i, i == last_i);
         process(ra, i, g0);
-        if (i + 2 < nseg) {
+        if (i1 < nseg) {
           tmem_ld_wait();
-          if (i + 4 < nseg) load_seg(i + 4, ra);
-          release(i + 2 == last_ovl_i, i + 2 == last_i);
-          process(rb, i + 2, g1);
+          if (i2 < nseg) load_seg(i2, ra);
+          release(i1 == last_ovl_i, i1 == last_i);
+          process(rb, i1, g1);
         }
         g0 = g2;
         g1 = g3;
@@ -620,10 +629,12 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   tc_fence_before();
   __syncthreads();
   if (p.stat_off && p.col_sums) {
-    // combine the four lane quadrants' partial sums and add them to the global fp64 accumulators
+    // combine the epilogue warps' partial sums and add them to the global fp64 accumulators
     const float* st = reinterpret_cast<const float*>(smem + p.stat_off);
     for (int i = threadIdx.x; i < 2 * p.n_pad; i += kConvThreads) {
-      const float v = st[i] + st[2 * p.n_pad + i] + st[4 * p.n_pad + i] + st[6 * p.n_pad + i];
+      float v = 0.f;
+#pragma unroll
+      for (int wq = 0; wq < kEpiWarps; ++wq) v += st[wq * 2 * p.n_pad + i];
       atomicAdd(p.col_sums + i, static_cast<double>(v));
     }
   }
@@ -796,8 +807,8 @@ extern "C" int mmlf_conv2x2(const mmlf_conv_args* a, void* stream) {
   const uint32_t stage_bytes = kABytes + 2u * p.n_pad * 64u;
   // shared-memory plan behind the operand stages: [epilogue staging | statistics | barriers + constants]
   const uint32_t epi_bytes = p.out_mode == 0 ? kEpiWarps * (p.dual ? 2u : 1u) * kSegBytes : 0u;
-  const uint32_t stat_bytes = p.col_sums ? 4u * 2u * p.n_pad * 4u : 0u;
-  const uint32_t aux_bytes = 192 + 2 * kMaxNPad * 4 + 64;   // barriers + TMEM pointer, then the per-channel constants
+  const uint32_t stat_bytes = p.col_sums ? kEpiWarps * 2u * p.n_pad * 4u : 0u;   // per epilogue warp: [2][n_pad] f32
+  const uint32_t aux_bytes = 256 + 2 * kMaxNPad * 4 + 64;   // barriers + TMEM pointer, then the per-channel constants
   const uint32_t tail_bytes = epi_bytes + ((stat_bytes + 15u) & ~15u) + aux_bytes;
   const uint32_t max_smem = 232448;   // 227 KB opt-in limit per CTA on sm_100
   int stages = static_cast<int>((max_smem - 1024 - tail_bytes) / stage_bytes);
