@@ -184,7 +184,7 @@ struct Wgrad2Params {
   int n_pad, kc, ksplits;
   int64_t slots_per_split;
   int tap_base[2];                              // row offset of tap (dy, 0), dy = CTA rank
-  int stages;
+  int stages, group;                            // pipeline stages; 64-slot chunks per stage
   int n_parts, part_n[2], part_col[2];          // MMA N parts: columns [part_col, part_col + part_n)
   int part_box0[2], part_boxes[2];              // per CTA: first B box of the part and number of boxes (1 or 2)
   int nb;                                       // B boxes per CTA and stage
@@ -200,7 +200,10 @@ conv2x2_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (tiles_addr - raw_addr);
-  const uint32_t stage_bytes = kWg2ABytes + static_cast<uint32_t>(p.nb) * kWgBox;
+  // A stage holds `group` 64-slot chunks: the MMA warp's per-stage cost (barrier wait, fence, election, commit: ~500
+  // cycles) is then paid once per 4 * group MMAs instead of once per 4.
+  const uint32_t sub_bytes = kWg2ABytes + static_cast<uint32_t>(p.nb) * kWgBox;
+  const uint32_t stage_bytes = static_cast<uint32_t>(p.group) * sub_bytes;
   uint8_t* aux = smem + static_cast<size_t>(p.stages) * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
   uint64_t* empty_bar = full_bar + kWg2MaxStages;
@@ -241,19 +244,22 @@ conv2x2_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
 
   if (warp == 0) {
     uint32_t stage = 0, phase = 0;
-    for (int ch = 0; ch < n_chunks; ++ch) {
-      const int row0 = static_cast<int>(k_begin + static_cast<int64_t>(ch) * kWgKb);
+    for (int ch0 = 0; ch0 < n_chunks; ch0 += p.group) {
+      const int n_here = n_chunks - ch0 < p.group ? n_chunks - ch0 : p.group;
       mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
       const uint32_t fb = smem_u32(&full_bar[stage]);
-      const uint32_t a_dst = tiles_addr + stage * stage_bytes;
-      const uint32_t b_dst = a_dst + kWg2ABytes;
       if (elect_one()) {
-        if (leader) mbar_arrive_expect_tx(fb, 2 * stage_bytes);
-        tma_load_2d_pair(a_dst, &tmap_act, fb, chunk * 64, row0 + p.tap_base[rank], kEvictNormal);
-        for (int part = 0; part < p.n_parts; ++part) {
-          const int col = p.part_col[part] + static_cast<int>(rank) * (p.part_n[part] >> 1);
-          for (int j = 0; j < p.part_boxes[part]; ++j)
-            tma_load_2d_pair(b_dst + (p.part_box0[part] + j) * kWgBox, &tmap_dout, fb, col + 64 * j, row0, kEvictNormal);
+        if (leader) mbar_arrive_expect_tx(fb, 2u * static_cast<uint32_t>(n_here) * sub_bytes);
+        for (int g = 0; g < n_here; ++g) {
+          const int row0 = static_cast<int>(k_begin + static_cast<int64_t>(ch0 + g) * kWgKb);
+          const uint32_t a_dst = tiles_addr + stage * stage_bytes + g * sub_bytes;
+          const uint32_t b_dst = a_dst + kWg2ABytes;
+          tma_load_2d_pair(a_dst, &tmap_act, fb, chunk * 64, row0 + p.tap_base[rank], kEvictNormal);
+          for (int part = 0; part < p.n_parts; ++part) {
+            const int col = p.part_col[part] + static_cast<int>(rank) * (p.part_n[part] >> 1);
+            for (int j = 0; j < p.part_boxes[part]; ++j)
+              tma_load_2d_pair(b_dst + (p.part_box0[part] + j) * kWgBox, &tmap_dout, fb, col + 64 * j, row0, kEvictNormal);
+          }
         }
       }
       __syncwarp();
@@ -270,26 +276,34 @@ conv2x2_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
       const uint32_t a_lo0 = static_cast<uint32_t>(adesc_t), b_lo0 = static_cast<uint32_t>(bdesc_t);
       const uint32_t desc_hi = static_cast<uint32_t>(adesc_t >> 32);
       uint32_t stage = 0, phase = 0, accumulate = 0;
-      for (int ch = 0; ch < n_chunks; ++ch) {
+      for (int ch0 = 0; ch0 < n_chunks; ch0 += p.group) {
+        const int n_here = n_chunks - ch0 < p.group ? n_chunks - ch0 : p.group;
         mbar_wait(smem_u32(&full_bar[stage]), phase);
         tc_fence_after();
-        const uint32_t a_addr = tiles_addr + stage * stage_bytes;
-        const uint32_t b_addr = a_addr + kWg2ABytes;
-        // A: two MN atoms (taps dx = 0, 1) 128 B apart; B: atoms kWgBox apart; 8-slot groups 1024 B apart
-        const uint32_t a_lo = a_lo0 + ((a_addr & 0x3FFFFu) >> 4);
-        const uint32_t b0_lo = b_lo0 + (((b_addr + p.part_box0[0] * kWgBox) & 0x3FFFFu) >> 4);
-        const uint32_t b1_lo = b_lo0 + (((b_addr + p.part_box0[1] * kWgBox) & 0x3FFFFu) >> 4);
-        if (elect_one()) {
-          if (p.n_parts > 1)
-            umma_f16_pair_entry<2, 128>(tmem_base + p.part_col[0], tmem_base + p.part_col[1], a_lo, b0_lo, b1_lo, desc_hi,
-                                        desc_hi, idesc0, idesc1, accumulate, 4);
-          else
-            umma_f16_pair_entry<1, 128>(tmem_base + p.part_col[0], tmem_base, a_lo, b0_lo, b0_lo, desc_hi, desc_hi, idesc0,
-                                        idesc0, accumulate, 4);
-          umma_commit_pair(smem_u32(&empty_bar[stage]));
-          if (ch == n_chunks - 1) umma_commit_pair(smem_u32(done_bar));
+        // warp-uniform chunk loop, election inside (keeps the descriptors in uniform registers)
+#pragma unroll 1
+        for (int g = 0; g < n_here; ++g) {
+          const uint32_t a_addr = tiles_addr + stage * stage_bytes + g * sub_bytes;
+          const uint32_t b_addr = a_addr + kWg2ABytes;
+          // A: two MN atoms (taps dx = 0, 1) 128 B apart; B: atoms kWgBox apart; 8-slot groups 1024 B apart
+          const uint32_t a_lo = a_lo0 + ((a_addr & 0x3FFFFu) >> 4);
+          const uint32_t b0_lo = b_lo0 + (((b_addr + p.part_box0[0] * kWgBox) & 0x3FFFFu) >> 4);
+          const uint32_t b1_lo = b_lo0 + (((b_addr + p.part_box0[1] * kWgBox) & 0x3FFFFu) >> 4);
+          if (elect_one()) {
+            if (p.n_parts > 1)
+              umma_f16_pair_entry<2, 128>(tmem_base + p.part_col[0], tmem_base + p.part_col[1], a_lo, b0_lo, b1_lo, desc_hi,
+                                          desc_hi, idesc0, idesc1, accumulate, 4);
+            else
+              umma_f16_pair_entry<1, 128>(tmem_base + p.part_col[0], tmem_base, a_lo, b0_lo, b0_lo, desc_hi, desc_hi, idesc0,
+                                          idesc0, accumulate, 4);
+          }
+          accumulate = 1;
+          __syncwarp();
         }
-        accumulate = 1;
+        if (elect_one()) {
+          umma_commit_pair(smem_u32(&empty_bar[stage]));
+          if (ch0 + n_here == n_chunks) umma_commit_pair(smem_u32(done_bar));
+        }
         __syncwarp();
         if (++stage == static_cast<uint32_t>(p.stages)) {
           stage = 0;
@@ -415,9 +429,23 @@ static int wgrad_pair(const void* dout, int ld_dout, int n_pad, const void* act,
   }
   p.ws = workspace;
   p.act_dtype = p.dout_dtype = dtype;
-  const uint32_t stage_bytes = kWg2ABytes + p.nb * kWgBox;
+  const uint32_t sub_bytes = kWg2ABytes + p.nb * kWgBox;
   const uint32_t aux_bytes = (2 * kWg2MaxStages + 1) * 8 + 16 + 64;
   const uint32_t max_smem = 232448;
+  // chunks per stage: as many as leave room for a 3-stage pipeline, at most 4
+  int group = static_cast<int>((max_smem - 1024 - aux_bytes) / (3 * sub_bytes));
+  if (group > 4) group = 4;
+  if (group < 1) group = 1;
+  {
+    static int forced = -1;
+    if (forced < 0) {
+      const char* e = getenv("MMLF_WGRAD_GROUP");
+      forced = e ? atoi(e) : 0;
+    }
+    if (forced > 0) group = forced;
+  }
+  p.group = group;
+  const uint32_t stage_bytes = group * sub_bytes;
   int stages = static_cast<int>((max_smem - 1024 - aux_bytes) / stage_bytes);
   if (stages > kWg2MaxStages) stages = kWg2MaxStages;
   MMLF_REQUIRE(stages >= 2, "wgrad: not enough shared memory");
