@@ -126,6 +126,8 @@ __global__ void upr_posterior_kernel(const float* __restrict__ mean, const float
 }
 
 // ---------------------------------------------------------------------------- DPP head
+constexpr int kHeadUnroll = 12;
+
 __global__ void dpp_head_kernel(const float* __restrict__ scores, const float* __restrict__ bins_t,
                                 const float* __restrict__ bins_n, int steps, int64_t B, int64_t HW,
                                 float* __restrict__ one_hot, float* __restrict__ post, float* __restrict__ mean,
@@ -140,24 +142,50 @@ __global__ void dpp_head_kernel(const float* __restrict__ scores, const float* _
   if (idx >= B * HW) return;
   const int64_t b = idx / HW, pix = idx - b * HW;
   const float* s = scores + b * steps * HW + pix;
+  // every loop handles kHeadUnroll channel planes per iteration with the loads issued first (one 4-byte load per plane
+  // and thread: the plain loops were latency bound at 23 % of the HBM rate); passes 2 and 3 re-read the scores from L2
   float mx = -INFINITY, z = 0.f;
-  for (int c = 0; c < steps; ++c) {
-    const float v = __ldg(s + c * HW);
-    mx = fmaxf(mx, v);
-    z += expf(v);                                      // unstabilised, as the reference
+  for (int c0 = 0; c0 < steps; c0 += kHeadUnroll) {
+    float v[kHeadUnroll];
+#pragma unroll
+    for (int u = 0; u < kHeadUnroll; ++u) v[u] = c0 + u < steps ? __ldg(s + (c0 + u) * HW) : -INFINITY;
+#pragma unroll
+    for (int u = 0; u < kHeadUnroll; ++u) {
+      if (c0 + u < steps) {
+        mx = fmaxf(mx, v[u]);
+        z += expf(v[u]);                                 // unstabilised, as the reference
+      }
+    }
   }
   float mu = 0.f;
-  for (int c = 0; c < steps; ++c) {
-    const float v = __ldg(s + c * HW);
-    const float oh = (v == mx) ? 1.f : 0.f;            // ties give a multi-hot vector
-    mu += sb[c] * oh;
-    if (one_hot) one_hot[b * steps * HW + c * HW + pix] = oh;
-    if (post) post[b * steps * HW + c * HW + pix] = expf(v) / z;
+  for (int c0 = 0; c0 < steps; c0 += kHeadUnroll) {
+    float v[kHeadUnroll];
+#pragma unroll
+    for (int u = 0; u < kHeadUnroll; ++u) v[u] = c0 + u < steps ? __ldg(s + (c0 + u) * HW) : 0.f;
+#pragma unroll
+    for (int u = 0; u < kHeadUnroll; ++u) {
+      const int c = c0 + u;
+      if (c < steps) {
+        const float oh = (v[u] == mx) ? 1.f : 0.f;       // ties give a multi-hot vector
+        mu += sb[c] * oh;
+        if (one_hot) __stcs(one_hot + b * steps * HW + c * HW + pix, oh);
+        if (post) __stcs(post + b * steps * HW + c * HW + pix, expf(v[u]) / z);
+      }
+    }
   }
   float acc = 0.f;
-  for (int c = 0; c < steps; ++c) {
-    const float d = sb[steps + c] - mu;
-    acc += d * d * (expf(__ldg(s + c * HW)) / z);
+  for (int c0 = 0; c0 < steps; c0 += kHeadUnroll) {
+    float v[kHeadUnroll];
+#pragma unroll
+    for (int u = 0; u < kHeadUnroll; ++u) v[u] = c0 + u < steps ? __ldg(s + (c0 + u) * HW) : 0.f;
+#pragma unroll
+    for (int u = 0; u < kHeadUnroll; ++u) {
+      const int c = c0 + u;
+      if (c < steps) {
+        const float d = sb[steps + c] - mu;
+        acc += d * d * (expf(v[u]) / z);
+      }
+    }
   }
   mean[idx] = mu;
   logvar[idx] = logf(acc);

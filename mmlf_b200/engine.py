@@ -85,6 +85,9 @@ class Engine:
         assert self.feat_ld <= 320 and self.wp <= 320, 'model_chs too large for the 320-column TMEM plan'
         self._pack_version = None
         self._fold_cache = {}
+        self._param_cache = None
+        self._buffer_cache = None
+        self._gpad_cache = {}
         self._build_specs()
 
     @property
@@ -136,10 +139,17 @@ class Engine:
 
     # ------------------------------------------------------------------ parameters
     def _params(self):
-        return dict(self.m.named_parameters())
+        # the Parameter / buffer objects of a module are stable (.to(), load_state_dict and the fused optimizer all
+        # update them in place), so the name -> tensor maps are built once: walking the module tree on every call cost
+        # a third of the host time of a training step
+        if self._param_cache is None:
+            self._param_cache = dict(self.m.named_parameters())
+        return self._param_cache
 
     def _buffers(self):
-        return dict(self.m.named_buffers())
+        if self._buffer_cache is None:
+            self._buffer_cache = dict(self.m.named_buffers())
+        return self._buffer_cache
 
     def repack(self, need_dgrad):
         """(Re)build the packed bf16 operands when the canonical fp32 parameters changed."""
@@ -169,13 +179,16 @@ class Engine:
         self._pack_version = (version, bool(need_dgrad))
 
     def _bn_padded(self, prefix, C_real, C, dev):
-        """gamma/beta padded with zeros to the channel pitch (fp32)."""
-        p = self._params()
-        g = torch.zeros(C, dtype=torch.float32, device=dev)
-        b = torch.zeros(C, dtype=torch.float32, device=dev)
-        g[:C_real].copy_(p[prefix + '.weight'].detach())
-        b[:C_real].copy_(p[prefix + '.bias'].detach())
-        return g, b
+        """gamma padded with zeros to the channel pitch (fp32); cached until the parameter changes."""
+        gamma = self._params()[prefix + '.weight']
+        key = (gamma._version, gamma.data_ptr())
+        hit = self._gpad_cache.get(prefix)
+        if hit is None or hit[0] != key:
+            g = torch.zeros(C, dtype=torch.float32, device=dev)
+            g[:C_real].copy_(gamma.detach())
+            hit = (key, g)
+            self._gpad_cache[prefix] = hit
+        return hit[1], None
 
     # ------------------------------------------------------------------ kernel launch helpers
     def conv(self, geo, x, ld_in, cs, w, n_pad, cin_pad, ctype, out, ld_out, *, bias=None, scale=None, shift=None,
@@ -236,6 +249,11 @@ class Engine:
         cin0_pad = pad16(n * c3)
         dual = save and self.act != GRAD          # keep a bf16 copy of the MMA operands of the backward pass
 
+        # per-forward scratch for the BatchNorm layers, allocated once (one launch each instead of five per block)
+        n_bn = len(self.stream_defs) * self.in_blocks + len(self.out_specs)
+        self._fwd_sums = torch.zeros((n_bn, 2 * 320), dtype=torch.float64, device=self.dev) if bn_train else None
+        self._fwd_consts = torch.empty((n_bn, 4, 320), dtype=torch.float32, device=self.dev) if bn_train else None
+        self._fwd_bn_idx = 0
         feats = self._slots(geo, self.feat_ld)
         featsg = self._slots(geo, self.feat_ld, GRAD) if dual else (feats if save else None)
         for si, (key, net, spatial) in enumerate(self.stream_defs):
@@ -326,14 +344,14 @@ class Engine:
             if save:
                 raise NotImplementedError('--train_eval_mode (training through eval-mode BatchNorm) is not supported')
             return rec
-        scale = torch.empty(Cp, dtype=torch.float32, device=self.dev)
-        shift = torch.empty(Cp, dtype=torch.float32, device=self.dev)
+        k = self._fwd_bn_idx
+        self._fwd_bn_idx += 1
+        consts = self._fwd_consts[k]
+        scale, shift, save_mean, save_invstd = consts[0, :Cp], consts[1, :Cp], consts[2, :Cp], consts[3, :Cp]
         z = self._slots(geo, Cp)
         # batch statistics (sum, sum of squares of the stored z) come out of the conv epilogue
-        sums = torch.zeros(2 * Cp, dtype=torch.float64, device=self.dev)
+        sums = self._fwd_sums[k, :2 * Cp]
         self.conv(geo, a1, c1.n_pad, c2, c2.w_fwd, Cp, c2.cin_pad, 1, z, Cp, bias=c2.bias_pad, col_sums=sums)
-        save_mean = torch.empty(Cp, dtype=torch.float32, device=self.dev)
-        save_invstd = torch.empty(Cp, dtype=torch.float32, device=self.dev)
         nbt = bufs.get(bnp + '.num_batches_tracked')
         call('mmlf_bn_finalize', _ptr(sums), C_real, Cp, geo.count, _ptr(gamma), _ptr(beta), _ptr(rmean), _ptr(rvar),
              _ptr(nbt), float(self.m.batchnorm_momentum), float(self.m.bn_eps), _ptr(scale), _ptr(shift),
@@ -371,6 +389,17 @@ class Engine:
         ws_bytes = max(_lib.lib().mmlf_conv2x2_wgrad_workspace(cs.n_pad, cs.cin_pad) for cs in self.all_convs())
         ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
         dwp = torch.empty(320 * 4 * 320, dtype=torch.float32, device=dev)
+        # scratch rows for the per-block reductions, zeroed / allocated once per backward pass
+        n_blk = len(tape['out']) + sum(len(r) for r in tape['streams'].values()) + 2
+        z64 = torch.zeros((2 * n_blk, 2 * 320), dtype=torch.float64, device=dev)
+        z32 = torch.zeros((n_blk, 320), dtype=torch.float32, device=dev)
+        e32 = torch.empty((n_blk, 2 * 320), dtype=torch.float32, device=dev)
+        pool = {'z64': 0, 'z32': 0, 'e32': 0}
+
+        def take(name, buf, n):
+            i = pool[name]
+            pool[name] = i + 1
+            return buf[i, :n]
 
         def conv_param_grads(cs, dout, ld_dout, actg, ld_act, dbias=None):
             """dW via the tcgen05 wgrad kernel (both operands in the gradient format); db from ``dbias`` when the
@@ -414,7 +443,7 @@ class Engine:
             call('mmlf_pack_views', _ptr(g_out), geo.B, self.oc, geo.H, geo.W, _ptr(gz), h2.n_pad, GRAD, st)
             conv_param_grads(h2, gz, h2.n_pad, hd['midg'], h1.n_pad)
             gmid = self._slots(geo, h1.n_pad, GRAD)
-            sums = torch.zeros(2 * h1.n_pad, dtype=torch.float64, device=dev)
+            sums = take('z64', z64, 2 * h1.n_pad)
             dgrad(h2, gz, h2.n_pad, gmid, h1.n_pad, gate_bits=hd['bits'], col_sums=sums)
             conv_param_grads(h1, gmid, h1.n_pad, hd['xg'], hd['ld_x'], dbias=sums.float())
         dgrad(h1, gmid, h1.n_pad, g_x, h1.cin_pad)
@@ -426,16 +455,16 @@ class Engine:
             dz = self._slots(geo, Cp, GRAD)
             db2 = None
             if self.has_bn:
-                sums = torch.zeros(2 * Cp, dtype=torch.float64, device=dev)
+                sums = take('z64', z64, 2 * Cp)
                 call('mmlf_bn_bwd_reduce', _ptr(gy), ld_gy, _ptr(rec['z']), Cp, _ptr(rec['scale']), _ptr(rec['shift']),
                      _ptr(rec['save_mean']), _ptr(rec['save_invstd']), Cp, geo.B, geo.H, geo.W, GRAD, self.act,
                      _ptr(sums), st)
                 gpad, _ = self._bn_padded(bnp, C_real, Cp, dev)
                 acc = bnp + '.weight' in grads
-                fsums = torch.empty(2 * Cp, dtype=torch.float32, device=dev)
+                fsums = take('e32', e32, 2 * Cp)
                 dgam = torch.empty(C_real, dtype=torch.float32, device=dev)
                 dbet = torch.empty(C_real, dtype=torch.float32, device=dev)
-                db2 = torch.zeros(Cp, dtype=torch.float32, device=dev)
+                db2 = take('z32', z32, Cp)
                 call('mmlf_bn_bwd_apply', _ptr(gy), ld_gy, _ptr(rec['z']), Cp, _ptr(rec['scale']), _ptr(rec['shift']),
                      _ptr(gpad), _ptr(rec['save_mean']), _ptr(rec['save_invstd']), _ptr(sums), geo.count, 1, C_real, Cp,
                      geo.B, geo.H, geo.W, GRAD, self.act, _ptr(dz), Cp, _ptr(dgam), _ptr(dbet), _ptr(fsums), _ptr(db2),
@@ -450,7 +479,7 @@ class Engine:
                      _ptr(dz), Cp, st)
             conv_param_grads(c2, dz, Cp, rec['a1g'], c1.n_pad, dbias=db2)
             da1 = self._slots(geo, c1.n_pad, GRAD)
-            sums1 = torch.zeros(2 * c1.n_pad, dtype=torch.float64, device=dev)
+            sums1 = take('z64', z64, 2 * c1.n_pad)
             dgrad(c2, dz, Cp, da1, c1.n_pad, gate_bits=rec['bits'], col_sums=sums1)
             conv_param_grads(c1, da1, c1.n_pad, rec['xg'], rec['ld_x'], dbias=sums1.float())
             if not need_gx:
