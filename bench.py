@@ -210,7 +210,7 @@ def main():
     ap.add_argument('--steps', type=int, default=8)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='train', choices=['train', 'infer', 'ese'])
+    ap.add_argument('--workload', default='train', choices=['train', 'infer', 'ese', 'bands'])
     ap.add_argument('--variant', default='base', choices=['base', 'upr', 'dpp'])
     ap.add_argument('--bs', type=int, default=512, help='global batch (train)')
     ap.add_argument('--ps', type=int, default=96, help='patch size (train)')
@@ -232,12 +232,14 @@ def main():
                    f'(9 views, 70 ch, 108 bins), fwd+loss+bwd+allreduce+Adam',
           'infer': f'{args.variant.upper()} full-LF inference, one 9x9-view {args.size}x{args.size} light field per GPU '
                    f'and step',
+          'bands': f'{args.variant.upper()} full-LF inference of ONE 9x9-view {args.size}x{args.size} light field per step, rows '
+                   f'sharded over the GPUs in bands with an 11-px halo, gathered on every rank',
           'ese': f'ESE (--val_ensamble) full-LF shift-ensemble inference, {ESE_MEMBERS} UPR members (shift -3.5..3.4 step '
                  f'0.1) of one 9x9-view {args.size}x{args.size} light field per step, members sharded over the GPUs, '
                  f'incl. shifts + Laplace-mixture reduce'}[args.workload]
-    strong = args.workload in ('train', 'ese')
+    strong = args.workload in ('train', 'ese', 'bands')
     config = {'workload': wl,
-              'global_batch': args.bs if args.workload == 'train' else (1 if args.workload == 'ese' else world),
+              'global_batch': args.bs if args.workload == 'train' else (1 if args.workload in ('ese', 'bands') else world),
               'parallelism': f'dp{world}', 'l2': 'inputs larger than L2 (>= 113 MB fp32 per step and GPU)',
               'activation_storage': args.precision, 'gradient_storage': 'bf16', 'accumulate': 'fp32'}
 
@@ -321,15 +323,22 @@ def main():
         views = [torch.rand((B, 9, 3, H, W), device=dev, generator=gen) for _ in range(4)]
         model.eval()
 
+        if args.workload == 'bands':
+            gen = torch.Generator(device=dev).manual_seed(1234)      # every rank holds the same light field
+            views = [torch.rand((B, 9, 3, H, W), device=dev, generator=gen) for _ in range(4)]
+
         def step(vs, gt_=None, mask_=None):
             with torch.no_grad():
+                if args.workload == 'bands':
+                    return parallel.banded_forward(model, vs)['mean']
                 out = model(*vs)
                 _ = out['mean']
                 if args.variant != 'base':
                     _ = out['posterior']
             return out['mean']
-        units_per_step = world * H * W / 1e6
-        flops_per_step = world * net_forward_flops(1, H, W, args.variant)
+        n_lf = 1 if args.workload == 'bands' else world
+        units_per_step = n_lf * H * W / 1e6
+        flops_per_step = n_lf * net_forward_flops(1, H, W, args.variant)
         host = [t.cpu().pin_memory() for t in views]
         gt = mask = None
 
@@ -406,6 +415,9 @@ def main():
         # the small head convs of BASE / UPR run partly on CUDA cores: negligible (< 0.1 %)
     elif args.workload == 'ese':
         conv_flops_rank = fwd                                # the profiling pass times single members
+    elif args.workload == 'bands':
+        lo_, hi_, a_, b_ = parallel.band_rows(H, rank, world, 11)
+        conv_flops_rank = net_forward_flops(1, b_ - a_, W, args.variant)
     else:
         conv_flops_rank = fwd
     conv_time = sum(conv_ms) / prof_steps / 1e3

@@ -61,7 +61,12 @@ def main(output_dir, dataset, model_invertible, model_discrete, val_loss_margin,
                 data[5] = data[5] - float(train_shift)
             h_views, v_views, i_views, d_views, center, gt, mpi, _, index = data
             mask = loss.create_mask_margin(gt.shape, val_loss_margin).to(dev)
-            output = model(h_views, v_views, i_views, d_views)
+            if world > 1 and not val_ensamble:
+                # one light field, rows sharded over the ranks in bands with a `model_radius` halo
+                output = parallel.banded_forward(model, [h_views, v_views, i_views, d_views],
+                                                 radius=kwargs.get('model_radius', 11))
+            else:
+                output = model(h_views, v_views, i_views, d_views)
             mse = mse_fn(output, gt, mask)
             bad_pix = bad_pix_fn(output, gt, mask)
             mse_avg += mse.item()

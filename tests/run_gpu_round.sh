@@ -16,6 +16,7 @@ timeout 600 python __graft_entry__.py smoke > $O/smoke_$TAG.log 2>&1; echo "smok
 timeout 900 python bench.py > $O/bench_train_$TAG.json 2> $O/bench_train_$TAG.err; echo "bench train: $?"
 timeout 600 python bench.py --workload infer > $O/bench_infer_$TAG.json 2> $O/bench_infer_$TAG.err; echo "bench infer: $?"
 timeout 600 python bench.py --workload ese --steps 3 > $O/bench_ese_$TAG.json 2> $O/bench_ese_$TAG.err; echo "bench ese: $?"
+timeout 600 python bench.py --workload bands --no-cpu-baseline > $O/bench_bands_$TAG.json 2> $O/bench_bands_$TAG.err; echo "bench bands: $?"
 timeout 600 python bench.py --variant upr --steps 4 --no-cpu-baseline > $O/bench_train_upr_$TAG.json 2> $O/bench_train_upr_$TAG.err; echo "bench upr: $?"
 timeout 600 python bench.py --variant dpp --steps 4 --no-cpu-baseline > $O/bench_train_dpp_$TAG.json 2> $O/bench_train_dpp_$TAG.err; echo "bench dpp: $?"
 timeout 600 python bench.py --bs 64 --no-cpu-baseline > $O/bench_train_bs64_$TAG.json 2> $O/bench_train_bs64_$TAG.err; echo "bench bs64: $?"
@@ -42,7 +43,9 @@ if [ "$2" != "noncu" ]; then
   cap bn_apply slot_map "bn_apply_relu"
   cap bn_bwd_reduce col_reduce "bn_bwd_reduce"
   cap bn_bwd_apply slot_map "bn_bwd_apply"
-  cap lf_shift lf_shift "lf_shift"
-  cap loss_ce loss_ce "loss_ce"
+  cap lf_shift lf_shift "lf_shift_kernel full"
+  cap shift_pack pack_views "shift_pack_kernel full"
+  cap loss_ce loss_ce "loss_ce_kernel 64x108x96x96 on-the-fly"
+  cap dpp_head dpp_head "dpp_head"
 fi
 ls -la $O | tail -n 40
