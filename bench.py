@@ -348,13 +348,13 @@ def main():
     barrier()
 
     # ---------------- timed region: inputs resident in HBM, CUDA events, max over ranks
-    # train: every C-ABI call is bracketed by a CUDA-event pair (the stream is always full at these sizes, so the pairs
-    # measure kernel time).  infer / ese: the product path replays a CUDA graph, which cannot be bracketed per kernel;
-    # the per-kernel times come from a second, un-graphed pass below.
+    # The timed region runs the product path without instrumentation (inference replays a CUDA graph, whose kernels
+    # cannot be bracketed one by one).  Per-kernel times come from a second pass below: same work, one stream, no graph,
+    # a CUDA-event pair around every launch.
     graphed = args.workload != 'train'
     sampler = ClockSampler(local) if rank == 0 else None
     _lib.launch_count = 0
-    _lib.set_profile(not graphed)
+    _lib.set_profile(False)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_wall0 = time.time()
@@ -365,37 +365,46 @@ def main():
     host_ms_per_step = (time.time() - t_wall0) * 1e3 / args.steps      # time the host needs to enqueue one step
     barrier()
     t_wall1 = time.time()
-    prof = _lib.set_profile(False)
     launches = _lib.launch_count
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = ms.item() / args.steps
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
-    prof_steps = args.steps
+    # ---------------- profiling pass
+    net = model
+    prof_steps = 2 if args.workload == 'train' else 3
     if graphed:
-        # un-graphed profiling pass: a device-side sleep in front of every forward lets the host enqueue the whole
-        # forward before the first kernel starts, so each event pair brackets exactly one kernel
-        net = model
         net.use_cuda_graph = False
-        prof_steps = 3
-        _lib.set_profile(True)
+    else:
+        net.engine.overlap_wgrad = False
+    _lib.set_profile(True)
+    for i in range(prof_steps):
+        if args.workload == 'train':
+            step(views, gt, mask)                 # the stream is always full at these sizes: pairs measure kernel time
+            continue
+        # a device-side sleep in front of every forward lets the host enqueue the whole forward before the first kernel
+        # starts, so each event pair brackets exactly one kernel
+        torch.cuda._sleep(20_000_000)
         with torch.no_grad():
-            for i in range(prof_steps):
-                torch.cuda._sleep(20_000_000)
-                if args.workload == 'ese':
-                    net.raw_forward(views, shift_disp=-3.5 + 0.1 * (7 * i + 3))
-                else:
-                    step(views, gt, mask)
-        torch.cuda.synchronize()
-        prof = _lib.set_profile(False)
+            if args.workload == 'ese':
+                net.raw_forward(views, shift_disp=-3.5 + 0.1 * (7 * i + 3))
+            else:
+                step(views, gt, mask)
+    torch.cuda.synchronize()
+    prof = _lib.set_profile(False)
+    if graphed:
         net.use_cuda_graph = True
+    else:
+        net.engine.overlap_wgrad = os.environ.get('MMLF_OVERLAP_WGRAD', '0') == '1'
+    barrier()
 
     # ---------------- per-kernel shares and the roofline of the dominant kernel (the tcgen05 conv)
     by_name = {}
     for name, a, b in prof:
         by_name.setdefault(name, []).append(a.elapsed_time(b))
     shares = {k: sum(v) / prof_steps for k, v in by_name.items()}
+    kernel_sum_ms = max(sum(shares.values()), 1e-9)           # summed kernel time of one profiled step / forward
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -426,15 +435,14 @@ def main():
                 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
                 'peak_source': peak_src, 'traffic': None, 'launches_per_step': n_conv,
                 'avg_launch_ms': (sum(conv_ms) / len(conv_ms)) if conv_ms else None,
-                'share_of_step': conv_time * 1e3 * (my_members if args.workload == 'ese' else 1) / ms_per_step}
-    if graphed:
-        roofline['note'] = ('value: CUDA-graph replay; kernel times: separate un-graphed pass of %d forward(s), events '
-                            'around every launch' % prof_steps)
+                'share_of_step': conv_time * 1e3 / kernel_sum_ms}
+    roofline['note'] = ('value: product path (%s); kernel times: separate single-stream pass of %d step(s), CUDA events around '
+                        'every launch' % ('CUDA-graph replay' if graphed else 'eager launches', prof_steps))
     if wgrad_ms:
         wg_time = sum(wgrad_ms) / prof_steps / 1e3
         wg_flops = fwd                                        # weight gradients cost one forward's worth of MACs
         roofline['wgrad'] = {'kernel': 'conv2x2_wgrad_kernel + reduce', 'achieved': wg_flops / wg_time / 1e12,
-                             'frac': wg_flops / wg_time / 1e12 / peak_tf, 'share_of_step': wg_time * 1e3 / ms_per_step}
+                             'frac': wg_flops / wg_time / 1e12 / peak_tf, 'share_of_step': wg_time * 1e3 / kernel_sum_ms}
     roofline['step'] = {'achieved': flops_per_step / world / (ms_per_step / 1e3) / 1e12,
                         'frac': flops_per_step / world / (ms_per_step / 1e3) / 1e12 / peak_tf,
                         'note': 'whole step, algorithmic FLOPs of SURVEY.md section 6 per GPU'}
@@ -491,7 +499,8 @@ def main():
             'scaling': 'strong' if strong else 'weak', 'vs_baseline': None,
             'dtype': args.precision + ' storage / fp32 accumulate', 'data': 'synthetic', 'config': config,
             'host_enqueue_ms_per_step': round(host_ms_per_step, 3), 'roofline': roofline, 'cpu_baseline': cpu_base, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
-            'kernel_ms_note': ('per training step' if not graphed else 'per single un-graphed forward (ESE: one member)'),
+            'kernel_ms_note': ('per training step, single-stream profiling pass' if not graphed else
+                               'per single un-graphed forward (ESE: one member)'),
             'kernel_ms_per_step': {k: round(v, 3) for k, v in sorted(shares.items(), key=lambda kv: -kv[1])}}
     print(json.dumps(line))
     if world > 1:
