@@ -142,48 +142,68 @@ __global__ void dpp_head_kernel(const float* __restrict__ scores, const float* _
   if (idx >= B * HW) return;
   const int64_t b = idx / HW, pix = idx - b * HW;
   const float* s = scores + b * steps * HW + pix;
-  // every loop handles kHeadUnroll channel planes per iteration with the loads issued first (one 4-byte load per plane
-  // and thread: the plain loops were latency bound at 23 % of the HBM rate); passes 2 and 3 re-read the scores from L2
+  // Every loop handles kHeadUnroll channel planes per iteration with the loads issued first (one 4-byte load per plane
+  // and thread).  Passes 2 and 3 re-read the scores from L2.  The kernel is issue bound: running pointers, exp through
+  // ex2.approx (__expf, relative error 2^-21; the posterior is checked to 2e-5) and one reciprocal of z per pixel.
   float mx = -INFINITY, z = 0.f;
+  const float* sp = s;
   for (int c0 = 0; c0 < steps; c0 += kHeadUnroll) {
     float v[kHeadUnroll];
 #pragma unroll
-    for (int u = 0; u < kHeadUnroll; ++u) v[u] = c0 + u < steps ? __ldg(s + (c0 + u) * HW) : -INFINITY;
+    for (int u = 0; u < kHeadUnroll; ++u) {
+      v[u] = c0 + u < steps ? __ldg(sp) : -INFINITY;
+      sp += HW;
+    }
 #pragma unroll
     for (int u = 0; u < kHeadUnroll; ++u) {
       if (c0 + u < steps) {
         mx = fmaxf(mx, v[u]);
-        z += expf(v[u]);                                 // unstabilised, as the reference
+        z += __expf(v[u]);                               // unstabilised, as the reference
       }
     }
   }
+  const float rz = 1.f / z;
   float mu = 0.f;
+  sp = s;
+  float* ohp = one_hot ? one_hot + b * steps * HW + pix : nullptr;
+  float* pp = post ? post + b * steps * HW + pix : nullptr;
   for (int c0 = 0; c0 < steps; c0 += kHeadUnroll) {
     float v[kHeadUnroll];
 #pragma unroll
-    for (int u = 0; u < kHeadUnroll; ++u) v[u] = c0 + u < steps ? __ldg(s + (c0 + u) * HW) : 0.f;
+    for (int u = 0; u < kHeadUnroll; ++u) {
+      v[u] = c0 + u < steps ? __ldg(sp) : 0.f;
+      sp += HW;
+    }
 #pragma unroll
     for (int u = 0; u < kHeadUnroll; ++u) {
       const int c = c0 + u;
       if (c < steps) {
         const float oh = (v[u] == mx) ? 1.f : 0.f;       // ties give a multi-hot vector
         mu += sb[c] * oh;
-        if (one_hot) __stcs(one_hot + b * steps * HW + c * HW + pix, oh);
-        if (post) __stcs(post + b * steps * HW + c * HW + pix, expf(v[u]) / z);
+        const float pc = __expf(v[u]) * rz;
+        if (ohp) __stcs(ohp, oh);
+        if (pp) __stcs(pp, pc);
+        v[u] = pc;
       }
+      if (ohp) ohp += HW;
+      if (pp) pp += HW;
     }
   }
   float acc = 0.f;
+  sp = s;
   for (int c0 = 0; c0 < steps; c0 += kHeadUnroll) {
     float v[kHeadUnroll];
 #pragma unroll
-    for (int u = 0; u < kHeadUnroll; ++u) v[u] = c0 + u < steps ? __ldg(s + (c0 + u) * HW) : 0.f;
+    for (int u = 0; u < kHeadUnroll; ++u) {
+      v[u] = c0 + u < steps ? __ldg(sp) : 0.f;
+      sp += HW;
+    }
 #pragma unroll
     for (int u = 0; u < kHeadUnroll; ++u) {
       const int c = c0 + u;
       if (c < steps) {
         const float d = sb[steps + c] - mu;
-        acc += d * d * (expf(v[u]) / z);
+        acc = fmaf(d * d, __expf(v[u]) * rz, acc);
       }
     }
   }
