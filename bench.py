@@ -215,7 +215,7 @@ def main():
     ap.add_argument('--bs', type=int, default=512, help='global batch (train)')
     ap.add_argument('--ps', type=int, default=96, help='patch size (train)')
     ap.add_argument('--size', type=int, default=512, help='light-field size (infer)')
-    ap.add_argument('--precision', default='fp16', choices=['fp16', 'bf16'], help='activation storage format')
+    ap.add_argument('--precision', default='fp16', choices=['fp16', 'bf16', 'split'], help='activation storage format')
     ap.add_argument('--cpu-batch', type=int, default=2)
     ap.add_argument('--cpu-size', type=int, default=128)
     ap.add_argument('--no-cpu-baseline', action='store_true')

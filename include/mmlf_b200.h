@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MMLF_ABI_VERSION 2
+#define MMLF_ABI_VERSION 3
 
 /* 16-bit storage formats.  Forward activations and weights are fp16 (11 significant bits; the reference's own GPU
  * path multiplies in TF32, 11 bits), gradients are bf16 (fp32 exponent range); accumulation is always fp32. */
@@ -63,6 +63,10 @@ int mmlf_shift_taps(double disp, int n, float* w0, float* w1, int* s0, int* s1);
  * views: [B][C][H][W] float32 (C = n*3); out: [n_slots][ld] bf16, channels >= C and halo slots zeroed. */
 int mmlf_pack_views(const float* views, int B, int C, int H, int W, void* out, int ld, int dtype, void* stream);
 
+/* Split-precision packing: hi = fp16(x) to columns [0, c_pad), lo = fp16(x - hi) to columns [c_pad, 2 c_pad) of
+ * out [n_slots][ld] (ld >= 2 * c_pad, c_pad a multiple of 8 and >= C). */
+int mmlf_pack_views_split(const float* views, int B, int C, int H, int W, void* out, int ld, int c_pad, void* stream);
+
 /* Fused Shift + pack for the ESE sweep (ensamble.py:63-70 + feed_forward.py:226-232): the shifted fp32 value
  * is rounded to bf16 and written straight into the slot layout.  stack: 0 = h, 1 = v, 2 = i, 3 = d. */
 int mmlf_shift_pack(const float* src, int stack, int B, int n, int H, int W, double disp, void* out, int ld,
@@ -80,6 +84,13 @@ int mmlf_shift_pack(const float* src, int stack, int B, int n, int H, int W, dou
  *            stored with pitch `group_pad` (the 4 x 70 -> 4 x 80 concatenated feature buffer); 1/cin/cin_pad else. */
 int mmlf_pack_conv_weight(const float* w, int cout, int cin, int spatial, int dgrad, int in_groups, int group_real,
                           int group_pad, void* out, int n_pad, int cin_pad, int dtype, void* stream);
+
+/* Split-precision operand for mmlf_conv_args.split_in: fp16 [n_pad][4 * 3 * kc * 64]; per tap the K blocks are
+ * [w_hi | w_lo | w_hi] (w' = w * weight_scale, w_hi = fp16(w'), w_lo = fp16(w' - w_hi)), matching the activation
+ * blocks [hi | hi | lo].  weight_scale is a power of two (64 in the engine) that lifts the residuals of typical conv
+ * weights (|w| ~ 0.03) out of the fp16 subnormal range; the caller divides it out through `scale` in the epilogue. */
+int mmlf_pack_conv_weight_split(const float* w, int cout, int cin, int spatial, int in_groups, int group_real,
+                                int group_pad, void* out, int n_pad, int cin_pad, float weight_scale, void* stream);
 
 /* Inverse for gradients: dw_packed [n_pad][4][cin_pad] f32 (same tap/column convention, forward orientation)
  * -> canonical (cout, cin, 2, 2) f32; accumulate != 0 adds (two streams share one module). */
@@ -120,6 +131,13 @@ typedef struct mmlf_conv_args {
   int ab_dtype;          /* storage format of `in` and `wpack`: MMLF_BF16 or MMLF_FP16                */
   int out_dtype;         /* storage format of `out` in out_mode 0                                     */
   int out2_dtype;        /* storage format of `out2`                                                  */
+  /* Split-precision inference ("3 x fp16", fp32-class products on the fp16 tensor cores): a value x is stored as
+   * hi = fp16(x) and lo = fp16(x - hi) and x * w is evaluated as hi*w_hi + hi*w_lo + lo*w_hi in the fp32 accumulator.
+   * split_in  != 0: `in` holds hi in columns [0, cin_pad) and lo in columns [split_in, split_in + cin_pad); `wpack`
+   *                 comes from mmlf_pack_conv_weight_split (three K blocks per tap); ab_dtype must be MMLF_FP16.
+   * split_out != 0: out_mode 0 writes hi to `out` and lo to `out + split_out` elements (same pitch); out2 must be NULL. */
+  int split_in;
+  int split_out;
 } mmlf_conv_args;
 
 /* 2x2 convolution as an implicit GEMM on tcgen05 (TMA-fed, TMEM accumulators, fused epilogue).  Forward of

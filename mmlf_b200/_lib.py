@@ -24,7 +24,8 @@ class ConvArgs(C.Structure):
                 ('gate_bits', c_p), ('relu_bits', c_p), ('ld_bits', c_i),
                 ('out', c_p), ('ld_out', c_i), ('out_mode', c_i), ('n_real', c_i),
                 ('out2', c_p), ('ld_out2', c_i), ('col_sums', c_p),
-                ('ab_dtype', c_i), ('out_dtype', c_i), ('out2_dtype', c_i)]
+                ('ab_dtype', c_i), ('out_dtype', c_i), ('out2_dtype', c_i),
+                ('split_in', c_i), ('split_out', c_i)]
 
 
 _PROTOS = {
@@ -35,8 +36,10 @@ _PROTOS = {
     'mmlf_lf_shift': (c_i, [c_p] * 8 + [c_i, c_i, c_i, c_i, c_d, c_p]),
     'mmlf_shift_taps': (c_i, [c_d, c_i, C.POINTER(c_f), C.POINTER(c_f), C.POINTER(c_i), C.POINTER(c_i)]),
     'mmlf_pack_views': (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p]),
+    'mmlf_pack_views_split': (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p]),
     'mmlf_shift_pack': (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_d, c_p, c_i, c_i, c_p]),
     'mmlf_pack_conv_weight': (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_p]),
+    'mmlf_pack_conv_weight_split': (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_f, c_p]),
     'mmlf_unpack_conv_wgrad': (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_p]),
     'mmlf_conv2x2': (c_i, [C.POINTER(ConvArgs), c_p]),
     'mmlf_conv2x2_simt': (c_i, [C.POINTER(ConvArgs), c_p]),
@@ -66,7 +69,7 @@ _PROTOS = {
 }
 
 EXPORTS = tuple(_PROTOS)
-ABI_VERSION = 2
+ABI_VERSION = 3
 _lib = None
 
 
@@ -90,7 +93,7 @@ def lib():
 
 
 # kernels launched per C-ABI call (for the launch count reported by bench.py)
-_KERNELS_PER_CALL = {'mmlf_conv2x2_wgrad': 2, 'mmlf_bn_bwd_apply': 2, 'mmlf_head_small_bwd': 2, 'mmlf_shift_taps': 0}
+_KERNELS_PER_CALL = {'mmlf_pack_views_split': 2, 'mmlf_conv2x2_wgrad': 2, 'mmlf_bn_bwd_apply': 2, 'mmlf_head_small_bwd': 2, 'mmlf_shift_taps': 0}
 launch_count = 0
 _profile = None          # when set to a list, call() appends (name, start_event, end_event)
 

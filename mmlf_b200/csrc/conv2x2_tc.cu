@@ -40,12 +40,13 @@ struct ConvParams {
   int64_t n_slots;
   int Hp, Wp, H, W;
   int n_pad, n_parts, n_part;
-  int n_kc, last_ksteps;
+  int n_kc, last_ksteps;                        // K chunks per tap (all terms) / 16-deep steps of a term's last chunk
+  int kc_term, lo_col;                          // chunks per split term (= n_kc unless split_in), column of the lo block
   int tap_off[4];
   int num_tiles, stages;
   int type, relu, out_mode, n_real, ld_out, ld_out2;
   int ab_dtype, out_dtype, out2_dtype;
-  int has_scale, dual, ld_bits;
+  int has_scale, dual, ld_bits, split_out;
   uint32_t epi_off, stat_off, aux_off;             // shared-memory offsets from the 1024-aligned base
   const float* bias;
   const float* scale;
@@ -153,6 +154,7 @@ enum : uint32_t {
   kFOut2F16 = 128,  // secondary output is fp16 (else bf16)
   kFDirect = 256,   // out_mode 1 / 2: fp32 rows or planar fp32, written straight from registers
   kFGeneric = 512,
+  kFSplit = 1024,   // second output = fp16 residual of the fp16 rounding of the first (split-precision inference)
 };
 
 template <uint32_t F> struct Flags {
@@ -166,6 +168,7 @@ template <uint32_t F> struct Flags {
   __device__ __forceinline__ static bool out_f16(const ConvParams& p) { return generic ? p.out_dtype == kFP16 : (F & kFOutF16) != 0; }
   __device__ __forceinline__ static bool out2_f16(const ConvParams& p) { return generic ? p.out2_dtype == kFP16 : (F & kFOut2F16) != 0; }
   __device__ __forceinline__ static bool direct(const ConvParams& p) { return generic ? p.out_mode != 0 : (F & kFDirect) != 0; }
+  __device__ __forceinline__ static bool split(const ConvParams& p) { return generic ? p.split_out != 0 : (F & kFSplit) != 0; }
 };
 
 // One epilogue warp's context for the staged (out_mode 0) path
@@ -235,7 +238,15 @@ __device__ __forceinline__ void epi_segment(const ConvParams& p, const EpiWarp& 
     if (o == 1 && !FL::dual(p)) break;
     const bool f16 = o ? FL::out2_f16(p) : FL::out_f16(p);
     uint32_t pk[16];
-    if (f16) {
+    if (o == 1 && FL::split(p)) {
+      // lo = fp16(x - float(fp16(x))): the part of x the first output lost
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const uint32_t hi2 = pack_f16x2_sat(x[2 * j], x[2 * j + 1]);
+        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi2));
+        pk[j] = pack_f16x2_sat(x[2 * j] - hf.x, x[2 * j + 1] - hf.y) & vmask;
+      }
+    } else if (f16) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) pk[j] = pack_f16x2_sat(x[2 * j], x[2 * j + 1]) & vmask;
     } else {
@@ -434,7 +445,10 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           const uint32_t b_dst = a_dst + kABytes;
           if (elect_one()) {
             if (leader) mbar_arrive_expect_tx(fb, tx_bytes);
-            tma_load_2d_pair(a_dst, &tmap_a, fb, kc * 64, arow, kEvictNormal);
+            // split precision: the K chunks of a tap are [hi | hi | lo] blocks of the activation columns
+            const int term = kc / p.kc_term;
+            const int a_col = (kc - term * p.kc_term) * 64 + (term == 2 ? p.lo_col : 0);
+            tma_load_2d_pair(a_dst, &tmap_a, fb, a_col, arow, kEvictNormal);
 #pragma unroll
             for (int dx = 0; dx < 2; ++dx) {
               const int kc_col = kcol + dx * p.n_kc * 64;
@@ -495,7 +509,7 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             if (prof) t_full += clock64() - tw;
             tc_fence_after();
             const uint32_t a_addr = tiles_addr + stage * stage_bytes;
-            const int ksteps = (kc == p.n_kc - 1) ? p.last_ksteps : 4;
+            const int ksteps = ((kc + 1) % p.kc_term == 0) ? p.last_ksteps : 4;
             const uint32_t a_lo = desc_lo0 + ((a_addr & 0x3FFFFu) >> 4);
             const uint32_t b_lo = desc_lo0 + (((a_addr + kABytes) & 0x3FFFFu) >> 4);
             const bool last = (dy == 1 && kc == p.n_kc - 1);
@@ -734,8 +748,21 @@ static int fill_params(const mmlf_conv_args* a, ConvParams& p) {
   p.n_parts = a->n_pad > 256 ? 2 : 1;
   p.n_part = a->n_pad / p.n_parts;
   MMLF_REQUIRE(p.n_part % 16 == 0, "conv2x2: n_pad %d does not split into MMA N multiples of 16", a->n_pad);
-  p.n_kc = ceil_div(a->cin_pad, 64);
-  p.last_ksteps = (a->cin_pad - (p.n_kc - 1) * 64) / 16;
+  p.kc_term = ceil_div(a->cin_pad, 64);
+  p.last_ksteps = (a->cin_pad - (p.kc_term - 1) * 64) / 16;
+  MMLF_REQUIRE(a->split_in >= 0 && a->split_out >= 0, "conv2x2: negative split offset");
+  if (a->split_in) {
+    MMLF_REQUIRE(a->ab_dtype == kFP16, "conv2x2: split-precision operands are fp16");
+    MMLF_REQUIRE(a->split_in % 8 == 0 && a->split_in >= a->cin_pad && a->ld_in >= a->split_in + a->cin_pad,
+                 "conv2x2: split_in %d does not fit cin_pad %d / ld_in %d", a->split_in, a->cin_pad, a->ld_in);
+  }
+  if (a->split_out) {
+    MMLF_REQUIRE(a->out_mode == 0 && !a->out2 && a->out_dtype == kFP16, "conv2x2: split_out needs a single fp16 out_mode-0 output");
+    MMLF_REQUIRE(a->split_out % 8 == 0 && a->split_out >= a->n_pad && a->ld_out >= a->split_out + a->n_pad,
+                 "conv2x2: split_out %d does not fit n_pad %d / ld_out %d", a->split_out, a->n_pad, a->ld_out);
+  }
+  p.n_kc = a->split_in ? 3 * p.kc_term : p.kc_term;
+  p.lo_col = a->split_in;
   if (a->type == 0) {
     p.tap_off[0] = 0; p.tap_off[1] = 1; p.tap_off[2] = p.Wp; p.tap_off[3] = p.Wp + 1;
   } else {
@@ -752,7 +779,8 @@ static int fill_params(const mmlf_conv_args* a, ConvParams& p) {
   p.out_dtype = a->out_dtype;
   p.out2_dtype = a->out2_dtype;
   p.has_scale = a->scale != nullptr;
-  p.dual = a->out2 != nullptr;
+  p.dual = a->out2 != nullptr || a->split_out != 0;
+  p.split_out = a->split_out != 0;
   p.ld_bits = a->ld_bits;
   p.bias = a->bias;
   p.scale = a->scale;
@@ -763,6 +791,11 @@ static int fill_params(const mmlf_conv_args* a, ConvParams& p) {
   p.out = a->out;
   p.out2 = a->out2;
   p.ld_out2 = a->ld_out2;
+  if (a->split_out) {                                       // the residual goes through the second-output path
+    p.out2 = reinterpret_cast<uint16_t*>(a->out) + a->split_out;
+    p.ld_out2 = a->ld_out;
+    p.out2_dtype = kFP16;
+  }
   p.stats = nullptr;
   p.stages = 0;
   p.epi_off = p.stat_off = p.aux_off = 0;
@@ -787,6 +820,8 @@ struct ConvVariant {
 static const ConvVariant kConvVariants[] = {
     MMLF_CONV_VARIANT(kFRelu | kFOutF16),                          // eval / no-grad: first conv of a block
     MMLF_CONV_VARIANT(kFScale | kFRelu | kFOutF16),                // eval: second conv with folded BatchNorm
+    MMLF_CONV_VARIANT(kFRelu | kFOutF16 | kFDual | kFOut2F16 | kFSplit),            // split-precision eval (hi + lo outputs)
+    MMLF_CONV_VARIANT(kFScale | kFRelu | kFOutF16 | kFDual | kFOut2F16 | kFSplit),
     MMLF_CONV_VARIANT(kFRelu | kFBits | kFDual | kFOutF16),        // training: first conv (fp16 + bf16 copy + bits)
     MMLF_CONV_VARIANT(kFStats | kFOutF16),                         // training: second conv with batch statistics
     MMLF_CONV_VARIANT(kFRelu),
@@ -821,7 +856,9 @@ extern "C" int mmlf_conv2x2(const mmlf_conv_args* a, void* stream) {
   const uint32_t smem_bytes = 1024 + p.aux_off + aux_bytes;
 
   CUtensorMap tmap_a, tmap_b;
-  if (int rc = make_tmap_2d_16(&tmap_a, a->in, a->cin_pad, p.n_slots, static_cast<uint64_t>(a->ld_in) * 2, 64, kABoxRows, 128))
+  // (split precision: the map also covers the lo block; chunk columns past cin_pad are never consumed by a k-step)
+  if (int rc = make_tmap_2d_16(&tmap_a, a->in, a->split_in ? a->split_in + a->cin_pad : a->cin_pad, p.n_slots,
+                               static_cast<uint64_t>(a->ld_in) * 2, 64, kABoxRows, 128))
     return rc;
   const uint64_t k_total = static_cast<uint64_t>(4) * p.n_kc * 64;
   if (int rc = make_tmap_2d_16(&tmap_b, a->wpack, k_total, p.n_pad, k_total * 2, 64, p.n_part / 2, 128)) return rc;
@@ -841,7 +878,8 @@ extern "C" int mmlf_conv2x2(const mmlf_conv_args* a, void* stream) {
   } else {
     mask = (p.has_scale ? kFScale : 0u) | (p.relu ? kFRelu : 0u) | (p.gate_bits ? kFGate : 0u) |
            (p.relu_bits ? kFBits : 0u) | (p.dual ? kFDual : 0u) | (p.col_sums ? kFStats : 0u) |
-           (p.out_dtype == kFP16 ? kFOutF16 : 0u) | (p.dual && p.out2_dtype == kFP16 ? kFOut2F16 : 0u);
+           (p.out_dtype == kFP16 ? kFOutF16 : 0u) | (p.dual && p.out2_dtype == kFP16 ? kFOut2F16 : 0u) |
+           (p.split_out ? kFSplit : 0u);
   }
   ConvKernel fn = kConvVariants[kNumConvVariants - 1].fn;
   for (int i = 0; i < kNumConvVariants - 1; ++i)
@@ -859,6 +897,7 @@ extern "C" int mmlf_conv2x2_simt(const mmlf_conv_args* a, void* stream) {
   ConvParams p;
   if (int rc = fill_params(a, p)) return rc;
   MMLF_REQUIRE(!(a->out2 || a->relu_bits || a->col_sums), "conv2x2_simt: out2 / relu_bits / col_sums are not supported");
+  MMLF_REQUIRE(!(a->split_in || a->split_out), "conv2x2_simt: split precision is not supported");
   const int64_t total = p.n_slots * (p.n_pad / 16);
   const int threads = 128;
   const int64_t blocks = ceil_div64(total, threads);

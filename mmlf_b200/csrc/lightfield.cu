@@ -319,6 +319,8 @@ struct PackParams {
   const float* views;
   __nv_bfloat16* out;
   int B, C, H, W, ld;
+  int cw;                        // channels written per slot (multiple of 8, <= ld); columns [cw, ld) are left alone
+  int residual;                  // write fp16(x - float(fp16(x))) instead of fp16(x) (split-precision lo block)
   int do_shift, stack, n, dtype;
   ShiftTaps taps;
 };
@@ -341,6 +343,14 @@ __device__ __forceinline__ float shifted_value(const float* __restrict__ plane, 
 
 constexpr int kPackTile = 128;                     // slot columns per CTA
 
+__device__ __forceinline__ uint32_t pack_pair(float a, float b, const PackParams& p) {
+  if (p.residual) {
+    a -= from16(to16(a, kFP16), kFP16);
+    b -= from16(to16(b, kFP16), kFP16);
+  }
+  return pack16x2(a, b, p.dtype);
+}
+
 __global__ void __launch_bounds__(256) pack_views_kernel(const PackParams p) {
   __shared__ float tile[32][kPackTile + 1];        // [channel][slot column], 32 channels per pass
   const int Wp = p.W + 1, Hp = p.H + 1;
@@ -348,7 +358,7 @@ __global__ void __launch_bounds__(256) pack_views_kernel(const PackParams p) {
   const int sy = blockIdx.y % Hp, b = blockIdx.y / Hp;
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
   const int64_t slot_row = (static_cast<int64_t>(b) * Hp + sy) * Wp;
-  for (int cbase = 0; cbase < p.ld; cbase += 32) {
+  for (int cbase = 0; cbase < p.cw; cbase += 32) {
     // load: warp w handles channels w, w+8, ...; lanes run along x, four columns (32 apart) per lane in flight
     for (int c = wrp; c < 32; c += 8) {
       const int ch = cbase + c;
@@ -380,12 +390,12 @@ __global__ void __launch_bounds__(256) pack_views_kernel(const PackParams p) {
     for (int pass = 0; pass < kPackTile / 64; ++pass) {
       const int slot = (threadIdx.x >> 2) + 64 * pass;
       const int sx = sx0 + slot;
-      if (sx < Wp && cbase + cq < p.ld) {
+      if (sx < Wp && cbase + cq < p.cw) {
         uint4 o;
-        o.x = pack16x2(tile[cq][slot], tile[cq + 1][slot], p.dtype);
-        o.y = pack16x2(tile[cq + 2][slot], tile[cq + 3][slot], p.dtype);
-        o.z = pack16x2(tile[cq + 4][slot], tile[cq + 5][slot], p.dtype);
-        o.w = pack16x2(tile[cq + 6][slot], tile[cq + 7][slot], p.dtype);
+        o.x = pack_pair(tile[cq][slot], tile[cq + 1][slot], p);
+        o.y = pack_pair(tile[cq + 2][slot], tile[cq + 3][slot], p);
+        o.z = pack_pair(tile[cq + 4][slot], tile[cq + 5][slot], p);
+        o.w = pack_pair(tile[cq + 6][slot], tile[cq + 7][slot], p);
         *reinterpret_cast<uint4*>(p.out + (slot_row + sx) * p.ld + cbase + cq) = o;
       }
     }
@@ -406,7 +416,7 @@ __global__ void __launch_bounds__(256) pack_views_vec_kernel(const PackParams p)
   const int x0 = X0 + 4 * lane, y = sy - 1;
   const bool has_w = p.do_shift && p.stack != 1, has_v = p.do_shift && p.stack != 0;
   const int vsign = p.stack == 2 ? -1 : +1;
-  for (int cbase = 0; cbase < p.ld; cbase += 32) {
+  for (int cbase = 0; cbase < p.cw; cbase += 32) {
     for (int c = wrp; c < 32; c += 8) {
       const int ch = cbase + c;
       float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -453,18 +463,18 @@ __global__ void __launch_bounds__(256) pack_views_vec_kernel(const PackParams p)
 #pragma unroll
     for (int pass = 0; pass < kPackTile / 64; ++pass) {
       const int px = (threadIdx.x >> 2) + 64 * pass;
-      if (X0 + px < W && cbase + cq < p.ld) {
+      if (X0 + px < W && cbase + cq < p.cw) {
         uint4 o;
-        o.x = pack16x2(tile[cq][px], tile[cq + 1][px], p.dtype);
-        o.y = pack16x2(tile[cq + 2][px], tile[cq + 3][px], p.dtype);
-        o.z = pack16x2(tile[cq + 4][px], tile[cq + 5][px], p.dtype);
-        o.w = pack16x2(tile[cq + 6][px], tile[cq + 7][px], p.dtype);
+        o.x = pack_pair(tile[cq][px], tile[cq + 1][px], p);
+        o.y = pack_pair(tile[cq + 2][px], tile[cq + 3][px], p);
+        o.z = pack_pair(tile[cq + 4][px], tile[cq + 5][px], p);
+        o.w = pack_pair(tile[cq + 6][px], tile[cq + 7][px], p);
         *reinterpret_cast<uint4*>(p.out + (slot_row + X0 + px + 1) * p.ld + cbase + cq) = o;
       }
     }
     __syncthreads();
   }
-  if (blockIdx.x == 0 && threadIdx.x * 8 < p.ld)            // halo column sx = 0
+  if (blockIdx.x == 0 && threadIdx.x * 8 < p.cw)            // halo column sx = 0
     *reinterpret_cast<uint4*>(p.out + slot_row * p.ld + threadIdx.x * 8) = make_uint4(0u, 0u, 0u, 0u);
 }
 
@@ -560,7 +570,7 @@ extern "C" int mmlf_lf_shift(const float* src_h, const float* src_v, const float
 }
 
 static int launch_pack(const float* views, int B, int C, int H, int W, void* out, int ld, int dtype, int do_shift,
-                       int stack, int n, double disp, void* stream) {
+                       int stack, int n, double disp, void* stream, int cw = 0, int residual = 0) {
   MMLF_REQUIRE(dtype == 0 || dtype == 1, "pack_views: dtype must be 0 (bf16) or 1 (fp16)");
   MMLF_REQUIRE(views && out, "pack_views: null buffer");
   MMLF_REQUIRE(ld % 8 == 0 && ld >= C, "pack_views: ld %d must be a multiple of 8 and >= C %d", ld, C);
@@ -569,6 +579,9 @@ static int launch_pack(const float* views, int B, int C, int H, int W, void* out
   p.views = views; p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.B = B; p.C = C; p.H = H; p.W = W; p.ld = ld;
   p.do_shift = do_shift; p.stack = stack; p.n = n; p.dtype = dtype;
+  p.cw = cw ? cw : ld;
+  p.residual = residual;
+  MMLF_REQUIRE(p.cw % 8 == 0 && p.cw >= C && p.cw <= ld, "pack_views: bad written-channel count %d", p.cw);
   if (do_shift) host_taps(disp, n, p.taps);
   const int64_t rows = static_cast<int64_t>(B) * (H + 1);
   // grid.y <= 65535: split the batch into slabs
@@ -597,6 +610,13 @@ static int launch_pack(const float* views, int B, int C, int H, int W, void* out
 extern "C" int mmlf_pack_views(const float* views, int B, int C, int H, int W, void* out, int ld, int dtype,
                                void* stream) {
   return launch_pack(views, B, C, H, W, out, ld, dtype, 0, 0, 0, 0.0, stream);
+}
+
+extern "C" int mmlf_pack_views_split(const float* views, int B, int C, int H, int W, void* out, int ld, int c_pad,
+                                     void* stream) {
+  MMLF_REQUIRE(c_pad % 8 == 0 && c_pad >= C && ld >= 2 * c_pad, "pack_views_split: bad c_pad %d / ld %d", c_pad, ld);
+  if (int rc = launch_pack(views, B, C, H, W, out, ld, kFP16, 0, 0, 0, 0.0, stream, c_pad, 0)) return rc;
+  return launch_pack(views, B, C, H, W, reinterpret_cast<uint16_t*>(out) + c_pad, ld, kFP16, 0, 0, 0, 0.0, stream, c_pad, 1);
 }
 
 extern "C" int mmlf_shift_pack(const float* src, int stack, int B, int n, int H, int W, double disp, void* out,

@@ -23,13 +23,17 @@ __host__ __device__ __forceinline__ int real_channel(int c, int groups, int grou
 
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int cout, int cin, int spatial, int dgrad,
                                         int groups, int group_real, int group_pad, uint16_t* __restrict__ out,
-                                        int n_pad, int n_kc, int dtype) {
-  const int k_total = 4 * n_kc * 64;
+                                        int n_pad, int n_kc, int dtype, int split, float wscale) {
+  // split: three K blocks per tap, [w_hi | w_lo | w_hi]
+  const int terms = split ? 3 : 1;
+  const int k_total = 4 * terms * n_kc * 64;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<int64_t>(n_pad) * k_total) return;
   const int row = static_cast<int>(idx / k_total);
   const int col = static_cast<int>(idx - static_cast<int64_t>(row) * k_total);
-  const int tap = col / (n_kc * 64), c = col - tap * n_kc * 64;
+  const int tap = col / (terms * n_kc * 64);
+  const int ct = col - tap * terms * n_kc * 64;
+  const int term = ct / (n_kc * 64), c = ct - term * n_kc * 64;
   int p = tap >> 1, q = tap & 1;
   float v = 0.f;
   int n, ci;
@@ -48,7 +52,9 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int cout, i
     eff_to_canonical(spatial, p, q, a, b);
     v = w[((static_cast<int64_t>(n) * cin + ci) * 2 + a) * 2 + b];
   }
-  out[idx] = to16(v, dtype);
+  v *= wscale;                                                      // power of two: exact
+  if (split && term == 1) v -= from16(to16(v, kFP16), kFP16);      // residual of the fp16 rounding
+  out[idx] = to16(v, split ? kFP16 : dtype);
 }
 
 __global__ void unpack_conv_wgrad_kernel(const float* __restrict__ dwp, int n_pad, int cin_pad, int cout, int cin,
@@ -89,8 +95,24 @@ extern "C" int mmlf_pack_conv_weight(const float* w, int cout, int cin, int spat
   const int n_kc = ceil_div(cin_pad, 64);
   const int64_t total = static_cast<int64_t>(n_pad) * 4 * n_kc * 64;
   pack_conv_weight_kernel<<<static_cast<unsigned>(ceil_div64(total, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      w, cout, cin, spatial, dgrad, in_groups, group_real, group_pad, reinterpret_cast<uint16_t*>(out), n_pad, n_kc, dtype);
+      w, cout, cin, spatial, dgrad, in_groups, group_real, group_pad, reinterpret_cast<uint16_t*>(out), n_pad, n_kc, dtype, 0, 1.0f);
   return check_launch("pack_conv_weight_kernel");
+}
+
+extern "C" int mmlf_pack_conv_weight_split(const float* w, int cout, int cin, int spatial, int in_groups, int group_real,
+                                           int group_pad, void* out, int n_pad, int cin_pad, float weight_scale, void* stream) {
+  MMLF_REQUIRE(w && out, "pack_conv_weight_split: null buffer");
+  MMLF_REQUIRE(weight_scale > 0.f, "pack_conv_weight_split: weight_scale must be positive");
+  MMLF_REQUIRE(spatial >= 0 && spatial <= 2, "pack_conv_weight_split: spatial must be 0..2");
+  MMLF_REQUIRE(in_groups >= 1 && group_real >= 1 && group_pad >= group_real && in_groups * group_real == cin,
+               "pack_conv_weight_split: bad channel groups");
+  MMLF_REQUIRE(n_pad % 16 == 0 && cin_pad % 16 == 0 && n_pad >= cout && cin_pad >= in_groups * group_pad,
+               "pack_conv_weight_split: bad pads");
+  const int n_kc = ceil_div(cin_pad, 64);
+  const int64_t total = static_cast<int64_t>(n_pad) * 4 * 3 * n_kc * 64;
+  pack_conv_weight_kernel<<<static_cast<unsigned>(ceil_div64(total, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, cout, cin, spatial, 0, in_groups, group_real, group_pad, reinterpret_cast<uint16_t*>(out), n_pad, n_kc, kFP16, 1, weight_scale);
+  return check_launch("pack_conv_weight_kernel(split)");
 }
 
 extern "C" int mmlf_unpack_conv_wgrad(const float* dw_packed, int n_pad, int cin_pad, int cout, int cin, int spatial,

@@ -18,6 +18,7 @@ from ._lib import BF16, FP16, ConvArgs, call
 
 _TORCH_DT = {BF16: torch.bfloat16, FP16: torch.float16}
 GRAD = BF16      # gradients are always bf16 (fp32 exponent range)
+SPLIT_WSCALE = 64.0   # split precision: weights are packed as w * 64 so that their fp16 residuals stay normal numbers
 
 
 def pad16(x):
@@ -57,6 +58,8 @@ class ConvSpec:
         self.cin_pad = groups * self.group_pad if groups > 1 else pad16(cin)
         self.n_pad = pad16(cout)
         self.w_fwd = None                     # bf16 [n_pad][4*kc*64]
+        self.w_split = None                   # fp16 [n_pad][4*3*kc*64] (split-precision inference)
+        self.unscale = None                   # f32 [n_pad] = 1 / SPLIT_WSCALE
         self.w_dgrad = None                   # bf16 [cin_pad][4*kc'*64]
         self.bias_pad = None                  # f32 [n_pad]
 
@@ -95,8 +98,15 @@ class Engine:
 
     @property
     def act(self):
-        """Storage format of forward activations and weights ('fp16' default, 'bf16' optional)."""
-        return FP16 if getattr(self.m, 'precision', 'fp16') == 'fp16' else BF16
+        """Storage format of forward activations and weights ('fp16' default, 'bf16' optional, 'split' = fp16 hi + lo)."""
+        return BF16 if getattr(self.m, 'precision', 'fp16') == 'bf16' else FP16
+
+    @property
+    def split(self):
+        """Split-precision inference (``model.precision = 'split'``): every activation and weight is carried as
+        fp16 hi + fp16 lo and every product as hi*hi + hi*lo + lo*hi in the fp32 accumulator -- fp32-class results on the
+        fp16 tensor cores at three times the MMA work.  Eval / no-grad only."""
+        return getattr(self.m, 'precision', 'fp16') == 'split'
 
     # ------------------------------------------------------------------ static plan
     def _build_specs(self):
@@ -162,7 +172,8 @@ class Engine:
     def repack(self, need_dgrad):
         """(Re)build the packed bf16 operands when the canonical fp32 parameters changed."""
         params = self._params()
-        version = tuple(p._version for p in params.values()) + tuple(p.data_ptr() for p in params.values()) + (self.act,)
+        version = tuple(p._version for p in params.values()) + tuple(p.data_ptr() for p in params.values()) + \
+            (self.act, self.split)
         if self._pack_version is not None and self._pack_version[0] == version and \
                 (self._pack_version[1] or not need_dgrad):
             return
@@ -175,6 +186,12 @@ class Engine:
             if cs.w_fwd is None:
                 cs.w_fwd = torch.empty((cs.n_pad, 4 * kc * 64), dtype=torch.int16, device=dev)
                 cs.bias_pad = torch.zeros(cs.n_pad, dtype=torch.float32, device=dev)
+            if self.split:
+                if cs.w_split is None:
+                    cs.w_split = torch.empty((cs.n_pad, 4 * 3 * kc * 64), dtype=torch.int16, device=dev)
+                    cs.unscale = torch.full((cs.n_pad,), 1.0 / SPLIT_WSCALE, dtype=torch.float32, device=dev)
+                call('mmlf_pack_conv_weight_split', _ptr(w), cs.cout, cs.cin, cs.spatial, cs.groups, cs.group_real,
+                     cs.group_pad, _ptr(cs.w_split), cs.n_pad, cs.cin_pad, SPLIT_WSCALE, st)
             call('mmlf_pack_conv_weight', _ptr(w), cs.cout, cs.cin, cs.spatial, 0, cs.groups, cs.group_real,
                  cs.group_pad, _ptr(cs.w_fwd), cs.n_pad, cs.cin_pad, self.act, st)
             cs.bias_pad[:cs.cout].copy_(b)
@@ -201,7 +218,7 @@ class Engine:
     # ------------------------------------------------------------------ kernel launch helpers
     def conv(self, geo, x, ld_in, cs, w, n_pad, cin_pad, ctype, out, ld_out, *, bias=None, scale=None, shift=None,
              relu=False, gate_bits=None, relu_bits=None, out_mode=0, n_real=0, simt=False, ab=None, out_dt=None,
-             out2=None, ld_out2=0, out2_dt=None, col_sums=None):
+             out2=None, ld_out2=0, out2_dt=None, col_sums=None, split_in=0, split_out=0):
         a = ConvArgs()
         a.ab_dtype = self.act if ab is None else ab
         a.out_dtype = self.act if out_dt is None else out_dt
@@ -220,6 +237,7 @@ class Engine:
         a.out2 = out2.data_ptr() if out2 is not None else None
         a.ld_out2 = ld_out2
         a.col_sums = col_sums.data_ptr() if col_sums is not None else None
+        a.split_in, a.split_out = split_in, split_out
         call('mmlf_conv2x2_simt' if simt else 'mmlf_conv2x2', C.byref(a), _stream())
 
     def _slots(self, geo, ch, dtype=None):
@@ -244,6 +262,10 @@ class Engine:
         produces it -- tcgen05 kind::f16 needs both operands of the weight-gradient GEMM in one format -- and the
         fp16 copies are dropped as soon as the next layer has consumed them."""
         _lib.require_device()
+        if self.split:
+            if save or training:
+                raise RuntimeError("precision='split' is an inference mode (model.eval(), torch.no_grad())")
+            return self._forward_split(views, shift_disp), None
         h = views[0]
         B, n, c3, H, W = h.shape
         self.dev = h.device
@@ -323,6 +345,78 @@ class Engine:
         if save:
             tape['head'] = {'xg': xg, 'ld_x': ld_x, 'mid': mid if self.small_head else None, 'midg': midg, 'bits': bits}
         return out, tape
+
+    def _forward_split(self, views, shift_disp=None):
+        """Eval-mode forward in split precision.  Slot arrays hold [hi | lo] blocks: an array of C channels has pitch
+        2 * C with hi in columns [0, C) and lo in [C, 2 C)."""
+        if shift_disp is not None:                      # ESE member: resample in fp32 first (bit-exact Shift kernel)
+            from . import ops
+            full = list(views) + [views[0]] * (4 - len(views))
+            views = ops.lf_shift(*full, float(shift_disp))[:len(views)]
+        h = views[0]
+        B, n, c3, H, W = h.shape
+        self.dev = h.device
+        geo = Geometry(B, H, W)
+        st = _stream()
+        self.repack(need_dgrad=False)
+        bufs, params = self._buffers(), self._params()
+        cin0_pad = pad16(n * c3)
+        half = torch.float16
+
+        def slots2(ch):
+            return torch.empty((geo.n_slots, 2 * ch), dtype=half, device=self.dev)
+
+        def block(x, ld_x, lo_x, c1, c2, bnp, y, ld_y, lo_y):
+            a1 = slots2(c1.n_pad)
+            self.conv(geo, x, ld_x, c1, c1.w_split, c1.n_pad, c1.cin_pad, 0, a1, 2 * c1.n_pad, scale=c1.unscale,
+                      shift=c1.bias_pad, relu=True, ab=FP16, out_dt=FP16, split_in=lo_x, split_out=c1.n_pad)
+            if self.has_bn:
+                gamma, beta = params[bnp + '.weight'].detach(), params[bnp + '.bias'].detach()
+                scale, shift = self._eval_fold(bnp, c2, gamma, beta, bufs[bnp + '.running_mean'], bufs[bnp + '.running_var'])
+                self.conv(geo, a1, 2 * c1.n_pad, c2, c2.w_split, c2.n_pad, c2.cin_pad, 1, y, ld_y,
+                          scale=scale * (1.0 / SPLIT_WSCALE), shift=shift, relu=True, ab=FP16, out_dt=FP16,
+                          split_in=c1.n_pad, split_out=lo_y)
+            else:
+                self.conv(geo, a1, 2 * c1.n_pad, c2, c2.w_split, c2.n_pad, c2.cin_pad, 1, y, ld_y, scale=c2.unscale,
+                          shift=c2.bias_pad, relu=True, ab=FP16, out_dt=FP16, split_in=c1.n_pad, split_out=lo_y)
+
+        feats = slots2(self.feat_ld)                    # hi blocks of the streams in [0, feat_ld), lo blocks behind
+        for si, (key, net, spatial) in enumerate(self.stream_defs):
+            v = views[si]
+            assert v.is_cuda and v.dtype == torch.float32 and v.is_contiguous()
+            x = slots2(cin0_pad)
+            call('mmlf_pack_views_split', _ptr(v), B, n * c3, H, W, _ptr(x), 2 * cin0_pad, cin0_pad, st)
+            ld_x, lo_x = 2 * cin0_pad, cin0_pad
+            blocks = self.in_specs[key]
+            for k, (c1, c2, bnp) in enumerate(blocks):
+                if k == len(blocks) - 1:
+                    y, ld_y, lo_y = feats[:, si * self.cp:], 2 * self.feat_ld, self.feat_ld
+                else:
+                    y, ld_y, lo_y = slots2(c2.n_pad), 2 * c2.n_pad, c2.n_pad
+                block(x, ld_x, lo_x, c1, c2, bnp, y, ld_y, lo_y)
+                x, ld_x, lo_x = y, ld_y, lo_y
+        x, ld_x, lo_x = feats, 2 * self.feat_ld, self.feat_ld
+        for c1, c2, bnp in self.out_specs:
+            y = slots2(c2.n_pad)
+            block(x, ld_x, lo_x, c1, c2, bnp, y, 2 * c2.n_pad, c2.n_pad)
+            x, ld_x, lo_x = y, 2 * c2.n_pad, c2.n_pad
+        h1 = self.head1
+        out = torch.empty((B, self.oc, H, W), dtype=torch.float32, device=self.dev)
+        if self.small_head:
+            mid = self._slots(geo, h1.n_pad, torch.float32)
+            self.conv(geo, x, ld_x, h1, h1.w_split, h1.n_pad, h1.cin_pad, 0, mid, h1.n_pad, scale=h1.unscale,
+                      shift=h1.bias_pad, relu=True, out_mode=1, ab=FP16, split_in=lo_x)
+            w2 = params[self.head2.name + '.weight'].detach()
+            b2 = params[self.head2.name + '.bias'].detach()
+            call('mmlf_head_small', _ptr(mid), h1.n_pad, self.oc, _ptr(w2), _ptr(b2), B, H, W, _ptr(out), st)
+        else:
+            h2 = self.head2
+            mid = slots2(h1.n_pad)
+            self.conv(geo, x, ld_x, h1, h1.w_split, h1.n_pad, h1.cin_pad, 0, mid, 2 * h1.n_pad, scale=h1.unscale,
+                      shift=h1.bias_pad, relu=True, ab=FP16, out_dt=FP16, split_in=lo_x, split_out=h1.n_pad)
+            self.conv(geo, mid, 2 * h1.n_pad, h2, h2.w_split, h2.n_pad, h2.cin_pad, 1, out, 0, scale=h2.unscale,
+                      shift=h2.bias_pad, out_mode=2, n_real=self.oc, ab=FP16, split_in=h1.n_pad)
+        return out
 
     def _block_fwd(self, geo, x, xg, ld_x, c1, c2, bnp, y, yg, ld_y, training, bn_train, save, bufs, params):
         """conv(k2,p1) -> ReLU -> conv(k2,p0) [-> BN] -> ReLU   (feed_forward.py:122-137).  x / y are the block input

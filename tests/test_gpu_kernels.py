@@ -147,6 +147,53 @@ def _conv_case(B, H, W, cin, cout, ctype, seed, simt, relu=True, mode=0, with_bn
         np.testing.assert_allclose(got, want, rtol=2e-4, atol=2e-4)
 
 
+@pytest.mark.parametrize('case', [(2, 12, 12, 27, 70, 0), (1, 20, 24, 280, 280, 1), (2, 9, 11, 70, 70, 1),
+                                  (1, 16, 16, 280, 108, 0)])
+def test_conv_split_precision(case):
+    """Split-precision conv (hi*hi + hi*lo + lo*hi on the fp16 tensor cores, fp32 accumulate): fp32-class agreement with
+    a float64 convolution of the fp32 operands, and the hi / lo outputs re-assemble the fp32 result."""
+    u = _u()
+    B, H, W, cin, cout, ctype = case
+    rng = np.random.RandomState(11)
+    Hp, Wp = H + 1, W + 1
+    cin_pad, n_pad = u.pad16(cin), u.pad16(cout)
+    w = (rng.normal(0, 1, (cout, cin, 2, 2)) / np.sqrt(4 * cin)).astype(np.float32)
+    b = rng.normal(0, 0.1, cout).astype(np.float32)
+    x = rng.normal(0, 1, (B, H, W, cin) if ctype == 0 else (B, Hp, Wp, cin)).astype(np.float32)
+    want = np.maximum(conv2x2(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), 1 if ctype == 0 else 0), 0)
+    hi = u.ROUND[u.FP16](x)
+    lo = u.ROUND[u.FP16](x - hi)
+    xs = torch.cat([u.to_slots(hi, cin_pad, ctype == 1, Hp, Wp, u.FP16), u.to_slots(lo, cin_pad, ctype == 1, Hp, Wp, u.FP16)], 1)
+    kc = (cin_pad + 63) // 64
+    wp = torch.empty((n_pad, 4 * 3 * kc * 64), dtype=torch.float16, device='cuda')
+    u.call('mmlf_pack_conv_weight_split', u.ptr(torch.from_numpy(w).cuda()), cout, cin, 0, 1, cin, cin_pad, u.ptr(wp), n_pad,
+           cin_pad, 64.0, u.stream())
+    bias = torch.zeros(n_pad, device='cuda')
+    bias[:cout] = torch.from_numpy(b)
+    unscale = torch.full((n_pad,), 1.0 / 64.0, device='cuda')
+    n_slots = B * Hp * Wp
+    out = torch.full((n_slots, 2 * n_pad), float('nan'), dtype=torch.float16, device='cuda')
+    a = u.ConvArgs()
+    a.in_, a.ld_in, a.cin_pad, a.wpack, a.n_pad = xs.data_ptr(), 2 * cin_pad, cin_pad, wp.data_ptr(), n_pad
+    a.B, a.H, a.W, a.type = B, H, W, ctype
+    a.scale, a.shift, a.relu = unscale.data_ptr(), bias.data_ptr(), 1
+    a.out, a.ld_out, a.out_mode = out.data_ptr(), 2 * n_pad, 0
+    a.ab_dtype, a.out_dtype, a.out2_dtype = u.FP16, u.FP16, u.FP16
+    a.split_in, a.split_out = cin_pad, n_pad
+    u.call('mmlf_conv2x2', u.C.byref(a), u.stream())
+    torch.cuda.synchronize()
+    full = out.float().cpu().numpy().reshape(B, Hp, Wp, 2, n_pad)
+    assert np.isfinite(full).all()
+    got = full[..., 0, :] + full[..., 1, :]                  # hi + lo
+    got = got[..., :cout] if ctype == 0 else got[:, 1:, 1:, :cout]
+    err = np.abs(got - want).max() / np.abs(want).max()
+    # measured 2e-7 (K = 108) ... 5.6e-6 (K = 1120): what is left is the tensor cores' fp32 accumulation, which truncates
+    # each of the K / 16 additions instead of rounding to nearest; the plain fp16 path is at ~5e-4 on the same data
+    assert err < 1e-5, err
+    if ctype == 1:
+        assert not full[:, 0].any() and not full[:, :, 0].any(), 'halo slots must be zero'
+
+
 CONV_CASES = [
     # B, H, W, cin, cout, type
     (2, 12, 12, 27, 70, 0), (2, 12, 12, 70, 70, 1), (1, 20, 24, 280, 280, 0), (1, 20, 24, 280, 280, 1),
