@@ -25,6 +25,12 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np  # noqa: E402
 
 ESE_MEMBERS = 70
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the ncu --set full capture
+# profiles/ncu_conv280_r01d.txt (not measurable inside an un-profiled run)
+CONV_TRAFFIC = {'bytes': 652835328,
+                'note': 'ncu capture profiles/ncu_conv280_r01d.txt: conv2x2_tc2 280->280 pad 0 on 64x96x96 patches, 347.7 MB '
+                        'read + 305.2 MB written per launch against 693.7 MB algorithmic (activations in + out; the 663 KB '
+                        'weight operand stays in L2)'}
 FULL_KW = dict(model_ksize=2, model_in_blocks=3, model_out_blocks=8, model_chs=70, model_views=9, model_cross=False,
                model_uncert=False, model_unet=False, model_discrete=False, model_no_batchnorm=False,
                model_batchnorm_momentum=0.1, val_disp_min=-3.5, val_disp_max=3.5)
@@ -433,7 +439,8 @@ def main():
     achieved = conv_flops_rank / conv_time / 1e12 if conv_time > 0 else 0.0
     roofline = {'kernel': 'conv2x2_tc_kernel (all forward + data-gradient launches of a step)', 'bound': 'tensor',
                 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
-                'peak_source': peak_src, 'traffic': None, 'launches_per_step': n_conv,
+                'peak_source': peak_src, 'traffic': CONV_TRAFFIC['bytes'], 'traffic_note': CONV_TRAFFIC['note'],
+                'launches_per_step': n_conv,
                 'avg_launch_ms': (sum(conv_ms) / len(conv_ms)) if conv_ms else None,
                 'share_of_step': conv_time * 1e3 / kernel_sum_ms}
     roofline['note'] = ('value: product path (%s); kernel times: separate single-stream pass of %d step(s), CUDA events around '
