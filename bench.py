@@ -185,6 +185,12 @@ def cpu_ese_step(size, members, threads):
 def run_cpu(args, steps, warmup):
     """Times the oracle port on the host cores on a bounded sample of the workload."""
     threads = os.cpu_count() or 1
+    try:
+        # torchrun exports OMP_NUM_THREADS=1 before the interpreter starts; the CPU arm uses all host cores
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=threads)
+    except Exception:  # pragma: no cover
+        pass
     if args.workload == 'train':
         b = args.cpu_batch
         step = cpu_train_step(args.variant, b, args.ps, threads)

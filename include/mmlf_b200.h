@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MMLF_ABI_VERSION 3
+#define MMLF_ABI_VERSION 4
 
 /* 16-bit storage formats.  Forward activations and weights are fp16 (11 significant bits; the reference's own GPU
  * path multiplies in TF32, 11 bits), gradients are bf16 (fp32 exponent range); accumulation is always fp32. */
@@ -138,6 +138,18 @@ typedef struct mmlf_conv_args {
    * split_out != 0: out_mode 0 writes hi to `out` and lo to `out + split_out` elements (same pitch); out2 must be NULL. */
   int split_in;
   int split_out;
+  /* BatchNorm-backward statistics fused into a data-gradient launch (out_mode 0, col_sums required): the output of this
+   * launch is g = d loss / d y for y = relu(z * bn_scale + bn_shift), the output of a training-mode BatchNorm whose
+   * pre-activation z (16-bit [n_slots][ld_z], format bn_z_dtype) the forward pass kept.  With m = (z * bn_scale +
+   * bn_shift > 0), col_sums then receives  [0][c] += sum_slots g*m  and  [1][c] += sum_slots g*m*(z - bn_mean)  over
+   * the stored (rounded) g -- exactly what mmlf_bn_bwd_reduce computes up to the factor invstd (mmlf_bn_bwd_apply with
+   * train = 2 applies it), without reading g and z again. */
+  const void* bn_z;      /* NULL = plain column sums                                                 */
+  int ld_z;
+  int bn_z_dtype;
+  const float* bn_scale; /* [n_pad] from mmlf_bn_finalize                                            */
+  const float* bn_shift;
+  const float* bn_mean;  /* [n_pad] save_mean                                                        */
 } mmlf_conv_args;
 
 /* 2x2 convolution as an implicit GEMM on tcgen05 (TMA-fed, TMEM accumulators, fused epilogue).  Forward of
@@ -197,7 +209,8 @@ int mmlf_bn_apply_relu(const void* z, int ld_z, const float* scale, const float*
 int mmlf_bn_bwd_reduce(const void* dy, int ld_dy, const void* z, int ld_z, const float* scale, const float* shift,
                        const float* save_mean, const float* save_invstd, int C, int B, int H, int W, int grad_dtype,
                        int act_dtype, double* sums, void* stream);
-/* Pass 2: dz = gamma * invstd * (g - sum_g / count - xhat * sum_gx / count) (16-bit, halo zero);
+/* Pass 2 (train = 2: sums[1] holds sum g*(z - mean) from a fused conv epilogue and is multiplied by invstd first):
+ * dz = gamma * invstd * (g - sum_g / count - xhat * sum_gx / count) (16-bit, halo zero);
  * dgamma = sum_gx, dbeta = sum_g (f32 [C_real]).  fsums: f32 scratch [2 * C].  train = 0 gives the eval-mode gradient
  * dz = g * gamma * invstd.  dz_colsum (optional, f32 [C]): += sum over slots of dz as stored = the bias gradient of
  * the convolution in front of the BatchNorm (feed_forward.py:125). */

@@ -25,7 +25,8 @@ class ConvArgs(C.Structure):
                 ('out', c_p), ('ld_out', c_i), ('out_mode', c_i), ('n_real', c_i),
                 ('out2', c_p), ('ld_out2', c_i), ('col_sums', c_p),
                 ('ab_dtype', c_i), ('out_dtype', c_i), ('out2_dtype', c_i),
-                ('split_in', c_i), ('split_out', c_i)]
+                ('split_in', c_i), ('split_out', c_i),
+                ('bn_z', c_p), ('ld_z', c_i), ('bn_z_dtype', c_i), ('bn_scale', c_p), ('bn_shift', c_p), ('bn_mean', c_p)]
 
 
 _PROTOS = {
@@ -69,7 +70,7 @@ _PROTOS = {
 }
 
 EXPORTS = tuple(_PROTOS)
-ABI_VERSION = 3
+ABI_VERSION = 4
 _lib = None
 
 

@@ -316,14 +316,17 @@ slot_map_kernel(const void* __restrict__ a, int ld_a, const void* __restrict__ y
 
 // per-channel means of the two backward reductions in fp32 (+ the parameter gradients dgamma = sum g*xhat, dbeta = sum g)
 __global__ void bn_bwd_means_kernel(const double* __restrict__ sums, double inv_count, int C_real, int C,
-                                    float* __restrict__ fsums, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                    float* __restrict__ fsums, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                    const float* __restrict__ invstd) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  // invstd != NULL: sums[1] holds sum g * (z - mean) (from the data-gradient conv epilogue); xhat = (z - mean) * invstd
+  const double sgx = invstd ? sums[C + c] * static_cast<double>(invstd[c]) : sums[C + c];
   fsums[c] = static_cast<float>(sums[c] * inv_count);
-  fsums[C + c] = static_cast<float>(sums[C + c] * inv_count);
+  fsums[C + c] = static_cast<float>(sgx * inv_count);
   if (c < C_real && dgamma && dbeta) {
     dbeta[c] = static_cast<float>(sums[c]);
-    dgamma[c] = static_cast<float>(sums[C + c]);
+    dgamma[c] = static_cast<float>(sgx);
   }
 }
 
@@ -466,7 +469,7 @@ extern "C" int mmlf_bn_bwd_apply(const void* dy, int ld_dy, const void* z, int l
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MMLF_REQUIRE(fsums != nullptr, "bn_bwd_apply: fsums scratch (float[2*C]) required");
   bn_bwd_means_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, 1.0 / static_cast<double>(count), C_real, C, fsums, dgamma,
-                                                         dbeta);
+                                                         dbeta, train == 2 ? save_invstd : nullptr);
   if (int rc = check_launch("bn_bwd_means")) return rc;
   const size_t smem = dz_colsum ? sizeof(float) * 256 * 8 : 0;
   if (train)

@@ -54,6 +54,11 @@ struct ConvParams {
   const uint32_t* gate_bits;
   uint32_t* relu_bits;
   double* col_sums;
+  const uint16_t* bn_z;                         // BatchNorm-backward statistics (kFBnBwd): pre-activation z of the BN layer
+  int ld_z, z_dtype;
+  const float* bn_scale;
+  const float* bn_shift;
+  const float* bn_mean;
   void* out;
   void* out2;
   long long* stats;                             // optional per-CTA cycle counters (debug): [grid][16]
@@ -155,6 +160,7 @@ enum : uint32_t {
   kFDirect = 256,   // out_mode 1 / 2: fp32 rows or planar fp32, written straight from registers
   kFGeneric = 512,
   kFSplit = 1024,   // second output = fp16 residual of the fp16 rounding of the first (split-precision inference)
+  kFBnBwd = 2048,   // column statistics are BatchNorm-backward sums (sum g*m, sum g*m*(z - mean)) instead of (sum, sum sq)
 };
 
 template <uint32_t F> struct Flags {
@@ -169,11 +175,13 @@ template <uint32_t F> struct Flags {
   __device__ __forceinline__ static bool out2_f16(const ConvParams& p) { return generic ? p.out2_dtype == kFP16 : (F & kFOut2F16) != 0; }
   __device__ __forceinline__ static bool direct(const ConvParams& p) { return generic ? p.out_mode != 0 : (F & kFDirect) != 0; }
   __device__ __forceinline__ static bool split(const ConvParams& p) { return generic ? p.split_out != 0 : (F & kFSplit) != 0; }
+  __device__ __forceinline__ static bool bnbwd(const ConvParams& p) { return generic ? p.bn_z != nullptr : (F & kFBnBwd) != 0; }
 };
 
 // One epilogue warp's context for the staged (out_mode 0) path
 struct EpiWarp {
   uint32_t stg_addr;        // shared address of this warp's staging rows: [1 + dual] x kSegBytes
+  uint32_t zstg_addr;       // staging rows of the BatchNorm pre-activation z (kFBnBwd), same layout
   float* s_stat;            // [2][n_pad] partial column sums of this warp's TMEM lane quadrant (or nullptr)
   const float* s_add;
   const float* s_mul;
@@ -187,6 +195,18 @@ __device__ __forceinline__ void epi_segment(const ConvParams& p, const EpiWarp& 
                                             int ncols, uint32_t gate_word, bool valid, int row0, int rows_valid,
                                             int lane) {
   using FL = Flags<F>;
+  // BatchNorm-backward statistics: this slot's z values of the segment (64 bytes), requested before anything else so that
+  // the loads overlap the epilogue math
+  uint4 zrow[4];
+  if (FL::bnbwd(p)) {
+    const int nch = ncols >> 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      zrow[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (j < nch && lane < rows_valid)
+        zrow[j] = __ldg(reinterpret_cast<const uint4*>(p.bn_z + (static_cast<int64_t>(row0) + lane) * p.ld_z + c0) + j);
+    }
+  }
   float x[32];
   {
     const float4* add4 = reinterpret_cast<const float4*>(w.s_add + c0);
@@ -257,6 +277,11 @@ __device__ __forceinline__ void epi_segment(const ConvParams& p, const EpiWarp& 
     for (int j = 0; j < 4; ++j)
       if (j < nch) sts128(row_addr + o * kSegBytes + ((j ^ sw) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
   }
+  if (FL::bnbwd(p)) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < nch) sts128(w.zstg_addr + lane * 64 + ((j ^ sw) << 4), zrow[j].x, zrow[j].y, zrow[j].z, zrow[j].w);
+  }
   __syncwarp();
   // write-out: 4 lanes cover the 64 staged bytes of one slot row, one store instruction covers 8 rows
 #pragma unroll
@@ -294,13 +319,33 @@ __device__ __forceinline__ void epi_segment(const ConvParams& p, const EpiWarp& 
       float s0 = 0.f, q0 = 0.f;
       const uint32_t col = w.stg_addr + (lane & 7) * 2;
       const uint32_t chunk = lane >> 3;
+      if (FL::bnbwd(p)) {
+        // BatchNorm-backward sums: the staged values are g = d loss / d y of y = relu(z * sc + sh); z of the same slots
+        // was staged next to them: accumulate g*m and g*m*(z - mean), m = (z * sc + sh > 0)
+        const int c = c0 + lane;
+        const float sc = __ldg(p.bn_scale + c), sh = __ldg(p.bn_shift + c), mu = __ldg(p.bn_mean + c);
+        const uint32_t zcol = w.zstg_addr + (lane & 7) * 2;
 #pragma unroll 8
-      for (int row = 0; row < 32; ++row) {
-        uint16_t v;
-        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(col + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)) : "memory");
-        const float f = FL::out_f16(p) ? __half2float(__ushort_as_half(v)) : __uint_as_float(static_cast<uint32_t>(v) << 16);
-        s0 += f;
-        q0 = fmaf(f, f, q0);
+        for (int row = 0; row < 32; ++row) {
+          const uint32_t off = row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4);
+          uint16_t v, zr;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(col + off) : "memory");
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(zr) : "r"(zcol + off) : "memory");
+          const float f = FL::out_f16(p) ? __half2float(__ushort_as_half(v)) : __uint_as_float(static_cast<uint32_t>(v) << 16);
+          const float zf = p.z_dtype == kFP16 ? __half2float(__ushort_as_half(zr)) : __uint_as_float(static_cast<uint32_t>(zr) << 16);
+          const float g = fmaf(zf, sc, sh) > 0.f ? f : 0.f;
+          s0 += g;
+          q0 = fmaf(g, zf - mu, q0);
+        }
+      } else {
+#pragma unroll 8
+        for (int row = 0; row < 32; ++row) {
+          uint16_t v;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(col + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)) : "memory");
+          const float f = FL::out_f16(p) ? __half2float(__ushort_as_half(v)) : __uint_as_float(static_cast<uint32_t>(v) << 16);
+          s0 += f;
+          q0 = fmaf(f, f, q0);
+        }
       }
       w.s_stat[c0 + lane] += s0;
       w.s_stat[p.n_pad + c0 + lane] += q0;
@@ -550,6 +595,7 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const int half = (warp - 2) >> 2;                    // 0: even segments of a tile, 1: odd segments
     EpiWarp w;
     w.stg_addr = tiles_addr + p.epi_off + (warp - 2) * (FL::dual(p) ? 2u : 1u) * kSegBytes;
+    w.zstg_addr = tiles_addr + p.epi_off + kEpiWarps * (FL::dual(p) ? 2u : 1u) * kSegBytes + (warp - 2) * kSegBytes;
     w.s_stat = (FL::stats(p) && p.stat_off) ? reinterpret_cast<float*>(smem + p.stat_off) + (warp - 2) * 2 * p.n_pad : nullptr;
     w.s_add = s_add;
     w.s_mul = s_mul;
@@ -788,6 +834,17 @@ static int fill_params(const mmlf_conv_args* a, ConvParams& p) {
   p.gate_bits = a->gate_bits;
   p.relu_bits = a->relu_bits;
   p.col_sums = a->col_sums;
+  p.bn_z = reinterpret_cast<const uint16_t*>(a->bn_z);
+  p.ld_z = a->ld_z;
+  p.z_dtype = a->bn_z_dtype;
+  p.bn_scale = a->bn_scale;
+  p.bn_shift = a->bn_shift;
+  p.bn_mean = a->bn_mean;
+  if (a->bn_z) {
+    MMLF_REQUIRE(a->col_sums && a->out_mode == 0, "conv2x2: bn_z needs col_sums and out_mode 0");
+    MMLF_REQUIRE(a->bn_scale && a->bn_shift && a->bn_mean, "conv2x2: bn_z needs bn_scale / bn_shift / bn_mean");
+    MMLF_REQUIRE(a->ld_z >= a->n_pad && (a->bn_z_dtype >> 1) == 0, "conv2x2: bad ld_z %d / bn_z_dtype", a->ld_z);
+  }
   p.out = a->out;
   p.out2 = a->out2;
   p.ld_out2 = a->ld_out2;
@@ -830,6 +887,7 @@ static const ConvVariant kConvVariants[] = {
     MMLF_CONV_VARIANT(kFStats),
     MMLF_CONV_VARIANT(0),                                          // data gradient
     MMLF_CONV_VARIANT(kFGate | kFStats),                           // data gradient through a ReLU + bias gradient
+    MMLF_CONV_VARIANT(kFStats | kFBnBwd),                          // data gradient + BatchNorm-backward statistics
     MMLF_CONV_VARIANT(kFDirect),                                   // heads (fp32 outputs)
     MMLF_CONV_VARIANT(kFGeneric),
 };
@@ -841,7 +899,7 @@ extern "C" int mmlf_conv2x2(const mmlf_conv_args* a, void* stream) {
   p.stats = g_conv_stats;
   const uint32_t stage_bytes = kABytes + 2u * p.n_pad * 64u;
   // shared-memory plan behind the operand stages: [epilogue staging | statistics | barriers + constants]
-  const uint32_t epi_bytes = p.out_mode == 0 ? kEpiWarps * (p.dual ? 2u : 1u) * kSegBytes : 0u;
+  const uint32_t epi_bytes = p.out_mode == 0 ? kEpiWarps * ((p.dual ? 2u : 1u) + (p.bn_z ? 1u : 0u)) * kSegBytes : 0u;
   const uint32_t stat_bytes = p.col_sums ? kEpiWarps * 2u * p.n_pad * 4u : 0u;   // per epilogue warp: [2][n_pad] f32
   const uint32_t aux_bytes = 256 + 2 * kMaxNPad * 4 + 64;   // barriers + TMEM pointer, then the per-channel constants
   const uint32_t tail_bytes = epi_bytes + ((stat_bytes + 15u) & ~15u) + aux_bytes;
@@ -879,7 +937,7 @@ extern "C" int mmlf_conv2x2(const mmlf_conv_args* a, void* stream) {
     mask = (p.has_scale ? kFScale : 0u) | (p.relu ? kFRelu : 0u) | (p.gate_bits ? kFGate : 0u) |
            (p.relu_bits ? kFBits : 0u) | (p.dual ? kFDual : 0u) | (p.col_sums ? kFStats : 0u) |
            (p.out_dtype == kFP16 ? kFOutF16 : 0u) | (p.dual && p.out2_dtype == kFP16 ? kFOut2F16 : 0u) |
-           (p.split_out ? kFSplit : 0u);
+           (p.split_out ? kFSplit : 0u) | (p.bn_z ? kFBnBwd : 0u);
   }
   ConvKernel fn = kConvVariants[kNumConvVariants - 1].fn;
   for (int i = 0; i < kNumConvVariants - 1; ++i)
@@ -897,7 +955,7 @@ extern "C" int mmlf_conv2x2_simt(const mmlf_conv_args* a, void* stream) {
   ConvParams p;
   if (int rc = fill_params(a, p)) return rc;
   MMLF_REQUIRE(!(a->out2 || a->relu_bits || a->col_sums), "conv2x2_simt: out2 / relu_bits / col_sums are not supported");
-  MMLF_REQUIRE(!(a->split_in || a->split_out), "conv2x2_simt: split precision is not supported");
+  MMLF_REQUIRE(!(a->split_in || a->split_out || a->bn_z), "conv2x2_simt: split precision / BN statistics are not supported");
   const int64_t total = p.n_slots * (p.n_pad / 16);
   const int threads = 128;
   const int64_t blocks = ceil_div64(total, threads);

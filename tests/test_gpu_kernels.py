@@ -194,6 +194,51 @@ def test_conv_split_precision(case):
         assert not full[:, 0].any() and not full[:, :, 0].any(), 'halo slots must be zero'
 
 
+@pytest.mark.parametrize('case', [(2, 12, 12, 280, 280, 1), (3, 9, 11, 70, 70, 1), (1, 20, 24, 280, 280, 0)])
+def test_conv_fused_bn_backward_statistics(case):
+    """Data-gradient launch with fused BatchNorm-backward statistics == mmlf_bn_bwd_reduce on the stored gradient."""
+    u = _u()
+    B, H, W, cin, cout, ctype = case
+    rng = np.random.RandomState(5)
+    Hp, Wp = H + 1, W + 1
+    cin_pad, n_pad = u.pad16(cin), u.pad16(cout)
+    n_slots = B * Hp * Wp
+    w = (rng.normal(0, 1, (cout, cin, 2, 2)) / np.sqrt(4 * cin)).astype(np.float32)
+    x = rng.normal(0, 1, (B, H, W, cin) if ctype == 0 else (B, Hp, Wp, cin)).astype(np.float32)
+    xs = u.to_slots(x, cin_pad, ctype == 1, Hp, Wp, u.BF16)
+    wp = u.pack_weight(w, dt=u.BF16)
+    z = (torch.randn((n_slots, n_pad), device='cuda') * 1.5 + 0.3).to(torch.float16)
+    scale = torch.zeros(n_pad, device='cuda')
+    shift = torch.zeros(n_pad, device='cuda')
+    mean = torch.zeros(n_pad, device='cuda')
+    invstd = torch.zeros(n_pad, device='cuda')
+    scale[:cout] = torch.from_numpy(rng.uniform(-1.5, 1.5, cout).astype(np.float32))
+    shift[:cout] = torch.from_numpy(rng.normal(0, 0.5, cout).astype(np.float32))
+    mean[:cout] = torch.from_numpy(rng.normal(0.3, 0.2, cout).astype(np.float32))
+    invstd[:cout] = torch.from_numpy(rng.uniform(0.5, 2.0, cout).astype(np.float32))
+    fused = torch.zeros(2 * n_pad, dtype=torch.float64, device='cuda')
+    out = torch.full((n_slots, n_pad), float('nan'), dtype=torch.bfloat16, device='cuda')
+    a = u.ConvArgs()
+    a.in_, a.ld_in, a.cin_pad, a.wpack, a.n_pad = xs.data_ptr(), cin_pad, cin_pad, wp.data_ptr(), n_pad
+    a.B, a.H, a.W, a.type = B, H, W, ctype
+    a.out, a.ld_out, a.out_mode = out.data_ptr(), n_pad, 0
+    a.col_sums = fused.data_ptr()
+    a.ab_dtype, a.out_dtype, a.out2_dtype = u.BF16, u.BF16, u.BF16
+    a.bn_z, a.ld_z, a.bn_z_dtype = z.data_ptr(), n_pad, u.FP16
+    a.bn_scale, a.bn_shift, a.bn_mean = scale.data_ptr(), shift.data_ptr(), mean.data_ptr()
+    u.call('mmlf_conv2x2', u.C.byref(a), u.stream())
+    # the plain data-gradient variant must produce the same gradient
+    plain = u.run_conv(xs, cin_pad, cin_pad, wp, n_pad, B, H, W, ctype, ab=u.BF16, out_dt=u.BF16)
+    assert torch.equal(out, plain)
+    want = torch.zeros(2 * n_pad, dtype=torch.float64, device='cuda')
+    u.call('mmlf_bn_bwd_reduce', u.ptr(out), n_pad, u.ptr(z), n_pad, u.ptr(scale), u.ptr(shift), u.ptr(mean), u.ptr(invstd),
+           n_pad, B, H, W, u.BF16, u.FP16, u.ptr(want), u.stream())
+    torch.cuda.synchronize()
+    f, wnt = fused.cpu().numpy().reshape(2, n_pad), want.cpu().numpy().reshape(2, n_pad)
+    np.testing.assert_allclose(f[0], wnt[0], rtol=2e-4, atol=2e-3)
+    np.testing.assert_allclose(f[1] * invstd.cpu().numpy(), wnt[1], rtol=2e-4, atol=4e-3)
+
+
 CONV_CASES = [
     # B, H, W, cin, cout, type
     (2, 12, 12, 27, 70, 0), (2, 12, 12, 70, 70, 1), (1, 20, 24, 280, 280, 0), (1, 20, 24, 280, 280, 1),

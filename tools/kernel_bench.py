@@ -88,7 +88,7 @@ class Bench:
         print(json.dumps(row), flush=True)
 
 
-def conv_case(bn, B, H, W, cin, cout, ctype, dt=FP16, relu=True, dual=False, bits=False, stats=False):
+def conv_case(bn, B, H, W, cin, cout, ctype, dt=FP16, relu=True, dual=False, bits=False, stats=False, bnbwd=False):
     n_slots = B * (H + 1) * (W + 1)
     cin_pad, n_pad = pad16(cin), pad16(cout)
     x = (torch.randn((n_slots, cin_pad), device=DEV) * 0.5).to(TD[dt])
@@ -100,7 +100,9 @@ def conv_case(bn, B, H, W, cin, cout, ctype, dt=FP16, relu=True, dual=False, bit
     out2 = torch.empty((n_slots, n_pad), dtype=torch.bfloat16, device=DEV) if dual else None
     rb = torch.empty((n_slots, (n_pad + 31) // 32), dtype=torch.int32, device=DEV) if bits else None
     bias = torch.zeros(n_pad, device=DEV)
-    sums = torch.zeros(2 * n_pad, dtype=torch.float64, device=DEV) if stats else None
+    sums = torch.zeros(2 * n_pad, dtype=torch.float64, device=DEV) if (stats or bnbwd) else None
+    zbn = torch.randn((n_slots, n_pad), device=DEV).to(torch.float16) if bnbwd else None
+    bnc = torch.rand((3, n_pad), device=DEV) if bnbwd else None
     a = ConvArgs()
     a.in_, a.ld_in, a.cin_pad, a.wpack, a.n_pad = x.data_ptr(), cin_pad, cin_pad, wp.data_ptr(), n_pad
     a.B, a.H, a.W, a.type = B, H, W, ctype
@@ -110,9 +112,12 @@ def conv_case(bn, B, H, W, cin, cout, ctype, dt=FP16, relu=True, dual=False, bit
     a.out, a.ld_out, a.out_mode = out.data_ptr(), n_pad, 0
     a.out2 = out2.data_ptr() if dual else None
     a.ld_out2 = n_pad
-    a.col_sums = sums.data_ptr() if stats else None
+    a.col_sums = sums.data_ptr() if sums is not None else None
+    if bnbwd:
+        a.bn_z, a.ld_z, a.bn_z_dtype = zbn.data_ptr(), n_pad, FP16
+        a.bn_scale, a.bn_shift, a.bn_mean = bnc[0].data_ptr(), bnc[1].data_ptr(), bnc[2].data_ptr()
     a.ab_dtype, a.out_dtype, a.out2_dtype = dt, dt, BF16
-    keep = (x, wp, out, out2, rb, bias, sums, w)
+    keep = (x, wp, out, out2, rb, bias, sums, w, zbn, bnc)
     m = n_slots if ctype == 0 else B * H * W
     flops = 2.0 * m * cout * 4 * cin
 
@@ -155,6 +160,9 @@ def main():
         'conv2x2 280->280 pad1 train': (Bt, ps, ps, 280, 280, 0, dict(dual=True, bits=True)),
         'conv2x2 280->280 pad0 train': (Bt, ps, ps, 280, 280, 1, dict(relu=False, stats=True)),
         'conv2x2 280->280 pad0 dgrad': (Bt, ps, ps, 280, 280, 1, dict(dt=BF16, relu=False)),
+        'conv2x2 280->280 pad0 dgrad + BN-bwd statistics': (Bt, ps, ps, 280, 280, 1, dict(dt=BF16, relu=False, bnbwd=True)),
+        'conv2x2 70->70 pad0 dgrad': (Bt, ps, ps, 70, 70, 1, dict(dt=BF16, relu=False)),
+        'conv2x2 70->70 pad0 dgrad + BN-bwd statistics': (Bt, ps, ps, 70, 70, 1, dict(dt=BF16, relu=False, bnbwd=True)),
         'conv2x2 70->70 pad1 train': (Bt, ps, ps, 70, 70, 0, dict(dual=True, bits=True)),
         'conv2x2 70->70 pad0 train': (Bt, ps, ps, 70, 70, 1, dict(relu=False, stats=True)),
         'conv2x2 27->70 pad1 train': (Bt, ps, ps, 27, 70, 0, dict(dual=True, bits=True)),
