@@ -55,6 +55,12 @@ int mmlf_lf_shift(const float* src_h, const float* src_v, const float* src_i, co
                   float* dst_v, float* dst_i, float* dst_d, int batch, int n, int H, int W, double disp,
                   void* stream);
 
+/* create_mask_texture (hci4d.py:38-69): mask[b][y][x] = (mean over 3 colours x wsize^2 zero-padded neighbours of
+ * |center[b][c][y+dy][x+dx] - center[b][c][y][x]| >= threshold) and (y, x) at least wsize / 2 away from the border.
+ * center: (B, 3, H, W) f32; mask: (B, H, W) int32; mae (optional): the mean-L1 map, (B, H, W) f32. */
+int mmlf_texture_mask(const float* center, int B, int H, int W, int wsize, double threshold, int32_t* mask, float* mae,
+                      void* stream);
+
 /* Host helper: the per-view taps of Shift (hci4d.py:934-938): weights rounded to f32, integer shifts.
  * All four arrays are HOST memory of length n. */
 int mmlf_shift_taps(double disp, int n, float* w0, float* w1, int* s0, int* s1);

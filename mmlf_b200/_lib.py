@@ -35,6 +35,7 @@ _PROTOS = {
     'mmlf_check_device': (c_i, []),
     'mmlf_lf_extract_u8': (c_i, [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
     'mmlf_lf_shift': (c_i, [c_p] * 8 + [c_i, c_i, c_i, c_i, c_d, c_p]),
+    'mmlf_texture_mask': (c_i, [c_p, c_i, c_i, c_i, c_i, c_d, c_p, c_p, c_p]),
     'mmlf_shift_taps': (c_i, [c_d, c_i, C.POINTER(c_f), C.POINTER(c_f), C.POINTER(c_i), C.POINTER(c_i)]),
     'mmlf_pack_views': (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p]),
     'mmlf_pack_views_split': (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p]),

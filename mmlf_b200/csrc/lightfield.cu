@@ -478,6 +478,50 @@ __global__ void __launch_bounds__(256) pack_views_vec_kernel(const PackParams p)
     *reinterpret_cast<uint4*>(p.out + slot_row * p.ld + threadIdx.x * 8) = make_uint4(0u, 0u, 0u, 0u);
 }
 
+// ------------------------------------------------------------------------------------------------ texture mask
+// create_mask_texture (hci4d.py:38-69): mean over 3 colours x wsize^2 zero-padded neighbours of |neighbour - centre|,
+// thresholded, with a margin of wsize / 2 masked out.  The reference materialises the unfolded (1, 3 * wsize^2, H * W)
+// tensor (1587 x the image for wsize 23); here one CTA stages a (32 + 2r) x (32 + 2r) x 3 tile in shared memory and
+// every thread walks its pixel's window from there.
+constexpr int kTexTile = 32;
+
+__global__ void __launch_bounds__(256) texture_mask_kernel(const float* __restrict__ center, int B, int H, int W,
+                                                            int wsize, float threshold, int32_t* __restrict__ mask,
+                                                            float* __restrict__ mae) {
+  extern __shared__ float tex_tile[];               // [3][T][T], T = kTexTile + 2r
+  const int r = wsize / 2, T = kTexTile + 2 * r;
+  const int b = blockIdx.z, y0 = blockIdx.y * kTexTile, x0 = blockIdx.x * kTexTile;
+  const float* img = center + static_cast<int64_t>(b) * 3 * H * W;
+  for (int i = threadIdx.x; i < 3 * T * T; i += blockDim.x) {
+    const int c = i / (T * T), rem = i - c * T * T;
+    const int ty = rem / T, tx = rem - ty * T;
+    const int y = y0 + ty - r, x = x0 + tx - r;
+    tex_tile[i] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(img + (static_cast<int64_t>(c) * H + y) * W + x) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kTexTile * kTexTile; i += blockDim.x) {
+    const int py = i / kTexTile, px = i - py * kTexTile;
+    const int y = y0 + py, x = x0 + px;
+    if (y >= H || x >= W) continue;
+    float acc = 0.f;
+    for (int c = 0; c < 3; ++c) {
+      const float* t = tex_tile + c * T * T;
+      const float ctr = t[(py + r) * T + px + r];
+      for (int dy = 0; dy < wsize; ++dy) {
+        const float* row = t + (py + dy) * T + px;
+        float racc = 0.f;
+        for (int dx = 0; dx < wsize; ++dx) racc += fabsf(row[dx] - ctr);
+        acc += racc;
+      }
+    }
+    const float m = acc / static_cast<float>(3 * wsize * wsize);
+    const bool inside = y >= r && y < H - r && x >= r && x < W - r;
+    const int64_t o = (static_cast<int64_t>(b) * H + y) * W + x;
+    mask[o] = (m >= threshold && inside) ? 1 : 0;
+    if (mae) mae[o] = m;
+  }
+}
+
 }  // namespace mmlf
 
 using namespace mmlf;
@@ -624,4 +668,23 @@ extern "C" int mmlf_shift_pack(const float* src, int stack, int B, int n, int H,
   MMLF_REQUIRE(stack >= 0 && stack < 4, "shift_pack: stack must be 0..3");
   MMLF_REQUIRE(n >= 1 && n <= 16, "shift_pack: n must be in [1, 16]");
   return launch_pack(src, B, n * 3, H, W, out, ld, dtype, 1, stack, n, disp, stream);
+}
+
+extern "C" int mmlf_texture_mask(const float* center, int B, int H, int W, int wsize, double threshold, int32_t* mask,
+                                 float* mae, void* stream) {
+  MMLF_REQUIRE(center && mask, "texture_mask: null buffer");
+  MMLF_REQUIRE(wsize >= 1 && (wsize & 1) && wsize <= 63, "texture_mask: wsize must be odd and <= 63");
+  MMLF_REQUIRE(B >= 1 && B <= 65535 && H >= 1 && W >= 1, "texture_mask: bad shape");
+  const int T = kTexTile + 2 * (wsize / 2);
+  const size_t smem = static_cast<size_t>(3) * T * T * sizeof(float);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(texture_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    MMLF_REQUIRE(e == cudaSuccess, "texture_mask: %s", cudaGetErrorString(e));
+    configured = smem;
+  }
+  dim3 grid(ceil_div(W, kTexTile), ceil_div(H, kTexTile), B);
+  texture_mask_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(center, B, H, W, wsize,
+                                                                              static_cast<float>(threshold), mask, mae);
+  return check_launch("texture_mask_kernel");
 }

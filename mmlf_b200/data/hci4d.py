@@ -1,6 +1,6 @@
 """Drop-in for the hot-path part of ``mmlf.data.hci4d`` (/root/reference/mmlf/data/hci4d.py): view-index
-extraction, ``Shift`` and ``RandomShift``.  Dataset scanning, PNG/PFM I/O and the CPU augmentation chain are out of
-scope."""
+extraction, ``Shift`` / ``RandomShift`` and the texture mask.  Dataset scanning, PNG/PFM I/O and the CPU augmentation
+chain are out of scope."""
 import math
 import random
 
@@ -20,6 +20,12 @@ def create_mask_margin(shape, margin=0):
         mask[..., :margin] = False
         mask[..., -margin:] = False
     return mask
+
+
+def create_mask_texture(center, wsize, threshold):
+    """hci4d.py:38-69 on the GPU: one smem-tiled stencil instead of a (1, 3 * wsize^2, H * W) unfold.  center: CUDA
+    tensor (B, 3, H, W); returns the int mask (B, H, W) with a margin of wsize // 2 zeroed."""
+    return ops.texture_mask(center, wsize, threshold)
 
 
 def view_indices(nviews=(9, 9)):

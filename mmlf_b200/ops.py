@@ -79,6 +79,19 @@ def _(h, v, i, d, disp):
     return [torch.empty_like(t) for t in (h, v, i, d)]
 
 
+def texture_mask(center, wsize, threshold, want_mae=False):
+    """center (B, 3, H, W) f32 -> int32 mask (B, H, W) [+ the windowed mean-L1 map]  (hci4d.py:38-69)."""
+    _lib.require_device()
+    center = _chk(center.contiguous(), torch.float32, 'center')
+    B, c3, H, W = center.shape
+    if c3 != 3:
+        raise RuntimeError('mmlf_b200: `center` must have 3 colour planes')
+    mask = torch.empty((B, H, W), dtype=torch.int32, device=center.device)
+    mae = torch.empty((B, H, W), dtype=torch.float32, device=center.device) if want_mae else None
+    call('mmlf_texture_mask', _p(center), B, H, W, int(wsize), float(threshold), _p(mask), _p(mae), _st())
+    return (mask, mae) if want_mae else mask
+
+
 # ----------------------------------------------------------------------------------------- heads
 @torch.library.custom_op('mmlf::upr_posterior', mutates_args=())
 def upr_posterior(mean: torch.Tensor, logvar: torch.Tensor, bins: torch.Tensor) -> torch.Tensor:

@@ -15,7 +15,8 @@ oracle is pinned against outputs of the reference itself, generated in the
 build container by ``oracle/gen_golden.py`` (imports ``/root/reference``) and
 committed under ``tests/golden/``; ``tests/test_oracle_golden.py`` replays them.
 """
-from .lf import view_indices, extract_stacks, shift, shift_taps, ese_shift_values  # noqa: F401
+from .lf import (view_indices, extract_stacks, shift, shift_taps, ese_shift_values,  # noqa: F401
+                 texture_mae, create_mask_texture)
 from .net import (FeedForwardOracle, torch_linspace_f32, np_linspace_f32,  # noqa: F401
                   bf16_round, fp16_round, laplacian)
 from .losses import (create_mask_margin, reg_to_class, mpi_to_weights, class_to_reg,  # noqa: F401

@@ -313,7 +313,31 @@ def gen_checkpoint():
     save('ref_checkpoint_tiny_out.npz', mean=o['mean'].numpy(), logvar=o['logvar'].numpy())
 
 
+# ---------------------------------------------------------------------------- f2
+def gen_texture():
+    """create_mask_texture (hci4d.py:38-69) on synthetic centre views with flat and textured regions; the windowed
+    mean-L1 map is stored too (same torch ops as the reference, before the threshold) so that the parity tests can
+    exclude pixels whose mean sits within float round-off of the threshold."""
+    rng = np.random.RandomState(17)
+    res = {}
+    for tag, (b, H, W, ws, thr) in {'a': (1, 48, 64, 23, 0.02), 'b': (2, 40, 40, 7, 0.05)}.items():
+        yy, xx = np.meshgrid(np.arange(H), np.arange(W), indexing='ij')
+        c = np.zeros((b, 3, H, W), np.float32)
+        for bi in range(b):
+            for ch in range(3):
+                tex = 0.5 + 0.3 * np.sin(0.9 * xx + ch) * np.cos(0.7 * yy + bi)
+                amp = np.clip((xx - W * 0.3) / (W * 0.5), 0, 1)          # flat on the left, textured on the right
+                c[bi, ch] = 0.4 + amp * (tex - 0.4) + rng.normal(0, 0.004, (H, W))
+        ct = T(c)
+        mask = hci4d.create_mask_texture(ct, ws, thr)
+        unf = torch.nn.functional.unfold(ct, kernel_size=ws, padding=ws // 2).view(b, 3, -1, H, W)
+        mae = torch.abs(unf - ct.unsqueeze(2)).mean((1, 2))
+        res.update({f'{tag}/center': c, f'{tag}/mask': mask.numpy().astype(np.int32), f'{tag}/mae': mae.numpy(),
+                    f'{tag}/wsize': np.array(ws), f'{tag}/threshold': np.array(thr)})
+    save('texture_mask.npz', **res)
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['indices', 'shift', 'bins', 'net', 'losses', 'ese', 'adam', 'checkpoint']
+    which = sys.argv[1:] or ['indices', 'shift', 'bins', 'net', 'losses', 'ese', 'adam', 'checkpoint', 'texture']
     for w in which:
         globals()['gen_' + w]()

@@ -4,6 +4,7 @@ Restates, with explicit index arithmetic instead of slice/concatenate:
   * view-index extraction        /root/reference/mmlf/data/hci4d.py:142-193
   * Shift.__call__               /root/reference/mmlf/data/hci4d.py:907-990
   * the ESE shift sweep values   /root/reference/mmlf/model/ensamble.py:61-62
+  * create_mask_texture          /root/reference/mmlf/data/hci4d.py:38-69
 """
 import math
 
@@ -117,3 +118,30 @@ def ese_shift_values(disp_min, disp_max, disp_step):
     """ensamble.py:61-62: the members are ``np.arange`` values in float64, with
     its round-off (member 35 of the default sweep is 3.1e-15, not 0)."""
     return [float(v) for v in np.arange(disp_min, disp_max, disp_step)]
+
+
+def texture_mae(center, wsize):
+    """hci4d.py:53-58: mean over the 3 colours and the wsize x wsize window (zero padded: ``unfold(padding=wsize//2)``)
+    of |neighbour - centre pixel|.  center (B, 3, H, W) float32 -> (B, H, W) float32 (accumulated in float64)."""
+    B, C, H, W = center.shape
+    r = wsize // 2
+    pad = np.zeros((B, C, H + 2 * r, W + 2 * r), np.float64)
+    pad[:, :, r:r + H, r:r + W] = center
+    acc = np.zeros((B, H, W), np.float64)
+    c64 = center.astype(np.float64)
+    for dy in range(wsize):
+        for dx in range(wsize):
+            acc += np.abs(pad[:, :, dy:dy + H, dx:dx + W] - c64).sum(1)
+    return (acc / (C * wsize * wsize)).astype(np.float32)
+
+
+def create_mask_texture(center, wsize, threshold):
+    """hci4d.py:38-69: (mean L1 >= threshold) with a margin of wsize // 2 masked out; int32 (B, H, W)."""
+    mask = (texture_mae(center, wsize) >= np.float32(threshold)).astype(np.int32)
+    r = wsize // 2
+    if r > 0:
+        mask[..., :r, :] = 0
+        mask[..., -r:, :] = 0
+        mask[..., :r] = 0
+        mask[..., -r:] = 0
+    return mask

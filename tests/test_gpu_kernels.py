@@ -58,6 +58,27 @@ def test_lf_shift_golden(golden):
         assert np.array_equal(res[6].cpu().numpy(), g[f'mpi{j}'])
 
 
+def test_texture_mask(golden):
+    from mmlf_b200 import ops
+    from mmlf_b200.data import hci4d
+    g = golden('texture_mask.npz')
+    for tag in ('a', 'b'):
+        c, ws, thr = g[f'{tag}/center'], int(g[f'{tag}/wsize']), float(g[f'{tag}/threshold'])
+        mask, mae = ops.texture_mask(torch.from_numpy(c).cuda(), ws, thr, want_mae=True)
+        np.testing.assert_allclose(mae.cpu().numpy(), g[f'{tag}/mae'], rtol=3e-6, atol=1e-8)
+        sure = np.abs(g[f'{tag}/mae'] - np.float32(thr)) > 1e-6
+        assert np.array_equal(mask.cpu().numpy()[sure], g[f'{tag}/mask'][sure])
+        assert np.array_equal(hci4d.create_mask_texture(torch.from_numpy(c).cuda(), ws, thr).cpu().numpy(), mask.cpu().numpy())
+    # full-size image, window 23 (the load_scene call, hci4d.py:241): oracle on a crop
+    rng = np.random.RandomState(3)
+    big = rng.uniform(0, 1, (1, 3, 512, 512)).astype(np.float32)
+    big[..., :200] = 0.5 + 0.01 * big[..., :200]
+    mask, mae = ops.texture_mask(torch.from_numpy(big).cuda(), 23, 0.02, want_mae=True)
+    want = oracle.texture_mae(big[..., 100:180, 150:260], 23)
+    np.testing.assert_allclose(mae.cpu().numpy()[0, 111:169, 161:249], want[0, 11:-11, 11:-11], rtol=3e-6)
+    assert not mask[0, :11].any() and not mask[0, :, -11:].any() and mask[0, 11:-11, 300:-11].all()
+
+
 def test_pack_views_and_shift_pack():
     u = _u()
     rng = np.random.RandomState(2)
