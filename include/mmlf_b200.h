@@ -299,6 +299,46 @@ int mmlf_ese_reduce(const float* means, const float* logvars, const float* disp,
 int mmlf_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
                    double eps, int64_t step, void* stream);
 
+/* ------------------------------------------------------------------ training augmentation chain */
+/* RandomDownSampling -> RandomShift -> RandomCrop(ps + 16) -> CenterCrop(ps) -> RandomRotate -> RedistColor -> Brightness
+ * -> Contrast (train/cli.py:78-87; hci4d.py:483-530, 894-1028, 533-664, 1031-1087, 667-785) as gather kernels over
+ * scenes resident in HBM, with the per-sample random parameters drawn by the HOST (python `random`, same draw order as
+ * the reference) and passed explicitly. */
+typedef struct mmlf_aug_sample {
+  int scene;             /* index into the scene arrays                                                  */
+  int f;                 /* down-sampling factor (x[::f, ::f])                                           */
+  int cy, cx;            /* top-left of the final ps x ps patch in the down-sampled image (crop y + 8, x + 8) */
+  int r;                 /* number of 90-degree rotations, 0..3                                          */
+  int src[4];            /* output stack s (h, v, i, d) reads input stack src[s] ...                      */
+  int flip[4];           /* ... with the view order reversed if flip[s]   (Rotate90 swaps h<->v, i<->d)  */
+  float w0[16], w1[16];  /* Shift taps of view k in the down-sampled image (mmlf_shift_taps)              */
+  int s0[16], s1[16];
+  double mat[9];         /* RedistColor matrix, row major                                                */
+  float bright;          /* Brightness factor (float32 of the python float)                              */
+  float contrast;        /* Contrast factor                                                              */
+  float one_minus_contrast; /* float32(1.0 - alpha), alpha the python float                              */
+  float disp_f;          /* float32(disp): gt -= disp                                                    */
+  double disp;           /* mpi[:, 4] -= disp (float64 array in the reference)                           */
+} mmlf_aug_sample;
+
+/* Host helper: fills src / flip / the Shift taps of a sample from (r, disp, n). */
+int mmlf_augment_fill(mmlf_aug_sample* s, int r, double disp, int n);
+
+/* Scenes: stacks (S, 4, n, 3, H, W) f32 (h, v, i, d), center (S, 3, H, W) f32, gt (S, H, W) f32, mpi (S, K, 5, H, W) f32,
+ * mask (S, H, W) int32.  samples: DEVICE array of B mmlf_aug_sample.
+ * Outputs: views (4, B, n, 3, ps, ps) f32 and center (B, 3, ps, ps) f32 up to and including Brightness; view_sums
+ * (double[B], zeroed by the caller) receives the sum of the h stack of each sample (for Contrast's mean);
+ * gt (B, ps, ps) f32, mpi (B, K, 5, ps, ps) f32 (float64 arithmetic, rounded once), mask (B, ps, ps) int32 (cropped
+ * but, like in the reference, NOT rotated). */
+int mmlf_augment_patches(const float* stacks, const float* center, const float* gt, const float* mpi,
+                         const int32_t* mask, int S, int n, int K, int H, int W, const mmlf_aug_sample* samples, int B,
+                         int ps, float* out_views, float* out_center, double* view_sums, float* out_gt, float* out_mpi,
+                         int32_t* out_mask, void* stream);
+/* Contrast (hci4d.py:739-751): x * alpha + mean * (1 - alpha) in place on views and center; mean[b] = float32(
+ * view_sums[b] / (n * 3 * ps * ps)) unless mean_override (f32 [B], e.g. numpy's own pairwise float32 mean) is given. */
+int mmlf_augment_contrast(float* views, float* center, const mmlf_aug_sample* samples, const double* view_sums,
+                          const float* mean_override, int B, int n, int ps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

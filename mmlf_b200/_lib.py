@@ -36,6 +36,10 @@ _PROTOS = {
     'mmlf_lf_extract_u8': (c_i, [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
     'mmlf_lf_shift': (c_i, [c_p] * 8 + [c_i, c_i, c_i, c_i, c_d, c_p]),
     'mmlf_texture_mask': (c_i, [c_p, c_i, c_i, c_i, c_i, c_d, c_p, c_p, c_p]),
+    'mmlf_augment_fill': (c_i, [c_p, c_i, c_d, c_i]),
+    'mmlf_augment_patches': (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_p, c_p, c_p,
+                                   c_p, c_p, c_p]),
+    'mmlf_augment_contrast': (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p]),
     'mmlf_shift_taps': (c_i, [c_d, c_i, C.POINTER(c_f), C.POINTER(c_f), C.POINTER(c_i), C.POINTER(c_i)]),
     'mmlf_pack_views': (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p]),
     'mmlf_pack_views_split': (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p]),
@@ -95,7 +99,7 @@ def lib():
 
 
 # kernels launched per C-ABI call (for the launch count reported by bench.py)
-_KERNELS_PER_CALL = {'mmlf_pack_views_split': 2, 'mmlf_conv2x2_wgrad': 2, 'mmlf_bn_bwd_apply': 2, 'mmlf_head_small_bwd': 2, 'mmlf_shift_taps': 0}
+_KERNELS_PER_CALL = {'mmlf_augment_fill': 0, 'mmlf_augment_patches': 2, 'mmlf_pack_views_split': 2, 'mmlf_conv2x2_wgrad': 2, 'mmlf_bn_bwd_apply': 2, 'mmlf_head_small_bwd': 2, 'mmlf_shift_taps': 0}
 launch_count = 0
 _profile = None          # when set to a list, call() appends (name, start_event, end_event)
 

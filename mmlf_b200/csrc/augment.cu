@@ -1,0 +1,231 @@
+// Training augmentation chain on the GPU: the reference composes, per sample and on CPU workers,
+//   RandomDownSampling -> RandomShift -> RandomCrop(ps + 16) -> CenterCrop(ps) -> RandomRotate -> RedistColor ->
+//   Brightness -> Contrast        (/root/reference/mmlf/train/cli.py:78-87, /root/reference/mmlf/data/hci4d.py)
+// and ships 2 GB of float32 patches per 512-patch step to the GPU.  Here the scenes stay resident in HBM and one gather
+// kernel evaluates the whole chain per output pixel from explicit per-sample parameters (drawn on the host in the
+// reference's order), with the reference's arithmetic (NumPy >= 2 promotion: float32 lerps and scalings, float64
+// colour products rounded to float32 after every accumulation) -- bit exact up to Contrast's mean, which NumPy sums
+// pairwise in float32 and this file sums in float64.
+#include <math.h>
+
+#include "../../include/mmlf_b200.h"
+#include "common.cuh"
+#include "host_util.h"
+
+static_assert(sizeof(mmlf_aug_sample) == 408, "mmlf_aug_sample layout (mirrored by mmlf_b200/data/augment.py::AugSample)");
+
+namespace mmlf {
+
+__device__ __forceinline__ int aug_src_index(int j, int s, int n, int sign) {      // as Shift: python slice semantics
+  if (s == 0 || s >= n || -s >= n) return j;
+  int r = j - sign * s;
+  if (r < 0) r += n;
+  if (r >= n) r -= n;
+  return r;
+}
+__device__ __forceinline__ float aug_lerp2(float a, float w0, float b, float w1) {
+  return __fadd_rn(__fmul_rn(a, w0), __fmul_rn(b, w1));
+}
+// patch coordinates before `r` rotations: out[y][x] = in[T^r(y, x)], T(y, x) = (x, n - 1 - y)   (hci4d.py:1057-1060)
+__device__ __forceinline__ void aug_unrotate(int r, int n, int y, int x, int& Y, int& X) {
+  Y = y; X = x;
+  for (int i = 0; i < r; ++i) {
+    const int t = Y;
+    Y = X;
+    X = n - 1 - t;
+  }
+}
+
+// One thread = one pixel of one view (3 colours) of one output stack, or of the centre view (stack index 4).
+__global__ void __launch_bounds__(256)
+augment_views_kernel(const float* __restrict__ stacks, const float* __restrict__ center, int n, int H, int W,
+                     const mmlf_aug_sample* __restrict__ samples, int B, int ps, float* __restrict__ out_views,
+                     float* __restrict__ out_center, double* __restrict__ view_sums) {
+  const int b = blockIdx.y;
+  const mmlf_aug_sample& sp = samples[b];
+  const int per_stack = n * ps * ps;
+  const int total = 4 * per_stack + ps * ps;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  double hsum = 0.0;
+  if (idx < total) {
+    const int so = idx / per_stack;                       // 0..3 stacks, 4 = centre
+    int rem = idx - so * per_stack;
+    const int k = so < 4 ? rem / (ps * ps) : 0;
+    rem -= k * ps * ps;
+    const int y = rem / ps, x = rem - y * ps;
+    int Y, X;
+    aug_unrotate(sp.r, ps, y, x, Y, X);
+    const int f = sp.f;
+    const int Hd = (H + f - 1) / f, Wd = (W + f - 1) / f;
+    const int yy = sp.cy + Y, xx = sp.cx + X;             // in the down-sampled (and shifted) image
+    const int64_t plane = static_cast<int64_t>(H) * W;
+    float v[3];
+    if (so == 4) {
+      const float* src = center + static_cast<int64_t>(sp.scene) * 3 * plane;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[c] = __ldg(src + c * plane + static_cast<int64_t>(yy * f) * W + xx * f);
+    } else {
+      const int si = sp.src[so];
+      const int ki = sp.flip[so] ? n - 1 - k : k;
+      const float* src = stacks + ((static_cast<int64_t>(sp.scene) * 4 + si) * n + ki) * 3 * plane;
+      const float w0 = sp.w0[ki], w1 = sp.w1[ki];
+      const int s0 = sp.s0[ki], s1 = sp.s1[ki];
+      const bool has_w = si != 1, has_v = si != 0;
+      const int vsign = si == 2 ? -1 : +1;
+      const int r0 = has_v ? aug_src_index(yy, s0, Hd, vsign) : yy;
+      const int r1 = has_v ? aug_src_index(yy, s1, Hd, vsign) : yy;
+      const int c0 = has_w ? aug_src_index(xx, s0, Wd, +1) : xx;
+      const int c1 = has_w ? aug_src_index(xx, s1, Wd, +1) : xx;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float* pl = src + c * plane;
+        const float* ra = pl + static_cast<int64_t>(r0 * f) * W;
+        const float* rb = pl + static_cast<int64_t>(r1 * f) * W;
+        const float t0 = has_w ? aug_lerp2(__ldg(ra + c0 * f), w0, __ldg(ra + c1 * f), w1) : __ldg(ra + xx * f);
+        if (!has_v) {
+          v[c] = t0;
+        } else {
+          const float t1 = has_w ? aug_lerp2(__ldg(rb + c0 * f), w0, __ldg(rb + c1 * f), w1) : __ldg(rb + xx * f);
+          v[c] = aug_lerp2(t0, w0, t1, w1);
+        }
+      }
+    }
+    // RedistColor (float64 products, float32 after every accumulation), then Brightness (float32)
+    float o[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float acc = static_cast<float>(__dmul_rn(sp.mat[3 * c + 0], static_cast<double>(v[0])));
+      acc = static_cast<float>(__dadd_rn(static_cast<double>(acc), __dmul_rn(sp.mat[3 * c + 1], static_cast<double>(v[1]))));
+      acc = static_cast<float>(__dadd_rn(static_cast<double>(acc), __dmul_rn(sp.mat[3 * c + 2], static_cast<double>(v[2]))));
+      o[c] = __fmul_rn(acc, sp.bright);
+    }
+    const int64_t pp = static_cast<int64_t>(ps) * ps;
+    if (so == 4) {
+      float* dst = out_center + static_cast<int64_t>(b) * 3 * pp + y * ps + x;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) dst[c * pp] = o[c];
+    } else {
+      float* dst = out_views + (((static_cast<int64_t>(so) * B + b) * n + k) * 3) * pp + y * ps + x;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) dst[c * pp] = o[c];
+      if (so == 0) hsum = static_cast<double>(o[0]) + static_cast<double>(o[1]) + static_cast<double>(o[2]);
+    }
+  }
+  // Contrast's mean is over the h stack (data[0]) after Brightness: block partial -> one atomic
+  __shared__ double red[8];
+  hsum = warp_sum(hsum);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = hsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    if (t != 0.0) atomicAdd(view_sums + b, t);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+augment_contrast_kernel(float* __restrict__ views, float* __restrict__ center, const mmlf_aug_sample* __restrict__ samples,
+                        const double* __restrict__ view_sums, const float* __restrict__ mean_override, int B, int n,
+                        int ps) {
+  const int b = blockIdx.y;
+  const int per_stack = n * 3 * ps * ps;
+  const int total = 4 * per_stack + 3 * ps * ps;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const float mean = mean_override ? mean_override[b] : static_cast<float>(view_sums[b] / static_cast<double>(per_stack));
+  const float a = samples[b].contrast;
+  const float off = __fmul_rn(mean, samples[b].one_minus_contrast);
+  float* p;
+  if (idx < 4 * per_stack) {
+    const int so = idx / per_stack, rem = idx - so * per_stack;
+    p = views + (static_cast<int64_t>(so) * B + b) * per_stack + rem;
+  } else {
+    p = center + static_cast<int64_t>(b) * 3 * ps * ps + (idx - 4 * per_stack);
+  }
+  *p = __fadd_rn(__fmul_rn(*p, a), off);
+}
+
+// gt, mpi (rotated like the views) and mask (cropped only)
+__global__ void __launch_bounds__(256)
+augment_targets_kernel(const float* __restrict__ gt, const float* __restrict__ mpi, const int32_t* __restrict__ mask, int K,
+                       int H, int W, const mmlf_aug_sample* __restrict__ samples, int ps, float* __restrict__ out_gt,
+                       float* __restrict__ out_mpi, int32_t* __restrict__ out_mask) {
+  const int b = blockIdx.y;
+  const mmlf_aug_sample& sp = samples[b];
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= ps * ps) return;
+  const int y = idx / ps, x = idx - y * ps;
+  int Y, X;
+  aug_unrotate(sp.r, ps, y, x, Y, X);
+  const int f = sp.f;
+  const int64_t plane = static_cast<int64_t>(H) * W;
+  const int64_t src = static_cast<int64_t>((sp.cy + Y) * f) * W + (sp.cx + X) * f;
+  const int64_t pp = static_cast<int64_t>(ps) * ps;
+  if (out_gt) {
+    // gt /= f; gt -= disp  (float32 array, python floats: hci4d.py:506, 984-985)
+    const float g = __fdiv_rn(__ldg(gt + sp.scene * plane + src), static_cast<float>(f));
+    out_gt[b * pp + idx] = __fsub_rn(g, sp.disp_f);
+  }
+  if (out_mpi) {
+    for (int k = 0; k < K; ++k) {
+      const float* m = mpi + (static_cast<int64_t>(sp.scene) * K + k) * 5 * plane + src;
+      float* o = out_mpi + (static_cast<int64_t>(b) * K + k) * 5 * pp + idx;
+      for (int c = 0; c < 4; ++c) o[c * pp] = __ldg(m + c * plane);
+      // float64 array in the reference: (d / f) - disp in double, rounded once by the later .float()
+      const double d = __dsub_rn(__ddiv_rn(static_cast<double>(__ldg(m + 4 * plane)), static_cast<double>(f)), sp.disp);
+      o[4 * pp] = static_cast<float>(d);
+    }
+  }
+  if (out_mask) {
+    const int64_t ms = static_cast<int64_t>((sp.cy + y) * f) * W + (sp.cx + x) * f;      // the mask is NOT rotated
+    out_mask[b * pp + idx] = __ldg(mask + sp.scene * plane + ms);
+  }
+}
+
+}  // namespace mmlf
+
+using namespace mmlf;
+
+extern "C" int mmlf_augment_fill(mmlf_aug_sample* s, int r, double disp, int n) {
+  MMLF_REQUIRE(s != nullptr && r >= 0 && r <= 3 && n >= 1 && n <= 16, "augment_fill: bad arguments");
+  s->r = r;
+  int src[4] = {0, 1, 2, 3}, flip[4] = {0, 0, 0, 0};
+  for (int i = 0; i < r; ++i) {                      // Rotate90: h' = v, v' = flip(h), i' = d, d' = flip(i)
+    const int ns[4] = {src[1], src[0], src[3], src[2]};
+    const int nf[4] = {flip[1], flip[0] ^ 1, flip[3], flip[2] ^ 1};
+    for (int k = 0; k < 4; ++k) { src[k] = ns[k]; flip[k] = nf[k]; }
+  }
+  for (int k = 0; k < 4; ++k) { s->src[k] = src[k]; s->flip[k] = flip[k]; }
+  s->disp = disp;
+  s->disp_f = static_cast<float>(disp);
+  return mmlf_shift_taps(disp, n, s->w0, s->w1, s->s0, s->s1);
+}
+
+extern "C" int mmlf_augment_patches(const float* stacks, const float* center, const float* gt, const float* mpi,
+                                    const int32_t* mask, int S, int n, int K, int H, int W, const mmlf_aug_sample* samples,
+                                    int B, int ps, float* out_views, float* out_center, double* view_sums, float* out_gt,
+                                    float* out_mpi, int32_t* out_mask, void* stream) {
+  MMLF_REQUIRE(stacks && center && samples && out_views && out_center && view_sums, "augment_patches: null buffer");
+  MMLF_REQUIRE(S >= 1 && n >= 1 && n <= 16 && B >= 1 && B <= 65535 && ps >= 1, "augment_patches: bad sizes");
+  MMLF_REQUIRE((!out_gt || gt) && (!out_mpi || (mpi && K >= 1)) && (!out_mask || mask), "augment_patches: missing source");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int total = 4 * n * ps * ps + ps * ps;
+  augment_views_kernel<<<dim3(ceil_div(total, 256), B), 256, 0, st>>>(stacks, center, n, H, W, samples, B, ps, out_views,
+                                                                      out_center, view_sums);
+  if (int rc = check_launch("augment_views_kernel")) return rc;
+  if (out_gt || out_mpi || out_mask) {
+    augment_targets_kernel<<<dim3(ceil_div(ps * ps, 256), B), 256, 0, st>>>(gt, mpi, mask, K, H, W, samples, ps, out_gt,
+                                                                            out_mpi, out_mask);
+    return check_launch("augment_targets_kernel");
+  }
+  return 0;
+}
+
+extern "C" int mmlf_augment_contrast(float* views, float* center, const mmlf_aug_sample* samples, const double* view_sums,
+                                     const float* mean_override, int B, int n, int ps, void* stream) {
+  MMLF_REQUIRE(views && center && samples && (view_sums || mean_override), "augment_contrast: null buffer");
+  const int total = 4 * n * 3 * ps * ps + 3 * ps * ps;
+  augment_contrast_kernel<<<dim3(ceil_div(total, 256), B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      views, center, samples, view_sums, mean_override, B, n, ps);
+  return check_launch("augment_contrast_kernel");
+}

@@ -69,7 +69,8 @@ from ..utils.dl import ModelSaver, mpi_to_weights, reg_to_class
 @click.option('--val_disp_max', default=3.5, help='Maximum disparity of dataset')
 @click.option('--val_disp_step', default=0.1, help='Disparity increment for ensamble')
 @click.option('--max_iterations', default=0, help='[mmlf_b200] stop after this many iterations (0 = never, like the reference)')
-def main(output_dir, max_iterations, **kwargs):
+@click.option('--gpu_augment', is_flag=True, help='[mmlf_b200] keep the scenes on the GPU and run the augmentation chain there')
+def main(output_dir, max_iterations, gpu_augment, **kwargs):
     assert not (kwargs['train_loss_strongest'] and kwargs['train_loss_multimodal'])
     if kwargs['model_invertible']:
         raise NotImplementedError('INNs are not supported anymore')          # train/cli.py:252
@@ -100,6 +101,28 @@ def main(output_dir, max_iterations, **kwargs):
         loss_fn, loss_uncert_fn = loss.MaskedL1Loss(), loss.ImprovedUncertaintyL1Loss()
     loss_discrete_fn = loss.MaskedCrossEntropy()
     mse_fn, bad_pix_fn = loss.MaskedMSELoss(), loss.MaskedBadPix()
+
+    augmenter = None
+    if gpu_augment and not kwargs['train_no_data_augment']:
+        # the reference's transform chain (train/cli.py:78-90) on the GPU: scenes resident in HBM, parameters drawn by the
+        # host `random` in the reference's order, one gather kernel per batch (mmlf_b200/data/augment.py)
+        import random
+        from ..data import hci4d
+        from ..data.augment import GpuAugmenter
+        side = max(4 * ps, kwargs['train_max_downscale'] * (ps + 17))
+        scenes = [synthetic.SyntheticLF(length=8, n=kwargs['model_views'], H=side, W=side, seed=7)[j] for j in range(8)]
+        augmenter = GpuAugmenter(scenes, dev)
+        if kwargs['train_shift'] != 0.0:                                       # static Shift first (train/cli.py:89-90)
+            for j in range(augmenter.S):
+                st = [augmenter.stacks[j, k] for k in range(4)]
+                hci4d.Shift(float(kwargs['train_shift']))(tuple(st) + (None, augmenter.gt[j], augmenter.mpi[j]))
+        random.seed(1234 + rank)
+
+        def gpu_batches():
+            while True:
+                ids, params = augmenter.draw(max(1, kwargs['train_bs'] // world), ps, random, kwargs['train_max_downscale'])
+                yield augmenter(ids, params)
+        trainloader = gpu_batches()
 
     i = 0
     if kwargs['train_resume']:                                                # train/cli.py:137-157
@@ -132,7 +155,7 @@ def main(output_dir, max_iterations, **kwargs):
             if kwargs['train_loss_strongest']:
                 inds = torch.max(mpi[:, :, 3, :, :], dim=1)[1].unsqueeze(1)
                 gt = torch.gather(mpi[:, :, 4, :, :], dim=1, index=inds).squeeze()
-            mask = mask.int() * loss.create_mask_margin(mask.shape, 11)       # train/cli.py:194
+            mask = mask.int() * loss.create_mask_margin(mask.shape, 11).to(mask.device)   # train/cli.py:194
             h_views, v_views, i_views, d_views = (t.to(dev, non_blocking=True) for t in (h_views, v_views, i_views, d_views))
             gt, mpi, mask = gt.to(dev), mpi.to(dev).float(), mask.to(dev)
             gt_classes = None

@@ -337,7 +337,39 @@ def gen_texture():
     save('texture_mask.npz', **res)
 
 
+# ---------------------------------------------------------------------------- f1
+def gen_augment():
+    """The reference's own augmentation chain (train/cli.py:78-87) under random.seed(s) on a small synthetic 9-tuple;
+    inputs once, outputs + the seed per case.  The parameters are NOT stored: the tests re-derive them by replaying the
+    draw order (oracle.augment.draw_params) from the same seed."""
+    import random
+    from torchvision import transforms
+    rng = np.random.RandomState(23)
+    n, H, W, ps = 9, 64, 64, 8
+    stacks = [rng.uniform(0, 1, (n, 3, H, W)).astype(np.float32) for _ in range(4)]
+    center = stacks[1][n // 2].copy()
+    gt = rng.uniform(-2, 2, (H, W)).astype(np.float32)
+    mpi = np.zeros((1, 5, H, W))
+    mpi[0, :3], mpi[0, 3], mpi[0, 4] = center, 1.0, gt
+    mask = (rng.uniform(size=(H, W)) > 0.3).astype(np.int64)
+    index = np.atleast_1d(3)
+    res = {'h': stacks[0], 'v': stacks[1], 'i': stacks[2], 'd': stacks[3], 'center': center, 'gt': gt, 'mpi': mpi,
+           'mask': mask, 'ps': np.array(ps), 'max_factor': np.array(2)}
+    chain = transforms.Compose([hci4d.RandomDownSampling(2), hci4d.RandomShift(1.0), hci4d.RandomCrop(ps + 2 * 4 * 2),
+                                hci4d.CenterCrop(ps), hci4d.RandomRotate(), hci4d.RedistColor(), hci4d.Brightness(),
+                                hci4d.Contrast()])
+    seeds = list(range(100, 112))
+    for s in seeds:
+        random.seed(s)
+        data = tuple(a.copy() for a in (*stacks, center, gt, mpi, mask, index))
+        out = chain(data)
+        for k, name in enumerate(('h', 'v', 'i', 'd', 'center', 'gt', 'mpi', 'mask')):
+            res[f'{s}/{name}'] = np.ascontiguousarray(out[k])
+    res['seeds'] = np.array(seeds)
+    save('augment.npz', **res)
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['indices', 'shift', 'bins', 'net', 'losses', 'ese', 'adam', 'checkpoint', 'texture']
+    which = sys.argv[1:] or ['indices', 'shift', 'bins', 'net', 'losses', 'ese', 'adam', 'checkpoint', 'texture', 'augment']
     for w in which:
         globals()['gen_' + w]()

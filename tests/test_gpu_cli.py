@@ -28,6 +28,7 @@ COMMON = ['--model_chs', '16', '--train_bs', '4', '--train_ps', '32', '--train_l
      ['--val_ensamble', '--val_disp_step', '1.0', '--train_shift', '2.5']),
     (['--model_discrete', '--train_loss_multimodal'], ['--model_discrete']),
     (['--model_cross'], []),
+    (['--gpu_augment', '--train_shift', '2.5', '--train_max_downscale', '2'], []),
 ])
 def test_train_then_validate_cli(tmp_path, flags, val_flags):
     out = str(tmp_path)

@@ -79,6 +79,39 @@ def test_texture_mask(golden):
     assert not mask[0, :11].any() and not mask[0, :, -11:].any() and mask[0, 11:-11, 300:-11].all()
 
 
+def test_augmentation_chain_against_the_reference(golden):
+    """GPU augmentation chain (one gather kernel + Contrast) against the reference's own Compose output: bit exact for
+    every tensor when Contrast is given NumPy's float32 mean; with the on-device float64 mean the views agree to 1 ulp."""
+    import random
+    from oracle import augment as A
+    from mmlf_b200.data.augment import GpuAugmenter, draw_params
+    g = golden('augment.npz')
+    sample = [g[k] for k in ('h', 'v', 'i', 'd', 'center', 'gt', 'mpi', 'mask')] + [np.atleast_1d(3)]
+    aug = GpuAugmenter([sample, sample])
+    seeds = [int(s) for s in g['seeds']]
+    params = [draw_params(random.Random(s), 64, 64, int(g['ps']), int(g['max_factor'])) for s in seeds]
+    means = [A.augment(sample, p)[1] for p in params]
+    ids = [i % 2 for i in range(len(seeds))]
+    out = aug(ids, params, mean_override=means)
+    names = ('h', 'v', 'i', 'd', 'center', 'gt', 'mpi', 'mask')
+    for j, s in enumerate(seeds):
+        for k, name in enumerate(names):
+            ref = g[f'{s}/{name}']
+            got = out[k][j].cpu().numpy()
+            if name == 'mpi':
+                ref = ref.astype(np.float32)                    # train/cli.py casts with .float() after the transforms
+            assert np.array_equal(got, ref.astype(got.dtype)), (s, name, np.abs(got - ref).max())
+    # on-device mean: float64 sum instead of NumPy's pairwise float32 sum
+    out2 = aug(ids, params)
+    dm = np.abs(aug.last_means.cpu().numpy() - np.array(means, np.float64)) / np.array(means, np.float64)
+    assert dm.max() < 1e-6
+    for k in range(5):
+        a, b = out2[k].cpu().numpy(), out[k].cpu().numpy()
+        assert np.abs(a - b).max() <= 2.4e-7 * max(1.0, np.abs(b).max())
+    for k in (5, 6, 7):
+        assert torch.equal(out2[k], out[k])
+
+
 def test_pack_views_and_shift_pack():
     u = _u()
     rng = np.random.RandomState(2)

@@ -242,6 +242,25 @@ def main():
                '33 distinct views read, 36 + 1 f32 planes written')
     del u8
 
+    # ------------------------------------------------------------------ augmentation chain
+    if bn.want('augment_views_kernel+augment_contrast_kernel'):
+        import random
+        from mmlf_b200.data.augment import GpuAugmenter
+        rs = np.random.RandomState(0)
+        scenes = []
+        for _ in range(4):
+            st = [rs.uniform(0, 1, (9, 3, 512, 512)).astype(np.float32) for _ in range(4)]
+            gt_ = rs.uniform(-2, 2, (512, 512)).astype(np.float32)
+            mp = np.zeros((1, 5, 512, 512), np.float32)
+            scenes.append((*st, st[1][4], gt_, mp, np.ones((512, 512), np.int32), np.atleast_1d(0)))
+        aug = GpuAugmenter(scenes)
+        ids, params = aug.draw(Bt, ps, random.Random(0), 4)
+        out_bytes = Bt * (4 * 27 + 3) * ps * ps * 4.0
+        # algorithmic: every output element written once (+ read and re-written by Contrast) and ~1 source element read
+        bn.hbm_row('augment_views_kernel+augment_contrast_kernel', f'{Bt} patches of 96 px from 512x512 scenes, full chain',
+                   4.0 * out_bytes, lambda: aug(ids, params),
+                   'gather with stride f (down-sampling) + 2-4 lerp taps; includes the host packing of the parameters')
+
     # ------------------------------------------------------------------ heads, targets, losses, ESE reduce, Adam
     B, H, W, S = Bt, ps, ps, 108
     px = B * H * W
