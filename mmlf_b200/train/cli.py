@@ -25,51 +25,63 @@ from ..optim import FusedAdam
 from ..utils.dl import ModelSaver, mpi_to_weights, reg_to_class
 
 
+# Option table of the reference CLI (train/cli.py:17-59): same names, defaults and types, applied programmatically;
+# the last two entries are extensions of this package.
+_OPTIONS = [
+    ('--model_ksize', dict(default=2)),
+    ('--model_in_blocks', dict(default=3)),
+    ('--model_out_blocks', dict(default=8)),
+    ('--model_chs', dict(default=70)),
+    ('--model_views', dict(default=9)),
+    ('--model_cross', dict(is_flag=True)),
+    ('--model_uncert', dict(is_flag=True)),
+    ('--model_discrete', dict(is_flag=True)),
+    ('--model_unet', dict(is_flag=True)),
+    ('--model_invertible', dict(is_flag=True)),
+    ('--model_clamp', dict(default=0.7)),
+    ('--model_act_norm', dict(default=0.7)),
+    ('--model_act_norm_type', dict(default='SOFTPLUS')),
+    ('--model_soft_permutation', dict(is_flag=True)),
+    ('--model_no_batchnorm', dict(is_flag=True)),
+    ('--model_batchnorm_momentum', dict(default=0.1)),
+    ('--train_trainset', dict(default='../lf-dataset/additional')),
+    ('--train_valset', dict(default='../lf-dataset/training')),
+    ('--train_no_data_augment', dict(is_flag=True)),
+    ('--train_num_workers', dict(default=4)),
+    ('--train_lr', dict(default=1e-5)),
+    ('--train_bs', dict(default=1)),
+    ('--train_ps', dict(default=32)),
+    ('--train_beta', dict(default=1.0)),
+    ('--train_mae_threshold', dict(default=0.02)),
+    ('--train_max_downscale', dict(default=4)),
+    ('--train_resume', dict(is_flag=True)),
+    ('--train_loss_padding', dict(default=None, type=float)),
+    ('--train_shift', dict(default=0.0, type=float)),
+    ('--train_loss_multimodal', dict(is_flag=True)),
+    ('--train_loss_strongest', dict(is_flag=True)),
+    ('--train_eval_mode', dict(is_flag=True)),
+    ('--train_eval_mode_start', dict(default=0)),
+    ('--train_warm_start', dict(is_flag=True)),
+    ('--train_cooling', dict(default=0)),
+    ('--val_interval', dict(default=100)),
+    ('--val_loss_margin', dict(default=15)),
+    ('--val_ensamble', dict(is_flag=True)),
+    ('--val_disp_min', dict(default=-3.5)),
+    ('--val_disp_max', dict(default=3.5)),
+    ('--val_disp_step', dict(default=0.1)),
+    ('--max_iterations', dict(default=0)),
+    ('--gpu_augment', dict(is_flag=True)),
+]
+
+
+def _with_options(fn):
+    for name, kw in reversed(_OPTIONS):
+        fn = click.option(name, **kw)(fn)
+    return click.argument('output_dir', type=click.Path(exists=True))(fn)
+
+
 @click.command()
-@click.argument('output_dir', type=click.Path(exists=True))
-@click.option('--model_ksize', default=2, help='Kernel size for convolutions, e.g. 3 for 3x3 kernels')
-@click.option('--model_in_blocks', default=3, help='Number of blocks for input network')
-@click.option('--model_out_blocks', default=8, help='Number of blocks for output network')
-@click.option('--model_chs', default=70, help='Number of channels for input network')
-@click.option('--model_views', default=9, help='Number of viewpoints of the input light field, e.g. 9 for 9+8 views')
-@click.option('--model_cross', is_flag=True, help='Only use cross input?')
-@click.option('--model_uncert', is_flag=True, help='Use uncertainty model?')
-@click.option('--model_discrete', is_flag=True, help='Discretize disparity output?')
-@click.option('--model_unet', is_flag=True, help='Use a U-Net after the multistream network?')
-@click.option('--model_invertible', is_flag=True, help='Use invertible architecture?')
-@click.option('--model_clamp', default=0.7, help='Output clamp for coupling block?')
-@click.option('--model_act_norm', default=0.7, help='Activation normalization for coupling block?')
-@click.option('--model_act_norm_type', default='SOFTPLUS', help='Type of activation normalization for coupling block?')
-@click.option('--model_soft_permutation', is_flag=True, help='Use soft permuation for coupling block?')
-@click.option('--model_no_batchnorm', is_flag=True, help='Disable BatchNorm layers')
-@click.option('--model_batchnorm_momentum', default=0.1, help='Momentum for BatchNorm layers')
-@click.option('--train_trainset', default='../lf-dataset/additional', help='Location of training dataset')
-@click.option('--train_valset', default='../lf-dataset/training', help='Location of validation dataset')
-@click.option('--train_no_data_augment', is_flag=True, help='Don\'t use any data augmentation?')
-@click.option('--train_num_workers', default=4, help='Number of workors for data loader')
-@click.option('--train_lr', default=1e-5, help='Learning rate')
-@click.option('--train_bs', default=1, help='Batch size')
-@click.option('--train_ps', default=32, help='Size of training patches')
-@click.option('--train_beta', default=1.0, help='Weighting between NLL and Cat CE')
-@click.option('--train_mae_threshold', default=0.02, help='If the MAE of one patch is under this threshold, no loss is applied')
-@click.option('--train_max_downscale', default=4, help='Maximum factor of down scaling for data augmentation')
-@click.option('--train_resume', is_flag=True, help='Resume training from old checkpoint?')
-@click.option('--train_loss_padding', default=None, type=float, help='Margin around ground truth to apply loss')
-@click.option('--train_shift', default=0.0, type=float, help='Static shift to apply to off-center training datasets')
-@click.option('--train_loss_multimodal', is_flag=True, help='Use multimodal training loss?')
-@click.option('--train_loss_strongest', is_flag=True, help='Use strongest depth instead of nearest?')
-@click.option('--train_eval_mode', is_flag=True, help='Also train in eval mode?')
-@click.option('--train_eval_mode_start', default=0, help='Start iteration for eval mode')
-@click.option('--train_warm_start', is_flag=True, help='Use lower learning rate during initial iterations?')
-@click.option('--train_cooling', default=0, help='Cooling interval')
-@click.option('--val_interval', default=100, help='Validation interval')
-@click.option('--val_loss_margin', default=15, help='Margin around each image to omit for the validation loss.')
-@click.option('--val_ensamble', is_flag=True, help='Use a network ensamble?')
-@click.option('--val_disp_min', default=-3.5, help='Minimum disparity of dataset')
-@click.option('--val_disp_max', default=3.5, help='Maximum disparity of dataset')
-@click.option('--val_disp_step', default=0.1, help='Disparity increment for ensamble')
-@click.option('--max_iterations', default=0, help='[mmlf_b200] stop after this many iterations (0 = never, like the reference)')
-@click.option('--gpu_augment', is_flag=True, help='[mmlf_b200] keep the scenes on the GPU and run the augmentation chain there')
+@_with_options
 def main(output_dir, max_iterations, gpu_augment, **kwargs):
     assert not (kwargs['train_loss_strongest'] and kwargs['train_loss_multimodal'])
     if kwargs['model_invertible']:

@@ -369,7 +369,23 @@ def gen_augment():
     save('augment.npz', **res)
 
 
+# ---------------------------------------------------------------------------- (b) boundary: the CLI surfaces
+def gen_cli():
+    """Option names, defaults, flags and types of the reference's two click commands (train/cli.py:17-59,
+    validate/cli.py:190-208), by introspection."""
+    import json
+    from mmlf.train import cli as tcli
+    from mmlf.validate import cli as vcli
+    res = {}
+    for name, cmd in (('train', tcli.main), ('validate', vcli.main)):
+        res[name] = [{'name': p.name, 'opts': list(p.opts), 'kind': type(p).__name__, 'default': p.default,
+                      'is_flag': bool(getattr(p, 'is_flag', False)), 'type': p.type.name} for p in cmd.params]
+    with open(os.path.join(OUT, 'cli_options.json'), 'w') as f:
+        json.dump(res, f, indent=1, default=str)
+    print('wrote cli_options.json', {k: len(v) for k, v in res.items()})
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['indices', 'shift', 'bins', 'net', 'losses', 'ese', 'adam', 'checkpoint', 'texture', 'augment']
+    which = sys.argv[1:] or ['indices', 'shift', 'bins', 'net', 'losses', 'ese', 'adam', 'checkpoint', 'texture', 'augment', 'cli']
     for w in which:
         globals()['gen_' + w]()

@@ -11,11 +11,13 @@ P="python -m pytest -q -m gpu -p no:cacheprovider"
 rm -f $O/parity_report.jsonl
 timeout 1200 $P tests/test_gpu_kernels.py > $O/test_kernels_$TAG.log 2>&1; echo "kernels: $?"; tail -n 2 $O/test_kernels_$TAG.log
 timeout 1200 $P tests/test_gpu_model.py > $O/test_model_$TAG.log 2>&1; echo "model: $?"; tail -n 2 $O/test_model_$TAG.log
+timeout 1200 $P tests/test_gpu_fullsize.py tests/test_gpu_cli.py > $O/test_fullsize_cli_$TAG.log 2>&1; echo "fullsize+cli: $?"; tail -n 2 $O/test_fullsize_cli_$TAG.log
 timeout 600 python __graft_entry__.py smoke > $O/smoke_$TAG.log 2>&1; echo "smoke: $?"; tail -n 1 $O/smoke_$TAG.log
 
 timeout 900 python bench.py > $O/bench_train_$TAG.json 2> $O/bench_train_$TAG.err; echo "bench train: $?"
 timeout 600 python bench.py --workload infer > $O/bench_infer_$TAG.json 2> $O/bench_infer_$TAG.err; echo "bench infer: $?"
 timeout 600 python bench.py --workload ese --steps 3 > $O/bench_ese_$TAG.json 2> $O/bench_ese_$TAG.err; echo "bench ese: $?"
+timeout 600 python bench.py --workload infer --precision split --no-cpu-baseline > $O/bench_infer_split_$TAG.json 2> $O/bench_infer_split_$TAG.err; echo "bench infer split: $?"
 timeout 600 python bench.py --workload bands --no-cpu-baseline > $O/bench_bands_$TAG.json 2> $O/bench_bands_$TAG.err; echo "bench bands: $?"
 timeout 600 python bench.py --variant upr --steps 4 --no-cpu-baseline > $O/bench_train_upr_$TAG.json 2> $O/bench_train_upr_$TAG.err; echo "bench upr: $?"
 timeout 600 python bench.py --variant dpp --steps 4 --no-cpu-baseline > $O/bench_train_dpp_$TAG.json 2> $O/bench_train_dpp_$TAG.err; echo "bench dpp: $?"
@@ -47,5 +49,6 @@ if [ "$2" != "noncu" ]; then
   cap shift_pack pack_views "shift_pack_kernel full"
   cap loss_ce loss_ce "loss_ce_kernel 64x108x96x96 on-the-fly"
   cap dpp_head dpp_head "dpp_head"
+  cap augment augment_views "augment"
 fi
 ls -la $O | tail -n 40

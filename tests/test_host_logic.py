@@ -107,3 +107,20 @@ def test_create_mask_margin_and_view_indices(golden):
             dds == list(gi[f'dds{n}'])
     with pytest.raises(AssertionError):
         hci4d.Shift(1)          # the reference requires a python float (hci4d.py:904)
+
+
+def test_cli_surfaces_match_the_reference():
+    """Every option of the reference's train / validate commands exists here with the same default, flag-ness and type
+    (tests/golden/cli_options.json: click introspection of the reference, oracle/gen_golden.py::gen_cli)."""
+    import json
+    from mmlf_b200.train.cli import main as tmain
+    from mmlf_b200.validate.cli import main as vmain
+    ref = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'cli_options.json')))
+    for name, cmd, extra in (('train', tmain, {'max_iterations', 'gpu_augment'}), ('validate', vmain, {'size'})):
+        mine = {p.name: p for p in cmd.params}
+        assert set(mine) - {r['name'] for r in ref[name]} == extra
+        for r in ref[name]:
+            p = mine[r['name']]
+            assert list(p.opts) == r['opts'] and type(p).__name__ == r['kind'], r['name']
+            assert bool(getattr(p, 'is_flag', False)) == r['is_flag'] and p.type.name == r['type'], r['name']
+            assert str(p.default) == str(r['default']), (r['name'], p.default, r['default'])
