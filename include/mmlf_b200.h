@@ -299,6 +299,22 @@ int mmlf_ese_reduce(const float* means, const float* logvars, const float* disp,
 int mmlf_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
                    double eps, int64_t step, void* stream);
 
+/* ------------------------------------------------------------------ validation metrics */
+/* laplace_to_discrete / lmm_to_discrete (validate/cli.py:91-118): means / logvars (K, B, HW) f32 (K = 1: one Laplacian),
+ * out (B, n_bins, HW) f64 = mean over the members of the Laplace-CDF differences over n_bins + 1 edges from
+ * x_min - step/2 to x_max + step/2.  float64 arithmetic; var = float32 exp of the float32 logvar, as in the reference. */
+int mmlf_lmm_to_discrete(const float* means, const float* logvars, int K, int64_t B, int64_t HW, int n_bins, double x_min,
+                         double x_max, double* out, void* stream);
+/* kl_divergence (validate/cli.py:174-187): dist / dist_gt (B, S, HW) f64 are epsilon-shifted and normalised IN PLACE
+ * like the reference does; value (optional, f64 [B * HW]) = sum_c gt log(gt / dist) per pixel; sums (optional, f64 [2],
+ * zeroed by the caller) += (sum value * mask, sum mask), mask (f64 [B * HW]) or NULL for all ones. */
+int mmlf_kl_divergence(double* dist, double* dist_gt, int S, int64_t B, int64_t HW, const double* mask, double* value,
+                       double* sums, void* stream);
+/* nll_discrete (validate/cli.py:51-70): weights /= sum, posterior /= sum * 7 after the epsilon shift (in place),
+ * value = sum_c weights * -log(posterior). */
+int mmlf_nll_discrete(double* weights, double* posterior, int S, int64_t B, int64_t HW, const double* mask, double* value,
+                      double* sums, void* stream);
+
 /* ------------------------------------------------------------------ training augmentation chain */
 /* RandomDownSampling -> RandomShift -> RandomCrop(ps + 16) -> CenterCrop(ps) -> RandomRotate -> RedistColor -> Brightness
  * -> Contrast (train/cli.py:78-87; hci4d.py:483-530, 894-1028, 533-664, 1031-1087, 667-785) as gather kernels over

@@ -36,6 +36,9 @@ _PROTOS = {
     'mmlf_lf_extract_u8': (c_i, [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
     'mmlf_lf_shift': (c_i, [c_p] * 8 + [c_i, c_i, c_i, c_i, c_d, c_p]),
     'mmlf_texture_mask': (c_i, [c_p, c_i, c_i, c_i, c_i, c_d, c_p, c_p, c_p]),
+    'mmlf_lmm_to_discrete': (c_i, [c_p, c_p, c_i, c_i64, c_i64, c_i, c_d, c_d, c_p, c_p]),
+    'mmlf_kl_divergence': (c_i, [c_p, c_p, c_i, c_i64, c_i64, c_p, c_p, c_p, c_p]),
+    'mmlf_nll_discrete': (c_i, [c_p, c_p, c_i, c_i64, c_i64, c_p, c_p, c_p, c_p]),
     'mmlf_augment_fill': (c_i, [c_p, c_i, c_d, c_i]),
     'mmlf_augment_patches': (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p, c_p, c_p, c_p,
                                    c_p, c_p, c_p]),

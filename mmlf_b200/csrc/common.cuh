@@ -324,4 +324,18 @@ __device__ __forceinline__ T warp_sum(T v) {
   return v;
 }
 
+// sum over the thread block (valid in thread 0); red: shared scratch of blockDim.x / 32 doubles
+__device__ __forceinline__ double block_sum_double(double v, double* red) {
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) red[wrp] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < (blockDim.x >> 5); ++w) r += red[w];
+  __syncthreads();
+  return r;   // valid in thread 0
+}
+
 }  // namespace mmlf

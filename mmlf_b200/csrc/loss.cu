@@ -12,19 +12,6 @@
 
 namespace mmlf {
 
-__device__ __forceinline__ double block_sum_double(double v, double* red) {
-  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if (lane == 0) red[wrp] = v;
-  __syncthreads();
-  double r = 0.0;
-  if (threadIdx.x == 0)
-    for (int w = 0; w < (blockDim.x >> 5); ++w) r += red[w];
-  __syncthreads();
-  return r;   // valid in thread 0
-}
-
 __global__ void __launch_bounds__(256)
 loss_prepass_kernel(const int32_t* __restrict__ mask, const int32_t* __restrict__ mask_padding,
                     const float* __restrict__ mpi, int K, int64_t B, int64_t HW, double* __restrict__ sums) {

@@ -15,6 +15,8 @@ from ..data import hci4d, synthetic
 from ..model import loss
 from ..model.ensamble import Ensamble
 from ..model.feed_forward import FeedForward
+from ..utils.dl import mpi_to_weights
+from . import metrics
 
 
 @click.command()
@@ -50,7 +52,7 @@ def main(output_dir, dataset, model_invertible, model_discrete, val_loss_margin,
     shift = hci4d.Shift(float(train_shift)) if train_shift != 0.0 else None
     with torch.no_grad():
         model.eval()
-        mse_avg = bad_pix_avg = 0.0
+        mse_avg = bad_pix_avg = kld_avg = kld_mm_avg = kld_um_avg = 0.0
         runtime = 0.0
         for i, data in enumerate(valloader):
             print(f'Processing scene {i}...')
@@ -74,11 +76,31 @@ def main(output_dir, dataset, model_invertible, model_discrete, val_loss_margin,
             _ = output['mean'].cpu()
             runtime = time.time() - t_start
             print(mse.item(), bad_pix.item())
+            # distribution metrics on the GPU (validate/cli.py:286-325), float64 like the numpy originals
+            mpi = mpi.to(dev).float()
+            dist_gt = mpi_to_weights(mpi, val_disp_min, val_disp_max, 108).double().contiguous()
+            mm_mask = metrics.multimodal_mask(mpi)
+            if val_ensamble:
+                # the reference hands exp(logvars) to lmm_to_discrete, which exponentiates again (:304, :93): kept
+                dist = metrics.lmm_to_discrete(108, val_disp_min, val_disp_max, output['means'], torch.exp(output['logvars']))
+            elif model_discrete:
+                dist = output['posterior'].double().contiguous()
+            elif kwargs.get('model_uncert'):
+                dist = metrics.laplace_to_discrete(108, val_disp_min, val_disp_max, output['mean'], output['logvar'])
+            else:
+                dist = metrics.mean_to_discrete(108, val_disp_min, val_disp_max, output['mean']).contiguous()
+            if dist.shape[1] == 108:
+                kld = metrics.kl_divergence(dist, dist_gt)               # three calls on the same, in-place normalised
+                kld_mm = metrics.kl_divergence(dist, dist_gt, mm_mask)   # arrays, as validate/cli.py:323-325
+                kld_um = metrics.kl_divergence(dist, dist_gt, 1.0 - mm_mask)
+                print(kld_um, kld_mm, kld)
+                kld_avg, kld_mm_avg, kld_um_avg = kld_avg + kld, kld_mm_avg + kld_mm, kld_um_avg + kld_um
         mse_avg /= (i + 1)
         bad_pix_avg /= (i + 1)
+        kld_avg, kld_mm_avg, kld_um_avg = kld_avg / (i + 1), kld_mm_avg / (i + 1), kld_um_avg / (i + 1)
     if rank == 0:
         print('MSE & BadPix007 & KLD_UM & KLD_MM & KLD & - & TIME \\\\')
-        print(f'{mse_avg:.3f} & {bad_pix_avg:.3f} & - & - & - & - & {runtime:.3f} \\\\')
+        print(f'{mse_avg:.3f} & {bad_pix_avg:.3f} & {kld_um_avg:.3f} & {kld_mm_avg:.3f} & {kld_avg:.3f} & - & {runtime:.3f} \\\\')
     return 0
 
 

@@ -25,4 +25,4 @@ from .losses import (create_mask_margin, reg_to_class, mpi_to_weights, class_to_
                      improved_multi_uncertainty_l1)
 from .ensemble import ensemble_forward, ensemble_reduce  # noqa: F401
 from .optim import adam_step  # noqa: F401
-from . import augment  # noqa: F401
+from . import augment, metrics  # noqa: F401

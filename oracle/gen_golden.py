@@ -369,6 +369,35 @@ def gen_augment():
     save('augment.npz', **res)
 
 
+# ---------------------------------------------------------------------------- f3
+def gen_metrics():
+    """The distribution metrics of validate/cli.py on small random inputs, incl. the three consecutive kl_divergence
+    calls of validate.main (:323-325) that see each other's in-place normalisation."""
+    import contextlib
+    import io
+    from mmlf.validate import cli as vcli
+    rng = np.random.RandomState(29)
+    K, B, H, W, S = 5, 1, 6, 7, 108
+    means = rng.uniform(-3, 3, (K, B, H, W)).astype(np.float32)
+    logvars = rng.normal(-1.0, 0.7, (K, B, H, W)).astype(np.float32)
+    mpi = rng.uniform(0, 1, (B, 3, 5, H, W))
+    mpi[:, :, 4] = rng.uniform(-3, 3, (B, 3, H, W))
+    dist_gt = rng.uniform(0, 1, (B, S, H, W)) * (rng.uniform(size=(B, S, H, W)) > 0.9)
+    res = {'means': means, 'logvars': logvars, 'mpi': mpi, 'dist_gt': dist_gt}
+    with contextlib.redirect_stdout(io.StringIO()):
+        res['laplace'] = vcli.laplace_to_discrete(S, -3.5, 3.5, means[0], logvars[0])
+        res['lmm'] = vcli.lmm_to_discrete(S, -3.5, 3.5, means, logvars)
+        res['mean_disc'] = vcli.mean_to_discrete(S, -3.5, 3.5, means[0])
+        mask = vcli.multimodal_mask(mpi)
+        res['mm_mask'] = mask
+        d, g = res['lmm'].copy(), dist_gt.copy()
+        res['kld'] = np.array([vcli.kl_divergence(d, g), vcli.kl_divergence(d, g, mask), vcli.kl_divergence(d, g, 1.0 - mask)])
+        res['kld_dist_after'], res['kld_gt_after'] = d, g
+        w, p = dist_gt.copy(), res['lmm'].copy()
+        res['nll'] = np.array(vcli.nll_discrete(w, p, -3.5, 3.5, None))
+    save('metrics.npz', **res)
+
+
 # ---------------------------------------------------------------------------- (b) boundary: the CLI surfaces
 def gen_cli():
     """Option names, defaults, flags and types of the reference's two click commands (train/cli.py:17-59,
@@ -386,6 +415,6 @@ def gen_cli():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['indices', 'shift', 'bins', 'net', 'losses', 'ese', 'adam', 'checkpoint', 'texture', 'augment', 'cli']
+    which = sys.argv[1:] or ['indices', 'shift', 'bins', 'net', 'losses', 'ese', 'adam', 'checkpoint', 'texture', 'augment', 'metrics', 'cli']
     for w in which:
         globals()['gen_' + w]()

@@ -79,6 +79,33 @@ def test_texture_mask(golden):
     assert not mask[0, :11].any() and not mask[0, :, -11:].any() and mask[0, 11:-11, 300:-11].all()
 
 
+def test_validation_metrics_against_the_reference(golden):
+    from mmlf_b200.validate import metrics as M
+    g = golden('metrics.npz')
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    lap = M.laplace_to_discrete(108, -3.5, 3.5, T(g['means'][0]), T(g['logvars'][0]))
+    np.testing.assert_allclose(lap.cpu().numpy(), g['laplace'], rtol=1e-5, atol=1e-9)   # float32 exp(logvar): 1 ulp
+    lmm = M.lmm_to_discrete(108, -3.5, 3.5, T(g['means']), T(g['logvars']))
+    np.testing.assert_allclose(lmm.cpu().numpy(), g['lmm'], rtol=1e-5, atol=1e-9)
+    assert abs(lmm.sum(1).mean().item() - g['lmm'].sum(1).mean()) < 1e-7
+    assert np.array_equal(M.mean_to_discrete(108, -3.5, 3.5, T(g['means'][0])).cpu().numpy(), g['mean_disc'])
+    mask = M.multimodal_mask(T(g['mpi']))
+    assert np.array_equal(mask.cpu().numpy(), g['mm_mask'])
+    d, gt = T(g['lmm'].copy()), T(g['dist_gt'].copy())            # the reference's own distribution: exact comparison
+    vals = [M.kl_divergence(d, gt), M.kl_divergence(d, gt, mask), M.kl_divergence(d, gt, 1.0 - mask)]
+    np.testing.assert_allclose(vals, g['kld'], rtol=1e-12)
+    np.testing.assert_allclose(d.cpu().numpy(), g['kld_dist_after'], rtol=1e-12)
+    np.testing.assert_allclose(gt.cpu().numpy(), g['kld_gt_after'], rtol=1e-12)
+    w, p = T(g['dist_gt'].copy()), T(g['lmm'].copy())
+    np.testing.assert_allclose(M.nll_discrete(w, p), float(g['nll']), rtol=1e-12)
+    # full size: 70 members, one 512 x 512 light field, mass conservation (the CDF differences telescope)
+    gen = torch.Generator(device='cuda').manual_seed(0)
+    means = torch.rand((70, 1, 512, 512), device='cuda', generator=gen) * 4 - 2
+    logvars = torch.randn((70, 1, 512, 512), device='cuda', generator=gen) * 0.5 - 1
+    big = M.lmm_to_discrete(108, -3.5, 3.5, means, logvars)
+    assert big.min().item() >= 0 and big.sum(1).max().item() <= 1 + 1e-12 and big.sum(1).min().item() > 0.5
+
+
 def test_augmentation_chain_against_the_reference(golden):
     """GPU augmentation chain (one gather kernel + Contrast) against the reference's own Compose output: bit exact for
     every tensor when Contrast is given NumPy's float32 mean; with the on-device float64 mean the views agree to 1 ulp."""
