@@ -44,6 +44,7 @@ struct ConvParams {
   int kc_term, lo_col;                          // chunks per split term (= n_kc unless split_in), column of the lo block
   int tap_off[4];
   int num_tiles, stages;
+  int pair_issue;                               // narrow layers: the MMA warp issues two pipeline stages per round
   int type, relu, out_mode, n_real, ld_out, ld_out2;
   int ab_dtype, out_dtype, out2_dtype;
   int has_scale, dual, ld_bits, split_out;
@@ -472,6 +473,42 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
     const int b_row0 = static_cast<int>(rank) * half_rows;
     const uint32_t tx_bytes = 2 * stage_bytes;
+    if (p.pair_issue) {
+      // ---- narrow layers: two stages per round, mirroring the MMA warp (both chunks of a dy, or both dy of a tile)
+      const int off_dy0 = p.tap_off[0], off_dy1 = p.tap_off[2];
+      const int n_kc = p.n_kc, rounds = p.n_kc;
+      const uint32_t n_stages = static_cast<uint32_t>(p.stages);
+      for (int tile = pair; tile < p.num_tiles; tile += n_pairs) {
+        const int row0 = tile * (2 * kTileM) + static_cast<int>(rank) * kTileM;
+#pragma unroll 1
+        for (int r = 0; r < rounds; ++r) {
+          long long tw = 0;
+          if (prof) tw = clock64();
+          mbar_wait(empty0 + stage * 8, phase ^ 1u);
+          mbar_wait(empty0 + stage * 8 + 8, phase ^ 1u);
+          if (prof) t_wait += clock64() - tw;
+          if (elect_one()) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const int dy = n_kc == 2 ? r : j, kc = n_kc == 2 ? j : 0;
+              const uint32_t fb = full0 + (stage + j) * 8;
+              const uint32_t a_dst = tiles_addr + (stage + j) * stage_bytes;
+              const int kcol = (2 * dy * n_kc + kc) * 64;
+              if (leader) mbar_arrive_expect_tx(fb, tx_bytes);
+              tma_load_2d_pair(a_dst, &tmap_a, fb, kc * 64, row0 + (dy ? off_dy1 : off_dy0), kEvictNormal);
+              tma_load_2d_pair(a_dst + kABytes, &tmap_b, fb, kcol, b_row0, kEvictLast);
+              tma_load_2d_pair(a_dst + kABytes + b_bytes, &tmap_b, fb, kcol + n_kc * 64, b_row0, kEvictLast);
+            }
+          }
+          __syncwarp();
+          stage += 2;
+          if (stage == n_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    } else
     for (int tile = pair; tile < p.num_tiles; tile += n_pairs) {
       const int row0 = tile * (2 * kTileM) + static_cast<int>(rank) * kTileM;
 #pragma unroll 1
@@ -533,7 +570,56 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
       uint32_t stage = 0, phase = 0;
       int it = 0;
-      long long t_full = 0, t_tmem = 0, t_begin = prof ? clock64() : 0;
+      long long t_full = 0, t_tmem = 0, t_issue = 0, t_commit = 0, t_begin = prof ? clock64() : 0;
+      if (p.pair_issue) {
+        // ---- narrow layers: two stages (both chunks of a dy, or both dy of a one-chunk tile) per round; everything
+        // loop-invariant is hoisted so that a round costs ~100 instructions of bookkeeping for up to 16 MMAs
+        const int k0 = p.n_kc == 2 ? 4 : p.last_ksteps, k1 = p.last_ksteps;
+        const int rounds = p.n_kc;                              // rounds per tile: 2 (one per dy) or 1
+        const uint32_t stage_lo = stage_bytes >> 4, bdx_lo = b_bytes >> 4;
+        const uint32_t a_lo_base = desc_lo0 + ((tiles_addr & 0x3FFFFu) >> 4);
+        const uint32_t n_stages = static_cast<uint32_t>(p.stages);
+        for (int tile = pair; tile < p.num_tiles; tile += n_pairs, ++it) {
+          const int par = quad ? (it & 3) : (it & 1);
+          long long tw = 0;
+          if (prof) tw = clock64();
+          mbar_wait(smem_u32(&tmem_empty_bar[par]), ((quad ? it >> 2 : it >> 1) & 1) ^ 1u);
+          if (prof) t_tmem += clock64() - tw;
+          const uint32_t acc_base = tmem_base + (quad ? par * 128 : (par ? base1 : 0));
+          const uint32_t tfull = smem_u32(&tmem_full_bar[par]);
+#pragma unroll 1
+          for (int r = 0; r < rounds; ++r) {
+            if (prof) tw = clock64();
+            mbar_wait(full0 + stage * 8, phase);
+            mbar_wait(full0 + stage * 8 + 8, phase);
+            if (prof) t_full += clock64() - tw;
+            tc_fence_after();
+            const uint32_t a0 = a_lo_base + stage * stage_lo, b0 = a0 + (kABytes >> 4);
+            const uint32_t a1 = a0 + stage_lo, b1 = b0 + stage_lo;
+            if (elect_one()) {
+              const long long ti0 = prof ? clock64() : 0;
+              umma_f16_pair_entry<1, 2>(acc_base, acc_base, a0, b0, b0, desc_hi, desc_hi, idesc, idesc, r ? 1u : 0u, k0);
+              umma_f16_pair_entry<1, 2>(acc_base, acc_base, a0 + 8, b0 + bdx_lo, b0, desc_hi, desc_hi, idesc, idesc, 1u, k0);
+              umma_f16_pair_entry<1, 2>(acc_base, acc_base, a1, b1, b1, desc_hi, desc_hi, idesc, idesc, 1u, k1);
+              umma_f16_pair_entry<1, 2>(acc_base, acc_base, a1 + 8, b1 + bdx_lo, b1, desc_hi, desc_hi, idesc, idesc, 1u, k1);
+              const long long ti1 = prof ? clock64() : 0;
+              umma_commit_pair(empty0 + stage * 8);
+              umma_commit_pair(empty0 + stage * 8 + 8);
+              if (r == rounds - 1) umma_commit_pair(tfull);
+              if (prof) {
+                t_issue += ti1 - ti0;
+                t_commit += clock64() - ti1;
+              }
+            }
+            __syncwarp();
+            stage += 2;
+            if (stage == n_stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      } else
       for (int tile = pair; tile < p.num_tiles; tile += n_pairs, ++it) {
         const int par = quad ? (it & 3) : (it & 1);
         long long tw = 0;
@@ -559,6 +645,7 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             const uint32_t b_lo = desc_lo0 + (((a_addr + kABytes) & 0x3FFFFu) >> 4);
             const bool last = (dy == 1 && kc == p.n_kc - 1);
             if (elect_one()) {
+              const long long ti0 = prof ? clock64() : 0;
               // dx = 0: rows [0, 128) of the box; dx = 1: rows [1, 129) = start address + 128 B (+8 in the descriptor)
               if (p.n_parts == 2) {
                 umma_f16_pair_entry<2, 2>(acc_base, acc_base + p.n_part, a_lo, b_lo, b_lo + (part_bytes >> 4), desc_hi, desc_hi,
@@ -571,8 +658,13 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 umma_f16_pair_entry<1, 2>(acc_base, acc_base, a_lo + 8, b_lo + (b_bytes >> 4), b_lo, desc_hi_dx1, desc_hi,
                                           idesc, idesc, 1u, ksteps);
               }
+              const long long ti1 = prof ? clock64() : 0;
               umma_commit_pair(empty0 + stage * 8);
               if (last) umma_commit_pair(smem_u32(&tmem_full_bar[par]));
+              if (prof) {
+                t_issue += ti1 - ti0;
+                t_commit += clock64() - ti1;
+              }
             }
             accumulate = 1;
             __syncwarp();
@@ -587,6 +679,10 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         p.stats[blockIdx.x * 16 + 2] = clock64() - t_begin;   // MMA issuer total
         p.stats[blockIdx.x * 16 + 3] = t_full;                // ... waiting for TMA data
         p.stats[blockIdx.x * 16 + 4] = t_tmem;                // ... waiting for the epilogue to free TMEM
+      }
+      if (prof && t_issue) {                                  // the elected lane
+        p.stats[blockIdx.x * 16 + 12] = t_issue;              // ... inside the MMA asm blocks
+        p.stats[blockIdx.x * 16 + 13] = t_commit;             // ... inside the commits
       }
     }
   } else {
@@ -809,6 +905,10 @@ static int fill_params(const mmlf_conv_args* a, ConvParams& p) {
   }
   p.n_kc = a->split_in ? 3 * p.kc_term : p.kc_term;
   p.lo_col = a->split_in;
+  // Narrow layers (the 70-channel in-nets, the heads): a pipeline stage holds only 2-8 short MMAs and the issuing warp's
+  // per-stage bookkeeping (~500 cycles measured against ~200 tensor cycles) bounds the kernel, so it issues two stages
+  // per round: both chunks of a dy (n_kc = 2) or both dy of a tile (n_kc = 1).  Needs an even stage count.
+  p.pair_issue = (p.n_parts == 1 && p.n_kc <= 2 && !a->split_in && !getenv("MMLF_NO_PAIR_ISSUE")) ? 1 : 0;
   if (a->type == 0) {
     p.tap_off[0] = 0; p.tap_off[1] = 1; p.tap_off[2] = p.Wp; p.tap_off[3] = p.Wp + 1;
   } else {
@@ -906,6 +1006,7 @@ extern "C" int mmlf_conv2x2(const mmlf_conv_args* a, void* stream) {
   const uint32_t max_smem = 232448;   // 227 KB opt-in limit per CTA on sm_100
   int stages = static_cast<int>((max_smem - 1024 - tail_bytes) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
+  if (p.pair_issue) stages &= ~1;                         // rounds of two stages
   MMLF_REQUIRE(stages >= 2, "conv2x2: not enough shared memory for a 2-stage pipeline (n_pad %d)", p.n_pad);
   p.stages = stages;
   p.epi_off = stages * stage_bytes;                       // multiple of 1024 (stage_bytes = 17408 + n_pad * 128)

@@ -28,6 +28,7 @@ names = ['producer total', 'producer wait-empty', 'mma total', 'mma wait-full(TM
 print(f'{B}x{H}x{W} {cin}->{cout} type {ctype}: {e0.elapsed_time(e1)*1e3:.1f} us; tiles/pair = {np.ceil(n_slots/256)/74:.2f}')
 for i, n in enumerate(names):
     print(f'  {n:28s} leader {lead[:, i].mean():10.0f}  peer {peer[:, i].mean():10.0f} cycles')
+print(f'  mma issue blocks {lead[:, 12].mean():10.0f}   commits {lead[:, 13].mean():10.0f} cycles')
 print(f'  SM clock during the kernel: {lead[:, 0].mean() / lead[:, 7].mean() * 1e3:.0f} MHz (producer cycles / globaltimer ns)')
 t0 = s[:, 8].min()
 for nm, col in (('kernel entry', 8), ('main loop entry', 9), ('epilogue done', 10), ('kernel exit', 11)):
