@@ -509,41 +509,58 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
       }
     } else
-    for (int tile = pair; tile < p.num_tiles; tile += n_pairs) {
-      const int row0 = tile * (2 * kTileM) + static_cast<int>(rank) * kTileM;
+    {
+      // everything loop-invariant in registers: the producer's reaction time (stage freed -> loads issued) is on the
+      // critical path of the 3-stage pipeline of the wide layers
+      const int off_dy0 = p.tap_off[0], off_dy1 = p.tap_off[2];
+      const int n_kc = p.n_kc, kc_term = p.kc_term, lo_col = p.lo_col, dx_cols = p.n_kc * 64;
+      const bool two_parts = p.n_parts == 2;
+      const int b_row1 = p.n_part + b_row0;
+      const uint32_t part_dst = static_cast<uint32_t>(half_rows) * 128u;
+      const uint32_t n_stages = static_cast<uint32_t>(p.stages);
+      uint32_t a_dst = tiles_addr;                           // shared-memory address of the current stage
+      uint32_t eb = empty0, fb = full0;
+      for (int tile = pair; tile < p.num_tiles; tile += n_pairs) {
+        const int row0 = tile * (2 * kTileM) + static_cast<int>(rank) * kTileM;
+        int kcol = 0;
 #pragma unroll 1
-      for (int dy = 0; dy < 2; ++dy) {
-        // taps (2 dy, 2 dy + 1) read rows r and r + 1: one box of 136 rows feeds both
-        const int arow = row0 + p.tap_off[2 * dy];
-        int kcol = 2 * dy * p.n_kc * 64;
+        for (int dy = 0; dy < 2; ++dy) {
+          // taps (2 dy, 2 dy + 1) read rows r and r + 1: one box of 136 rows feeds both
+          const int arow = row0 + (dy ? off_dy1 : off_dy0);
+          // split precision: the K chunks of a tap are [hi | hi | lo] blocks of the activation columns
+          int kci = 0, term = 0;
 #pragma unroll 1
-        for (int kc = 0; kc < p.n_kc; ++kc, kcol += 64) {
-          long long tw = 0;
-          if (prof) tw = clock64();
-          mbar_wait(empty0 + stage * 8, phase ^ 1u);
-          if (prof) t_wait += clock64() - tw;
-          const uint32_t fb = full0 + stage * 8;
-          const uint32_t a_dst = tiles_addr + stage * stage_bytes;
-          const uint32_t b_dst = a_dst + kABytes;
-          if (elect_one()) {
-            if (leader) mbar_arrive_expect_tx(fb, tx_bytes);
-            // split precision: the K chunks of a tap are [hi | hi | lo] blocks of the activation columns
-            const int term = kc / p.kc_term;
-            const int a_col = (kc - term * p.kc_term) * 64 + (term == 2 ? p.lo_col : 0);
-            tma_load_2d_pair(a_dst, &tmap_a, fb, a_col, arow, kEvictNormal);
-#pragma unroll
-            for (int dx = 0; dx < 2; ++dx) {
-              const int kc_col = kcol + dx * p.n_kc * 64;
-              tma_load_2d_pair(b_dst + dx * b_bytes, &tmap_b, fb, kc_col, b_row0, kEvictLast);
-              if (p.n_parts == 2)
-                tma_load_2d_pair(b_dst + dx * b_bytes + half_rows * 128, &tmap_b, fb, kc_col, p.n_part + b_row0, kEvictLast);
+          for (int kc = 0; kc < n_kc; ++kc, kcol += 64) {
+            long long tw = 0;
+            if (prof) tw = clock64();
+            mbar_wait(eb, phase ^ 1u);
+            if (prof) t_wait += clock64() - tw;
+            if (elect_one()) {
+              if (leader) mbar_arrive_expect_tx(fb, tx_bytes);
+              tma_load_2d_pair(a_dst, &tmap_a, fb, kci * 64 + (term == 2 ? lo_col : 0), arow, kEvictNormal);
+              const uint32_t b_dst = a_dst + kABytes;
+              tma_load_2d_pair(b_dst, &tmap_b, fb, kcol, b_row0, kEvictLast);
+              if (two_parts) tma_load_2d_pair(b_dst + part_dst, &tmap_b, fb, kcol, b_row1, kEvictLast);
+              tma_load_2d_pair(b_dst + b_bytes, &tmap_b, fb, kcol + dx_cols, b_row0, kEvictLast);
+              if (two_parts) tma_load_2d_pair(b_dst + b_bytes + part_dst, &tmap_b, fb, kcol + dx_cols, b_row1, kEvictLast);
+            }
+            __syncwarp();
+            if (++kci == kc_term) {
+              kci = 0;
+              ++term;
+            }
+            a_dst += stage_bytes;
+            eb += 8;
+            fb += 8;
+            if (++stage == n_stages) {
+              stage = 0;
+              phase ^= 1u;
+              a_dst = tiles_addr;
+              eb = empty0;
+              fb = full0;
             }
           }
-          __syncwarp();
-          if (++stage == static_cast<uint32_t>(p.stages)) {
-            stage = 0;
-            phase ^= 1u;
-          }
+          kcol += dx_cols;                                   // skip the dx = 1 tap's columns of this dy
         }
       }
     }
@@ -619,7 +636,8 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             }
           }
         }
-      } else
+      } else {
+      const int n_kc = p.n_kc, kc_term = p.kc_term, last_ksteps = p.last_ksteps;
       for (int tile = pair; tile < p.num_tiles; tile += n_pairs, ++it) {
         const int par = quad ? (it & 3) : (it & 1);
         long long tw = 0;
@@ -633,17 +651,22 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         uint32_t accumulate = 0;
 #pragma unroll 1
         for (int dy = 0; dy < 2; ++dy) {
+          int kci = 0;                                         // chunk index inside the current split term
 #pragma unroll 1
-          for (int kc = 0; kc < p.n_kc; ++kc) {
+          for (int kc = 0; kc < n_kc; ++kc) {
             if (prof) tw = clock64();
             mbar_wait(full0 + stage * 8, phase);
             if (prof) t_full += clock64() - tw;
             tc_fence_after();
             const uint32_t a_addr = tiles_addr + stage * stage_bytes;
-            const int ksteps = ((kc + 1) % p.kc_term == 0) ? p.last_ksteps : 4;
+            int ksteps = 4;
+            if (++kci == kc_term) {
+              kci = 0;
+              ksteps = last_ksteps;
+            }
             const uint32_t a_lo = desc_lo0 + ((a_addr & 0x3FFFFu) >> 4);
             const uint32_t b_lo = desc_lo0 + (((a_addr + kABytes) & 0x3FFFFu) >> 4);
-            const bool last = (dy == 1 && kc == p.n_kc - 1);
+            const bool last = (dy == 1 && kc == n_kc - 1);
             if (elect_one()) {
               const long long ti0 = prof ? clock64() : 0;
               // dx = 0: rows [0, 128) of the box; dx = 1: rows [1, 129) = start address + 128 B (+8 in the descriptor)
@@ -674,6 +697,7 @@ conv2x2_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             }
           }
         }
+      }
       }
       if (prof && lane == 0) {
         p.stats[blockIdx.x * 16 + 2] = clock64() - t_begin;   // MMA issuer total
