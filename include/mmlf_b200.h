@@ -98,6 +98,19 @@ int mmlf_pack_conv_weight(const float* w, int cout, int cin, int spatial, int dg
 int mmlf_pack_conv_weight_split(const float* w, int cout, int cin, int spatial, int in_groups, int group_real,
                                 int group_pad, void* out, int n_pad, int cin_pad, float weight_scale, void* stream);
 
+/* All weight packings of a training / inference step in ONE launch (the per-layer calls above cost ~150 launches of
+ * 5-7 us per step, 2.5 % of a 64-patch step).  jobs: DEVICE array; a job = one mmlf_pack_conv_weight[_split] call,
+ * plus the zero-padded fp32 copy of the bias when bias / bias_pad are set. */
+typedef struct mmlf_pack_job {
+  const float* w;          /* (cout, cin, 2, 2) f32                                            */
+  void* out;               /* packed operand [n_pad][4 * terms * ceil(cin_pad / 64) * 64]      */
+  const float* bias;       /* (cout) f32 or NULL                                               */
+  float* bias_pad;         /* (n_pad) f32 or NULL: bias_pad[i] = i < cout ? bias[i] : 0        */
+  int cout, cin, spatial, dgrad, in_groups, group_real, group_pad, n_pad, cin_pad, dtype, split;
+  float weight_scale;      /* split only (else 1)                                              */
+} mmlf_pack_job;
+int mmlf_pack_conv_weights_batch(const mmlf_pack_job* jobs, int n_jobs, int64_t max_elems, void* stream);
+
 /* Inverse for gradients: dw_packed [n_pad][4][cin_pad] f32 (same tap/column convention, forward orientation)
  * -> canonical (cout, cin, 2, 2) f32; accumulate != 0 adds (two streams share one module). */
 int mmlf_unpack_conv_wgrad(const float* dw_packed, int n_pad, int cin_pad, int cout, int cin, int spatial,

@@ -49,6 +49,7 @@ _PROTOS = {
     'mmlf_shift_pack': (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_d, c_p, c_i, c_i, c_p]),
     'mmlf_pack_conv_weight': (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_p]),
     'mmlf_pack_conv_weight_split': (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_f, c_p]),
+    'mmlf_pack_conv_weights_batch': (c_i, [c_p, c_i, c_i64, c_p]),
     'mmlf_unpack_conv_wgrad': (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_p]),
     'mmlf_conv2x2': (c_i, [C.POINTER(ConvArgs), c_p]),
     'mmlf_conv2x2_simt': (c_i, [C.POINTER(ConvArgs), c_p]),

@@ -21,13 +21,13 @@ __host__ __device__ __forceinline__ int real_channel(int c, int groups, int grou
   return g * group_real + cc;
 }
 
-__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int cout, int cin, int spatial, int dgrad,
-                                        int groups, int group_real, int group_pad, uint16_t* __restrict__ out,
-                                        int n_pad, int n_kc, int dtype, int split, float wscale) {
+__device__ __forceinline__ void pack_conv_weight_elem(int64_t idx, const float* __restrict__ w, int cout, int cin,
+                                                      int spatial, int dgrad, int groups, int group_real, int group_pad,
+                                                      uint16_t* __restrict__ out, int n_pad, int n_kc, int dtype,
+                                                      int split, float wscale) {
   // split: three K blocks per tap, [w_hi | w_lo | w_hi]
   const int terms = split ? 3 : 1;
   const int k_total = 4 * terms * n_kc * 64;
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<int64_t>(n_pad) * k_total) return;
   const int row = static_cast<int>(idx / k_total);
   const int col = static_cast<int>(idx - static_cast<int64_t>(row) * k_total);
@@ -55,6 +55,27 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int cout, i
   v *= wscale;                                                      // power of two: exact
   if (split && term == 1) v -= from16(to16(v, kFP16), kFP16);      // residual of the fp16 rounding
   out[idx] = to16(v, split ? kFP16 : dtype);
+}
+
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int cout, int cin, int spatial, int dgrad,
+                                        int groups, int group_real, int group_pad, uint16_t* __restrict__ out,
+                                        int n_pad, int n_kc, int dtype, int split, float wscale) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  pack_conv_weight_elem(idx, w, cout, cin, spatial, dgrad, groups, group_real, group_pad, out, n_pad, n_kc, dtype, split, wscale);
+}
+
+// blockIdx.y = job, blockIdx.x strides over the job's elements (the grid is sized for a fraction of the largest job)
+__global__ void __launch_bounds__(256)
+pack_conv_weights_batch_kernel(const mmlf_pack_job* __restrict__ jobs) {
+  const mmlf_pack_job j = jobs[blockIdx.y];
+  const int n_kc = (j.cin_pad + 63) / 64;
+  const int64_t total = static_cast<int64_t>(j.n_pad) * 4 * (j.split ? 3 : 1) * n_kc * 64;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    pack_conv_weight_elem(idx, j.w, j.cout, j.cin, j.spatial, j.dgrad, j.in_groups, j.group_real, j.group_pad,
+                          reinterpret_cast<uint16_t*>(j.out), j.n_pad, n_kc, j.dtype, j.split, j.weight_scale);
+  if (j.bias_pad && blockIdx.x == 0)
+    for (int i = threadIdx.x; i < j.n_pad; i += blockDim.x) j.bias_pad[i] = (j.bias && i < j.cout) ? j.bias[i] : 0.f;
 }
 
 __global__ void unpack_conv_wgrad_kernel(const float* __restrict__ dwp, int n_pad, int cin_pad, int cout, int cin,
@@ -113,6 +134,15 @@ extern "C" int mmlf_pack_conv_weight_split(const float* w, int cout, int cin, in
   pack_conv_weight_kernel<<<static_cast<unsigned>(ceil_div64(total, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       w, cout, cin, spatial, 0, in_groups, group_real, group_pad, reinterpret_cast<uint16_t*>(out), n_pad, n_kc, kFP16, 1, weight_scale);
   return check_launch("pack_conv_weight_kernel(split)");
+}
+
+extern "C" int mmlf_pack_conv_weights_batch(const mmlf_pack_job* jobs, int n_jobs, int64_t max_elems, void* stream) {
+  static_assert(sizeof(mmlf_pack_job) == 80, "mmlf_pack_job layout (mirrored by mmlf_b200/engine.py::PackJob)");
+  MMLF_REQUIRE(jobs && n_jobs >= 1 && n_jobs <= 65535 && max_elems >= 1, "pack_conv_weights_batch: bad arguments");
+  // 16 elements per thread for the largest job: ~90 blocks per 280 x 280 layer, one wave for the whole network
+  const unsigned bx = static_cast<unsigned>(ceil_div64(max_elems, 256 * 16));
+  pack_conv_weights_batch_kernel<<<dim3(bx, static_cast<unsigned>(n_jobs)), 256, 0, static_cast<cudaStream_t>(stream)>>>(jobs);
+  return check_launch("pack_conv_weights_batch_kernel");
 }
 
 extern "C" int mmlf_unpack_conv_wgrad(const float* dw_packed, int n_pad, int cin_pad, int cout, int cin, int spatial,

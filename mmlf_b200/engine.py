@@ -30,6 +30,14 @@ def bits_words(n_pad):
     return (n_pad + 31) // 32
 
 
+class PackJob(C.Structure):
+    """Mirror of ``mmlf_pack_job`` (include/mmlf_b200.h): one weight packing of the batched launch."""
+    _fields_ = [('w', C.c_void_p), ('out', C.c_void_p), ('bias', C.c_void_p), ('bias_pad', C.c_void_p),
+                ('cout', C.c_int), ('cin', C.c_int), ('spatial', C.c_int), ('dgrad', C.c_int), ('in_groups', C.c_int),
+                ('group_real', C.c_int), ('group_pad', C.c_int), ('n_pad', C.c_int), ('cin_pad', C.c_int),
+                ('dtype', C.c_int), ('split', C.c_int), ('weight_scale', C.c_float)]
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
@@ -88,6 +96,7 @@ class Engine:
         self.wp = pad16(self.width)                     # 288
         assert self.feat_ld <= 320 and self.wp <= 320, 'model_chs too large for the 320-column TMEM plan'
         self._pack_version = None
+        self._pack_jobs = None
         self._fold_cache = {}
         self._param_cache = None
         self._buffer_cache = None
@@ -183,29 +192,38 @@ class Engine:
                 (self._pack_version[1] or not need_dgrad):
             return
         dev = next(iter(params.values())).device
-        st = _stream()
-        for cs in self.all_convs():
-            w = params[cs.name + '.weight'].detach()
-            b = params[cs.name + '.bias'].detach()
-            kc = cs.kc
-            if cs.w_fwd is None:
-                cs.w_fwd = torch.empty((cs.n_pad, 4 * kc * 64), dtype=torch.int16, device=dev)
-                cs.bias_pad = torch.zeros(cs.n_pad, dtype=torch.float32, device=dev)
-            if self.split:
-                if cs.w_split is None:
-                    cs.w_split = torch.empty((cs.n_pad, 4 * 3 * kc * 64), dtype=torch.int16, device=dev)
-                    cs.unscale = torch.full((cs.n_pad,), 1.0 / SPLIT_WSCALE, dtype=torch.float32, device=dev)
-                call('mmlf_pack_conv_weight_split', _ptr(w), cs.cout, cs.cin, cs.spatial, cs.groups, cs.group_real,
-                     cs.group_pad, _ptr(cs.w_split), cs.n_pad, cs.cin_pad, SPLIT_WSCALE, st)
-            call('mmlf_pack_conv_weight', _ptr(w), cs.cout, cs.cin, cs.spatial, 0, cs.groups, cs.group_real,
-                 cs.group_pad, _ptr(cs.w_fwd), cs.n_pad, cs.cin_pad, self.act, st)
-            cs.bias_pad[:cs.cout].copy_(b)
-            if need_dgrad:
-                kd = (cs.n_pad + 63) // 64
-                if cs.w_dgrad is None:
-                    cs.w_dgrad = torch.empty((cs.cin_pad, 4 * kd * 64), dtype=torch.int16, device=dev)
-                call('mmlf_pack_conv_weight', _ptr(w), cs.cout, cs.cin, cs.spatial, 1, cs.groups, cs.group_real,
-                     cs.group_pad, _ptr(cs.w_dgrad), cs.cin_pad, cs.n_pad, GRAD, st)
+        # every packing of the step (forward, split and data-gradient operands, padded biases) is one job of ONE
+        # launch; the job table lives on the device and is rebuilt only when a buffer moves
+        key = version[len(params):] + (bool(need_dgrad),)
+        if self._pack_jobs is None or self._pack_jobs[0] != key:
+            jobs = []
+            for cs in self.all_convs():
+                w = params[cs.name + '.weight'].detach()
+                b = params[cs.name + '.bias'].detach()
+                kc = cs.kc
+                if cs.w_fwd is None:
+                    cs.w_fwd = torch.empty((cs.n_pad, 4 * kc * 64), dtype=torch.int16, device=dev)
+                    cs.bias_pad = torch.zeros(cs.n_pad, dtype=torch.float32, device=dev)
+                if self.split:
+                    if cs.w_split is None:
+                        cs.w_split = torch.empty((cs.n_pad, 4 * 3 * kc * 64), dtype=torch.int16, device=dev)
+                        cs.unscale = torch.full((cs.n_pad,), 1.0 / SPLIT_WSCALE, dtype=torch.float32, device=dev)
+                    jobs.append(PackJob(w.data_ptr(), cs.w_split.data_ptr(), 0, 0, cs.cout, cs.cin, cs.spatial, 0, cs.groups,
+                                        cs.group_real, cs.group_pad, cs.n_pad, cs.cin_pad, 1, 1, SPLIT_WSCALE))
+                jobs.append(PackJob(w.data_ptr(), cs.w_fwd.data_ptr(), b.data_ptr(), cs.bias_pad.data_ptr(), cs.cout, cs.cin,
+                                    cs.spatial, 0, cs.groups, cs.group_real, cs.group_pad, cs.n_pad, cs.cin_pad, self.act, 0, 1.0))
+                if need_dgrad:
+                    kd = (cs.n_pad + 63) // 64
+                    if cs.w_dgrad is None:
+                        cs.w_dgrad = torch.empty((cs.cin_pad, 4 * kd * 64), dtype=torch.int16, device=dev)
+                    jobs.append(PackJob(w.data_ptr(), cs.w_dgrad.data_ptr(), 0, 0, cs.cout, cs.cin, cs.spatial, 1, cs.groups,
+                                        cs.group_real, cs.group_pad, cs.cin_pad, cs.n_pad, GRAD, 0, 1.0))
+            arr = (PackJob * len(jobs))(*jobs)
+            table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+            max_elems = max(j.n_pad * 4 * (3 if j.split else 1) * ((j.cin_pad + 63) // 64) * 64 for j in jobs)
+            self._pack_jobs = (key, table, len(jobs), max_elems)
+        _, table, n_jobs, max_elems = self._pack_jobs
+        call('mmlf_pack_conv_weights_batch', _ptr(table), n_jobs, max_elems, _stream())
         self._pack_version = (version, bool(need_dgrad))
 
     def _bn_padded(self, prefix, C_real, C, dev):

@@ -58,6 +58,45 @@ def test_lf_shift_golden(golden):
         assert np.array_equal(res[6].cpu().numpy(), g[f'mpi{j}'])
 
 
+def test_batched_weight_packing_equals_the_per_layer_calls():
+    """mmlf_pack_conv_weights_batch (one launch for all layers of a step) == mmlf_pack_conv_weight[_split] per layer."""
+    u = _u()
+    from mmlf_b200.engine import PackJob
+    rng = np.random.RandomState(2)
+    cases = [(70, 27, 1, 0, 0, u.FP16), (70, 70, 2, 0, 0, u.FP16), (280, 280, 0, 0, 0, u.BF16), (280, 280, 0, 1, 0, u.BF16),
+             (108, 280, 0, 0, 0, u.FP16), (2, 280, 0, 1, 0, u.BF16), (70, 70, 0, 0, 1, u.FP16)]
+    jobs, refs, outs, keep = [], [], [], []
+    for cout, cin, spatial, dgrad, split, dt in cases:
+        w = rng.normal(0, 0.1, (cout, cin, 2, 2)).astype(np.float32)
+        b = rng.normal(0, 0.1, cout).astype(np.float32)
+        wd, bd = torch.from_numpy(w).cuda(), torch.from_numpy(b).cuda()
+        n_pad, cin_pad = (u.pad16(cout), u.pad16(cin)) if not dgrad else (u.pad16(cin), u.pad16(cout))
+        kc = (cin_pad + 63) // 64
+        out = torch.zeros((n_pad, 4 * (3 if split else 1) * kc * 64), dtype=torch.int16, device='cuda')
+        bias_pad = torch.full((n_pad,), 7.0, device='cuda')
+        if split:
+            ref = torch.zeros_like(out)
+            u.call('mmlf_pack_conv_weight_split', u.ptr(wd), cout, cin, spatial, 1, cin, u.pad16(cin), u.ptr(ref), n_pad, cin_pad,
+                   64.0, u.stream())
+        else:
+            ref = u.pack_weight(w, spatial=spatial, dgrad=dgrad, n_pad=n_pad, cin_pad=cin_pad, dt=dt).view(torch.int16)
+        jobs.append(PackJob(wd.data_ptr(), out.data_ptr(), 0 if dgrad else bd.data_ptr(), 0 if dgrad else bias_pad.data_ptr(),
+                            cout, cin, spatial, dgrad, 1, cin, u.pad16(cin), n_pad, cin_pad, dt, split, 64.0 if split else 1.0))
+        refs.append((ref, b, dgrad, cout))
+        outs.append((out, bias_pad))
+        keep += [wd, bd]
+    arr = (PackJob * len(jobs))(*jobs)
+    table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).cuda()
+    max_elems = max(o.numel() for o, _ in outs)
+    u.call('mmlf_pack_conv_weights_batch', u.ptr(table), len(jobs), max_elems, u.stream())
+    torch.cuda.synchronize()
+    for (ref, b, dgrad, cout), (out, bias_pad) in zip(refs, outs):
+        assert torch.equal(out, ref.reshape(out.shape))
+        if not dgrad:
+            bp = bias_pad.cpu().numpy()
+            assert np.array_equal(bp[:cout], b) and not bp[cout:].any()
+
+
 def test_texture_mask(golden):
     from mmlf_b200 import ops
     from mmlf_b200.data import hci4d
