@@ -465,12 +465,21 @@ class Engine:
             return rec
         gamma, beta = params[bnp + '.weight'].detach(), params[bnp + '.bias'].detach()
         rmean, rvar = bufs[bnp + '.running_mean'], bufs[bnp + '.running_var']
-        if not bn_train:
+        if not bn_train and not save:
             # eval: BN folded into the conv epilogue, y = relu(acc * scale + shift)
             scale, shift = self._eval_fold(bnp, c2, gamma, beta, rmean, rvar)
             self.conv(geo, a1, c1.n_pad, c2, c2.w_fwd, Cp, c2.cin_pad, 1, y, ld_y, scale=scale, shift=shift, relu=True)
-            if save:
-                raise NotImplementedError('--train_eval_mode (training through eval-mode BatchNorm) is not supported')
+            return rec
+        if not bn_train:
+            # --train_eval_mode (train/cli.py:227-230): gradients through a BatchNorm that normalises with its RUNNING
+            # statistics.  Same tape as the training path (z kept, ReLU mask recomputed from it), the constants come
+            # from the running statistics and the backward pass drops the batch-mean terms (bn_bwd_apply train = 0).
+            scale, shift, save_mean, save_invstd = self._eval_consts(bnp, c2, gamma, beta, rmean, rvar)
+            z = self._slots(geo, Cp)
+            self.conv(geo, a1, c1.n_pad, c2, c2.w_fwd, Cp, c2.cin_pad, 1, z, Cp, bias=c2.bias_pad)
+            call('mmlf_bn_apply_relu', _ptr(z), Cp, _ptr(scale), _ptr(shift), Cp, geo.B, geo.H, geo.W, self.act, _ptr(y),
+                 ld_y, _ptr(yg) if dual else C.c_void_p(0), ld_y, GRAD, st)
+            rec.update(z=z, scale=scale, shift=shift, save_mean=save_mean, save_invstd=save_invstd, bn_eval=True)
             return rec
         k = self._fwd_bn_idx
         self._fwd_bn_idx += 1
@@ -505,6 +514,18 @@ class Engine:
              _ptr(c2.bias_pad), float(self.m.bn_eps), _ptr(scale), _ptr(shift), _stream())
         self._fold_cache[bnp] = (key, scale, shift)
         return scale, shift
+
+    def _eval_consts(self, bnp, c2, gamma, beta, rmean, rvar):
+        """Eval-mode BN constants for a differentiable forward: scale / shift applied to z (conv bias included in z),
+        and the running mean / inverse standard deviation on the padded channel pitch."""
+        Cp, Cr = c2.n_pad, c2.cout
+        consts = torch.zeros((4, Cp), dtype=torch.float32, device=self.dev)
+        scale, shift, mean, invstd = consts[0], consts[1], consts[2], consts[3]
+        call('mmlf_bn_fold_eval', Cr, Cp, _ptr(gamma), _ptr(beta), _ptr(rmean), _ptr(rvar), C.c_void_p(0),
+             float(self.m.bn_eps), _ptr(scale), _ptr(shift), _stream())
+        mean[:Cr].copy_(rmean)
+        invstd[:Cr].copy_(torch.rsqrt(rvar + float(self.m.bn_eps)))
+        return scale, shift, mean, invstd
 
     # ------------------------------------------------------------------ backward
     def backward(self, tape, g_out):
@@ -589,7 +610,8 @@ class Engine:
         def bn_of(prev_rec, cin_pad):
             """BatchNorm whose output feeds a conv with `cin_pad` input channels: its backward statistics can come out
             of that conv's data-gradient epilogue (saves one read of the gradient and of z per BN layer)."""
-            if not self.fuse_bn_bwd or prev_rec is None or 'z' not in prev_rec or prev_rec['c2'].n_pad != cin_pad:
+            if not self.fuse_bn_bwd or prev_rec is None or 'z' not in prev_rec or prev_rec['c2'].n_pad != cin_pad \
+                    or prev_rec.get('bn_eval'):
                 return None, None
             if cin_pad < 256:
                 # narrow layers are epilogue bound already: measured 0.075 -> 0.105 ms for the 70-channel data gradient
@@ -650,7 +672,7 @@ class Engine:
                 db2 = take('z32', z32, Cp)
                 call('mmlf_bn_bwd_apply', _ptr(gy), ld_gy, _ptr(rec['z']), Cp, _ptr(rec['scale']), _ptr(rec['shift']),
                      _ptr(gpad), _ptr(rec['save_mean']), _ptr(rec['save_invstd']), _ptr(sums), geo.count,
-                     1 if pre_sums is None else 2, C_real, Cp,
+                     0 if rec.get('bn_eval') else (1 if pre_sums is None else 2), C_real, Cp,
                      geo.B, geo.H, geo.W, GRAD, self.act, _ptr(dz), Cp, _ptr(dgam), _ptr(dbet), _ptr(fsums), _ptr(db2),
                      st)
                 if acc:

@@ -86,8 +86,6 @@ def main(output_dir, max_iterations, gpu_augment, **kwargs):
     assert not (kwargs['train_loss_strongest'] and kwargs['train_loss_multimodal'])
     if kwargs['model_invertible']:
         raise NotImplementedError('INNs are not supported anymore')          # train/cli.py:252
-    if kwargs['train_eval_mode']:
-        raise NotImplementedError('--train_eval_mode is not supported by the B200 path')
     kwargs['model_radius'] = (kwargs['model_in_blocks'] + kwargs['model_out_blocks']) * ((kwargs['model_ksize'] + 1) // 2)
     if kwargs['val_ensamble']:
         kwargs['model_uncert'] = True                                          # train/cli.py:68-69
@@ -183,7 +181,10 @@ def main(output_dir, max_iterations, gpu_augment, **kwargs):
                     mask_padding = (torch.abs(gt) < kwargs['train_loss_padding']).int()
             if kwargs['train_loss_multimodal']:
                 gt = mpi
-            model.train()
+            if kwargs['train_eval_mode'] and i >= kwargs['train_eval_mode_start']:   # train/cli.py:227-230
+                model.eval()
+            else:
+                model.train()
             if kwargs['train_warm_start'] and i <= 1000:                      # train/cli.py:233-236
                 for g in optimizer.param_groups:
                     g['lr'] = kwargs['train_lr'] * float(i) / 1000.0

@@ -211,6 +211,32 @@ def gen_net():
     save('net_tiny_base_nobn.npz', **_run_net(kw, 11, 2, 20, 20, 21, store_state=True, wscale=2.8))
 
 
+def gen_evalmode():
+    """--train_eval_mode (train/cli.py:227-230): the training step with the model in eval() mode, i.e. gradients through
+    BatchNorm layers that normalise with their running statistics (which must not change)."""
+    kw = fx.model_kwargs('base', False, chs=8)
+    torch.manual_seed(0)
+    model = FeedForward(**kw)
+    with torch.no_grad():
+        fx.perturb_state(model.state_dict(), 11, wscale=2.0)
+        _calibrate_bn(model, kw, 11, 20, 20)
+    out = {'state/' + k: v.numpy().copy() for k, v in model.state_dict().items()}
+    h, v, i, d, gt = fx.synth_batch(23, 2, 20, 20)
+    mask = fx.synth_mask(24, 2, 20, 20)
+    model.eval()
+    o = model(T(h), T(v), T(i), T(d))
+    lossv = _loss_for('base', False)(o, T(gt), T(mask))
+    lossv.backward()
+    out['loss'] = np.array(lossv.item(), np.float64)
+    out['mean'] = o['mean'].detach().numpy()
+    for name, p in model.named_parameters():
+        out['grad/' + name] = p.grad.numpy()
+    for k, vv in model.state_dict().items():
+        if 'running' in k or 'num_batches' in k:
+            assert np.array_equal(vv.numpy(), out['state/' + k])          # eval mode leaves the statistics alone
+    save('net_tiny_base_evalmode.npz', **out)
+
+
 # ---------------------------------------------------------------------------- losses
 def gen_losses():
     rng = np.random.RandomState(17)
@@ -415,6 +441,6 @@ def gen_cli():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['indices', 'shift', 'bins', 'net', 'losses', 'ese', 'adam', 'checkpoint', 'texture', 'augment', 'metrics', 'cli']
+    which = sys.argv[1:] or ['indices', 'shift', 'bins', 'net', 'losses', 'ese', 'adam', 'checkpoint', 'texture', 'augment', 'metrics', 'evalmode', 'cli']
     for w in which:
         globals()['gen_' + w]()

@@ -165,7 +165,9 @@ class FeedForwardOracle:
             zq = self._q(z)                                   # CUDA path stores z as bf16, stats from fp32
         else:
             mean, var = self.p[prefix + '.3.running_mean'], self.p[prefix + '.3.running_var']
-            zq = z                                            # eval: BN folded into the conv epilogue
+            # eval: BN folded into the conv epilogue (z never stored); a differentiable eval-mode forward
+            # (--train_eval_mode) keeps z for the backward pass in the activation format like the training path
+            zq = self._q(z) if getattr(self, '_keep_z', False) else z
         invstd = (1.0 / np.sqrt(var.astype(np.float64) + self.eps)).astype(np.float32)
         xhat = (zq - mean) * invstd
         y = self._q(np.maximum(xhat * g + be, 0))
@@ -208,6 +210,7 @@ class FeedForwardOracle:
     # -- forward (feed_forward.py:206-305) ---------------------------------------
     def forward(self, h_views, v_views, i_views=None, d_views=None, keep_tape=False):
         b, n, c, h, w = h_views.shape
+        self._keep_z = keep_tape
         nhwc = lambda t: self._q(np.ascontiguousarray(  # noqa: E731
             t.reshape(b, n * c, h, w).transpose(0, 2, 3, 1)))
         tapes = {}

@@ -413,6 +413,44 @@ def test_fused_bn_backward_statistics_match_the_standalone_reduction(golden):
     assert cos > 0.999, cos
 
 
+def test_train_eval_mode_gradients(golden):
+    """--train_eval_mode (train/cli.py:227-230): backward through eval-mode BatchNorm (running statistics, no batch-mean
+    terms) against the reference's autograd and the emulating oracle; the running statistics must not move."""
+    from mmlf_b200.model import loss as L
+    g = golden('net_tiny_base_evalmode.npz')
+    kw = fx.model_kwargs('base', False, chs=8)
+    state = _state(g)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    h, v, i, d, gt = fx.synth_batch(23, 2, 20, 20)
+    mask = fx.synth_mask(24, 2, 20, 20)
+    m = _build(kw, state)
+    m.eval()
+    out = m(T(h), T(v), T(i), T(d))
+    lossv = L.MaskedL1Loss()(out, T(gt), T(mask))
+    lossv.backward()
+    emu = oracle.FeedForwardOracle(state, quant='fp16')
+    e = emu.forward(h, v, i, d, keep_tape=True)
+    ev, eg = olosses.masked_l1({'mean': e['mean'], 'logvar': None, 'scores': None}, gt, mask)
+    egrads = emu.backward(eg['mean'][:, None])
+    assert abs(lossv.item() - float(g['loss'])) <= 0.01 * abs(float(g['loss'])) + 2e-3
+    assert abs(lossv.item() - float(ev)) <= 0.005 * abs(float(ev)) + 2e-3
+    acc = {'gr': 0.0, 'ge': 0.0, 'gg': 0.0, 'rr': 0.0, 'ee': 0.0}
+    for pname, p in m.named_parameters():
+        got = p.grad.cpu().numpy().astype(np.float64)
+        assert np.isfinite(got).all(), pname
+        ref, em = g['grad/' + pname].astype(np.float64), egrads[pname].astype(np.float64)
+        acc['gr'] += (got * ref).sum(); acc['ge'] += (got * em).sum(); acc['gg'] += (got ** 2).sum()   # noqa: E702
+        acc['rr'] += (ref ** 2).sum(); acc['ee'] += (em ** 2).sum()                                    # noqa: E702
+    cos_ref = acc['gr'] / np.sqrt(acc['gg'] * acc['rr'])
+    cos_emu = acc['ge'] / np.sqrt(acc['gg'] * acc['ee'])
+    report(test='net_tiny_base_evalmode', mode='train_eval_mode', key='grads', cos_vs_ref=cos_ref, cos_vs_emu=cos_emu)
+    assert cos_emu >= 0.93 and cos_ref >= 0.85, f'gradient cosine vs emu {cos_emu:.4f} vs ref {cos_ref:.4f}'
+    sd = m.state_dict()
+    for k, val in state.items():
+        if 'running' in k or 'num_batches' in k:
+            assert np.array_equal(sd[k].cpu().numpy(), val), k
+
+
 def test_no_cpu_fallback():
     from mmlf_b200.model.feed_forward import FeedForward
     m = FeedForward(**fx.model_kwargs('base', False, chs=8))
