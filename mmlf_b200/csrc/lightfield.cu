@@ -235,8 +235,9 @@ __device__ __forceinline__ void wlerp4(const float (&f)[8], int o, int d0, int d
     default: g[0] = f[3]; g[1] = f[4]; g[2] = f[5]; g[3] = f[6]; g[4] = f[7]; break;
   }
   if (d0 == 0) {
+    // (a select, not g[j + d1]: a run-time index would move the window to local memory)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) t[j] = lerp2(g[j], w0, g[j + d1], w1);
+    for (int j = 0; j < 4; ++j) t[j] = lerp2(g[j], w0, d1 ? g[j + 1] : g[j], w1);
   } else {
 #pragma unroll
     for (int j = 0; j < 4; ++j) t[j] = lerp2(g[j + 1], w0, g[j], w1);
@@ -244,15 +245,16 @@ __device__ __forceinline__ void wlerp4(const float (&f)[8], int o, int d0, int d
 }
 
 template <int R>
-__global__ void __launch_bounds__(256) lf_shift_vec_kernel(const ShiftParams p, int64_t total) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
+__global__ void __launch_bounds__(256) lf_shift_vec_kernel(const ShiftParams p, int planes) {
+  // grid: x = blocks of 256 threads inside a plane, (y, z) = plane; the plane decode is block-uniform and the in-plane
+  // index needs one 32-bit division (the flat 64-bit index cost ~300 of the kernel's 680 instructions per thread)
   const int W = p.W, H = p.H, w4 = W >> 2;
   const int nyb = (H + R - 1) / R;
-  const int x0 = static_cast<int>(i % w4) * 4;
-  const int64_t q = i / w4;
-  const int yb = static_cast<int>(q % nyb);
-  int pl = static_cast<int>(q / nyb);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int pl = blockIdx.z * gridDim.y + blockIdx.y;
+  if (i >= nyb * w4 || pl >= planes) return;
+  const int yb = i / w4;
+  const int x0 = (i - yb * w4) * 4;
   const int planes_per_stack = p.batch * p.n * 3;
   const int stack = pl / planes_per_stack;
   pl -= stack * planes_per_stack;
@@ -584,14 +586,23 @@ extern "C" int mmlf_lf_shift(const float* src_h, const float* src_v, const float
         rows_per_thread = e ? atoi(e) : 4;
       }
       const int R = rows_per_thread;
-      const int64_t total = planes * ceil_div(H, R) * (W / 4);
-      MMLF_REQUIRE(ceil_div64(total, 256) < (1ll << 31), "lf_shift: too many planes");
-      const unsigned grid = static_cast<unsigned>(ceil_div64(total, 256));
+      const int64_t in_plane = static_cast<int64_t>(ceil_div(H, R)) * (W / 4);
+      MMLF_REQUIRE(in_plane < (1ll << 30) && planes < (1ll << 30), "lf_shift: too many planes / pixels");
+      const unsigned gy = planes < 32768 ? static_cast<unsigned>(planes) : 32768u;
+      // block size with the fewest idle threads in a plane's last block (96-px patches: 576 threads = 3 x 192)
+      unsigned bs = 256;
+      int64_t waste = ceil_div64(in_plane, 256) * 256 - in_plane;
+      for (unsigned c : {192u, 128u}) {
+        const int64_t w = ceil_div64(in_plane, c) * c - in_plane;
+        if (w < waste) { waste = w; bs = c; }
+      }
+      const dim3 grid(static_cast<unsigned>(ceil_div64(in_plane, bs)), gy, static_cast<unsigned>(ceil_div64(planes, gy)));
+      const int np = static_cast<int>(planes);
       cudaStream_t st = static_cast<cudaStream_t>(stream);
-      if (R == 1) lf_shift_vec_kernel<1><<<grid, 256, 0, st>>>(p, total);
-      else if (R == 2) lf_shift_vec_kernel<2><<<grid, 256, 0, st>>>(p, total);
-      else if (R == 8) lf_shift_vec_kernel<8><<<grid, 256, 0, st>>>(p, total);
-      else lf_shift_vec_kernel<4><<<grid, 256, 0, st>>>(p, total);
+      if (R == 1) lf_shift_vec_kernel<1><<<grid, bs, 0, st>>>(p, np);
+      else if (R == 2) lf_shift_vec_kernel<2><<<grid, bs, 0, st>>>(p, np);
+      else if (R == 8) lf_shift_vec_kernel<8><<<grid, bs, 0, st>>>(p, np);
+      else lf_shift_vec_kernel<4><<<grid, bs, 0, st>>>(p, np);
       return check_launch("lf_shift_vec_kernel");
     }
   }
