@@ -26,10 +26,10 @@ import numpy as np  # noqa: E402
 
 ESE_MEMBERS = 70
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the ncu --set full capture
-# profiles/ncu_conv280_r01d.txt (not measurable inside an un-profiled run)
-CONV_TRAFFIC = {'bytes': 652835328,
-                'note': 'ncu capture profiles/ncu_conv280_r01d.txt: conv2x2_tc2 280->280 pad 0 on 64x96x96 patches, 347.7 MB '
-                        'read + 305.2 MB written per launch against 693.7 MB algorithmic (activations in + out; the 663 KB '
+# profiles/ncu_conv280_r01g.txt (not measurable inside an un-profiled run)
+CONV_TRAFFIC = {'bytes': 653180160,
+                'note': 'ncu capture profiles/ncu_conv280_r01g.txt: conv2x2_tc2 280->280 pad 0 on 64x96x96 patches, 347.7 MB '
+                        'read + 305.5 MB written per launch against 693.7 MB algorithmic (activations in + out; the 663 KB '
                         'weight operand stays in L2)'}
 FULL_KW = dict(model_ksize=2, model_in_blocks=3, model_out_blocks=8, model_chs=70, model_views=9, model_cross=False,
                model_uncert=False, model_unet=False, model_discrete=False, model_no_batchnorm=False,
