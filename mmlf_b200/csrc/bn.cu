@@ -5,6 +5,7 @@
 // reads contiguous runs of the channel-last rows.
 #include "../../include/mmlf_b200.h"
 #include "common.cuh"
+#include <stdlib.h>
 #include "host_util.h"
 
 namespace mmlf {
@@ -339,10 +340,15 @@ static SlotDiv make_div(int Hp, int Wp, int64_t n_slots) {
   d.exact = n_slots < (1 << 24);
   return d;
 }
-static int map_grid(int64_t n_slots, int C) {
+// Grid of the slot passes: enough blocks for >= 4 slots per thread, capped at `per_sm` blocks per SM.  Measured on B200
+// (64 x 96 x 96 patches): the light passes (BN apply, ReLU backward, convert: 16 resident blocks per SM) are fastest with
+// many short blocks; the BatchNorm-backward apply pass (119 registers: two resident blocks per SM, 40 per-channel
+// constants to load and a shared-memory column reduction + atomics per block) and the column reductions gain 8-16 %
+// as persistent grids of two blocks per SM (C = 280: 0.228 -> 0.205 ms and 0.142 -> 0.131 ms).
+static int map_grid(int64_t n_slots, int C, int per_sm = 16) {
   const int lanes = 256 / (C / 8);
   int64_t want = ceil_div64(n_slots, static_cast<int64_t>(lanes) * 4);     // >= 4 slots per thread
-  const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * per_sm;
   if (want > cap) want = cap;
   if (want < 1) want = 1;
   return static_cast<int>(want);
@@ -350,7 +356,7 @@ static int map_grid(int64_t n_slots, int C) {
 
 static int red_grid(int64_t n_slots, int lanes) {
   int64_t want = ceil_div64(n_slots, static_cast<int64_t>(lanes) * 8);
-  int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+  int64_t cap = static_cast<int64_t>(sm_count()) * 2;
   if (want > cap) want = cap;
   if (want < 1) want = 1;
   return static_cast<int>(want);
@@ -464,7 +470,7 @@ extern "C" int mmlf_bn_bwd_apply(const void* dy, int ld_dy, const void* z, int l
   MMLF_REQUIRE(dy && z && scale && shift && gamma && save_mean && save_invstd && sums && dz, "bn_bwd_apply: null buffer");
   CHECK_C(C);
   const int64_t n_slots = static_cast<int64_t>(B) * (H + 1) * (W + 1);
-  const int blocks = map_grid(n_slots, C);
+  const int blocks = map_grid(n_slots, C, 2);
   const SlotDiv dv = make_div(H + 1, W + 1, n_slots);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   MMLF_REQUIRE(fsums != nullptr, "bn_bwd_apply: fsums scratch (float[2*C]) required");
