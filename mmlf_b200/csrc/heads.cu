@@ -211,6 +211,67 @@ __global__ void dpp_head_kernel(const float* __restrict__ scores, const float* _
   logvar[idx] = logf(acc);
 }
 
+// Shared-memory variant (HW % 128 == 0, 16-byte aligned scores): the block's [steps][128 pixels] score tile is fetched
+// ONCE with 16-byte cp.async (no registers, the whole 55 KB tile in flight per block) and all three passes run from
+// shared memory.  The single-pass-per-plane kernel above re-read the scores for passes 2 and 3 and, at 255 MB per launch
+// against 126 MB of L2, most of those re-reads went to DRAM (ncu: 714 MB read for 257 MB algorithmic).
+constexpr int kHeadTile = 128;
+
+__global__ void __launch_bounds__(kHeadTile)
+dpp_head_smem_kernel(const float* __restrict__ scores, const float* __restrict__ bins_t, const float* __restrict__ bins_n,
+                     int steps, int64_t HW, float* __restrict__ one_hot, float* __restrict__ post,
+                     float* __restrict__ mean, float* __restrict__ logvar) {
+  extern __shared__ __align__(16) float hs[];         // tile [steps][128] | bins_t | bins_n
+  float* tile = hs;
+  float* sb = hs + static_cast<size_t>(steps) * kHeadTile;
+  const int64_t idx0 = static_cast<int64_t>(blockIdx.x) * kHeadTile;     // first pixel of the block (never straddles b)
+  const int64_t b = idx0 / HW, pix0 = idx0 - b * HW;
+  const float* s = scores + b * steps * HW + pix0;
+  for (int i = threadIdx.x; i < steps * (kHeadTile / 4); i += kHeadTile) {
+    const int c = i / (kHeadTile / 4), q = i - c * (kHeadTile / 4);
+    const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(tile + c * kHeadTile + 4 * q));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(s + static_cast<int64_t>(c) * HW + 4 * q) : "memory");
+  }
+  for (int i = threadIdx.x; i < steps; i += kHeadTile) {
+    sb[i] = bins_t[i];
+    sb[steps + i] = bins_n[i];
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  float* col = tile + threadIdx.x;                    // this thread's pixel: conflict-free column walk
+  float mx = -INFINITY, z = 0.f;
+#pragma unroll 4
+  for (int c = 0; c < steps; ++c) {
+    const float v = col[c * kHeadTile];
+    mx = fmaxf(mx, v);
+    z += __expf(v);                                   // unstabilised, as the reference
+  }
+  const float rz = 1.f / z;
+  const int64_t o0 = b * steps * HW + pix0 + threadIdx.x;
+  float* ohp = one_hot ? one_hot + o0 : nullptr;
+  float* pp = post ? post + o0 : nullptr;
+  float mu = 0.f;
+#pragma unroll 4
+  for (int c = 0; c < steps; ++c) {
+    const float v = col[c * kHeadTile];
+    const float oh = (v == mx) ? 1.f : 0.f;           // ties give a multi-hot vector
+    mu += sb[c] * oh;
+    const float pc = __expf(v) * rz;
+    col[c * kHeadTile] = pc;                          // pass 3 reads the posterior back
+    if (ohp) __stcs(ohp + static_cast<int64_t>(c) * HW, oh);
+    if (pp) __stcs(pp + static_cast<int64_t>(c) * HW, pc);
+  }
+  float acc = 0.f;
+#pragma unroll 4
+  for (int c = 0; c < steps; ++c) {
+    const float d = sb[steps + c] - mu;
+    acc = fmaf(d * d, col[c * kHeadTile], acc);
+  }
+  mean[idx0 + threadIdx.x] = mu;
+  logvar[idx0 + threadIdx.x] = logf(acc);
+}
+
 // ---------------------------------------------------------------------------- DPP targets
 __global__ void reg_to_class_kernel(const float* __restrict__ gt, const float* __restrict__ bins, int steps,
                                     float half_step, int64_t B, int64_t HW, float* __restrict__ out) {
@@ -329,6 +390,18 @@ extern "C" int mmlf_upr_posterior(const float* mean, const float* logvar, const 
 extern "C" int mmlf_dpp_head(const float* scores, const float* bins_t, const float* bins_n, int steps, int64_t B,
                              int64_t HW, float* one_hot, float* posterior, float* mean, float* logvar, void* stream) {
   MMLF_REQUIRE(scores && bins_t && bins_n && mean && logvar, "dpp_head: null buffer");
+  const size_t tile_smem = (static_cast<size_t>(steps) * kHeadTile + 2 * steps) * sizeof(float);
+  if (HW % kHeadTile == 0 && tile_smem <= 200 * 1024 && reinterpret_cast<uintptr_t>(scores) % 16 == 0) {
+    static size_t configured = 0;
+    if (tile_smem > 48 * 1024 && tile_smem > configured) {
+      cudaError_t e = cudaFuncSetAttribute(dpp_head_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      MMLF_REQUIRE(e == cudaSuccess, "dpp_head: %s", cudaGetErrorString(e));
+      configured = 200 * 1024;
+    }
+    dpp_head_smem_kernel<<<static_cast<unsigned>(B * HW / kHeadTile), kHeadTile, tile_smem, static_cast<cudaStream_t>(stream)>>>(
+        scores, bins_t, bins_n, steps, HW, one_hot, posterior, mean, logvar);
+    return check_launch("dpp_head_smem");
+  }
   dpp_head_kernel<<<blocks_for(B * HW, 128), 128, 2 * steps * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       scores, bins_t, bins_n, steps, B, HW, one_hot, posterior, mean, logvar);
   return check_launch("dpp_head");

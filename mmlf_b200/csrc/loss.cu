@@ -198,6 +198,73 @@ loss_ce_kernel(const float* __restrict__ scores, const float* __restrict__ targe
   if (threadIdx.x == 0) atomicAdd(loss_sum, r);
 }
 
+// Shared-memory variant (HW % 128 == 0, 16-byte aligned inputs): the block's [steps][128 pixels] score tile (and the
+// dense target tile, if there is one) is fetched once with 16-byte cp.async and both passes -- value, then gradient --
+// run from shared memory; same arithmetic, in the same order, as loss_ce_kernel.
+constexpr int kCeTile = 128;
+
+__global__ void __launch_bounds__(kCeTile)
+loss_ce_smem_kernel(const float* __restrict__ scores, const float* __restrict__ target, const float* __restrict__ gt,
+                    const float* __restrict__ bins, float half_step, int steps, const int32_t* __restrict__ mask,
+                    const double* __restrict__ sums, int64_t HW, double* __restrict__ loss_sum,
+                    float* __restrict__ g_scores) {
+  __shared__ double red[4];
+  extern __shared__ __align__(16) float cs[];        // scores tile [steps][128] | target tile (dense) | bins
+  float* tile = cs;
+  float* ttile = target ? cs + static_cast<size_t>(steps) * kCeTile : nullptr;
+  float* sb = cs + static_cast<size_t>(steps) * kCeTile * (target ? 2 : 1);
+  const int64_t idx0 = static_cast<int64_t>(blockIdx.x) * kCeTile;
+  const int64_t b = idx0 / HW, pix0 = idx0 - b * HW;
+  const int64_t base = b * steps * HW + pix0;
+  for (int i = threadIdx.x; i < steps * (kCeTile / 4); i += kCeTile) {
+    const int c = i / (kCeTile / 4), q = i - c * (kCeTile / 4);
+    const int64_t off = base + static_cast<int64_t>(c) * HW + 4 * q;
+    const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(tile + c * kCeTile + 4 * q));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(scores + off) : "memory");
+    if (target) {
+      const uint32_t dst2 = static_cast<uint32_t>(__cvta_generic_to_shared(ttile + c * kCeTile + 4 * q));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst2), "l"(target + off) : "memory");
+    }
+  }
+  for (int i = threadIdx.x; i < steps; i += kCeTile) sb[i] = bins ? bins[i] : 0.f;
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  const int64_t idx = idx0 + threadIdx.x;
+  const double cnt = sums[0];
+  const float scale = cnt == 0.0 ? 1.f : static_cast<float>(1.0 / cnt);
+  const float g = gt ? gt[idx] : 0.f;
+  const float m = static_cast<float>(mask[idx]);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  float* col = tile + threadIdx.x;
+  const float* tcol = target ? ttile + threadIdx.x : nullptr;
+  float z = 0.f, dot = 0.f;
+#pragma unroll 4
+  for (int c = 0; c < steps; ++c) {
+    const float raw = col[c * kCeTile];
+    const float v = fmaxf(raw, 0.f);                                 // ReLU on the logits (loss.py:146)
+    const float tc = tcol ? tcol[c * kCeTile] : (fabsf(sb[c] - g) < half_step ? 1.f : 0.f);
+    const float e = __expf(v);                                       // unstabilised (loss.py:147-149)
+    z += e;
+    dot = fmaf(v, tc, dot);
+    col[c * kCeTile] = raw > 0.f ? e : -1.f;                         // the gradient pass reuses exp(raw); -1 = gated off
+  }
+  const float l = -logf(expf(dot) / z);
+  const double acc = static_cast<double>(l * m);
+  if (g_scores) {
+    float* go = g_scores + base + threadIdx.x;
+    const float k = m * scale;
+    const float krz = k / z;
+#pragma unroll 4
+    for (int c = 0; c < steps; ++c) {
+      const float e = col[c * kCeTile];
+      const float tc = tcol ? tcol[c * kCeTile] : (fabsf(sb[c] - g) < half_step ? 1.f : 0.f);
+      __stcs(go + static_cast<int64_t>(c) * HW, e > 0.f ? fmaf(e, krz, -tc * k) : 0.f);
+    }
+  }
+  const double r = block_sum_double(acc, red);
+  if (threadIdx.x == 0) atomicAdd(loss_sum, r);
+}
+
 // torch.optim.Adam single-tensor update: exp_avg.lerp_(g, 1-b1); exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2);
 // denom = exp_avg_sq.sqrt() / sqrt(bc2) + eps; p.addcdiv_(exp_avg, denom, value=-lr/bc1)
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
@@ -254,6 +321,19 @@ extern "C" int mmlf_loss_cross_entropy(const float* scores, const float* target,
                                        int64_t HW, double* loss_sum, float* g_scores, void* stream) {
   MMLF_REQUIRE(scores && mask && sums && loss_sum, "loss_cross_entropy: null buffer");
   MMLF_REQUIRE(target || (gt && bins_t), "loss_cross_entropy: need a target tensor or gt + bins");
+  const size_t tile_smem = (static_cast<size_t>(steps) * kCeTile * (target ? 2 : 1) + steps) * sizeof(float);
+  if (HW % kCeTile == 0 && tile_smem <= 200 * 1024 && reinterpret_cast<uintptr_t>(scores) % 16 == 0 &&
+      reinterpret_cast<uintptr_t>(target) % 16 == 0) {
+    static size_t configured = 0;
+    if (tile_smem > 48 * 1024 && tile_smem > configured) {
+      cudaError_t e = cudaFuncSetAttribute(loss_ce_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      MMLF_REQUIRE(e == cudaSuccess, "loss_cross_entropy: %s", cudaGetErrorString(e));
+      configured = 200 * 1024;
+    }
+    loss_ce_smem_kernel<<<static_cast<unsigned>(B * HW / kCeTile), kCeTile, tile_smem, static_cast<cudaStream_t>(stream)>>>(
+        scores, target, gt, bins_t, static_cast<float>(half_step), steps, mask, sums, HW, loss_sum, g_scores);
+    return check_launch("loss_cross_entropy_smem");
+  }
   loss_ce_kernel<<<static_cast<unsigned>(ceil_div64(B * HW, 128)), 128, steps * sizeof(float),
                    static_cast<cudaStream_t>(stream)>>>(scores, target, gt, bins_t, static_cast<float>(half_step), steps,
                                                         mask, sums, B, HW, loss_sum, g_scores);

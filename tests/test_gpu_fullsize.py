@@ -133,6 +133,32 @@ def test_loss_is_additive_over_batch_shards_at_full_size():
     assert abs(whole.item() - ref) < 1e-5 * abs(ref)
 
 
+def test_shared_memory_cross_entropy_equals_the_generic_kernel():
+    """loss_ce: the shared-memory kernel (HW % 128 == 0, 16-byte aligned inputs) gives bit-identical gradients and the same
+    value as the generic kernel, for the on-the-fly and the dense target; a copy of the scores at a 4-byte offset takes
+    the generic path."""
+    from mmlf_b200 import ops
+    from mmlf_b200.utils import dl
+    g = torch.Generator(device='cuda').manual_seed(8)
+    B, S, H, W = 8, 108, 96, 96
+    scores = torch.randn((B, S, H, W), device='cuda', generator=g) * 2
+    gt = torch.rand((B, H, W), device='cuda', generator=g) * 6 - 3
+    mask = (torch.rand((B, H, W), device='cuda', generator=g) > 0.2).int()
+    bins_t = ops.torch_bins(-3.5, 3.5, S, 'cuda')
+    sums = ops.loss_prepass(mask)
+    buf = torch.empty(scores.numel() + 1, device='cuda')
+    shifted = buf[1:].view(scores.shape)
+    shifted.copy_(scores)
+    dense = dl.reg_to_class(gt, -3.5, 3.5, S)
+    for tgt, gt_, bins in ((None, gt, bins_t), (dense, None, None)):
+        l1, g1 = ops.loss_cross_entropy(scores, tgt, gt_, bins, 7.0 / S / 2.0, mask, sums)
+        l2, g2 = ops.loss_cross_entropy(shifted, tgt, gt_, bins, 7.0 / S / 2.0, mask, sums)
+        assert torch.equal(g1, g2)
+        assert abs(l1.item() - l2.item()) <= 1e-12 * abs(l2.item())
+    # on-the-fly target == dense target
+    assert torch.equal(g1, ops.loss_cross_entropy(scores, None, gt, bins_t, 7.0 / S / 2.0, mask, sums)[1])
+
+
 def test_posteriors_are_normalised_at_full_size():
     """DPP softmax posterior sums to 1 per pixel (108 bins, 64 x 96 x 96); the one-hot marks the arg-max; the ESE Laplace
     mixture is non-negative and its mean/logvar are members of the ensemble."""
@@ -144,6 +170,14 @@ def test_posteriors_are_normalised_at_full_size():
     assert (post.sum(1) - 1).abs().max().item() < 1e-5
     assert torch.equal(one_hot.argmax(1), scores.argmax(1)) and one_hot.sum().item() == 64 * 96 * 96
     assert torch.equal(mean, bins_t[scores.argmax(1)])
+    # the shared-memory kernel (HW % 128 == 0, 16-byte aligned scores) == the generic kernel, bit for bit: a copy of the
+    # scores at a 4-byte offset takes the generic path
+    buf = torch.empty(scores.numel() + 1, device='cuda')
+    shifted = buf[1:].view(scores.shape)
+    shifted.copy_(scores)
+    assert shifted.data_ptr() % 16 == 4
+    for a, b in zip((one_hot, post, mean, logvar), ops.dpp_head(shifted, bins_t, bins_n)):
+        assert torch.equal(a, b)
     K = 70
     means = torch.randn((K, 1, 512, 512), device='cuda', generator=g)
     logvars = torch.randn((K, 1, 512, 512), device='cuda', generator=g) * 0.3
