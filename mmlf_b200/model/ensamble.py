@@ -11,7 +11,7 @@ class Ensamble(nn.Module):
 
     Per member the Shift resampling is fused into the bf16 packing kernel (no fp32 clone + ~600 tiny kernels as in
     ensamble.py:63-70); the 70x70 Laplace mixture and the arg-min gather are one kernel.  Under torchrun the members
-    are sharded round-robin over the ranks and all-gathered.
+    are sharded round-robin over the ranks and all-gathered, and the reduce is sharded over the pixels.
     """
 
     def __init__(self, model, val_disp_min, val_disp_max, val_disp_step, **kwarg):
@@ -63,5 +63,5 @@ class Ensamble(nn.Module):
             self._disp = ops.numpy_bins(self.disp_min, self.disp_max, K, dev)   # K points, inclusive (ensamble.py:90-92)
             self._disp_key = key
         disp = self._disp
-        mean, logvar, posterior = ops.ese_reduce(means, logvars, disp)
+        mean, logvar, posterior = parallel.sharded_ese_reduce(ops.ese_reduce, means, logvars, disp, rank, world)
         return {'mean': mean, 'logvar': logvar, 'means': means, 'logvars': logvars, 'posterior': posterior}
