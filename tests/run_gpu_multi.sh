@@ -8,6 +8,7 @@ O=gpurun_out; mkdir -p $O
 nvidia-smi --query-gpu=index,name --format=csv,noheader > $O/gpus_n$N.txt
 nvidia-smi topo -m >> $O/gpus_n$N.txt 2>&1
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517"
+timeout 600 $TR tests/gpu_multi_check.py > $O/multi_check_n${N}_$TAG.txt 2>&1; echo "multi check n=$N: $?"; grep -E "OK|MISMATCH" $O/multi_check_n${N}_$TAG.txt
 for wl in train ese bands infer; do
   timeout 900 $TR bench.py --gpus $N --workload $wl --steps 5 --warmup 3 > $O/bench_${wl}_n${N}_$TAG.json 2> $O/bench_${wl}_n${N}_$TAG.err
   echo "bench $wl n=$N: $?"; tail -c 400 $O/bench_${wl}_n${N}_$TAG.err

@@ -217,7 +217,7 @@ def _body_ese(rank, world):
         return [torch.from_numpy(m), torch.from_numpy(lv), torch.from_numpy(post)]
     ops.ese_reduce = ese_reduce
     rng = np.random.RandomState(1)
-    views = [torch.from_numpy(rng.uniform(0, 1, (1, 9, 3, 6, 7)).astype(np.float32)) for _ in range(4)]
+    views = [torch.from_numpy(rng.uniform(0, 1, (1, 9, 3, 5, 7)).astype(np.float32)) for _ in range(4)]   # 35 pixels: uneven pixel shards (18 + 17)
     net = _FakeNet()
     net.calls = []
     ens = Ensamble(net, -1.0, 1.0, 0.3)                     # 7 members: ranks get 4 + 3
