@@ -65,3 +65,36 @@ def test_product_never_imports_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), f
+
+
+def test_header_is_plain_c_and_struct_layouts_match_the_ctypes_mirrors(tmp_path):
+    """include/mmlf_b200.h compiles as C99 (no C++ / CUDA / torch types at the boundary) and the structs that cross it
+    have the size and field offsets of their ctypes mirrors."""
+    import shutil
+    import subprocess
+    from mmlf_b200 import _lib
+    from mmlf_b200.data.augment import AugSample
+    from mmlf_b200.engine import PackJob
+    if shutil.which('gcc') is None:
+        pytest.skip('gcc not available')
+    mirrors = {'mmlf_conv_args': _lib.ConvArgs, 'mmlf_pack_job': PackJob, 'mmlf_aug_sample': AugSample}
+    rename = {'in_': 'in'}
+    lines = ['#include "mmlf_b200.h"', '#include <stdio.h>', '#include <stddef.h>', 'int main(void) {']
+    for cname, cls in mirrors.items():
+        lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf(" %zu", offsetof({cname}, {rename.get(fname, fname)}));')
+        lines.append('  printf("\\n");')
+    lines += ['  return 0;', '}']
+    src = tmp_path / 'abi.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'abi'
+    subprocess.run(['gcc', '-std=c99', '-Wall', '-Werror', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)],
+                   check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    for line in out:
+        parts = line.split()
+        cls = mirrors[parts[0]]
+        got = [int(x) for x in parts[1:]]
+        want = [ctypes.sizeof(cls)] + [getattr(cls, f).offset for f, _ in cls._fields_]
+        assert got == want, f'{parts[0]}: C layout {got} != ctypes mirror {want}'
