@@ -932,7 +932,8 @@ static int fill_params(const mmlf_conv_args* a, ConvParams& p) {
   // Narrow layers (the 70-channel in-nets, the heads): a pipeline stage holds only 2-8 short MMAs and the issuing warp's
   // per-stage bookkeeping (~500 cycles measured against ~200 tensor cycles) bounds the kernel, so it issues two stages
   // per round: both chunks of a dy (n_kc = 2) or both dy of a tile (n_kc = 1).  Needs an even stage count.
-  p.pair_issue = (p.n_parts == 1 && p.n_kc <= 2 && !a->split_in && !getenv("MMLF_NO_PAIR_ISSUE")) ? 1 : 0;
+  static const bool no_pair_issue = getenv("MMLF_NO_PAIR_ISSUE") != nullptr;    // debugging switch: one stage per round
+  p.pair_issue = (p.n_parts == 1 && p.n_kc <= 2 && !a->split_in && !no_pair_issue) ? 1 : 0;
   if (a->type == 0) {
     p.tap_off[0] = 0; p.tap_off[1] = 1; p.tap_off[2] = p.Wp; p.tap_off[3] = p.Wp + 1;
   } else {
