@@ -27,7 +27,7 @@ COMMON = ['--model_chs', '16', '--train_bs', '4', '--train_ps', '32', '--train_l
     (['--train_shift', '2.5', '--model_uncert', '--val_ensamble', '--val_disp_step', '1.0'],
      ['--val_ensamble', '--val_disp_step', '1.0', '--train_shift', '2.5']),
     (['--model_discrete', '--train_loss_multimodal'], ['--model_discrete']),
-    (['--model_cross'], []),
+    (['--model_cross', '--train_eval_mode', '--train_eval_mode_start', '1'], []),      # iterations 1, 2 train in eval() mode
     (['--gpu_augment', '--train_shift', '2.5', '--train_max_downscale', '2'], []),
 ])
 def test_train_then_validate_cli(tmp_path, flags, val_flags):
