@@ -413,6 +413,54 @@ def test_fused_bn_backward_statistics_match_the_standalone_reduction(golden):
     assert cos > 0.999, cos
 
 
+@pytest.mark.parametrize('over', [dict(model_in_blocks=2, model_out_blocks=4, model_views=7),
+                                  dict(model_in_blocks=1, model_out_blocks=2, model_views=5, model_cross=True)])
+def test_other_topologies_against_the_emulating_oracle(over):
+    """--model_in_blocks / --model_out_blocks / --model_views other than the published 3 / 8 / 9 (feed_forward.py:25-27):
+    default-initialised UPR model, eval outputs and one training step against the oracle with the same rounding points
+    (the oracle itself is pinned against the reference in tests/test_oracle_golden.py)."""
+    from mmlf_b200.model import loss as L
+    from mmlf_b200.model.feed_forward import FeedForward
+    cross = over.get('model_cross', False)
+    kw = fx.model_kwargs('upr', cross, chs=8, **over)
+    n = kw['model_views']
+    torch.manual_seed(0)
+    m = FeedForward(**kw).cuda()
+    assert m.steps == (2 if cross else 4) * n * 3
+    state = {k: v.detach().cpu().numpy().copy() for k, v in m.state_dict().items()}
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    h, v, i, d, gt = fx.synth_batch(41, 2, 20, 20, n=n)
+    mask = fx.synth_mask(42, 2, 20, 20)
+    emu = oracle.FeedForwardOracle(state, quant='fp16', model_cross=cross, model_uncert=True, model_views=n)
+    m.eval()
+    with torch.no_grad():
+        out = m(T(h), T(v), T(i), T(d))
+    e = emu.forward(h, v, i, d)
+    for key in ('mean', 'logvar'):
+        scale = float(np.abs(e[key]).max()) + 1e-6
+        err = _rel(out[key].cpu().numpy(), e[key], scale)
+        report(test='topology_%d_%d_%d' % (kw['model_in_blocks'], kw['model_out_blocks'], n), mode='eval', key=key, max_vs_emu=err)
+        assert err <= MAX_VS_EMU, (key, err)
+    assert out['posterior'].shape == (2, m.steps, 20, 20)
+    m.train()
+    emu.training = True
+    out = m(T(h), T(v), T(i), T(d))
+    lossv = L.ImprovedUncertaintyL1Loss()(out, T(gt), T(mask))
+    lossv.backward()
+    e = emu.forward(h, v, i, d, keep_tape=True)
+    ev, eg = olosses.improved_uncertainty_l1({'mean': e['mean'], 'logvar': e['logvar'], 'scores': None}, gt, mask)
+    assert abs(lossv.item() - float(ev)) <= 0.005 * abs(float(ev)) + 2e-3
+    egrads = emu.backward(np.stack([eg['mean'], eg['logvar']], 1))
+    ge = gg = ee = 0.0
+    for pname, p in m.named_parameters():
+        got, em = p.grad.cpu().numpy().astype(np.float64), egrads[pname].astype(np.float64)
+        assert np.isfinite(got).all() and got.shape == em.shape, pname
+        ge, gg, ee = ge + (got * em).sum(), gg + (got ** 2).sum(), ee + (em ** 2).sum()
+    cos = ge / np.sqrt(gg * ee)
+    report(test='topology_%d_%d_%d' % (kw['model_in_blocks'], kw['model_out_blocks'], n), mode='train', key='grads', cos_vs_emu=cos)
+    assert cos >= 0.93, cos
+
+
 def test_train_eval_mode_gradients(golden):
     """--train_eval_mode (train/cli.py:227-230): backward through eval-mode BatchNorm (running statistics, no batch-mean
     terms) against the reference's autograd and the emulating oracle; the running statistics must not move."""
