@@ -205,6 +205,10 @@ def gen_net():
         save(f'net_full_{variant}.npz', **res)
     kw = fx.model_kwargs('base', True, chs=70)
     save('net_full_base_cross.npz', **_run_net(kw, 13, 1, 16, 16, 33, store_state=False, sample_stride=97))
+    # odd --model_ksize (symmetric padding k // 2 for both convs of a block, feed_forward.py:86-88): oracle-only fixture, the
+    # CUDA path implements the published ksize = 2
+    kw = fx.model_kwargs('base', False, chs=8, model_ksize=3)
+    save('net_tiny_base_k3.npz', **_run_net(kw, 11, 2, 20, 20, 21, store_state=True, wscale=1.0))
     # no-batchnorm topology (state_dict index 3 vanishes, feed_forward.py:132-135)
     kw = fx.model_kwargs('base', False, chs=8, model_no_batchnorm=True)
     # without BN the scale of the activations is set by the weights alone: x2.8 keeps the output from collapsing

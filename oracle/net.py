@@ -66,36 +66,37 @@ def laplacian(x, mu, b):
 # ----------------------------------------------------------------------------
 # layers (NHWC internally)
 # ----------------------------------------------------------------------------
-TAPS = ((0, 0), (0, 1), (1, 0), (1, 1))
-
-
 def conv2x2(x, w, b, pad):
-    """nn.Conv2d(cin, cout, 2, padding=pad) on NHWC x (feed_forward.py:123,125).
-    w: (cout, cin, 2, 2), b: (cout,)."""
+    """nn.Conv2d(cin, cout, k, padding=pad) on NHWC x (feed_forward.py:123,125); k = w.shape[2] (2 in the published
+    model; odd --model_ksize values use the same code).  w: (cout, cin, k, k), b: (cout,)."""
+    k = w.shape[2]
     if pad:
         x = np.pad(x, ((0, 0), (pad, pad), (pad, pad), (0, 0)))
     B, H, W, C = x.shape
-    Ho, Wo = H - 1, W - 1
+    Ho, Wo = H - k + 1, W - k + 1
     out = np.zeros((B * Ho * Wo, w.shape[0]), np.float32)
-    for dy, dx in TAPS:
-        a = x[:, dy:dy + Ho, dx:dx + Wo, :].reshape(-1, C)
-        out += a @ w[:, :, dy, dx].T
+    for dy in range(k):
+        for dx in range(k):
+            a = x[:, dy:dy + Ho, dx:dx + Wo, :].reshape(-1, C)
+            out += a @ w[:, :, dy, dx].T
     out += b
     return out.reshape(B, Ho, Wo, -1)
 
 
 def conv2x2_bwd(x, w, gout, pad):
     """Gradients of conv2x2: returns (gx, gw, gb)."""
+    k = w.shape[2]
     xp = np.pad(x, ((0, 0), (pad, pad), (pad, pad), (0, 0))) if pad else x
     B, H, W, C = xp.shape
-    Ho, Wo = H - 1, W - 1
+    Ho, Wo = H - k + 1, W - k + 1
     g2 = gout.reshape(-1, gout.shape[-1])
     gw = np.zeros_like(w)
     gxp = np.zeros_like(xp)
-    for dy, dx in TAPS:
-        a = xp[:, dy:dy + Ho, dx:dx + Wo, :].reshape(-1, C)
-        gw[:, :, dy, dx] = g2.T @ a
-        gxp[:, dy:dy + Ho, dx:dx + Wo, :] += (g2 @ w[:, :, dy, dx]).reshape(B, Ho, Wo, C)
+    for dy in range(k):
+        for dx in range(k):
+            a = xp[:, dy:dy + Ho, dx:dx + Wo, :].reshape(-1, C)
+            gw[:, :, dy, dx] = g2.T @ a
+            gxp[:, dy:dy + Ho, dx:dx + Wo, :] += (g2 @ w[:, :, dy, dx]).reshape(B, Ho, Wo, C)
     gx = gxp[:, pad:H - pad, pad:W - pad, :] if pad else gxp
     return gx, gw, g2.sum(0)
 
@@ -115,6 +116,9 @@ class FeedForwardOracle:
         self.has_bn = 'in_net_hv.0.3.running_mean' in self.p
         self.in_blocks = 1 + max(int(k.split('.')[1]) for k in self.p if k.startswith('in_net_hv.'))
         self.out_blocks = 1 + max(int(k.split('.')[1]) for k in self.p if k.startswith('out_net.'))
+        # kernel size from the weights; paddings as feed_forward.py:86-92 (even k: k//2 then k//2 - 1, odd k: k//2 twice)
+        k = self.p['in_net_hv.0.0.weight'].shape[2]
+        self.ksize, self.pad1, self.pad2 = k, k // 2, (k // 2 if k % 2 else k // 2 - 1)
         self.training = False
 
     # -- precision emulation ---------------------------------------------------
@@ -138,11 +142,11 @@ class FeedForwardOracle:
     def _block_fwd(self, prefix, x, bn, tape, head_fp32=False, relu_out=True):
         w1, b1 = self._w(prefix + '.0.weight'), self.p[prefix + '.0.bias']
         w2, b2 = self._w(prefix + '.2.weight'), self.p[prefix + '.2.bias']
-        a1 = np.maximum(conv2x2(x, w1, b1, 1), 0)
+        a1 = np.maximum(conv2x2(x, w1, b1, self.pad1), 0)
         a1 = a1 if head_fp32 else self._q(a1)
         if head_fp32 and self.quant:
             w2 = self.p[prefix + '.2.weight']          # tiny head conv2 runs in fp32 on CUDA cores
-        z = conv2x2(a1, w2, b2, 0)
+        z = conv2x2(a1, w2, b2, self.pad2)
         rec = {'prefix': prefix, 'x': x, 'a1': a1, 'bn': bn, 'relu_out': relu_out}
         if not bn:
             if relu_out:                       # --model_no_batchnorm: index 3 is the ReLU (feed_forward.py:132-135)
@@ -195,9 +199,9 @@ class FeedForwardOracle:
             gz = self._qg(gy * (rec['y'] > 0)) if rec['relu_out'] else gy
         w1, w2 = self._w(prefix + '.0.weight', grad=True), self._w(prefix + '.2.weight', grad=True)
         # the weight-gradient GEMM reads its activation operand converted to the gradient format (bf16)
-        ga1, gw2, gb2 = conv2x2_bwd(self._qg(rec['a1']), w2, gz, 0)
+        ga1, gw2, gb2 = conv2x2_bwd(self._qg(rec['a1']), w2, gz, self.pad2)
         ga1 = self._qg(ga1 * (rec['a1'] > 0))
-        gx, gw1, gb1 = conv2x2_bwd(self._qg(rec['x']), w1, ga1, 1)
+        gx, gw1, gb1 = conv2x2_bwd(self._qg(rec['x']), w1, ga1, self.pad1)
         grads[prefix + '.0.weight'], grads[prefix + '.0.bias'] = gw1, gb1
         grads[prefix + '.2.weight'], grads[prefix + '.2.bias'] = gw2, gb2
         return (self._qg(gx) if need_gx else None), grads
