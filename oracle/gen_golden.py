@@ -215,6 +215,38 @@ def gen_net():
     save('net_tiny_base_nobn.npz', **_run_net(kw, 11, 2, 20, 20, 21, store_state=True, wscale=2.8))
 
 
+def gen_unet():
+    """--model_unet (feed_forward.py:99-100, 189-204; unet.py): UPR model with the U-Net out-net.  The 31 M parameters are
+    not stored: names + shapes are, and fixtures.synth_state regenerates the values from the seed."""
+    kw = fx.model_kwargs('upr', False, chs=8, model_unet=True)
+    torch.manual_seed(0)
+    model = FeedForward(**kw)
+    shapes = [(k, tuple(v.shape)) for k, v in model.state_dict().items()]
+    state = fx.synth_state(shapes, 17)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in state.items()})
+    B, H, W = 2, 32, 32
+    h, v, i, d, gt = fx.synth_batch(51, B, H, W)
+    mask = fx.synth_mask(52, B, H, W)
+    out = {'names': np.array([k for k, _ in shapes]), 'shapes': np.array([','.join(map(str, s)) for _, s in shapes])}
+    model.eval()
+    with torch.no_grad():
+        o = model(T(h), T(v), T(i), T(d))
+    out['eval/mean'], out['eval/logvar'] = o['mean'].numpy(), o['logvar'].numpy()
+    model.train()
+    o = model(T(h), T(v), T(i), T(d))
+    lossv = _loss_for('upr', False)(o, T(gt), T(mask))
+    lossv.backward()
+    out['train/loss'] = np.array(lossv.item(), np.float64)
+    out['train/mean'], out['train/logvar'] = o['mean'].detach().numpy(), o['logvar'].detach().numpy()
+    for name, p in model.named_parameters():
+        g = p.grad.numpy()
+        out['grad/' + name] = g.reshape(-1)[::97].copy() if g.size > 4096 else g
+    for k, vv in model.state_dict().items():
+        if 'running' in k and 'out_net' in k and vv.numel() <= 128:
+            out['after/' + k] = vv.numpy().copy()
+    save('net_unet_upr.npz', **out)
+
+
 def gen_evalmode():
     """--train_eval_mode (train/cli.py:227-230): the training step with the model in eval() mode, i.e. gradients through
     BatchNorm layers that normalise with their running statistics (which must not change)."""
@@ -445,6 +477,6 @@ def gen_cli():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['indices', 'shift', 'bins', 'net', 'losses', 'ese', 'adam', 'checkpoint', 'texture', 'augment', 'metrics', 'evalmode', 'cli']
+    which = sys.argv[1:] or ['indices', 'shift', 'bins', 'net', 'losses', 'ese', 'adam', 'checkpoint', 'texture', 'augment', 'metrics', 'evalmode', 'unet', 'cli']
     for w in which:
         globals()['gen_' + w]()

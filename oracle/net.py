@@ -115,7 +115,8 @@ class FeedForwardOracle:
         self.steps = (2 if model_cross else 4) * model_views * 3      # feed_forward.py:81-84
         self.has_bn = 'in_net_hv.0.3.running_mean' in self.p
         self.in_blocks = 1 + max(int(k.split('.')[1]) for k in self.p if k.startswith('in_net_hv.'))
-        self.out_blocks = 1 + max(int(k.split('.')[1]) for k in self.p if k.startswith('out_net.'))
+        self.unet = any(k.startswith('out_net.down_path.') for k in self.p)          # --model_unet (feed_forward.py:99-100)
+        self.out_blocks = 0 if self.unet else 1 + max(int(k.split('.')[1]) for k in self.p if k.startswith('out_net.'))
         # kernel size from the weights; paddings as feed_forward.py:86-92 (even k: k//2 then k//2 - 1, odd k: k//2 twice)
         k = self.p['in_net_hv.0.0.weight'].shape[2]
         self.ksize, self.pad1, self.pad2 = k, k // 2, (k // 2 if k % 2 else k // 2 - 1)
@@ -234,11 +235,15 @@ class FeedForwardOracle:
             feats.append(self._in_net('in_net_id', nhwc(d_views), tapes['d']))
         x = np.concatenate(feats, -1)                                  # feed_forward.py:263-267
         tapes['o'] = []
-        for k in range(self.out_blocks - 1):
-            x = self._block_fwd(f'out_net.{k}', x, self.has_bn, tapes['o'])
-        small_head = not self.discrete
-        out = self._block_fwd(f'out_net.{self.out_blocks - 1}', x, False, tapes['o'],
-                              head_fp32=small_head, relu_out=False)
+        if self.unet:
+            from . import unet
+            out, tapes['unet'] = unet.forward(self.p, x, self.training)
+        else:
+            for k in range(self.out_blocks - 1):
+                x = self._block_fwd(f'out_net.{k}', x, self.has_bn, tapes['o'])
+            small_head = not self.discrete
+            out = self._block_fwd(f'out_net.{self.out_blocks - 1}', x, False, tapes['o'],
+                                  head_fp32=small_head, relu_out=False)
         output = np.ascontiguousarray(out.transpose(0, 3, 1, 2))        # NCHW
         if keep_tape:
             self._tapes = tapes
@@ -272,6 +277,10 @@ class FeedForwardOracle:
                 grads[k] = grads[k] + v if k in grads else v
 
         g = np.ascontiguousarray(g_output.transpose(0, 2, 3, 1)).astype(np.float32)
+        if self.unet:
+            from . import unet
+            g, d = unet.backward(self.p, tapes['unet'], g, self.training)
+            acc(d)
         for rec in reversed(tapes['o']):
             g, d = self._block_bwd(rec, g)
             acc(d)

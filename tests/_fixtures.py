@@ -139,3 +139,28 @@ def perturb_state(state, seed, wscale=2.0):
         else:  # conv bias
             put(rng.uniform(-0.1, 0.1, shape))
     return state
+
+
+def synth_state(shapes, seed):
+    """Deterministic parameters / buffers for a list of (name, shape): He-scaled conv weights, small biases, randomised
+    BatchNorm affine and running statistics.  Used for fixtures whose state is too large to store (the U-Net out-net:
+    31 M parameters): the generator loads these values into the reference model, the test regenerates them."""
+    rng = np.random.RandomState(seed)
+    state = {}
+    for name, shape in shapes:
+        shape = tuple(int(x) for x in shape)
+        leaf = name.rsplit('.', 1)[1]
+        if leaf == 'num_batches_tracked':
+            state[name] = np.zeros(shape, np.int64)
+        elif leaf == 'running_mean':
+            state[name] = rng.uniform(-0.2, 0.2, shape).astype(np.float32)
+        elif leaf == 'running_var':
+            state[name] = rng.uniform(0.5, 1.5, shape).astype(np.float32)
+        elif len(shape) == 4:                                        # conv / transposed-conv weight
+            fan_in = shape[1] * shape[2] * shape[3] if '.up.' not in name else shape[0]
+            state[name] = (rng.standard_normal(shape) * np.sqrt(2.0 / fan_in)).astype(np.float32)
+        elif leaf == 'weight':                                       # BatchNorm gamma
+            state[name] = rng.uniform(0.5, 1.5, shape).astype(np.float32)
+        else:                                                        # biases, BatchNorm beta
+            state[name] = rng.uniform(-0.1, 0.1, shape).astype(np.float32)
+    return state
