@@ -426,7 +426,7 @@ def main():
     if not peak_tf:
         peak_tf, peak_src = 1400.0, 'fallback (B200_PROFILING.md: sustained ~1.4 PFLOP/s)'
     conv_ms = by_name.get('mmlf_conv2x2', [])
-    wgrad_ms = by_name.get('mmlf_conv2x2_wgrad', [])
+    wgrad_ms = by_name.get('mmlf_conv2x2_wgrad', []) + by_name.get('mmlf_conv2x2_wgrad_canonical', [])
     n_conv = len(conv_ms) / prof_steps
     # algorithmic flops of all conv2x2 launches of one step on this rank: forward convs + data gradients
     Bl = B

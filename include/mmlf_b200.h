@@ -188,6 +188,13 @@ int64_t mmlf_conv2x2_wgrad_workspace(int n_pad, int cin_pad);
 int mmlf_conv2x2_wgrad(const void* dout, int ld_dout, int n_pad, const void* act, int ld_act, int cin_pad, int B,
                        int H, int W, int type, int act_dtype, int dout_dtype, float* workspace, float* dw,
                        void* stream);
+/* The same weight gradient written straight into the canonical (cout, cin, 2, 2) f32 tensor of the parameter (+= when
+ * accumulate): the K-split reduction undoes the per-stream tap mapping (spatial) and the channel-group padding of
+ * mmlf_pack_conv_weight itself, i.e. mmlf_conv2x2_wgrad + mmlf_unpack_conv_wgrad in one reduction launch. */
+int mmlf_conv2x2_wgrad_canonical(const void* dout, int ld_dout, int n_pad, const void* act, int ld_act, int cin_pad,
+                                 int B, int H, int W, int type, int act_dtype, int dout_dtype, float* workspace, int cout,
+                                 int cin, int spatial, int in_groups, int group_real, int group_pad, float* dw,
+                                 int accumulate, void* stream);
 
 /* Format conversion of a 16-bit slot array (C channels per slot, multiple of 8). */
 int mmlf_convert16(const void* src, int ld_src, int src_dtype, void* dst, int ld_dst, int dst_dtype, int C,

@@ -55,6 +55,8 @@ _PROTOS = {
     'mmlf_conv2x2_simt': (c_i, [C.POINTER(ConvArgs), c_p]),
     'mmlf_conv2x2_wgrad_workspace': (c_i64, [c_i, c_i]),
     'mmlf_conv2x2_wgrad': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
+    'mmlf_conv2x2_wgrad_canonical': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p,
+                                           c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_p]),
     'mmlf_convert16': (c_i, [c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_i64, c_p]),
     'mmlf_colsum16': (c_i, [c_p, c_i, c_i, c_i64, c_i, c_p, c_i, c_p]),
     'mmlf_bn_stats': (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
@@ -103,7 +105,7 @@ def lib():
 
 
 # kernels launched per C-ABI call (for the launch count reported by bench.py)
-_KERNELS_PER_CALL = {'mmlf_augment_fill': 0, 'mmlf_augment_patches': 2, 'mmlf_pack_views_split': 2, 'mmlf_conv2x2_wgrad': 2, 'mmlf_bn_bwd_apply': 2, 'mmlf_head_small_bwd': 2, 'mmlf_shift_taps': 0}
+_KERNELS_PER_CALL = {'mmlf_augment_fill': 0, 'mmlf_augment_patches': 2, 'mmlf_pack_views_split': 2, 'mmlf_conv2x2_wgrad': 2, 'mmlf_conv2x2_wgrad_canonical': 2, 'mmlf_bn_bwd_apply': 2, 'mmlf_head_small_bwd': 2, 'mmlf_shift_taps': 0}
 launch_count = 0
 _profile = None          # when set to a list, call() appends (name, start_event, end_event)
 

@@ -364,6 +364,50 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int ksplits, i
   dw[(static_cast<int64_t>(n) * 4 + tap) * cin_pad + c] = acc;
 }
 
+// Canonical layout of the weight gradient (what autograd hands to the optimizer): dw[cout][cin][2][2], with the
+// per-stream tap mapping and the channel-group padding undone (the inverse of mmlf_pack_conv_weight).
+struct WgradCanon {
+  float* dw;
+  int cout, cin, spatial, groups, group_real, group_pad, accumulate;
+};
+
+// same reduction as wgrad_reduce_kernel (same order over the K splits), written straight into the canonical tensor:
+// consecutive threads walk n (contiguous in the workspace) for a fixed (tap, real input channel)
+__global__ void wgrad_reduce_canon_kernel(const float* __restrict__ ws, int ksplits, int m_rows, int ws_ld, int kc,
+                                          const WgradCanon o) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<int64_t>(o.cout) * 4 * o.cin) return;
+  const int n = static_cast<int>(idx % o.cout);
+  const int tc = static_cast<int>(idx / o.cout);
+  const int tap = tc / o.cin, ci = tc - tap * o.cin;
+  const int g = ci / o.group_real, c = g * o.group_pad + (ci - g * o.group_real);      // padded channel of the operand
+  const int m = (tap * kc + (c >> 6)) * 64 + (c & 63);
+  float acc = 0.f;
+  for (int k = 0; k < ksplits; ++k) acc += ws[(static_cast<int64_t>(k) * m_rows + m) * ws_ld + n];
+  // effective tap (p, q) of this stream -> canonical tap (a, b) of w[., ., a, b]  (weights.cu: eff_to_canonical)
+  const int p = tap >> 1, q = tap & 1;
+  int a, b;
+  if (o.spatial == 0) { a = p; b = q; }
+  else if (o.spatial == 1) { a = q; b = p; }
+  else { a = q; b = 1 - p; }
+  float* dst = o.dw + ((static_cast<int64_t>(n) * o.cin + ci) * 2 + a) * 2 + b;
+  *dst = o.accumulate ? *dst + acc : acc;
+}
+
+static int launch_wgrad_reduce(const float* ws, int ksplits, int m_rows, int ws_ld, int kc, int n_pad, int cin_pad,
+                               float* dw, const WgradCanon* canon, cudaStream_t st) {
+  if (canon) {
+    const int64_t total = static_cast<int64_t>(canon->cout) * 4 * canon->cin;
+    wgrad_reduce_canon_kernel<<<static_cast<unsigned>(ceil_div64(total, 256)), 256, 0, st>>>(ws, ksplits, m_rows, ws_ld, kc,
+                                                                                             *canon);
+    return check_launch("wgrad_reduce_canon_kernel");
+  }
+  const int64_t total = static_cast<int64_t>(n_pad) * 4 * cin_pad;
+  wgrad_reduce_kernel<<<static_cast<unsigned>(ceil_div64(total, 256)), 256, 0, st>>>(ws, ksplits, m_rows, ws_ld, kc, n_pad,
+                                                                                     cin_pad, dw);
+  return check_launch("wgrad_reduce_kernel");
+}
+
 static int wgrad_impl() {
   // MMLF_WGRAD_IMPL=1 selects the single-CTA kernel (debugging); default is the CTA-pair kernel
   static int impl = -1;
@@ -398,7 +442,7 @@ extern "C" int64_t mmlf_conv2x2_wgrad_workspace(int n_pad, int cin_pad) {
 }
 
 static int wgrad_pair(const void* dout, int ld_dout, int n_pad, const void* act, int ld_act, int cin_pad, int B, int H,
-                      int W, int type, int dtype, float* workspace, float* dw, void* stream) {
+                      int W, int type, int dtype, float* workspace, float* dw, const WgradCanon* canon, void* stream) {
   Wgrad2Params p;
   const int Wp = W + 1;
   p.n_slots = static_cast<int64_t>(B) * (H + 1) * Wp;
@@ -464,23 +508,21 @@ static int wgrad_pair(const void* dout, int ld_dout, int n_pad, const void* act,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   conv2x2_wgrad2_kernel<<<2 * p.kc * p.ksplits, kWgThreads, smem_bytes, st>>>(tmap_act, tmap_dout, p);
   if (int rc = check_launch("conv2x2_wgrad2_kernel")) return rc;
-  const int64_t total = static_cast<int64_t>(n_pad) * 4 * cin_pad;
-  wgrad_reduce_kernel<<<static_cast<unsigned>(ceil_div64(total, 256)), 256, 0, st>>>(
-      workspace, p.ksplits, 4 * p.kc * 64, p.ws_ld, p.kc, n_pad, cin_pad, dw);
-  return check_launch("wgrad_reduce_kernel");
+  return launch_wgrad_reduce(workspace, p.ksplits, 4 * p.kc * 64, p.ws_ld, p.kc, n_pad, cin_pad, dw, canon, st);
 }
 
-extern "C" int mmlf_conv2x2_wgrad(const void* dout, int ld_dout, int n_pad, const void* act, int ld_act, int cin_pad,
-                                  int B, int H, int W, int type, int act_dtype, int dout_dtype, float* workspace, float* dw,
-                                  void* stream) {
-  MMLF_REQUIRE(dout && act && workspace && dw, "wgrad: null buffer");
+static int wgrad_common(const void* dout, int ld_dout, int n_pad, const void* act, int ld_act, int cin_pad, int B, int H,
+                        int W, int type, int act_dtype, int dout_dtype, float* workspace, float* dw,
+                        const WgradCanon* canon, void* stream) {
+  MMLF_REQUIRE(dout && act && workspace && (dw || canon), "wgrad: null buffer");
   MMLF_REQUIRE((act_dtype | dout_dtype) >> 1 == 0, "wgrad: dtype codes are 0 (bf16) or 1 (fp16)");
   MMLF_REQUIRE(act_dtype == dout_dtype, "wgrad: both operands must share one 16-bit format (convert with mmlf_convert16)");
   MMLF_REQUIRE(n_pad % 16 == 0 && n_pad >= 16 && n_pad <= 320, "wgrad: n_pad %d must be a multiple of 16 in [16, 320]", n_pad);
   MMLF_REQUIRE(cin_pad % 16 == 0 && cin_pad >= 16 && cin_pad <= 320, "wgrad: cin_pad %d must be a multiple of 16 in [16, 320]", cin_pad);
   MMLF_REQUIRE(ld_dout % 8 == 0 && ld_act % 8 == 0 && ld_dout >= n_pad && ld_act >= cin_pad, "wgrad: bad row pitch");
   MMLF_REQUIRE(type == 0 || type == 1, "wgrad: type must be 0 or 1");
-  if (wgrad_impl() == 2) return wgrad_pair(dout, ld_dout, n_pad, act, ld_act, cin_pad, B, H, W, type, act_dtype, workspace, dw, stream);
+  if (wgrad_impl() == 2)
+    return wgrad_pair(dout, ld_dout, n_pad, act, ld_act, cin_pad, B, H, W, type, act_dtype, workspace, dw, canon, stream);
   WgradParams p;
   const int Hp = H + 1, Wp = W + 1;
   p.n_slots = static_cast<int64_t>(B) * Hp * Wp;
@@ -525,8 +567,27 @@ extern "C" int mmlf_conv2x2_wgrad(const void* dout, int ld_dout, int n_pad, cons
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   conv2x2_wgrad_kernel<<<p.n_mblocks * p.ksplits, kWgThreads, smem_bytes, st>>>(tmap_act, tmap_dout, p);
   if (int rc = check_launch("conv2x2_wgrad_kernel")) return rc;
-  const int64_t total = static_cast<int64_t>(n_pad) * 4 * cin_pad;
-  wgrad_reduce_kernel<<<static_cast<unsigned>(ceil_div64(total, 256)), 256, 0, st>>>(
-      workspace, p.ksplits, p.n_mblocks * 128, p.ws_ld, p.kc, n_pad, cin_pad, dw);
-  return check_launch("wgrad_reduce_kernel");
+  return launch_wgrad_reduce(workspace, p.ksplits, p.n_mblocks * 128, p.ws_ld, p.kc, n_pad, cin_pad, dw, canon, st);
+}
+
+extern "C" int mmlf_conv2x2_wgrad(const void* dout, int ld_dout, int n_pad, const void* act, int ld_act, int cin_pad,
+                                  int B, int H, int W, int type, int act_dtype, int dout_dtype, float* workspace, float* dw,
+                                  void* stream) {
+  MMLF_REQUIRE(dw, "wgrad: null buffer");
+  return wgrad_common(dout, ld_dout, n_pad, act, ld_act, cin_pad, B, H, W, type, act_dtype, dout_dtype, workspace, dw,
+                      nullptr, stream);
+}
+
+extern "C" int mmlf_conv2x2_wgrad_canonical(const void* dout, int ld_dout, int n_pad, const void* act, int ld_act,
+                                            int cin_pad, int B, int H, int W, int type, int act_dtype, int dout_dtype,
+                                            float* workspace, int cout, int cin, int spatial, int in_groups, int group_real,
+                                            int group_pad, float* dw, int accumulate, void* stream) {
+  MMLF_REQUIRE(dw, "wgrad_canonical: null buffer");
+  MMLF_REQUIRE(spatial >= 0 && spatial <= 2, "wgrad_canonical: spatial must be 0..2");
+  MMLF_REQUIRE(in_groups >= 1 && group_real >= 1 && group_pad >= group_real && in_groups * group_real == cin &&
+                   n_pad >= cout && cin_pad >= in_groups * group_pad,
+               "wgrad_canonical: inconsistent channel layout");
+  const WgradCanon canon{dw, cout, cin, spatial, in_groups, group_real, group_pad, accumulate};
+  return wgrad_common(dout, ld_dout, n_pad, act, ld_act, cin_pad, B, H, W, type, act_dtype, dout_dtype, workspace, nullptr,
+                      &canon, stream);
 }

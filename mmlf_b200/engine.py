@@ -537,7 +537,6 @@ class Engine:
         dev = self.dev
         ws_bytes = max(_lib.lib().mmlf_conv2x2_wgrad_workspace(cs.n_pad, cs.cin_pad) for cs in self.all_convs())
         ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
-        dwp = torch.empty(320 * 4 * 320, dtype=torch.float32, device=dev)
         # scratch rows for the per-block reductions, zeroed / allocated once per backward pass
         n_blk = len(tape['out']) + sum(len(r) for r in tape['streams'].values()) + 2
         z64 = torch.zeros((3 * n_blk, 2 * 320), dtype=torch.float64, device=dev)
@@ -586,10 +585,10 @@ class Engine:
 
             def work():
                 sst = _stream()
-                call('mmlf_conv2x2_wgrad', _ptr(dout), ld_dout, cs.n_pad, _ptr(actg), ld_act, cs.cin_pad, geo.B, geo.H,
-                     geo.W, cs.type, GRAD, GRAD, _ptr(ws), _ptr(dwp), sst)
-                call('mmlf_unpack_conv_wgrad', _ptr(dwp), cs.n_pad, cs.cin_pad, cs.cout, cs.cin, cs.spatial, cs.groups,
-                     cs.group_real, cs.group_pad, _ptr(grads[wname]), 1 if acc else 0, sst)
+                # the K-split reduction writes (or accumulates into) the canonical (cout, cin, 2, 2) gradient directly
+                call('mmlf_conv2x2_wgrad_canonical', _ptr(dout), ld_dout, cs.n_pad, _ptr(actg), ld_act, cs.cin_pad, geo.B,
+                     geo.H, geo.W, cs.type, GRAD, GRAD, _ptr(ws), cs.cout, cs.cin, cs.spatial, cs.groups, cs.group_real,
+                     cs.group_pad, _ptr(grads[wname]), 1 if acc else 0, sst)
                 if dbias is None:
                     call('mmlf_colsum16', _ptr(dout), ld_dout, cs.n_pad, geo.n_slots, GRAD, _ptr(grads[bname]), 1, sst)
                 else:

@@ -510,6 +510,37 @@ def test_conv_wgrad(case, act_dt):
     np.testing.assert_allclose(db.cpu().numpy()[:cout], gb, rtol=1e-4, atol=1e-3)
 
 
+@pytest.mark.parametrize('case', [(2, 12, 12, 70, 70, 1, 1, 1), (2, 12, 12, 27, 70, 0, 2, 1), (1, 20, 20, 280, 280, 0, 0, 4),
+                                  (1, 16, 16, 280, 2, 0, 0, 1)])
+def test_conv_wgrad_canonical_equals_wgrad_plus_unpack(case):
+    """mmlf_conv2x2_wgrad_canonical (K-split reduction straight into the (cout, cin, 2, 2) gradient, per-stream tap
+    mapping and channel groups undone) == mmlf_conv2x2_wgrad + mmlf_unpack_conv_wgrad bit for bit, also accumulating."""
+    u = _u()
+    B, H, W, cin, cout, ctype, spatial, groups = case
+    rng = np.random.RandomState(19)
+    Hp, Wp = H + 1, W + 1
+    group_real = cin // groups
+    group_pad = u.pad16(group_real)
+    cin_pad, n_pad = groups * group_pad, u.pad16(cout)
+    n_slots = B * Hp * Wp
+    xs = torch.from_numpy(rng.normal(0, 1, (n_slots, cin_pad)).astype(np.float32)).cuda().to(torch.bfloat16)
+    gs = torch.from_numpy(rng.normal(0, 1, (n_slots, n_pad)).astype(np.float32)).cuda().to(torch.bfloat16)
+    ws = torch.empty(u._lib.lib().mmlf_conv2x2_wgrad_workspace(n_pad, cin_pad) // 4, dtype=torch.float32, device='cuda')
+    dwp = torch.empty((n_pad, 4, cin_pad), dtype=torch.float32, device='cuda')
+    base = torch.from_numpy(rng.normal(0, 1, (cout, cin, 2, 2)).astype(np.float32)).cuda()
+    for accumulate in (0, 1):
+        want, got = base.clone(), base.clone()
+        u.call('mmlf_conv2x2_wgrad', u.ptr(gs), n_pad, n_pad, u.ptr(xs), cin_pad, cin_pad, B, H, W, ctype, u.BF16, u.BF16,
+               u.ptr(ws), u.ptr(dwp), u.stream())
+        u.call('mmlf_unpack_conv_wgrad', u.ptr(dwp), n_pad, cin_pad, cout, cin, spatial, groups, group_real, group_pad,
+               u.ptr(want), accumulate, u.stream())
+        u.call('mmlf_conv2x2_wgrad_canonical', u.ptr(gs), n_pad, n_pad, u.ptr(xs), cin_pad, cin_pad, B, H, W, ctype, u.BF16,
+               u.BF16, u.ptr(ws), cout, cin, spatial, groups, group_real, group_pad, u.ptr(got), accumulate, u.stream())
+        torch.cuda.synchronize()
+        assert torch.equal(got, want), (case, accumulate)
+        assert not torch.equal(got, base)
+
+
 def test_weight_pack_variants():
     """The three spatial variants against the reference's permute/flip plumbing (feed_forward.py:236-256)."""
     u = _u()
