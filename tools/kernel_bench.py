@@ -284,7 +284,7 @@ def main():
     bn.hbm_row('reg_to_class_kernel', f'{B}x96x96 -> 108 bins', px * (4.0 + 4 * S), lambda: ops.reg_to_class_op(gt, bins_t, 3.5 / S))
     bn.hbm_row('upr_posterior_kernel', f'{B}x96x96 -> 108 bins', px * (8.0 + 4 * S), lambda: ops.upr_posterior(mean, logvar, bins_n))
     bn.hbm_row('dpp_head_kernel', f'{B}x108x96x96', px * (4.0 * S + 8.0 * S + 8), lambda: ops.dpp_head(scores, bins_t, bins_n),
-               'scores read once (re-reads hit L2), one_hot + posterior + mean + logvar written')
+               'scores read once (shared-memory tile), one_hot + posterior + mean + logvar written')
     del scores, tgt
     K = 70
     means = torch.randn((K, 1, 512, 512), device=DEV, generator=g)
