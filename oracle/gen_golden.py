@@ -127,7 +127,7 @@ def _calibrate_bn(model, kw, seed, H, W):
     cal = FeedForward(**dict(kw, model_batchnorm_momentum=1.0))
     cal.load_state_dict(model.state_dict())
     cal.train()
-    h, v, i, d, _ = fx.synth_batch(seed + 100, 2, H, W)
+    h, v, i, d, _ = fx.synth_batch(seed + 100, 2, H, W, n=kw['model_views'])
     cal(T(h), T(v), T(i), T(d))
     rng = np.random.RandomState(seed + 1)
     sd = model.state_dict()
@@ -150,7 +150,7 @@ def _run_net(kw, state_seed, B, H, W, in_seed, store_state, multimodal=False, sa
     for k, v in sd.items():
         if store_state or 'running' in k:
             out['state/' + k] = v.numpy().copy()
-    h, v, i, d, gt = fx.synth_batch(in_seed, B, H, W)
+    h, v, i, d, gt = fx.synth_batch(in_seed, B, H, W, n=kw['model_views'])
     mask = fx.synth_mask(in_seed + 1, B, H, W)
     mpi = fx.synth_mpi(in_seed + 2, gt)
     args = [T(h), T(v), T(i), T(d)]
@@ -205,6 +205,9 @@ def gen_net():
         save(f'net_full_{variant}.npz', **res)
     kw = fx.model_kwargs('base', True, chs=70)
     save('net_full_base_cross.npz', **_run_net(kw, 13, 1, 16, 16, 33, store_state=False, sample_stride=97))
+    # another topology: --model_in_blocks 2 --model_out_blocks 4 --model_views 7 (84 bins)
+    kw = fx.model_kwargs('upr', False, chs=8, model_in_blocks=2, model_out_blocks=4, model_views=7)
+    save('net_tiny_upr_topo247.npz', **_run_net(kw, 11, 2, 20, 20, 21, store_state=True))
     # odd --model_ksize (symmetric padding k // 2 for both convs of a block, feed_forward.py:86-88): oracle-only fixture, the
     # CUDA path implements the published ksize = 2
     kw = fx.model_kwargs('base', False, chs=8, model_ksize=3)
