@@ -54,6 +54,17 @@ def draw_params(rng, H, W, ps, max_factor=4, shift_range=1.0, level=0.9):
     return dict(f=f, disp=disp, y=y, x=x, r=r, mat=m, bright=bright, contrast=contrast, ps=ps)
 
 
+def draw_params_plain(rng, H, W, ps):
+    """``--train_no_data_augment`` (train/cli.py:72-76): RandomCrop(ps + 16) -> CenterCrop(ps) only; every other stage of
+    the fused chain gets its identity parameters (factor 1, zero shift, no rotation, identity colour matrix, gains of 1 --
+    the Contrast pass is skipped by the caller, it is not an exact identity in float32)."""
+    size = ps + 2 * 4 * 2
+    assert H > size and W > size, 'patch + margin does not fit the scene (hci4d.py:656-657)'
+    y = rng.randint(0, H - size)
+    x = rng.randint(0, W - size)
+    return dict(f=1, disp=0.0, y=y, x=x, r=0, mat=np.eye(3), bright=1.0, contrast=1.0, ps=ps)
+
+
 def pack_samples(params, scene_ids, n):
     """list of draw_params() dicts (+ scene index each) -> ctypes array of mmlf_aug_sample (host memory)."""
     arr = (AugSample * len(params))()
@@ -81,7 +92,7 @@ class GpuAugmenter:
 
     def __init__(self, scenes, device='cuda'):
         _lib.require_device()
-        T = lambda a, dt: torch.as_tensor(np.asarray(a)).to(dt)  # noqa: E731
+        T = lambda a, dt: (a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a))).to(device=device, dtype=dt)  # noqa: E731
         self.stacks = torch.stack([torch.stack([T(s[k], torch.float32) for k in range(4)]) for s in scenes]).to(device)
         self.center = torch.stack([T(s[4], torch.float32) for s in scenes]).to(device).contiguous()
         self.gt = torch.stack([T(s[5], torch.float32) for s in scenes]).to(device).contiguous()
@@ -93,12 +104,14 @@ class GpuAugmenter:
         self.K = self.mpi.shape[1]
         self.device = self.stacks.device
 
-    def draw(self, B, ps, rng=_random, max_factor=4):
+    def draw(self, B, ps, rng=_random, max_factor=4, plain=False):
         """B scene indices + parameter sets from the host RNG (scene first, as the DataLoader picks the item first)."""
         ids = [rng.randrange(self.S) for _ in range(B)]
+        if plain:
+            return ids, [draw_params_plain(rng, self.H, self.W, ps) for _ in range(B)]
         return ids, [draw_params(rng, self.H, self.W, ps, max_factor) for _ in range(B)]
 
-    def __call__(self, scene_ids, params, mean_override=None):
+    def __call__(self, scene_ids, params, mean_override=None, plain=False):
         """-> (h, v, i, d (B, n, 3, ps, ps), center (B, 3, ps, ps), gt (B, ps, ps), mpi (B, K, 5, ps, ps) f32,
         mask (B, ps, ps) int32, index (B, 1)) on the GPU."""
         B, ps, n = len(params), int(params[0]['ps']), self.n
@@ -118,7 +131,8 @@ class GpuAugmenter:
         mo = None
         if mean_override is not None:
             mo = torch.as_tensor(np.asarray(mean_override, dtype=np.float32)).to(dev)
-        call('mmlf_augment_contrast', P(views), P(center), P(samples), P(sums), P(mo), B, n, ps, st)
+        if not plain:
+            call('mmlf_augment_contrast', P(views), P(center), P(samples), P(sums), P(mo), B, n, ps, st)
         index = torch.from_numpy(np.stack([self.index[i] for i in scene_ids]))
         self.last_means = sums / float(n * 3 * ps * ps)
         return views[0], views[1], views[2], views[3], center, gt, mpi, mask, index

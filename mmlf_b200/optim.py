@@ -41,6 +41,23 @@ class FusedAdam(torch.optim.Optimizer):
             off += k
         self._flat = (ps, flat_p, flat_g, flat_m, flat_v)
 
+    def broadcast_state_(self, src=0):
+        """Every rank takes rank `src`'s flat parameters and Adam moments (no-op single-process); see
+        parallel.broadcast_module_."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        if self._flat is None:
+            self._flatten()
+        ps, flat_p, flat_g, flat_m, flat_v = self._flat
+        for t in (flat_p, flat_m, flat_v):
+            dist.broadcast(t, src)
+        steps = torch.tensor([float(self.state[ps[0]]['step'])], device=flat_p.device)
+        dist.broadcast(steps, src)
+        for p in ps:
+            self.state[p]['step'] = torch.tensor(float(steps.item()))
+        torch.autograd.graph.increment_version(ps)
+
     @property
     def flat_grad(self):
         """The flat gradient buffer (all-reduce this in data-parallel training)."""

@@ -36,6 +36,19 @@ def all_reduce_sum_(t):
     return t
 
 
+def broadcast_module_(module, src=0):
+    """Every rank takes rank `src`'s parameters and buffers (no-op single-process).  The data-parallel training loop
+    only exchanges gradients, so the replicas must START identical -- torch.nn.DataParallel gets this by re-replicating
+    from device 0 every step (train/cli.py:159)."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return module
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t.data, src)
+    torch.autograd.graph.increment_version([t for t in list(module.parameters()) + list(module.buffers())])
+    return module
+
+
 def shard_batch(tensors, rank, world):
     """Contiguous dim-0 shard of each tensor (DataParallel scatter, train/cli.py:245)."""
     out = []

@@ -5,8 +5,17 @@ Differences, all on the B200 side of the boundary:
   * one process per GPU under torchrun (NCCL all-reduce of one flat gradient bucket + the loss normalisers) replaces
     the single-process ``torch.nn.DataParallel`` of train/cli.py:159;
   * ``torch.optim.Adam`` is replaced by the fused flat-buffer Adam (same update rule, same state_dict format);
-  * the dataset is the synthetic light-field source unless ``--train_trainset`` names an existing directory with a
-    loader the user supplies (the HCI4D file loader and CPU augmentations are out of scope).
+  * ``--train_trainset`` / ``--train_valset`` are HCI4D directories exactly as upstream (train/cli.py:95-104).  The scenes
+    are decoded once, cached in HBM, and the transform chain of train/cli.py:72-92 (static ``Shift``, then the random
+    augmentations or, with ``--train_no_data_augment``, the plain crop) runs as the fused GPU gather of
+    ``mmlf_b200.data.augment`` with its parameters drawn by the host ``random`` in the reference's order -- there are no
+    CPU dataset workers, so ``--train_num_workers`` is accepted and unused on that path;
+  * a dataset directory that does not exist is an ERROR.  ``--synthetic`` (extra flag) asks for the seeded synthetic
+    light-field source instead (no HCI data offline); it prints a warning, and records ``synthetic: True`` in the
+    checkpoint's hyper-parameters so that such a checkpoint cannot be mistaken for a real run;
+  * every rank starts from rank 0's parameters and buffers (broadcast after construction / ``--train_resume``), like
+    DataParallel's per-step replication from device 0; BatchNorm running statistics stay rank-local during training
+    (DataParallel's replicas do the same) and rank 0's are the ones checkpointed.
 ``--max_iterations`` (extra option, default 0 = run forever like the reference) bounds the loop for tests.
 """
 import os
@@ -71,18 +80,19 @@ _OPTIONS = [
     ('--val_disp_step', dict(default=0.1)),
     ('--max_iterations', dict(default=0)),
     ('--gpu_augment', dict(is_flag=True)),
+    (('--synthetic', 'synthetic_data'), dict(is_flag=True)),
 ]
 
 
 def _with_options(fn):
     for name, kw in reversed(_OPTIONS):
-        fn = click.option(name, **kw)(fn)
+        fn = click.option(*((name,) if isinstance(name, str) else name), **kw)(fn)
     return click.argument('output_dir', type=click.Path(exists=True))(fn)
 
 
 @click.command()
 @_with_options
-def main(output_dir, max_iterations, gpu_augment, **kwargs):
+def main(output_dir, max_iterations, gpu_augment, synthetic_data, **kwargs):
     assert not (kwargs['train_loss_strongest'] and kwargs['train_loss_multimodal'])
     if kwargs['model_invertible']:
         raise NotImplementedError('INNs are not supported anymore')          # train/cli.py:252
@@ -94,14 +104,32 @@ def main(output_dir, max_iterations, gpu_augment, **kwargs):
     dev = torch.device('cuda', local)
     torch.cuda.set_device(dev)
     ps = kwargs['train_ps']
-    # synthetic stand-in for HCI4D(train_trainset, transform=[Shift(train_shift), ...augmentations...])
-    trainset = synthetic.SyntheticLF(length=4096, n=kwargs['model_views'], H=ps, W=ps, seed=1)
-    sampler = torch.utils.data.distributed.DistributedSampler(trainset, world, rank, shuffle=True) if world > 1 else None
-    trainloader = torch.utils.data.DataLoader(trainset, batch_size=max(1, kwargs['train_bs'] // world),
-                                              shuffle=sampler is None, sampler=sampler,
-                                              num_workers=kwargs['train_num_workers'])
-    valset = synthetic.SyntheticLF(length=2, n=kwargs['model_views'], H=4 * ps, W=4 * ps, seed=2, name='val')
-    valloader = torch.utils.data.DataLoader(valset, batch_size=1, shuffle=False, num_workers=1)
+    import random
+    from ..data import hci4d
+    from ..data.augment import GpuAugmenter
+    random.seed(1234 + rank)
+    sampler = None
+    per_rank_bs = max(1, kwargs['train_bs'] // world)
+    if synthetic_data:
+        if rank == 0:
+            print('WARNING: --synthetic: training and validating on SYNTHETIC light fields, not on '
+                  f"{kwargs['train_trainset']!r} / {kwargs['train_valset']!r}", file=sys.stderr)
+        kwargs['synthetic'] = True
+        trainset = synthetic.SyntheticLF(length=4096, n=kwargs['model_views'], H=ps, W=ps, seed=1)
+        sampler = torch.utils.data.distributed.DistributedSampler(trainset, world, rank, shuffle=True) if world > 1 else None
+        trainloader = torch.utils.data.DataLoader(trainset, batch_size=per_rank_bs, shuffle=sampler is None,
+                                                  sampler=sampler, num_workers=kwargs['train_num_workers'])
+        valset = synthetic.SyntheticLF(length=2, n=kwargs['model_views'], H=4 * ps, W=4 * ps, seed=2, name='val')
+        train_scenes = None
+    else:
+        for opt in ('train_trainset', 'train_valset'):
+            if not os.path.isdir(kwargs[opt]):
+                raise click.UsageError(f"--{opt} {kwargs[opt]!r} is not a directory (HCI4D layout, train/cli.py:95-104); "
+                                       'pass --synthetic to train on the synthetic light-field source instead')
+        nv = (kwargs['model_views'], kwargs['model_views'])
+        train_scenes = hci4d.HCI4D(kwargs['train_trainset'], nviews=nv, cache=True, length=4096, device=dev)
+        valset = hci4d.HCI4D(kwargs['train_valset'], nviews=nv, cache=True, device=dev)
+        trainloader = None
 
     model = FeedForward(**kwargs).to(dev)
     optimizer = FusedAdam(model.parameters(), lr=kwargs['train_lr'])
@@ -113,26 +141,27 @@ def main(output_dir, max_iterations, gpu_augment, **kwargs):
     mse_fn, bad_pix_fn = loss.MaskedMSELoss(), loss.MaskedBadPix()
 
     augmenter = None
-    if gpu_augment and not kwargs['train_no_data_augment']:
-        # the reference's transform chain (train/cli.py:78-90) on the GPU: scenes resident in HBM, parameters drawn by the
+    if train_scenes is not None or (gpu_augment and not kwargs['train_no_data_augment']):
+        # the reference's transform chain (train/cli.py:72-92) on the GPU: scenes resident in HBM, parameters drawn by the
         # host `random` in the reference's order, one gather kernel per batch (mmlf_b200/data/augment.py)
-        import random
-        from ..data import hci4d
-        from ..data.augment import GpuAugmenter
-        side = max(4 * ps, kwargs['train_max_downscale'] * (ps + 17))
-        scenes = [synthetic.SyntheticLF(length=8, n=kwargs['model_views'], H=side, W=side, seed=7)[j] for j in range(8)]
+        if train_scenes is not None:
+            scenes = train_scenes.data
+        else:
+            side = max(4 * ps, kwargs['train_max_downscale'] * (ps + 17))
+            scenes = [synthetic.SyntheticLF(length=8, n=kwargs['model_views'], H=side, W=side, seed=7)[j] for j in range(8)]
         augmenter = GpuAugmenter(scenes, dev)
         if kwargs['train_shift'] != 0.0:                                       # static Shift first (train/cli.py:89-90)
             for j in range(augmenter.S):
                 st = [augmenter.stacks[j, k] for k in range(4)]
                 hci4d.Shift(float(kwargs['train_shift']))(tuple(st) + (None, augmenter.gt[j], augmenter.mpi[j]))
-        random.seed(1234 + rank)
+        plain = bool(kwargs['train_no_data_augment'])
 
         def gpu_batches():
             while True:
-                ids, params = augmenter.draw(max(1, kwargs['train_bs'] // world), ps, random, kwargs['train_max_downscale'])
-                yield augmenter(ids, params)
+                ids, params = augmenter.draw(per_rank_bs, ps, random, kwargs['train_max_downscale'], plain=plain)
+                yield augmenter(ids, params, plain=plain)
         trainloader = gpu_batches()
+    static_shift = float(kwargs['train_shift']) if (augmenter is None and kwargs['train_shift'] != 0.0) else None
 
     i = 0
     if kwargs['train_resume']:                                                # train/cli.py:137-157
@@ -146,6 +175,10 @@ def main(output_dir, max_iterations, gpu_augment, **kwargs):
         for param_group in optimizer.param_groups:
             param_group['lr'] = kwargs['train_lr']
         i = state['iteration']
+    # one replica: every rank continues from rank 0's parameters, buffers and Adam moments (DataParallel replicates from
+    # device 0 every step, train/cli.py:159; here the ranks stay identical because they apply the same summed gradient)
+    parallel.broadcast_module_(model)
+    optimizer.broadcast_state_()
     val_model = Ensamble(model, **kwargs) if kwargs['val_ensamble'] else model
 
     log = None
@@ -159,7 +192,18 @@ def main(output_dir, max_iterations, gpu_augment, **kwargs):
     loss_val_avg = mse_avg = bad_pix_avg = 0.0
     dims = (2 if kwargs['model_cross'] else 4) * kwargs['model_views'] * 3
     time_start = 0
+    epoch = 0
+
+    def val_batches():
+        """The validation scenes one by one with a batch dimension of 1 (DataLoader(valset, batch_size=1), train/cli.py:101)."""
+        for j in range(len(valset)):
+            item = valset[j]
+            yield [torch.as_tensor(t).unsqueeze(0) for t in item]
+
     while True:
+        if sampler is not None:
+            sampler.set_epoch(epoch)                                          # reshuffle every pass, like shuffle=True
+        epoch += 1
         for data in trainloader:
             h_views, v_views, i_views, d_views, center, gt, mpi, mask, index = data
             if kwargs['train_loss_strongest']:
@@ -168,6 +212,10 @@ def main(output_dir, max_iterations, gpu_augment, **kwargs):
             mask = mask.int() * loss.create_mask_margin(mask.shape, 11).to(mask.device)   # train/cli.py:194
             h_views, v_views, i_views, d_views = (t.to(dev, non_blocking=True) for t in (h_views, v_views, i_views, d_views))
             gt, mpi, mask = gt.to(dev), mpi.to(dev).float(), mask.to(dev)
+            if static_shift is not None:        # Shift(train_shift) of train/cli.py:89-90 on the DataLoader path, on the GPU
+                hci4d.Shift(static_shift)((h_views, v_views, i_views, d_views))
+                gt = gt - static_shift
+                mpi[:, :, 4] -= static_shift
             gt_classes = None
             if kwargs['model_discrete']:                                      # targets are built on the GPU
                 gt_classes = (mpi_to_weights(mpi, kwargs['val_disp_min'], kwargs['val_disp_max'], dims)
@@ -209,7 +257,7 @@ def main(output_dir, max_iterations, gpu_augment, **kwargs):
                 with torch.no_grad():
                     model.eval()
                     loss_val_avg = mse_avg = bad_pix_avg = 0.0
-                    for j, vdata in enumerate(valloader):
+                    for j, vdata in enumerate(val_batches()):
                         vh, vv, vi, vd, center, vgt, vmpi, _, index = vdata
                         vh, vv, vi, vd = (t.to(dev) for t in (vh, vv, vi, vd))
                         vgt, vmpi = vgt.to(dev), vmpi.to(dev).float()

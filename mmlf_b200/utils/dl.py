@@ -1,5 +1,7 @@
 """Drop-in for the hot-path part of ``mmlf.utils.dl`` (/root/reference/mmlf/utils/dl.py): the checkpoint writer and
-the disparity <-> bin helpers.  ``save_img`` / ``BatchIter`` are out of scope (PNG writer / unused helper)."""
+the disparity <-> bin helpers, plus ``save_img`` (PNG writer used by ``HCI4D.save_batch``).  ``BatchIter`` is an unused
+helper upstream and not provided."""
+import numpy as np
 import torch
 
 from .. import ops
@@ -54,3 +56,20 @@ def class_to_reg(arr, start, stop, n_steps):
     DPP head kernel computes `mean` directly)."""
     result = torch.linspace(start, stop, n_steps).view((1, -1, 1, 1)).to(arr.device)
     return torch.sum(result * arr, 1)
+
+
+def save_img(fname, arr):
+    """utils/dl.py:75-105: (3, h, w) rgb or (h, w) grey array / tensor -> 8-bit PNG; values outside [0, 1] are min-max
+    normalised first.  The float -> uint8 step is skimage.img_as_ubyte's: ``rint(x * 255)``.  PIL instead of skimage
+    (not installed in this image); host-side file I/O."""
+    from PIL import Image
+    if not isinstance(arr, np.ndarray):
+        arr = arr.detach().cpu().numpy()
+    arr = np.asarray(arr, dtype=np.float64 if arr.dtype == np.float64 else np.float32)
+    a_min, a_max = np.min(arr), np.max(arr)
+    if a_min < 0.0 or a_max > 1.0:
+        arr = (arr - a_min) / (a_max - a_min)
+    if arr.ndim == 3:
+        arr = np.transpose(arr, (1, 2, 0))
+    img = np.clip(np.rint(arr * 255.0), 0, 255).astype(np.uint8)
+    Image.fromarray(img).save(fname)

@@ -276,6 +276,169 @@ def gen_evalmode():
     save('net_tiny_base_evalmode.npz', **out)
 
 
+# ---------------------------------------------------------------------------- trained-like full-width fixtures
+TRAINED = dict(B=8, ps=32, lr=1e-3, trunk_steps=30, head_steps=60, traj_steps=20, n_batches=4, seed0=200, grad_stride=13)
+
+
+def _trained_batch(k):
+    """Batch k of the trained-like fixtures: 8 synthetic 32 x 32 light fields + mask + multi-plane target."""
+    c = TRAINED
+    h, v, i, d, gt = fx.synth_batch(c['seed0'] + k, c['B'], c['ps'], c['ps'])
+    mask = fx.synth_mask(c['seed0'] + 50 + k, c['B'], c['ps'], c['ps'], margin=3)
+    return [T(h), T(v), T(i), T(d)], gt, mask
+
+
+def _variant_loss(model, variant, o, gt, mask):
+    if variant == 'dpp':
+        target = dl.reg_to_class(T(gt), -3.5, 3.5, model.steps)
+        return rloss.MaskedCrossEntropy()(o, target, T(mask))
+    return _loss_for(variant, False)(o, T(gt), T(mask))
+
+
+def gen_trained():
+    """Well-conditioned, non-degenerate full-width (chs = 70) states: the reference model after real training steps.
+
+    The trunk (in-nets + out-net blocks 0..6) is trained as a BASE model for 30 Adam steps (lr 1e-3, B = 8, 32 px,
+    train-mode BatchNorm) from the torch.manual_seed(0) default init; its conv-weight DELTAS are quantised to int8 per
+    tensor so that the 4.6 M parameters cost 4.6 MB once (the init is re-created from the seed by the tests).  UPR and
+    DPP take the same trunk and train their own head (trunk frozen).  Everything the fixture records -- eval outputs,
+    one training step (loss, outputs, gradients), a 20-step Adam loss trajectory -- is computed by the reference FROM THE
+    QUANTISED STATE, i.e. from exactly the weights the tests rebuild."""
+    c = TRAINED
+    batches = [_trained_batch(k) for k in range(c['n_batches'])]
+    kw = fx.model_kwargs('base', False, chs=70)
+    torch.manual_seed(0)
+    model = FeedForward(**kw)
+    init = {k: v.detach().numpy().copy() for k, v in model.state_dict().items()}
+    opt = torch.optim.Adam(model.parameters(), lr=c['lr'])
+    model.train()
+    for s in range(c['trunk_steps']):
+        args, gt, mask = batches[s % c['n_batches']]
+        opt.zero_grad()
+        lossv = _variant_loss(model, 'base', model(*args), gt, mask)
+        lossv.backward()
+        opt.step()
+        print('trunk step', s, lossv.item())
+    trunk = {}
+    for k, v in model.state_dict().items():
+        if k.startswith('out_net.7.'):
+            continue
+        a = v.detach().numpy()
+        if a.ndim == 4:                                   # conv weight: int8 delta from the seeded init
+            q, scale = fx.quantise_delta(a, init[k])
+            trunk['q/' + k], trunk['s/' + k] = q, scale
+        else:
+            trunk['f/' + k] = a.copy()
+    save('net_trained_trunk.npz', **trunk)
+    trunk_state = fx.trained_trunk_state(trunk, init)
+
+    for variant in ('base', 'upr', 'dpp'):
+        kw = fx.model_kwargs(variant, False, chs=70)
+        torch.manual_seed(0)
+        model = FeedForward(**kw)
+        sd = model.state_dict()
+        for k, a in trunk_state.items():
+            sd[k].copy_(T(np.array(a)))
+        # ---- head: trained with the trunk frozen
+        head = [p for n, p in model.named_parameters() if n.startswith('out_net.7.')]
+        for n, p in model.named_parameters():
+            p.requires_grad_(n.startswith('out_net.7.'))
+        opt = torch.optim.Adam(head, lr=c['lr'])
+        model.train()
+        for s in range(c['head_steps']):
+            args, gt, mask = batches[s % c['n_batches']]
+            opt.zero_grad()
+            lossv = _variant_loss(model, variant, model(*args), gt, mask)
+            lossv.backward()
+            opt.step()
+            if s % 10 == 0:
+                print(variant, 'head step', s, lossv.item())
+        for p in model.parameters():
+            p.requires_grad_(True)
+            p.grad = None
+        out = {}
+        for k, v in model.state_dict().items():
+            if k.startswith('out_net.7.') or 'running' in k or 'num_batches' in k:
+                out['state/' + k] = v.detach().numpy().copy()
+        start_state = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        # ---- eval forward on batch 0
+        args, gt, mask = batches[0]
+        model.eval()
+        with torch.no_grad():
+            o = model(*[a.clone() for a in args])
+        for k, t in o.items():
+            if t is None:
+                continue
+            a = t.numpy()
+            if a.ndim == 4 and a.shape[1] > 2:            # 108-plane tensors: light fields 0 and 5 only
+                a = a[[0, 5]]
+            out['eval/' + k] = a.copy()
+        # ---- one training step (forward + loss + backward) on batch 0
+        model.train()
+        o = model(*[a.clone() for a in args])
+        lossv = _variant_loss(model, variant, o, gt, mask)
+        lossv.backward()
+        out['train/loss'] = np.array(lossv.item(), np.float64)
+        for k in ('mean', 'logvar', 'scores'):
+            if o[k] is not None:
+                a = o[k].detach().numpy()
+                out['train/' + k] = (a[[0, 5]] if a.ndim == 4 else a).copy()
+        for name, p in model.named_parameters():
+            g = p.grad.numpy()
+            out['grad/' + name] = g.reshape(-1)[::c['grad_stride']].copy() if g.size > 4096 else g.copy()
+            out['gnorm/' + name] = np.array(np.sqrt((g.astype(np.float64) ** 2).sum()))
+        for k, vv in model.state_dict().items():
+            if 'running' in k or 'num_batches' in k:
+                out['after/' + k] = vv.numpy().copy()
+        # ---- 20-step Adam trajectory from the start state (train/cli.py:243-258: forward, loss, backward, step)
+        model.load_state_dict(start_state)
+        opt = torch.optim.Adam(model.parameters(), lr=c['lr'])
+        traj = []
+        for s in range(c['traj_steps']):
+            args, gt, mask = batches[s % c['n_batches']]
+            opt.zero_grad()
+            lossv = _variant_loss(model, variant, model(*args), gt, mask)
+            lossv.backward()
+            opt.step()
+            traj.append(lossv.item())
+        out['traj/loss'] = np.array(traj, np.float64)
+        model.eval()
+        with torch.no_grad():
+            o = model(*[a.clone() for a in batches[0][0]])
+        key = 'scores' if variant == 'dpp' else 'mean'
+        a = o[key].numpy()
+        out['traj/final_eval_' + key] = (a[[0, 5]] if a.ndim == 4 else a).copy()
+        print(variant, 'trajectory', traj[0], '->', traj[-1])
+        save(f'net_trained_{variant}.npz', **out)
+
+
+def gen_randomshift():
+    """RandomShift (hci4d.py:993-1028) under random.seed(s): the drawn disparity and the resampled stacks, numpy branch."""
+    import random
+    rng = np.random.RandomState(31)
+    H = W = 16
+    base = [rng.uniform(0, 1, (9, 3, H, W)).astype(np.float32) for _ in range(4)]
+    gt = rng.uniform(-2, 2, (H, W)).astype(np.float32)
+    mpi = rng.uniform(-2, 2, (2, 5, H, W)).astype(np.float64)
+    out = {'gt': gt, 'mpi': mpi}
+    for k, b in enumerate(base):
+        out[f'in{k}'] = b
+    cases = [(101, 1.0), (102, 1.0), (103, 2.5), (104, (-0.5, 3.0)), (105, (1.0, 1.0))]
+    for j, (seed, rg) in enumerate(cases):
+        random.seed(seed)
+        data = [b.copy() for b in base] + [np.zeros(1), gt.copy(), mpi.copy()]
+        res = hci4d.RandomShift(rg)(tuple(data))
+        for k in range(4):
+            out[f'out{j}_{k}'] = res[k]
+        out[f'gt{j}'], out[f'mpi{j}'] = res[5], res[6]
+        out[f'disp{j}'] = np.array(float(gt[0, 0]) - float(res[5][0, 0]))
+    out['seeds'] = np.array([s for s, _ in cases])
+    out['ranges'] = np.array([(r if isinstance(r, tuple) else (-r, r)) for _, r in cases], np.float64)
+    out['is_tuple'] = np.array([isinstance(r, tuple) for _, r in cases])
+    save('randomshift.npz', **out)
+
+
+
 # ---------------------------------------------------------------------------- losses
 def gen_losses():
     rng = np.random.RandomState(17)
@@ -480,6 +643,6 @@ def gen_cli():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['indices', 'shift', 'bins', 'net', 'losses', 'ese', 'adam', 'checkpoint', 'texture', 'augment', 'metrics', 'evalmode', 'unet', 'cli']
+    which = sys.argv[1:] or ['indices', 'shift', 'bins', 'net', 'losses', 'ese', 'adam', 'checkpoint', 'texture', 'augment', 'metrics', 'evalmode', 'unet', 'cli', 'trained', 'randomshift']
     for w in which:
         globals()['gen_' + w]()

@@ -164,3 +164,91 @@ def synth_state(shapes, seed):
         else:                                                        # biases, BatchNorm beta
             state[name] = rng.uniform(-0.1, 0.1, shape).astype(np.float32)
     return state
+
+
+# ----------------------------------------------------------------------------- trained-like full-width fixtures
+def quantise_delta(w, w_init):
+    """int8 quantisation of a trained weight's difference from its seeded initial value: (q int8, scale float32)."""
+    delta = (np.asarray(w, np.float32) - np.asarray(w_init, np.float32)).astype(np.float32)
+    scale = np.float32(max(float(np.abs(delta).max()), 1e-12) / 127.0)
+    q = np.clip(np.rint(delta / scale), -127, 127).astype(np.int8)
+    return q, np.array(scale, np.float32)
+
+
+def trained_trunk_state(trunk, init):
+    """Rebuild the trunk state (in-nets + out-net blocks 0..6) of tests/golden/net_trained_trunk.npz:
+    conv weights = seeded init + int8 delta * scale (one float32 multiply, one float32 add -> reproducible anywhere),
+    everything else stored as is.  ``init``: name -> numpy array of the torch.manual_seed(0) default initialisation."""
+    keys = trunk.files if hasattr(trunk, 'files') else trunk.keys()
+    state = {}
+    for k in keys:
+        tag, name = k[:2], k[2:]
+        if tag == 'q/':
+            d = (trunk[k].astype(np.float32) * np.float32(trunk['s/' + name])).astype(np.float32)
+            state[name] = (np.asarray(init[name], np.float32) + d).astype(np.float32)
+        elif tag == 'f/':
+            state[name] = np.array(trunk[k])
+    return state
+
+
+TRAINED = dict(B=8, ps=32, lr=1e-3, traj_steps=20, n_batches=4, seed0=200, grad_stride=13)
+
+
+def trained_batch(k):
+    """Batch k of the trained-like fixtures (same recipe as oracle/gen_golden.py::_trained_batch)."""
+    c = TRAINED
+    h, v, i, d, gt = synth_batch(c['seed0'] + k, c['B'], c['ps'], c['ps'])
+    mask = synth_mask(c['seed0'] + 50 + k, c['B'], c['ps'], c['ps'], margin=3)
+    return (h, v, i, d), gt, mask
+
+
+def trained_state(variant, init, trunk, g):
+    """Full state of the trained-like fixture `net_trained_<variant>.npz` (g): trunk + the variant's head and BatchNorm
+    statistics.  ``init``: the variant's own torch.manual_seed(0) default init (numpy)."""
+    state = {k: np.array(v) for k, v in init.items()}
+    state.update(trained_trunk_state(trunk, init))
+    for k in g.files:
+        if k.startswith('state/'):
+            state[k[6:]] = np.array(g[k])
+    return state
+
+
+# ----------------------------------------------------------------------------- on-disk HCI4D-style scenes
+def write_pfm(fname, img):
+    """Minimal little-endian PFM writer, independent of mmlf_b200.utils.pfm (rows as given: callers store bottom-up)."""
+    img = np.ascontiguousarray(img, dtype='<f4')
+    with open(fname, 'wb') as f:
+        f.write(b'Pf\n%d %d\n-1.000000\n' % (img.shape[1], img.shape[0]))
+        img.tofile(f)
+
+
+def write_hci_scene(scene_dir, seed, H=64, W=64, n=9, with_mask=False, with_mpi=False):
+    """One scene in the layout of the HCI 4D Light Field Dataset (hci4d.py:82-95): input_Cam000..080.png (row-major view
+    grid), gt_disp_lowres.pfm (stored bottom-up), plus distractor files the loader must skip.  Returns
+    (views uint8 (n*n, H, W, 3), gt float32 (H, W))."""
+    import os
+    from PIL import Image
+    os.makedirs(scene_dir, exist_ok=True)
+    views, gt = synth_lf(seed, H, W, n)
+    u8 = np.clip(np.rint(views * 255.0), 0, 255).astype(np.uint8)              # (n, n, 3, H, W)
+    u8 = np.ascontiguousarray(u8.reshape(n * n, 3, H, W).transpose(0, 2, 3, 1))
+    for j in range(n * n):
+        Image.fromarray(u8[j]).save(os.path.join(scene_dir, f'input_Cam{j:03d}.png'))
+    Image.fromarray(u8[0]).save(os.path.join(scene_dir, 'center_normals.png'))    # filtered out by name (hci4d.py:134-137)
+    Image.fromarray(u8[1]).save(os.path.join(scene_dir, 'objectids_highres.png'))
+    write_pfm(os.path.join(scene_dir, 'gt_disp_lowres.pfm'), gt[::-1])
+    write_pfm(os.path.join(scene_dir, 'gt_depth_lowres.pfm'), 2 * gt[::-1])      # loses against the 'disp' file (:199-201)
+    if with_mask:
+        m = np.zeros((H, W, 3), np.uint8)
+        m[4:, :, :] = 255
+        Image.fromarray(m).save(os.path.join(scene_dir, 'mask.png'))
+    if with_mpi:
+        rng = np.random.RandomState(seed + 7)
+        mpi = np.zeros((H, W, 3, 5), np.float32)                                 # stored (H, W, K, 5), bottom-up
+        mpi[..., :3] = rng.uniform(0, 1, (H, W, 3, 3))
+        mpi[..., 0, 3], mpi[..., 1, 3], mpi[..., 2, 3] = 0.7, 0.3, 0.0
+        mpi[..., 0, 4] = gt
+        mpi[..., 1, 4] = gt + 1.0
+        mpi[3, 5, 2, 4] = np.nan                                                 # NaNs become 0 (hci4d.py:220)
+        np.savez(os.path.join(scene_dir, 'gt_mpi_lowres.npz'), mpi=mpi[::-1])
+    return u8, gt

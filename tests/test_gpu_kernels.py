@@ -730,3 +730,75 @@ def test_adam_against_golden(golden):
         np.testing.assert_allclose(p.cpu().numpy(), g[f'p{s + 1}'], rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(m.cpu().numpy(), g['exp_avg'], rtol=1e-5, atol=1e-7)
     np.testing.assert_allclose(v.cpu().numpy(), g['exp_avg_sq'], rtol=1e-5, atol=1e-9)
+
+
+def test_random_shift_against_the_reference(golden):
+    """RandomShift (hci4d.py:993-1028) under random.seed(s): the same disparity is drawn from the host `random` stream and
+    the resampled stacks / corrected gt / mpi are bit-identical to the reference's numpy branch -- on CUDA tensors and,
+    staged through the GPU, on numpy arrays (the reference's dataset-transform usage)."""
+    import random
+    from mmlf_b200.data import hci4d
+    g = golden('randomshift.npz')
+    for j, seed in enumerate(g['seeds']):
+        lo, hi = (float(x) for x in g['ranges'][j])
+        rg = (lo, hi) if bool(g['is_tuple'][j]) else hi
+        for numpy_in in (False, True):
+            random.seed(int(seed))
+            stacks = [g[f'in{k}'].copy() for k in range(4)]
+            gt, mpi = g['gt'].copy(), g['mpi'].copy()
+            if not numpy_in:
+                stacks = [torch.from_numpy(a).cuda() for a in stacks]
+                gt, mpi = torch.from_numpy(gt).cuda(), torch.from_numpy(mpi).cuda()
+            res = hci4d.RandomShift(rg)(tuple(stacks) + (np.zeros(1), gt, mpi))
+            host = lambda t: t if isinstance(t, np.ndarray) else t.cpu().numpy()  # noqa: E731
+            for k in range(4):
+                assert res[k] is stacks[k]                                          # in place, like the reference
+                assert np.array_equal(host(res[k]), g[f'out{j}_{k}']), (j, k, numpy_in)
+            assert np.array_equal(host(res[5]), g[f'gt{j}']) and np.array_equal(host(res[6]), g[f'mpi{j}'])
+    with pytest.raises(AssertionError):
+        hci4d.RandomShift(-1.0)
+    with pytest.raises(AssertionError):
+        hci4d.RandomShift(1)
+
+
+def test_hci4d_loader_against_the_oracle(tmp_path):
+    """HCI4D.load_scene (hci4d.py:124-254) on an on-disk scene in the dataset's layout: PNG decode on the host, crosshair
+    extraction + u8 -> f32 and the texture mask on the GPU; bit-exact against the oracle's extraction of the same bytes."""
+    import _fixtures as fx
+    import oracle
+    from mmlf_b200.data import hci4d
+    root = tmp_path / 'training'
+    u8a, gta = fx.write_hci_scene(str(root / 'boxes'), 5, 48, 40, with_mask=True, with_mpi=True)
+    u8b, gtb = fx.write_hci_scene(str(root / 'cotton'), 6, 48, 40)
+    ds = hci4d.HCI4D(str(root), cache=True)
+    assert ds.scenes_names == ['boxes', 'cotton'] and len(ds) == 2 and ds.name == 'training'
+    assert len(hci4d.HCI4D(str(root), length=4096)) == 4096
+    for idx, (u8, gt) in enumerate(((u8a, gta), (u8b, gtb))):
+        item = ds[idx]
+        want = oracle.extract_stacks(u8)
+        for k in range(5):
+            assert item[k].is_cuda and np.array_equal(item[k].cpu().numpy(), want[k]), k
+        assert np.array_equal(item[5].cpu().numpy(), gt)                            # PFM is stored bottom-up
+        assert item[8].tolist() == [idx]
+        tex = oracle.create_mask_texture(want[4][None], 23, 0.02)[0]
+        sure = np.abs(oracle.texture_mae(want[4][None], 23)[0] - np.float32(0.02)) > 1e-6    # not within round-off of the threshold
+        mask = item[7].cpu().numpy()
+        assert mask.dtype == np.int64 and mask.shape == gt.shape
+        if idx == 0:
+            assert not mask[:4].any() and np.array_equal(mask[4:][sure[4:]], tex[4:][sure[4:]])   # mask.png zeroes rows 0..3
+            mpi = item[6].cpu().numpy()
+            assert mpi.shape == (3, 5, 48, 40) and mpi[2, 4, 3, 5] == 0.0           # NaN -> 0
+            assert np.array_equal(mpi[0, 4], gt) and np.array_equal(mpi[1, 3], np.full_like(gt, 0.3))
+        else:
+            assert np.array_equal(mask[sure], tex[sure])
+            mpi = item[6].cpu().numpy()
+            assert mpi.shape == (1, 5, 48, 40) and mpi.dtype == np.float64
+            assert np.array_equal(mpi[0, :3], want[4]) and np.array_equal(mpi[0, 4], gt) and (mpi[0, 3] == 1).all()
+    # the Shift transform works on a copy: the cached scene is untouched (hci4d.py:288-291)
+    ds.transform = hci4d.Shift(1.5)
+    shifted = ds[1]
+    assert np.array_equal(ds.data[1][5].cpu().numpy(), gtb)
+    assert np.array_equal(shifted[5].cpu().numpy(), gtb - np.float32(1.5))
+    want = oracle.shift(tuple(a.copy() for a in oracle.extract_stacks(u8b)[:4]), 1.5)
+    for k in range(4):
+        assert np.array_equal(shifted[k].cpu().numpy(), want[k])

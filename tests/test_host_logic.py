@@ -116,7 +116,8 @@ def test_cli_surfaces_match_the_reference():
     from mmlf_b200.train.cli import main as tmain
     from mmlf_b200.validate.cli import main as vmain
     ref = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'cli_options.json')))
-    for name, cmd, extra in (('train', tmain, {'max_iterations', 'gpu_augment'}), ('validate', vmain, {'size'})):
+    for name, cmd, extra in (('train', tmain, {'max_iterations', 'gpu_augment', 'synthetic_data'}),
+                             ('validate', vmain, {'size', 'synthetic_data'})):
         mine = {p.name: p for p in cmd.params}
         assert set(mine) - {r['name'] for r in ref[name]} == extra
         for r in ref[name]:
@@ -124,3 +125,50 @@ def test_cli_surfaces_match_the_reference():
             assert list(p.opts) == r['opts'] and type(p).__name__ == r['kind'], r['name']
             assert bool(getattr(p, 'is_flag', False)) == r['is_flag'] and p.type.name == r['type'], r['name']
             assert str(p.default) == str(r['default']), (r['name'], p.default, r['default'])
+
+
+def test_pfm_roundtrip_and_scene_file_selection(tmp_path):
+    """Host side of the HCI4D loader (hci4d.py:129-138, 196-213; utils/pfm.py): file filters, ground-truth pick, PFM I/O."""
+    from mmlf_b200.data import hci4d
+    from mmlf_b200.utils import dl, pfm
+    rng = np.random.RandomState(0)
+    img = rng.uniform(-3, 3, (7, 5)).astype(np.float32)
+    pfm.save(str(tmp_path / 'a.pfm'), img)
+    assert np.array_equal(pfm.load(str(tmp_path / 'a.pfm')), img)
+    fx.write_pfm(str(tmp_path / 'b.pfm'), img)                      # independent writer -> our reader
+    assert np.array_equal(pfm.load(str(tmp_path / 'b.pfm')), img)
+    col = rng.uniform(0, 1, (4, 6, 3)).astype(np.float32)
+    pfm.save(str(tmp_path / 'c.pfm'), col)
+    assert np.array_equal(pfm.load(str(tmp_path / 'c.pfm')), col)
+    with pytest.raises(Exception):
+        pfm.save(str(tmp_path / 'd.pfm'), img.astype(np.float64))
+    (tmp_path / 'e.pfm').write_bytes(b'P6\n1 1\n-1\n0000')
+    with pytest.raises(Exception):
+        pfm.load(str(tmp_path / 'e.pfm'))
+    files = [f'input_Cam{j:03d}.png' for j in (2, 0, 1)] + ['mask.png', 'a_normals.png', 'objectids.png', 'x_edges.jpg',
+                                                             'specular.png', 'unused_1.png', 'gt_disp_lowres.pfm', 'notes.txt']
+    assert hci4d.scene_view_files(files) == ['input_Cam000.png', 'input_Cam001.png', 'input_Cam002.png']
+    assert hci4d.pick_gt_file(['x.txt'], 40) is None
+    assert hci4d.pick_gt_file(['only.pfm'], 40) == 'only.pfm'
+    assert hci4d.pick_gt_file(['gt_depth_lowres.pfm', 'gt_disp_lowres.pfm'], 40) == 'gt_disp_lowres.pfm'
+    assert hci4d.pick_gt_file(['gt_disp_highres.pfm', 'gt_disp_lowres.pfm'], 40) == 'gt_disp_lowres.pfm'
+    assert hci4d.pick_gt_file(['gt_disp_lowres_Cam040.pfm', 'gt_disp_lowres_Cam000.pfm'], 40) == 'gt_disp_lowres_Cam040.pfm'
+    # save_img: values outside [0, 1] are min-max normalised, CHW -> HWC, rint(x * 255)
+    from PIL import Image
+    dl.save_img(str(tmp_path / 'g.png'), np.array([[0.0, 0.5], [1.0, 0.25]], np.float32))
+    assert np.asarray(Image.open(str(tmp_path / 'g.png'))).tolist() == [[0, 128], [255, 64]]
+    dl.save_img(str(tmp_path / 'h.png'), np.array([[-1.0, 3.0]], np.float32))
+    assert np.asarray(Image.open(str(tmp_path / 'h.png'))).tolist() == [[0, 255]]
+    dl.save_img(str(tmp_path / 'i.png'), torch.zeros(3, 2, 4))
+    assert np.asarray(Image.open(str(tmp_path / 'i.png'))).shape == (2, 4, 3)
+
+
+def test_hci4d_requires_scene_directories(tmp_path):
+    from mmlf_b200.data import hci4d
+    with pytest.raises(FileNotFoundError):
+        hci4d.HCI4D(str(tmp_path))
+    (tmp_path / 'boxes').mkdir()
+    ds = hci4d.HCI4D(str(tmp_path), device='cpu')
+    assert ds.scenes_names == ['boxes'] and len(ds) == 1
+    with pytest.raises(FileNotFoundError):
+        ds.load_scene(0)                                            # no view images in the scene
