@@ -7,8 +7,14 @@
 
 workload train (default): one training step of the 4-stream FeedForward model -- forward, masked loss, backward,
 gradient all-reduce, Adam -- on a global batch of 512 patches of 96 x 96 px, 9 views per stack (BASELINE.json
-configs[1]); the batch is sharded over the ranks (strong scaling: the global batch is fixed).
+configs[1]); the batch is sharded over the ranks (strong scaling: the global batch is fixed).  The step is the product's
+``mmlf_b200.train.step.TrainStep`` (what ``mmlf.train.cli`` runs): one CUDA-graph replay per step.
 workload infer: full-light-field inference, one 9x9-view 512 x 512 light field per rank and step.
+workload ese / bands: the 70-member shift ensemble / the row bands of ONE light field sharded over the ranks.
+
+The default run prints the BASE-train headline line and nests the other BASELINE.json configs under ``secondary``
+(``infer``, ``upr_train``, ``dpp_train``, ``ese``, ``bands``: each with value, e2e, roofline, measured in the same process,
+one after the other); ``--no-secondary`` or an explicit ``--workload`` / ``--variant`` prints that one workload alone.
 """
 import argparse
 import json
@@ -125,9 +131,8 @@ def cpu_train_step(variant, b, ps, threads):
     import oracle
     from oracle import losses as olosses
     torch.set_num_threads(threads)
-    from mmlf_b200.model.feed_forward import FeedForward   # parameter containers only (same init as the reference)
-    torch.manual_seed(0)
-    state = {k: v.numpy().copy() for k, v in FeedForward(**model_kwargs(variant)).state_dict().items()}
+    from oracle.init import default_state          # the reference's default init (torch.manual_seed(0)); no product code
+    state = default_state(**model_kwargs(variant))
     net = oracle.FeedForwardOracle(state, model_uncert=(variant == 'upr'), model_discrete=(variant == 'dpp'))
     net.training = True
     rng = np.random.RandomState(0)
@@ -159,9 +164,8 @@ def cpu_infer_step(variant, size, threads):
     import torch
     import oracle
     torch.set_num_threads(threads)
-    from mmlf_b200.model.feed_forward import FeedForward
-    torch.manual_seed(0)
-    state = {k: v.numpy().copy() for k, v in FeedForward(**model_kwargs(variant)).state_dict().items()}
+    from oracle.init import default_state
+    state = default_state(**model_kwargs(variant))
     net = oracle.FeedForwardOracle(state, model_uncert=(variant == 'upr'), model_discrete=(variant == 'dpp'))
     rng = np.random.RandomState(0)
     views = [rng.uniform(0, 1, (1, 9, 3, size, size)).astype(np.float32) for _ in range(4)]
@@ -172,9 +176,8 @@ def cpu_ese_step(size, members, threads):
     import torch
     import oracle
     torch.set_num_threads(threads)
-    from mmlf_b200.model.feed_forward import FeedForward
-    torch.manual_seed(0)
-    state = {k: v.numpy().copy() for k, v in FeedForward(**model_kwargs('upr')).state_dict().items()}
+    from oracle.init import default_state
+    state = default_state(**model_kwargs('upr'))
     net = oracle.FeedForwardOracle(state, model_uncert=True)
     rng = np.random.RandomState(0)
     views = [rng.uniform(0, 1, (1, 9, 3, size, size)).astype(np.float32) for _ in range(4)]
@@ -216,28 +219,8 @@ def run_cpu(args, steps, warmup):
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=8)
-    ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='train', choices=['train', 'infer', 'ese', 'bands'])
-    ap.add_argument('--variant', default='base', choices=['base', 'upr', 'dpp'])
-    ap.add_argument('--bs', type=int, default=512, help='global batch (train)')
-    ap.add_argument('--ps', type=int, default=96, help='patch size (train)')
-    ap.add_argument('--size', type=int, default=512, help='light-field size (infer)')
-    ap.add_argument('--precision', default='fp16', choices=['fp16', 'bf16', 'split'], help='activation storage format')
-    ap.add_argument('--cpu-batch', type=int, default=2)
-    ap.add_argument('--cpu-size', type=int, default=128)
-    ap.add_argument('--no-cpu-baseline', action='store_true')
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
-    if args.workload == 'ese':
-        args.variant = 'upr'                                 # --val_ensamble forces model_uncert (train/cli.py:68-69)
-
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
+def describe(args, world):
+    """metric / unit / config of one workload (BASELINE.json's metric and configs)."""
     metric = ('train patches/s (bs512, 96px)' if args.workload == 'train' else 'full-LF inference Mpx/s')
     unit = 'patches/s' if args.workload == 'train' else 'Mpx/s'
     wl = {'train': f'{args.variant.upper()} training step bs={args.bs} ps={args.ps}, 4-stream FeedForward '
@@ -254,35 +237,42 @@ def main():
               'global_batch': args.bs if args.workload == 'train' else (1 if args.workload in ('ese', 'bands') else world),
               'parallelism': f'dp{world}', 'l2': 'inputs larger than L2 (>= 113 MB fp32 per step and GPU)',
               'activation_storage': args.precision, 'gradient_storage': 'bf16', 'accumulate': 'fp32'}
+    return metric, unit, config, strong
 
-    if args.impl == 'reference':
-        if rank != 0:
-            return
-        base, dt = run_cpu(args, max(args.steps, 1), min(args.warmup, 1))
-        line = {'impl': 'reference', 'metric': metric, 'value': base['value'], 'unit': unit, 'n_gpus': world,
-                'steps': args.steps, 'warmup': min(args.warmup, 1), 'ms_per_step': dt * 1e3, 'higher_is_better': True,
-                'scaling': 'strong' if strong else 'weak', 'vs_baseline': None, 'dtype': 'f32',
-                'data': 'synthetic', 'config': config, 'cpu_baseline': base,
-                'e2e': {'value': base['value'], 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-                'gpu_launches': 0}
-        print(json.dumps(line))
-        return
 
+def run_reference(args, world):
+    """--impl reference: the CPU restatement of the reference algorithm (oracle/, numpy fp32) on the host cores, with the
+    warm-up / step counts it was given, each step a bounded sample of the workload (stated in config.sample)."""
+    metric, unit, config, strong = describe(args, world)
+    base, dt = run_cpu(args, max(args.steps, 1), max(args.warmup, 0))
+    config = {'workload': config['workload'], 'global_batch': config['global_batch'], 'parallelism': 'host cores',
+              'sample': base['sample'], 'arithmetic': 'fp32 numpy (oracle/ port of the reference algorithm)'}
+    return {'impl': 'reference', 'metric': metric, 'value': base['value'], 'unit': unit, 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
+            'scaling': 'strong' if strong else 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic', 'config': config, 'cpu_baseline': base,
+            'e2e': {'value': base['value'], 'unit': unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+
+
+def run_gpu(args, rank, world, local, with_cpu_baseline, sample_clocks=True):
+    """One workload on the GPUs -> the JSON line (dict) on rank 0, None elsewhere."""
+    import gc
     import torch
     import torch.distributed as dist
     from mmlf_b200 import _lib, parallel
     from mmlf_b200.model.feed_forward import FeedForward
     from mmlf_b200.model import loss as L
     from mmlf_b200.optim import FusedAdam
-    from mmlf_b200.utils import dl
+    from mmlf_b200.train.step import TrainStep
 
-    rank, world, local = parallel.init_from_env('nccl')
-    torch.cuda.set_device(local)
+    metric, unit, config, strong = describe(args, world)
     dev = torch.device('cuda', local)
     torch.manual_seed(0)
     model = FeedForward(**model_kwargs(args.variant)).to(dev)
     model.precision = args.precision
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    train_step = None
 
     def barrier():
         if world > 1:
@@ -296,21 +286,14 @@ def main():
         gt = torch.rand((B, H, W), device=dev, generator=gen) * 4 - 2
         mask = L.create_mask_margin((B, H, W), 11).to(torch.int32).to(dev)
         opt = FusedAdam(model.parameters(), lr=1e-3)
-        loss_fn = {'base': L.MaskedL1Loss(), 'upr': L.ImprovedUncertaintyL1Loss(), 'dpp': L.MaskedCrossEntropy()}[args.variant]
         model.train()
+        # the product's training step (mmlf.train.cli): forward + loss + backward + all-reduce + Adam, one graph replay;
+        # DPP builds its one-hot class target inside the loss kernel (utils/dl.py:109-131)
+        train_step = TrainStep(model, opt, {'base': 'l1', 'upr': 'upr', 'dpp': 'ce'}[args.variant], ce_from_gt=True)
+        config['step'] = 'mmlf_b200.train.step.TrainStep (CUDA-graph replay)'
 
         def step(vs, gt_, mask_):
-            opt.zero_grad()
-            out = model(*vs)
-            if args.variant == 'dpp':
-                tgt = dl.reg_to_class(gt_, -3.5, 3.5, model.steps)
-                lossv = loss_fn(out, tgt, mask_)
-            else:
-                lossv = loss_fn(out, gt_, mask_)
-            lossv.backward()
-            parallel.all_reduce_sum_(opt.flat_grad)          # DataParallel's reduce-add (train/cli.py:159)
-            opt.step()
-            return lossv
+            return train_step(vs[0], vs[1], vs[2], vs[3], gt_, mask_)
         units_per_step = args.bs
         flops_per_step = train_step_flops(args.bs, H, W, args.variant)
         host = [t.cpu().pin_memory() for t in views + [gt, mask]]
@@ -325,7 +308,6 @@ def main():
         def step(vs, gt_=None, mask_=None):
             with torch.no_grad():
                 return ens(*vs)['mean']
-        my_members = len(range(rank, ESE_MEMBERS, world))
         units_per_step = H * W / 1e6
         flops_per_step = ESE_MEMBERS * net_forward_flops(1, H, W, 'upr')
         host = [t.cpu().pin_memory() for t in views]
@@ -354,17 +336,16 @@ def main():
         host = [t.cpu().pin_memory() for t in views]
         gt = mask = None
 
-    # ---------------- warm-up
+    # ---------------- warm-up (the first training step also captures the graph)
     for _ in range(args.warmup):
         step(views, gt, mask)
     barrier()
 
     # ---------------- timed region: inputs resident in HBM, CUDA events, max over ranks
-    # The timed region runs the product path without instrumentation (inference replays a CUDA graph, whose kernels
-    # cannot be bracketed one by one).  Per-kernel times come from a second pass below: same work, one stream, no graph,
-    # a CUDA-event pair around every launch.
-    graphed = args.workload != 'train'
-    sampler = ClockSampler(local) if rank == 0 else None
+    # The timed region runs the product path without instrumentation (training and inference both replay CUDA graphs,
+    # whose kernels cannot be bracketed one by one).  Per-kernel times come from a separate pass below: same work, one
+    # stream, no graph, a CUDA-event pair around every launch.
+    sampler = ClockSampler(local) if (rank == 0 and sample_clocks) else None
     _lib.launch_count = 0
     _lib.set_profile(False)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -383,82 +364,6 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = ms.item() / args.steps
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
-    # ---------------- profiling pass
-    net = model
-    prof_steps = 2 if args.workload == 'train' else 3
-    if graphed:
-        net.use_cuda_graph = False
-    else:
-        net.engine.overlap_wgrad = False
-    _lib.set_profile(True)
-    for i in range(prof_steps):
-        if args.workload == 'train':
-            step(views, gt, mask)                 # the stream is always full at these sizes: pairs measure kernel time
-            continue
-        # a device-side sleep in front of every forward lets the host enqueue the whole forward before the first kernel
-        # starts, so each event pair brackets exactly one kernel
-        torch.cuda._sleep(20_000_000)
-        with torch.no_grad():
-            if args.workload == 'ese':
-                net.raw_forward(views, shift_disp=-3.5 + 0.1 * (7 * i + 3))
-            else:
-                step(views, gt, mask)
-    torch.cuda.synchronize()
-    prof = _lib.set_profile(False)
-    if graphed:
-        net.use_cuda_graph = True
-    else:
-        net.engine.overlap_wgrad = os.environ.get('MMLF_OVERLAP_WGRAD', '0') == '1'
-    barrier()
-
-    # ---------------- per-kernel shares and the roofline of the dominant kernel (the tcgen05 conv)
-    by_name = {}
-    for name, a, b in prof:
-        by_name.setdefault(name, []).append(a.elapsed_time(b))
-    shares = {k: sum(v) / prof_steps for k, v in by_name.items()}
-    kernel_sum_ms = max(sum(shares.values()), 1e-9)           # summed kernel time of one profiled step / forward
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-    except OSError:
-        pass
-    peak_tf, peak_src = peaks.get('bf16_tflops_sustained'), 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)'
-    if not peak_tf:
-        peak_tf, peak_src = 1400.0, 'fallback (B200_PROFILING.md: sustained ~1.4 PFLOP/s)'
-    conv_ms = by_name.get('mmlf_conv2x2', [])
-    wgrad_ms = by_name.get('mmlf_conv2x2_wgrad', []) + by_name.get('mmlf_conv2x2_wgrad_canonical', [])
-    n_conv = len(conv_ms) / prof_steps
-    # algorithmic flops of all conv2x2 launches of one step on this rank: forward convs + data gradients
-    Bl = B
-    fwd = net_forward_flops(Bl, H, W, args.variant)
-    if args.workload == 'train':
-        conv_flops_rank = 2.0 * fwd - 4 * conv_flops(Bl, H, W, 27, 70, 0)
-        # the small head convs of BASE / UPR run partly on CUDA cores: negligible (< 0.1 %)
-    elif args.workload == 'ese':
-        conv_flops_rank = fwd                                # the profiling pass times single members
-    elif args.workload == 'bands':
-        lo_, hi_, a_, b_ = parallel.band_rows(H, rank, world, 11)
-        conv_flops_rank = net_forward_flops(1, b_ - a_, W, args.variant)
-    else:
-        conv_flops_rank = fwd
-    conv_time = sum(conv_ms) / prof_steps / 1e3
-    achieved = conv_flops_rank / conv_time / 1e12 if conv_time > 0 else 0.0
-    roofline = {'kernel': 'conv2x2_tc_kernel (all forward + data-gradient launches of a step)', 'bound': 'tensor',
-                'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
-                'peak_source': peak_src, 'traffic': CONV_TRAFFIC['bytes'], 'traffic_note': CONV_TRAFFIC['note'],
-                'launches_per_step': n_conv,
-                'avg_launch_ms': (sum(conv_ms) / len(conv_ms)) if conv_ms else None,
-                'share_of_step': conv_time * 1e3 / kernel_sum_ms}
-    roofline['note'] = ('value: product path (%s); kernel times: separate single-stream pass of %d step(s), CUDA events around '
-                        'every launch' % ('CUDA-graph replay' if graphed else 'eager launches', prof_steps))
-    if wgrad_ms:
-        wg_time = sum(wgrad_ms) / prof_steps / 1e3
-        wg_flops = fwd                                        # weight gradients cost one forward's worth of MACs
-        roofline['wgrad'] = {'kernel': 'conv2x2_wgrad_kernel + reduce', 'achieved': wg_flops / wg_time / 1e12,
-                             'frac': wg_flops / wg_time / 1e12 / peak_tf, 'share_of_step': wg_time * 1e3 / kernel_sum_ms}
-    roofline['step'] = {'achieved': flops_per_step / world / (ms_per_step / 1e3) / 1e12,
-                        'frac': flops_per_step / world / (ms_per_step / 1e3) / 1e12 / peak_tf,
-                        'note': 'whole step, algorithmic FLOPs of SURVEY.md section 6 per GPU'}
 
     # ---------------- end to end: host (pinned) inputs copied in every step, loss read back every step
     copy_stream = torch.cuda.Stream()
@@ -468,8 +373,8 @@ def main():
 
     def upload(slot):
         with torch.cuda.stream(copy_stream):
-            for d, s in zip(bufs[slot], host):
-                d.copy_(s, non_blocking=True)
+            for d, s_ in zip(bufs[slot], host):
+                d.copy_(s_, non_blocking=True)
             ready[slot].record(copy_stream)
 
     e2e_steps = max(3, min(args.steps, 5))
@@ -544,25 +449,182 @@ def main():
                       '(mmlf_lf_extract_u8) + forward on the GPU, result read back every step'}
         except Exception as ex:                                         # an extra measurement must not cost the bench line
             e2e_u8 = {'error': repr(ex)[:200]}
+    del bufs
 
+    # ---------------- profiling pass: un-graphed, one CUDA-event pair around every C-ABI call
+    net = model
+    prof_steps = (2 if args.workload == 'train' else 3) if args.profile_steps is None else args.profile_steps
+    by_name = {}
+    if prof_steps > 0:
+        if train_step is not None:
+            # the captured graph owns the activation memory of a whole step (88 GB at 512 patches): release it before the
+            # eager pass allocates its own
+            train_step._graphs.clear()
+            gc.collect()
+            torch.cuda.empty_cache()
+            net.engine.overlap_wgrad = False
+        else:
+            net.use_cuda_graph = False
+        _lib.set_profile(True)
+        for i in range(prof_steps):
+            if args.workload == 'train':
+                step(views, gt, mask)             # the stream is always full at these sizes: pairs measure kernel time
+                continue
+            # a device-side sleep in front of every forward lets the host enqueue the whole forward before the first
+            # kernel starts, so each event pair brackets exactly one kernel
+            torch.cuda._sleep(20_000_000)
+            with torch.no_grad():
+                if args.workload == 'ese':
+                    net.raw_forward(views, shift_disp=-3.5 + 0.1 * (7 * i + 3))
+                else:
+                    step(views, gt, mask)
+        torch.cuda.synchronize()
+        prof = _lib.set_profile(False)
+        if train_step is None:
+            net.use_cuda_graph = True
+        barrier()
+        for name, a, b in prof:
+            by_name.setdefault(name, []).append(a.elapsed_time(b))
+
+    # ---------------- per-kernel shares and the roofline of the dominant kernel (the tcgen05 conv)
+    shares = {k: sum(v) / prof_steps for k, v in by_name.items()}
+    kernel_sum_ms = max(sum(shares.values()), 1e-9)           # summed kernel time of one profiled step / forward
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except OSError:
+        pass
+    peak_tf, peak_src = peaks.get('bf16_tflops_sustained'), 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)'
+    if not peak_tf:
+        peak_tf, peak_src = 1400.0, 'fallback (B200_PROFILING.md: sustained ~1.4 PFLOP/s)'
+    conv_ms = by_name.get('mmlf_conv2x2', [])
+    wgrad_ms = by_name.get('mmlf_conv2x2_wgrad', []) + by_name.get('mmlf_conv2x2_wgrad_canonical', [])
+    roofline = None
+    fwd = net_forward_flops(B, H, W, args.variant)
+    if conv_ms:
+        n_conv = len(conv_ms) / prof_steps
+        # algorithmic flops of all conv2x2 launches of one step on this rank: forward convs + data gradients
+        if args.workload == 'train':
+            conv_flops_rank = 2.0 * fwd - 4 * conv_flops(B, H, W, 27, 70, 0)
+            # the small head convs of BASE / UPR run partly on CUDA cores: negligible (< 0.1 %)
+        elif args.workload == 'bands':
+            lo_, hi_, a_, b_ = parallel.band_rows(H, rank, world, 11)
+            conv_flops_rank = net_forward_flops(1, b_ - a_, W, args.variant)
+        else:
+            conv_flops_rank = fwd                            # ESE: the profiling pass times single members
+        conv_time = sum(conv_ms) / prof_steps / 1e3
+        achieved = conv_flops_rank / conv_time / 1e12
+        roofline = {'kernel': 'conv2x2_tc_kernel (all forward + data-gradient launches of a step)', 'bound': 'tensor',
+                    'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
+                    'peak_source': peak_src, 'traffic': CONV_TRAFFIC['bytes'], 'traffic_note': CONV_TRAFFIC['note'],
+                    'launches_per_step': n_conv, 'avg_launch_ms': sum(conv_ms) / len(conv_ms),
+                    'share_of_step': conv_time * 1e3 / kernel_sum_ms,
+                    'note': 'value: product path (CUDA-graph replay); kernel times: separate single-stream un-graphed pass '
+                            'of %d step(s), CUDA events around every launch' % prof_steps}
+        if wgrad_ms:
+            wg_time = sum(wgrad_ms) / prof_steps / 1e3
+            roofline['wgrad'] = {'kernel': 'conv2x2_wgrad_kernel + reduce', 'achieved': fwd / wg_time / 1e12,
+                                 'frac': fwd / wg_time / 1e12 / peak_tf, 'share_of_step': wg_time * 1e3 / kernel_sum_ms}
+    step_tf = flops_per_step / world / (ms_per_step / 1e3) / 1e12
+    if roofline is None:
+        roofline = {'kernel': 'whole step (no per-kernel pass in this run)', 'bound': 'tensor', 'achieved': step_tf,
+                    'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': step_tf / peak_tf, 'peak_source': peak_src, 'traffic': None}
+    roofline['step'] = {'achieved': step_tf, 'frac': step_tf / peak_tf,
+                        'note': 'whole step, algorithmic FLOPs of SURVEY.md section 6 per GPU'}
+    if shares:
+        bn = sum(v for k, v in shares.items() if k.startswith('mmlf_bn_'))
+        roofline['kernel_sum_ms'] = round(kernel_sum_ms, 3)
+        roofline['idle_frac_of_step'] = round(max(0.0, 1.0 - kernel_sum_ms / ms_per_step), 4)
+        roofline['batchnorm_share_of_kernel_time'] = round(bn / kernel_sum_ms, 4)
+
+    # free this workload's memory before the next one
+    train_step = None
+    del model, views, host
+    gc.collect()
+    torch.cuda.empty_cache()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
     cpu_base = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and with_cpu_baseline:
         cpu_base, _ = run_cpu(args, 2, 1)
     line = {'metric': metric, 'value': units_per_step / (ms_per_step / 1e3), 'unit': unit, 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
             'scaling': 'strong' if strong else 'weak', 'vs_baseline': None,
             'dtype': args.precision + ' storage / fp32 accumulate', 'data': 'synthetic', 'config': config,
-            'host_enqueue_ms_per_step': round(host_ms_per_step, 3), 'roofline': roofline, 'cpu_baseline': cpu_base, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
-            'kernel_ms_note': ('per training step, single-stream profiling pass' if not graphed else
-                               'per single un-graphed forward (ESE: one member)'),
-            'kernel_ms_per_step': {k: round(v, 3) for k, v in sorted(shares.items(), key=lambda kv: -kv[1])}}
+            'host_enqueue_ms_per_step': round(host_ms_per_step, 3), 'roofline': roofline, 'cpu_baseline': cpu_base,
+            'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks}
+    if shares:
+        line['kernel_ms_note'] = ('per training step, single-stream un-graphed profiling pass' if args.workload == 'train'
+                                  else 'per single un-graphed forward (ESE: one member)')
+        line['kernel_ms_per_step'] = {k: round(v, 3) for k, v in sorted(shares.items(), key=lambda kv: -kv[1])}
     if e2e_u8 is not None:
         line['e2e_u8_views'] = e2e_u8
-    print(json.dumps(line))
+    return line
+
+
+# the other BASELINE.json configs, nested under `secondary` of the default line: (key, workload, variant, steps)
+SECONDARY = [('infer', 'infer', 'base', 10), ('upr_train', 'train', 'upr', 4), ('dpp_train', 'train', 'dpp', 4),
+             ('ese', 'ese', 'upr', 3), ('bands', 'bands', 'base', 10)]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=8)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default=None, choices=['train', 'infer', 'ese', 'bands'])
+    ap.add_argument('--variant', default=None, choices=['base', 'upr', 'dpp'])
+    ap.add_argument('--bs', type=int, default=512, help='global batch (train)')
+    ap.add_argument('--ps', type=int, default=96, help='patch size (train)')
+    ap.add_argument('--size', type=int, default=512, help='light-field size (infer)')
+    ap.add_argument('--precision', default='fp16', choices=['fp16', 'bf16', 'split'], help='activation storage format')
+    ap.add_argument('--cpu-batch', type=int, default=2)
+    ap.add_argument('--cpu-size', type=int, default=128)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-secondary', action='store_true', help='only the headline workload')
+    ap.add_argument('--profile-steps', type=int, default=None, help='steps of the per-kernel pass (0 = skip it)')
+    args = ap.parse_args()
+    # the headline line (no --workload / --variant) also measures the other BASELINE configs
+    secondary = args.workload is None and args.variant is None and not args.no_secondary and args.impl == 'b200'
+    args.workload = args.workload or 'train'
+    args.variant = args.variant or 'base'
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+    if args.workload == 'ese':
+        args.variant = 'upr'                                 # --val_ensamble forces model_uncert (train/cli.py:68-69)
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.impl == 'reference':
+        if rank == 0:
+            print(json.dumps(run_reference(args, world)))
+        return
+
+    import copy
+    import torch
+    import torch.distributed as dist
+    from mmlf_b200 import parallel
+    rank, world, local = parallel.init_from_env('nccl')
+    torch.cuda.set_device(local)
+    line = run_gpu(args, rank, world, local, with_cpu_baseline=not args.no_cpu_baseline)
+    if secondary:
+        sec = {}
+        for key, workload, variant, steps in SECONDARY:
+            a = copy.copy(args)
+            a.workload, a.variant, a.steps, a.warmup, a.profile_steps = workload, variant, steps, 3, 1
+            try:
+                res = run_gpu(a, rank, world, local, with_cpu_baseline=False, sample_clocks=False)
+            except Exception as ex:                           # a secondary measurement must not cost the headline line
+                res = {'error': repr(ex)[:300]}
+                torch.cuda.empty_cache()
+            if rank == 0 and res is not None:
+                keep = ('metric', 'value', 'unit', 'ms_per_step', 'scaling', 'steps', 'warmup', 'config', 'e2e', 'roofline',
+                        'gpu_launches', 'host_enqueue_ms_per_step', 'kernel_ms_per_step', 'e2e_u8_views', 'error')
+                sec[key] = {k: res[k] for k in keep if k in res}
+        if rank == 0:
+            line['secondary'] = sec
+    if rank == 0:
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

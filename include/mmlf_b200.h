@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MMLF_ABI_VERSION 4
+#define MMLF_ABI_VERSION 5
 
 /* 16-bit storage formats.  Forward activations and weights are fp16 (11 significant bits; the reference's own GPU
  * path multiplies in TF32, 11 bits), gradients are bf16 (fp32 exponent range); accumulation is always fp32. */
@@ -237,13 +237,15 @@ int mmlf_bn_bwd_reduce(const void* dy, int ld_dy, const void* z, int ld_z, const
                        int act_dtype, double* sums, void* stream);
 /* Pass 2 (train = 2: sums[1] holds sum g*(z - mean) from a fused conv epilogue and is multiplied by invstd first):
  * dz = gamma * invstd * (g - sum_g / count - xhat * sum_gx / count) (16-bit, halo zero);
- * dgamma = sum_gx, dbeta = sum_g (f32 [C_real]).  fsums: f32 scratch [2 * C].  train = 0 gives the eval-mode gradient
- * dz = g * gamma * invstd.  dz_colsum (optional, f32 [C]): += sum over slots of dz as stored = the bias gradient of
- * the convolution in front of the BatchNorm (feed_forward.py:125). */
+ * dgamma (+)= sum_gx, dbeta (+)= sum_g (f32 [C_real]; `accumulate` != 0 adds to what is there -- the shared in-nets are
+ * called twice per forward).  gamma: the module's weight, f32 [C_real] (NOT padded).  fsums: f32 scratch [3 * C].
+ * train = 0 gives the eval-mode gradient dz = g * gamma * invstd.  dz_colsum (optional, f32 [C]): += sum over slots of
+ * dz as stored = the bias gradient of the convolution in front of the BatchNorm (feed_forward.py:125). */
 int mmlf_bn_bwd_apply(const void* dy, int ld_dy, const void* z, int ld_z, const float* scale, const float* shift,
                       const float* gamma, const float* save_mean, const float* save_invstd, const double* sums,
                       int64_t count, int train, int C_real, int C, int B, int H, int W, int grad_dtype, int act_dtype,
-                      void* dz, int ld_dz, float* dgamma, float* dbeta, float* fsums, float* dz_colsum, void* stream);
+                      void* dz, int ld_dz, float* dgamma, float* dbeta, int accumulate, float* fsums, float* dz_colsum,
+                      void* stream);
 
 /* ReLU backward alone (blocks without BatchNorm): dz = dy * (y > 0), bf16 slots. */
 int mmlf_relu_bwd(const void* dy, int ld_dy, const void* y, int ld_y, int C, int64_t n_slots, int grad_dtype,
@@ -295,10 +297,14 @@ int mmlf_loss_prepass(const int32_t* mask, const int32_t* mask_padding, const fl
  *       4 MaskedMSELoss (:114-122, value only)    5 MaskedBadPix (:177-187, value only, threshold in `param`)
  * target: gt (B, H, W) for kinds 0/2/4/5, mpi (B, K, 5, H, W) for kinds 1/3.  sums: the (all-reduced) pre-pass sums.
  * loss_sum (double[1], zeroed): receives the un-normalised masked sum; value = loss_sum / max(sums[0], 1 if 0).
- * g_mean / g_logvar (B, H, W) f32 or NULL: d value / d mean, d value / d logvar. */
+ * g_mean / g_logvar (B, H, W) f32 or NULL: d value / d mean, d value / d logvar.
+ * pred_stride: element stride between the images of mean / logvar / g_mean / g_logvar (0 = HW, i.e. dense): with
+ * 2 * HW, mean = out and logvar = out + HW address the planes of the network output (B, 2, H, W) in place
+ * (feed_forward.py:270,293: `output[:, 0]`, `output[:, 1]`), and the gradients land in a (B, 2, H, W) tensor likewise. */
 int mmlf_loss_regression(int kind, const float* mean, const float* logvar, const float* target, int K,
                          const int32_t* mask, const int32_t* mask_padding, const double* sums, double param,
-                         int64_t B, int64_t HW, double* loss_sum, float* g_mean, float* g_logvar, void* stream);
+                         int64_t B, int64_t HW, double* loss_sum, float* g_mean, float* g_logvar, int64_t pred_stride,
+                         void* stream);
 
 /* MaskedCrossEntropy (loss.py:145-160): l = logsumexp(relu(s)) - sum_c relu(s_c) t_c, masked mean.
  * target (B, S, H, W) f32 or, if NULL, built on the fly from gt with reg_to_class (utils/dl.py:109-131).
@@ -318,6 +324,35 @@ int mmlf_ese_reduce(const float* means, const float* logvars, const float* disp,
  * step = 1-based step count after the increment. */
 int mmlf_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
                    double eps, int64_t step, void* stream);
+/* The same update with its step-dependent scalars in DEVICE memory, so that the launch can sit in a captured CUDA graph
+ * and be replayed with a new learning rate / step count (train/cli.py:233-241 changes lr every iteration):
+ * hyper: double[4] = { lr (written by the host before each replay), step count BEFORE this update (advanced here),
+ * scratch, scratch }.  Two launches: a one-thread kernel advances the step and derives lr / bias_correction1 and
+ * sqrt(bias_correction2) in float64 exactly like the host version, then the element-wise update. */
+int mmlf_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, double* hyper, double beta1,
+                       double beta2, double eps, void* stream);
+
+/* ------------------------------------------------------------------ small fixed-cost helpers of a training step */
+/* cudaMemsetAsync(ptr, 0, bytes) on `stream` (accumulator scratch of the column-sum / statistics kernels). */
+int mmlf_zero(void* ptr, int64_t bytes, void* stream);
+
+/* One launch for all the short per-parameter vector updates at the end of a backward pass (conv bias gradients from the
+ * float64 / padded-pitch column sums of the kernels that produced the gradients, accumulation for shared modules):
+ *     dst[i] = (accumulate ? dst[i] : 0) + (float) src[i],  i < n.
+ * jobs: DEVICE array of n_jobs descriptors (built once by the host; every pointer in it is a device pointer). */
+typedef struct mmlf_vec_job {
+  const void* src;    /* f32 or f64 */
+  float* dst;
+  int32_t n;
+  int32_t src_f64;    /* 1: src is double */
+  int32_t accumulate;
+  int32_t pad_;
+} mmlf_vec_job;
+int mmlf_vec_jobs(const mmlf_vec_job* jobs, int n_jobs, void* stream);
+
+/* loss value of the masked losses without a host sync and without framework glue: out[0] = (float)(loss_sum[0] /
+ * (sums[0] == 0 ? 1 : sums[0]))  (loss.py:73-77: no division when the mask is empty). */
+int mmlf_loss_finish(const double* loss_sum, const double* sums, float* out, void* stream);
 
 /* ------------------------------------------------------------------ validation metrics */
 /* laplace_to_discrete / lmm_to_discrete (validate/cli.py:91-118): means / logvars (K, B, HW) f32 (K = 1: one Laplacian),

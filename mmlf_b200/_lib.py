@@ -65,7 +65,7 @@ _PROTOS = {
     'mmlf_bn_apply_relu': (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_p, c_i, c_i, c_p]),
     'mmlf_bn_bwd_reduce': (c_i, [c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     'mmlf_bn_bwd_apply': (c_i, [c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i, c_i, c_i, c_i, c_i,
-                                c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p]),
+                                c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_p]),
     'mmlf_relu_bwd': (c_i, [c_p, c_i, c_p, c_i, c_i, c_i64, c_i, c_i, c_p, c_i, c_p]),
     'mmlf_head_small': (c_i, [c_p, c_i, c_i, c_p, c_p, c_i, c_i, c_i, c_p, c_p]),
     'mmlf_head_small_bwd': (c_i, [c_p, c_p, c_i, c_i, c_p, c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_p]),
@@ -74,14 +74,18 @@ _PROTOS = {
     'mmlf_reg_to_class': (c_i, [c_p, c_p, c_i, c_d, c_i64, c_i64, c_p, c_p]),
     'mmlf_mpi_to_weights': (c_i, [c_p, c_i, c_p, c_i, c_d, c_i64, c_i64, c_p, c_p]),
     'mmlf_loss_prepass': (c_i, [c_p, c_p, c_p, c_i, c_i64, c_i64, c_p, c_p]),
-    'mmlf_loss_regression': (c_i, [c_i, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_d, c_i64, c_i64, c_p, c_p, c_p, c_p]),
+    'mmlf_loss_regression': (c_i, [c_i, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_d, c_i64, c_i64, c_p, c_p, c_p, c_i64, c_p]),
     'mmlf_loss_cross_entropy': (c_i, [c_p, c_p, c_p, c_p, c_d, c_i, c_p, c_p, c_i64, c_i64, c_p, c_p, c_p]),
     'mmlf_ese_reduce': (c_i, [c_p, c_p, c_p, c_i, c_i64, c_i64, c_p, c_p, c_p, c_p]),
     'mmlf_adam_step': (c_i, [c_p, c_p, c_p, c_p, c_i64, c_d, c_d, c_d, c_d, c_i64, c_p]),
+    'mmlf_adam_step_dev': (c_i, [c_p, c_p, c_p, c_p, c_i64, c_p, c_d, c_d, c_d, c_p]),
+    'mmlf_zero': (c_i, [c_p, c_i64, c_p]),
+    'mmlf_vec_jobs': (c_i, [c_p, c_i, c_p]),
+    'mmlf_loss_finish': (c_i, [c_p, c_p, c_p, c_p]),
 }
 
 EXPORTS = tuple(_PROTOS)
-ABI_VERSION = 4
+ABI_VERSION = 5
 _lib = None
 
 
@@ -105,7 +109,7 @@ def lib():
 
 
 # kernels launched per C-ABI call (for the launch count reported by bench.py)
-_KERNELS_PER_CALL = {'mmlf_augment_fill': 0, 'mmlf_augment_patches': 2, 'mmlf_pack_views_split': 2, 'mmlf_conv2x2_wgrad': 2, 'mmlf_conv2x2_wgrad_canonical': 2, 'mmlf_bn_bwd_apply': 2, 'mmlf_head_small_bwd': 2, 'mmlf_shift_taps': 0}
+_KERNELS_PER_CALL = {'mmlf_zero': 0, 'mmlf_adam_step_dev': 2, 'mmlf_augment_fill': 0, 'mmlf_augment_patches': 2, 'mmlf_pack_views_split': 2, 'mmlf_conv2x2_wgrad': 2, 'mmlf_conv2x2_wgrad_canonical': 2, 'mmlf_bn_bwd_apply': 2, 'mmlf_head_small_bwd': 2, 'mmlf_shift_taps': 0}
 launch_count = 0
 _profile = None          # when set to a list, call() appends (name, start_event, end_event)
 

@@ -316,8 +316,10 @@ slot_map_kernel(const void* __restrict__ a, int ld_a, const void* __restrict__ y
 }
 
 // per-channel means of the two backward reductions in fp32 (+ the parameter gradients dgamma = sum g*xhat, dbeta = sum g)
+// (also pads gamma to the channel pitch: fsums[2 C + c] = c < C_real ? gamma[c] : 0, read by the slot pass)
 __global__ void bn_bwd_means_kernel(const double* __restrict__ sums, double inv_count, int C_real, int C,
                                     float* __restrict__ fsums, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                    int accumulate, const float* __restrict__ gamma,
                                     const float* __restrict__ invstd) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -325,9 +327,11 @@ __global__ void bn_bwd_means_kernel(const double* __restrict__ sums, double inv_
   const double sgx = invstd ? sums[C + c] * static_cast<double>(invstd[c]) : sums[C + c];
   fsums[c] = static_cast<float>(sums[c] * inv_count);
   fsums[C + c] = static_cast<float>(sgx * inv_count);
+  fsums[2 * C + c] = c < C_real ? gamma[c] : 0.0f;
   if (c < C_real && dgamma && dbeta) {
-    dbeta[c] = static_cast<float>(sums[c]);
-    dgamma[c] = static_cast<float>(sgx);
+    const float db = static_cast<float>(sums[c]), dg = static_cast<float>(sgx);
+    dbeta[c] = accumulate ? dbeta[c] + db : db;
+    dgamma[c] = accumulate ? dgamma[c] + dg : dg;
   }
 }
 
@@ -466,24 +470,26 @@ extern "C" int mmlf_bn_bwd_apply(const void* dy, int ld_dy, const void* z, int l
                                  const float* shift, const float* gamma, const float* save_mean,
                                  const float* save_invstd, const double* sums, int64_t count, int train, int C_real,
                                  int C, int B, int H, int W, int grad_dtype, int act_dtype, void* dz, int ld_dz,
-                                 float* dgamma, float* dbeta, float* fsums, float* dz_colsum, void* stream) {
+                                 float* dgamma, float* dbeta, int accumulate, float* fsums, float* dz_colsum,
+                                 void* stream) {
   MMLF_REQUIRE(dy && z && scale && shift && gamma && save_mean && save_invstd && sums && dz, "bn_bwd_apply: null buffer");
   CHECK_C(C);
   const int64_t n_slots = static_cast<int64_t>(B) * (H + 1) * (W + 1);
   const int blocks = map_grid(n_slots, C, 2);
   const SlotDiv dv = make_div(H + 1, W + 1, n_slots);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  MMLF_REQUIRE(fsums != nullptr, "bn_bwd_apply: fsums scratch (float[2*C]) required");
+  MMLF_REQUIRE(fsums != nullptr, "bn_bwd_apply: fsums scratch (float[3*C]) required");
   bn_bwd_means_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, 1.0 / static_cast<double>(count), C_real, C, fsums, dgamma,
-                                                         dbeta, train == 2 ? save_invstd : nullptr);
+                                                         dbeta, accumulate, gamma, train == 2 ? save_invstd : nullptr);
   if (int rc = check_launch("bn_bwd_means")) return rc;
+  const float* gamma_pad = fsums + 2 * C;            // gamma on the padded channel pitch, written by the kernel above
   const size_t smem = dz_colsum ? sizeof(float) * 256 * 8 : 0;
   if (train)
-    slot_map_kernel<2><<<blocks, 256, smem, st>>>(dy, ld_dy, nullptr, 0, z, ld_z, gamma, save_mean, save_invstd, fsums,
+    slot_map_kernel<2><<<blocks, 256, smem, st>>>(dy, ld_dy, nullptr, 0, z, ld_z, gamma_pad, save_mean, save_invstd, fsums,
                                                   scale, shift, C, dv, n_slots, dz, ld_dz, nullptr, 0, 0, dz_colsum,
                                                   grad_dtype, act_dtype);
   else
-    slot_map_kernel<3><<<blocks, 256, smem, st>>>(dy, ld_dy, nullptr, 0, z, ld_z, gamma, save_mean, save_invstd, fsums,
+    slot_map_kernel<3><<<blocks, 256, smem, st>>>(dy, ld_dy, nullptr, 0, z, ld_z, gamma_pad, save_mean, save_invstd, fsums,
                                                   scale, shift, C, dv, n_slots, dz, ld_dz, nullptr, 0, 0, dz_colsum,
                                                   grad_dtype, act_dtype);
   return check_launch("bn_bwd_apply");

@@ -77,9 +77,32 @@ int sm_count() {
   return n;
 }
 
+__global__ void vec_jobs_kernel(const mmlf_vec_job* __restrict__ jobs) {
+  const mmlf_vec_job j = jobs[blockIdx.x];
+  for (int i = threadIdx.x; i < j.n; i += blockDim.x) {
+    const float v = j.src_f64 ? static_cast<float>(static_cast<const double*>(j.src)[i])
+                              : static_cast<const float*>(j.src)[i];
+    j.dst[i] = j.accumulate ? j.dst[i] + v : v;
+  }
+}
+
 }  // namespace mmlf
 
 extern "C" {
+
+int mmlf_zero(void* ptr, int64_t bytes, void* stream) {
+  MMLF_REQUIRE(ptr != nullptr && bytes >= 0, "zero: bad arguments");
+  cudaError_t e = cudaMemsetAsync(ptr, 0, static_cast<size_t>(bytes), static_cast<cudaStream_t>(stream));
+  MMLF_REQUIRE(e == cudaSuccess, "zero: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int mmlf_vec_jobs(const mmlf_vec_job* jobs, int n_jobs, void* stream) {
+  MMLF_REQUIRE(jobs != nullptr && n_jobs >= 0, "vec_jobs: bad arguments");
+  if (n_jobs == 0) return 0;
+  mmlf::vec_jobs_kernel<<<n_jobs, 128, 0, static_cast<cudaStream_t>(stream)>>>(jobs);
+  return mmlf::check_launch("vec_jobs");
+}
 
 const char* mmlf_last_error(void) { return mmlf::g_err; }
 int mmlf_abi_version(void) { return MMLF_ABI_VERSION; }

@@ -44,7 +44,7 @@ loss_regression_kernel(int kind, const float* __restrict__ mean, const float* __
                        const float* __restrict__ target, int K, const int32_t* __restrict__ mask,
                        const int32_t* __restrict__ mask_padding, const double* __restrict__ sums, float param,
                        int64_t B, int64_t HW, double* __restrict__ loss_sum, float* __restrict__ g_mean,
-                       float* __restrict__ g_logvar) {
+                       float* __restrict__ g_logvar, int64_t pred_stride) {
   __shared__ double red[8];
   const double cnt = sums[0];
   const float scale = cnt == 0.0 ? 1.f : static_cast<float>(1.0 / cnt);
@@ -63,7 +63,9 @@ loss_regression_kernel(int kind, const float* __restrict__ mean, const float* __
   for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < B * HW;
        idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const float m = static_cast<float>(mask[idx]);
-    const float mu = mean[idx];
+    // mean / logvar and their gradients may be planes of one (B, OC, H, W) tensor: batch stride pred_stride
+    const int64_t pidx = pred_stride == HW ? idx : (idx / HW) * pred_stride + (idx % HW);
+    const float mu = mean[pidx];
     float l = 0.f, gm = 0.f, gl = 0.f;
     if (kind == 0 || kind == 4 || kind == 5) {
       const float d = mu - target[idx];
@@ -71,7 +73,7 @@ loss_regression_kernel(int kind, const float* __restrict__ mean, const float* __
       else if (kind == 4) { l = d * d; }
       else { l = fabsf(d) > param ? 1.f : 0.f; }
     } else if (kind == 2) {
-      const float lv = logvar[idx];
+      const float lv = logvar[pidx];
       const float d = mu - target[idx];
       const float e = expf(-lv);
       l = e * fabsf(d) + lv;
@@ -85,7 +87,7 @@ loss_regression_kernel(int kind, const float* __restrict__ mean, const float* __
       }
     } else {                                                  // multi-plane targets (B, K, 5, H, W)
       const int64_t b = idx / HW, pix = idx - b * HW;
-      const float lv = kind == 3 ? logvar[idx] : 0.f;
+      const float lv = kind == 3 ? logvar[pidx] : 0.f;
       const float e = kind == 3 ? expf(-lv) : 1.f;
       float ws = 0.f, sl = 0.f, sg = 0.f, sad = 0.f;
       for (int k = 0; k < K; ++k) {
@@ -107,8 +109,8 @@ loss_regression_kernel(int kind, const float* __restrict__ mean, const float* __
       }
     }
     acc += static_cast<double>(l * m);
-    if (g_mean) g_mean[idx] = gm * m * scale;
-    if (g_logvar) g_logvar[idx] = gl * m * scale;
+    if (g_mean) g_mean[pidx] = gm * m * scale;
+    if (g_logvar) g_logvar[pidx] = gl * m * scale;
   }
   const double r = block_sum_double(acc, red);
   if (threadIdx.x == 0) atomicAdd(loss_sum, r);
@@ -281,6 +283,37 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   p[i] = p[i] - step_size * (mi / denom);
 }
 
+// Adam with its step-dependent scalars in device memory (graph-replayable): hyper = { lr, step, step_size, sqrt(bc2) }
+__global__ void adam_prepare_kernel(double* __restrict__ hyper, double beta1, double beta2) {
+  const double step = hyper[1] + 1.0;
+  hyper[1] = step;
+  const double bc1 = 1.0 - pow(beta1, step);
+  const double bc2 = 1.0 - pow(beta2, step);
+  hyper[2] = hyper[0] / bc1;
+  hyper[3] = sqrt(bc2);
+}
+
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, int64_t n, float one_minus_b1, float b2, float one_minus_b2,
+                                const double* __restrict__ hyper, float eps) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float step_size = static_cast<float>(hyper[2]), bc2_sqrt = static_cast<float>(hyper[3]);
+  const float gi = g[i];
+  const float mi = m[i] + one_minus_b1 * (gi - m[i]);
+  const float vi = v[i] * b2 + one_minus_b2 * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] = p[i] - step_size * (mi / denom);
+}
+
+__global__ void loss_finish_kernel(const double* __restrict__ loss_sum, const double* __restrict__ sums,
+                                   float* __restrict__ out) {
+  const double cnt = sums[0];
+  out[0] = static_cast<float>(loss_sum[0] / (cnt == 0.0 ? 1.0 : cnt));
+}
+
 static int grid_for(int64_t n, int threads, int per_thread) {
   int64_t want = ceil_div64(n, static_cast<int64_t>(threads) * per_thread);
   const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
@@ -305,14 +338,16 @@ extern "C" int mmlf_loss_prepass(const int32_t* mask, const int32_t* mask_paddin
 extern "C" int mmlf_loss_regression(int kind, const float* mean, const float* logvar, const float* target, int K,
                                     const int32_t* mask, const int32_t* mask_padding, const double* sums, double param,
                                     int64_t B, int64_t HW, double* loss_sum, float* g_mean, float* g_logvar,
-                                    void* stream) {
+                                    int64_t pred_stride, void* stream) {
   MMLF_REQUIRE(kind >= 0 && kind <= 5, "loss_regression: kind must be 0..5");
+  if (pred_stride == 0) pred_stride = HW;
+  MMLF_REQUIRE(pred_stride >= HW, "loss_regression: pred_stride must be 0 (= HW) or >= HW");
   MMLF_REQUIRE(mean && target && mask && sums && loss_sum, "loss_regression: null buffer");
   MMLF_REQUIRE((kind != 2 && kind != 3) || logvar, "loss_regression: logvar required for the uncertainty losses");
   MMLF_REQUIRE((kind != 1 && kind != 3) || (K >= 1 && K <= 64), "loss_regression: bad K");
   loss_regression_kernel<<<grid_for(B * HW, 256, 2), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       kind, mean, logvar, target, K, mask, mask_padding, sums, static_cast<float>(param), B, HW, loss_sum, g_mean,
-      g_logvar);
+      g_logvar, pred_stride);
   return check_launch("loss_regression");
 }
 
@@ -349,4 +384,22 @@ extern "C" int mmlf_adam_step(float* p, const float* g, float* m, float* v, int6
       p, g, m, v, n, static_cast<float>(1.0 - beta1), static_cast<float>(beta2), static_cast<float>(1.0 - beta2),
       static_cast<float>(lr / bc1), static_cast<float>(sqrt(bc2)), static_cast<float>(eps));
   return check_launch("adam_step");
+}
+
+extern "C" int mmlf_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, double* hyper, double beta1,
+                                  double beta2, double eps, void* stream) {
+  MMLF_REQUIRE(p && g && m && v && hyper, "adam_step_dev: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  adam_prepare_kernel<<<1, 1, 0, st>>>(hyper, beta1, beta2);
+  if (int rc = check_launch("adam_prepare")) return rc;
+  adam_dev_kernel<<<static_cast<unsigned>(ceil_div64(n, 256)), 256, 0, st>>>(
+      p, g, m, v, n, static_cast<float>(1.0 - beta1), static_cast<float>(beta2), static_cast<float>(1.0 - beta2), hyper,
+      static_cast<float>(eps));
+  return check_launch("adam_step_dev");
+}
+
+extern "C" int mmlf_loss_finish(const double* loss_sum, const double* sums, float* out, void* stream) {
+  MMLF_REQUIRE(loss_sum && sums && out, "loss_finish: null buffer");
+  loss_finish_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(loss_sum, sums, out);
+  return check_launch("loss_finish");
 }

@@ -38,8 +38,19 @@ class PackJob(C.Structure):
                 ('dtype', C.c_int), ('split', C.c_int), ('weight_scale', C.c_float)]
 
 
+class VecJob(C.Structure):
+    """Mirror of ``mmlf_vec_job`` (include/mmlf_b200.h): one short vector update of the end-of-backward launch."""
+    _fields_ = [('src', C.c_void_p), ('dst', C.c_void_p), ('n', C.c_int32), ('src_f64', C.c_int32),
+                ('accumulate', C.c_int32), ('pad_', C.c_int32)]
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _zero(t):
+    """cudaMemsetAsync on the current stream (no framework fill kernel)."""
+    call('mmlf_zero', _ptr(t), t.numel() * t.element_size(), _stream())
 
 
 def _stream():
@@ -100,7 +111,11 @@ class Engine:
         self._fold_cache = {}
         self._param_cache = None
         self._buffer_cache = None
-        self._gpad_cache = {}
+        self._scratch_cache = {}
+        self._gflat = None
+        self._glayout = None
+        self._vec_jobs = None
+        self._ws = None
         self._side = None
         # BatchNorm-backward statistics out of the data-gradient epilogue: implemented and tested, but opt-in
         # (MMLF_BN_FUSE=1).  Measured on B200: the wide data gradient goes from 0.293 to 0.382 ms (the epilogue becomes the
@@ -226,17 +241,37 @@ class Engine:
         call('mmlf_pack_conv_weights_batch', _ptr(table), n_jobs, max_elems, _stream())
         self._pack_version = (version, bool(need_dgrad))
 
-    def _bn_padded(self, prefix, C_real, C, dev):
-        """gamma padded with zeros to the channel pitch (fp32); cached until the parameter changes."""
-        gamma = self._params()[prefix + '.weight']
-        key = (gamma._version, gamma.data_ptr())
-        hit = self._gpad_cache.get(prefix)
-        if hit is None or hit[0] != key:
-            g = torch.zeros(C, dtype=torch.float32, device=dev)
-            g[:C_real].copy_(gamma.detach())
-            hit = (key, g)
-            self._gpad_cache[prefix] = hit
-        return hit[1], None
+    # ------------------------------------------------------------------ persistent scratch / gradient buffer
+    def _scratch(self, geo):
+        """Accumulator scratch of a step, allocated once per (device, topology): the statistics / column-sum rows the
+        kernels add into (zeroed by ONE memset per pass) and the float32 per-channel rows of the BatchNorm backward."""
+        key = str(self.dev)
+        sc = self._scratch_cache.get(key)
+        if sc is None:
+            n_bn = len(self.stream_defs) * self.in_blocks + len(self.out_specs)
+            n_blk = n_bn + 2
+            fwd64 = torch.empty((max(n_bn, 1), 2 * 320), dtype=torch.float64, device=self.dev)
+            # backward accumulators in one allocation so that one memset clears them: [3 n_blk rows of 640 doubles |
+            # n_blk rows of 2 x 320 floats]
+            n64, n32 = 3 * n_blk * 640, 2 * n_blk * 320
+            acc = torch.empty(n64 * 8 + n32 * 4, dtype=torch.uint8, device=self.dev)
+            z64 = acc[:n64 * 8].view(torch.float64).view(3 * n_blk, 640)
+            z32 = acc[n64 * 8:].view(torch.float32).view(2 * n_blk, 320)
+            e32 = torch.empty((n_blk, 3 * 320), dtype=torch.float32, device=self.dev)
+            sc = dict(fwd64=fwd64, acc=acc, z64=z64, z32=z32, e32=e32)
+            self._scratch_cache[key] = sc
+        return sc
+
+    def grad_layout(self):
+        """name -> (offset, numel, shape) of every parameter in one flat float32 buffer, in named_parameters() order --
+        the layout of FusedAdam's flat buffers, so a training step can write gradients straight into the optimizer's."""
+        if self._glayout is None:
+            off, lay = 0, {}
+            for name, p in self._params().items():
+                lay[name] = (off, p.numel(), tuple(p.shape))
+                off += p.numel()
+            self._glayout = (lay, off)
+        return self._glayout
 
     # ------------------------------------------------------------------ kernel launch helpers
     def conv(self, geo, x, ld_in, cs, w, n_pad, cin_pad, ctype, out, ld_out, *, bias=None, scale=None, shift=None,
@@ -288,6 +323,15 @@ class Engine:
         produces it -- tcgen05 kind::f16 needs both operands of the weight-gradient GEMM in one format -- and the
         fp16 copies are dropped as soon as the next layer has consumed them."""
         _lib.require_device()
+        # validate BEFORE the first launch: a kernel handed host pointers faults asynchronously and poisons the context
+        for v in views:
+            if not (isinstance(v, torch.Tensor) and v.is_cuda and v.dtype == torch.float32 and v.is_contiguous()):
+                raise RuntimeError('mmlf_b200: view stacks must be contiguous float32 CUDA tensors (feed_forward.py:226-232 '
+                                   'uses .view); there is no CPU path')
+        p0 = next(iter(self._params().values()))
+        if p0.device != views[0].device:
+            raise RuntimeError(f'mmlf_b200: the model lives on {p0.device} but the inputs on {views[0].device}; '
+                               'move the module with .cuda() / .to(device) first (there is no CPU path)')
         if self.split:
             if save or training:
                 raise RuntimeError("precision='split' is an inference mode (model.eval(), torch.no_grad())")
@@ -307,7 +351,10 @@ class Engine:
 
         # per-forward scratch for the BatchNorm layers, allocated once (one launch each instead of five per block)
         n_bn = len(self.stream_defs) * self.in_blocks + len(self.out_specs)
-        self._fwd_sums = torch.zeros((n_bn, 2 * 320), dtype=torch.float64, device=self.dev) if bn_train else None
+        self._fwd_sums = None
+        if bn_train:
+            self._fwd_sums = self._scratch(geo)['fwd64']
+            _zero(self._fwd_sums)
         self._fwd_consts = torch.empty((n_bn, 4, 320), dtype=torch.float32, device=self.dev) if bn_train else None
         self._fwd_bn_idx = 0
         feats = self._slots(geo, self.feat_ld)
@@ -528,21 +575,56 @@ class Engine:
         return scale, shift, mean, invstd
 
     # ------------------------------------------------------------------ backward
-    def backward(self, tape, g_out):
-        """g_out: (B, OC, H, W) fp32.  Returns {param name: fp32 gradient} for every parameter."""
+    def backward(self, tape, g_out, flat=None):
+        """g_out: (B, OC, H, W) fp32.  Every parameter gradient is written into one flat float32 buffer laid out like
+        :meth:`grad_layout` -- ``flat`` if given (the optimizer's gradient buffer: no copies, nothing returned through
+        autograd), else a buffer owned by the engine.  Returns {param name: view into that buffer}.
+
+        No framework kernel runs here: accumulator scratch is cleared by one memset, weight gradients are reduced
+        straight into their slice, BatchNorm gamma / beta gradients are written (or accumulated, for the shared in-nets)
+        by the kernel that computes them, and all the short bias-gradient vectors are finished by ONE launch over a
+        device job table at the end (``mmlf_vec_jobs``)."""
         geo = tape['geo']
         st = _stream()
         params = self._params()
-        grads = {}
         dev = self.dev
-        ws_bytes = max(_lib.lib().mmlf_conv2x2_wgrad_workspace(cs.n_pad, cs.cin_pad) for cs in self.all_convs())
-        ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
-        # scratch rows for the per-block reductions, zeroed / allocated once per backward pass
-        n_blk = len(tape['out']) + sum(len(r) for r in tape['streams'].values()) + 2
-        z64 = torch.zeros((3 * n_blk, 2 * 320), dtype=torch.float64, device=dev)
-        z32 = torch.zeros((n_blk, 320), dtype=torch.float32, device=dev)
-        e32 = torch.empty((n_blk, 2 * 320), dtype=torch.float32, device=dev)
+        layout, total = self.grad_layout()
+        if flat is None:
+            # the previous pass's buffer may still be some parameter's .grad (autograd adopted our views): never
+            # overwrite it, hand out a new one instead
+            lo = self._gflat.data_ptr() if self._gflat is not None else 0
+            hi = lo + total * 4
+            if self._gflat is None or self._gflat.device != dev or \
+                    any(p.grad is not None and lo <= p.grad.data_ptr() < hi for p in params.values()):
+                self._gflat = torch.empty(total, dtype=torch.float32, device=dev)
+            flat = self._gflat
+            _zero(flat)
+            written = None
+        else:
+            assert flat.numel() == total and flat.dtype == torch.float32 and flat.is_contiguous()
+            written = set()          # the caller's buffer holds earlier gradients: accumulate from the first write on
+        base = flat.data_ptr()
+
+        def gptr(name):
+            return C.c_void_p(base + 4 * layout[name][0])
+
+        seen = set()
+
+        def first(name):
+            """True when this is the first write to `name` in this pass AND the buffer was cleared for it."""
+            new = name not in seen
+            seen.add(name)
+            return new and written is None
+
+        if self._ws is None or self._ws.device != dev:
+            ws_bytes = max(_lib.lib().mmlf_conv2x2_wgrad_workspace(cs.n_pad, cs.cin_pad) for cs in self.all_convs())
+            self._ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
+        ws = self._ws
+        sc = self._scratch(geo)
+        z64, z32, e32 = sc['z64'], sc['z32'], sc['e32']
+        _zero(sc['acc'])
         pool = {'z64': 0, 'z32': 0, 'e32': 0}
+        jobs = []                                       # (src ptr, src is f64, dst name, n, accumulate)
 
         def take(name, buf, n):
             i = pool[name]
@@ -574,32 +656,37 @@ class Engine:
                 hold0.clear()
 
         def conv_param_grads(cs, dout, ld_dout, actg, ld_act, dbias=None):
-            """dW via the tcgen05 wgrad kernel (both operands in the gradient format); db from ``dbias`` when the
-            kernel that produced ``dout`` already summed its columns, else via a column-sum pass.  Accumulates for
-            modules that are called twice per forward."""
+            """dW via the tcgen05 wgrad kernel (both operands in the gradient format), reduced straight into the
+            parameter's slice of the flat buffer; db from ``dbias`` = (scratch row, is_float64) when the kernel that
+            produced ``dout`` already summed its columns, else via a column-sum pass into a scratch row.  Accumulates
+            for modules that are called twice per forward."""
             wname, bname = cs.name + '.weight', cs.name + '.bias'
-            acc = wname in grads
-            if not acc:
-                grads[wname] = torch.empty_like(params[wname], memory_format=torch.contiguous_format)
-                grads[bname] = torch.zeros(cs.n_pad, dtype=torch.float32, device=dev)
+            acc = 0 if first(wname) else 1
+            first(bname)
+            if dbias is None:
+                row = take('z32', z32, cs.n_pad)
+                dbias = (row, False)
+
+                def colsum(sst):
+                    call('mmlf_colsum16', _ptr(dout), ld_dout, cs.n_pad, geo.n_slots, GRAD, _ptr(row), 1, sst)
+            else:
+                colsum = None
+            jobs.append((dbias[0].data_ptr(), 1 if dbias[1] else 0, bname, cs.cout, acc))
 
             def work():
                 sst = _stream()
-                # the K-split reduction writes (or accumulates into) the canonical (cout, cin, 2, 2) gradient directly
                 call('mmlf_conv2x2_wgrad_canonical', _ptr(dout), ld_dout, cs.n_pad, _ptr(actg), ld_act, cs.cin_pad, geo.B,
                      geo.H, geo.W, cs.type, GRAD, GRAD, _ptr(ws), cs.cout, cs.cin, cs.spatial, cs.groups, cs.group_real,
-                     cs.group_pad, _ptr(grads[wname]), 1 if acc else 0, sst)
-                if dbias is None:
-                    call('mmlf_colsum16', _ptr(dout), ld_dout, cs.n_pad, geo.n_slots, GRAD, _ptr(grads[bname]), 1, sst)
-                else:
-                    grads[bname] += dbias[:cs.n_pad]
+                     cs.group_pad, gptr(wname), acc, sst)
+                if colsum is not None:
+                    colsum(sst)
             if side is None:
                 work()
                 return
             side.wait_stream(main)                         # producers of dout / actg / dbias, allocation of the grads
             with torch.cuda.stream(side):
                 work()
-            held.extend(t for t in (dout, actg, dbias) if t is not None)
+            held.extend(t for t in (dout, actg) if t is not None)
 
         def dgrad(cs, dout, ld_dout, out, ld_out, gate_bits=None, col_sums=None, bn=None):
             """Data gradient: the conv kernel of the other type with rotated, transposed weights."""
@@ -628,10 +715,10 @@ class Engine:
             h2n = self.head2.name
             w2 = params[h2n + '.weight'].detach()
             gmid = self._slots(geo, h1.n_pad, GRAD)
-            grads[h2n + '.weight'] = torch.zeros_like(params[h2n + '.weight'])
-            grads[h2n + '.bias'] = torch.zeros_like(params[h2n + '.bias'])
+            if written is not None or not (first(h2n + '.weight') and first(h2n + '.bias')):
+                pass                                   # head_small_bwd adds into its outputs: both cases are correct
             call('mmlf_head_small_bwd', _ptr(g_out), _ptr(hd['mid']), h1.n_pad, self.oc, _ptr(w2), geo.B, geo.H, geo.W,
-                 _ptr(gmid), h1.n_pad, _ptr(grads[h2n + '.weight']), _ptr(grads[h2n + '.bias']), st)
+                 _ptr(gmid), h1.n_pad, gptr(h2n + '.weight'), gptr(h2n + '.bias'), st)
             conv_param_grads(h1, gmid, h1.n_pad, hd['xg'], hd['ld_x'])
         else:
             h2 = self.head2
@@ -641,7 +728,7 @@ class Engine:
             gmid = self._slots(geo, h1.n_pad, GRAD)
             sums = take('z64', z64, 2 * h1.n_pad)
             dgrad(h2, gz, h2.n_pad, gmid, h1.n_pad, gate_bits=hd['bits'], col_sums=sums)
-            conv_param_grads(h1, gmid, h1.n_pad, hd['xg'], hd['ld_x'], dbias=sums.float())
+            conv_param_grads(h1, gmid, h1.n_pad, hd['xg'], hd['ld_x'], dbias=(sums, True))
         pre, bn = bn_of(tape['out'][-1] if tape['out'] else None, h1.cin_pad)
         dgrad(h1, gmid, h1.n_pad, g_x, h1.cin_pad, col_sums=pre, bn=bn)
         gy, ld_gy = g_x, h1.cin_pad
@@ -663,22 +750,17 @@ class Engine:
                          GRAD, self.act, _ptr(sums), st)
                 else:
                     sums = pre_sums
-                gpad, _ = self._bn_padded(bnp, C_real, Cp, dev)
-                acc = bnp + '.weight' in grads
-                fsums = take('e32', e32, 2 * Cp)
-                dgam = torch.empty(C_real, dtype=torch.float32, device=dev)
-                dbet = torch.empty(C_real, dtype=torch.float32, device=dev)
+                gamma = params[bnp + '.weight'].detach()
+                acc = 0 if first(bnp + '.weight') else 1
+                first(bnp + '.bias')
+                fsums = take('e32', e32, 3 * Cp)
                 db2 = take('z32', z32, Cp)
                 call('mmlf_bn_bwd_apply', _ptr(gy), ld_gy, _ptr(rec['z']), Cp, _ptr(rec['scale']), _ptr(rec['shift']),
-                     _ptr(gpad), _ptr(rec['save_mean']), _ptr(rec['save_invstd']), _ptr(sums), geo.count,
+                     _ptr(gamma), _ptr(rec['save_mean']), _ptr(rec['save_invstd']), _ptr(sums), geo.count,
                      0 if rec.get('bn_eval') else (1 if pre_sums is None else 2), C_real, Cp,
-                     geo.B, geo.H, geo.W, GRAD, self.act, _ptr(dz), Cp, _ptr(dgam), _ptr(dbet), _ptr(fsums), _ptr(db2),
-                     st)
-                if acc:
-                    grads[bnp + '.weight'] += dgam
-                    grads[bnp + '.bias'] += dbet
-                else:
-                    grads[bnp + '.weight'], grads[bnp + '.bias'] = dgam, dbet
+                     geo.B, geo.H, geo.W, GRAD, self.act, _ptr(dz), Cp, gptr(bnp + '.weight'), gptr(bnp + '.bias'), acc,
+                     _ptr(fsums), _ptr(db2), st)
+                db2 = (db2, False)
             else:
                 call('mmlf_relu_bwd', _ptr(gy), ld_gy, _ptr(rec['yg']), rec['ld_y'], Cp, geo.n_slots, GRAD, GRAD,
                      _ptr(dz), Cp, st)
@@ -692,7 +774,7 @@ class Engine:
                 gx = self._slots(geo, c1.cin_pad, GRAD)
                 psums, bn = bn_of(prev_rec, c1.cin_pad)
                 dgrad(c1, da1, c1.n_pad, gx, c1.cin_pad, col_sums=psums, bn=bn)
-            conv_param_grads(c1, da1, c1.n_pad, rec['xg'], rec['ld_x'], dbias=sums1.float())
+            conv_param_grads(c1, da1, c1.n_pad, rec['xg'], rec['ld_x'], dbias=(sums1, True))
             end_block()
             return gx, psums
 
@@ -710,9 +792,11 @@ class Engine:
                 ld_g = recs[j]['c1'].cin_pad
         if side is not None:
             main.wait_stream(side)
-        # bias gradients were accumulated on the padded pitch
-        for cs in self.all_convs():
-            bname = cs.name + '.bias'
-            if bname in grads and grads[bname].numel() != cs.cout:
-                grads[bname] = grads[bname][:cs.cout].contiguous()
-        return grads
+        # ---- all the short vectors in one launch; the device job table is rebuilt only when a pointer moved
+        key = tuple((src, f64, base + 4 * layout[name][0], n, acc) for src, f64, name, n, acc in jobs)
+        if self._vec_jobs is None or self._vec_jobs[0] != key:
+            arr = (VecJob * len(key))(*[VecJob(src, dst, n, f64, acc, 0) for src, f64, dst, n, acc in key])
+            table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+            self._vec_jobs = (key, table)
+        call('mmlf_vec_jobs', _ptr(self._vec_jobs[1]), len(key), st)
+        return {name: flat[off:off + n].view(shape) for name, (off, n, shape) in layout.items()}

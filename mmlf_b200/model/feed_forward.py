@@ -176,8 +176,10 @@ class FeedForward(nn.Module):
     # from Python the GPU waits for the host (measured: 3.5 ms per light field against 2.3 ms of kernel time), so the
     # eval-mode launch sequence is captured once per (input shapes, shifts, parameter version) and replayed.
     def _state_version(self):
-        return tuple(t._version for t in self.parameters()) + tuple(t._version for t in self.buffers()) + \
-            (getattr(self, 'precision', 'fp16'),)
+        # version counters AND addresses: FusedAdam re-homes every p.data into its flat buffer without a version bump, and a
+        # captured graph holds raw pointers (head weights, BatchNorm statistics)
+        ts = list(self.parameters()) + list(self.buffers())
+        return tuple(t._version for t in ts) + tuple(t.data_ptr() for t in ts) + (getattr(self, 'precision', 'fp16'),)
 
     def graphed_eval(self, views, shifts=(None,)):
         """Eval-mode raw network outputs for each entry of `shifts` (None = no Shift; a float = ESE member with the Shift
@@ -199,7 +201,7 @@ class FeedForward(nn.Module):
             from .. import _lib
             graph = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode='thread_local'):
                 outs = [self.engine.forward(static_in, False, save=False, shift_disp=sd)[0] for sd in shifts]
             n_launches = _lib.launch_count - n0
             _lib.launch_count = n0                        # captured, not executed

@@ -36,8 +36,7 @@ def _as_f32(t):
 
 def _finish(loss_sum, sums):
     """value = sum / count, with no division when count == 0 (loss.py:73-77) -- without a host sync."""
-    cnt = sums[0]
-    return (loss_sum[0] / torch.where(cnt == 0, torch.ones_like(cnt), cnt)).to(torch.float32)
+    return ops.loss_finish(loss_sum, sums)
 
 
 class _RegressionLoss(torch.autograd.Function):

@@ -197,38 +197,95 @@ def adam_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor
 
 
 # ----------------------------------------------------------------------------------------- losses (raw, no autograd)
+def zero_(t):
+    """Clear a contiguous tensor with cudaMemsetAsync on the current stream (no framework fill kernel)."""
+    assert t.is_cuda and t.is_contiguous()
+    call('mmlf_zero', _p(t), t.numel() * t.element_size(), _st())
+    return t
+
+
+def zeros_f64(n, device):
+    """Zeroed float64 accumulator: cudaMemsetAsync through the C-ABI, no framework fill kernel."""
+    t = torch.empty(n, dtype=torch.float64, device=device)
+    call('mmlf_zero', _p(t), n * 8, _st())
+    return t
+
+
+def _batch_strided(t, name):
+    """A (B, H, W) float32 CUDA tensor whose images are dense but may be spaced by any batch stride (a plane of the
+    (B, OC, H, W) network output): returned as is with its stride, otherwise made contiguous."""
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise RuntimeError(f'mmlf_b200: `{name}` must be a CUDA tensor (there is no CPU fallback)')
+    if t.dtype != torch.float32:
+        raise RuntimeError(f'mmlf_b200: `{name}` must be torch.float32, got {t.dtype}')
+    if t.dim() == 3 and t.stride(2) == 1 and t.stride(1) == t.shape[2] and t.stride(0) >= t.shape[1] * t.shape[2]:
+        return t, t.stride(0)
+    t = t.contiguous()
+    return t, t.numel() // t.shape[0]
+
+
 def loss_prepass(mask, mask_padding=None, mpi=None):
     """-> double[8] device tensor of normalisers (see include/mmlf_b200.h)."""
     _lib.require_device()
     mask = _chk(mask, torch.int32, 'mask')
     B = mask.shape[0]
     HW = mask.numel() // B
-    sums = torch.zeros(8, dtype=torch.float64, device=mask.device)
+    sums = zeros_f64(8, mask.device)
     K = mpi.shape[1] if mpi is not None else 0
     call('mmlf_loss_prepass', _p(mask), _p(mask_padding), _p(mpi), K, B, HW, _p(sums), _st())
     return sums
 
 
 def loss_regression(kind, mean, logvar, target, mask, mask_padding, sums, param=0.0, want_grad=True):
-    mean = _chk(mean.contiguous(), torch.float32, 'mean')
+    """mean / logvar may be planes of the (B, OC, H, W) network output (``output[:, 0]``): they are read in place through
+    their batch stride.  Gradients come back dense (B, H, W)."""
+    shape = tuple(mean.shape)
+    mean, stride = _batch_strided(mean.reshape(mean.shape[0], -1, mean.shape[-1]) if mean.dim() != 3 else mean, 'mean')
     if logvar is not None:
-        logvar = _chk(logvar.contiguous(), torch.float32, 'logvar')
+        logvar, s2 = _batch_strided(logvar.reshape(mean.shape) if logvar.dim() != 3 else logvar, 'logvar')
+        if s2 != stride:
+            mean, logvar = mean.contiguous(), logvar.contiguous()
+            stride = mean.numel() // mean.shape[0]
     target = _chk(target, torch.float32, 'target')
     B = mean.shape[0]
     HW = mean.numel() // B
     K = target.shape[1] if kind in (1, 3) else 0
-    loss_sum = torch.zeros(1, dtype=torch.float64, device=mean.device)
-    g_mean = torch.empty_like(mean) if want_grad and kind in (0, 1, 2, 3) else None
-    g_logvar = torch.empty_like(mean) if want_grad and kind in (2, 3) else None
-    call('mmlf_loss_regression', kind, _p(mean), _p(logvar), _p(target), K, _p(mask), _p(mask_padding), _p(sums),
-         float(param), B, HW, _p(loss_sum), _p(g_mean), _p(g_logvar), _st())
+    loss_sum = zeros_f64(1, mean.device)
+    dense = stride == HW
+    g_mean = torch.empty(shape, dtype=torch.float32, device=mean.device) if want_grad and kind in (0, 1, 2, 3) else None
+    g_logvar = torch.empty(shape, dtype=torch.float32, device=mean.device) if want_grad and kind in (2, 3) else None
+    if dense or not want_grad:
+        call('mmlf_loss_regression', kind, _p(mean), _p(logvar), _p(target), K, _p(mask), _p(mask_padding), _p(sums),
+             float(param), B, HW, _p(loss_sum), _p(g_mean), _p(g_logvar), stride, _st())
+    else:
+        # strided predictions, dense gradients: the kernel has ONE stride for both, so write the gradients through a
+        # tensor with the predictions' stride and hand out its planes
+        gbuf = torch.empty((B, stride), dtype=torch.float32, device=mean.device)
+        gm = gbuf[:, :HW]
+        gl = gbuf[:, HW:2 * HW] if (g_logvar is not None and stride >= 2 * HW) else None
+        if g_logvar is not None and gl is None:
+            mean, logvar = mean.contiguous(), logvar.contiguous()
+            call('mmlf_loss_regression', kind, _p(mean), _p(logvar), _p(target), K, _p(mask), _p(mask_padding), _p(sums),
+                 float(param), B, HW, _p(loss_sum), _p(g_mean), _p(g_logvar), HW, _st())
+        else:
+            call('mmlf_loss_regression', kind, _p(mean), _p(logvar), _p(target), K, _p(mask), _p(mask_padding), _p(sums),
+                 float(param), B, HW, _p(loss_sum), _p(gm), _p(gl), stride, _st())
+            g_mean = gm.view((B,) + shape[1:])
+            g_logvar = gl.view((B,) + shape[1:]) if gl is not None else None
     return loss_sum, g_mean, g_logvar
+
+
+def loss_finish(loss_sum, sums):
+    """value = loss_sum / count with no division when the mask is empty (loss.py:73-77), on the device."""
+    out = torch.empty(1, dtype=torch.float32, device=loss_sum.device)
+    call('mmlf_loss_finish', _p(loss_sum), _p(sums), _p(out), _st())
+    return out[0]
 
 
 def loss_cross_entropy(scores, target, gt, bins_t, half_step, mask, sums, want_grad=True):
     scores = _chk(scores, torch.float32, 'scores')
     B, S, H, W = scores.shape
-    loss_sum = torch.zeros(1, dtype=torch.float64, device=scores.device)
+    loss_sum = zeros_f64(1, scores.device)
     g = torch.empty_like(scores) if want_grad else None
     call('mmlf_loss_cross_entropy', _p(scores), _p(target), _p(gt), _p(bins_t), float(half_step), S, _p(mask),
          _p(sums), B, H * W, _p(loss_sum), _p(g), _st())

@@ -4,7 +4,9 @@ loop (warm start, cooling, periodic validation, log.csv, checkpoint.pt through M
 Differences, all on the B200 side of the boundary:
   * one process per GPU under torchrun (NCCL all-reduce of one flat gradient bucket + the loss normalisers) replaces
     the single-process ``torch.nn.DataParallel`` of train/cli.py:159;
-  * ``torch.optim.Adam`` is replaced by the fused flat-buffer Adam (same update rule, same state_dict format);
+  * ``torch.optim.Adam`` is replaced by the fused flat-buffer Adam (same update rule, same state_dict format), and the
+    body of the loop (train/cli.py:243-258: forward, loss, backward, optimizer step) is ``mmlf_b200.train.step.TrainStep``:
+    one captured CUDA graph per batch shape, replayed every iteration;
   * ``--train_trainset`` / ``--train_valset`` are HCI4D directories exactly as upstream (train/cli.py:95-104).  The scenes
     are decoded once, cached in HBM, and the transform chain of train/cli.py:72-92 (static ``Shift``, then the random
     augmentations or, with ``--train_no_data_augment``, the plain crop) runs as the fused GPU gather of
@@ -29,9 +31,11 @@ from .. import parallel
 from ..data import synthetic
 from ..model import loss
 from ..model.ensamble import Ensamble
+from ..utils.dl import mpi_to_weights
 from ..model.feed_forward import FeedForward
 from ..optim import FusedAdam
-from ..utils.dl import ModelSaver, mpi_to_weights, reg_to_class
+from ..utils.dl import ModelSaver
+from .step import TrainStep
 
 
 # Option table of the reference CLI (train/cli.py:17-59): same names, defaults and types, applied programmatically;
@@ -137,7 +141,6 @@ def main(output_dir, max_iterations, gpu_augment, synthetic_data, **kwargs):
         loss_fn, loss_uncert_fn = loss.MultiMaskedL1Loss(), loss.ImprovedMultiUncertaintyL1Loss()
     else:
         loss_fn, loss_uncert_fn = loss.MaskedL1Loss(), loss.ImprovedUncertaintyL1Loss()
-    loss_discrete_fn = loss.MaskedCrossEntropy()
     mse_fn, bad_pix_fn = loss.MaskedMSELoss(), loss.MaskedBadPix()
 
     augmenter = None
@@ -180,6 +183,14 @@ def main(output_dir, max_iterations, gpu_augment, synthetic_data, **kwargs):
     parallel.broadcast_module_(model)
     optimizer.broadcast_state_()
     val_model = Ensamble(model, **kwargs) if kwargs['val_ensamble'] else model
+    if kwargs['model_uncert']:
+        step_loss = 'multi_upr' if kwargs['train_loss_multimodal'] else 'upr'
+    elif kwargs['model_discrete']:
+        step_loss = 'ce'
+    else:
+        step_loss = 'multi_l1' if kwargs['train_loss_multimodal'] else 'l1'
+    train_step = TrainStep(model, optimizer, step_loss,
+                           ce_from_gt=kwargs['model_discrete'] and not kwargs['train_loss_multimodal'])
 
     log = None
     header = f'{"iter":>7}, loss_train,   loss_val,        mse, badpix_007, time_elapsed'
@@ -193,6 +204,7 @@ def main(output_dir, max_iterations, gpu_augment, synthetic_data, **kwargs):
     dims = (2 if kwargs['model_cross'] else 4) * kwargs['model_views'] * 3
     time_start = 0
     epoch = 0
+    margin_masks = {}
 
     def val_batches():
         """The validation scenes one by one with a batch dimension of 1 (DataLoader(valset, batch_size=1), train/cli.py:101)."""
@@ -209,18 +221,16 @@ def main(output_dir, max_iterations, gpu_augment, synthetic_data, **kwargs):
             if kwargs['train_loss_strongest']:
                 inds = torch.max(mpi[:, :, 3, :, :], dim=1)[1].unsqueeze(1)
                 gt = torch.gather(mpi[:, :, 4, :, :], dim=1, index=inds).squeeze()
-            mask = mask.int() * loss.create_mask_margin(mask.shape, 11).to(mask.device)   # train/cli.py:194
+            mkey = (tuple(mask.shape), str(mask.device))
+            if mkey not in margin_masks:
+                margin_masks[mkey] = loss.create_mask_margin(mask.shape, 11).to(mask.device)
+            mask = mask.int() * margin_masks[mkey]                               # train/cli.py:194
             h_views, v_views, i_views, d_views = (t.to(dev, non_blocking=True) for t in (h_views, v_views, i_views, d_views))
             gt, mpi, mask = gt.to(dev), mpi.to(dev).float(), mask.to(dev)
             if static_shift is not None:        # Shift(train_shift) of train/cli.py:89-90 on the DataLoader path, on the GPU
                 hci4d.Shift(static_shift)((h_views, v_views, i_views, d_views))
                 gt = gt - static_shift
                 mpi[:, :, 4] -= static_shift
-            gt_classes = None
-            if kwargs['model_discrete']:                                      # targets are built on the GPU
-                gt_classes = (mpi_to_weights(mpi, kwargs['val_disp_min'], kwargs['val_disp_max'], dims)
-                              if kwargs['train_loss_multimodal'] else
-                              reg_to_class(gt, kwargs['val_disp_min'], kwargs['val_disp_max'], dims))
             mask_padding = None
             if kwargs['train_loss_padding'] is not None:
                 if kwargs['train_loss_multimodal']:
@@ -240,17 +250,14 @@ def main(output_dir, max_iterations, gpu_augment, synthetic_data, **kwargs):
                 lr = kwargs['train_lr'] / (10.0 ** (i / kwargs['train_cooling'] - 1.0))
                 for g in optimizer.param_groups:
                     g['lr'] = lr
-            optimizer.zero_grad()
-            output = model(h_views, v_views, i_views, d_views)
-            if kwargs['model_uncert']:
-                loss_train = loss_uncert_fn(output, gt, mask, mask_padding)
-            elif kwargs['model_discrete']:
-                loss_train = loss_discrete_fn(output, gt_classes, mask)
+            # forward + loss + backward + gradient all-reduce + Adam: one graph replay (train/cli.py:243-258).  For
+            # --model_discrete the class targets (utils/dl.py:109-157) are built inside the loss kernel from gt, or on the
+            # GPU from the MPI planes for --train_loss_multimodal.
+            if kwargs['model_discrete'] and kwargs['train_loss_multimodal']:
+                target = mpi_to_weights(mpi, kwargs['val_disp_min'], kwargs['val_disp_max'], dims)
             else:
-                loss_train = loss_fn(output, gt, mask)
-            loss_train.backward()
-            parallel.all_reduce_sum_(optimizer.flat_grad)                     # replaces DataParallel's reduce-add
-            optimizer.step()
+                target = gt
+            loss_train = train_step(h_views, v_views, i_views, d_views, target, mask, mask_padding)
             time_elap = time.time() - time_start
 
             if i % kwargs['val_interval'] == 0:

@@ -277,7 +277,8 @@ def gen_evalmode():
 
 
 # ---------------------------------------------------------------------------- trained-like full-width fixtures
-TRAINED = dict(B=8, ps=32, lr=1e-3, trunk_steps=30, head_steps=60, traj_steps=20, n_batches=4, seed0=200, grad_stride=13)
+TRAINED = dict(B=8, ps=32, lr=1e-3, traj_lr=2e-4, trunk_steps=30, head_steps=60, traj_steps=20, n_batches=4, seed0=200,
+               grad_stride=13)
 
 
 def _trained_batch(k):
@@ -310,26 +311,30 @@ def gen_trained():
     torch.manual_seed(0)
     model = FeedForward(**kw)
     init = {k: v.detach().numpy().copy() for k, v in model.state_dict().items()}
-    opt = torch.optim.Adam(model.parameters(), lr=c['lr'])
-    model.train()
-    for s in range(c['trunk_steps']):
-        args, gt, mask = batches[s % c['n_batches']]
-        opt.zero_grad()
-        lossv = _variant_loss(model, 'base', model(*args), gt, mask)
-        lossv.backward()
-        opt.step()
-        print('trunk step', s, lossv.item())
-    trunk = {}
-    for k, v in model.state_dict().items():
-        if k.startswith('out_net.7.'):
-            continue
-        a = v.detach().numpy()
-        if a.ndim == 4:                                   # conv weight: int8 delta from the seeded init
-            q, scale = fx.quantise_delta(a, init[k])
-            trunk['q/' + k], trunk['s/' + k] = q, scale
-        else:
-            trunk['f/' + k] = a.copy()
-    save('net_trained_trunk.npz', **trunk)
+    trunk_file = os.path.join(OUT, 'net_trained_trunk.npz')
+    if os.environ.get('KEEP_TRUNK') == '1' and os.path.exists(trunk_file):
+        trunk = dict(np.load(trunk_file))                 # regenerate the per-variant files on the committed trunk
+    else:
+        opt = torch.optim.Adam(model.parameters(), lr=c['lr'])
+        model.train()
+        for s in range(c['trunk_steps']):
+            args, gt, mask = batches[s % c['n_batches']]
+            opt.zero_grad()
+            lossv = _variant_loss(model, 'base', model(*args), gt, mask)
+            lossv.backward()
+            opt.step()
+            print('trunk step', s, lossv.item())
+        trunk = {}
+        for k, v in model.state_dict().items():
+            if k.startswith('out_net.7.'):
+                continue
+            a = v.detach().numpy()
+            if a.ndim == 4:                                   # conv weight: int8 delta from the seeded init
+                q, scale = fx.quantise_delta(a, init[k])
+                trunk['q/' + k], trunk['s/' + k] = q, scale
+            else:
+                trunk['f/' + k] = a.copy()
+        save('net_trained_trunk.npz', **trunk)
     trunk_state = fx.trained_trunk_state(trunk, init)
 
     for variant in ('base', 'upr', 'dpp'):
@@ -392,7 +397,7 @@ def gen_trained():
                 out['after/' + k] = vv.numpy().copy()
         # ---- 20-step Adam trajectory from the start state (train/cli.py:243-258: forward, loss, backward, step)
         model.load_state_dict(start_state)
-        opt = torch.optim.Adam(model.parameters(), lr=c['lr'])
+        opt = torch.optim.Adam(model.parameters(), lr=c['traj_lr'])
         traj = []
         for s in range(c['traj_steps']):
             args, gt, mask = batches[s % c['n_batches']]
@@ -402,12 +407,11 @@ def gen_trained():
             opt.step()
             traj.append(lossv.item())
         out['traj/loss'] = np.array(traj, np.float64)
-        model.eval()
-        with torch.no_grad():
+        with torch.no_grad():                     # training mode (batch statistics): see the test for why not eval()
             o = model(*[a.clone() for a in batches[0][0]])
         key = 'scores' if variant == 'dpp' else 'mean'
         a = o[key].numpy()
-        out['traj/final_eval_' + key] = (a[[0, 5]] if a.ndim == 4 else a).copy()
+        out['traj/final_train_' + key] = (a[[0, 5]] if a.ndim == 4 else a).copy()
         print(variant, 'trajectory', traj[0], '->', traj[-1])
         save(f'net_trained_{variant}.npz', **out)
 

@@ -191,7 +191,7 @@ def trained_trunk_state(trunk, init):
     return state
 
 
-TRAINED = dict(B=8, ps=32, lr=1e-3, traj_steps=20, n_batches=4, seed0=200, grad_stride=13)
+TRAINED = dict(B=8, ps=32, lr=1e-3, traj_lr=2e-4, traj_steps=20, n_batches=4, seed0=200, grad_stride=13)
 
 
 def trained_batch(k):

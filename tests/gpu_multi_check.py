@@ -49,6 +49,34 @@ def main():
         err = (band[k] - whole[k]).abs().max().item()
         print(f'rank {rank} bands {k}: max_abs_diff={err:.3e}')
         ok &= err <= 1e-6
+    # ---- data-parallel training: ranks built from DIFFERENT seeds become one replica after the rank-0 broadcast and stay
+    # bit-identical over captured TrainStep steps on different data (NCCL all-reduce of normalisers + gradients in-graph)
+    from mmlf_b200.optim import FusedAdam
+    from mmlf_b200.train.step import TrainStep
+    torch.manual_seed(100 + rank)
+    tm = FeedForward(**dict(KW, model_chs=16)).to(dev).train()
+    opt = FusedAdam(tm.parameters(), lr=1e-3)
+    parallel.broadcast_module_(tm)
+    opt.broadcast_state_()
+    step = TrainStep(tm, opt, 'upr')
+    g2 = torch.Generator(device=dev).manual_seed(77 + rank)        # every rank trains on its own shard
+    losses = []
+    for it in range(4):
+        tv = [torch.rand((4, 9, 3, 32, 32), device=dev, generator=g2) for _ in range(4)]
+        tgt = torch.rand((4, 32, 32), device=dev, generator=g2) * 2 - 1
+        tmask = (torch.rand((4, 32, 32), device=dev, generator=g2) > 0.2).to(torch.int32)
+        losses.append(step(*tv, tgt, tmask).item())
+    flat = opt.flat_buffers[0]
+    parts = [torch.empty_like(flat) for _ in range(world)]
+    torch.distributed.all_gather(parts, flat)
+    same = all(torch.equal(parts[0], p) for p in parts)
+    lt = torch.tensor(losses, device=dev, dtype=torch.float64)
+    lparts = [torch.empty_like(lt) for _ in range(world)]
+    torch.distributed.all_gather(lparts, lt)
+    lsame = all(torch.equal(lparts[0], p) for p in lparts)          # the loss is the GLOBAL masked mean on every rank
+    print(f'rank {rank} train replicas: params identical={same} losses identical={lsame} replays={step.replays} '
+          f'loss {losses[0]:.5f} -> {losses[-1]:.5f}')
+    ok &= same and lsame and step.replays == 3
     print(f'rank {rank}: {"OK" if ok else "MISMATCH"}')
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f'{n} declared in include/mmlf_b200.h but not exported'
     # and the ctypes prototype table covers the header
     assert set(names) == set(_lib.EXPORTS)
-    assert _lib.lib().mmlf_abi_version() == _lib.ABI_VERSION == 4
+    assert _lib.lib().mmlf_abi_version() == _lib.ABI_VERSION == 5
 
 
 def test_shift_taps_host_helper_matches_oracle():

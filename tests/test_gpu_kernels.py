@@ -611,15 +611,22 @@ def test_bn_train_roundtrip():
     bs = torch.zeros(2 * Cp, dtype=torch.float64, device='cuda')
     u.call('mmlf_bn_bwd_reduce', u.ptr(gys), Cp, u.ptr(zs), Cp, u.ptr(scale), u.ptr(shift), u.ptr(smean), u.ptr(sinv),
            Cp, B, H, W, G, A, u.ptr(bs), u.stream())
-    gpad = torch.zeros(Cp, device='cuda')
-    gpad[:Cr] = d['gamma']
     dz = torch.full((B * Hp * Wp, Cp), float('nan'), dtype=torch.bfloat16, device='cuda')
     dgam, dbet = torch.empty(Cr, device='cuda'), torch.empty(Cr, device='cuda')
     dzsum = torch.zeros(Cp, device='cuda')
-    u.call('mmlf_bn_bwd_apply', u.ptr(gys), Cp, u.ptr(zs), Cp, u.ptr(scale), u.ptr(shift), u.ptr(gpad), u.ptr(smean),
-           u.ptr(sinv), u.ptr(bs), n, 1, Cr, Cp, B, H, W, G, A, u.ptr(dz), Cp, u.ptr(dgam), u.ptr(dbet),
-           u.ptr(torch.empty(2 * Cp, device='cuda')), u.ptr(dzsum), u.stream())
+    fs = torch.full((3 * Cp,), float('nan'), device='cuda')
+    u.call('mmlf_bn_bwd_apply', u.ptr(gys), Cp, u.ptr(zs), Cp, u.ptr(scale), u.ptr(shift), u.ptr(d['gamma']), u.ptr(smean),
+           u.ptr(sinv), u.ptr(bs), n, 1, Cr, Cp, B, H, W, G, A, u.ptr(dz), Cp, u.ptr(dgam), u.ptr(dbet), 0,
+           u.ptr(fs), u.ptr(dzsum), u.stream())
+    # accumulate = 1 (second call of a shared in-net): dgamma / dbeta add to what is there, dz is the same
+    dz_b = torch.full_like(dz, float('nan'))
+    dgam2, dbet2 = dgam.clone(), dbet.clone()
+    u.call('mmlf_bn_bwd_apply', u.ptr(gys), Cp, u.ptr(zs), Cp, u.ptr(scale), u.ptr(shift), u.ptr(d['gamma']), u.ptr(smean),
+           u.ptr(sinv), u.ptr(bs), n, 1, Cr, Cp, B, H, W, G, A, u.ptr(dz_b), Cp, u.ptr(dgam2), u.ptr(dbet2), 1,
+           u.ptr(fs), u.ptr(torch.zeros(Cp, device='cuda')), u.stream())
     torch.cuda.synchronize()
+    assert torch.equal(dz, dz_b) and torch.equal(dgam2, 2 * dgam) and torch.equal(dbet2, 2 * dbet)
+    assert torch.equal(fs[2 * Cp:2 * Cp + Cr], d['gamma']) and not fs[2 * Cp + Cr:].any()      # gamma on the padded pitch
     np.testing.assert_allclose(dzsum.cpu().numpy(), dz.double().sum(0).cpu().numpy(), rtol=1e-4, atol=1e-3)
     yq = full[:, 1:, 1:, :Cr]
     g = gy * (yq > 0)

@@ -118,8 +118,13 @@ def _install_loss_standins():
         g_logvar = (gl * m * scale).float() if (want_grad and gl is not None) else None
         return loss_sum, g_mean, g_logvar
 
+    def loss_finish(loss_sum, sums):
+        cnt = sums[0]
+        return (loss_sum[0] / torch.where(cnt == 0, torch.ones_like(cnt), cnt)).to(torch.float32)
+
     ops.loss_prepass = loss_prepass
     ops.loss_regression = loss_regression
+    ops.loss_finish = loss_finish
 
 
 def _loss_inputs():
@@ -281,3 +286,43 @@ def test_band_rows_cover_image(H, world, radius):
         assert a == max(0, lo - radius) and b == min(H, hi + radius)
         rows += list(range(lo, hi))
     assert rows == list(range(H))
+
+
+# ------------------------------------------------------------------------------------------- replica consistency
+def _case_broadcast(rank, world):
+    """every rank builds its model from its own RNG; parallel.broadcast_module_ and
+    FusedAdam.broadcast_state_ make them one replica (parameters, buffers, Adam moments, step count)."""
+    import _fixtures as fx
+    from mmlf_b200 import parallel
+    from mmlf_b200.model.feed_forward import FeedForward
+    from mmlf_b200.optim import FusedAdam
+    torch.manual_seed(100 + rank)                                  # different weights per rank
+    m = FeedForward(**fx.model_kwargs('upr', False, chs=8))
+    with torch.no_grad():
+        for b in m.buffers():
+            if b.dtype.is_floating_point:
+                b.add_(float(rank))
+    opt = FusedAdam(m.parameters(), lr=1e-3)
+    opt._flatten()
+    opt._flat[3].fill_(float(rank + 1))                            # exp_avg
+    opt.set_host_step(7 * (rank + 1))
+    before = torch.cat([p.detach().reshape(-1) for p in m.parameters()]).clone()
+    parallel.broadcast_module_(m)
+    opt.broadcast_state_()
+    flat = torch.cat([p.detach().reshape(-1) for p in m.parameters()] +
+                     [b.detach().reshape(-1).double().float() for b in m.buffers()] + [opt._flat[3], opt._flat[4]])
+    parts = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(parts, flat)
+    same = all(torch.equal(parts[0], p) for p in parts)
+    changed = bool((before != torch.cat([p.detach().reshape(-1) for p in m.parameters()])).any())
+    return dict(same=same, changed=changed, step=opt.host_step(), views_ok=all(
+        p.data_ptr() == opt._flat[1].data_ptr() + 4 * off for p, off in zip(
+            m.parameters(), np.cumsum([0] + [q.numel() for q in m.parameters()][:-1]).tolist())))
+
+
+def test_ranks_start_from_one_replica():
+    res = _run('_case_broadcast')
+    assert res[0]['same'] and res[1]['same']
+    assert not res[0]['changed'] and res[1]['changed']              # rank 1 took rank 0's weights
+    assert res[0]['step'] == res[1]['step'] == 7
+    assert res[0]['views_ok'] and res[1]['views_ok']                # parameters are still views of the flat buffer

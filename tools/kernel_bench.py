@@ -204,7 +204,7 @@ def main():
         invstd = torch.ones(Cp, device=DEV)
         gamma = torch.ones(Cp, device=DEV)
         sums = torch.zeros(2 * Cp, dtype=torch.float64, device=DEV)
-        fsums = torch.empty(2 * Cp, device=DEV)
+        fsums = torch.empty(3 * Cp, device=DEV)
         dgam, dbet, db2 = torch.empty(C_real, device=DEV), torch.empty(C_real, device=DEV), torch.zeros(Cp, device=DEV)
         bn.hbm_row('slot_map_kernel<bn_apply_relu>', f'C={C_real} train, fp16 z -> fp16 y + bf16 y', px * C_real * 6.0,
                    lambda: call('mmlf_bn_apply_relu', P(z), Cp, P(scale), P(shift), Cp, Bt, ps, ps, FP16, P(y), Cp, P(y2), Cp,
@@ -214,7 +214,7 @@ def main():
                                 ps, BF16, FP16, P(sums), ST()), 'read dy, z')
         bn.hbm_row('slot_map_kernel<bn_bwd_apply>', f'C={C_real} train', px * C_real * 6.0,
                    lambda: call('mmlf_bn_bwd_apply', P(dy), Cp, P(z), Cp, P(scale), P(shift), P(gamma), P(mean), P(invstd),
-                                P(sums), px, 1, C_real, Cp, Bt, ps, ps, BF16, FP16, P(dz), Cp, P(dgam), P(dbet), P(fsums),
+                                P(sums), px, 1, C_real, Cp, Bt, ps, ps, BF16, FP16, P(dz), Cp, P(dgam), P(dbet), 0, P(fsums),
                                 P(db2), ST()), 'read dy, z, write dz (+ column sums of dz)')
         del z, dy, y, y2, dz
         torch.cuda.empty_cache()
