@@ -338,13 +338,16 @@ int mmlf_zero(void* ptr, int64_t bytes, void* stream);
 
 /* One launch for all the short per-parameter vector updates at the end of a backward pass (conv bias gradients from the
  * float64 / padded-pitch column sums of the kernels that produced the gradients, accumulation for shared modules):
- *     dst[i] = (accumulate ? dst[i] : 0) + (float) src[i],  i < n.
- * jobs: DEVICE array of n_jobs descriptors (built once by the host; every pointer in it is a device pointer). */
+ *     dst[i] = (accumulate ? dst[i] : 0) + (float) src[i] [+ (float) src2[i]],  i < n.
+ * jobs: DEVICE array of n_jobs descriptors (built once by the host; every pointer in it is a device pointer).  Two jobs
+ * of one launch must not share a dst (they run concurrently): a parameter with two contributions -- the shared in-nets
+ * are called twice per forward -- names both in ONE job. */
 typedef struct mmlf_vec_job {
   const void* src;    /* f32 or f64 */
+  const void* src2;   /* optional second contribution, or NULL */
   float* dst;
   int32_t n;
-  int32_t src_f64;    /* 1: src is double */
+  int32_t src_f64;    /* bit 0: src is double, bit 1: src2 is double */
   int32_t accumulate;
   int32_t pad_;
 } mmlf_vec_job;
@@ -353,6 +356,58 @@ int mmlf_vec_jobs(const mmlf_vec_job* jobs, int n_jobs, void* stream);
 /* loss value of the masked losses without a host sync and without framework glue: out[0] = (float)(loss_sum[0] /
  * (sums[0] == 0 ? 1 : sums[0]))  (loss.py:73-77: no division when the mask is empty). */
 int mmlf_loss_finish(const double* loss_sum, const double* sums, float* out, void* stream);
+
+/* ------------------------------------------------------------------ generic float32 layers
+ * Odd --model_ksize (feed_forward.py:86-92) and the --model_unet out-net (unet.py:8-132) run on CUDA-core float32
+ * kernels over dense channel-last tensors: B x H x W pixels, C channels, rows of pitch ld >= C ([B*H*W][ld]). */
+
+/* nn.Conv2d / nn.ConvTranspose2d weight -> GEMM operand [K][N] (float32):
+ *   mode 0: conv forward, w (cout, cin, k, k) -> [(dy*k + dx)*cin + ci][co]
+ *   mode 1: conv data gradient -> [((k-1-dy)*k + (k-1-dx))*cout + co][ci]
+ *   mode 2: ConvTranspose2d(cin, cout, 2, stride 2) forward, w (cin, cout, 2, 2) -> [ci][(dy*2 + dx)*cout + co]
+ *   mode 3: its data gradient -> [(dy*2 + dx)*cout + co][ci]
+ * spatial (modes 0 / 1): the stream plumbing of feed_forward.py:236-256 folded into the taps -- 0 none, 1 transposed
+ * (h stream), 2 transposed + flipped (i stream): effective tap (dy, dx) reads w[..][dx][k-1-dy]. */
+int mmlf_g_pack_weight(const float* w, int cout, int cin, int k, int spatial, int mode, float* out, void* stream);
+/* y[b][oy][ox][n] = act(bias[n] + sum_{dy,dx,ci} x[b][oy+dy-pad][ox+dx-pad][ci] * wg[(dy*k+dx)*cin+ci][n]), zero padding,
+ * output (H + 2 pad - k + 1) x (W + 2 pad - k + 1); bias may be NULL; relu != 0 clamps at zero. */
+int mmlf_g_conv(const float* x, int ld_x, const float* wg, const float* bias, int B, int H, int W, int cin, int cout,
+                int k, int pad, int relu, float* y, int ld_y, void* stream);
+/* Weight gradient, ADDED into the canonical parameter gradient dw (zeroed by the caller once per backward pass):
+ * (cout, cin, k, k) with the `spatial` tap mapping undone, or -- transposed != 0, k = 1, cout = 4 * cout_t, dy in
+ * space-to-depth form -- the (cin, cout_t, 2, 2) gradient of a ConvTranspose2d. */
+int mmlf_g_conv_wgrad(const float* x, int ld_x, const float* dy, int ld_dy, int B, int H, int W, int cin, int cout, int k,
+                      int pad, int spatial, int transposed, float* dw, void* stream);
+/* out[c] += sum_rows x[row][c] (bias gradients). */
+int mmlf_g_colsum(const float* x, int ld, int C, int64_t n_rows, float* out, void* stream);
+/* BatchNorm statistics: sums[c] += sum x, sums[C + c] += sum x^2 (double[2 * C], zeroed by the caller); finish with
+ * mmlf_bn_finalize(sums, C, C, ...). */
+int mmlf_g_bn_stats(const float* x, int ld, int C, int64_t n_rows, double* sums, void* stream);
+/* y = x * scale[c] + shift[c], optionally rectified (BatchNorm apply; scale / shift from mmlf_bn_finalize / _fold_eval). */
+int mmlf_g_affine(const float* x, int ld_x, const float* scale, const float* shift, int C, int64_t n_rows, int relu,
+                  float* y, int ld_y, void* stream);
+/* BatchNorm backward.  x: the layer's input, gate (optional): the layer's OUTPUT after a ReLU (g = dy * (gate > 0)).
+ * sums: double[2 * C] scratch, zeroed by the caller.  dx = gamma * invstd * (g - mean(g) - xhat * mean(g * xhat)) in
+ * training mode, g * gamma * invstd for an eval-mode BatchNorm (train = 0).  dgamma / dbeta are ADDED to. */
+int mmlf_g_bn_bwd(const float* dy, int ld_dy, const float* x, int ld_x, const float* gate, int ld_gate,
+                  const float* gamma, const float* mean, const float* invstd, double* sums, int64_t count, int train,
+                  int C, int64_t n_rows, float* dx, int ld_dx, float* dgamma, float* dbeta, void* stream);
+/* out = dy * (y > 0). */
+int mmlf_g_relu_bwd(const float* dy, int ld_dy, const float* y, int ld_y, int C, int64_t n_rows, float* out, int ld_out,
+                    void* stream);
+/* F.max_pool2d(x, 2) (unet.py:71) on dense (B, H, W, C): y (B, H/2, W/2, C), idx = arg-max position in the window
+ * (first maximum, row-major); the backward pass writes every element of dx (B, H, W, C). */
+int mmlf_g_maxpool2(const float* x, int B, int H, int W, int C, float* y, uint8_t* idx, void* stream);
+int mmlf_g_maxpool2_bwd(const float* dy, const uint8_t* idx, int B, int H, int W, int C, float* dx, void* stream);
+/* dst[b][yd0+y][xd0+x][cd0+c] (+)= src[b][ys0+y][xs0+x][cs0+c] for a h x w x C window (centre crop + concat of
+ * unet.py:118-131 and their gradients). */
+int mmlf_g_copy_window(const float* src, int Hs, int Ws, int ld_s, int cs0, int ys0, int xs0, float* dst, int Hd, int Wd,
+                       int ld_d, int cd0, int yd0, int xd0, int B, int h, int w, int C, int accumulate, void* stream);
+/* Depth-to-space of a transposed convolution evaluated as a 1x1 convolution to 4 * C channels: y4 (B, H, W, 4*C dense,
+ * tap-major) -> out (B, 2H, 2W, C at channel offset c0 of pitch ld); inverse != 0 gathers the other way. */
+int mmlf_g_depth_to_space(float* y4, float* out, int ld, int c0, int B, int H, int W, int C, int inverse, void* stream);
+/* (B, C, H, W) <-> (B, H, W, C at pitch ld): to_nhwc != 0 reads nchw and writes nhwc, else the reverse. */
+int mmlf_g_layout(float* nchw, float* nhwc, int ld, int B, int C, int H, int W, int to_nhwc, void* stream);
 
 /* ------------------------------------------------------------------ validation metrics */
 /* laplace_to_discrete / lmm_to_discrete (validate/cli.py:91-118): means / logvars (K, B, HW) f32 (K = 1: one Laplacian),

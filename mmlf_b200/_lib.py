@@ -82,6 +82,21 @@ _PROTOS = {
     'mmlf_zero': (c_i, [c_p, c_i64, c_p]),
     'mmlf_vec_jobs': (c_i, [c_p, c_i, c_p]),
     'mmlf_loss_finish': (c_i, [c_p, c_p, c_p, c_p]),
+    'mmlf_g_pack_weight': (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
+    'mmlf_g_conv': (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_p]),
+    'mmlf_g_conv_wgrad': (c_i, [c_p, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
+    'mmlf_g_colsum': (c_i, [c_p, c_i, c_i, c_i64, c_p, c_p]),
+    'mmlf_g_bn_stats': (c_i, [c_p, c_i, c_i, c_i64, c_p, c_p]),
+    'mmlf_g_affine': (c_i, [c_p, c_i, c_p, c_p, c_i, c_i64, c_i, c_p, c_i, c_p]),
+    'mmlf_g_bn_bwd': (c_i, [c_p, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_i64, c_i, c_i, c_i64, c_p, c_i, c_p, c_p,
+                            c_p]),
+    'mmlf_g_relu_bwd': (c_i, [c_p, c_i, c_p, c_i, c_i, c_i64, c_p, c_i, c_p]),
+    'mmlf_g_maxpool2': (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
+    'mmlf_g_maxpool2_bwd': (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
+    'mmlf_g_copy_window': (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i,
+                                 c_i, c_p]),
+    'mmlf_g_depth_to_space': (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p]),
+    'mmlf_g_layout': (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p]),
 }
 
 EXPORTS = tuple(_PROTOS)
@@ -109,8 +124,9 @@ def lib():
 
 
 # kernels launched per C-ABI call (for the launch count reported by bench.py)
-_KERNELS_PER_CALL = {'mmlf_zero': 0, 'mmlf_adam_step_dev': 2, 'mmlf_augment_fill': 0, 'mmlf_augment_patches': 2, 'mmlf_pack_views_split': 2, 'mmlf_conv2x2_wgrad': 2, 'mmlf_conv2x2_wgrad_canonical': 2, 'mmlf_bn_bwd_apply': 2, 'mmlf_head_small_bwd': 2, 'mmlf_shift_taps': 0}
+_KERNELS_PER_CALL = {'mmlf_g_bn_bwd': 3, 'mmlf_zero': 0, 'mmlf_adam_step_dev': 2, 'mmlf_augment_fill': 0, 'mmlf_augment_patches': 2, 'mmlf_pack_views_split': 2, 'mmlf_conv2x2_wgrad': 2, 'mmlf_conv2x2_wgrad_canonical': 2, 'mmlf_bn_bwd_apply': 2, 'mmlf_head_small_bwd': 2, 'mmlf_shift_taps': 0}
 launch_count = 0
+_TRACE = os.environ.get('MMLF_TRACE', '0') == '1'      # print every C-ABI call (debugging aid)
 _profile = None          # when set to a list, call() appends (name, start_event, end_event)
 
 
@@ -136,6 +152,9 @@ def call(name, *args):
         _profile.append((name, e0, e1))
     else:
         rc = getattr(l, name)(*args)
+    if _TRACE:
+        import sys
+        print(f'[mmlf] {name} -> {rc}', file=sys.stderr, flush=True)
     if rc != 0:
         raise RuntimeError(f'{name} failed ({rc}): {l.mmlf_last_error().decode()}')
     launch_count += _KERNELS_PER_CALL.get(name, 1)
@@ -152,3 +171,22 @@ def require_device():
     if not _device_ok:
         call('mmlf_check_device')
         _device_ok = True
+
+
+class no_gc_during_capture:
+    """Context manager around a CUDA-graph capture: the cyclic garbage collector must not run inside it.  A collection that
+    happens to free a dead model's CUDAGraph (module <-> engine reference cycles are only freed by the collector) calls
+    cudaGraphExecDestroy while this thread is capturing -- "operation not permitted when stream is capturing" -- and
+    invalidates the capture (seen on B200: the 70-member ESE capture allocates enough Python objects to trigger one)."""
+
+    def __enter__(self):
+        import gc
+        self._was = gc.isenabled()
+        gc.collect()
+        gc.disable()
+
+    def __exit__(self, *exc):
+        import gc
+        if self._was:
+            gc.enable()
+        return False

@@ -80,8 +80,11 @@ int sm_count() {
 __global__ void vec_jobs_kernel(const mmlf_vec_job* __restrict__ jobs) {
   const mmlf_vec_job j = jobs[blockIdx.x];
   for (int i = threadIdx.x; i < j.n; i += blockDim.x) {
-    const float v = j.src_f64 ? static_cast<float>(static_cast<const double*>(j.src)[i])
+    float v = (j.src_f64 & 1) ? static_cast<float>(static_cast<const double*>(j.src)[i])
                               : static_cast<const float*>(j.src)[i];
+    if (j.src2)
+      v += (j.src_f64 & 2) ? static_cast<float>(static_cast<const double*>(j.src2)[i])
+                           : static_cast<const float*>(j.src2)[i];
     j.dst[i] = j.accumulate ? j.dst[i] + v : v;
   }
 }

@@ -40,7 +40,7 @@ class PackJob(C.Structure):
 
 class VecJob(C.Structure):
     """Mirror of ``mmlf_vec_job`` (include/mmlf_b200.h): one short vector update of the end-of-backward launch."""
-    _fields_ = [('src', C.c_void_p), ('dst', C.c_void_p), ('n', C.c_int32), ('src_f64', C.c_int32),
+    _fields_ = [('src', C.c_void_p), ('src2', C.c_void_p), ('dst', C.c_void_p), ('n', C.c_int32), ('src_f64', C.c_int32),
                 ('accumulate', C.c_int32), ('pad_', C.c_int32)]
 
 
@@ -107,15 +107,16 @@ class Engine:
         self.wp = pad16(self.width)                     # 288
         assert self.feat_ld <= 320 and self.wp <= 320, 'model_chs too large for the 320-column TMEM plan'
         self._pack_version = None
-        self._pack_jobs = None
+        self._pack_jobs = {}          # key -> device job table; never dropped: captured graphs hold their addresses
         self._fold_cache = {}
         self._param_cache = None
         self._buffer_cache = None
         self._scratch_cache = {}
         self._gflat = None
         self._glayout = None
-        self._vec_jobs = None
+        self._vec_jobs = {}           # key -> device job table (kept for the same reason)
         self._ws = None
+        self._pinned_tables = set()
         self._side = None
         # BatchNorm-backward statistics out of the data-gradient epilogue: implemented and tested, but opt-in
         # (MMLF_BN_FUSE=1).  Measured on B200: the wide data gradient goes from 0.293 to 0.382 ms (the epilogue becomes the
@@ -210,7 +211,7 @@ class Engine:
         # every packing of the step (forward, split and data-gradient operands, padded biases) is one job of ONE
         # launch; the job table lives on the device and is rebuilt only when a buffer moves
         key = version[len(params):] + (bool(need_dgrad),)
-        if self._pack_jobs is None or self._pack_jobs[0] != key:
+        if key not in self._pack_jobs:
             jobs = []
             for cs in self.all_convs():
                 w = params[cs.name + '.weight'].detach()
@@ -236,8 +237,8 @@ class Engine:
             arr = (PackJob * len(jobs))(*jobs)
             table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
             max_elems = max(j.n_pad * 4 * (3 if j.split else 1) * ((j.cin_pad + 63) // 64) * 64 for j in jobs)
-            self._pack_jobs = (key, table, len(jobs), max_elems)
-        _, table, n_jobs, max_elems = self._pack_jobs
+            self._pack_jobs[key] = (table, len(jobs), max_elems)
+        table, n_jobs, max_elems = self._pack_jobs[key]
         call('mmlf_pack_conv_weights_batch', _ptr(table), n_jobs, max_elems, _stream())
         self._pack_version = (version, bool(need_dgrad))
 
@@ -549,8 +550,9 @@ class Engine:
 
     def _eval_fold(self, bnp, c2, gamma, beta, rmean, rvar):
         """Eval-mode BN folded to per-channel scale / shift; cached until a parameter or running statistic changes."""
-        key = (gamma._version, beta._version, rmean._version, rvar._version, c2.bias_pad._version,
-               gamma.data_ptr(), rmean.data_ptr())
+        cbias = self._params()[c2.name + '.bias']
+        key = (gamma._version, beta._version, rmean._version, rvar._version, cbias._version, gamma.data_ptr(),
+               rmean.data_ptr(), cbias.data_ptr())
         hit = self._fold_cache.get(bnp)
         if hit is not None and hit[0] == key:
             return hit[1], hit[2]
@@ -624,7 +626,7 @@ class Engine:
         z64, z32, e32 = sc['z64'], sc['z32'], sc['e32']
         _zero(sc['acc'])
         pool = {'z64': 0, 'z32': 0, 'e32': 0}
-        jobs = []                                       # (src ptr, src is f64, dst name, n, accumulate)
+        jobs = {}                                       # dst name -> [n, accumulate into dst, (src ptr, is f64), ...]
 
         def take(name, buf, n):
             i = pool[name]
@@ -671,7 +673,8 @@ class Engine:
                     call('mmlf_colsum16', _ptr(dout), ld_dout, cs.n_pad, geo.n_slots, GRAD, _ptr(row), 1, sst)
             else:
                 colsum = None
-            jobs.append((dbias[0].data_ptr(), 1 if dbias[1] else 0, bname, cs.cout, acc))
+            # one job per destination (jobs of a launch run concurrently): a second call of a shared module adds a source
+            jobs.setdefault(bname, [cs.cout, 0 if written is None else 1]).append((dbias[0].data_ptr(), bool(dbias[1])))
 
             def work():
                 sst = _stream()
@@ -715,8 +718,7 @@ class Engine:
             h2n = self.head2.name
             w2 = params[h2n + '.weight'].detach()
             gmid = self._slots(geo, h1.n_pad, GRAD)
-            if written is not None or not (first(h2n + '.weight') and first(h2n + '.bias')):
-                pass                                   # head_small_bwd adds into its outputs: both cases are correct
+            first(h2n + '.weight'), first(h2n + '.bias')      # head_small_bwd adds into its (cleared) outputs
             call('mmlf_head_small_bwd', _ptr(g_out), _ptr(hd['mid']), h1.n_pad, self.oc, _ptr(w2), geo.B, geo.H, geo.W,
                  _ptr(gmid), h1.n_pad, gptr(h2n + '.weight'), gptr(h2n + '.bias'), st)
             conv_param_grads(h1, gmid, h1.n_pad, hd['xg'], hd['ld_x'])
@@ -793,10 +795,21 @@ class Engine:
         if side is not None:
             main.wait_stream(side)
         # ---- all the short vectors in one launch; the device job table is rebuilt only when a pointer moved
-        key = tuple((src, f64, base + 4 * layout[name][0], n, acc) for src, f64, name, n, acc in jobs)
-        if self._vec_jobs is None or self._vec_jobs[0] != key:
-            arr = (VecJob * len(key))(*[VecJob(src, dst, n, f64, acc, 0) for src, f64, dst, n, acc in key])
-            table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
-            self._vec_jobs = (key, table)
-        call('mmlf_vec_jobs', _ptr(self._vec_jobs[1]), len(key), st)
+        key = []
+        for name, (n, acc, *srcs) in jobs.items():
+            assert len(srcs) <= 2, 'a module is called at most twice per forward'
+            s2 = srcs[1] if len(srcs) > 1 else (0, False)
+            key.append((srcs[0][0], s2[0], base + 4 * layout[name][0], n, int(srcs[0][1]) | (int(s2[1]) << 1), acc))
+        key = tuple(key)
+        if key not in self._vec_jobs:
+            if len(self._vec_jobs) >= 8 and not torch.cuda.is_current_stream_capturing():
+                # eager passes that keep moving their gradient buffer: drop the oldest tables, but never one that a live
+                # captured step may address (those are registered in _pinned_tables)
+                for old in [k for k in self._vec_jobs if k not in self._pinned_tables][:4]:
+                    del self._vec_jobs[old]
+            arr = (VecJob * len(key))(*[VecJob(s1, s2 or None, dst, n, f64, acc, 0) for s1, s2, dst, n, f64, acc in key])
+            self._vec_jobs[key] = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+        if torch.cuda.is_current_stream_capturing():
+            self._pinned_tables.add(key)
+        call('mmlf_vec_jobs', _ptr(self._vec_jobs[key]), len(key), st)
         return {name: flat[off:off + n].view(shape) for name, (off, n, shape) in layout.items()}

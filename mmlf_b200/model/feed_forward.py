@@ -83,12 +83,13 @@ class FeedForward(nn.Module):
                  model_uncert, model_unet, model_discrete, model_no_batchnorm, model_batchnorm_momentum,
                  val_disp_min, val_disp_max, **kwargs):
         super(FeedForward, self).__init__()
-        if model_ksize != 2:
-            raise NotImplementedError('mmlf_b200 implements the published model_ksize=2 topology only '
-                                      '(SURVEY.md section 8f.4 lists odd kernel sizes as a later row)')
-        if model_unet:
-            raise NotImplementedError('--model_unet is out of scope of the B200 hot path (SURVEY.md section 2, row 9)')
+        if model_ksize < 1 or model_ksize > 7:
+            raise NotImplementedError('model_ksize must be in 1..7: 2 is the published topology (tensor-core path), the '
+                                      'others run on the float32 layer kernels (SURVEY.md section 8f.4)')
+        if model_unet and model_discrete:
+            raise NotImplementedError('--model_unet has a 1- or 2-channel head (feed_forward.py:196-202)')
         self.ksize = model_ksize
+        self.unet = bool(model_unet)
         self.chs = model_chs
         self.views = model_views
         self.cross = model_cross
@@ -104,14 +105,14 @@ class FeedForward(nn.Module):
             self.steps = 2
         self.steps *= model_views * 3                                   # feed_forward.py:81-84
         self.padding1 = model_ksize // 2                                 # feed_forward.py:86-92
-        self.padding2 = model_ksize // 2 - 1
+        self.padding2 = model_ksize // 2 if model_ksize % 2 == 1 else model_ksize // 2 - 1
         self.n_in_blocks = model_in_blocks
         self.n_out_blocks = model_out_blocks
 
         self.in_net_hv = self.init_in_net(model_in_blocks)
         if not model_cross:
             self.in_net_id = self.init_in_net(model_in_blocks)
-        self.out_net = self.init_out_net(model_out_blocks)
+        self.out_net = self.init_unet() if model_unet else self.init_out_net(model_out_blocks)   # feed_forward.py:99-102
         self._engine = None
         self._bins = {}
         self._graphs = {}
@@ -153,11 +154,28 @@ class FeedForward(nn.Module):
         blocks.append(self.block(chs, out_chs, False))
         return nn.Sequential(*blocks)
 
+    def init_unet(self, depth=5):
+        """feed_forward.py:189-204: the out-net as a U-Net (3x3 convs, BatchNorm, depth 5); head of 1 or 2 channels."""
+        from .unet import UNet
+        chs = (2 if self.cross else 4) * self.chs
+        self.out_chs = 2 if self.uncert else 1
+        return UNet(chs, self.out_chs, depth)
+
+    # -- the engine, captured graphs and device tables are run-time caches: never copied or pickled with the module
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state.update(_engine=None, _bins={}, _graphs={})
+        return state
+
     # -- execution
     @property
     def engine(self):
         if self._engine is None:
-            self._engine = Engine(self)
+            if self.ksize == 2 and not self.unet:
+                self._engine = Engine(self)                  # published topology: tcgen05 implicit GEMM path
+            else:
+                from ..engine_generic import GenericEngine   # odd ksize / U-Net out-net: float32 layer kernels
+                self._engine = GenericEngine(self)
         return self._engine
 
     def _bin_tables(self, device):
@@ -201,7 +219,7 @@ class FeedForward(nn.Module):
             from .. import _lib
             graph = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count
-            with torch.cuda.graph(graph, capture_error_mode='thread_local'):
+            with _lib.no_gc_during_capture(), torch.cuda.graph(graph):
                 outs = [self.engine.forward(static_in, False, save=False, shift_disp=sd)[0] for sd in shifts]
             n_launches = _lib.launch_count - n0
             _lib.launch_count = n0                        # captured, not executed

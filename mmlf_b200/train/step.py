@@ -70,6 +70,9 @@ class TrainStep:
         m, eng = self.model, self.model.engine
         views = S['views']
         flat_p, flat_g, flat_m, flat_v = self.opt.flat_buffers
+        # the packed tensor-core operands are re-derived from the fp32 parameters in EVERY step (one launch): the step
+        # itself changes them, and a captured step must contain that launch whatever the version counters say
+        eng._pack_version = None
         out, tape = eng.forward(views, m.training, save=True)
         B, OC, H, W = out.shape
         HW = H * W
@@ -203,7 +206,7 @@ class TrainStep:
                 torch.cuda.empty_cache()                      # the warm-up's activations must not double the footprint
                 g = torch.cuda.CUDAGraph()
                 n1 = _lib.launch_count
-                with torch.cuda.graph(g, capture_error_mode='thread_local'):
+                with _lib.no_gc_during_capture(), torch.cuda.graph(g, capture_error_mode='thread_local'):
                     self._body(S)
                 _lib.launch_count = n1
                 S['graph'] = g

@@ -55,12 +55,27 @@ def test_init_matches_reference_rng_stream(golden):
                                  'loss'}
 
 
-def test_unsupported_topologies_raise():
+def test_other_topologies_construct_with_the_reference_layout(golden):
+    """--model_ksize 3 and --model_unet: same state_dict keys / shapes as the reference fixtures."""
+    from mmlf_b200.engine import Engine
+    from mmlf_b200.engine_generic import GenericEngine
     from mmlf_b200.model.feed_forward import FeedForward
+    m3 = FeedForward(**fx.model_kwargs('base', chs=8, model_ksize=3))
+    g3 = golden('net_tiny_base_k3.npz')
+    want = {k[6:]: g3[k].shape for k in g3.files if k.startswith('state/')}
+    assert {k: tuple(v.shape) for k, v in m3.state_dict().items()} == want
+    assert (m3.padding1, m3.padding2) == (1, 1) and isinstance(m3.engine, GenericEngine)
+    mu = FeedForward(**fx.model_kwargs('upr', chs=8, model_unet=True))
+    gu = golden('net_unet_upr.npz')
+    names = [str(n) for n in gu['names']]
+    shapes = [tuple(int(x) for x in s.split(',')) if s else () for s in (str(t) for t in gu['shapes'])]
+    assert [(k, tuple(v.shape)) for k, v in mu.state_dict().items()] == list(zip(names, shapes))
+    assert isinstance(mu.engine, GenericEngine) and mu.out_chs == 2
+    assert isinstance(FeedForward(**fx.model_kwargs('base', chs=8)).engine, Engine)
     with pytest.raises(NotImplementedError):
-        FeedForward(**fx.model_kwargs('base', model_ksize=3))
+        FeedForward(**fx.model_kwargs('base', model_ksize=9))
     with pytest.raises(NotImplementedError):
-        FeedForward(**fx.model_kwargs('base', model_unet=True))
+        FeedForward(**fx.model_kwargs('dpp', model_unet=True))
 
 
 def test_lazy_outputs():
