@@ -538,6 +538,8 @@ def run_gpu(args, rank, world, local, with_cpu_baseline, sample_clocks=True):
         roofline['batchnorm_share_of_kernel_time'] = round(bn / kernel_sum_ms, 4)
 
     # free this workload's memory before the next one
+    if train_step is not None:
+        train_step.close()
     train_step = None
     del model, views, host
     gc.collect()

@@ -77,6 +77,13 @@ int mmlf_pack_views_split(const float* views, int B, int C, int H, int W, void* 
  * is rounded to bf16 and written straight into the slot layout.  stack: 0 = h, 1 = v, 2 = i, 3 = d. */
 int mmlf_shift_pack(const float* src, int stack, int B, int n, int H, int W, double disp, void* out, int ld,
                     int dtype, void* stream);
+/* All stacks of a forward pass in ONE launch (grid.z = stack), each optionally written twice from the same read: `out`
+ * in `dtype` and `out2` (NULL = none) in `dtype2` -- the bf16 twin of the fp16 activations that the weight-gradient GEMM
+ * reads.  views / out / out2: HOST arrays of n_stacks device pointers, stacks[i] = 0 h, 1 v, 2 i, 3 d (only used when
+ * do_shift != 0: the ESE Shift of mmlf_shift_pack with disparity `disp`).  Each source (B, n, 3, H, W) f32. */
+int mmlf_pack_stacks(const float* const* views, const int* stacks, int n_stacks, int B, int n, int H, int W,
+                     void* const* out, void* const* out2, int ld, int dtype, int dtype2, int do_shift, double disp,
+                     void* stream);
 
 /* ------------------------------------------------------------------ convolution (mmlf/model/feed_forward.py:122-137) */
 

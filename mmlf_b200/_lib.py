@@ -47,6 +47,7 @@ _PROTOS = {
     'mmlf_pack_views': (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p]),
     'mmlf_pack_views_split': (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_p]),
     'mmlf_shift_pack': (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_d, c_p, c_i, c_i, c_p]),
+    'mmlf_pack_stacks': (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_d, c_p]),
     'mmlf_pack_conv_weight': (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_i, c_p]),
     'mmlf_pack_conv_weight_split': (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_i, c_f, c_p]),
     'mmlf_pack_conv_weights_batch': (c_i, [c_p, c_i, c_i64, c_p]),

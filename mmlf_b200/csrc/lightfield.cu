@@ -18,6 +18,16 @@ struct ExtractParams {
   int n, H, W;
 };
 
+// Correctly rounded x / 255 for a byte value x without the IEEE-division slow path: q = x * fl(1 / 255), one Newton
+// correction through two FMAs.  Equal to __fdiv_rn(x, 255) for all 256 inputs (checked exhaustively in exact rational
+// arithmetic, and by tests/test_gpu_kernels.py::test_lf_extract_bit_exact which feeds every byte value).
+__device__ __forceinline__ float div255(uint8_t b) {
+  const float x = static_cast<float>(b), rc = 0.003921568859368563f;
+  const float q = __fmul_rn(x, rc);
+  const float r = __fmaf_rn(-q, 255.f, x);
+  return __fmaf_rn(r, rc, q);
+}
+
 __global__ void lf_extract_kernel(const uint8_t* __restrict__ views, const ExtractParams p) {
   // one thread = 4 consecutive pixels of one view of one stack
   const int W4 = p.W >> 2;
@@ -40,11 +50,11 @@ __global__ void lf_extract_kernel(const uint8_t* __restrict__ views, const Extra
   for (int c = 0; c < 3; ++c) {
     float4 v;
     // img_as_float(u8).astype(f32) == correctly rounded x / 255 (hci4d.py:156-157)
-    v.x = __fdiv_rn(static_cast<float>(px[c]), 255.f);
-    v.y = __fdiv_rn(static_cast<float>(px[3 + c]), 255.f);
-    v.z = __fdiv_rn(static_cast<float>(px[6 + c]), 255.f);
-    v.w = __fdiv_rn(static_cast<float>(px[9 + c]), 255.f);
-    *reinterpret_cast<float4*>(dst + c * plane) = v;
+    v.x = div255(px[c]);
+    v.y = div255(px[3 + c]);
+    v.z = div255(px[6 + c]);
+    v.w = div255(px[9 + c]);
+    __stcs(reinterpret_cast<float4*>(dst + c * plane), v);
     if (p.center && stack == 1 && k == p.n / 2)
       *reinterpret_cast<float4*>(p.center + c * plane + static_cast<int64_t>(y) * p.W + x) = v;
   }
@@ -320,6 +330,13 @@ __global__ void __launch_bounds__(256) lf_shift_vec_kernel(const ShiftParams p, 
 struct PackParams {
   const float* views;
   __nv_bfloat16* out;
+  // multi-stack launches (blockIdx.z = stack): all stacks of a forward pass in ONE launch, optionally with a second copy
+  // in another 16-bit format written from the same tile (the bf16 twin the weight-gradient GEMM reads)
+  const float* views4[4];
+  __nv_bfloat16* out4[4];
+  __nv_bfloat16* out2_4[4];
+  int stack4[4];
+  int n_stacks, dtype2;
   int B, C, H, W, ld;
   int cw;                        // channels written per slot (multiple of 8, <= ld); columns [cw, ld) are left alone
   int residual;                  // write fp16(x - float(fp16(x))) instead of fp16(x) (split-precision lo block)
@@ -345,16 +362,26 @@ __device__ __forceinline__ float shifted_value(const float* __restrict__ plane, 
 
 constexpr int kPackTile = 128;                     // slot columns per CTA
 
-__device__ __forceinline__ uint32_t pack_pair(float a, float b, const PackParams& p) {
+__device__ __forceinline__ uint32_t pack_pair(float a, float b, const PackParams& p, int dtype) {
   if (p.residual) {
     a -= from16(to16(a, kFP16), kFP16);
     b -= from16(to16(b, kFP16), kFP16);
   }
-  return pack16x2(a, b, p.dtype);
+  return pack16x2(a, b, dtype);
 }
+__device__ __forceinline__ uint32_t pack_pair(float a, float b, const PackParams& p) { return pack_pair(a, b, p, p.dtype); }
+
+#define MMLF_PACK_SELECT()                                                                                           \
+  const int zz = blockIdx.z;                                                                                          \
+  const bool multi = p.n_stacks > 0;                                                                                  \
+  const float* pviews = !multi ? p.views : zz == 0 ? p.views4[0] : zz == 1 ? p.views4[1] : zz == 2 ? p.views4[2] : p.views4[3]; \
+  __nv_bfloat16* pout = !multi ? p.out : zz == 0 ? p.out4[0] : zz == 1 ? p.out4[1] : zz == 2 ? p.out4[2] : p.out4[3];    \
+  __nv_bfloat16* out2 = !multi ? nullptr : zz == 0 ? p.out2_4[0] : zz == 1 ? p.out2_4[1] : zz == 2 ? p.out2_4[2] : p.out2_4[3]; \
+  const int pstack = !multi ? p.stack : zz == 0 ? p.stack4[0] : zz == 1 ? p.stack4[1] : zz == 2 ? p.stack4[2] : p.stack4[3];
 
 __global__ void __launch_bounds__(256) pack_views_kernel(const PackParams p) {
   __shared__ float tile[32][kPackTile + 1];        // [channel][slot column], 32 channels per pass
+  MMLF_PACK_SELECT()
   const int Wp = p.W + 1, Hp = p.H + 1;
   const int sx0 = blockIdx.x * kPackTile;
   const int sy = blockIdx.y % Hp, b = blockIdx.y / Hp;
@@ -365,7 +392,7 @@ __global__ void __launch_bounds__(256) pack_views_kernel(const PackParams p) {
     for (int c = wrp; c < 32; c += 8) {
       const int ch = cbase + c;
       const bool row_ok = ch < p.C && sy >= 1;
-      const float* plane = p.views + (static_cast<int64_t>(b) * p.C + (row_ok ? ch : 0)) * p.H * p.W;
+      const float* plane = pviews + (static_cast<int64_t>(b) * p.C + (row_ok ? ch : 0)) * p.H * p.W;
       float w0 = 0.f, w1 = 0.f;
       int s0 = 0, s1 = 0;
       if (p.do_shift && row_ok) {
@@ -378,7 +405,7 @@ __global__ void __launch_bounds__(256) pack_views_kernel(const PackParams p) {
         const int sx = sx0 + lane + 32 * j;
         v[j] = 0.f;
         if (row_ok && sx >= 1 && sx < Wp) {
-          if (p.do_shift) v[j] = shifted_value(plane, sy - 1, sx - 1, p.H, p.W, p.stack, w0, w1, s0, s1);
+          if (p.do_shift) v[j] = shifted_value(plane, sy - 1, sx - 1, p.H, p.W, pstack, w0, w1, s0, s1);
           else v[j] = __ldg(plane + static_cast<int64_t>(sy - 1) * p.W + (sx - 1));
         }
       }
@@ -398,7 +425,14 @@ __global__ void __launch_bounds__(256) pack_views_kernel(const PackParams p) {
         o.y = pack_pair(tile[cq + 2][slot], tile[cq + 3][slot], p);
         o.z = pack_pair(tile[cq + 4][slot], tile[cq + 5][slot], p);
         o.w = pack_pair(tile[cq + 6][slot], tile[cq + 7][slot], p);
-        *reinterpret_cast<uint4*>(p.out + (slot_row + sx) * p.ld + cbase + cq) = o;
+        *reinterpret_cast<uint4*>(pout + (slot_row + sx) * p.ld + cbase + cq) = o;
+        if (out2) {
+          o.x = pack_pair(tile[cq][slot], tile[cq + 1][slot], p, p.dtype2);
+          o.y = pack_pair(tile[cq + 2][slot], tile[cq + 3][slot], p, p.dtype2);
+          o.z = pack_pair(tile[cq + 4][slot], tile[cq + 5][slot], p, p.dtype2);
+          o.w = pack_pair(tile[cq + 6][slot], tile[cq + 7][slot], p, p.dtype2);
+          *reinterpret_cast<uint4*>(out2 + (slot_row + sx) * p.ld + cbase + cq) = o;
+        }
       }
     }
     __syncthreads();
@@ -410,20 +444,21 @@ __global__ void __launch_bounds__(256) pack_views_kernel(const PackParams p) {
 // through shared memory and written as 16-byte channel groups.  Slot column 0 (the halo) is written by the first tile.
 __global__ void __launch_bounds__(256) pack_views_vec_kernel(const PackParams p) {
   __shared__ __align__(16) float tile[32][kPackTile + 4];   // [channel][pixel], 16-byte aligned rows
+  MMLF_PACK_SELECT()
   const int Wp = p.W + 1, Hp = p.H + 1, W = p.W, H = p.H;
   const int X0 = blockIdx.x * kPackTile;
   const int sy = blockIdx.y % Hp, b = blockIdx.y / Hp;
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
   const int64_t slot_row = (static_cast<int64_t>(b) * Hp + sy) * Wp;
   const int x0 = X0 + 4 * lane, y = sy - 1;
-  const bool has_w = p.do_shift && p.stack != 1, has_v = p.do_shift && p.stack != 0;
-  const int vsign = p.stack == 2 ? -1 : +1;
+  const bool has_w = p.do_shift && pstack != 1, has_v = p.do_shift && pstack != 0;
+  const int vsign = pstack == 2 ? -1 : +1;
   for (int cbase = 0; cbase < p.cw; cbase += 32) {
     for (int c = wrp; c < 32; c += 8) {
       const int ch = cbase + c;
       float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
       if (ch < p.C && sy >= 1 && x0 < W) {
-        const float* plane = p.views + (static_cast<int64_t>(b) * p.C + ch) * H * W;
+        const float* plane = pviews + (static_cast<int64_t>(b) * p.C + ch) * H * W;
         if (!p.do_shift) {
           val = __ldg(reinterpret_cast<const float4*>(plane + static_cast<int64_t>(y) * W + x0));
         } else {
@@ -471,13 +506,22 @@ __global__ void __launch_bounds__(256) pack_views_vec_kernel(const PackParams p)
         o.y = pack_pair(tile[cq + 2][px], tile[cq + 3][px], p);
         o.z = pack_pair(tile[cq + 4][px], tile[cq + 5][px], p);
         o.w = pack_pair(tile[cq + 6][px], tile[cq + 7][px], p);
-        *reinterpret_cast<uint4*>(p.out + (slot_row + X0 + px + 1) * p.ld + cbase + cq) = o;
+        *reinterpret_cast<uint4*>(pout + (slot_row + X0 + px + 1) * p.ld + cbase + cq) = o;
+        if (out2) {
+          o.x = pack_pair(tile[cq][px], tile[cq + 1][px], p, p.dtype2);
+          o.y = pack_pair(tile[cq + 2][px], tile[cq + 3][px], p, p.dtype2);
+          o.z = pack_pair(tile[cq + 4][px], tile[cq + 5][px], p, p.dtype2);
+          o.w = pack_pair(tile[cq + 6][px], tile[cq + 7][px], p, p.dtype2);
+          *reinterpret_cast<uint4*>(out2 + (slot_row + X0 + px + 1) * p.ld + cbase + cq) = o;
+        }
       }
     }
     __syncthreads();
   }
-  if (blockIdx.x == 0 && threadIdx.x * 8 < p.cw)            // halo column sx = 0
-    *reinterpret_cast<uint4*>(p.out + slot_row * p.ld + threadIdx.x * 8) = make_uint4(0u, 0u, 0u, 0u);
+  if (blockIdx.x == 0 && threadIdx.x * 8 < p.cw) {          // halo column sx = 0
+    *reinterpret_cast<uint4*>(pout + slot_row * p.ld + threadIdx.x * 8) = make_uint4(0u, 0u, 0u, 0u);
+    if (out2) *reinterpret_cast<uint4*>(out2 + slot_row * p.ld + threadIdx.x * 8) = make_uint4(0u, 0u, 0u, 0u);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ texture mask
@@ -631,6 +675,7 @@ static int launch_pack(const float* views, int B, int C, int H, int W, void* out
   MMLF_REQUIRE(ld % 8 == 0 && ld >= C, "pack_views: ld %d must be a multiple of 8 and >= C %d", ld, C);
   MMLF_REQUIRE(static_cast<int64_t>(B) * (H + 1) <= 65535 * 1024ll, "pack_views: batch too large");
   PackParams p;
+  p.n_stacks = 0; p.dtype2 = dtype;
   p.views = views; p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.B = B; p.C = C; p.H = H; p.W = W; p.ld = ld;
   p.do_shift = do_shift; p.stack = stack; p.n = n; p.dtype = dtype;
@@ -679,6 +724,43 @@ extern "C" int mmlf_shift_pack(const float* src, int stack, int B, int n, int H,
   MMLF_REQUIRE(stack >= 0 && stack < 4, "shift_pack: stack must be 0..3");
   MMLF_REQUIRE(n >= 1 && n <= 16, "shift_pack: n must be in [1, 16]");
   return launch_pack(src, B, n * 3, H, W, out, ld, dtype, 1, stack, n, disp, stream);
+}
+
+extern "C" int mmlf_pack_stacks(const float* const* views, const int* stacks, int n_stacks, int B, int n, int H, int W,
+                                void* const* out, void* const* out2, int ld, int dtype, int dtype2, int do_shift,
+                                double disp, void* stream) {
+  MMLF_REQUIRE(views && stacks && out && n_stacks >= 1 && n_stacks <= 4, "pack_stacks: 1..4 stacks");
+  MMLF_REQUIRE((dtype == 0 || dtype == 1) && (dtype2 == 0 || dtype2 == 1), "pack_stacks: dtype must be 0 (bf16) or 1 (fp16)");
+  MMLF_REQUIRE(n >= 1 && n <= 16, "pack_stacks: n must be in [1, 16]");
+  const int C = n * 3;
+  MMLF_REQUIRE(ld % 8 == 0 && ld >= C, "pack_stacks: ld %d must be a multiple of 8 and >= C %d", ld, C);
+  MMLF_REQUIRE(static_cast<int64_t>(B) * (H + 1) <= 65535, "pack_stacks: batch * (H + 1) must fit one grid dimension");
+  PackParams p;
+  p.views = nullptr; p.out = nullptr;
+  p.n_stacks = n_stacks; p.dtype = dtype; p.dtype2 = dtype2;
+  p.B = B; p.C = C; p.H = H; p.W = W; p.ld = ld; p.cw = ld; p.residual = 0;
+  p.do_shift = do_shift; p.stack = 0; p.n = n;
+  bool vec = W % 4 == 0 && W >= 8;
+  for (int i = 0; i < 4; ++i) {
+    const int j = i < n_stacks ? i : 0;
+    MMLF_REQUIRE(views[j] && out[j], "pack_stacks: null buffer");
+    MMLF_REQUIRE(stacks[j] >= 0 && stacks[j] < 4, "pack_stacks: stack must be 0..3");
+    p.views4[i] = views[j];
+    p.out4[i] = reinterpret_cast<__nv_bfloat16*>(out[j]);
+    p.out2_4[i] = out2 ? reinterpret_cast<__nv_bfloat16*>(out2[j]) : nullptr;
+    p.stack4[i] = stacks[j];
+    vec = vec && reinterpret_cast<uintptr_t>(views[j]) % 16 == 0 && reinterpret_cast<uintptr_t>(out[j]) % 16 == 0 &&
+          (!out2 || reinterpret_cast<uintptr_t>(out2[j]) % 16 == 0);
+  }
+  if (do_shift) host_taps(disp, n, p.taps);
+  if (vec) {
+    dim3 grid(ceil_div(W, kPackTile), static_cast<unsigned>(B * (H + 1)), n_stacks);
+    pack_views_vec_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  } else {
+    dim3 grid(ceil_div(W + 1, kPackTile), static_cast<unsigned>(B * (H + 1)), n_stacks);
+    pack_views_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  }
+  return check_launch("pack_stacks");
 }
 
 extern "C" int mmlf_texture_mask(const float* center, int B, int H, int W, int wsize, double threshold, int32_t* mask,

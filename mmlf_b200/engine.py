@@ -360,17 +360,25 @@ class Engine:
         self._fwd_bn_idx = 0
         feats = self._slots(geo, self.feat_ld)
         featsg = self._slots(geo, self.feat_ld, GRAD) if dual else (feats if save else None)
+        # all view stacks -> slot layout in ONE launch (grid.z = stack), the bf16 twins written from the same read;
+        # with `shift_disp` the ESE Shift is fused into it
+        ns = len(self.stream_defs)
+        xs = [self._slots(geo, cin0_pad) for _ in range(ns)]
+        xgs = [self._slots(geo, cin0_pad, GRAD) for _ in range(ns)] if dual else (xs if save else [None] * ns)
+        if B * (H + 1) <= 65535:
+            PtrArr, IntArr = C.c_void_p * ns, C.c_int * ns
+            call('mmlf_pack_stacks', PtrArr(*[views[si].data_ptr() for si in range(ns)]), IntArr(*range(ns)), ns, B, n, H,
+                 W, PtrArr(*[t.data_ptr() for t in xs]), PtrArr(*[t.data_ptr() for t in xgs]) if dual else None, cin0_pad,
+                 self.act, GRAD, 0 if shift_disp is None else 1, 0.0 if shift_disp is None else float(shift_disp), st)
+        else:                                              # very large batches: one (slab-splitting) launch per stack
+            for si in range(ns):
+                for dst, dt in ((xs[si], self.act),) + (((xgs[si], GRAD),) if dual else ()):
+                    if shift_disp is None:
+                        call('mmlf_pack_views', _ptr(views[si]), B, n * c3, H, W, _ptr(dst), cin0_pad, dt, st)
+                    else:
+                        call('mmlf_shift_pack', _ptr(views[si]), si, B, n, H, W, float(shift_disp), _ptr(dst), cin0_pad, dt, st)
         for si, (key, net, spatial) in enumerate(self.stream_defs):
-            v = views[si]
-            assert v.is_cuda and v.dtype == torch.float32 and v.is_contiguous(), \
-                'view stacks must be contiguous fp32 CUDA tensors (feed_forward.py:226-232 uses .view)'
-            x = self._slots(geo, cin0_pad)
-            xg = self._slots(geo, cin0_pad, GRAD) if dual else (x if save else None)
-            for dst, dt in ((x, self.act),) + (((xg, GRAD),) if dual else ()):
-                if shift_disp is None:
-                    call('mmlf_pack_views', _ptr(v), B, n * c3, H, W, _ptr(dst), cin0_pad, dt, st)
-                else:
-                    call('mmlf_shift_pack', _ptr(v), si, B, n, H, W, float(shift_disp), _ptr(dst), cin0_pad, dt, st)
+            x, xg = xs[si], xgs[si]
             ld_x = cin0_pad
             recs = []
             blocks = self.in_specs[key]

@@ -287,6 +287,7 @@ def main(output_dir, max_iterations, gpu_augment, synthetic_data, **kwargs):
             i += 1
             time_start = time.time()
             if max_iterations and i >= max_iterations:
+                train_step.close()                    # captured NCCL kernels must go before the process group does
                 return 0
 
 

@@ -65,6 +65,15 @@ class TrainStep:
         self.launches_per_step = 0
         self.replays = 0
 
+    def close(self):
+        """Drop the captured graphs (and the activation memory they own).  Call it before tearing down a multi-rank
+        process group: a live graph holds NCCL kernels of that communicator, and destroying the group under it can hang."""
+        import gc
+        torch.cuda.synchronize()
+        self._graphs.clear()
+        gc.collect()
+        torch.cuda.empty_cache()
+
     # ------------------------------------------------------------------ the work of one step, on static buffers
     def _body(self, S):
         m, eng = self.model, self.model.engine

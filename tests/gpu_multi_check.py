@@ -77,7 +77,10 @@ def main():
     print(f'rank {rank} train replicas: params identical={same} losses identical={lsame} replays={step.replays} '
           f'loss {losses[0]:.5f} -> {losses[-1]:.5f}')
     ok &= same and lsame and step.replays == 3
-    print(f'rank {rank}: {"OK" if ok else "MISMATCH"}')
+    print(f'rank {rank}: {"OK" if ok else "MISMATCH"}', flush=True)
+    step.close()                                               # graphs with NCCL kernels go before the process group
+    del step, opt, tm
+    torch.cuda.synchronize()
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
     sys.exit(0 if ok else 1)

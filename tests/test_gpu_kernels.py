@@ -809,3 +809,40 @@ def test_hci4d_loader_against_the_oracle(tmp_path):
     want = oracle.shift(tuple(a.copy() for a in oracle.extract_stacks(u8b)[:4]), 1.5)
     for k in range(4):
         assert np.array_equal(shifted[k].cpu().numpy(), want[k])
+
+
+@pytest.mark.parametrize('shape', [(2, 9, 20, 24), (1, 9, 17, 19), (3, 5, 32, 32)])
+def test_pack_stacks_equals_the_per_stack_launches(shape):
+    """mmlf_pack_stacks (all stacks of a forward in one launch, optional second copy in another 16-bit format, optional fused
+    ESE Shift) == mmlf_pack_views / mmlf_shift_pack per stack and format, bit for bit."""
+    import ctypes as C
+    u = _u()
+    B, n, H, W = shape
+    g = torch.Generator(device='cuda').manual_seed(3)
+    views = [torch.rand((B, n, 3, H, W), device='cuda', generator=g) for _ in range(4)]
+    ld = u.pad16(n * 3)
+    n_slots = B * (H + 1) * (W + 1)
+    for disp in (None, 2.5, -0.7):
+        for ns in (4, 2):
+            outs = [torch.full((n_slots, ld), 7.0, dtype=torch.float16, device='cuda') for _ in range(ns)]
+            outs2 = [torch.full((n_slots, ld), 7.0, dtype=torch.bfloat16, device='cuda') for _ in range(ns)]
+            PA, IA = C.c_void_p * ns, C.c_int * ns
+            u.call('mmlf_pack_stacks', PA(*[v.data_ptr() for v in views[:ns]]), IA(*range(ns)), ns, B, n, H, W,
+                   PA(*[t.data_ptr() for t in outs]), PA(*[t.data_ptr() for t in outs2]), ld, u.FP16, u.BF16,
+                   0 if disp is None else 1, 0.0 if disp is None else disp, u.stream())
+            for si in range(ns):
+                for dt, got in ((u.FP16, outs[si]), (u.BF16, outs2[si])):
+                    want = torch.full((n_slots, ld), 7.0, dtype=u.TDT[dt], device='cuda')
+                    if disp is None:
+                        u.call('mmlf_pack_views', u.ptr(views[si]), B, n * 3, H, W, u.ptr(want), ld, dt, u.stream())
+                    else:
+                        u.call('mmlf_shift_pack', u.ptr(views[si]), si, B, n, H, W, disp, u.ptr(want), ld, dt, u.stream())
+                    torch.cuda.synchronize()
+                    assert torch.equal(got.view(torch.int16), want.view(torch.int16)), (disp, ns, si, dt)
+            # without a second output
+            only = [torch.full((n_slots, ld), 7.0, dtype=torch.float16, device='cuda') for _ in range(ns)]
+            u.call('mmlf_pack_stacks', PA(*[v.data_ptr() for v in views[:ns]]), IA(*range(ns)), ns, B, n, H, W,
+                   PA(*[t.data_ptr() for t in only]), None, ld, u.FP16, u.BF16, 0 if disp is None else 1,
+                   0.0 if disp is None else disp, u.stream())
+            torch.cuda.synchronize()
+            assert all(torch.equal(a, b) for a, b in zip(only, outs))

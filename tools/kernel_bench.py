@@ -234,7 +234,23 @@ def main():
         bn.hbm_row('shift_pack_kernel', f'{tag}, stack i (two lerps), disp 2.5', B * 27 * H * W * 4.0 + B * H * W * 64.0,
                    lambda: call('mmlf_shift_pack', P(views[2]), 2, B, 9, H, W, 2.5, P(slots), 32, FP16, ST()),
                    'Shift fused into the packing')
-        del views, outs, slots
+        s4 = [torch.empty((B * (H + 1) * (W + 1), 32), dtype=torch.float16, device=DEV) for _ in range(4)]
+        s4g = [torch.empty((B * (H + 1) * (W + 1), 32), dtype=torch.bfloat16, device=DEV) for _ in range(4)]
+        PA, IA = C.c_void_p * 4, C.c_int * 4
+        vp, sp, gp, ia = PA(*[v.data_ptr() for v in views]), PA(*[t.data_ptr() for t in s4]), \
+            PA(*[t.data_ptr() for t in s4g]), IA(0, 1, 2, 3)
+        bn.hbm_row('pack_views_kernel (pack_stacks)', f'{tag}, 4 stacks in one launch', 4 * (B * 27 * H * W * 4.0 + B * H * W * 64.0),
+                   lambda: call('mmlf_pack_stacks', vp, ia, 4, B, 9, H, W, sp, None, 32, FP16, BF16, 0, 0.0, ST()),
+                   'what an inference forward launches: read f32 planes, write 32-channel fp16 slots')
+        bn.hbm_row('pack_views_kernel (pack_stacks)', f'{tag}, 4 stacks, fp16 + bf16 copies',
+                   4 * (B * 27 * H * W * 4.0 + 2 * B * H * W * 64.0),
+                   lambda: call('mmlf_pack_stacks', vp, ia, 4, B, 9, H, W, sp, gp, 32, FP16, BF16, 0, 0.0, ST()),
+                   'what a training forward launches: one read, both formats written')
+        bn.hbm_row('shift_pack_kernel (pack_stacks)', f'{tag}, 4 stacks in one launch, disp 2.5',
+                   4 * (B * 27 * H * W * 4.0 + B * H * W * 64.0),
+                   lambda: call('mmlf_pack_stacks', vp, ia, 4, B, 9, H, W, sp, None, 32, FP16, BF16, 1, 2.5, ST()),
+                   'what an ESE member launches: Shift fused into the packing')
+        del views, outs, slots, s4, s4g
         torch.cuda.empty_cache()
     u8 = torch.randint(0, 256, (81, 512, 512, 3), dtype=torch.uint8, device=DEV, generator=g)
     bn.hbm_row('lf_extract_kernel', '81 u8 views 512x512 -> 4 stacks + centre f32',
