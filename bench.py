@@ -405,19 +405,23 @@ def run_gpu(args, rank, world, local, with_cpu_baseline, sample_clocks=True):
            'd2h_bytes_per_step': d2h * world, 'steps': e2e_steps,
            'note': 'pinned host inputs, double-buffered H2D on a copy stream, result read back every step'}
 
-    # ---------------- inference from the raw light field: the 81 uint8 views a dataset holds (hci4d.py:151-193) are
-    # copied in (64 MB instead of 113 MB of float32 stacks), the crosshair extraction runs on the GPU (mmlf_lf_extract_u8)
+    # ---------------- inference from the raw light field, as mmlf_b200.data.hci4d.HCI4D feeds it: of the 81 uint8 views a
+    # scene holds (hci4d.py:151-193) only the 33 the four crosshair stacks read are copied in (25.9 MB instead of 113 MB
+    # of float32 stacks), the extraction + u8 -> f32 runs on the GPU (mmlf_lf_extract_u8) in front of the forward
     e2e_u8 = None
     if args.workload == 'infer':
         try:
             from mmlf_b200.data import hci4d
             g8 = torch.Generator().manual_seed(99)
-            host8 = torch.randint(0, 256, (81, H, W, 3), dtype=torch.uint8, generator=g8).pin_memory()
-            dbuf = [torch.empty_like(host8, device=dev) for _ in range(2)]
+            us, vs, ids, dds = hci4d.view_indices((9, 9))
+            need = sorted(set(us + vs + ids + dds))
+            host8 = torch.randint(0, 256, (len(need), H, W, 3), dtype=torch.uint8, generator=g8).pin_memory()
+            dbuf = [torch.zeros((81, H, W, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
 
             def upload8(slot):
                 with torch.cuda.stream(copy_stream):
-                    dbuf[slot].copy_(host8, non_blocking=True)
+                    for j, vi in enumerate(need):
+                        dbuf[slot][vi].copy_(host8[j], non_blocking=True)
                     ready[slot].record(copy_stream)
 
             def step8(slot):
@@ -445,8 +449,9 @@ def run_gpu(args, rank, world, local, with_cpu_baseline, sample_clocks=True):
                 dist.all_reduce(ms3, op=dist.ReduceOp.MAX)
             e2e_u8 = {'value': units_per_step / (ms3.item() / e2e_steps / 1e3), 'unit': unit,
                       'h2d_bytes_per_step': host8.numel() * world, 'd2h_bytes_per_step': res.numel() * 4 * world,
-                      'steps': e2e_steps, 'note': '81 uint8 views (H, W, 3) from pinned host memory, crosshair extraction '
-                      '(mmlf_lf_extract_u8) + forward on the GPU, result read back every step'}
+                      'steps': e2e_steps, 'note': 'the 33 uint8 views (H, W, 3) of the crosshair from pinned host memory (what '
+                      'HCI4D.load_scene uploads), extraction (mmlf_lf_extract_u8) + forward on the GPU, result read back '
+                      'every step'}
         except Exception as ex:                                         # an extra measurement must not cost the bench line
             e2e_u8 = {'error': repr(ex)[:200]}
     del bufs
@@ -559,7 +564,12 @@ def run_gpu(args, rank, world, local, with_cpu_baseline, sample_clocks=True):
         line['kernel_ms_note'] = ('per training step, single-stream un-graphed profiling pass' if args.workload == 'train'
                                   else 'per single un-graphed forward (ESE: one member)')
         line['kernel_ms_per_step'] = {k: round(v, 3) for k, v in sorted(shares.items(), key=lambda kv: -kv[1])}
-    if e2e_u8 is not None:
+    if e2e_u8 is not None and 'value' in e2e_u8:
+        # full-LF inference: the public data path is the HCI4D loader's (uint8 views in, extraction on the GPU); the
+        # float32-stacks number (113 MB of H2D per light field: PCIe bound) is kept beside it
+        line['e2e_f32_stacks'] = dict(e2e, note=e2e['note'] + '; inputs = the four float32 stacks')
+        line['e2e'] = e2e_u8
+    elif e2e_u8 is not None:
         line['e2e_u8_views'] = e2e_u8
     return line
 
@@ -621,7 +631,7 @@ def main():
                 torch.cuda.empty_cache()
             if rank == 0 and res is not None:
                 keep = ('metric', 'value', 'unit', 'ms_per_step', 'scaling', 'steps', 'warmup', 'config', 'e2e', 'roofline',
-                        'gpu_launches', 'host_enqueue_ms_per_step', 'kernel_ms_per_step', 'e2e_u8_views', 'error')
+                        'gpu_launches', 'host_enqueue_ms_per_step', 'kernel_ms_per_step', 'e2e_u8_views', 'e2e_f32_stacks', 'error')
                 sec[key] = {k: res[k] for k in keep if k in res}
         if rank == 0:
             line['secondary'] = sec

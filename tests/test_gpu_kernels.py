@@ -184,7 +184,8 @@ def test_pack_views_and_shift_pack():
     for B, n, H, W, dt in ((2, 9, 10, 14, u.BF16), (2, 9, 10, 14, u.FP16), (1, 9, 5, 300, u.FP16)):
         v = rng.uniform(0, 1, (B, n, 3, H, W)).astype(np.float32)
         out = torch.full((B * (H + 1) * (W + 1), 32), float('nan'), dtype=u.TDT[dt], device='cuda')
-        u.call('mmlf_pack_views', u.ptr(torch.from_numpy(v).cuda()), B, n * 3, H, W, u.ptr(out), 32, dt, u.stream())
+        vd = torch.from_numpy(v).cuda()                     # named: a temporary would be freed before the launch
+        u.call('mmlf_pack_views', u.ptr(vd), B, n * 3, H, W, u.ptr(out), 32, dt, u.stream())
         got = out.float().cpu().numpy().reshape(B, H + 1, W + 1, 32)
         want = np.zeros_like(got)
         want[:, 1:, 1:, :27] = u.ROUND[dt](v.reshape(B, 27, H, W).transpose(0, 2, 3, 1))
@@ -197,7 +198,8 @@ def test_pack_views_and_shift_pack():
             sh = oracle.shift(tuple(stacks), disp)
             for k in range(4):
                 o = torch.full((B * (Hs + 1) * (Ws + 1), 32), float('nan'), dtype=torch.float16, device='cuda')
-                u.call('mmlf_shift_pack', u.ptr(torch.from_numpy(stacks[k]).cuda()), k, B, n, Hs, Ws, float(disp),
+                sd = torch.from_numpy(stacks[k]).cuda()
+                u.call('mmlf_shift_pack', u.ptr(sd), k, B, n, Hs, Ws, float(disp),
                        u.ptr(o), 32, u.FP16, u.stream())
                 got = o.float().cpu().numpy().reshape(B, Hs + 1, Ws + 1, 32)
                 want = np.zeros_like(got)
@@ -286,7 +288,8 @@ def test_conv_split_precision(case):
     xs = torch.cat([u.to_slots(hi, cin_pad, ctype == 1, Hp, Wp, u.FP16), u.to_slots(lo, cin_pad, ctype == 1, Hp, Wp, u.FP16)], 1)
     kc = (cin_pad + 63) // 64
     wp = torch.empty((n_pad, 4 * 3 * kc * 64), dtype=torch.float16, device='cuda')
-    u.call('mmlf_pack_conv_weight_split', u.ptr(torch.from_numpy(w).cuda()), cout, cin, 0, 1, cin, cin_pad, u.ptr(wp), n_pad,
+    wd = torch.from_numpy(w).cuda()
+    u.call('mmlf_pack_conv_weight_split', u.ptr(wd), cout, cin, 0, 1, cin, cin_pad, u.ptr(wp), n_pad,
            cin_pad, 64.0, u.stream())
     bias = torch.zeros(n_pad, device='cuda')
     bias[:cout] = torch.from_numpy(b)
@@ -620,10 +623,11 @@ def test_bn_train_roundtrip():
            u.ptr(fs), u.ptr(dzsum), u.stream())
     # accumulate = 1 (second call of a shared in-net): dgamma / dbeta add to what is there, dz is the same
     dz_b = torch.full_like(dz, float('nan'))
+    dzsum2 = torch.zeros(Cp, device='cuda')
     dgam2, dbet2 = dgam.clone(), dbet.clone()
     u.call('mmlf_bn_bwd_apply', u.ptr(gys), Cp, u.ptr(zs), Cp, u.ptr(scale), u.ptr(shift), u.ptr(d['gamma']), u.ptr(smean),
            u.ptr(sinv), u.ptr(bs), n, 1, Cr, Cp, B, H, W, G, A, u.ptr(dz_b), Cp, u.ptr(dgam2), u.ptr(dbet2), 1,
-           u.ptr(fs), u.ptr(torch.zeros(Cp, device='cuda')), u.stream())
+           u.ptr(fs), u.ptr(dzsum2), u.stream())
     torch.cuda.synchronize()
     assert torch.equal(dz, dz_b) and torch.equal(dgam2, 2 * dgam) and torch.equal(dbet2, 2 * dbet)
     assert torch.equal(fs[2 * Cp:2 * Cp + Cr], d['gamma']) and not fs[2 * Cp + Cr:].any()      # gamma on the padded pitch
