@@ -190,7 +190,9 @@ int mmlf_conv2x2_simt(const mmlf_conv_args* args, void* stream);
  *   dw[n][tap][c] = sum_slots dout[slot][n] * act[slot + tap_offset(type)][c]
  * dout: bf16 [n_slots][ld_dout] (n_pad channels), act: bf16 [n_slots][ld_act] (cin_pad channels).
  * workspace: f32, at least mmlf_conv2x2_wgrad_workspace(...) bytes.  dw: f32 [n_pad][4][cin_pad].
- * act_dtype must equal dout_dtype: tcgen05.mma kind::f16 faults on mixed f16 x bf16 operands (measured on B200). */
+ * act_dtype may differ from dout_dtype (fp16 activations x bf16 gradients): tcgen05.mma kind::f16 faults on mixed f16 x bf16
+ * operands (measured on B200), so the kernel converts its activation boxes to dout_dtype in shared memory after the TMA
+ * load -- bit-identical to mmlf_convert16 followed by a same-format launch, without the extra copy in HBM. */
 int64_t mmlf_conv2x2_wgrad_workspace(int n_pad, int cin_pad);
 int mmlf_conv2x2_wgrad(const void* dout, int ld_dout, int n_pad, const void* act, int ld_act, int cin_pad, int B,
                        int H, int W, int type, int act_dtype, int dout_dtype, float* workspace, float* dw,

@@ -176,6 +176,18 @@ conv2x2_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_
 // The gradient operand is split in N between the two CTAs (each supplies half of the columns of every MMA, loaded as
 // boxes that START at its slice so both CTAs use identical shared-memory offsets).  Per stage and CTA: 9 KB of
 // activations + <= 24 KB of gradients for 64 slots x 256 x 288 MACs, versus 16 + 40 KB for 128 x 288 before.
+// two packed 16-bit floats: fp16 -> bf16 (round to nearest even) or bf16 -> fp16
+__device__ __forceinline__ uint32_t convert16x2(uint32_t x, bool to_bf16) {
+  if (to_bf16) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&x));
+    const __nv_bfloat162 b = __float22bfloat162_rn(f);
+    return *reinterpret_cast<const uint32_t*>(&b);
+  }
+  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&x));
+  const __half2 h = __float22half2_rn(f);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
 constexpr int kWg2ABytes = 72 * 128;
 constexpr int kWg2MaxStages = 8;
 
@@ -208,7 +220,14 @@ conv2x2_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
   uint64_t* empty_bar = full_bar + kWg2MaxStages;
   uint64_t* done_bar = empty_bar + kWg2MaxStages;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(done_bar + 1);
+  uint64_t* afull_bar = done_bar + 1;              // mixed formats: this CTA's activation boxes of a stage have landed
+  uint64_t* conv_bar = afull_bar + kWg2MaxStages;  // (leader's copy) both CTAs have converted them: 2 x 4 warps arrive
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(conv_bar + kWg2MaxStages);
+  // Mixed operand formats (fp16 activations x bf16 gradients): tcgen05.mma kind::f16 faults on them, and a bf16 copy of
+  // every activation written by the forward pass costs a third of the BatchNorm-apply / first-conv store traffic.  So the
+  // activation boxes are converted IN PLACE in shared memory by the four warps that otherwise only run the epilogue:
+  // TMA -> afull_bar (per CTA) -> convert -> fence.proxy.async -> conv_bar (leader) -> MMA.
+  const bool cvt = p.act_dtype != p.dout_dtype;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -229,6 +248,8 @@ conv2x2_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
       for (int i = 0; i < p.stages; ++i) {
         mbar_init(smem_u32(&full_bar[i]), 1);
         mbar_init(smem_u32(&empty_bar[i]), 1);
+        mbar_init(smem_u32(&afull_bar[i]), 1);
+        mbar_init(smem_u32(&conv_bar[i]), 8);
       }
       mbar_init(smem_u32(done_bar), 1);
       fence_barrier_init();
@@ -249,12 +270,19 @@ conv2x2_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
       mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
       const uint32_t fb = smem_u32(&full_bar[stage]);
       if (elect_one()) {
-        if (leader) mbar_arrive_expect_tx(fb, 2u * static_cast<uint32_t>(n_here) * sub_bytes);
+        const uint32_t afb = smem_u32(&afull_bar[stage]);
+        if (cvt) {
+          mbar_arrive_expect_tx(afb, static_cast<uint32_t>(n_here) * kWg2ABytes);
+          if (leader) mbar_arrive_expect_tx(fb, 2u * static_cast<uint32_t>(n_here) * (sub_bytes - kWg2ABytes));
+        } else if (leader) {
+          mbar_arrive_expect_tx(fb, 2u * static_cast<uint32_t>(n_here) * sub_bytes);
+        }
         for (int g = 0; g < n_here; ++g) {
           const int row0 = static_cast<int>(k_begin + static_cast<int64_t>(ch0 + g) * kWgKb);
           const uint32_t a_dst = tiles_addr + stage * stage_bytes + g * sub_bytes;
           const uint32_t b_dst = a_dst + kWg2ABytes;
-          tma_load_2d_pair(a_dst, &tmap_act, fb, chunk * 64, row0 + p.tap_base[rank], kEvictNormal);
+          if (cvt) tma_load_2d_hint(a_dst, &tmap_act, afb, chunk * 64, row0 + p.tap_base[rank], kEvictNormal);
+          else tma_load_2d_pair(a_dst, &tmap_act, fb, chunk * 64, row0 + p.tap_base[rank], kEvictNormal);
           for (int part = 0; part < p.n_parts; ++part) {
             const int col = p.part_col[part] + static_cast<int>(rank) * (p.part_n[part] >> 1);
             for (int j = 0; j < p.part_boxes[part]; ++j)
@@ -270,8 +298,9 @@ conv2x2_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
     }
   } else if (warp == 1) {
     if (leader) {
-      const uint32_t idesc0 = make_idesc_16(256, p.part_n[0], 1, 1, p.act_dtype, p.dout_dtype);
-      const uint32_t idesc1 = make_idesc_16(256, p.n_parts > 1 ? p.part_n[1] : 16, 1, 1, p.act_dtype, p.dout_dtype);
+      const int a_fmt = cvt ? p.dout_dtype : p.act_dtype;          // format of the activation boxes when the MMAs read them
+      const uint32_t idesc0 = make_idesc_16(256, p.part_n[0], 1, 1, a_fmt, p.dout_dtype);
+      const uint32_t idesc1 = make_idesc_16(256, p.n_parts > 1 ? p.part_n[1] : 16, 1, 1, a_fmt, p.dout_dtype);
       const uint64_t adesc_t = make_sw128_desc(0, 128, 1024), bdesc_t = make_sw128_desc(0, kWgBox, 1024);
       const uint32_t a_lo0 = static_cast<uint32_t>(adesc_t), b_lo0 = static_cast<uint32_t>(bdesc_t);
       const uint32_t desc_hi = static_cast<uint32_t>(adesc_t >> 32);
@@ -279,6 +308,7 @@ conv2x2_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
       for (int ch0 = 0; ch0 < n_chunks; ch0 += p.group) {
         const int n_here = n_chunks - ch0 < p.group ? n_chunks - ch0 : p.group;
         mbar_wait(smem_u32(&full_bar[stage]), phase);
+        if (cvt) mbar_wait(smem_u32(&conv_bar[stage]), phase);
         tc_fence_after();
         // warp-uniform chunk loop, election inside (keeps the descriptors in uniform registers)
 #pragma unroll 1
@@ -316,6 +346,48 @@ conv2x2_wgrad2_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid
       }
     }
   } else {
+    if (cvt) {
+      const int tid = static_cast<int>(threadIdx.x) - 64;           // 0 .. 127
+      const bool to_bf16 = p.dout_dtype == 0;
+      uint32_t stage = 0, phase = 0;
+      for (int ch0 = 0; ch0 < n_chunks; ch0 += p.group) {
+        const int n_here = n_chunks - ch0 < p.group ? n_chunks - ch0 : p.group;
+        mbar_wait(smem_u32(&afull_bar[stage]), phase);
+        // 576 16-byte pieces per box, 4.5 per thread: all loads of a box in flight before the first conversion (the loop
+        // was latency bound with one piece at a time: +12 % on the whole kernel)
+#pragma unroll 1
+        for (int g = 0; g < n_here; ++g) {
+          uint4* tile = reinterpret_cast<uint4*>(smem + static_cast<size_t>(stage) * stage_bytes + static_cast<size_t>(g) * sub_bytes);
+          constexpr int kPieces = kWg2ABytes / 16, kPer = (kPieces + 127) / 128;
+          uint4 v[kPer];
+#pragma unroll
+          for (int j = 0; j < kPer; ++j) {
+            const int i = tid + 128 * j;
+            if (i < kPieces) v[j] = tile[i];
+          }
+#pragma unroll
+          for (int j = 0; j < kPer; ++j) {
+            v[j].x = convert16x2(v[j].x, to_bf16);
+            v[j].y = convert16x2(v[j].y, to_bf16);
+            v[j].z = convert16x2(v[j].z, to_bf16);
+            v[j].w = convert16x2(v[j].w, to_bf16);
+          }
+#pragma unroll
+          for (int j = 0; j < kPer; ++j) {
+            const int i = tid + 128 * j;
+            if (i < kPieces) tile[i] = v[j];
+          }
+        }
+        // generic-proxy writes -> visible to the async proxy (tcgen05.mma reads shared memory through it), then signal
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(smem_u32(&conv_bar[stage]));
+        if (++stage == static_cast<uint32_t>(p.stages)) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
     const int q = warp & 3;
     mbar_wait(smem_u32(done_bar), 0);
     tc_fence_after();
@@ -442,7 +514,8 @@ extern "C" int64_t mmlf_conv2x2_wgrad_workspace(int n_pad, int cin_pad) {
 }
 
 static int wgrad_pair(const void* dout, int ld_dout, int n_pad, const void* act, int ld_act, int cin_pad, int B, int H,
-                      int W, int type, int dtype, float* workspace, float* dw, const WgradCanon* canon, void* stream) {
+                      int W, int type, int act_dtype, int dout_dtype, float* workspace, float* dw, const WgradCanon* canon,
+                      void* stream) {
   Wgrad2Params p;
   const int Wp = W + 1;
   p.n_slots = static_cast<int64_t>(B) * (H + 1) * Wp;
@@ -472,9 +545,10 @@ static int wgrad_pair(const void* dout, int ld_dout, int n_pad, const void* act,
     MMLF_REQUIRE(i >= p.n_parts || p.part_n[i] % 16 == 0, "wgrad: N part %d is not a multiple of 16", p.part_n[i]);
   }
   p.ws = workspace;
-  p.act_dtype = p.dout_dtype = dtype;
+  p.act_dtype = act_dtype;
+  p.dout_dtype = dout_dtype;
   const uint32_t sub_bytes = kWg2ABytes + p.nb * kWgBox;
-  const uint32_t aux_bytes = (2 * kWg2MaxStages + 1) * 8 + 16 + 64;
+  const uint32_t aux_bytes = (4 * kWg2MaxStages + 1) * 8 + 16 + 64;
   const uint32_t max_smem = 232448;
   // chunks per stage: as many as leave room for a 3-stage pipeline, at most 4
   int group = static_cast<int>((max_smem - 1024 - aux_bytes) / (3 * sub_bytes));
@@ -516,13 +590,15 @@ static int wgrad_common(const void* dout, int ld_dout, int n_pad, const void* ac
                         const WgradCanon* canon, void* stream) {
   MMLF_REQUIRE(dout && act && workspace && (dw || canon), "wgrad: null buffer");
   MMLF_REQUIRE((act_dtype | dout_dtype) >> 1 == 0, "wgrad: dtype codes are 0 (bf16) or 1 (fp16)");
-  MMLF_REQUIRE(act_dtype == dout_dtype, "wgrad: both operands must share one 16-bit format (convert with mmlf_convert16)");
+  MMLF_REQUIRE(act_dtype == dout_dtype || wgrad_impl() == 2,
+               "wgrad: the single-CTA debugging kernel needs both operands in one 16-bit format");
   MMLF_REQUIRE(n_pad % 16 == 0 && n_pad >= 16 && n_pad <= 320, "wgrad: n_pad %d must be a multiple of 16 in [16, 320]", n_pad);
   MMLF_REQUIRE(cin_pad % 16 == 0 && cin_pad >= 16 && cin_pad <= 320, "wgrad: cin_pad %d must be a multiple of 16 in [16, 320]", cin_pad);
   MMLF_REQUIRE(ld_dout % 8 == 0 && ld_act % 8 == 0 && ld_dout >= n_pad && ld_act >= cin_pad, "wgrad: bad row pitch");
   MMLF_REQUIRE(type == 0 || type == 1, "wgrad: type must be 0 or 1");
   if (wgrad_impl() == 2)
-    return wgrad_pair(dout, ld_dout, n_pad, act, ld_act, cin_pad, B, H, W, type, act_dtype, workspace, dw, canon, stream);
+    return wgrad_pair(dout, ld_dout, n_pad, act, ld_act, cin_pad, B, H, W, type, act_dtype, dout_dtype, workspace, dw, canon,
+                      stream);
   WgradParams p;
   const int Hp = H + 1, Wp = W + 1;
   p.n_slots = static_cast<int64_t>(B) * Hp * Wp;

@@ -124,6 +124,14 @@ class Engine:
         # the conv kernel's own roofline fraction drops from 0.69 to 0.65.
         self.fuse_bn_bwd = os.environ.get('MMLF_BN_FUSE', '0') == '1'
         self.overlap_wgrad = os.environ.get('MMLF_OVERLAP_WGRAD', '0') == '1'
+        # MMLF_SINGLE_ACT=1: keep ONE copy of every activation; the weight-gradient GEMM then reads the fp16 activations
+        # against the bf16 gradients by converting its activation boxes in shared memory (conv2x2_wgrad.cu).  Saves 30 % of
+        # the activation memory, but measured on B200 it is a wash to a loss in time: bn_apply_relu 183 -> 138 us and the
+        # first conv of a block ~ -45 us per out-net block, against +33..40 us on EACH of the block's two weight-gradient
+        # launches (351 -> 385 us: the extra shared-memory traffic of the in-place conversion competes with the MMA operand
+        # fetch); B = 512 step 209.8 -> 219.5 ms.  Default: the round-1 scheme, a bf16 twin of every activation written by
+        # the kernel that produces it.
+        self.mixed_wgrad = os.environ.get('MMLF_SINGLE_ACT', '0') == '1'
         self._build_specs()
 
     @property
@@ -344,11 +352,12 @@ class Engine:
         st = _stream()
         self.repack(need_dgrad=save)
         bn_train = training and self.has_bn
-        tape = {'geo': geo, 'streams': {}, 'out': [], 'bn_train': bn_train} if save else None
+        tape = {'geo': geo, 'streams': {}, 'out': [], 'bn_train': bn_train,
+                'act_dt': self.act if self.mixed_wgrad else GRAD} if save else None
         bufs = self._buffers()
         params = self._params()
         cin0_pad = pad16(n * c3)
-        dual = save and self.act != GRAD          # keep a bf16 copy of the MMA operands of the backward pass
+        dual = save and self.act != GRAD and not self.mixed_wgrad   # bf16 twins of the backward pass's MMA operands
 
         # per-forward scratch for the BatchNorm layers, allocated once (one launch each instead of five per block)
         n_bn = len(self.stream_defs) * self.in_blocks + len(self.out_specs)
@@ -504,7 +513,7 @@ class Engine:
         """conv(k2,p1) -> ReLU -> conv(k2,p0) [-> BN] -> ReLU   (feed_forward.py:122-137).  x / y are the block input
         and output in the activation format, xg / yg their gradient-format twins (None unless ``save``)."""
         st = _stream()
-        dual = save and self.act != GRAD
+        dual = save and self.act != GRAD and not self.mixed_wgrad
         a1 = self._slots(geo, c1.n_pad)
         a1g = bits = None
         if save:
@@ -687,7 +696,7 @@ class Engine:
             def work():
                 sst = _stream()
                 call('mmlf_conv2x2_wgrad_canonical', _ptr(dout), ld_dout, cs.n_pad, _ptr(actg), ld_act, cs.cin_pad, geo.B,
-                     geo.H, geo.W, cs.type, GRAD, GRAD, _ptr(ws), cs.cout, cs.cin, cs.spatial, cs.groups, cs.group_real,
+                     geo.H, geo.W, cs.type, tape['act_dt'], GRAD, _ptr(ws), cs.cout, cs.cin, cs.spatial, cs.groups, cs.group_real,
                      cs.group_pad, gptr(wname), acc, sst)
                 if colsum is not None:
                     colsum(sst)
@@ -772,7 +781,7 @@ class Engine:
                      _ptr(fsums), _ptr(db2), st)
                 db2 = (db2, False)
             else:
-                call('mmlf_relu_bwd', _ptr(gy), ld_gy, _ptr(rec['yg']), rec['ld_y'], Cp, geo.n_slots, GRAD, GRAD,
+                call('mmlf_relu_bwd', _ptr(gy), ld_gy, _ptr(rec['yg']), rec['ld_y'], Cp, geo.n_slots, GRAD, tape['act_dt'],
                      _ptr(dz), Cp, st)
             # data gradients first (critical path), then the weight gradients of the same operands on the side stream
             da1 = self._slots(geo, c1.n_pad, GRAD)

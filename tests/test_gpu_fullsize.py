@@ -250,3 +250,14 @@ def test_model_on_a_tiny_image_and_single_member_ensemble(golden):
         ens = Ensamble(m, -3.5, 3.5, 7.0)                      # np.arange(-3.5, 3.5, 7.0) = [-3.5]: one member
         r = ens(T(h), T(v), T(i), T(d))
         assert r['means'].shape[0] == 1 and torch.equal(r['mean'], r['means'][0]) and torch.equal(r['logvar'], r['logvars'][0])
+
+
+# ------------------------------------------------------------------------------------------------ oracle at BASELINE size
+@pytest.mark.parametrize('case', [(1, 96, 96, 280, 280, 0), (1, 96, 96, 280, 280, 1), (1, 512, 512, 280, 280, 1),
+                                  (1, 512, 512, 280, 280, 0)])
+def test_tensor_core_conv_against_the_oracle_at_baseline_size(case):
+    """The numpy oracle can do ONE image at the benchmark sizes: a 96 x 96 patch and a 512 x 512 light-field tile of the
+    280 -> 280 out-net convolutions (both block positions), tcgen05 kernel vs oracle within one ulp of the fp16 storage
+    (the BatchNorm passes at this size: tests/test_gpu_kernels.py::test_bn_train_roundtrip[shape1])."""
+    from test_gpu_kernels import _conv_case
+    _conv_case(*case, seed=21, simt=False, dt=1)

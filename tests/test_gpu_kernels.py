@@ -491,21 +491,28 @@ def test_conv_wgrad(case, act_dt):
     w = np.zeros((cout, cin, 2, 2), np.float32)
     _, gw, gb = conv2x2_bwd(x, w, gout, 1 if ctype == 0 else 0)
     xs = u.to_slots(x, cin_pad, ctype == 1, Hp, Wp, act_dt)
-    if act_dt == u.FP16:
-        x = bf16_round(x)
-        _, gw, gb = conv2x2_bwd(x, w, gout, 1 if ctype == 0 else 0)
-        xb = torch.full_like(xs, float('nan'), dtype=torch.bfloat16)
-        u.call('mmlf_convert16', u.ptr(xs), cin_pad, u.FP16, u.ptr(xb), cin_pad, u.BF16, cin_pad, B * Hp * Wp, u.stream())
-        xs = xb
     gs = u.to_slots(gout, n_pad, ctype == 0, Hp, Wp)
     ws_bytes = u._lib.lib().mmlf_conv2x2_wgrad_workspace(n_pad, cin_pad)
     ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device='cuda')
+    dw_mixed = None
+    if act_dt == u.FP16:
+        x = bf16_round(x)
+        _, gw, gb = conv2x2_bwd(x, w, gout, 1 if ctype == 0 else 0)
+        # mixed formats straight into the kernel: the fp16 activation boxes are converted to bf16 in shared memory
+        dw_mixed = torch.full((n_pad, 4, cin_pad), float('nan'), dtype=torch.float32, device='cuda')
+        u.call('mmlf_conv2x2_wgrad', u.ptr(gs), n_pad, n_pad, u.ptr(xs), cin_pad, cin_pad, B, H, W, ctype, u.FP16, u.BF16,
+               u.ptr(ws), u.ptr(dw_mixed), u.stream())
+        xb = torch.full_like(xs, float('nan'), dtype=torch.bfloat16)
+        u.call('mmlf_convert16', u.ptr(xs), cin_pad, u.FP16, u.ptr(xb), cin_pad, u.BF16, cin_pad, B * Hp * Wp, u.stream())
+        xs = xb
     dwp = torch.full((n_pad, 4, cin_pad), float('nan'), dtype=torch.float32, device='cuda')
     u.call('mmlf_conv2x2_wgrad', u.ptr(gs), n_pad, n_pad, u.ptr(xs), cin_pad, cin_pad, B, H, W, ctype, u.BF16, u.BF16,
            u.ptr(ws), u.ptr(dwp), u.stream())
     dw = torch.empty((cout, cin, 2, 2), dtype=torch.float32, device='cuda')
     u.call('mmlf_unpack_conv_wgrad', u.ptr(dwp), n_pad, cin_pad, cout, cin, 0, 1, cin, cin_pad, u.ptr(dw), 0, u.stream())
     torch.cuda.synchronize()
+    if dw_mixed is not None:                 # same operand values, same MMAs: bit-identical to convert-then-multiply
+        assert torch.equal(dw_mixed, dwp), 'in-kernel fp16 -> bf16 conversion differs from mmlf_convert16 + wgrad'
     scale = np.abs(gw).max()
     assert np.abs(dw.cpu().numpy() - gw).max() <= 2e-4 * scale + 1e-4
     db = torch.zeros(n_pad, device='cuda')
@@ -569,10 +576,13 @@ def test_weight_pack_variants():
 
 
 # ------------------------------------------------------------------------------------------------ batch norm
-def test_bn_train_roundtrip():
+@pytest.mark.parametrize('shape', [(2, 9, 13, 70), (1, 96, 96, 280)])
+def test_bn_train_roundtrip(shape):
+    """BatchNorm forward (statistics, finalize, apply + ReLU) and backward (reduce, apply) against float64 numpy; the
+    second shape is one BASELINE-size patch of the out-net (96 x 96 px, 280 channels)."""
     u = _u()
     rng = np.random.RandomState(14)
-    B, H, W, Cr = 2, 9, 13, 70
+    B, H, W, Cr = shape
     Cp = u.pad16(Cr)
     Hp, Wp = H + 1, W + 1
     A, G = u.FP16, u.BF16
@@ -637,9 +647,10 @@ def test_bn_train_roundtrip():
     invstd = (1 / np.sqrt(var + 1e-5)).astype(np.float32)
     xhat = ((z - mean) * invstd).astype(np.float32)
     g2, x2 = g.reshape(-1, Cr), xhat.reshape(-1, Cr)
-    want_dz = gamma * invstd * (g - g2.mean(0) - xhat * (g2 * x2).mean(0))
-    np.testing.assert_allclose(dbet.cpu().numpy(), g2.sum(0), rtol=1e-4, atol=1e-3)
-    np.testing.assert_allclose(dgam.cpu().numpy(), (g2 * x2).sum(0), rtol=1e-4, atol=1e-3)
+    want_dz = (gamma * invstd * (g - g2.astype(np.float64).mean(0) - xhat * (g2.astype(np.float64) * x2).mean(0))).astype(np.float32)
+    g64, x64 = g2.astype(np.float64), x2.astype(np.float64)
+    np.testing.assert_allclose(dbet.cpu().numpy(), g64.sum(0), rtol=1e-4, atol=2e-3)
+    np.testing.assert_allclose(dgam.cpu().numpy(), (g64 * x64).sum(0), rtol=1e-4, atol=2e-3)
     dzf = dz.float().cpu().numpy().reshape(B, Hp, Wp, Cp)
     assert not dzf[:, 0].any() and not dzf[:, :, 0].any()
     u.assert_close_bf16(dzf[:, 1:, 1:, :Cr], want_dz, 'bn_bwd_apply', ulps=1.01, atol=2e-3)

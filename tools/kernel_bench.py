@@ -127,17 +127,17 @@ def conv_case(bn, B, H, W, cin, cout, ctype, dt=FP16, relu=True, dual=False, bit
     return fn, flops
 
 
-def wgrad_case(B, H, W, cin, cout, ctype):
+def wgrad_case(B, H, W, cin, cout, ctype, act_dt=BF16):
     n_slots = B * (H + 1) * (W + 1)
     cin_pad, n_pad = pad16(cin), pad16(cout)
-    act = (torch.randn((n_slots, cin_pad), device=DEV) * 0.5).to(torch.bfloat16)
+    act = (torch.randn((n_slots, cin_pad), device=DEV) * 0.5).to(TD[act_dt])
     dout = (torch.randn((n_slots, n_pad), device=DEV) * 0.5).to(torch.bfloat16)
     ws = torch.empty(_lib.lib().mmlf_conv2x2_wgrad_workspace(n_pad, cin_pad) // 4, dtype=torch.float32, device=DEV)
     dw = torch.empty(n_pad * 4 * cin_pad, dtype=torch.float32, device=DEV)
     m = n_slots if ctype == 0 else B * H * W
 
     def fn():
-        call('mmlf_conv2x2_wgrad', P(dout), n_pad, n_pad, P(act), cin_pad, cin_pad, B, H, W, ctype, BF16, BF16, P(ws),
+        call('mmlf_conv2x2_wgrad', P(dout), n_pad, n_pad, P(act), cin_pad, cin_pad, B, H, W, ctype, act_dt, BF16, P(ws),
              P(dw), ST())
     fn.keep = (act, dout, ws, dw)
     return fn, 2.0 * m * cout * 4 * cin
@@ -185,6 +185,11 @@ def main():
         if bn.want('conv2x2_wgrad2_kernel+wgrad_reduce_kernel ' + name):
             fn, flops = wgrad_case(B, H, W, cin, cout, ct)
             bn.tc_row('conv2x2_wgrad2_kernel+wgrad_reduce_kernel', name, flops, fn)
+        mixed = name + ', fp16 act x bf16 grad'
+        if bn.want('conv2x2_wgrad2_kernel+wgrad_reduce_kernel ' + mixed):
+            fn, flops = wgrad_case(B, H, W, cin, cout, ct, FP16)
+            bn.tc_row('conv2x2_wgrad2_kernel+wgrad_reduce_kernel', mixed, flops, fn,
+                      'what the training step launches: activation boxes converted to bf16 in shared memory')
             del fn
             torch.cuda.empty_cache()
 
@@ -209,6 +214,9 @@ def main():
         bn.hbm_row('slot_map_kernel<bn_apply_relu>', f'C={C_real} train, fp16 z -> fp16 y + bf16 y', px * C_real * 6.0,
                    lambda: call('mmlf_bn_apply_relu', P(z), Cp, P(scale), P(shift), Cp, Bt, ps, ps, FP16, P(y), Cp, P(y2), Cp,
                                 BF16, ST()), 'read z, write y twice (conv operand fp16 + wgrad operand bf16)')
+        bn.hbm_row('slot_map_kernel<bn_apply_relu>', f'C={C_real} train, fp16 z -> fp16 y', px * C_real * 4.0,
+                   lambda: call('mmlf_bn_apply_relu', P(z), Cp, P(scale), P(shift), Cp, Bt, ps, ps, FP16, P(y), Cp, P(None), Cp,
+                                BF16, ST()), 'what the training step launches: read z, write y once')
         bn.hbm_row('col_reduce_kernel<bn_bwd_reduce>', f'C={C_real} train', px * C_real * 4.0,
                    lambda: call('mmlf_bn_bwd_reduce', P(dy), Cp, P(z), Cp, P(scale), P(shift), P(mean), P(invstd), Cp, Bt, ps,
                                 ps, BF16, FP16, P(sums), ST()), 'read dy, z')
