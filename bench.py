@@ -32,10 +32,10 @@ import numpy as np  # noqa: E402
 
 ESE_MEMBERS = 70
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the ncu --set full capture
-# profiles/ncu_conv280_r01g.txt (not measurable inside an un-profiled run)
-CONV_TRAFFIC = {'bytes': 653180160,
-                'note': 'ncu capture profiles/ncu_conv280_r01g.txt: conv2x2_tc2 280->280 pad 0 on 64x96x96 patches, 347.7 MB '
-                        'read + 305.5 MB written per launch against 693.7 MB algorithmic (activations in + out; the 663 KB '
+# profiles/ncu_conv280_r02.txt (not measurable inside an un-profiled run)
+CONV_TRAFFIC = {'bytes': 653921024,
+                'note': 'ncu capture profiles/ncu_conv280_r02.txt: conv2x2_tc2 280->280 pad 0 on 64x96x96 patches, 347.9 MB '
+                        'read + 306.1 MB written per launch against 693.7 MB algorithmic (activations in + out; the 663 KB '
                         'weight operand stays in L2)'}
 FULL_KW = dict(model_ksize=2, model_in_blocks=3, model_out_blocks=8, model_chs=70, model_views=9, model_cross=False,
                model_uncert=False, model_unet=False, model_discrete=False, model_no_batchnorm=False,
@@ -324,6 +324,8 @@ def run_gpu(args, rank, world, local, with_cpu_baseline, sample_clocks=True):
         def step(vs, gt_=None, mask_=None):
             with torch.no_grad():
                 if args.workload == 'bands':
+                    if vs[0].shape[-2] != H:               # e2e: only this rank's band (+ halo) was uploaded
+                        return parallel.banded_forward(model, vs, full_height=H)['mean']
                     return parallel.banded_forward(model, vs)['mean']
                 out = model(*vs)
                 _ = out['mean']
@@ -333,7 +335,12 @@ def run_gpu(args, rank, world, local, with_cpu_baseline, sample_clocks=True):
         n_lf = 1 if args.workload == 'bands' else world
         units_per_step = n_lf * H * W / 1e6
         flops_per_step = n_lf * net_forward_flops(1, H, W, args.variant)
-        host = [t.cpu().pin_memory() for t in views]
+        if args.workload == 'bands' and world > 1:
+            # end to end, each rank reads only the rows of its band + halo from the host
+            _lo, _hi, a_, b_ = parallel.band_rows(H, rank, world, 11)
+            host = [t[..., a_:b_, :].contiguous().cpu().pin_memory() for t in views]
+        else:
+            host = [t.cpu().pin_memory() for t in views]
         gt = mask = None
 
     # ---------------- warm-up (the first training step also captures the graph)

@@ -156,15 +156,23 @@ def gather_bands(band, H, rank, world, radius, dim):
     return torch.cat(rows, dim)
 
 
-def banded_forward(model, views, radius=11):
+def banded_forward(model, views, radius=11, full_height=None):
     """Full-image inference of one light field sharded by rows over the ranks: the FCN's receptive field is
     `radius` = 11 px for the published topology (3 + 8 blocks of 2x2 conv pairs; `model_radius` in train/cli.py:95),
     so each rank runs the network on its band + halo and keeps its own rows.  Any circular Shift must already have
-    been applied to the whole image.  Returns the gathered dict {'mean', 'logvar'} (B, H, W) / {'scores'} (B, S, H, W)."""
+    been applied to the whole image.  With `full_height` the caller passes only its band's rows.  Returns the gathered dict {'mean', 'logvar'} (B, H, W) / {'scores'} (B, S, H, W)."""
     rank, world = shard_info()
-    H = views[0].shape[-2]
-    lo, hi, a, b = band_rows(H, rank, world, radius)
-    out = model(*[None if v is None else v[..., a:b, :].contiguous() for v in views])
+    if full_height is None:
+        H = views[0].shape[-2]
+        lo, hi, a, b = band_rows(H, rank, world, radius)
+        out = model(*[None if v is None else v[..., a:b, :].contiguous() for v in views])
+    else:
+        # `views` already hold only this rank's rows [a, b) of a light field of `full_height` rows (a loader that reads or
+        # uploads just its band: band_rows(full_height, rank, world, radius) says which)
+        H = full_height
+        lo, hi, a, b = band_rows(H, rank, world, radius)
+        assert views[0].shape[-2] == b - a, (views[0].shape, a, b)
+        out = model(*views)
     res = {}
     for k in ('mean', 'logvar', 'scores'):
         t = out[k]

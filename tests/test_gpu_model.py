@@ -664,3 +664,35 @@ def test_finite_differences_on_the_trained_model(golden):
     fd = (lp - lm) / (2 * eps)
     report(test='finite_difference_trained', analytic=gnorm2, fd=fd, loss=lossv.item(), rel=abs(fd - gnorm2) / gnorm2)
     assert abs(fd - gnorm2) <= 0.05 * gnorm2, (fd, gnorm2)
+
+
+def test_single_activation_copy_gives_the_same_gradients(golden):
+    """Engine option mixed_wgrad (MMLF_SINGLE_ACT=1): no bf16 twins of the activations, the weight-gradient kernel converts
+    the fp16 activation boxes in shared memory.  Same forward, and gradients equal to the default scheme up to the double
+    rounding bf16(fp16(x)) vs bf16(x) of the operand."""
+    m, g = _trained(golden, 'upr')
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    (h, v, i, d), gt, mask = fx.trained_batch(2)
+    args, gt_t, mask_t = [T(a) for a in (h, v, i, d)], T(gt), T(mask)
+    m.train()
+    state0 = {k: b.clone() for k, b in m.named_buffers()}
+    res = {}
+    for mixed in (False, True):
+        for k, b in m.named_buffers():
+            b.copy_(state0[k])
+        m.engine.mixed_wgrad = mixed
+        m.zero_grad()
+        lossv = _variant_loss('upr', m, m(*args), gt_t, mask_t)
+        lossv.backward()
+        res[mixed] = (lossv.item(), {n: p.grad.double().clone() for n, p in m.named_parameters()})
+    m.engine.mixed_wgrad = False
+    assert res[False][0] == res[True][0]                       # the forward pass is the same
+    dot = na = nb = 0.0
+    for n in res[False][1]:
+        a, b = res[False][1][n], res[True][1][n]
+        dot, na, nb = dot + float((a * b).sum()), na + float((a * a).sum()), nb + float((b * b).sum())
+        if not (n.endswith('.2.bias') and not n.startswith('out_net.7.')):
+            assert float((a - b).norm()) <= 2e-2 * float(a.norm()) + 1e-12, n
+    cos = dot / (na * nb) ** 0.5
+    report(test='single_activation_copy', cosine=cos)
+    assert cos >= 0.9999, cos
