@@ -198,3 +198,35 @@ def test_train_step_follows_the_reference_trajectory(golden, variant):
     rel = np.abs(np.array(traj) - ref) / np.maximum(np.abs(ref), 0.5 * np.abs(ref).max())
     assert step.replays == c['traj_steps'] - 1
     assert rel.max() <= 0.03, (traj, ref.tolist())
+
+
+@pytest.mark.parametrize('over', [dict(model_cross=True), dict(model_no_batchnorm=True),
+                                  dict(model_in_blocks=2, model_out_blocks=3, model_views=5)])
+def test_train_step_on_other_topologies(over):
+    """--model_cross (two stacks), --model_no_batchnorm and a shallower network through the captured step: three steps on
+    one batch, the second and third replayed; same losses as the eager autograd path on a twin model."""
+    from mmlf_b200.model import loss as L
+    from mmlf_b200.model.feed_forward import FeedForward
+    from mmlf_b200.optim import FusedAdam
+    from mmlf_b200.train.step import TrainStep
+    n = over.get('model_views', 9)
+    torch.manual_seed(5)
+    m_e = FeedForward(**fx.model_kwargs('upr', over.get('model_cross', False), chs=16, **{k: v for k, v in over.items() if k != 'model_cross'}))
+    with torch.no_grad():
+        m_e.out_net[len(m_e.out_net) - 1][0].bias.fill_(0.5)
+    m_e = m_e.cuda()
+    m_s = copy.deepcopy(m_e)
+    h, v, i, d, gt = fx.synth_batch(310, 4, 24, 24, n=n)
+    views = [T(a) for a in (h, v, i, d)]
+    gt_t, mask_t = T(gt), T(fx.synth_mask(311, 4, 24, 24))
+    opt_e, opt_s = FusedAdam(m_e.parameters(), lr=1e-4), FusedAdam(m_s.parameters(), lr=1e-4)
+    step = TrainStep(m_s, opt_s, 'upr')
+    m_e.train(), m_s.train()
+    for it in range(3):
+        opt_e.zero_grad()
+        le = L.ImprovedUncertaintyL1Loss()(m_e(*views), gt_t, mask_t)
+        le.backward()
+        opt_e.step()
+        ls = step(*views, gt_t, mask_t)
+        assert np.isfinite(ls.item()) and abs(le.item() - ls.item()) <= 2e-3 * abs(le.item()) + 1e-5, (it, le.item(), ls.item())
+    assert step.replays == 2
