@@ -254,6 +254,19 @@ __device__ __forceinline__ void wlerp4(const float (&f)[8], int o, int d0, int d
   }
 }
 
+// the same lerp with the taps ordered by column: window[j] * wa + window[j + dd] * wb (dd uniform; used by the packing kernel)
+__device__ __forceinline__ void wlerp4w(const float (&f)[8], int o, int dd, float wa, float wb, float (&t)[4]) {
+  float g[5];
+  switch (o) {
+    case 0: g[0] = f[0]; g[1] = f[1]; g[2] = f[2]; g[3] = f[3]; g[4] = f[4]; break;
+    case 1: g[0] = f[1]; g[1] = f[2]; g[2] = f[3]; g[3] = f[4]; g[4] = f[5]; break;
+    case 2: g[0] = f[2]; g[1] = f[3]; g[2] = f[4]; g[3] = f[5]; g[4] = f[6]; break;
+    default: g[0] = f[3]; g[1] = f[4]; g[2] = f[5]; g[3] = f[6]; g[4] = f[7]; break;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) t[j] = __fadd_rn(__fmul_rn(g[j], wa), __fmul_rn(dd ? g[j + 1] : g[j], wb));
+}
+
 template <int R>
 __global__ void __launch_bounds__(256) lf_shift_vec_kernel(const ShiftParams p, int planes) {
   // grid: x = blocks of 256 threads inside a plane, (y, z) = plane; the plane decode is block-uniform and the in-plane
@@ -340,6 +353,7 @@ struct PackParams {
   int B, C, H, W, ld;
   int cw;                        // channels written per slot (multiple of 8, <= ld); columns [cw, ld) are left alone
   int residual;                  // write fp16(x - float(fp16(x))) instead of fp16(x) (split-precision lo block)
+  int rows_per_cta;              // vector kernel: consecutive slot rows per CTA
   int do_shift, stack, n, dtype;
   ShiftTaps taps;
 };
@@ -439,89 +453,172 @@ __global__ void __launch_bounds__(256) pack_views_kernel(const PackParams p) {
   }
 }
 
-// Vector variant for W % 4 == 0: one CTA = one slot row x 128 pixels; a lane owns 4 consecutive pixels of a channel, read
-// with aligned 128-bit loads (the Shift taps through the same two-float4 window as lf_shift_vec_kernel), transposed
-// through shared memory and written as 16-byte channel groups.  Slot column 0 (the halo) is written by the first tile.
-__global__ void __launch_bounds__(256) pack_views_vec_kernel(const PackParams p) {
-  __shared__ __align__(16) float tile[32][kPackTile + 4];   // [channel][pixel], 16-byte aligned rows
-  MMLF_PACK_SELECT()
+// Vector variant for W % 4 == 0: one CTA = `rows_per_cta` consecutive slot rows x 128 pixels; a lane owns 4 consecutive
+// pixels of a channel, read with aligned 128-bit loads (the Shift taps through the same two-float4 window as
+// lf_shift_vec_kernel), transposed through shared memory and written as 16-byte channel groups.  Slot column 0 (the halo)
+// is written by the first tile.  MODE (block-uniform): 0 = plain copy, 1 = W taps only (stack 0), 2 = H taps only
+// (stack 1), 3 = both (stacks 2, 3).  The loads of a batch of channels (4; 2 with both taps = 8 x 128 bit) are all issued
+// before the first dependent instruction: ncu had the one-channel-at-a-time loop waiting on a single load per thread
+// (42 % of the stall samples on its first use).  Shared-memory columns are XOR-swizzled by the 8-channel group so that
+// the channel-major reads of the store phase hit 32 different banks (they were 4-way conflicts: 132-float rows put the
+// four channel groups of a slot on the same bank).
+__device__ __forceinline__ float4 ldg4_if(const float* ptr, bool ok) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ok) v = __ldg(reinterpret_cast<const float4*>(ptr));
+  return v;
+}
+__device__ __forceinline__ int pack_col(int c, int px) { return px ^ (((c >> 3) & 3) << 3); }
+
+template <int MODE>
+__device__ __forceinline__ void pack_vec_rows(const PackParams& p, const float* __restrict__ pviews, __nv_bfloat16* pout,
+                                              __nv_bfloat16* out2, int pstack, float (*tile)[kPackTile + 4], int row0,
+                                              int row1) {
+  constexpr bool has_w = MODE == 1 || MODE == 3, has_v = MODE == 2 || MODE == 3;
+  constexpr int kWarps = MODE == 0 ? 8 : 9;        // = blockDim.x / 32 (see pack_views_vec_kernel)
   const int Wp = p.W + 1, Hp = p.H + 1, W = p.W, H = p.H;
   const int X0 = blockIdx.x * kPackTile;
-  const int sy = blockIdx.y % Hp, b = blockIdx.y / Hp;
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  const int64_t slot_row = (static_cast<int64_t>(b) * Hp + sy) * Wp;
-  const int x0 = X0 + 4 * lane, y = sy - 1;
-  const bool has_w = p.do_shift && pstack != 1, has_v = p.do_shift && pstack != 0;
+  const int x0 = X0 + 4 * lane;
+  const bool x_ok = x0 < W;
+  const int xl = x_ok ? x0 : 0;                    // addresses stay in range for the predicated-off lanes
   const int vsign = pstack == 2 ? -1 : +1;
-  for (int cbase = 0; cbase < p.cw; cbase += 32) {
-    for (int c = wrp; c < 32; c += 8) {
-      const int ch = cbase + c;
-      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ch < p.C && sy >= 1 && x0 < W) {
-        const float* plane = pviews + (static_cast<int64_t>(b) * p.C + ch) * H * W;
-        if (!p.do_shift) {
-          val = __ldg(reinterpret_cast<const float4*>(plane + static_cast<int64_t>(y) * W + x0));
-        } else {
-          const int view = ch / 3;
+  const int cq = (threadIdx.x & 3) * 8;
+  for (int row = row0; row < row1; ++row) {
+    const int sy = row % Hp, b = row / Hp;
+    const int y = sy >= 1 ? sy - 1 : 0;
+    const int64_t slot_row = static_cast<int64_t>(row) * Wp;
+    for (int cbase = 0; cbase < p.cw; cbase += 32) {
+      if (MODE == 0) {
+        // plain copy: warp w owns channels w, w + 8, w + 16, w + 24 of the group; the four loads are issued together
+        float4 val[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int ch = cbase + wrp + 8 * j;
+          const int chl = ch < p.C ? ch : 0;
+          const float* plane = pviews + (static_cast<int64_t>(b) * p.C + chl) * H * W;
+          val[j] = ldg4_if(plane + static_cast<int64_t>(y) * W + xl, ch < p.C && sy >= 1 && x_ok);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = wrp + 8 * j;
+          *reinterpret_cast<float4*>(&tile[c][pack_col(c, 4 * lane)]) = val[j];
+        }
+      } else {
+        // Shift fused in: warp w owns VIEWS (three colour planes with the same taps), so the tap rows, the window start
+        // and the weights are derived once per view instead of once per channel (the kernel is instruction-issue bound:
+        // ~200 instructions per channel and lane group before, most of them index arithmetic)
+        const int cend = cbase + 32 < p.C ? cbase + 32 : p.C;
+        for (int view = cbase / 3 + wrp; 3 * view < cend; view += kWarps) {
           const float w0 = p.taps.w0[view], w1 = p.taps.w1[view];
           const int s0 = p.taps.s0[view], s1 = p.taps.s1[view];
-          const int ra = has_v ? src_index(y, s0, H, vsign) : y;
-          const int rb = has_v ? src_index(y, s1, H, vsign) : y;
-          float t0[4], t1[4];
+          int ra = y, rb = y;
+          if (has_v) { ra = src_index(y, s0, H, vsign); rb = src_index(y, s1, H, vsign); }
+          int o = 0, dd = 0, a = xl, a2 = xl;
+          float wa = w0, wb = w1;
           if (has_w) {
+            // source columns (x - e0) mod W and (x - e1) mod W: neighbours (or equal); the 8-float window starts at the
+            // aligned float4 holding the circularly smaller one.  tap0 * w0 + tap1 * w1 is evaluated as
+            // window[j] * wa + window[j + dd] * wb (the float add commutes bit for bit)
             const int e0 = eff_shift(s0, W), e1 = eff_shift(s1, W);
-            const int c0 = wrap(x0 - e0, W), c1 = wrap(x0 - e1, W);
+            const int c0 = wrap(xl - e0, W), c1 = wrap(xl - e1, W);
             const int up = wrap(c1 - c0, W);
-            int m, d0, d1;
-            if (up <= 1) { m = c0; d0 = 0; d1 = up; } else { m = c1; d0 = 1; d1 = 0; }
-            const int o = m & 3, a = m - o;
-            float f[8];
-            load8(plane + static_cast<int64_t>(ra) * W, a, W, f);
-            wlerp4(f, o, d0, d1, w0, w1, t0);
-            if (has_v) {
-              load8(plane + static_cast<int64_t>(rb) * W, a, W, f);
-              wlerp4(f, o, d0, d1, w0, w1, t1);
-            }
-          } else {
-            const float4 u = __ldg(reinterpret_cast<const float4*>(plane + static_cast<int64_t>(ra) * W + x0));
-            const float4 v = __ldg(reinterpret_cast<const float4*>(plane + static_cast<int64_t>(rb) * W + x0));
-            t0[0] = u.x; t0[1] = u.y; t0[2] = u.z; t0[3] = u.w;
-            t1[0] = v.x; t1[1] = v.y; t1[2] = v.z; t1[3] = v.w;
+            int m;
+            if (up <= 1) { m = c0; dd = up; } else { m = c1; dd = 1; wa = w1; wb = w0; }
+            o = m & 3;
+            a = m - o;
+            a2 = a + 4;
+            if (a2 >= W) a2 -= W;
           }
-          if (has_v) val = make_float4(lerp2(t0[0], w0, t1[0], w1), lerp2(t0[1], w0, t1[1], w1), lerp2(t0[2], w0, t1[2], w1),
-                                       lerp2(t0[3], w0, t1[3], w1));
-          else val = make_float4(t0[0], t0[1], t0[2], t0[3]);
-        }
-      }
-      *reinterpret_cast<float4*>(&tile[c][4 * lane]) = val;
-    }
-    __syncthreads();
-    const int cq = (threadIdx.x & 3) * 8;
+          const int64_t offa = static_cast<int64_t>(ra) * W, offb = static_cast<int64_t>(rb) * W;
+          float fa[3][8], fb[3][8];
+          bool live[3];
 #pragma unroll
-    for (int pass = 0; pass < kPackTile / 64; ++pass) {
-      const int px = (threadIdx.x >> 2) + 64 * pass;
-      if (X0 + px < W && cbase + cq < p.cw) {
-        uint4 o;
-        o.x = pack_pair(tile[cq][px], tile[cq + 1][px], p);
-        o.y = pack_pair(tile[cq + 2][px], tile[cq + 3][px], p);
-        o.z = pack_pair(tile[cq + 4][px], tile[cq + 5][px], p);
-        o.w = pack_pair(tile[cq + 6][px], tile[cq + 7][px], p);
-        *reinterpret_cast<uint4*>(pout + (slot_row + X0 + px + 1) * p.ld + cbase + cq) = o;
-        if (out2) {
-          o.x = pack_pair(tile[cq][px], tile[cq + 1][px], p, p.dtype2);
-          o.y = pack_pair(tile[cq + 2][px], tile[cq + 3][px], p, p.dtype2);
-          o.z = pack_pair(tile[cq + 4][px], tile[cq + 5][px], p, p.dtype2);
-          o.w = pack_pair(tile[cq + 6][px], tile[cq + 7][px], p, p.dtype2);
-          *reinterpret_cast<uint4*>(out2 + (slot_row + X0 + px + 1) * p.ld + cbase + cq) = o;
+          for (int k = 0; k < 3; ++k) {
+            const int ch = 3 * view + k;
+            live[k] = ch >= cbase && ch < cend;
+            const bool ok = live[k] && sy >= 1 && x_ok;
+            const float* plane = pviews + (static_cast<int64_t>(b) * p.C + (live[k] ? ch : 0)) * H * W;
+            const float4 lo = ldg4_if(plane + offa + a, ok);
+            fa[k][0] = lo.x; fa[k][1] = lo.y; fa[k][2] = lo.z; fa[k][3] = lo.w;
+            if (has_w) {
+              const float4 hi = ldg4_if(plane + offa + a2, ok);
+              fa[k][4] = hi.x; fa[k][5] = hi.y; fa[k][6] = hi.z; fa[k][7] = hi.w;
+            }
+            if (has_v) {
+              const float4 lo2 = ldg4_if(plane + offb + a, ok);
+              fb[k][0] = lo2.x; fb[k][1] = lo2.y; fb[k][2] = lo2.z; fb[k][3] = lo2.w;
+              if (has_w) {
+                const float4 hi2 = ldg4_if(plane + offb + a2, ok);
+                fb[k][4] = hi2.x; fb[k][5] = hi2.y; fb[k][6] = hi2.z; fb[k][7] = hi2.w;
+              }
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            if (!live[k]) continue;
+            const int c = 3 * view + k - cbase;
+            float t0[4], t1[4];
+            if (has_w) {
+              wlerp4w(fa[k], o, dd, wa, wb, t0);
+              if (has_v) wlerp4w(fb[k], o, dd, wa, wb, t1);
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) { t0[q] = fa[k][q]; if (has_v) t1[q] = fb[k][q]; }
+            }
+            float4 val;
+            if (has_v) val = make_float4(lerp2(t0[0], w0, t1[0], w1), lerp2(t0[1], w0, t1[1], w1),
+                                         lerp2(t0[2], w0, t1[2], w1), lerp2(t0[3], w0, t1[3], w1));
+            else val = make_float4(t0[0], t0[1], t0[2], t0[3]);
+            *reinterpret_cast<float4*>(&tile[c][pack_col(c, 4 * lane)]) = val;
+          }
+        }
+        // channels of the group beyond C: zeros
+        for (int c = (p.C > cbase ? p.C - cbase : 0) + wrp; c < 32; c += kWarps)
+          *reinterpret_cast<float4*>(&tile[c][pack_col(c, 4 * lane)]) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int pass = 0; pass < kPackTile / 64; ++pass) {
+        const int px = (threadIdx.x >> 2) + 64 * pass;
+        if (threadIdx.x < 256 && X0 + px < W && cbase + cq < p.cw) {
+          const int col = pack_col(cq, px);        // the 8 channels of a group share the swizzle
+          float v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = tile[cq + k][col];
+          uint4 q;
+          q.x = pack_pair(v[0], v[1], p); q.y = pack_pair(v[2], v[3], p);
+          q.z = pack_pair(v[4], v[5], p); q.w = pack_pair(v[6], v[7], p);
+          *reinterpret_cast<uint4*>(pout + (slot_row + X0 + px + 1) * p.ld + cbase + cq) = q;
+          if (out2) {
+            q.x = pack_pair(v[0], v[1], p, p.dtype2); q.y = pack_pair(v[2], v[3], p, p.dtype2);
+            q.z = pack_pair(v[4], v[5], p, p.dtype2); q.w = pack_pair(v[6], v[7], p, p.dtype2);
+            *reinterpret_cast<uint4*>(out2 + (slot_row + X0 + px + 1) * p.ld + cbase + cq) = q;
+          }
         }
       }
+      __syncthreads();
     }
-    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x * 8 < p.cw) {          // halo column sx = 0
+      *reinterpret_cast<uint4*>(pout + slot_row * p.ld + threadIdx.x * 8) = make_uint4(0u, 0u, 0u, 0u);
+      if (out2) *reinterpret_cast<uint4*>(out2 + slot_row * p.ld + threadIdx.x * 8) = make_uint4(0u, 0u, 0u, 0u);
+    }
   }
-  if (blockIdx.x == 0 && threadIdx.x * 8 < p.cw) {          // halo column sx = 0
-    *reinterpret_cast<uint4*>(pout + slot_row * p.ld + threadIdx.x * 8) = make_uint4(0u, 0u, 0u, 0u);
-    if (out2) *reinterpret_cast<uint4*>(out2 + slot_row * p.ld + threadIdx.x * 8) = make_uint4(0u, 0u, 0u, 0u);
-  }
+}
+
+// SHIFT = false: 256 threads, warp w loads channels w, w + 8, ...; SHIFT = true: 288 threads, one warp per view of a
+// 9-view stack (ncu: with 8 warps the ninth view made warp 0 work twice as long and the other seven wait at the barrier,
+// 27 % of the stall samples); the ninth warp sits out the store phase.
+template <bool SHIFT>
+__global__ void __launch_bounds__(SHIFT ? 288 : 256, SHIFT ? 3 : 4) pack_views_vec_kernel(const PackParams p) {
+  __shared__ __align__(16) float tile[32][kPackTile + 4];   // [channel][pixel ^ swizzle], 16-byte aligned rows
+  MMLF_PACK_SELECT()
+  const int n_rows = p.B * (p.H + 1);
+  const int row0 = blockIdx.y * p.rows_per_cta;
+  const int row1 = row0 + p.rows_per_cta < n_rows ? row0 + p.rows_per_cta : n_rows;
+  if (!SHIFT) pack_vec_rows<0>(p, pviews, pout, out2, pstack, tile, row0, row1);
+  else if (pstack == 0) pack_vec_rows<1>(p, pviews, pout, out2, pstack, tile, row0, row1);
+  else if (pstack == 1) pack_vec_rows<2>(p, pviews, pout, out2, pstack, tile, row0, row1);
+  else pack_vec_rows<3>(p, pviews, pout, out2, pstack, tile, row0, row1);
 }
 
 // ------------------------------------------------------------------------------------------------ texture mask
@@ -668,6 +765,19 @@ extern "C" int mmlf_lf_shift(const float* src_h, const float* src_v, const float
   return check_launch("lf_shift_kernel");
 }
 
+// rows per CTA of the vector kernel: enough CTAs for ~8 waves of 8 resident blocks per SM, at most 8 rows each
+// (MMLF_PACK_ROWS overrides, for sweeps)
+static int pack_rows_per_cta(int64_t n_rows, int tiles_x, int n_stacks) {
+  const char* e = getenv("MMLF_PACK_ROWS");           // read per call: the tests switch it inside one process
+  const int forced = e ? atoi(e) : 0;
+  if (forced > 0) return forced < n_rows ? forced : static_cast<int>(n_rows);
+  const int64_t target = 148ll * 8 * 8;
+  int64_t r = n_rows * tiles_x * n_stacks / target;
+  if (r < 1) r = 1;
+  if (r > 8) r = 8;
+  return static_cast<int>(r);
+}
+
 static int launch_pack(const float* views, int B, int C, int H, int W, void* out, int ld, int dtype, int do_shift,
                        int stack, int n, double disp, void* stream, int cw = 0, int residual = 0) {
   MMLF_REQUIRE(dtype == 0 || dtype == 1, "pack_views: dtype must be 0 (bf16) or 1 (fp16)");
@@ -681,6 +791,7 @@ static int launch_pack(const float* views, int B, int C, int H, int W, void* out
   p.do_shift = do_shift; p.stack = stack; p.n = n; p.dtype = dtype;
   p.cw = cw ? cw : ld;
   p.residual = residual;
+  p.rows_per_cta = 1;
   MMLF_REQUIRE(p.cw % 8 == 0 && p.cw >= C && p.cw <= ld, "pack_views: bad written-channel count %d", p.cw);
   if (do_shift) host_taps(disp, n, p.taps);
   const int64_t rows = static_cast<int64_t>(B) * (H + 1);
@@ -696,8 +807,10 @@ static int launch_pack(const float* views, int B, int C, int H, int W, void* out
     const bool vec = W % 4 == 0 && W >= 8 && reinterpret_cast<uintptr_t>(q.views) % 16 == 0 &&
                      reinterpret_cast<uintptr_t>(q.out) % 16 == 0;
     if (vec) {
-      dim3 grid(ceil_div(W, kPackTile), static_cast<unsigned>(nb * (H + 1)));
-      pack_views_vec_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(q);
+      q.rows_per_cta = pack_rows_per_cta(static_cast<int64_t>(nb) * (H + 1), ceil_div(W, kPackTile), 1);
+      dim3 grid(ceil_div(W, kPackTile), static_cast<unsigned>(ceil_div(nb * (H + 1), q.rows_per_cta)));
+      if (q.do_shift) pack_views_vec_kernel<true><<<grid, 288, 0, static_cast<cudaStream_t>(stream)>>>(q);
+      else pack_views_vec_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(q);
     } else {
       dim3 grid(ceil_div(W + 1, kPackTile), static_cast<unsigned>(nb * (H + 1)));
       pack_views_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(q);
@@ -738,7 +851,7 @@ extern "C" int mmlf_pack_stacks(const float* const* views, const int* stacks, in
   PackParams p;
   p.views = nullptr; p.out = nullptr;
   p.n_stacks = n_stacks; p.dtype = dtype; p.dtype2 = dtype2;
-  p.B = B; p.C = C; p.H = H; p.W = W; p.ld = ld; p.cw = ld; p.residual = 0;
+  p.B = B; p.C = C; p.H = H; p.W = W; p.ld = ld; p.cw = ld; p.residual = 0; p.rows_per_cta = 1;
   p.do_shift = do_shift; p.stack = 0; p.n = n;
   bool vec = W % 4 == 0 && W >= 8;
   for (int i = 0; i < 4; ++i) {
@@ -754,8 +867,10 @@ extern "C" int mmlf_pack_stacks(const float* const* views, const int* stacks, in
   }
   if (do_shift) host_taps(disp, n, p.taps);
   if (vec) {
-    dim3 grid(ceil_div(W, kPackTile), static_cast<unsigned>(B * (H + 1)), n_stacks);
-    pack_views_vec_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    p.rows_per_cta = pack_rows_per_cta(static_cast<int64_t>(B) * (H + 1), ceil_div(W, kPackTile), n_stacks);
+    dim3 grid(ceil_div(W, kPackTile), static_cast<unsigned>(ceil_div(B * (H + 1), p.rows_per_cta)), n_stacks);
+    if (p.do_shift) pack_views_vec_kernel<true><<<grid, 288, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    else pack_views_vec_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   } else {
     dim3 grid(ceil_div(W + 1, kPackTile), static_cast<unsigned>(B * (H + 1)), n_stacks);
     pack_views_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);

@@ -826,6 +826,34 @@ def test_hci4d_loader_against_the_oracle(tmp_path):
         assert np.array_equal(shifted[k].cpu().numpy(), want[k])
 
 
+@pytest.mark.parametrize('rows', ['', '3', '8'])
+def test_pack_rows_per_cta(rows, monkeypatch):
+    """The vector packing kernel walks `rows_per_cta` slot rows per CTA (chosen from the problem size; MMLF_PACK_ROWS
+    forces it): every choice, including a ragged last group, gives the oracle's bits -- plain and with the fused Shift."""
+    u = _u()
+    if rows:
+        monkeypatch.setenv('MMLF_PACK_ROWS', rows)
+    else:
+        monkeypatch.delenv('MMLF_PACK_ROWS', raising=False)
+    rng = np.random.RandomState(11)
+    B, n = 2, 9
+    for H, W in ((9, 136), (6, 96), (10, 260)):
+        stacks = [rng.uniform(0, 1, (B, n, 3, H, W)).astype(np.float32) for _ in range(4)]
+        for disp in (None, 2.5, -3.75):
+            sh = stacks if disp is None else oracle.shift(tuple(stacks), disp)
+            for k in range(4):
+                o = torch.full((B * (H + 1) * (W + 1), 32), float('nan'), dtype=torch.float16, device='cuda')
+                sd = torch.from_numpy(stacks[k]).cuda()
+                if disp is None:
+                    u.call('mmlf_pack_views', u.ptr(sd), B, n * 3, H, W, u.ptr(o), 32, u.FP16, u.stream())
+                else:
+                    u.call('mmlf_shift_pack', u.ptr(sd), k, B, n, H, W, float(disp), u.ptr(o), 32, u.FP16, u.stream())
+                got = o.float().cpu().numpy().reshape(B, H + 1, W + 1, 32)
+                want = np.zeros_like(got)
+                want[:, 1:, 1:, :27] = u.ROUND[u.FP16](sh[k].reshape(B, 27, H, W).transpose(0, 2, 3, 1))
+                assert np.array_equal(got, want), (rows, disp, k, H, W)
+
+
 @pytest.mark.parametrize('shape', [(2, 9, 20, 24), (1, 9, 17, 19), (3, 5, 32, 32)])
 def test_pack_stacks_equals_the_per_stack_launches(shape):
     """mmlf_pack_stacks (all stacks of a forward in one launch, optional second copy in another 16-bit format, optional fused

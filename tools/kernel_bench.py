@@ -95,14 +95,24 @@ class Bench:
         self.rows.append(row)
         print(json.dumps(row), flush=True)
 
-    def tc_row(self, name, what, flops, fn, note=''):
+    def tc_row(self, name, what, flops, fn, note='', nbytes=0):
+        """A GEMM-shaped kernel: its roof is the larger of flops / sustained tensor peak and algorithmic bytes / HBM rate
+        (the 27- and 70-channel layers have 67-122 FLOP per byte, below the ridge of ~209: they are HBM-bound)."""
         if not self.want(name + ' ' + what):
             return
         t = timeit(fn, self.args.reps)
         tf = flops / t / 1e12
-        row = {'kernel': name, 'case': what, 'bound': 'tensor', 'ms': t * 1e3, 'algorithmic_GFLOP': flops / 1e9,
-               'achieved': tf, 'peak': self.tf_sus, 'unit': 'TFLOP/s', 'frac': tf / self.tf_sus,
-               'frac_of_burst_peak': tf / self.tf_burst, 'note': note}
+        gbs = nbytes / t / 1e9
+        f_tc, f_hbm = tf / self.tf_sus, gbs / self.hbm
+        row = {'kernel': name, 'case': what, 'ms': t * 1e3, 'algorithmic_GFLOP': flops / 1e9,
+               'algorithmic_MB': nbytes / 1e6, 'flop_per_byte': flops / nbytes if nbytes else None}
+        if f_hbm > f_tc:
+            row.update(bound='hbm', achieved=gbs, peak=self.hbm, unit='GB/s', frac=f_hbm, frac_of_tensor_peak=f_tc,
+                       tflops=tf)
+        else:
+            row.update(bound='tensor', achieved=tf, peak=self.tf_sus, unit='TFLOP/s', frac=f_tc,
+                       frac_of_burst_peak=tf / self.tf_burst, frac_of_hbm_peak=f_hbm)
+        row['note'] = note
         self.rows.append(row)
         print(json.dumps(row), flush=True)
 
@@ -139,11 +149,14 @@ def conv_case(bn, B, H, W, cin, cout, ctype, dt=FP16, relu=True, dual=False, bit
     keep = (x, wp, out, out2, rb, bias, sums, w, zbn, bnc)
     m = n_slots if ctype == 0 else B * H * W
     flops = 2.0 * m * cout * 4 * cin
+    # algorithmic HBM bytes: the input slots once, every output array once (weights: < 1 MB, L2 resident)
+    nbytes = n_slots * 2 * (cin_pad + n_pad * (2 if dual else 1) + (n_pad if bnbwd else 0)) + \
+        (n_slots * 4 * ((n_pad + 31) // 32) if bits else 0)
 
     def fn():
         call('mmlf_conv2x2', C.byref(a), ST())
     fn.keep = keep
-    return fn, flops
+    return fn, flops, nbytes
 
 
 def wgrad_case(B, H, W, cin, cout, ctype, act_dt=BF16):
@@ -159,7 +172,7 @@ def wgrad_case(B, H, W, cin, cout, ctype, act_dt=BF16):
         call('mmlf_conv2x2_wgrad', P(dout), n_pad, n_pad, P(act), cin_pad, cin_pad, B, H, W, ctype, act_dt, BF16, P(ws),
              P(dw), ST())
     fn.keep = (act, dout, ws, dw)
-    return fn, 2.0 * m * cout * 4 * cin
+    return fn, 2.0 * m * cout * 4 * cin, n_slots * 2 * (cin_pad + n_pad)
 
 
 def main():
@@ -191,8 +204,8 @@ def main():
         'conv2x2 280->108 pad1 infer': (1, 512, 512, 280, 108, 0, {}),
     }.items():
         if bn.want('conv2x2_tc2_kernel ' + name):
-            fn, flops = conv_case(bn, B, H, W, cin, cout, ct, **kw)
-            bn.tc_row('conv2x2_tc2_kernel', name, flops, fn)
+            fn, flops, nbytes = conv_case(bn, B, H, W, cin, cout, ct, **kw)
+            bn.tc_row('conv2x2_tc2_kernel', name, flops, fn, nbytes=nbytes)
             del fn
             torch.cuda.empty_cache()
     for name, (B, H, W, cin, cout, ct) in {
@@ -202,13 +215,13 @@ def main():
         'wgrad 27->70 pad1 train': (Bt, ps, ps, 27, 70, 0),
     }.items():
         if bn.want('conv2x2_wgrad2_kernel+wgrad_reduce_kernel ' + name):
-            fn, flops = wgrad_case(B, H, W, cin, cout, ct)
-            bn.tc_row('conv2x2_wgrad2_kernel+wgrad_reduce_kernel', name, flops, fn)
+            fn, flops, nbytes = wgrad_case(B, H, W, cin, cout, ct)
+            bn.tc_row('conv2x2_wgrad2_kernel+wgrad_reduce_kernel', name, flops, fn, nbytes=nbytes)
         mixed = name + ', fp16 act x bf16 grad'
         if bn.want('conv2x2_wgrad2_kernel+wgrad_reduce_kernel ' + mixed):
-            fn, flops = wgrad_case(B, H, W, cin, cout, ct, FP16)
+            fn, flops, nbytes = wgrad_case(B, H, W, cin, cout, ct, FP16)
             bn.tc_row('conv2x2_wgrad2_kernel+wgrad_reduce_kernel', mixed, flops, fn,
-                      'what the training step launches: activation boxes converted to bf16 in shared memory')
+                      'the MMLF_SINGLE_ACT=1 option: activation boxes converted to bf16 in shared memory', nbytes=nbytes)
             del fn
             torch.cuda.empty_cache()
 
@@ -232,10 +245,10 @@ def main():
         dgam, dbet, db2 = torch.empty(C_real, device=DEV), torch.empty(C_real, device=DEV), torch.zeros(Cp, device=DEV)
         bn.hbm_row('slot_map_kernel<bn_apply_relu>', f'C={C_real} train, fp16 z -> fp16 y + bf16 y', px * C_real * 6.0,
                    lambda: call('mmlf_bn_apply_relu', P(z), Cp, P(scale), P(shift), Cp, Bt, ps, ps, FP16, P(y), Cp, P(y2), Cp,
-                                BF16, ST()), 'read z, write y twice (conv operand fp16 + wgrad operand bf16)')
+                                BF16, ST()), 'what the training step launches: read z, write y twice (conv operand fp16 + wgrad operand bf16)')
         bn.hbm_row('slot_map_kernel<bn_apply_relu>', f'C={C_real} train, fp16 z -> fp16 y', px * C_real * 4.0,
                    lambda: call('mmlf_bn_apply_relu', P(z), Cp, P(scale), P(shift), Cp, Bt, ps, ps, FP16, P(y), Cp, P(None), Cp,
-                                BF16, ST()), 'what the training step launches: read z, write y once')
+                                BF16, ST()), 'the MMLF_SINGLE_ACT=1 option: read z, write y once')
         bn.hbm_row('col_reduce_kernel<bn_bwd_reduce>', f'C={C_real} train', px * C_real * 4.0,
                    lambda: call('mmlf_bn_bwd_reduce', P(dy), Cp, P(z), Cp, P(scale), P(shift), P(mean), P(invstd), Cp, Bt, ps,
                                 ps, BF16, FP16, P(sums), ST()), 'read dy, z')

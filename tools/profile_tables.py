@@ -34,12 +34,17 @@ def bench_table(tag):
 
 
 def kernel_table(tag):
-    print('| kernel | case | time | achieved | frac |')
-    print('|---|---|---|---|---|')
+    print('| kernel | case | time | bound | achieved | frac of that roof | other roof |')
+    print('|---|---|---|---|---|---|---|')
     for line in open(os.path.join(P, f'kernel_roofline_{tag}.jsonl')):
         d = json.loads(line)
-        print(f"| {d['kernel'].replace('_kernel', '')} | {d['case']} | {d['ms'] * 1e3:.1f} µs | {d['achieved']:.0f} {d['unit']} | "
-              f"{d['frac']:.2f} |")
+        other = ''
+        if d.get('frac_of_tensor_peak') is not None:
+            other = f"{d['tflops']:.0f} TFLOP/s = {d['frac_of_tensor_peak']:.2f} of tensor"
+        elif d.get('frac_of_hbm_peak'):
+            other = f"{d['frac_of_hbm_peak']:.2f} of HBM"
+        print(f"| {d['kernel'].replace('_kernel', '')} | {d['case']} | {d['ms'] * 1e3:.1f} µs | {d['bound']} | "
+              f"{d['achieved']:.0f} {d['unit']} | {d['frac']:.2f} | {other} |")
 
 
 def ncu_table(tag):
