@@ -254,17 +254,14 @@ __device__ __forceinline__ void wlerp4(const float (&f)[8], int o, int d0, int d
   }
 }
 
-// the same lerp with the taps ordered by column: window[j] * wa + window[j + dd] * wb (dd uniform; used by the packing kernel)
-__device__ __forceinline__ void wlerp4w(const float (&f)[8], int o, int dd, float wa, float wb, float (&t)[4]) {
-  float g[5];
-  switch (o) {
-    case 0: g[0] = f[0]; g[1] = f[1]; g[2] = f[2]; g[3] = f[3]; g[4] = f[4]; break;
-    case 1: g[0] = f[1]; g[1] = f[2]; g[2] = f[3]; g[3] = f[4]; g[4] = f[5]; break;
-    case 2: g[0] = f[2]; g[1] = f[3]; g[2] = f[4]; g[3] = f[5]; g[4] = f[6]; break;
-    default: g[0] = f[3]; g[1] = f[4]; g[2] = f[5]; g[3] = f[6]; g[4] = f[7]; break;
-  }
+// W lerp of the packing kernel, taps ordered by column: window[O + j] * wa + window[O + j + DD] * wb (the float add commutes
+// bit for bit, so this equals tap0 * w0 + tap1 * w1 of wlerp4).  Window offset and tap distance are template parameters:
+// the selection costs no instructions
+template <int V> struct IntTag { static constexpr int value = V; };
+template <int O, int DD>
+__device__ __forceinline__ void wlerp4s(const float (&f)[8], float wa, float wb, float (&t)[4]) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) t[j] = __fadd_rn(__fmul_rn(g[j], wa), __fmul_rn(dd ? g[j + 1] : g[j], wb));
+  for (int j = 0; j < 4; ++j) t[j] = __fadd_rn(__fmul_rn(f[O + j], wa), __fmul_rn(f[O + j + DD], wb));
 }
 
 template <int R>
@@ -529,47 +526,71 @@ __device__ __forceinline__ void pack_vec_rows(const PackParams& p, const float* 
             a2 = a + 4;
             if (a2 >= W) a2 -= W;
           }
-          const int64_t offa = static_cast<int64_t>(ra) * W, offb = static_cast<int64_t>(rb) * W;
+          // every address below is valid memory (predicated-off lanes / halo rows use x = 0 / y = 0, C is a multiple of
+          // 3), so the loads are unconditional and the zero halo is a select at the end: no zero-initialisation and no
+          // predicate logic around the 12 loads of a view
+          const float* vbase = pviews + (static_cast<int64_t>(b) * p.C + 3 * view) * H * W;
+          const int HW = H * W;
+          const int oa = ra * W + a, oa2 = ra * W + a2, ob = rb * W + a, ob2 = rb * W + a2;
+          const bool zero = !(sy >= 1 && x_ok);
           float fa[3][8], fb[3][8];
           bool live[3];
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
             const int ch = 3 * view + k;
             live[k] = ch >= cbase && ch < cend;
-            const bool ok = live[k] && sy >= 1 && x_ok;
-            const float* plane = pviews + (static_cast<int64_t>(b) * p.C + (live[k] ? ch : 0)) * H * W;
-            const float4 lo = ldg4_if(plane + offa + a, ok);
+            const float* plane = vbase + k * HW;
+            const float4 lo = __ldg(reinterpret_cast<const float4*>(plane + oa));
             fa[k][0] = lo.x; fa[k][1] = lo.y; fa[k][2] = lo.z; fa[k][3] = lo.w;
             if (has_w) {
-              const float4 hi = ldg4_if(plane + offa + a2, ok);
+              const float4 hi = __ldg(reinterpret_cast<const float4*>(plane + oa2));
               fa[k][4] = hi.x; fa[k][5] = hi.y; fa[k][6] = hi.z; fa[k][7] = hi.w;
             }
             if (has_v) {
-              const float4 lo2 = ldg4_if(plane + offb + a, ok);
+              const float4 lo2 = __ldg(reinterpret_cast<const float4*>(plane + ob));
               fb[k][0] = lo2.x; fb[k][1] = lo2.y; fb[k][2] = lo2.z; fb[k][3] = lo2.w;
               if (has_w) {
-                const float4 hi2 = ldg4_if(plane + offb + a2, ok);
+                const float4 hi2 = __ldg(reinterpret_cast<const float4*>(plane + ob2));
                 fb[k][4] = hi2.x; fb[k][5] = hi2.y; fb[k][6] = hi2.z; fb[k][7] = hi2.w;
               }
             }
           }
+          // arithmetic of the three colour planes, specialised on the (view-uniform) window offset and tap distance
+          auto finish = [&](auto tag) {
+            constexpr int O = decltype(tag)::value >> 1, DD = decltype(tag)::value & 1;
 #pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            if (!live[k]) continue;
-            const int c = 3 * view + k - cbase;
-            float t0[4], t1[4];
-            if (has_w) {
-              wlerp4w(fa[k], o, dd, wa, wb, t0);
-              if (has_v) wlerp4w(fb[k], o, dd, wa, wb, t1);
-            } else {
+            for (int k = 0; k < 3; ++k) {
+              if (!live[k]) continue;
+              const int c = 3 * view + k - cbase;
+              float t0[4], t1[4];
+              if (has_w) {
+                wlerp4s<O, DD>(fa[k], wa, wb, t0);
+                if (has_v) wlerp4s<O, DD>(fb[k], wa, wb, t1);
+              } else {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) { t0[q] = fa[k][q]; if (has_v) t1[q] = fb[k][q]; }
+                for (int q = 0; q < 4; ++q) { t0[q] = fa[k][q]; if (has_v) t1[q] = fb[k][q]; }
+              }
+              float4 val;
+              if (has_v) val = make_float4(lerp2(t0[0], w0, t1[0], w1), lerp2(t0[1], w0, t1[1], w1),
+                                           lerp2(t0[2], w0, t1[2], w1), lerp2(t0[3], w0, t1[3], w1));
+              else val = make_float4(t0[0], t0[1], t0[2], t0[3]);
+              if (zero) val = make_float4(0.f, 0.f, 0.f, 0.f);
+              *reinterpret_cast<float4*>(&tile[c][pack_col(c, 4 * lane)]) = val;
             }
-            float4 val;
-            if (has_v) val = make_float4(lerp2(t0[0], w0, t1[0], w1), lerp2(t0[1], w0, t1[1], w1),
-                                         lerp2(t0[2], w0, t1[2], w1), lerp2(t0[3], w0, t1[3], w1));
-            else val = make_float4(t0[0], t0[1], t0[2], t0[3]);
-            *reinterpret_cast<float4*>(&tile[c][pack_col(c, 4 * lane)]) = val;
+          };
+          if (!has_w) {
+            finish(IntTag<0>{});
+          } else {
+            switch (2 * o + dd) {                  // uniform across the warp
+              case 0: finish(IntTag<0>{}); break;
+              case 1: finish(IntTag<1>{}); break;
+              case 2: finish(IntTag<2>{}); break;
+              case 3: finish(IntTag<3>{}); break;
+              case 4: finish(IntTag<4>{}); break;
+              case 5: finish(IntTag<5>{}); break;
+              case 6: finish(IntTag<6>{}); break;
+              default: finish(IntTag<7>{}); break;
+            }
           }
         }
         // channels of the group beyond C: zeros
