@@ -570,7 +570,10 @@ def run_gpu(args, rank, world, local, with_cpu_baseline, sample_clocks=True):
     if shares:
         bn = sum(v for k, v in shares.items() if k.startswith('mmlf_bn_'))
         roofline['kernel_sum_ms'] = round(kernel_sum_ms, 3)
-        roofline['idle_frac_of_step'] = round(max(0.0, 1.0 - kernel_sum_ms / ms_per_step), 4)
+        # only meaningful for training: the inference / ESE passes time ONE un-graphed forward (ESE: one member of 70) with an
+        # event pair per kernel, which is not comparable with the replayed step
+        roofline['idle_frac_of_step'] = (round(max(0.0, 1.0 - kernel_sum_ms / ms_per_step), 4)
+                                         if args.workload == 'train' else None)
         roofline['batchnorm_share_of_kernel_time'] = round(bn / kernel_sum_ms, 4)
 
     # free this workload's memory before the next one

@@ -443,35 +443,71 @@ struct WgradCanon {
   int cout, cin, spatial, groups, group_real, group_pad, accumulate;
 };
 
-// same reduction as wgrad_reduce_kernel (same order over the K splits), written straight into the canonical tensor:
-// consecutive threads walk n (contiguous in the workspace) for a fixed (tap, real input channel)
-__global__ void wgrad_reduce_canon_kernel(const float* __restrict__ ws, int ksplits, int m_rows, int ws_ld, int kc,
-                                          const WgradCanon o) {
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= static_cast<int64_t>(o.cout) * 4 * o.cin) return;
-  const int n = static_cast<int>(idx % o.cout);
-  const int tc = static_cast<int>(idx / o.cout);
-  const int tap = tc / o.cin, ci = tc - tap * o.cin;
-  const int g = ci / o.group_real, c = g * o.group_pad + (ci - g * o.group_real);      // padded channel of the operand
-  const int m = (tap * kc + (c >> 6)) * 64 + (c & 63);
-  float acc = 0.f;
-  for (int k = 0; k < ksplits; ++k) acc += ws[(static_cast<int64_t>(k) * m_rows + m) * ws_ld + n];
-  // effective tap (p, q) of this stream -> canonical tap (a, b) of w[., ., a, b]  (weights.cu: eff_to_canonical)
-  const int p = tap >> 1, q = tap & 1;
-  int a, b;
-  if (o.spatial == 0) { a = p; b = q; }
-  else if (o.spatial == 1) { a = q; b = p; }
-  else { a = q; b = 1 - p; }
-  float* dst = o.dw + ((static_cast<int64_t>(n) * o.cin + ci) * 2 + a) * 2 + b;
-  *dst = o.accumulate ? *dst + acc : acc;
+// same reduction as wgrad_reduce_kernel (same order over the K splits), written straight into the canonical tensor.
+// One block = 32 output channels x 4 input channels x 4 taps: the partial sums are read along n (contiguous in the
+// workspace, a warp per (tap, channel) pair), transposed through shared memory and written as one float4 per (n, channel)
+// = the four taps, 64 contiguous bytes per output channel.  (The first version wrote one float per thread at a stride of
+// 16 * cin bytes: 19 us per 280 -> 280 layer for 18 MB of L2-resident partial sums, 39 launches per training step.)
+constexpr int kRedTN = 32, kRedTC = 4;
+__global__ void __launch_bounds__(256) wgrad_reduce_canon_kernel(const float* __restrict__ ws, int ksplits, int m_rows,
+                                                                  int ws_ld, int kc, const WgradCanon o) {
+  __shared__ __align__(16) float tile[kRedTN][kRedTC * 4 + 4];      // [n][channel * 4 + canonical tap], padded rows
+  const int n0 = blockIdx.x * kRedTN, ci0 = blockIdx.y * kRedTC;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int n = n0 + lane;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int pair = wrp + 8 * r;                                   // (tap, local channel)
+    const int tap = pair >> 2, cl = pair & 3, ci = ci0 + cl;
+    float acc = 0.f;
+    if (ci < o.cin && n < o.cout) {
+      const int g = ci / o.group_real, c = g * o.group_pad + (ci - g * o.group_real);    // padded channel of the operand
+      const int m = (tap * kc + (c >> 6)) * 64 + (c & 63);
+      const float* src = ws + static_cast<int64_t>(m) * ws_ld + n;
+      const int64_t kstride = static_cast<int64_t>(m_rows) * ws_ld;
+      int k = 0;
+      for (; k + 4 <= ksplits; k += 4) {                            // four loads in flight, summed in the order of k
+        const float v0 = src[(k + 0) * kstride], v1 = src[(k + 1) * kstride], v2 = src[(k + 2) * kstride],
+                    v3 = src[(k + 3) * kstride];
+        acc += v0; acc += v1; acc += v2; acc += v3;
+      }
+      for (; k < ksplits; ++k) acc += src[k * kstride];
+    }
+    // effective tap (p, q) of this stream -> canonical tap (a, b) of w[., ., a, b]  (weights.cu: eff_to_canonical)
+    const int p = tap >> 1, q = tap & 1;
+    int a, b;
+    if (o.spatial == 0) { a = p; b = q; }
+    else if (o.spatial == 1) { a = q; b = p; }
+    else { a = q; b = 1 - p; }
+    tile[lane][cl * 4 + a * 2 + b] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < kRedTN * kRedTC) {
+    const int nl = threadIdx.x >> 2, cl = threadIdx.x & 3;
+    const int nn = n0 + nl, ci = ci0 + cl;
+    if (nn < o.cout && ci < o.cin) {
+      float4 v = *reinterpret_cast<const float4*>(&tile[nl][cl * 4]);
+      float* dst = o.dw + (static_cast<int64_t>(nn) * o.cin + ci) * 4;
+      if ((reinterpret_cast<uintptr_t>(o.dw) & 15) == 0) {          // block-uniform: slices of a flat gradient buffer
+        float4* d4 = reinterpret_cast<float4*>(dst);                // behind an odd-sized bias are only 4-byte aligned
+        if (o.accumulate) {
+          const float4 d = *d4;
+          v.x = d.x + v.x; v.y = d.y + v.y; v.z = d.z + v.z; v.w = d.w + v.w;
+        }
+        *d4 = v;
+      } else {
+        if (o.accumulate) { v.x = dst[0] + v.x; v.y = dst[1] + v.y; v.z = dst[2] + v.z; v.w = dst[3] + v.w; }
+        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+      }
+    }
+  }
 }
 
 static int launch_wgrad_reduce(const float* ws, int ksplits, int m_rows, int ws_ld, int kc, int n_pad, int cin_pad,
                                float* dw, const WgradCanon* canon, cudaStream_t st) {
   if (canon) {
-    const int64_t total = static_cast<int64_t>(canon->cout) * 4 * canon->cin;
-    wgrad_reduce_canon_kernel<<<static_cast<unsigned>(ceil_div64(total, 256)), 256, 0, st>>>(ws, ksplits, m_rows, ws_ld, kc,
-                                                                                             *canon);
+    const dim3 grid(ceil_div(canon->cout, kRedTN), ceil_div(canon->cin, kRedTC));
+    wgrad_reduce_canon_kernel<<<grid, 256, 0, st>>>(ws, ksplits, m_rows, ws_ld, kc, *canon);
     return check_launch("wgrad_reduce_canon_kernel");
   }
   const int64_t total = static_cast<int64_t>(n_pad) * 4 * cin_pad;

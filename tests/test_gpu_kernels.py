@@ -549,6 +549,15 @@ def test_conv_wgrad_canonical_equals_wgrad_plus_unpack(case):
         torch.cuda.synchronize()
         assert torch.equal(got, want), (case, accumulate)
         assert not torch.equal(got, base)
+        # a destination that is only 4-byte aligned (a slice of the flat gradient buffer behind an odd-sized bias)
+        buf = torch.full((base.numel() + 8,), 7.0, dtype=torch.float32, device='cuda')
+        odd = buf[1:1 + base.numel()].view(base.shape)
+        odd.copy_(base)
+        u.call('mmlf_conv2x2_wgrad_canonical', u.ptr(gs), n_pad, n_pad, u.ptr(xs), cin_pad, cin_pad, B, H, W, ctype, u.BF16,
+               u.BF16, u.ptr(ws), cout, cin, spatial, groups, group_real, group_pad, odd.data_ptr(), accumulate, u.stream())
+        torch.cuda.synchronize()
+        assert torch.equal(odd, want), (case, accumulate, 'unaligned')
+        assert buf[0].item() == 7.0 and bool((buf[1 + base.numel():] == 7.0).all())
 
 
 def test_weight_pack_variants():
