@@ -35,10 +35,10 @@ if [ "$2" != "noncu" ]; then
   $CMD > $O/plain_infer.log 2>&1 &&
   timeout 900 $NCU --metrics gpu__time_duration.sum --graph-profiling node -c 400 --csv --log-file $O/launches_infer_$TAG.csv $CMD > $O/ncu_launch_infer.log 2>&1
   echo "ncu launch list infer: $?"
-  # full captures, one kernel each, from the per-kernel bench (3 warm-up launches skipped)
+  # full captures, one kernel each, from the per-kernel bench (eager launches, warm-up launches skipped)
   cap() {   # name, kernel regex, --only filter
-    python tools/kernel_bench.py --only "$3" --reps 1 > $O/plain_$1.log 2>&1 &&
-    timeout 600 $NCU --set full --import-source on -k "regex:$2" -s 3 -c 1 -f -o $O/prof_$1_$TAG python tools/kernel_bench.py --only "$3" --reps 1 > $O/ncu_$1.log 2>&1
+    MMLF_BENCH_EAGER=1 python tools/kernel_bench.py --only "$3" --reps 1 > $O/plain_$1.log 2>&1 &&
+    MMLF_BENCH_EAGER=1 timeout 600 $NCU --set full --import-source on -k "regex:$2" -s 2 -c 1 -f -o $O/prof_$1_$TAG python tools/kernel_bench.py --only "$3" --reps 1 > $O/ncu_$1.log 2>&1
     tail -n 1 $O/ncu_$1.log
   }
   cap conv280 conv2x2_tc2 "conv2x2 280->280 pad0 train"
@@ -48,8 +48,8 @@ if [ "$2" != "noncu" ]; then
   cap bn_bwd_reduce col_reduce "bn_bwd_reduce"
   cap bn_bwd_apply slot_map "bn_bwd_apply"
   cap lf_shift lf_shift "lf_shift_kernel full"
-  cap pack_stacks pack_views "full LF 512x512, 4 stacks, fp16"
-  cap shift_pack pack_views "full LF 512x512, 4 stacks in one launch, disp"
+  cap pack_stacks pack_views "pack_views_kernel (pack_stacks) full LF 512x512, 4 stacks, fp16"
+  cap shift_pack pack_views "shift_pack_kernel (pack_stacks) full"
   cap upr_posterior upr_posterior "upr_posterior"
   cap ese_reduce ese_reduce "ese_reduce"
   cap lf_extract lf_extract "lf_extract"

@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Per-kernel roofline table of the hot path (GPU box): every kernel of include/mmlf_b200.h at the BASELINE.json sizes,
 timed with CUDA events over back-to-back launches (the stream stays full, so host launch cost is hidden), against the
-measured peaks of MEASURED_PEAKS.json.  One JSON line per kernel on stdout; `--only NAME` restricts to kernels whose name
-contains NAME (used as the ncu target: `ncu --set full -k regex:... python tools/kernel_bench.py --only lf_shift --reps 1`).
+measured peaks of MEASURED_PEAKS.json.  One JSON line per kernel on stdout; `--only NAME[|NAME...]` restricts to kernels whose name
+contains one of the NAMEs (used as the ncu target: `ncu --set full -k regex:... python tools/kernel_bench.py --only lf_shift --reps 1`).
 
 Algorithmic bytes / flops per unit follow SURVEY.md section 8(d) and DESIGN.md section 4.
 """
@@ -83,7 +83,7 @@ class Bench:
         self.rows = []
 
     def want(self, name):
-        return self.args.only is None or any(o in name for o in self.args.only.split(','))
+        return self.args.only is None or any(o in name for o in self.args.only.split('|'))
 
     def hbm_row(self, name, what, nbytes, fn, note='', allow_graph=True):
         if not self.want(name + ' ' + what):
