@@ -36,23 +36,28 @@ __device__ __forceinline__ void aug_unrotate(int r, int n, int y, int x, int& Y,
   }
 }
 
-// One thread = one pixel of one view (3 colours) of one output stack, or of the centre view (stack index 4).
+// One block = 256 pixels of ONE view (3 colours) of one output stack, or of the centre view (stack index 4): stack, view,
+// taps and every sample parameter are block-uniform (the first version decoded stack / view / pixel from a flat index with
+// three run-time divisions per thread and re-read the sample record per thread; ncu: instruction bound).
 __global__ void __launch_bounds__(256)
 augment_views_kernel(const float* __restrict__ stacks, const float* __restrict__ center, int n, int H, int W,
                      const mmlf_aug_sample* __restrict__ samples, int B, int ps, float* __restrict__ out_views,
                      float* __restrict__ out_center, double* __restrict__ view_sums) {
   const int b = blockIdx.y;
   const mmlf_aug_sample& sp = samples[b];
-  const int per_stack = n * ps * ps;
-  const int total = 4 * per_stack + ps * ps;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pp_i = ps * ps;
+  const int chunks = (pp_i + 255) >> 8;
+  const int plane_id = blockIdx.x / chunks;               // 0 .. 4n - 1: (stack, view); 4n: the centre view
+  const int so = plane_id < 4 * n ? plane_id / n : 4;
+  const int k = so < 4 ? plane_id - so * n : 0;
+  const int rem = (blockIdx.x - plane_id * chunks) * 256 + threadIdx.x;
   double hsum = 0.0;
-  if (idx < total) {
-    const int so = idx / per_stack;                       // 0..3 stacks, 4 = centre
-    int rem = idx - so * per_stack;
-    const int k = so < 4 ? rem / (ps * ps) : 0;
-    rem -= k * ps * ps;
-    const int y = rem / ps, x = rem - y * ps;
+  if (rem < pp_i) {
+    // consecutive threads walk the SOURCE row: for an odd number of quarter turns the source column runs along the
+    // output y, so the pixel index is decoded column-major there -- coalesced loads (up to 12 per thread) at the price
+    // of 3 strided 4-byte stores, which the L2 merges
+    const int q = rem / ps, t = rem - q * ps;
+    const int y = (sp.r & 1) ? t : q, x = (sp.r & 1) ? q : t;
     int Y, X;
     aug_unrotate(sp.r, ps, y, x, Y, X);
     const int f = sp.f;
@@ -76,16 +81,24 @@ augment_views_kernel(const float* __restrict__ stacks, const float* __restrict__
       const int r1 = has_v ? aug_src_index(yy, s1, Hd, vsign) : yy;
       const int c0 = has_w ? aug_src_index(xx, s0, Wd, +1) : xx;
       const int c1 = has_w ? aug_src_index(xx, s1, Wd, +1) : xx;
+      // all loads of the pixel first (element offsets inside a plane fit 32 bits)
+      const int oa0 = r0 * f * W + c0 * f, oa1 = r0 * f * W + c1 * f, ob0 = r1 * f * W + c0 * f, ob1 = r1 * f * W + c1 * f;
+      float a0[3], a1[3], b0[3], b1[3];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const float* pl = src + c * plane;
-        const float* ra = pl + static_cast<int64_t>(r0 * f) * W;
-        const float* rb = pl + static_cast<int64_t>(r1 * f) * W;
-        const float t0 = has_w ? aug_lerp2(__ldg(ra + c0 * f), w0, __ldg(ra + c1 * f), w1) : __ldg(ra + xx * f);
+        a0[c] = __ldg(pl + oa0);
+        a1[c] = has_w ? __ldg(pl + oa1) : 0.f;
+        b0[c] = has_v ? __ldg(pl + ob0) : 0.f;
+        b1[c] = has_v && has_w ? __ldg(pl + ob1) : 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float t0 = has_w ? aug_lerp2(a0[c], w0, a1[c], w1) : a0[c];
         if (!has_v) {
           v[c] = t0;
         } else {
-          const float t1 = has_w ? aug_lerp2(__ldg(rb + c0 * f), w0, __ldg(rb + c1 * f), w1) : __ldg(rb + xx * f);
+          const float t1 = has_w ? aug_lerp2(b0[c], w0, b1[c], w1) : b0[c];
           v[c] = aug_lerp2(t0, w0, t1, w1);
         }
       }
@@ -112,6 +125,7 @@ augment_views_kernel(const float* __restrict__ stacks, const float* __restrict__
     }
   }
   // Contrast's mean is over the h stack (data[0]) after Brightness: block partial -> one atomic
+  if (so != 0) return;                                    // block-uniform
   __shared__ double red[8];
   hsum = warp_sum(hsum);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = hsum;
@@ -123,6 +137,10 @@ augment_views_kernel(const float* __restrict__ stacks, const float* __restrict__
   }
 }
 
+// x * contrast + mean * (1 - contrast) over the four stacks and the centre view of a sample.  The mean (a float64
+// division) is derived once per block -- per thread it made this elementwise pass SFU bound (418 us for 64 patches) -- and
+// a thread handles four consecutive floats (V = 4) when the plane size allows 128-bit accesses.
+template <int V>
 __global__ void __launch_bounds__(256)
 augment_contrast_kernel(float* __restrict__ views, float* __restrict__ center, const mmlf_aug_sample* __restrict__ samples,
                         const double* __restrict__ view_sums, const float* __restrict__ mean_override, int B, int n,
@@ -130,11 +148,16 @@ augment_contrast_kernel(float* __restrict__ views, float* __restrict__ center, c
   const int b = blockIdx.y;
   const int per_stack = n * 3 * ps * ps;
   const int total = 4 * per_stack + 3 * ps * ps;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float s_off;
+  if (threadIdx.x == 0) {
+    const float mean = mean_override ? mean_override[b] : static_cast<float>(view_sums[b] / static_cast<double>(per_stack));
+    s_off = __fmul_rn(mean, samples[b].one_minus_contrast);
+  }
+  __syncthreads();
+  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) * V;
   if (idx >= total) return;
-  const float mean = mean_override ? mean_override[b] : static_cast<float>(view_sums[b] / static_cast<double>(per_stack));
   const float a = samples[b].contrast;
-  const float off = __fmul_rn(mean, samples[b].one_minus_contrast);
+  const float off = s_off;
   float* p;
   if (idx < 4 * per_stack) {
     const int so = idx / per_stack, rem = idx - so * per_stack;
@@ -142,7 +165,14 @@ augment_contrast_kernel(float* __restrict__ views, float* __restrict__ center, c
   } else {
     p = center + static_cast<int64_t>(b) * 3 * ps * ps + (idx - 4 * per_stack);
   }
-  *p = __fadd_rn(__fmul_rn(*p, a), off);
+  if (V == 4) {
+    float4 x = *reinterpret_cast<float4*>(p);
+    x.x = __fadd_rn(__fmul_rn(x.x, a), off); x.y = __fadd_rn(__fmul_rn(x.y, a), off);
+    x.z = __fadd_rn(__fmul_rn(x.z, a), off); x.w = __fadd_rn(__fmul_rn(x.w, a), off);
+    *reinterpret_cast<float4*>(p) = x;
+  } else {
+    *p = __fadd_rn(__fmul_rn(*p, a), off);
+  }
 }
 
 // gt, mpi (rotated like the views) and mask (cropped only)
@@ -209,8 +239,8 @@ extern "C" int mmlf_augment_patches(const float* stacks, const float* center, co
   MMLF_REQUIRE(S >= 1 && n >= 1 && n <= 16 && B >= 1 && B <= 65535 && ps >= 1, "augment_patches: bad sizes");
   MMLF_REQUIRE((!out_gt || gt) && (!out_mpi || (mpi && K >= 1)) && (!out_mask || mask), "augment_patches: missing source");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int total = 4 * n * ps * ps + ps * ps;
-  augment_views_kernel<<<dim3(ceil_div(total, 256), B), 256, 0, st>>>(stacks, center, n, H, W, samples, B, ps, out_views,
+  const int blocks = (4 * n + 1) * ceil_div(ps * ps, 256);      // one view plane per group of blocks
+  augment_views_kernel<<<dim3(blocks, B), 256, 0, st>>>(stacks, center, n, H, W, samples, B, ps, out_views,
                                                                       out_center, view_sums);
   if (int rc = check_launch("augment_views_kernel")) return rc;
   if (out_gt || out_mpi || out_mask) {
@@ -225,7 +255,14 @@ extern "C" int mmlf_augment_contrast(float* views, float* center, const mmlf_aug
                                      const float* mean_override, int B, int n, int ps, void* stream) {
   MMLF_REQUIRE(views && center && samples && (view_sums || mean_override), "augment_contrast: null buffer");
   const int total = 4 * n * 3 * ps * ps + 3 * ps * ps;
-  augment_contrast_kernel<<<dim3(ceil_div(total, 256), B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      views, center, samples, view_sums, mean_override, B, n, ps);
+  // 128-bit path: every stack / centre block starts on a multiple of 4 floats and the buffers are 16-byte aligned
+  const bool vec = (ps * ps) % 4 == 0 && reinterpret_cast<uintptr_t>(views) % 16 == 0 &&
+                   reinterpret_cast<uintptr_t>(center) % 16 == 0;
+  if (vec)
+    augment_contrast_kernel<4><<<dim3(ceil_div(total / 4, 256), B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        views, center, samples, view_sums, mean_override, B, n, ps);
+  else
+    augment_contrast_kernel<1><<<dim3(ceil_div(total, 256), B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        views, center, samples, view_sums, mean_override, B, n, ps);
   return check_launch("augment_contrast_kernel");
 }

@@ -111,13 +111,14 @@ class GpuAugmenter:
             return ids, [draw_params_plain(rng, self.H, self.W, ps) for _ in range(B)]
         return ids, [draw_params(rng, self.H, self.W, ps, max_factor) for _ in range(B)]
 
-    def __call__(self, scene_ids, params, mean_override=None, plain=False):
-        """-> (h, v, i, d (B, n, 3, ps, ps), center (B, 3, ps, ps), gt (B, ps, ps), mpi (B, K, 5, ps, ps) f32,
-        mask (B, ps, ps) int32, index (B, 1)) on the GPU."""
-        B, ps, n = len(params), int(params[0]['ps']), self.n
-        host = pack_samples(params, scene_ids, n)
-        dev = self.device
-        samples = torch.frombuffer(bytearray(bytes(host)), dtype=torch.uint8).to(dev)
+    def pack(self, scene_ids, params):
+        """Host side of one batch: the parameter records of its samples, uploaded -> device tensor for ``run``."""
+        host = pack_samples(params, scene_ids, self.n)
+        return torch.frombuffer(bytearray(bytes(host)), dtype=torch.uint8).to(self.device)
+
+    def run(self, samples, B, ps, mean_override=None, plain=False):
+        """Device side: the two kernels over packed sample records (no host work besides the launches)."""
+        n, dev = self.n, self.device
         views = torch.empty((4, B, n, 3, ps, ps), dtype=torch.float32, device=dev)
         center = torch.empty((B, 3, ps, ps), dtype=torch.float32, device=dev)
         sums = torch.zeros(B, dtype=torch.float64, device=dev)
@@ -133,6 +134,13 @@ class GpuAugmenter:
             mo = torch.as_tensor(np.asarray(mean_override, dtype=np.float32)).to(dev)
         if not plain:
             call('mmlf_augment_contrast', P(views), P(center), P(samples), P(sums), P(mo), B, n, ps, st)
-        index = torch.from_numpy(np.stack([self.index[i] for i in scene_ids]))
         self.last_means = sums / float(n * 3 * ps * ps)
+        return views, center, gt, mpi, mask
+
+    def __call__(self, scene_ids, params, mean_override=None, plain=False):
+        """-> (h, v, i, d (B, n, 3, ps, ps), center (B, 3, ps, ps), gt (B, ps, ps), mpi (B, K, 5, ps, ps) f32,
+        mask (B, ps, ps) int32, index (B, 1)) on the GPU."""
+        B, ps = len(params), int(params[0]['ps'])
+        views, center, gt, mpi, mask = self.run(self.pack(scene_ids, params), B, ps, mean_override, plain)
+        index = torch.from_numpy(np.stack([self.index[i] for i in scene_ids]))
         return views[0], views[1], views[2], views[3], center, gt, mpi, mask, index

@@ -212,11 +212,26 @@ def main(output_dir, max_iterations, gpu_augment, synthetic_data, **kwargs):
             item = valset[j]
             yield [torch.as_tensor(t).unsqueeze(0) for t in item]
 
+    # The log line of iteration i (train/cli.py:296-299) needs the loss on the host.  Reading it right after the step is
+    # enqueued would stall the host until the step has finished and leave the GPU idle while the next batch is prepared
+    # (GPU augmentation: ~2 ms of host work per 64 patches), so the read-back is deferred until the next batch has been
+    # prepared and its kernels are queued behind the running step -- and always happens before the next step overwrites
+    # the loss buffer.  Same lines, same order.
+    pending = []
+
+    def flush_log():
+        while pending:
+            it_, loss_dev, lv, ms_, bp, te = pending.pop(0)
+            line = f'{it_:>7}, {loss_dev.item():.8f}, {lv:.8f}, {ms_:.8f}, {bp:.8f}, {te:.8f}'
+            print(line)
+            print(line, file=log, flush=True)
+
     while True:
         if sampler is not None:
             sampler.set_epoch(epoch)                                          # reshuffle every pass, like shuffle=True
         epoch += 1
         for data in trainloader:
+            flush_log()                                   # iteration i - 1, now that batch i is on its way
             h_views, v_views, i_views, d_views, center, gt, mpi, mask, index = data
             if kwargs['train_loss_strongest']:
                 inds = torch.max(mpi[:, :, 3, :, :], dim=1)[1].unsqueeze(1)
@@ -281,12 +296,11 @@ def main(output_dir, max_iterations, gpu_augment, synthetic_data, **kwargs):
                         model_saver(os.path.join(output_dir, 'checkpoint.pt'), model, optimizer, kwargs, None, i,
                                     loss_val_avg)
             if rank == 0:
-                line = f'{i:>7}, {loss_train.item():.8f}, {loss_val_avg:.8f}, {mse_avg:.8f}, {bad_pix_avg:.8f}, {time_elap:.8f}'
-                print(line)
-                print(line, file=log, flush=True)
+                pending.append((i, loss_train, loss_val_avg, mse_avg, bad_pix_avg, time_elap))
             i += 1
             time_start = time.time()
             if max_iterations and i >= max_iterations:
+                flush_log()
                 train_step.close()                    # captured NCCL kernels must go before the process group does
                 return 0
 

@@ -313,10 +313,14 @@ def main():
         ids, params = aug.draw(Bt, ps, random.Random(0), 4)
         out_bytes = Bt * (4 * 27 + 3) * ps * ps * 4.0
         # algorithmic: every output element written once (+ read and re-written by Contrast) and ~1 source element read
+        packed = aug.pack(ids, params)
         bn.hbm_row('augment_views_kernel+augment_contrast_kernel', f'{Bt} patches of 96 px from 512x512 scenes, full chain',
+                   4.0 * out_bytes, lambda: aug.run(packed, Bt, ps),
+                   'gather with stride f (down-sampling) + 2-4 lerp taps; the two kernels over packed sample records')
+        bn.hbm_row('GpuAugmenter.__call__', f'{Bt} patches of 96 px: host packing of the records + upload + the two kernels',
                    4.0 * out_bytes, lambda: aug(ids, params),
-                   'gather with stride f (down-sampling) + 2-4 lerp taps; includes the host packing of the parameters (eager '
-                   'launches: the parameter upload cannot be captured)', allow_graph=False)
+                   'host bound (ctypes record packing); the training loop prepares batch i + 1 while step i runs',
+                   allow_graph=False)
 
     # ------------------------------------------------------------------ heads, targets, losses, ESE reduce, Adam
     B, H, W, S = Bt, ps, ps, 108
