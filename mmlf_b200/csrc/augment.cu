@@ -36,28 +36,32 @@ __device__ __forceinline__ void aug_unrotate(int r, int n, int y, int x, int& Y,
   }
 }
 
-// One block = 256 pixels of ONE view (3 colours) of one output stack, or of the centre view (stack index 4): stack, view,
-// taps and every sample parameter are block-uniform (the first version decoded stack / view / pixel from a flat index with
-// three run-time divisions per thread and re-read the sample record per thread; ncu: instruction bound).
+// One block = a 16 x 16 output tile of ONE view (3 colours) of one output stack, or of the centre view (stack index 4):
+// stack, view, taps and every sample parameter are block-uniform (the first version decoded stack / view / pixel from a
+// flat index with three run-time divisions per thread).  Threads are laid out along the SOURCE row: for an odd number of
+// quarter turns the source column runs along the output y, so the tile is computed transposed and turned in shared
+// memory -- loads and stores both touch whole 64-byte runs (the flat version stored 19 sectors per request on average).
+constexpr int kAugTile = 16;
 __global__ void __launch_bounds__(256)
 augment_views_kernel(const float* __restrict__ stacks, const float* __restrict__ center, int n, int H, int W,
                      const mmlf_aug_sample* __restrict__ samples, int B, int ps, float* __restrict__ out_views,
                      float* __restrict__ out_center, double* __restrict__ view_sums) {
+  __shared__ float turn[3][kAugTile][kAugTile + 1];
   const int b = blockIdx.y;
   const mmlf_aug_sample& sp = samples[b];
-  const int pp_i = ps * ps;
-  const int chunks = (pp_i + 255) >> 8;
-  const int plane_id = blockIdx.x / chunks;               // 0 .. 4n - 1: (stack, view); 4n: the centre view
+  const int tiles = (ps + kAugTile - 1) / kAugTile;
+  const int plane_id = blockIdx.x / (tiles * tiles);      // 0 .. 4n - 1: (stack, view); 4n: the centre view
+  const int tile_id = blockIdx.x - plane_id * tiles * tiles;
   const int so = plane_id < 4 * n ? plane_id / n : 4;
   const int k = so < 4 ? plane_id - so * n : 0;
-  const int rem = (blockIdx.x - plane_id * chunks) * 256 + threadIdx.x;
+  const int ty0 = (tile_id / tiles) * kAugTile, tx0 = (tile_id % tiles) * kAugTile;
+  const int tq = threadIdx.x >> 4, tt = threadIdx.x & 15;  // tt runs along the source row
+  const bool odd = sp.r & 1;
+  const int y = ty0 + (odd ? tt : tq), x = tx0 + (odd ? tq : tt);
+  const bool inside = y < ps && x < ps;
   double hsum = 0.0;
-  if (rem < pp_i) {
-    // consecutive threads walk the SOURCE row: for an odd number of quarter turns the source column runs along the
-    // output y, so the pixel index is decoded column-major there -- coalesced loads (up to 12 per thread) at the price
-    // of 3 strided 4-byte stores, which the L2 merges
-    const int q = rem / ps, t = rem - q * ps;
-    const int y = (sp.r & 1) ? t : q, x = (sp.r & 1) ? q : t;
+  float o[3] = {0.f, 0.f, 0.f};
+  if (inside) {
     int Y, X;
     aug_unrotate(sp.r, ps, y, x, Y, X);
     const int f = sp.f;
@@ -104,7 +108,6 @@ augment_views_kernel(const float* __restrict__ stacks, const float* __restrict__
       }
     }
     // RedistColor (float64 products, float32 after every accumulation), then Brightness (float32)
-    float o[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float acc = static_cast<float>(__dmul_rn(sp.mat[3 * c + 0], static_cast<double>(v[0])));
@@ -112,17 +115,26 @@ augment_views_kernel(const float* __restrict__ stacks, const float* __restrict__
       acc = static_cast<float>(__dadd_rn(static_cast<double>(acc), __dmul_rn(sp.mat[3 * c + 2], static_cast<double>(v[2]))));
       o[c] = __fmul_rn(acc, sp.bright);
     }
+    if (so == 0) hsum = static_cast<double>(o[0]) + static_cast<double>(o[1]) + static_cast<double>(o[2]);
+  }
+  // store: thread (tq, tt) writes output pixel (ty0 + tq, tx0 + tt); transposed tiles go through shared memory
+  int oy = y, ox = x;
+  if (odd) {                                              // block-uniform
+#pragma unroll
+    for (int c = 0; c < 3; ++c) turn[c][tt][tq] = o[c];   // [output y - ty0][output x - tx0]
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c] = turn[c][tq][tt];
+    oy = ty0 + tq;
+    ox = tx0 + tt;
+  }
+  if (oy < ps && ox < ps) {
     const int64_t pp = static_cast<int64_t>(ps) * ps;
-    if (so == 4) {
-      float* dst = out_center + static_cast<int64_t>(b) * 3 * pp + y * ps + x;
+    float* dst = so == 4 ? out_center + static_cast<int64_t>(b) * 3 * pp
+                         : out_views + (((static_cast<int64_t>(so) * B + b) * n + k) * 3) * pp;
+    dst += oy * ps + ox;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) dst[c * pp] = o[c];
-    } else {
-      float* dst = out_views + (((static_cast<int64_t>(so) * B + b) * n + k) * 3) * pp + y * ps + x;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) dst[c * pp] = o[c];
-      if (so == 0) hsum = static_cast<double>(o[0]) + static_cast<double>(o[1]) + static_cast<double>(o[2]);
-    }
+    for (int c = 0; c < 3; ++c) dst[c * pp] = o[c];
   }
   // Contrast's mean is over the h stack (data[0]) after Brightness: block partial -> one atomic
   if (so != 0) return;                                    // block-uniform
@@ -239,7 +251,8 @@ extern "C" int mmlf_augment_patches(const float* stacks, const float* center, co
   MMLF_REQUIRE(S >= 1 && n >= 1 && n <= 16 && B >= 1 && B <= 65535 && ps >= 1, "augment_patches: bad sizes");
   MMLF_REQUIRE((!out_gt || gt) && (!out_mpi || (mpi && K >= 1)) && (!out_mask || mask), "augment_patches: missing source");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int blocks = (4 * n + 1) * ceil_div(ps * ps, 256);      // one view plane per group of blocks
+  const int tiles = ceil_div(ps, 16);
+  const int blocks = (4 * n + 1) * tiles * tiles;               // 16 x 16 output tiles, one view plane per group of blocks
   augment_views_kernel<<<dim3(blocks, B), 256, 0, st>>>(stacks, center, n, H, W, samples, B, ps, out_views,
                                                                       out_center, view_sums);
   if (int rc = check_launch("augment_views_kernel")) return rc;

@@ -178,6 +178,38 @@ def test_augmentation_chain_against_the_reference(golden):
         assert torch.equal(out2[k], out[k])
 
 
+def test_augmentation_chain_multi_tile_against_the_oracle():
+    """The same chain at a patch size that spans several 16 x 16 tiles with a ragged edge (ps = 40), every rotation and
+    down-sampling factor, against the numpy oracle (pinned to the reference by the golden of the test above): bit exact
+    with the oracle's float32 Contrast mean."""
+    import random
+    from oracle import augment as A
+    from mmlf_b200.data.augment import GpuAugmenter, draw_params
+    rs = np.random.RandomState(5)
+    H = W = 184                                                  # (40 + 16) * 3 = 168 fits with max_factor 3
+    sample = [rs.uniform(0, 1, (9, 3, H, W)).astype(np.float32) for _ in range(4)]
+    sample += [sample[1][4].copy(), rs.uniform(-2, 2, (H, W)).astype(np.float32),
+               rs.uniform(-2, 2, (2, 5, H, W)).astype(np.float32).astype(np.float64),      # float64 array of float32 values
+               (rs.uniform(0, 1, (H, W)) > 0.3).astype(np.int32), np.atleast_1d(7)]
+    aug = GpuAugmenter([sample])
+    params, seen = [], set()
+    seed = 0
+    while len(seen) < 12 and seed < 400:                         # every (rotation, factor) pair once
+        p = draw_params(random.Random(seed), H, W, 40, 3)
+        seed += 1
+        if (p['r'], p['f']) not in seen:
+            seen.add((p['r'], p['f']))
+            params.append(p)
+    assert len(seen) == 12
+    refs = [A.augment(sample, p) for p in params]
+    out = aug([0] * len(params), params, mean_override=[m for _, m in refs])
+    for j, (ref, _) in enumerate(refs):
+        for k, name in enumerate(('h', 'v', 'i', 'd', 'center', 'gt', 'mpi', 'mask')):
+            want = ref[k].astype(np.float32) if name == 'mpi' else ref[k]
+            got = out[k][j].cpu().numpy()
+            assert np.array_equal(got, want.astype(got.dtype)), (params[j]['r'], params[j]['f'], name)
+
+
 def test_pack_views_and_shift_pack():
     u = _u()
     rng = np.random.RandomState(2)
