@@ -70,6 +70,35 @@ def net_forward_flops(B, H, W, variant, chs=70, views=9, streams=4, in_blocks=3,
     return f
 
 
+def conv_split(B, H, W, variant, training, chs=70, views=9, streams=4, in_blocks=3, out_blocks=8):
+    """Algorithmic work of the conv2x2 launches (forward [+ data gradients]) split into the wide out-net layers (FLOPs) and
+    the narrow in-net layers (FLOPs and HBM bytes: every input slot array read once, every output array written once;
+    16-bit storage on the padded channel pitch, training forward: bf16 twins + ReLU bits of the first conv of a block)."""
+    def pad16(c):
+        return (c + 15) // 16 * 16
+    n_slots = B * (H + 1) * (W + 1)
+    narrow_fl = narrow_by = 0.0
+    for _ in range(streams):
+        cin = views * 3
+        for k in range(in_blocks):
+            f1, f2 = conv_flops(B, H, W, cin, chs, 0), conv_flops(B, H, W, chs, chs, 1)
+            narrow_fl += f1 + f2
+            outs = 2 if training else 1
+            narrow_by += n_slots * 2.0 * (pad16(cin) + outs * pad16(chs)) + (n_slots * 4.0 * ((pad16(chs) + 31) // 32) if training else 0)
+            narrow_by += n_slots * 2.0 * (pad16(chs) + pad16(chs))             # second conv: a1 in, z (or y) out
+            if training:
+                narrow_fl += f2 + (f1 if k > 0 else 0.0)                         # data gradients
+                narrow_by += n_slots * 2.0 * 2 * pad16(chs) + n_slots * 4.0 * ((pad16(chs) + 31) // 32)
+                if k > 0:
+                    narrow_by += n_slots * 2.0 * (pad16(chs) + pad16(cin))
+            cin = chs
+    w = streams * chs
+    wide_fl = (out_blocks - 1) * (conv_flops(B, H, W, w, w, 0) + conv_flops(B, H, W, w, w, 1))
+    if training:
+        wide_fl *= 2.0
+    return wide_fl, narrow_fl, narrow_by
+
+
 def train_step_flops(B, H, W, variant):
     """forward + weight gradients + data gradients (none for the first conv of each stream): SURVEY.md section 6."""
     fwd = net_forward_flops(B, H, W, variant)
@@ -490,7 +519,7 @@ def run_gpu(args, rank, world, local, with_cpu_baseline, sample_clocks=True):
     # ---------------- profiling pass: un-graphed, one CUDA-event pair around every C-ABI call
     net = model
     prof_steps = (2 if args.workload == 'train' else 3) if args.profile_steps is None else args.profile_steps
-    by_name = {}
+    by_name, by_tag = {}, {}
     if prof_steps > 0:
         if train_step is not None:
             # the captured graph owns the activation memory of a whole step (88 GB at 512 patches): release it before the
@@ -520,7 +549,10 @@ def run_gpu(args, rank, world, local, with_cpu_baseline, sample_clocks=True):
             net.use_cuda_graph = True
         barrier()
         for name, a, b in prof:
-            by_name.setdefault(name, []).append(a.elapsed_time(b))
+            base, _, tag = name.partition('#')           # the engine tags conv launches narrow / wide / head
+            by_name.setdefault(base, []).append(a.elapsed_time(b))
+            if tag:
+                by_tag.setdefault((base, tag), []).append(a.elapsed_time(b))
 
     # ---------------- per-kernel shares and the roofline of the dominant kernel (the tcgen05 conv)
     shares = {k: sum(v) / prof_steps for k, v in by_name.items()}
@@ -557,6 +589,22 @@ def run_gpu(args, rank, world, local, with_cpu_baseline, sample_clocks=True):
                     'share_of_step': conv_time * 1e3 / kernel_sum_ms,
                     'note': 'value: product path (CUDA-graph replay); kernel times: separate single-stream un-graphed pass '
                             'of %d step(s), CUDA events around every launch' % prof_steps}
+        # the same launches split by the roof that binds them: the 280-channel layers against the
+        # tensor peak, the 27 / 70-channel in-nets (67-122 FLOP per byte) against the HBM rate
+        if by_tag and args.workload in ('train', 'infer'):
+            hbm = peaks.get('hbm_gbs') or 6500.0
+            wide_fl, narrow_fl, narrow_by = conv_split(B, H, W, args.variant, args.workload == 'train')
+            split = {}
+            t_w = sum(by_tag.get(('mmlf_conv2x2', 'wide'), [])) / prof_steps / 1e3
+            t_n = sum(by_tag.get(('mmlf_conv2x2', 'narrow'), [])) / prof_steps / 1e3
+            if t_w > 0:
+                split['wide'] = {'bound': 'tensor', 'ms': t_w * 1e3, 'achieved': wide_fl / t_w / 1e12, 'unit': 'TFLOP/s',
+                                 'frac': wide_fl / t_w / 1e12 / peak_tf}
+            if t_n > 0:
+                split['narrow'] = {'bound': 'hbm', 'ms': t_n * 1e3, 'achieved': narrow_by / t_n / 1e9, 'unit': 'GB/s',
+                                   'peak': hbm, 'frac': narrow_by / t_n / 1e9 / hbm,
+                                   'frac_of_tensor_peak': narrow_fl / t_n / 1e12 / peak_tf}
+            roofline['by_layer_width'] = split
         if wgrad_ms:
             wg_time = sum(wgrad_ms) / prof_steps / 1e3
             roofline['wgrad'] = {'kernel': 'conv2x2_wgrad_kernel + reduce', 'achieved': fwd / wg_time / 1e12,

@@ -129,6 +129,7 @@ _KERNELS_PER_CALL = {'mmlf_g_bn_bwd': 3, 'mmlf_zero': 0, 'mmlf_adam_step_dev': 2
 launch_count = 0
 _TRACE = os.environ.get('MMLF_TRACE', '0') == '1'      # print every C-ABI call (debugging aid)
 _profile = None          # when set to a list, call() appends (name, start_event, end_event)
+profile_tag = None       # optional label of the NEXT profiled call (the engine marks narrow / wide convolutions): name#tag
 
 
 def set_profile(enabled):
@@ -142,7 +143,7 @@ def set_profile(enabled):
 
 def call(name, *args):
     """Call an ``int``-returning entry point and raise with the library's error text on failure."""
-    global launch_count
+    global launch_count, profile_tag
     l = lib()
     if _profile is not None:
         import torch
@@ -150,7 +151,8 @@ def call(name, *args):
         e0.record()
         rc = getattr(l, name)(*args)
         e1.record()
-        _profile.append((name, e0, e1))
+        _profile.append((name if profile_tag is None else f'{name}#{profile_tag}', e0, e1))
+        profile_tag = None
     else:
         rc = getattr(l, name)(*args)
     if _TRACE:

@@ -308,6 +308,8 @@ class Engine:
         if bn is not None:            # BatchNorm-backward statistics fused into this (data-gradient) launch
             a.bn_z, a.ld_z, a.bn_z_dtype = bn['z'].data_ptr(), bn['ld_z'], bn['dtype']
             a.bn_scale, a.bn_shift, a.bn_mean = bn['scale'].data_ptr(), bn['shift'].data_ptr(), bn['mean'].data_ptr()
+        if _lib._profile is not None:     # bench.py's per-kernel pass: which roof binds this launch
+            _lib.profile_tag = 'narrow' if cin_pad <= 128 else ('wide' if n_pad > 128 else 'head')
         call('mmlf_conv2x2_simt' if simt else 'mmlf_conv2x2', C.byref(a), _stream())
 
     def _slots(self, geo, ch, dtype=None):
@@ -695,6 +697,8 @@ class Engine:
 
             def work():
                 sst = _stream()
+                if _lib._profile is not None:
+                    _lib.profile_tag = 'narrow' if cs.cin_pad <= 128 else ('wide' if cs.n_pad > 128 else 'head')
                 call('mmlf_conv2x2_wgrad_canonical', _ptr(dout), ld_dout, cs.n_pad, _ptr(actg), ld_act, cs.cin_pad, geo.B,
                      geo.H, geo.W, cs.type, tape['act_dt'], GRAD, _ptr(ws), cs.cout, cs.cin, cs.spatial, cs.groups, cs.group_real,
                      cs.group_pad, gptr(wname), acc, sst)
