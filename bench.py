@@ -609,6 +609,13 @@ def run_gpu(args, rank, world, local, with_cpu_baseline, sample_clocks=True):
             wg_time = sum(wgrad_ms) / prof_steps / 1e3
             roofline['wgrad'] = {'kernel': 'conv2x2_wgrad_kernel + reduce', 'achieved': fwd / wg_time / 1e12,
                                  'frac': fwd / wg_time / 1e12 / peak_tf, 'share_of_step': wg_time * 1e3 / kernel_sum_ms}
+            if by_tag:
+                wide_fl, narrow_fl, _ = conv_split(B, H, W, args.variant, False)
+                for tag, fl in (('wide', wide_fl), ('narrow', narrow_fl)):
+                    tt = sum(by_tag.get(('mmlf_conv2x2_wgrad_canonical', tag), [])) / prof_steps / 1e3
+                    if tt > 0:
+                        roofline['wgrad'][tag] = {'ms': tt * 1e3, 'achieved': fl / tt / 1e12, 'frac': fl / tt / 1e12 / peak_tf,
+                                                  'frac_of_burst_peak': fl / tt / 1e12 / (peaks.get('bf16_tflops') or 1600.0)}
     step_tf = flops_per_step / world / (ms_per_step / 1e3) / 1e12
     if roofline is None:
         roofline = {'kernel': 'whole step (no per-kernel pass in this run)', 'bound': 'tensor', 'achieved': step_tf,

@@ -149,6 +149,8 @@ def readme(tag):
         roof = f"{r['achieved']:.0f} TFLOP/s = {r['frac']:.2f}" if r.get('achieved') else '–'
         if r.get('wgrad'):
             roof += f"; wgrad {r['wgrad']['frac']:.2f}"
+            if r['wgrad'].get('wide'):
+                roof += f" (280-ch layers {r['wgrad']['wide']['frac']:.2f})"
         bw = r.get('by_layer_width') or {}
         if bw.get('wide') and bw.get('narrow'):
             roof += f"; 280-ch layers {bw['wide']['frac']:.2f}, in-nets {bw['narrow']['frac']:.2f} of the HBM rate"
