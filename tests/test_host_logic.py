@@ -187,3 +187,34 @@ def test_hci4d_requires_scene_directories(tmp_path):
     assert ds.scenes_names == ['boxes'] and len(ds) == 1
     with pytest.raises(FileNotFoundError):
         ds.load_scene(0)                                            # no view images in the scene
+
+
+def test_bench_flop_accounting_is_self_consistent():
+    """bench.py's per-width split of the conv work (roofline.by_layer_width) adds up to the whole-network figures it is
+    reported beside: wide + narrow + head == net_forward_flops; training = forward + data gradients of everything but the
+    first conv of each stream; the narrow layers sit below the tensor/HBM ridge (they are HBM-bound), the wide ones above."""
+    import importlib.util
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(root, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    B, H, W = 64, 96, 96
+    for variant, oc in (('base', 1), ('upr', 2), ('dpp', 108)):
+        fwd = bench.net_forward_flops(B, H, W, variant)
+        wide, narrow, nbytes = bench.conv_split(B, H, W, variant, False)
+        head = bench.conv_flops(B, H, W, 280, oc, 0) + bench.conv_flops(B, H, W, oc, oc, 1)
+        assert abs(wide + narrow + head - fwd) <= 1e-9 * fwd
+        wide_t, narrow_t, nbytes_t = bench.conv_split(B, H, W, variant, True)
+        first = 4 * bench.conv_flops(B, H, W, 27, 70, 0)
+        assert abs(wide_t - 2 * wide) <= 1e-9 * wide and abs(narrow_t - (2 * narrow - first)) <= 1e-9 * narrow
+        assert nbytes_t > 2 * nbytes                     # twins, ReLU bits and the data gradients' traffic
+        # arithmetic intensity against the ridge of the measured peaks (fallback: 1400 TFLOP/s / 6.5 TB/s)
+        try:
+            pk = json.load(open(os.path.join(root, 'MEASURED_PEAKS.json')))
+            ridge = pk['bf16_tflops_sustained'] * 1e12 / (pk['hbm_gbs'] * 1e9)
+        except (OSError, KeyError):
+            ridge = 1400e12 / 6500e9
+        assert narrow / nbytes < ridge and narrow_t / nbytes_t < ridge
+        n_slots = B * (H + 1) * (W + 1)
+        assert bench.conv_flops(B, H, W, 280, 280, 1) / (n_slots * 2.0 * 2 * 288) > ridge
