@@ -89,6 +89,7 @@ def readme(tag):
     split = _j(f'bench_infer_split_{tag}.json')
     ref = _j(f'bench_reference_{tag}.json')
     n2, n8 = _j(f'bench_n2_{tag}.json'), _j(f'bench_n8_{tag}.json')
+    n4 = _j(f'bench_n4_{tag}.json')
     try:
         pk = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
     except OSError:
@@ -188,9 +189,9 @@ def readme(tag):
           f"bs = 512 {sa['ms_per_step']:.2f} ms, 64 patches {sa64['ms_per_step']:.2f} ms -- see DESIGN.md §4.2.")
     # ---- scaling
     if n2 or n8:
-        w(f"\n## Scaling (`bench_n2_{tag}.json`, `bench_n8_{tag}.json`: `torchrun`, one rank per GPU, NCCL all-reduces captured in the step graph)\n")
-        w('| workload | N = 1 | N = 2 | N = 8 | 8-GPU speed-up (value / e2e) |')
-        w('|---|---|---|---|---|')
+        w(f"\n## Scaling (`bench_n2_{tag}.json`, `bench_n4_{tag}.json`, `bench_n8_{tag}.json`: `torchrun`, one rank per GPU, NCCL all-reduces captured in the step graph)\n")
+        w('| workload | N = 1 | N = 2 | N = 4 | N = 8 | 8-GPU speed-up (value / e2e) |')
+        w('|---|---|---|---|---|---|')
 
         def pick(d, key):
             if not d:
@@ -200,14 +201,16 @@ def readme(tag):
                            ('full-LF inference, one light field per GPU (weak)', 'infer'), ('ESE, members sharded', 'ese'),
                            ('one light field, row bands', 'bands')):
             a, b, c = pick(head, key), pick(n2, key), pick(n8, key)
+            m4 = pick(n4, key)
             sp = '–'
             if a and c:
                 sp = f"{c['value'] / a['value']:.2f}× / {c['e2e']['value'] / a['e2e']['value']:.2f}×"
             w(f"| {label} | {_fmt(a and a['value'])} | {_fmt(b and b['value'])} (e2e {_fmt(b and b['e2e']['value'])}) | "
+              f"{_fmt(m4 and m4['value'])} (e2e {_fmt(m4 and m4['e2e']['value'])}) | "
               + (f"{_fmt(c['value'])} {c['unit']} ({c['ms_per_step']:.2f} ms)" if c else '–') + f" | {sp} |")
         w(f"\n`multi_check_n2_{tag}.txt`: sharded ESE and row-band inference bit-identical to the single-process result on both ranks; ranks\n"
           'built from different seeds are one replica after the rank-0 broadcast and stay bit-identical over captured training steps.\n'
-          f'`multi_check_n8_{tag}.txt`: the same on 8 ranks.  The row-band line is latency bound (0.8 ms per light field at 8 GPUs).')
+          f'`multi_check_n4_{tag}.txt`, `multi_check_n8_{tag}.txt`: the same on 4 and 8 ranks.  The row-band line is latency bound (0.8 ms per light field at 8 GPUs).')
     # ---- kernel table
     w(f"\n## Per-kernel roofline (`kernel_roofline_{tag}.jsonl`, `tools/kernel_bench.py`)\n")
     w('Each kernel alone at the BASELINE sizes (64 patches of 96 px = the per-GPU share at 8 GPUs, or one 512×512 light field), 20\n'
