@@ -218,3 +218,19 @@ def test_bench_flop_accounting_is_self_consistent():
         assert narrow / nbytes < ridge and narrow_t / nbytes_t < ridge
         n_slots = B * (H + 1) * (W + 1)
         assert bench.conv_flops(B, H, W, 280, 280, 1) / (n_slots * 2.0 * 2 * 288) > ridge
+
+
+def test_profiles_readme_is_regenerable():
+    """profiles/README.md is written by tools/profile_tables.py from the evidence files next to it: the committed text is
+    what the tool prints today (so the numbers in it are the files' numbers, not typed ones)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'tools', 'profile_tables.py'), '--readme', 'r02'],
+                       capture_output=True, text=True, cwd=root, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    committed = open(os.path.join(root, 'profiles', 'README.md')).read()
+    # MEASURED_PEAKS.json is driver-written and may be absent or differ on another box: compare everything below the header
+    cut = '## Test / parity evidence'
+    assert cut in r.stdout and cut in committed
+    assert r.stdout[r.stdout.index(cut):].strip() == committed[committed.index(cut):].strip()
